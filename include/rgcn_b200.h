@@ -1,0 +1,175 @@
+/*
+ * rgcn_b200.h — C ABI of the B200-native RGCN message-passing hot path.
+ *
+ * Drop-in boundary for arnold117/PrimeKG-RGCN-LinkPrediction (reference paths are relative
+ * to /root/reference).  The reference has no FFI: its hot path is the Python call chain
+ *   DrugDiseaseModel.forward            src/models/rgcn.py:300-331
+ *   -> DrugDiseaseRGCN.forward          src/models/rgcn.py:97-130
+ *   -> torch_geometric RGCNConv.forward called at src/models/rgcn.py:123, :128 (third party)
+ *   -> LinkPredictor.forward            src/models/rgcn.py:189-213
+ *   -> LinkPredictor.score_all_tails    src/models/rgcn.py:215-243
+ * Each entry point below names the reference computation it replaces.  The Python host side
+ * (primekg-rgcn-linkprediction_b200/) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - sizes are explicit, nothing is allocated inside: workspaces are passed in and sized by
+ *     the *_workspace_bytes twin;
+ *   - all work is enqueued on `stream` (a cudaStream_t), no implicit synchronisation unless
+ *     the function's comment says so;
+ *   - return value 0 = ok, otherwise an RGCN_E* code; rgcn_last_error() gives the message of
+ *     the calling thread's last failure.
+ *   - feature matrices are row-major fp32, rows 16-byte aligned (ld % 4 == 0), feature width d
+ *     a multiple of 4 and at most 1024.
+ */
+#ifndef RGCN_B200_H_
+#define RGCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGCN_B200_ABI_VERSION 1
+
+enum {
+  RGCN_OK = 0,
+  RGCN_EINVAL = 1,      /* bad argument (shape / alignment / null)            */
+  RGCN_ERANGE = 2,      /* an edge endpoint or relation id is out of range    */
+  RGCN_ECUDA = 3,       /* a CUDA runtime call failed                         */
+  RGCN_EWORKSPACE = 4,  /* workspace too small                                */
+  RGCN_EUNSUPPORTED = 5 /* device is not sm_100 / feature not compiled        */
+};
+
+typedef void* rgcn_stream_t; /* cudaStream_t */
+
+int rgcn_abi_version(void);
+/* Copies the calling thread's last error message (NUL terminated) into buf; returns its length. */
+int rgcn_last_error(char* buf, size_t buf_len);
+/* 0 when the current device is compute capability 10.x, RGCN_EUNSUPPORTED otherwise. */
+int rgcn_check_device(void);
+/* Number of kernels of this library launched so far by this process (all threads). */
+int64_t rgcn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph preprocessing.  Replaces, once per graph, the per-relation boolean masks
+ * `edge_index[:, edge_type == r]` that RGCNConv evaluates on every call
+ * (call sites src/models/rgcn.py:123, :128; input format src/preprocess.py:240-261).
+ *
+ * Builds the CSR keyed by (dst, relation)  [key = dst * R + rel, n_dst * R keys] and the
+ * transposed CSR keyed by (src, relation) [key = src * R + rel, n_src * R keys].  Inside one
+ * key the ORIGINAL edge order is kept (stable LSD radix sort), so the result is bit-identical
+ * to a stable sort of the keys.
+ *
+ *   src, dst, rel   [E] int64 (edge_index row 0, row 1, edge_type)
+ *   rowptr   [n_dst*R + 1] int32    col   [E] int32 (= src[perm])     perm   [E] int32
+ *   rowptr_t [n_src*R + 1] int32    row_t [E] int32 (= dst[perm_t])   perm_t [E] int32
+ *   inv_cnt  [n_dst*R] float   1 / max(in-degree of (dst, rel), 1)
+ *   w_t      [E] float         inv_cnt[row_t[e] * R + rel(e)] in transposed order
+ *   status   [4] int32         [0] bit0: src out of range, bit1: dst, bit2: rel;
+ *                              [1] number of hub segments (> hub_threshold edges);
+ *                              [2] longest (dst, rel) segment; [3] longest (src, rel) segment
+ * The call is asynchronous; the caller synchronises and inspects status[0] (non-zero => the
+ * arrays are unspecified and the Python layer raises IndexError, where PyG would hit a
+ * device-side assert).
+ * ------------------------------------------------------------------------------------------ */
+size_t rgcn_csr_build_workspace_bytes(int64_t E, int64_t n_dst, int64_t n_src, int32_t R);
+int rgcn_csr_build(const int64_t* src, const int64_t* dst, const int64_t* rel, int64_t E,
+                   int64_t n_dst, int64_t n_src, int32_t R,
+                   int32_t* rowptr, int32_t* col, int32_t* perm,
+                   int32_t* rowptr_t, int32_t* row_t, int32_t* perm_t,
+                   float* inv_cnt, float* w_t, int32_t* status,
+                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hub plan (one per CSR orientation, once per graph).  Power-law graphs have (row, relation)
+ * segments with 10^4 edges; segments longer than 128 edges are cut into 512-edge chunks that
+ * whole thread blocks reduce in a fixed order (no atomics).  hub_keys receives the sorted keys of
+ * those segments, hub_chunk_ptr the exclusive prefix of their chunk counts (cap_hubs + 1 entries;
+ * entries past n_hubs repeat the total).  cap_hubs >= E / 128 + 1 is always enough.
+ * SYNCHRONISES the stream: the two counts are returned to the host.
+ * ------------------------------------------------------------------------------------------ */
+size_t rgcn_hub_plan_workspace_bytes(int64_t n_keys, int64_t cap_hubs);
+int rgcn_hub_plan(const int32_t* rowptr, int64_t n_keys, int32_t* hub_keys, int32_t* hub_chunk_ptr,
+                  int64_t cap_hubs, int32_t* n_hubs_host, int32_t* n_chunks_host,
+                  void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+/* One orientation of the relation-keyed CSR as the aggregation kernels consume it. */
+typedef struct rgcn_csr {
+  const int32_t* rowptr;        /* [n_rows * R + 1]                                   */
+  const int32_t* idx;           /* [E] gathered row per edge (col, or row_t)          */
+  const float* w;               /* [E] per-edge weight, or NULL => mean per segment   */
+  int64_t n_rows;
+  int64_t E;
+  int32_t R;
+  int32_t n_hubs;
+  int32_t n_chunks;
+  int32_t reserved_;
+  const int32_t* hub_keys;      /* [n_hubs]                                           */
+  const int32_t* hub_chunk_ptr; /* [n_hubs + 1]                                       */
+} rgcn_csr_t;
+
+/* ------------------------------------------------------------------------------------------
+ * Neighbourhood aggregation, forward.  Replaces, for all relations at once,
+ *   x_j = x.index_select(0, src_r);  s = scatter_add(x_j, dst_r);  h_r = s / clamp(cnt, 1)
+ * of RGCNConv's loop path (src/models/rgcn.py:123, :128).
+ *
+ *   H[i, r*d : (r+1)*d] = (1 / max(cnt(i, r), 1)) * sum_{e in seg(i, r)} X[col[e], :]
+ * One group of d/4 lanes per destination row, 128-bit loads, serial left-to-right fp32 sum inside
+ * a segment (= the order of CPU index_add_), no atomics; segments longer than the hub threshold
+ * are split over whole thread blocks and reduced in a fixed order.
+ *   out_bf16 != 0 : H is written as bf16 (the "bf16-transform" mode), else fp32.
+ *   comp != NULL (basis decomposition, comp [R, B] fp32): instead of R blocks the kernel writes the
+ *   B basis-mixed blocks  Z[i, b*d:(b+1)*d] = sum_r comp[r, b] * h_r[i]   (H is then [n_rows, B*d]).
+ * ------------------------------------------------------------------------------------------ */
+size_t rgcn_aggregate_workspace_bytes(const rgcn_csr_t* g, int32_t d);
+int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d,
+                       const float* comp, int32_t B,
+                       void* H, int64_t ldh, int32_t out_bf16,
+                       void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Neighbourhood aggregation, backward (grad-X).  Replaces autograd's backward of the gather /
+ * scatter-mean (index_select backward = index_add_ with atomics on CUDA), reached from
+ * loss.backward() at src/train.py:306.  Runs over the TRANSPOSED CSR, atomic-free and
+ * deterministic:
+ *   gX[j, :] = init[j, :] + sum_r sum_{e in seg_t(j, r)} w_t[e] * gH[row_t[e], r*d : (r+1)*d]
+ * `init` (may be NULL) carries the root/self-loop term gO @ root^T.
+ * ------------------------------------------------------------------------------------------ */
+int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
+                       const float* init, int64_t ld_init,
+                       float* gX, int64_t ldgx,
+                       void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DistMult decoder.  Replaces node_embeddings[head], [tail] (src/models/rgcn.py:325-326) +
+ * LinkPredictor.forward (src/models/rgcn.py:207-211) with one gather-and-score kernel:
+ *   score[p] = sum_k emb_h[hp, k] * r_p[k] * emb_t[tp, k],   hp = head ? head[p] : p, tp likewise
+ * (head == tail == NULL is the stand-alone LinkPredictor.forward on already gathered rows;
+ *  emb_h == emb_t == encoder output with index arrays is the fused DrugDiseaseModel.forward).
+ * r_p = rel_rows[p, :] when rel_rows != NULL (rows already gathered and dropped-out by the
+ * caller), else rel_table[rel[p], :].
+ * Backward: g_h[hp] += g[p] * r_p * t_p ; g_t[tp] += g[p] * h_p * r_p ;
+ *           g_rel_rows[p] = g[p] * h_p * t_p  and/or  g_rel_table[rel[p]] += the same.
+ * With an index array the target rows may repeat: the buffer must be zero-filled by the caller
+ * and duplicates are combined with fp32 atomics; without one the rows are plain stores.
+ * ------------------------------------------------------------------------------------------ */
+int rgcn_distmult_fwd(const float* emb_h, int64_t ld_h, const float* emb_t, int64_t ld_t,
+                      const int64_t* head, const int64_t* tail, const int64_t* rel,
+                      const float* rel_table, const float* rel_rows,
+                      int64_t n_pairs, int32_t d, float* score, rgcn_stream_t stream);
+int rgcn_distmult_bwd(const float* emb_h, int64_t ld_h, const float* emb_t, int64_t ld_t,
+                      const int64_t* head, const int64_t* tail, const int64_t* rel,
+                      const float* rel_table, const float* rel_rows, const float* g_score,
+                      int64_t n_pairs, int32_t d, float* g_h, int64_t ld_gh, float* g_t, int64_t ld_gt,
+                      float* g_rel_table, float* g_rel_rows, rgcn_stream_t stream);
+/* flag[0] = 1 when any head/tail is outside [0, n_nodes) or any rel outside [0, n_rel). */
+int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,
+                     int64_t n_nodes, int32_t n_rel, int32_t* flag, rgcn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGCN_B200_H_ */

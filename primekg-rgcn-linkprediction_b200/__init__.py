@@ -1,0 +1,14 @@
+"""B200-native (sm_100a) RGCN message-passing hot path for PrimeKG link prediction.
+
+A from-scratch implementation of the one hot path of arnold117/PrimeKG-RGCN-LinkPrediction
+(reference src/models/rgcn.py): hand-written CUDA kernels behind a C ABI
+(``include/rgcn_b200.h`` -> ``csrc/librgcn_b200.so``), bound with ctypes, behind the reference's own
+``nn.Module`` API.  No CPU fallback: see ``oracle/`` for the CPU restatement used by the tests.
+"""
+from .conv import RGCNConv, default_mode
+from .graph import RelGraph, clear_graph_cache, get_graph
+from .modules import DrugDiseaseModel, DrugDiseaseRGCN, LinkPredictor
+
+__all__ = ["RGCNConv", "DrugDiseaseRGCN", "LinkPredictor", "DrugDiseaseModel", "RelGraph", "get_graph",
+           "clear_graph_cache", "default_mode"]
+__version__ = "0.1.0"

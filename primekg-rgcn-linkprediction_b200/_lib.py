@@ -1,0 +1,88 @@
+"""ctypes binding of ``csrc/librgcn_b200.so`` (the C ABI declared in ``include/rgcn_b200.h``).
+
+There is NO CPU fallback: if the library is missing or the device is not a B200-class GPU the
+product path raises.  (The CPU restatement lives in ``oracle/`` and is test infrastructure.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librgcn_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+p = C.c_void_p
+i32, i64, sz = C.c_int32, C.c_int64, C.c_size_t
+
+
+class CsrStruct(C.Structure):
+    """Mirror of ``rgcn_csr_t`` (include/rgcn_b200.h)."""
+    _fields_ = [("rowptr", p), ("idx", p), ("w", p), ("n_rows", i64), ("E", i64), ("R", i32),
+                ("n_hubs", i32), ("n_chunks", i32), ("reserved_", i32), ("hub_keys", p),
+                ("hub_chunk_ptr", p)]
+
+
+PCSR = C.POINTER(CsrStruct)
+
+# name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
+PROTOTYPES = {
+    "rgcn_abi_version": (C.c_int, []),
+    "rgcn_last_error": (C.c_int, [C.c_char_p, sz]),
+    "rgcn_check_device": (C.c_int, []),
+    "rgcn_launch_count": (i64, []),
+    "rgcn_csr_build_workspace_bytes": (sz, [i64, i64, i64, i32]),
+    "rgcn_csr_build": (C.c_int, [p, p, p, i64, i64, i64, i32, p, p, p, p, p, p, p, p, p, p, sz, p]),
+    "rgcn_hub_plan_workspace_bytes": (sz, [i64, i64]),
+    "rgcn_hub_plan": (C.c_int, [p, i64, p, p, i64, C.POINTER(i32), C.POINTER(i32), p, sz, p]),
+    "rgcn_aggregate_workspace_bytes": (sz, [PCSR, i32]),
+    "rgcn_aggregate_fwd": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, i32, p, sz, p]),
+    "rgcn_aggregate_bwd": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, p, sz, p]),
+    "rgcn_distmult_fwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, i64, i32, p, p]),
+    "rgcn_distmult_bwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, i64, i32, p, i64, p, i64, p, p, p]),
+    "rgcn_check_pairs": (C.c_int, [p, p, p, i64, i64, i32, p, p]),
+}
+
+
+class RGCNLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RGCNLibraryError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:  # pragma: no cover
+                raise RGCNLibraryError(f"{LIB_PATH} does not export {name}; rebuild the library") from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.rgcn_abi_version() != 1:
+            raise RGCNLibraryError("ABI version mismatch between the Python host side and librgcn_b200.so")
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    load().rgcn_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RGCNLibraryError(f"{what or 'librgcn_b200'} failed (code {rc}): {last_error()}")

@@ -1,0 +1,123 @@
+"""RGCNConv operator: PyG-compatible module over the sm_100a kernels.
+
+Replaces ``torch_geometric.nn.RGCNConv`` as the reference uses it (import src/models/rgcn.py:17,
+construction :72-85, calls :123 and :128): same constructor arguments, parameter names, shapes,
+initialisation (PyG ``glorot`` / zeros, in PyG's order) and ``forward(x, edge_index, edge_type)``.
+
+    x'_i = root^T x_i + bias + sum_r (1 / |N_r(i)|) sum_{j in N_r(i)} W_r^T x_j        (mean per (dst, relation))
+
+Formulation: aggregate first (gather width d_in <= d_out, like the reference), then ONE dense
+contraction over the concatenated K = (R+1) * d_in.  Backward runs the mirrored gather over the
+transposed CSR (deterministic, no atomics) and the dense dgrad / wgrad contractions.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import dense, ops
+from .graph import RelGraph, get_graph
+
+
+def default_mode() -> str:
+    m = os.environ.get("PRIMEKG_RGCN_MODE", "fp32").lower()
+    if m not in dense.MODES:
+        raise ValueError(f"PRIMEKG_RGCN_MODE must be one of {dense.MODES}, got {m!r}")
+    return m
+
+
+class _RGCNLayerFn(torch.autograd.Function):
+    """out = [relu]( H(x) @ Wf + x @ root + bias ),  Wf = W.view(R * d_in, d_out)."""
+
+    @staticmethod
+    def forward(ctx, x, W, root, bias, graph: RelGraph, relu: bool, mode: str):
+        R, d_in, d_out = W.shape
+        x = x.contiguous()
+        H = ops.aggregate_fwd(graph, x, out_bf16=False)
+        out = dense.transform_fwd(H, W.reshape(R * d_in, d_out), x, root, bias, relu, mode)
+        ctx.graph, ctx.relu, ctx.mode = graph, relu, mode
+        ctx.save_for_backward(x, H, W, root, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gO):
+        x, H, W, root, out = ctx.saved_tensors
+        graph, mode = ctx.graph, ctx.mode
+        R, d_in, d_out = W.shape
+        gO = gO.contiguous()
+        if ctx.relu:
+            gO = gO * (out > 0)
+        need_x, need_W, need_root, need_b = ctx.needs_input_grad[:4]
+        gx = gW = groot = gb = None
+        if need_x:
+            Wcat = torch.cat([W.reshape(R * d_in, d_out), root], 0)
+            gA = dense.transform_dgrad(gO, Wcat, mode)                 # [N, (R+1) * d_in]
+            gx = ops.aggregate_bwd(graph, gA, d_in, init=gA[:, R * d_in:])
+        if need_W or need_root or need_b:
+            gWf, groot, gb = dense.transform_wgrad(H, x, gO, mode)
+            gW = gWf.view(R, d_in, d_out)
+        return gx, gW, groot, gb, None, None, None
+
+
+def _glorot_(t: Optional[torch.Tensor]) -> None:
+    # torch_geometric.nn.inits.glorot: fans are the LAST TWO dims (not nn.init.xavier_uniform_'s)
+    if t is not None:
+        a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+        t.data.uniform_(-a, a)
+
+
+class RGCNConv(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, num_relations: int, num_bases: Optional[int] = None,
+                 mode: Optional[str] = None):
+        super().__init__()
+        if in_channels % 4 or out_channels % 4:
+            raise ValueError("the sm_100a kernels need channel counts that are multiples of 4")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_bases = num_relations, num_bases
+        self.mode = mode
+        if num_bases is not None:
+            self.weight = nn.Parameter(torch.empty(num_bases, in_channels, out_channels))
+            self.comp = nn.Parameter(torch.empty(num_relations, num_bases))
+        else:
+            self.weight = nn.Parameter(torch.empty(num_relations, in_channels, out_channels))
+            self.register_parameter("comp", None)
+        self.root = nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        _glorot_(self.weight)
+        _glorot_(self.comp)
+        _glorot_(self.root)
+        self.bias.data.zero_()
+
+    def relation_weights(self) -> torch.Tensor:
+        """[R, d_in, d_out]; with bases W_r = sum_b comp[r, b] V_b (differentiable)."""
+        if self.comp is None:
+            return self.weight
+        B = self.weight.size(0)
+        return (self.comp @ self.weight.view(B, -1)).view(self.num_relations, self.in_channels, self.out_channels)
+
+    def forward_graph(self, x: torch.Tensor, graph: RelGraph, relu: bool = False) -> torch.Tensor:
+        if x.dim() != 2 or x.size(1) != self.in_channels:
+            raise ValueError(f"x must be [N, {self.in_channels}]")
+        if graph.R != self.num_relations:
+            raise ValueError("graph and layer disagree on the number of relations")
+        return _RGCNLayerFn.apply(x, self.relation_weights(), self.root, self.bias, graph, relu,
+                                  self.mode or default_mode())
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_type: torch.Tensor) -> torch.Tensor:
+        if edge_type is None:
+            raise ValueError("edge_type is required")
+        if not x.is_cuda:
+            raise RuntimeError("RGCNConv (B200) needs CUDA tensors: there is no CPU implementation of this path")
+        graph = get_graph(edge_index, edge_type, x.size(0), self.num_relations)
+        return self.forward_graph(x, graph)
+
+    def extra_repr(self) -> str:
+        return (f"{self.in_channels}, {self.out_channels}, num_relations={self.num_relations}, "
+                f"num_bases={self.num_bases}")

@@ -1,0 +1,346 @@
+// Segmented gather + reduce over a relation-keyed CSR: the neighbourhood aggregation of RGCNConv
+// (reference call sites src/models/rgcn.py:123, :128) and its transpose for backward.
+//
+// One family of kernels serves forward and backward:
+//   s(i, r)  = sum_{e in seg(i, r)} w(e) * F[idx[e], r * src_rel_stride : +d]     (w = 1 when edge_w == NULL)
+//   h(i, r)  = s / max(len, 1)                       when edge_w == NULL  (scatter-MEAN)
+//            = s                                     otherwise
+//   MIX_NONE : O[i, r*d : (r+1)*d] = h(i, r)                                   forward, full weights
+//   MIX_SUM  : O[i, :]             = init[i, :] + sum_r h(i, r)                backward (grad-X)
+//   MIX_BASIS: O[i, b*d : (b+1)*d] = sum_r comp[r, b] * h(i, r)                basis decomposition
+//
+// Mapping: a group of G = min(32, d/4) lanes owns one row i and walks its R segments; every lane
+// holds VPL float4 of the d-wide accumulator, issues U independent 128-bit row loads per step and
+// adds them left to right, i.e. in the CSR's (= original) edge order.  No atomics anywhere.
+// Segments longer than kHubThreshold ("hubs", power-law graphs have rows with 10^4 edges) are cut
+// into kHubChunk-edge chunks that whole blocks reduce beforehand (hub_partial_kernel) into a
+// partial buffer; the row kernel then adds the chunk partials in chunk order.  Everything is
+// deterministic: same bits on every run.
+#include "common.cuh"
+
+namespace rgcn {
+
+enum { MIX_NONE = 0, MIX_SUM = 1, MIX_BASIS = 2 };
+constexpr int kMaxBasis = 8;
+
+struct AggParams {
+  const int32_t* rowptr;
+  const int32_t* idx;
+  const float* edge_w;       // nullable
+  const int32_t* hub_keys;   // sorted keys of hub segments
+  const int32_t* hub_chunk_ptr;
+  int32_t n_hubs;
+  int64_t n_rows;
+  int32_t R;
+  const float* F;            // gathered feature matrix
+  int64_t ldf;
+  int32_t src_rel_stride;    // column offset per relation inside a gathered row (0 forward, d backward)
+  int32_t d;
+  const float* comp;         // [R, ldcomp] (MIX_BASIS)
+  int32_t ldcomp;
+  int32_t B;
+  const float* init;         // nullable (MIX_SUM)
+  int64_t ld_init;
+  void* O;
+  int64_t ldo;
+  int32_t out_bf16;
+  float* partials;           // [n_chunks, d]
+};
+
+// ---- hub chunks: one block per chunk --------------------------------------------------------
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) hub_partial_kernel(AggParams p) {
+  constexpr int GROUPS = 256 / G;
+  __shared__ float4 red[GROUPS][G * VPL];
+  const int chunk = blockIdx.x;
+  // which hub does this chunk belong to: last h with hub_chunk_ptr[h] <= chunk
+  int lo = 0, hi = p.n_hubs;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(p.hub_chunk_ptr + mid) <= chunk) lo = mid; else hi = mid;
+  }
+  const int hub = lo;
+  const int key = __ldg(p.hub_keys + hub);
+  const int r = key % p.R;
+  const int seg_beg = __ldg(p.rowptr + key), seg_end = __ldg(p.rowptr + key + 1);
+  const int c_beg = seg_beg + (chunk - __ldg(p.hub_chunk_ptr + hub)) * kHubChunk;
+  const int c_end = min(c_beg + kHubChunk, seg_end);
+  const int nvec = p.d >> 2;
+  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+  // each group sums a contiguous slice of the chunk, left to right
+  constexpr int PER = kHubChunk / GROUPS;
+  const int g_beg = c_beg + grp * PER, g_end = min(g_beg + PER, c_end);
+  float4 acc[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* Fb = p.F + (size_t)r * p.src_rel_stride;
+  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  for (int e = g_beg; e < g_end; e += U) {
+    float4 v[U][VPL];
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = e + u < g_end;
+      const int j = ok ? __ldg(p.idx + e + u) : 0;
+      w[u] = (ok && p.edge_w) ? __ldg(p.edge_w + e + u) : 1.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = k * G + lane;
+        v[u][k] = (ok && vi < nvec) ? ldg4(Fb + (size_t)j * p.ldf + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (p.edge_w) fma4(acc[k], w[u], v[u][k]); else add4(acc[k], v[u][k]);
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) red[grp][k * G + lane] = acc[k];
+  __syncthreads();
+  // fixed-order reduce over the groups, one thread per float4 column
+  for (int vi = threadIdx.x; vi < nvec; vi += 256) {
+    float4 s = red[0][vi];
+    for (int g = 1; g < GROUPS; ++g) add4(s, red[g][vi]);
+    reinterpret_cast<float4*>(p.partials + (size_t)chunk * p.d)[vi] = s;
+  }
+}
+
+__device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int col, const float4& v) {
+  if (p.out_bf16) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.O) + row * p.ldo + col) = pk;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.O) + row * p.ldo + col) = v;
+  }
+}
+
+// ---- rows: one G-lane group per row ----------------------------------------------------------
+template <int G, int VPL, int MIX>
+__global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
+  constexpr int GROUPS = 256 / G;
+  constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
+  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS
+  if (MIX == MIX_BASIS) {
+    for (int t = threadIdx.x; t < p.R * p.B; t += 256) s_comp[t] = p.comp[(t / p.B) * p.ldcomp + (t % p.B)];
+    __syncthreads();
+  }
+  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int nvec = p.d >> 2;
+  const int64_t row = (int64_t)blockIdx.x * GROUPS + grp;
+  if (row >= p.n_rows) return;
+  const int64_t key0 = row * p.R;
+
+  float4 mix[NB][VPL];
+  if (MIX != MIX_NONE) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) mix[b][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MIX == MIX_SUM && p.init) {
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vi = k * G + lane;
+        if (vi < nvec) mix[0][k] = ldg4(p.init + row * p.ld_init + vi * 4);
+      }
+    }
+  }
+
+  for (int rbase = 0; rbase < p.R; rbase += G) {
+    // the group's lanes fetch G consecutive (beg, end) pairs with two coalesced loads
+    const int rl = rbase + lane;
+    const int my_beg = (rl < p.R) ? __ldg(p.rowptr + key0 + rl) : 0;
+    const int my_end = (rl < p.R) ? __ldg(p.rowptr + key0 + rl + 1) : 0;
+    const int rcount = min(G, p.R - rbase);
+    for (int rr = 0; rr < rcount; ++rr) {
+      const int r = rbase + rr;
+      const int beg = __shfl_sync(gmask, my_beg, rr, G);
+      const int end = __shfl_sync(gmask, my_end, rr, G);
+      const int len = end - beg;
+      if (len == 0 && MIX != MIX_NONE) continue;
+      float4 acc[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (len > kHubThreshold) {
+        // hub: add the chunk partials in chunk order
+        const int key = (int)(key0 + r);
+        int lo = 0, hi = p.n_hubs;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(p.hub_keys + mid) <= key) lo = mid; else hi = mid;
+        }
+        const int c0 = __ldg(p.hub_chunk_ptr + lo), c1 = __ldg(p.hub_chunk_ptr + lo + 1);
+        for (int c = c0; c < c1; ++c) {
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const int vi = k * G + lane;
+            if (vi < nvec) add4(acc[k], reinterpret_cast<const float4*>(p.partials + (size_t)c * p.d)[vi]);
+          }
+        }
+      } else if (len > 0) {
+        const float* Fb = p.F + (size_t)r * p.src_rel_stride;
+        for (int e = beg; e < end; e += U) {
+          float4 v[U][VPL];
+          float w[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool ok = e + u < end;
+            const int j = ok ? __ldg(p.idx + e + u) : 0;
+            w[u] = (ok && p.edge_w) ? __ldg(p.edge_w + e + u) : 1.f;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+              const int vi = k * G + lane;
+              v[u][k] = (ok && vi < nvec) ? ldg4(Fb + (size_t)j * p.ldf + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+              if (p.edge_w) fma4(acc[k], w[u], v[u][k]); else add4(acc[k], v[u][k]);
+            }
+        }
+      }
+      if (!p.edge_w && len > 1) {
+        const float c = (float)len;   // s / clamp(cnt, 1): a true division, like the reference
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = div4(acc[k], c);
+      }
+      if (MIX == MIX_NONE) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int vi = k * G + lane;
+          if (vi < nvec) store_vec(p, row, r * p.d + vi * 4, acc[k]);
+        }
+      } else if (MIX == MIX_SUM) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) add4(mix[0][k], acc[k]);
+      } else {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          if (b < p.B) {
+            const float c = s_comp[r * p.B + b];
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) fma4(mix[b][k], c, acc[k]);
+          }
+        }
+      }
+    }
+  }
+  if (MIX != MIX_NONE) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (b < p.B) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int vi = k * G + lane;
+          if (vi < nvec) store_vec(p, row, b * p.d + vi * 4, mix[b][k]);
+        }
+      }
+    }
+  }
+}
+
+template <int G, int VPL>
+static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
+  constexpr int GROUPS = 256 / G;
+  if (n_chunks > 0) {
+    hub_partial_kernel<G, VPL><<<n_chunks, 256, 0, st>>>(p);
+    RGCN_LAUNCH_CHECK();
+  }
+  if (p.n_rows == 0) return RGCN_OK;
+  const unsigned grid = (unsigned)((p.n_rows + GROUPS - 1) / GROUPS);
+  if (mix == MIX_NONE) {
+    aggregate_rows_kernel<G, VPL, MIX_NONE><<<grid, 256, 0, st>>>(p);
+  } else if (mix == MIX_SUM) {
+    aggregate_rows_kernel<G, VPL, MIX_SUM><<<grid, 256, 0, st>>>(p);
+  } else {
+    aggregate_rows_kernel<G, VPL, MIX_BASIS><<<grid, 256, (size_t)p.R * p.B * sizeof(float), st>>>(p);
+  }
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+static int dispatch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
+  const int nvec = p.d >> 2;
+  if (nvec <= 4) return launch_agg<4, 1>(p, mix, n_chunks, st);
+  if (nvec <= 8) return launch_agg<8, 1>(p, mix, n_chunks, st);
+  if (nvec <= 16) return launch_agg<16, 1>(p, mix, n_chunks, st);
+  if (nvec <= 32) return launch_agg<32, 1>(p, mix, n_chunks, st);
+  if (nvec <= 64) return launch_agg<32, 2>(p, mix, n_chunks, st);
+  if (nvec <= 128) return launch_agg<32, 4>(p, mix, n_chunks, st);
+  return launch_agg<32, 8>(p, mix, n_chunks, st);
+}
+
+static int check_common(const rgcn_csr_t* g, const float* F, int64_t ldf, int32_t d, const void* ws,
+                        size_t ws_bytes) {
+  RGCN_CHECK_ARG(g && g->rowptr && (g->idx || g->E == 0), "aggregate: null CSR arrays");
+  RGCN_CHECK_ARG(g->R >= 1 && g->n_rows >= 0, "aggregate: bad n_rows/R");
+  RGCN_CHECK_ARG(d >= 4 && d <= 1024 && d % 4 == 0, "aggregate: feature width d=%d must be a multiple of 4 in [4,1024]", d);
+  RGCN_CHECK_ARG(F && ldf % 4 == 0 && ((uintptr_t)F & 15) == 0, "aggregate: feature matrix must be 16-byte aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(g->n_chunks == 0 || (g->hub_keys && g->hub_chunk_ptr && g->n_hubs > 0), "aggregate: hub plan missing");
+  if (g->n_chunks > 0 && (!ws || ws_bytes < (size_t)g->n_chunks * d * sizeof(float))) {
+    set_error("aggregate: workspace too small (%zu < %zu)", ws_bytes, (size_t)g->n_chunks * d * sizeof(float));
+    return RGCN_EWORKSPACE;
+  }
+  return RGCN_OK;
+}
+
+}  // namespace rgcn
+
+using namespace rgcn;
+
+extern "C" size_t rgcn_aggregate_workspace_bytes(const rgcn_csr_t* g, int32_t d) {
+  if (!g) return 0;
+  return align_up((size_t)g->n_chunks * (size_t)d * sizeof(float), 256);
+}
+
+extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d,
+                                  const float* comp, int32_t B, void* H, int64_t ldh, int32_t out_bf16,
+                                  void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+  int rc = check_common(g, X, ldx, d, workspace, workspace_bytes);
+  if (rc) return rc;
+  RGCN_CHECK_ARG(H && ((uintptr_t)H & 15) == 0 && ldh % 4 == 0, "aggregate_fwd: output must be 16-byte aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(!comp || (B >= 1), "aggregate_fwd: bad number of bases");
+  AggParams p{};
+  p.rowptr = g->rowptr; p.idx = g->idx; p.edge_w = g->w;
+  p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs;
+  p.n_rows = g->n_rows; p.R = g->R;
+  p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d;
+  p.O = H; p.ldo = ldh; p.out_bf16 = out_bf16; p.partials = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!comp) return dispatch_agg(p, MIX_NONE, g->n_chunks, st);
+  // basis blocks are produced kMaxBasis at a time (registers hold B * d/lanes accumulators)
+  for (int b0 = 0; b0 < B; b0 += kMaxBasis) {
+    AggParams q = p;
+    q.comp = comp + b0; q.ldcomp = B; q.B = (B - b0 < kMaxBasis) ? (B - b0) : kMaxBasis;
+    q.O = out_bf16 ? (void*)((__nv_bfloat16*)H + (size_t)b0 * d) : (void*)((float*)H + (size_t)b0 * d);
+    rc = dispatch_agg(q, MIX_BASIS, b0 == 0 ? g->n_chunks : 0, st);   // chunk partials do not depend on b
+    if (rc) return rc;
+  }
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
+                                  const float* init, int64_t ld_init, float* gX, int64_t ldgx,
+                                  void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+  int rc = check_common(gt, gH, ldg, d, workspace, workspace_bytes);
+  if (rc) return rc;
+  RGCN_CHECK_ARG(gX && ((uintptr_t)gX & 15) == 0 && ldgx % 4 == 0, "aggregate_bwd: output must be 16-byte aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(!init || (((uintptr_t)init & 15) == 0 && ld_init % 4 == 0), "aggregate_bwd: init must be 16-byte aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(gt->w || gt->E == 0, "aggregate_bwd: the transposed CSR needs per-edge weights w_t");
+  AggParams p{};
+  p.rowptr = gt->rowptr; p.idx = gt->idx; p.edge_w = gt->w;
+  p.hub_keys = gt->hub_keys; p.hub_chunk_ptr = gt->hub_chunk_ptr; p.n_hubs = gt->n_hubs;
+  p.n_rows = gt->n_rows; p.R = gt->R;
+  p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d;
+  p.init = init; p.ld_init = ld_init; p.B = 1;
+  p.O = gX; p.ldo = ldgx; p.out_bf16 = 0; p.partials = (float*)workspace;
+  return dispatch_agg(p, MIX_SUM, gt->n_chunks, (cudaStream_t)stream);
+}

@@ -1,0 +1,156 @@
+"""Device-resident relational graph: (dst, rel) CSR + (src, rel) transposed CSR + hub plans.
+
+Built once per ``(edge_index, edge_type)`` pair by ``rgcn_csr_build`` / ``rgcn_hub_plan`` and cached:
+the reference passes the SAME tensor objects on every step (src/train.py:130-135, :291-293, :389-391;
+src/evaluate.py:251-254), so the cache hits on every call after the first.
+
+HBM layout (all int32 / fp32, contiguous):
+    rowptr   [n_dst * R + 1]   col   [E]   perm   [E]        keyed dst * R + rel
+    rowptr_t [n_src * R + 1]   row_t [E]   perm_t [E]  w_t [E]   keyed src * R + rel
+    inv_cnt  [n_dst * R]       1 / max(|N_r(i)|, 1)
+    hub_keys / hub_chunk_ptr   per orientation (segments > 128 edges, cut into 512-edge chunks)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Orientation:
+    """One CSR orientation + its hub plan, and the ``rgcn_csr_t`` handed to the kernels."""
+
+    def __init__(self, rowptr, idx, w, n_rows, R, E):
+        self.rowptr, self.idx, self.w = rowptr, idx, w
+        self.n_rows, self.R, self.E = int(n_rows), int(R), int(E)
+        self.hub_keys = self.hub_chunk_ptr = None
+        self.n_hubs = self.n_chunks = 0
+        self._plan_hubs()
+        self.struct = _lib.CsrStruct(
+            _ptr(rowptr), _ptr(idx), _ptr(w), self.n_rows, self.E, self.R, self.n_hubs, self.n_chunks, 0,
+            _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr))
+        self.ref = C.byref(self.struct)
+        self._ws = {}
+
+    def _plan_hubs(self):
+        lib = _lib.load()
+        dev = self.rowptr.device
+        cap = self.E // 128 + 1
+        n_keys = self.n_rows * self.R
+        hub_keys = torch.empty(cap, dtype=torch.int32, device=dev)
+        chunk_ptr = torch.empty(cap + 1, dtype=torch.int32, device=dev)
+        ws_bytes = lib.rgcn_hub_plan_workspace_bytes(n_keys, cap)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        nh, nc = C.c_int32(0), C.c_int32(0)
+        _lib.check(lib.rgcn_hub_plan(_ptr(self.rowptr), n_keys, _ptr(hub_keys), _ptr(chunk_ptr), cap,
+                                     C.byref(nh), C.byref(nc), _ptr(ws), ws_bytes, _stream(dev)), "rgcn_hub_plan")
+        self.n_hubs, self.n_chunks = int(nh.value), int(nc.value)
+        if self.n_hubs:
+            self.hub_keys = hub_keys[: self.n_hubs].clone()
+            self.hub_chunk_ptr = chunk_ptr[: self.n_hubs + 1].clone()
+
+    def workspace(self, d: int) -> Optional[torch.Tensor]:
+        """Chunk-partial buffer for feature width d (kept; sized n_chunks * d floats)."""
+        if self.n_chunks == 0:
+            return None
+        ws = self._ws.get(d)
+        if ws is None:
+            ws = torch.empty(self.n_chunks * d + 64, dtype=torch.float32, device=self.rowptr.device)
+            self._ws[d] = ws
+        return ws
+
+
+class RelGraph:
+    """The preprocessed graph.  ``n_dst`` rows are aggregated into, ``n_src`` rows are gathered from
+    (equal on one GPU; a destination-range shard has n_dst < n_src)."""
+
+    def __init__(self, src: torch.Tensor, dst: torch.Tensor, rel: torch.Tensor, n_dst: int, n_src: int,
+                 num_relations: int):
+        lib = _lib.load()
+        if not src.is_cuda:
+            raise RuntimeError("RelGraph needs CUDA tensors: the RGCN B200 path has no CPU implementation")
+        _lib.check(lib.rgcn_check_device(), "rgcn_check_device")
+        src, dst, rel = (t.contiguous().to(torch.int64) for t in (src, dst, rel))
+        E = int(rel.numel())
+        if src.numel() != E or dst.numel() != E:
+            raise ValueError("edge_index and edge_type disagree on the number of edges")
+        dev = src.device
+        R = int(num_relations)
+        self.n_dst, self.n_src, self.R, self.E, self.device = int(n_dst), int(n_src), R, E, dev
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(n_dst * R + 1, **i32)
+        self.rowptr_t = torch.empty(n_src * R + 1, **i32)
+        self.col, self.perm = torch.empty(E, **i32), torch.empty(E, **i32)
+        self.row_t, self.perm_t = torch.empty(E, **i32), torch.empty(E, **i32)
+        self.inv_cnt = torch.empty(n_dst * R, dtype=torch.float32, device=dev)
+        self.w_t = torch.empty(E, dtype=torch.float32, device=dev)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        ws_bytes = lib.rgcn_csr_build_workspace_bytes(E, n_dst, n_src, R)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.rgcn_csr_build(
+                _ptr(src), _ptr(dst), _ptr(rel), E, n_dst, n_src, R,
+                _ptr(self.rowptr), _ptr(self.col), _ptr(self.perm),
+                _ptr(self.rowptr_t), _ptr(self.row_t), _ptr(self.perm_t),
+                _ptr(self.inv_cnt), _ptr(self.w_t), _ptr(status), _ptr(ws), ws_bytes, _stream(dev)),
+                "rgcn_csr_build")
+            st = status.cpu().tolist()          # one-off synchronisation per graph
+            if st[0]:
+                what = [n for b, n in ((1, "source index"), (2, "destination index"), (4, "edge_type")) if st[0] & b]
+                raise IndexError(f"graph has out-of-range {', '.join(what)} "
+                                 f"(n_src={n_src}, n_dst={n_dst}, num_relations={R})")
+            self.max_seg, self.max_seg_t = st[2], st[3]
+            self.fwd = _Orientation(self.rowptr, self.col, None, n_dst, R, E)
+            self.bwd = _Orientation(self.rowptr_t, self.row_t, self.w_t, n_src, R, E)
+        del ws
+
+    @classmethod
+    def from_edges(cls, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_relations: int):
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise ValueError("edge_index must have shape [2, E]")
+        if edge_type is None:
+            raise ValueError("edge_type is required")          # PyG asserts the same
+        return cls(edge_index[0], edge_index[1], edge_type, num_nodes, num_nodes, num_relations)
+
+
+# ---- cache keyed on tensor identity -------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_MAX = 8
+
+
+def get_graph(edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_relations: int) -> RelGraph:
+    """Cached ``RelGraph`` for this ``(edge_index, edge_type)`` pair.
+
+    An entry is valid only while the tensors it was built from are alive and unmodified
+    (weak references + ``_version``), so a recycled allocation can never alias a stale graph."""
+    key = (edge_index.data_ptr(), edge_type.data_ptr(), tuple(edge_index.shape), edge_index.stride(),
+           str(edge_index.device), int(num_nodes), int(num_relations))
+    hit = _CACHE.get(key)
+    if hit is not None:
+        g, r_ei, r_et, v_ei, v_et = hit
+        if r_ei() is not None and r_et() is not None and edge_index._version == v_ei and edge_type._version == v_et:
+            _CACHE.move_to_end(key)
+            return g
+        del _CACHE[key]
+    g = RelGraph.from_edges(edge_index, edge_type, num_nodes, num_relations)
+    _CACHE[key] = (g, weakref.ref(edge_index), weakref.ref(edge_type), edge_index._version, edge_type._version)
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+    return g
+
+
+def clear_graph_cache() -> None:
+    _CACHE.clear()

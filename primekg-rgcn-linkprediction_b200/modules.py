@@ -1,0 +1,186 @@
+"""The reference's model trio on the sm_100a kernels — same constructor arguments, attribute names,
+state-dict keys, method set and error behaviour as reference src/models/rgcn.py:
+
+    DrugDiseaseRGCN  (:21-142)   node_embeddings, conv1, conv2, dropout
+    LinkPredictor    (:145-243)  relation_embeddings, dropout
+    DrugDiseaseModel (:246-415)  encoder, decoder; forward / predict / predict_all_tails / get_embeddings
+
+so that src/train.py, src/evaluate.py and the analysis scripts of the reference run unchanged on top
+(`from models.rgcn import DrugDiseaseModel`).  State-dict keys: encoder.node_embeddings.weight,
+encoder.conv{1,2}.{weight,[comp],root,bias}, decoder.relation_embeddings.weight — 2,078,208
+parameters at the defaults (reference results/results.json:29).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .conv import RGCNConv
+from .graph import get_graph
+
+
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: this is the B200 (sm_100a) implementation and has no CPU path; "
+                           "move the model and its inputs to a CUDA device")
+
+
+class DrugDiseaseRGCN(nn.Module):
+    """RGCN encoder: Embedding(N, d_e) -> RGCNConv -> ReLU -> Dropout -> RGCNConv (reference :51-130).
+    ``num_layers`` > 2 appends further ReLU/Dropout/RGCNConv(hidden, hidden) stages (the extension
+    pattern of reference guide/MODEL_ARCHITECTURE.md:245-249; used by the 3-layer 10 M-node config)."""
+
+    def __init__(self, num_nodes: int, num_relations: int, embedding_dim: int = 64, hidden_dim: int = 128,
+                 dropout: float = 0.5, num_bases: Optional[int] = None, num_layers: int = 2):
+        super().__init__()
+        self.num_nodes = num_nodes
+        self.num_relations = num_relations
+        self.embedding_dim = embedding_dim
+        self.hidden_dim = hidden_dim
+        # construction order = the reference's, so a seeded init draws the same random stream
+        self.node_embeddings = nn.Embedding(num_nodes, embedding_dim)
+        self.conv1 = RGCNConv(embedding_dim, hidden_dim, num_relations, num_bases=num_bases)
+        self.conv2 = RGCNConv(hidden_dim, hidden_dim, num_relations, num_bases=num_bases)
+        if num_layers > 2:
+            self.extra_convs = nn.ModuleList(
+                RGCNConv(hidden_dim, hidden_dim, num_relations, num_bases=num_bases) for _ in range(num_layers - 2))
+        self.dropout = nn.Dropout(dropout)
+        self._init_embeddings()
+
+    def _init_embeddings(self) -> None:
+        nn.init.xavier_uniform_(self.node_embeddings.weight)
+
+    def _layers(self):
+        yield self.conv1
+        yield self.conv2
+        if hasattr(self, "extra_convs"):
+            yield from self.extra_convs
+
+    def forward(self, edge_index: torch.Tensor, edge_type: torch.Tensor,
+                node_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = self.node_embeddings.weight if node_indices is None else self.node_embeddings(node_indices)
+        _need_cuda(x, "DrugDiseaseRGCN.forward")
+        graph = get_graph(edge_index, edge_type, x.size(0), self.num_relations)
+        layers = list(self._layers())
+        for li, conv in enumerate(layers):
+            last = li == len(layers) - 1
+            x = conv.forward_graph(x, graph, relu=not last)      # ReLU fused into the layer epilogue
+            if not last:
+                x = self.dropout(x)
+        return x
+
+    def get_node_embeddings(self, node_indices: torch.Tensor) -> torch.Tensor:
+        return self.node_embeddings(node_indices)
+
+
+class _DistMultGather(torch.autograd.Function):
+    """score[p] = <emb[head[p]], r_p, emb[tail[p]]> with the row gathers fused into the kernel."""
+
+    @staticmethod
+    def forward(ctx, emb, head, tail, rel, rel_table, rel_rows):
+        ctx.save_for_backward(emb, head, tail, rel, rel_table, rel_rows)
+        return ops.distmult_fwd(emb, emb, head, tail, rel, rel_table, rel_rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, head, tail, rel, rel_table, rel_rows = ctx.saved_tensors
+        g_emb, _, g_tab, g_rows = ops.distmult_bwd(emb, emb, head, tail, rel, rel_table, rel_rows, g,
+                                                   ctx.needs_input_grad[4])
+        return (g_emb if ctx.needs_input_grad[0] else None), None, None, None, g_tab, g_rows
+
+
+class _DistMultRows(torch.autograd.Function):
+    """score[p] = <head_emb[p], r_p, tail_emb[p]> on rows the caller already gathered."""
+
+    @staticmethod
+    def forward(ctx, head_emb, tail_emb, rel, rel_table, rel_rows):
+        ctx.save_for_backward(head_emb, tail_emb, rel, rel_table, rel_rows)
+        return ops.distmult_fwd(head_emb, tail_emb, None, None, rel, rel_table, rel_rows)
+
+    @staticmethod
+    def backward(ctx, g):
+        head_emb, tail_emb, rel, rel_table, rel_rows = ctx.saved_tensors
+        g_h, g_t, g_tab, g_rows = ops.distmult_bwd(head_emb, tail_emb, None, None, rel, rel_table, rel_rows, g,
+                                                   ctx.needs_input_grad[3])
+        return g_h, g_t, None, g_tab, g_rows
+
+
+class LinkPredictor(nn.Module):
+    """DistMult decoder (reference :165-243): score(h, r, t) = sum_k h_k r_k t_k."""
+
+    def __init__(self, num_relations: int, embedding_dim: int, dropout: float = 0.0):
+        super().__init__()
+        self.num_relations = num_relations
+        self.embedding_dim = embedding_dim
+        self.relation_embeddings = nn.Embedding(num_relations, embedding_dim)
+        self.dropout = nn.Dropout(dropout)
+        self._init_embeddings()
+
+    def _init_embeddings(self) -> None:
+        nn.init.xavier_uniform_(self.relation_embeddings.weight)
+
+    def _relation_operand(self, relation_types):
+        """(rel_table, rel_rows): dropout active => rows gathered + dropped by torch's own RNG
+        (reference :207-208), otherwise the kernel reads the table directly."""
+        if self.training and self.dropout.p > 0:
+            return None, self.dropout(self.relation_embeddings(relation_types))
+        return self.relation_embeddings.weight, None
+
+    def forward(self, head_embeddings: torch.Tensor, tail_embeddings: torch.Tensor,
+                relation_types: torch.Tensor) -> torch.Tensor:
+        _need_cuda(head_embeddings, "LinkPredictor.forward")
+        table, rows = self._relation_operand(relation_types)
+        return _DistMultRows.apply(head_embeddings, tail_embeddings, relation_types, table, rows)
+
+    def score_pairs(self, node_embeddings: torch.Tensor, head_indices: torch.Tensor, tail_indices: torch.Tensor,
+                    relation_types: torch.Tensor) -> torch.Tensor:
+        """Fused form of ``forward(emb[head], emb[tail], rel)`` (reference :325-329)."""
+        _need_cuda(node_embeddings, "LinkPredictor.score_pairs")
+        table, rows = self._relation_operand(relation_types)
+        return _DistMultGather.apply(node_embeddings, head_indices, tail_indices, relation_types, table, rows)
+
+    def score_all_tails(self, head_embeddings: torch.Tensor, relation_types: torch.Tensor,
+                        all_tail_embeddings: torch.Tensor) -> torch.Tensor:
+        """(h * r) @ T^T -> [batch, num_entities] (reference :234-241; no dropout here, as there)."""
+        _need_cuda(head_embeddings, "LinkPredictor.score_all_tails")
+        hr = head_embeddings * self.relation_embeddings(relation_types)
+        return hr @ all_tail_embeddings.t()
+
+
+class DrugDiseaseModel(nn.Module):
+    """Encoder + decoder (reference :267-415)."""
+
+    def __init__(self, num_nodes: int, num_relations: int, embedding_dim: int = 64, hidden_dim: int = 128,
+                 dropout: float = 0.5, decoder_dropout: float = 0.0, num_bases: Optional[int] = None,
+                 num_layers: int = 2):
+        super().__init__()
+        self.num_nodes = num_nodes
+        self.num_relations = num_relations
+        self.hidden_dim = hidden_dim
+        self.encoder = DrugDiseaseRGCN(num_nodes=num_nodes, num_relations=num_relations,
+                                       embedding_dim=embedding_dim, hidden_dim=hidden_dim, dropout=dropout,
+                                       num_bases=num_bases, num_layers=num_layers)
+        self.decoder = LinkPredictor(num_relations=num_relations, embedding_dim=hidden_dim, dropout=decoder_dropout)
+
+    def forward(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:
+        node_embeddings = self.encoder(edge_index, edge_type)
+        return self.decoder.score_pairs(node_embeddings, head_indices, tail_indices, relation_types)
+
+    def predict(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:
+        self.eval()
+        with torch.no_grad():
+            return self.forward(edge_index, edge_type, head_indices, tail_indices, relation_types)
+
+    def predict_all_tails(self, edge_index, edge_type, head_indices, relation_types) -> torch.Tensor:
+        self.eval()
+        with torch.no_grad():
+            emb = self.encoder(edge_index, edge_type)
+            return self.decoder.score_all_tails(emb[head_indices], relation_types, emb)
+
+    def get_embeddings(self, edge_index, edge_type) -> torch.Tensor:
+        self.eval()
+        with torch.no_grad():
+            return self.encoder(edge_index, edge_type)

@@ -1,0 +1,391 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI) against the CPU oracle, the golden
+fixtures produced by the unmodified reference model file, and size-independent properties at the
+benchmark's full size.
+
+Tolerances (BASELINE.json north_star): bit-exact for CSR / index construction; rtol 1e-4 for fp32
+embeddings, losses and scores; 2e-2 in the bf16-transform mode.  Gradients of sums over ~10^3 terms
+are compared at rtol 1e-3 / small atol (different but fixed summation orders).
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, load_val_graph
+from oracle import rgcn_ref as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def pkg(lib_built):
+    return lib_built
+
+
+def _graphs():
+    from primekg_rgcn_linkprediction_b200 import synth
+    v = load_val_graph()
+    out = {
+        "uniform_small": (synth.uniform_kg(100, 500, 3, seed=1), None),
+        "uniform_r30": (synth.uniform_kg(5000, 60_000, 30, seed=2), None),
+        "primekg_100k": (synth.primekg_subgraph(100_000, seed=3), None),
+        "one_relation": (synth.uniform_kg(257, 4000, 1, seed=4), None),
+    }
+    g = {k: (kg.edge_index, kg.edge_type, kg.num_nodes, kg.num_relations) for k, (kg, _) in out.items()}
+    g["val_fixture"] = (v["edge_index"], v["edge_type"], v["num_nodes"], v["num_relations"])
+    g["empty"] = (torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64), 17, 3)
+    # ragged: isolated nodes, a node with only relation-1 in-edges, a multi-edge, a self loop
+    g["ragged"] = (torch.tensor([[0, 1, 1, 2, 0, 2, 6, 6], [1, 0, 0, 0, 3, 3, 6, 0]]),
+                   torch.tensor([0, 0, 0, 0, 1, 1, 2, 2]), 9, 3)
+    return g
+
+
+GRAPHS = None
+
+
+def graphs():
+    global GRAPHS
+    if GRAPHS is None:
+        GRAPHS = _graphs()
+    return GRAPHS
+
+
+GRAPH_NAMES = ["uniform_small", "uniform_r30", "primekg_100k", "one_relation", "val_fixture", "empty", "ragged"]
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) graph preprocessing: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GRAPH_NAMES)
+def test_csr_bit_exact(pkg, name):
+    ei, et, N, R = graphs()[name]
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    rowptr, col, perm, rowptr_t, row_t, perm_t = O.csr_oracle(ei, et, N, R)
+    for got, want, what in ((g.rowptr, rowptr, "rowptr"), (g.col, col, "col"), (g.perm, perm, "perm"),
+                            (g.rowptr_t, rowptr_t, "rowptr_t"), (g.row_t, row_t, "row_t"), (g.perm_t, perm_t, "perm_t")):
+        assert torch.equal(got.cpu().to(torch.int64), want), what
+    cnt = (rowptr[1:] - rowptr[:-1]).clamp(min=1).to(torch.float32)
+    assert torch.equal(g.inv_cnt.cpu(), 1.0 / cnt)
+    if ei.size(1):
+        w = (1.0 / cnt)[(ei[1] * R + et)[perm_t]]
+        assert torch.equal(g.w_t.cpu(), w)
+        assert g.max_seg == int((rowptr[1:] - rowptr[:-1]).max())
+        assert g.max_seg_t == int((rowptr_t[1:] - rowptr_t[:-1]).max())
+
+
+def test_csr_rejects_out_of_range(pkg):
+    ei = torch.tensor([[0, 5], [1, 0]], device=DEV)
+    with pytest.raises(IndexError):
+        pkg.RelGraph.from_edges(ei, torch.tensor([0, 0], device=DEV), 5, 1)
+    with pytest.raises(IndexError):
+        pkg.RelGraph.from_edges(torch.tensor([[0], [1]], device=DEV), torch.tensor([3], device=DEV), 5, 3)
+    with pytest.raises(IndexError):
+        pkg.RelGraph.from_edges(torch.tensor([[0], [-1]], device=DEV), torch.tensor([0], device=DEV), 5, 3)
+
+
+def test_graph_cache_identity_and_invalidation(pkg):
+    ei, et, N, R = graphs()["uniform_small"]
+    ei, et = ei.to(DEV), et.to(DEV)
+    pkg.clear_graph_cache()
+    g1 = pkg.get_graph(ei, et, N, R)
+    assert pkg.get_graph(ei, et, N, R) is g1                 # same tensors every step => cache hit
+    et[0] = (et[0] + 1) % R                                  # in-place edit bumps _version
+    g2 = pkg.get_graph(ei, et, N, R)
+    assert g2 is not g1
+    rowptr = O.csr_oracle(ei.cpu(), et.cpu(), N, R)[0]
+    assert torch.equal(g2.rowptr.cpu().to(torch.int64), rowptr)
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) aggregation forward / backward
+# ------------------------------------------------------------------------------------------------
+def _means_ref(x, ei, et, N, R):
+    out = []
+    for r in range(R):
+        m = et == r
+        s = torch.zeros(N, x.size(1), dtype=x.dtype).index_add_(0, ei[1][m], x[ei[0][m]])
+        c = torch.zeros(N, dtype=x.dtype).index_add_(0, ei[1][m], torch.ones(int(m.sum()), dtype=x.dtype)).clamp_(min=1)
+        out.append(s / c[:, None])
+    return torch.cat(out, 1)
+
+
+@pytest.mark.parametrize("name", GRAPH_NAMES)
+@pytest.mark.parametrize("d", [16, 64, 128, 256, 100])
+def test_aggregate_fwd(pkg, name, d):
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()[name]
+    if N * R * d > 60_000_000:
+        pytest.skip("oracle too slow at this size")
+    torch.manual_seed(0)
+    x = torch.randn(N, d)
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    H = ops.aggregate_fwd(g, x.to(DEV)).cpu()
+    want = _means_ref(x, ei, et, N, R)
+    torch.testing.assert_close(H, want, rtol=1e-5, atol=1e-5)
+    # segments below the hub threshold are summed serially in original edge order => identical bits
+    cnt = (g.rowptr[1:] - g.rowptr[:-1]).cpu().view(N, R)
+    small = (cnt <= 128)[:, :, None].expand(N, R, d).reshape(N, R * d)
+    assert torch.equal(H[small], want[small])
+    Hb = ops.aggregate_fwd(g, x.to(DEV), out_bf16=True).cpu()
+    assert torch.equal(Hb, H.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("name", ["uniform_small", "uniform_r30", "primekg_100k", "val_fixture", "ragged", "empty"])
+@pytest.mark.parametrize("d", [64, 256])
+def test_aggregate_bwd(pkg, name, d):
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()[name]
+    if N * R * d > 60_000_000:
+        pytest.skip("oracle too slow at this size")
+    torch.manual_seed(1)
+    x = torch.randn(N, d, dtype=torch.float64, requires_grad=True)
+    gA = torch.randn(N, (R + 1) * d)
+    H = _means_ref(x, ei, et, N, R)
+    (H * gA[:, : R * d].double()).sum().backward()
+    want = x.grad.float() + gA[:, R * d:]
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    gAd = gA.to(DEV)
+    got = ops.aggregate_bwd(g, gAd, d, init=gAd[:, R * d:]).cpu()
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    got2 = ops.aggregate_bwd(g, gAd, d, init=gAd[:, R * d:]).cpu()
+    assert torch.equal(got, got2)                            # deterministic: no atomics
+
+
+def test_aggregate_basis_mix(pkg):
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()["uniform_r30"]
+    torch.manual_seed(2)
+    d, B = 64, 8
+    x = torch.randn(N, d)
+    comp = torch.randn(R, B)
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    Z = ops.aggregate_fwd(g, x.to(DEV), comp=comp.to(DEV)).cpu()
+    H = _means_ref(x, ei, et, N, R).view(N, R, d)
+    want = torch.einsum("nrd,rb->nbd", H, comp).reshape(N, B * d)
+    torch.testing.assert_close(Z, want, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# the layer and the whole model against the goldens of the unmodified reference file
+# ------------------------------------------------------------------------------------------------
+def test_micro_graph_exact(pkg):
+    g = load_golden("micro")
+    conv = pkg.RGCNConv(4, 4, 2)
+    with torch.no_grad():
+        conv.weight.copy_(g["weight"]); conv.root.copy_(g["root"]); conv.bias.copy_(g["bias"])
+    conv.to(DEV)
+    out = conv(g["x"].to(DEV), g["edge_index"].to(DEV), g["edge_type"].to(DEV))
+    torch.testing.assert_close(out.cpu(), g["expected"], rtol=1e-6, atol=1e-4)
+
+
+def _product_model(pkg, g, mode="fp32"):
+    m = pkg.DrugDiseaseModel(g["num_nodes"], g["num_relations"], g["embedding_dim"], g["hidden_dim"], dropout=0.0,
+                             decoder_dropout=0.0, num_bases=g["num_bases"])
+    m.load_state_dict(g["state_dict"], strict=True)          # reference-trained checkpoints load as they are
+    for c in (m.encoder.conv1, m.encoder.conv2):
+        c.mode = mode
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("name", ["small_full", "small_basis", "small_default_init"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_model_matches_reference_goldens(pkg, name, mode):
+    g = load_golden(name)
+    m = _product_model(pkg, g, mode)
+    rtol, atol = (1e-4, 1e-5) if mode == "fp32" else (2e-2, 2e-2)
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    m.train()
+    scores = m(ei, et, g["heads"].to(DEV), g["tails"].to(DEV), g["rels"].to(DEV))
+    loss = F.binary_cross_entropy_with_logits(scores, g["labels"].to(DEV))
+    loss.backward()
+    smax = float(g["scores"].abs().max())
+    torch.testing.assert_close(scores.detach().cpu(), g["scores"], rtol=rtol, atol=atol * max(1.0, smax))
+    torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=rtol, atol=atol)
+    for k, p in m.named_parameters():
+        want = g["grads"][k]
+        scale = float(want.abs().max()) + 1e-12
+        grtol, gatol = (1e-3, 1e-5 * scale) if mode == "fp32" else (5e-2, 3e-2 * scale)
+        torch.testing.assert_close(p.grad.cpu(), want, rtol=grtol, atol=gatol, msg=lambda s: f"{name}/{mode}/{k}: {s}")
+    emb = m.get_embeddings(ei, et)
+    emax = float(g["embeddings"].abs().max())
+    torch.testing.assert_close(emb.cpu(), g["embeddings"], rtol=rtol, atol=atol * max(1.0, emax))
+    if mode == "fp32":
+        all_t = m.predict_all_tails(ei, et, g["heads"][:8].to(DEV), g["rels"][:8].to(DEV))
+        torch.testing.assert_close(all_t.cpu(), g["all_tail_scores"], rtol=1e-4, atol=1e-4 * max(1.0, smax))
+        dec = m.decoder(emb[g["heads"].to(DEV)], emb[g["tails"].to(DEV)], g["rels"].to(DEV))
+        torch.testing.assert_close(dec.cpu(), g["decoder_scores"], rtol=1e-4, atol=1e-5 * max(1.0, smax))
+        pred = m.predict(ei, et, g["heads"].to(DEV), g["tails"].to(DEV), g["rels"].to(DEV))
+        torch.testing.assert_close(pred.cpu(), g["scores"], rtol=1e-4, atol=1e-5 * max(1.0, smax))
+
+
+def test_real_fixture_graph_rows(pkg):
+    """The reference's own validation graph: seeded init must consume the RNG in the reference's order and
+    the encoder must reproduce the reference's rows."""
+    v = load_val_graph()
+    torch.manual_seed(v["seed"])
+    m = pkg.DrugDiseaseModel(v["num_nodes"], v["num_relations"], 64, 128, dropout=0.5, decoder_dropout=0.1)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "conv" in k and not k.endswith("bias"):
+                p.mul_(v["conv_scale"])
+    m.to(DEV)
+    emb = m.get_embeddings(v["edge_index"].to(DEV), v["edge_type"].to(DEV)).cpu()
+    torch.testing.assert_close(emb[v["rows"]], v["emb_rows"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(emb.double().sum(0), v["emb_colsum"], rtol=1e-4, atol=1e-3)
+
+
+def test_decoder_rows_backward(pkg):
+    torch.manual_seed(4)
+    B, d, R = 37, 128, 3
+    dec = pkg.LinkPredictor(R, d).to(DEV)
+    ref = O.DecoderRef(R, d)
+    ref.load_state_dict(dec.state_dict())
+    h = torch.randn(B, d, requires_grad=True)
+    t = torch.randn(B, d, requires_grad=True)
+    rel = torch.randint(0, R, (B,))
+    hd, td = h.detach().to(DEV).requires_grad_(), t.detach().to(DEV).requires_grad_()
+    s = dec(hd, td, rel.to(DEV))
+    s.sum().backward()
+    sr = ref(h, t, rel)
+    sr.sum().backward()
+    torch.testing.assert_close(s.detach().cpu(), sr.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(hd.grad.cpu(), h.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(td.grad.cpu(), t.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dec.relation_embeddings.weight.grad.cpu(), ref.relation_embeddings.weight.grad,
+                               rtol=1e-4, atol=1e-4)
+
+
+def test_decoder_dropout_path_trains(pkg):
+    torch.manual_seed(5)
+    g = load_golden("small_full")
+    m = pkg.DrugDiseaseModel(g["num_nodes"], g["num_relations"], g["embedding_dim"], g["hidden_dim"], dropout=0.5,
+                             decoder_dropout=0.1).to(DEV)
+    m.train()
+    s = m(g["edge_index"].to(DEV), g["edge_type"].to(DEV), g["heads"].to(DEV), g["tails"].to(DEV), g["rels"].to(DEV))
+    F.binary_cross_entropy_with_logits(s, g["labels"].to(DEV)).backward()
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_encoder_deterministic(pkg):
+    g = load_golden("small_full")
+    m = _product_model(pkg, g)
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    outs, grads = [], []
+    for _ in range(2):
+        m.zero_grad()
+        e = m.encoder(ei, et)
+        e.square().sum().backward()
+        outs.append(e.detach().clone())
+        grads.append(m.encoder.node_embeddings.weight.grad.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(grads[0], grads[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# reference self-tests (src/models/rgcn.py:422-570): shapes
+# ------------------------------------------------------------------------------------------------
+def test_reference_shape_selftests(pkg):
+    torch.manual_seed(0)
+    enc = pkg.DrugDiseaseRGCN(100, 3, 64, 128).to(DEV)
+    ei = torch.randint(0, 100, (2, 500), device=DEV)
+    et = torch.randint(0, 3, (500,), device=DEV)
+    assert enc(ei, et).shape == (100, 128)
+    dec = pkg.LinkPredictor(3, 128).to(DEV)
+    h, t = torch.randn(32, 128, device=DEV), torch.randn(32, 128, device=DEV)
+    rel = torch.randint(0, 3, (32,), device=DEV)
+    assert dec(h, t, rel).shape == (32,)
+    assert dec.score_all_tails(h, rel, torch.randn(100, 128, device=DEV)).shape == (32, 100)
+    model = pkg.DrugDiseaseModel(100, 3, 64, 128).to(DEV)
+    heads, tails = torch.randint(0, 100, (32,), device=DEV), torch.randint(0, 100, (32,), device=DEV)
+    assert model(ei, et, heads, tails, rel).shape == (32,)
+    assert model.predict(ei, et, heads, tails, rel).shape == (32,)
+    assert model.predict_all_tails(ei, et, heads, rel).shape == (32, 100)
+    assert model.get_embeddings(ei, et).shape == (100, 128)
+    assert enc.get_node_embeddings(heads).shape == (32, 64)
+    sub = enc(ei, et, node_indices=torch.arange(100, device=DEV))
+    assert sub.shape == (100, 128)
+
+
+def test_error_behaviour(pkg):
+    conv = pkg.RGCNConv(8, 8, 2).to(DEV)
+    x = torch.randn(5, 8, device=DEV)
+    ei = torch.tensor([[0, 1], [1, 2]], device=DEV)
+    with pytest.raises(ValueError):
+        conv(x, ei, None)
+    with pytest.raises(IndexError):
+        conv(x, torch.tensor([[0, 7], [1, 2]], device=DEV), torch.tensor([0, 1], device=DEV))
+    with pytest.raises(RuntimeError):
+        pkg.RGCNConv(8, 8, 2)(x.cpu(), ei.cpu(), torch.tensor([0, 1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# full benchmark size (cfg2: 30,926 nodes / 849,456 edges / 3 relations, 64 -> 256 -> 256)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cfg2():
+    from primekg_rgcn_linkprediction_b200 import synth
+    kg = synth.primekg_subgraph()
+    return kg, synth.link_batch(kg, 1024)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_full_size_step_against_oracle_on_device(pkg, cfg2, mode):
+    """cfg2 at full size: the oracle restatement runs on the same GPU through stock torch ops."""
+    kg, (heads, tails, rels, labels) = cfg2
+    torch.manual_seed(42)
+    m = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, 256, dropout=0.0, decoder_dropout=0.0)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "conv" in k and not k.endswith("bias"):
+                p.mul_(4.0)
+    ref = O.ModelRef(kg.num_nodes, kg.num_relations, 64, 256, 0.0, 0.0)
+    ref.load_state_dict(m.state_dict())
+    for c in (m.encoder.conv1, m.encoder.conv2):
+        c.mode = mode
+    m.to(DEV).train(); ref.to(DEV).train()
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    b = [t.to(DEV) for t in (heads, tails, rels, labels)]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        s = m(ei, et, b[0], b[1], b[2])
+        loss = F.binary_cross_entropy_with_logits(s, b[3])
+        loss.backward()
+        rl, rs = O.train_step_ref(ref, ei, et, b[0], b[1], b[2], b[3])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    rtol, atol = (1e-4, 1e-5) if mode == "fp32" else (2e-2, 2e-2)
+    smax = float(rs.abs().max())
+    torch.testing.assert_close(s.detach(), rs, rtol=rtol, atol=atol * max(1.0, smax))
+    torch.testing.assert_close(loss.detach(), rl, rtol=rtol, atol=atol)
+    for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        scale = float(q.grad.abs().max()) + 1e-12
+        grtol, gatol = (1e-3, 2e-5 * scale) if mode == "fp32" else (5e-2, 3e-2 * scale)
+        torch.testing.assert_close(p.grad, q.grad, rtol=grtol, atol=gatol, msg=lambda t: f"{mode}/{k}: {t}")
+
+
+def test_full_size_properties(pkg, cfg2):
+    """Size-independent properties at 849,456 edges: linearity of the aggregation, the count-weighted
+    checksum  sum_i cnt(i, r) * H_r[i] = sum_{e of type r} x[src[e]], and adjointness <agg(x), g> = <x, agg^T(g)>."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    kg, _ = cfg2
+    N, R, d = kg.num_nodes, kg.num_relations, 64
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    g = pkg.get_graph(ei, et, N, R)
+    torch.manual_seed(9)
+    x, y = torch.randn(N, d, device=DEV), torch.randn(N, d, device=DEV)
+    Hx, Hy, Hxy = ops.aggregate_fwd(g, x), ops.aggregate_fwd(g, y), ops.aggregate_fwd(g, 2.0 * x + y)
+    torch.testing.assert_close(Hxy, 2.0 * Hx + Hy, rtol=1e-4, atol=1e-4)
+    cnt = (g.rowptr[1:] - g.rowptr[:-1]).view(N, R).double()
+    for r in range(R):
+        lhs = (Hx[:, r * d:(r + 1) * d].double() * cnt[:, r:r + 1]).sum(0)
+        rhs = x[ei[0][et == r]].double().sum(0)
+        torch.testing.assert_close(lhs, rhs, rtol=1e-6, atol=1e-3)
+    gA = torch.randn(N, (R + 1) * d, device=DEV)
+    gA[:, R * d:] = 0
+    gx = ops.aggregate_bwd(g, gA, d, init=gA[:, R * d:])
+    torch.testing.assert_close((Hx.double() * gA[:, : R * d].double()).sum(), (x.double() * gx.double()).sum(),
+                               rtol=1e-6, atol=1e-2)

@@ -1,0 +1,134 @@
+"""CPU tests of the host side: the C-ABI library builds, loads and exports every symbol the header
+declares (no compute without a GPU); module surface, state-dict layout, seeded init order; the synthetic
+workload generator; loud failure on CPU tensors."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from oracle import rgcn_ref as O
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "rgcn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"^\s*(?:int|size_t|int64_t)\s+(rgcn_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_library_exports_every_header_symbol(lib_built):
+    from primekg_rgcn_linkprediction_b200 import _lib
+    names = _header_symbols()
+    assert len(names) >= 12
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rgcn_b200.h but not exported"
+    assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
+    assert _lib.load().rgcn_abi_version() == 1
+
+
+def test_library_argument_errors_without_gpu(lib_built):
+    """Argument validation happens before any CUDA call, so it is testable here."""
+    from primekg_rgcn_linkprediction_b200 import _lib
+    lib = _lib.load()
+    rc = lib.rgcn_csr_build(None, None, None, -1, 1, 1, 1, None, None, None, None, None, None, None, None, None,
+                            None, 0, None)
+    assert rc == 1 and "negative" in _lib.last_error()
+    g = _lib.CsrStruct()
+    rc = lib.rgcn_aggregate_fwd(ctypes.byref(g), None, 0, 6, None, 0, None, 0, 0, None, 0, None)
+    assert rc == 1
+    with pytest.raises(_lib.RGCNLibraryError):
+        _lib.check(rc, "rgcn_aggregate_fwd")
+
+
+def test_csr_struct_matches_header_layout():
+    from primekg_rgcn_linkprediction_b200 import _lib
+    # 3 pointers, 2 int64, 4 int32, 2 pointers
+    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 2 * 8 + 4 * 4 + 2 * 8
+    assert _lib.CsrStruct.hub_keys.offset == 56
+
+
+def test_module_surface_and_state_dict(lib_built):
+    pkg = lib_built
+    m = pkg.DrugDiseaseModel(30926, 3)
+    assert sum(p.numel() for p in m.parameters()) == 2_078_208         # reference results/results.json:29
+    ref = O.ModelRef(30926, 3)
+    assert list(m.state_dict().keys()) == list(ref.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert m.state_dict()[k].shape == v.shape, k
+    for attr in ("node_embeddings", "conv1", "conv2", "dropout", "num_nodes", "num_relations", "embedding_dim",
+                 "hidden_dim"):
+        assert hasattr(m.encoder, attr)
+    assert hasattr(m.decoder, "relation_embeddings") and hasattr(m.decoder, "score_all_tails")
+    for meth in ("forward", "predict", "predict_all_tails", "get_embeddings"):
+        assert callable(getattr(m, meth))
+    mb = pkg.DrugDiseaseModel(50, 6, 16, 24, num_bases=2)
+    assert mb.encoder.conv1.weight.shape == (2, 16, 24) and mb.encoder.conv1.comp.shape == (6, 2)
+    g = load_golden("small_basis")
+    mb2 = pkg.DrugDiseaseModel(g["num_nodes"], g["num_relations"], g["embedding_dim"], g["hidden_dim"],
+                               num_bases=g["num_bases"])
+    mb2.load_state_dict(g["state_dict"], strict=True)
+
+
+@pytest.mark.parametrize("bases", [None, 4])
+def test_seeded_init_draws_the_reference_stream(lib_built, bases):
+    """Same seed => same parameters as the restated reference constructor (PyG glorot for the conv
+    layers, xavier_uniform_ for both embedding tables, in the reference's construction order)."""
+    torch.manual_seed(123)
+    a = lib_built.DrugDiseaseModel(300, 5, 32, 48, num_bases=bases)
+    torch.manual_seed(123)
+    b = O.ModelRef(300, 5, 32, 48, num_bases=bases)
+    for (k, p), (k2, q) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert k == k2 and torch.equal(p, q), k
+
+
+def test_cpu_tensors_fail_loudly(lib_built):
+    pkg = lib_built
+    m = pkg.DrugDiseaseModel(10, 2, 8, 8)
+    ei = torch.tensor([[0, 1], [1, 2]])
+    et = torch.tensor([0, 1])
+    idx = torch.tensor([0])
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(ei, et, idx, idx, idx)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m.decoder(torch.randn(1, 8), torch.randn(1, 8), idx)
+    with pytest.raises(RuntimeError):
+        pkg.RGCNConv(8, 8, 2)(torch.randn(3, 8), ei, et)
+
+
+def test_dropin_module_file_exports_the_reference_names(lib_built):
+    import importlib
+    mod = importlib.import_module("src.models.rgcn")
+    for n in ("DrugDiseaseRGCN", "LinkPredictor", "DrugDiseaseModel"):
+        assert getattr(mod, n) is getattr(lib_built, n)
+
+
+def test_synthetic_primekg_subgraph_shape():
+    from primekg_rgcn_linkprediction_b200 import synth
+    kg = synth.primekg_subgraph()
+    assert kg.num_nodes == 30_926 and kg.num_relations == 3 and kg.num_edges == 849_456
+    ei, et = kg.edge_index, kg.edge_type
+    assert ei.dtype == torch.int64 and et.dtype == torch.int64
+    # consecutive (a->b),(b->a) columns of the same type: reference src/preprocess.py:228-234
+    assert torch.equal(ei[0, 0::2], ei[1, 1::2]) and torch.equal(ei[1, 0::2], ei[0, 1::2])
+    assert torch.equal(et[0::2], et[1::2])
+    blocks = synth.CFG1_BLOCKS
+    for r, (a, b, _) in enumerate(synth.CFG1_RELS):
+        s, d = ei[0, 0::2][et[0::2] == r], ei[1, 0::2][et[0::2] == r]
+        assert int(s.min()) >= blocks[a][0] and int(s.max()) < blocks[a][1]
+        assert int(d.min()) >= blocks[b][0] and int(d.max()) < blocks[b][1]
+    again = synth.primekg_subgraph()
+    assert torch.equal(again.edge_index, ei)                         # seeded => reproducible
+    deg = torch.bincount(ei[1], minlength=kg.num_nodes)
+    assert int(deg.max()) > 2000 and float(deg.float().median()) < 30    # hubs + a long tail
+    h, t, rl, y = synth.link_batch(kg, 1024)
+    assert h.shape == t.shape == rl.shape == y.shape == (2048,) and int(y.sum()) == 1024
+
+
+def test_synthetic_full_kg_shape():
+    from primekg_rgcn_linkprediction_b200 import synth
+    kg = synth.primekg_full(num_directed_edges=200_000)
+    assert kg.num_nodes == 129_375 and kg.num_relations == 30 and kg.num_edges == 200_000
+    assert int(kg.edge_type.max()) == 29 and int(kg.edge_index.max()) < 129_375
