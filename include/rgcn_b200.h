@@ -144,6 +144,33 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Relational transform on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM, weight tiles by
+ * TMA).  Replaces the R+1 matmuls `h_r @ W_r`, `x @ root` per layer of RGCNConv's loop path
+ * (src/models/rgcn.py:123, :128) and their autograd transposes (src/train.py:306), concatenated
+ * along K:  A = [A1 | A2] = [H | X]  ([n_rows, K1 + K2]),  W = [W1 ; W2] = [weight.view(R*d_in, d_out) ; root].
+ *   fwd   : out = A @ W + bias (, ReLU)                                   [n_rows, d_out]
+ *   dgrad : gA  = (gO * [relu_out > 0]) @ W^T                             [n_rows, K1 + K2]
+ *   wgrad : [gW1 ; gW2] = A^T @ (gO * [relu_out > 0]),  gbias = column sums of the masked gO
+ * relu_out (nullable) is the layer's post-ReLU output, used as the ReLU-backward mask.
+ * mode 0 = "fp32": operands split into bf16 hi + lo, three products (error ~1e-5 relative);
+ * mode 1 = "bf16": operands rounded to bf16, one product.  fp32 accumulation in both.
+ * Everything is deterministic (fixed split-K reduction order).  K1, K2, d_out multiples of 4.
+ * ------------------------------------------------------------------------------------------ */
+size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K1, int32_t K2, int32_t d_out);
+int rgcn_transform_fwd(const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
+                       const float* W1, const float* W2, const float* bias, int32_t relu,
+                       int64_t n_rows, int32_t d_out, float* out, int64_t ldo, int32_t mode,
+                       void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+int rgcn_transform_dgrad(const float* gO, int64_t ldg, const float* relu_out, int64_t ld_ro, int32_t d_out,
+                         const float* W1, int32_t K1, const float* W2, int32_t K2,
+                         int64_t n_rows, float* gA, int64_t ldga, int32_t mode,
+                         void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+int rgcn_transform_wgrad(const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
+                         const float* gO, int64_t ldg, const float* relu_out, int64_t ld_ro, int32_t d_out,
+                         int64_t n_rows, float* gW1, float* gW2, float* gbias, int32_t mode,
+                         void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * DistMult decoder.  Replaces node_embeddings[head], [tail] (src/models/rgcn.py:325-326) +
  * LinkPredictor.forward (src/models/rgcn.py:207-211) with one gather-and-score kernel:
  *   score[p] = sum_k emb_h[hp, k] * r_p[k] * emb_t[tp, k],   hp = head ? head[p] : p, tp likewise

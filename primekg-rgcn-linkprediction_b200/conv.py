@@ -49,16 +49,15 @@ class _RGCNLayerFn(torch.autograd.Function):
         graph, mode = ctx.graph, ctx.mode
         R, d_in, d_out = W.shape
         gO = gO.contiguous()
-        if ctx.relu:
-            gO = gO * (out > 0)
+        Wf = W.reshape(R * d_in, d_out)
         need_x, need_W, need_root, need_b = ctx.needs_input_grad[:4]
         gx = gW = groot = gb = None
         if need_x:
-            Wcat = torch.cat([W.reshape(R * d_in, d_out), root], 0)
-            gA = dense.transform_dgrad(gO, Wcat, mode)                 # [N, (R+1) * d_in]
+            # ReLU backward is applied inside the loaders (mask = post-ReLU output > 0)
+            gA = dense.transform_dgrad(gO, out, Wf, root, mode)           # [N, (R+1) * d_in]
             gx = ops.aggregate_bwd(graph, gA, d_in, init=gA[:, R * d_in:])
         if need_W or need_root or need_b:
-            gWf, groot, gb = dense.transform_wgrad(H, x, gO, mode)
+            gWf, groot, gb = dense.transform_wgrad(H, x, gO, out, mode)
             gW = gWf.view(R, d_in, d_out)
         return gx, gW, groot, gb, None, None, None
 

@@ -136,3 +136,109 @@ def distmult_bwd(emb_h, emb_t, head, tail, rel, rel_table, rel_rows, g_score, ne
                                      _ptr(g_h), g_h.stride(0), _ptr(g_t), g_t.stride(0), _ptr(g_tab), _ptr(g_rows),
                                      _stream(dev)), "rgcn_distmult_bwd")
     return g_h, (None if shared else g_t), g_tab, g_rows
+
+
+# ---- relational transform on the tensor cores -------------------------------------------------------
+_WS = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Per-device scratch reused by every transform call (all calls are ordered on one stream)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def _mode_id(mode: str) -> int:
+    if mode == "fp32":
+        return 0
+    if mode == "bf16":
+        return 1
+    raise ValueError(f"mode must be 'fp32' or 'bf16', got {mode!r}")
+
+
+def _w2d(w: torch.Tensor, name: str) -> torch.Tensor:
+    if not w.is_cuda or w.dtype != torch.float32:
+        raise TypeError(f"{name} must be a CUDA float32 tensor")
+    return w.detach().contiguous()
+
+
+def transform_fwd(A1: torch.Tensor, A2: Optional[torch.Tensor], W1: torch.Tensor, W2: Optional[torch.Tensor],
+                  bias: Optional[torch.Tensor], relu: bool, mode: str) -> torch.Tensor:
+    """out = [A1 | A2] @ [W1 ; W2] + bias (, ReLU) — tcgen05 kernel."""
+    lib = _lib.load()
+    A1 = _f32c(A1, "A1")
+    n, K1 = A1.shape
+    K2 = 0
+    if A2 is not None:
+        A2 = _f32c(A2, "A2")
+        K2 = A2.size(1)
+        W2 = _w2d(W2, "W2")
+    W1 = _w2d(W1, "W1")
+    d_out = W1.size(-1)
+    if W1.numel() != K1 * d_out or (K2 and W2.numel() != K2 * d_out):
+        raise ValueError("weight shapes do not match the operands")
+    if bias is not None:
+        bias = bias.detach().contiguous()
+    out = torch.empty(n, d_out, dtype=torch.float32, device=A1.device)
+    nb = lib.rgcn_transform_workspace_bytes(n, K1, K2, d_out)
+    ws = _workspace(A1.device, nb)
+    _lib.check(lib.rgcn_transform_fwd(_ptr(A1), A1.stride(0), K1, _ptr(A2), 0 if A2 is None else A2.stride(0), K2,
+                                      _ptr(W1), _ptr(W2), _ptr(bias), int(relu), n, d_out, _ptr(out), out.stride(0),
+                                      _mode_id(mode), _ptr(ws), ws.numel(), _stream(A1.device)), "rgcn_transform_fwd")
+    return out
+
+
+def transform_dgrad(gO: torch.Tensor, relu_out: Optional[torch.Tensor], W1: torch.Tensor, W2: Optional[torch.Tensor],
+                    mode: str) -> torch.Tensor:
+    """gA = (gO * [relu_out > 0]) @ [W1 ; W2]^T  -> [n, K1 + K2]."""
+    lib = _lib.load()
+    gO = _f32c(gO, "gO")
+    n, d_out = gO.shape
+    W1 = _w2d(W1, "W1")
+    K1 = W1.numel() // d_out
+    K2 = 0
+    if W2 is not None:
+        W2 = _w2d(W2, "W2")
+        K2 = W2.numel() // d_out
+    if relu_out is not None:
+        relu_out = _f32c(relu_out, "relu_out")
+    gA = torch.empty(n, K1 + K2, dtype=torch.float32, device=gO.device)
+    nb = lib.rgcn_transform_workspace_bytes(n, K1, K2, d_out)
+    ws = _workspace(gO.device, nb)
+    _lib.check(lib.rgcn_transform_dgrad(_ptr(gO), gO.stride(0), _ptr(relu_out),
+                                        0 if relu_out is None else relu_out.stride(0), d_out, _ptr(W1), K1, _ptr(W2), K2,
+                                        n, _ptr(gA), gA.stride(0), _mode_id(mode), _ptr(ws), ws.numel(),
+                                        _stream(gO.device)), "rgcn_transform_dgrad")
+    return gA
+
+
+def transform_wgrad(A1: torch.Tensor, A2: Optional[torch.Tensor], gO: torch.Tensor, relu_out: Optional[torch.Tensor],
+                    mode: str):
+    """(gW1 [K1, d_out], gW2 [K2, d_out] | None, gbias [d_out]) = [A1 | A2]^T @ masked gO, column sums."""
+    lib = _lib.load()
+    A1 = _f32c(A1, "A1")
+    gO = _f32c(gO, "gO")
+    n, K1 = A1.shape
+    d_out = gO.size(1)
+    K2 = 0
+    if A2 is not None:
+        A2 = _f32c(A2, "A2")
+        K2 = A2.size(1)
+    if relu_out is not None:
+        relu_out = _f32c(relu_out, "relu_out")
+    dev = gO.device
+    gW1 = torch.empty(K1, d_out, dtype=torch.float32, device=dev)
+    gW2 = torch.empty(K2, d_out, dtype=torch.float32, device=dev) if K2 else None
+    gb = torch.empty(d_out, dtype=torch.float32, device=dev)
+    nb = lib.rgcn_transform_workspace_bytes(n, K1, K2, d_out)
+    ws = _workspace(dev, nb)
+    _lib.check(lib.rgcn_transform_wgrad(_ptr(A1), A1.stride(0), K1, _ptr(A2), 0 if A2 is None else A2.stride(0), K2,
+                                        _ptr(gO), gO.stride(0), _ptr(relu_out),
+                                        0 if relu_out is None else relu_out.stride(0), d_out, n, _ptr(gW1), _ptr(gW2),
+                                        _ptr(gb), _mode_id(mode), _ptr(ws), ws.numel(), _stream(dev)),
+               "rgcn_transform_wgrad")
+    return gW1, gW2, gb

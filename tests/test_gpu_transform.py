@@ -1,0 +1,89 @@
+"""GPU tests of the tcgen05 relational-transform kernels against fp64 torch matmuls.
+
+Tolerances: mode "fp32" (bf16 hi/lo split, 3 products) — 1e-4 of the output scale, comfortably inside
+BASELINE.json's rtol 1e-4; mode "bf16" — 2e-2."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+SHAPES = [  # (rows, K1, K2, d_out)
+    (300, 48, 16, 32),          # golden-test dims: R=3, d_in=16, d_out=32
+    (140, 96, 16, 24),          # d_out not a multiple of 32
+    (1000, 192, 64, 128),       # cfg1 layer 1
+    (5000, 384, 128, 128),      # cfg1 layer 2
+    (4097, 768, 256, 256),      # cfg2 layer 2, ragged row count
+    (130, 64, 0, 512),          # two N tiles, single source
+]
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _err(got, want):
+    return float((got.double() - want).abs().max() / (want.abs().max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops(lib_built):
+    from primekg_rgcn_linkprediction_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("relu", [False, True])
+def test_transform_fwd(ops, shape, mode, relu):
+    n, K1, K2, N = shape
+    torch.manual_seed(0)
+    A1 = torch.randn(n, K1, device=DEV)
+    A2 = torch.randn(n, K2, device=DEV) if K2 else None
+    W1 = torch.randn(K1, N, device=DEV) / (K1 + K2) ** 0.5
+    W2 = torch.randn(K2, N, device=DEV) / (K1 + K2) ** 0.5 if K2 else None
+    b = torch.randn(N, device=DEV)
+    out = ops.transform_fwd(A1, A2, W1, W2, b, relu, mode)
+    want = A1.double() @ W1.double() + b.double()
+    if K2:
+        want = want + A2.double() @ W2.double()
+    if relu:
+        want = want.clamp(min=0)
+    assert _err(out, want) < TOL[mode], (shape, mode, _err(out, want))
+    out2 = ops.transform_fwd(A1, A2, W1, W2, b, relu, mode)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_transform_dgrad(ops, shape, mode, masked):
+    n, K1, K2, N = shape
+    torch.manual_seed(1)
+    gO = torch.randn(n, N, device=DEV)
+    ro = torch.randn(n, N, device=DEV).clamp(min=0) if masked else None
+    W1 = torch.randn(K1, N, device=DEV) / N ** 0.5
+    W2 = torch.randn(K2, N, device=DEV) / N ** 0.5 if K2 else None
+    gA = ops.transform_dgrad(gO, ro, W1, W2, mode)
+    g = gO.double() * (ro > 0) if masked else gO.double()
+    W = torch.cat([W1, W2], 0) if K2 else W1
+    want = g @ W.double().t()
+    assert gA.shape == (n, K1 + K2)
+    assert _err(gA, want) < TOL[mode], (shape, mode, _err(gA, want))
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(30926, 768, 256, 256)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_transform_wgrad(ops, shape, mode, masked):
+    n, K1, K2, N = shape
+    torch.manual_seed(2)
+    A1 = torch.randn(n, K1, device=DEV)
+    A2 = torch.randn(n, K2, device=DEV) if K2 else None
+    gO = torch.randn(n, N, device=DEV)
+    ro = torch.randn(n, N, device=DEV).clamp(min=0) if masked else None
+    gW1, gW2, gb = ops.transform_wgrad(A1, A2, gO, ro, mode)
+    g = gO.double() * (ro > 0) if masked else gO.double()
+    assert _err(gW1, A1.double().t() @ g) < TOL[mode], (shape, mode, "gW1", _err(gW1, A1.double().t() @ g))
+    if K2:
+        assert _err(gW2, A2.double().t() @ g) < TOL[mode], (shape, mode, "gW2")
+    assert _err(gb, g.sum(0)) < 1e-5, (shape, mode, "gbias", _err(gb, g.sum(0)))
+    again = ops.transform_wgrad(A1, A2, gO, ro, mode)
+    assert torch.equal(gW1, again[0]) and torch.equal(gb, again[2])          # deterministic split-K
