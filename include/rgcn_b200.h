@@ -177,7 +177,8 @@ int rgcn_transform_wgrad(const float* A1, int64_t lda1, int32_t K1, const float*
  * (head == tail == NULL is the stand-alone LinkPredictor.forward on already gathered rows;
  *  emb_h == emb_t == encoder output with index arrays is the fused DrugDiseaseModel.forward).
  * r_p = rel_rows[p, :] when rel_rows != NULL (rows already gathered and dropped-out by the
- * caller), else rel_table[rel[p], :].
+ * caller), else rel_table[rel[p], :]; either is multiplied element-wise by rel_scale[p, :] when
+ * rel_scale != NULL (the dropout mask / (1 - p) of src/models/rgcn.py:208, drawn by the caller).
  * Backward: g_h[hp] += g[p] * r_p * t_p ; g_t[tp] += g[p] * h_p * r_p ;
  *           g_rel_rows[p] = g[p] * h_p * t_p  and/or  g_rel_table[rel[p]] += the same.
  * With an index array the target rows may repeat: the buffer must be zero-filled by the caller
@@ -185,12 +186,12 @@ int rgcn_transform_wgrad(const float* A1, int64_t lda1, int32_t K1, const float*
  * ------------------------------------------------------------------------------------------ */
 int rgcn_distmult_fwd(const float* emb_h, int64_t ld_h, const float* emb_t, int64_t ld_t,
                       const int64_t* head, const int64_t* tail, const int64_t* rel,
-                      const float* rel_table, const float* rel_rows,
+                      const float* rel_table, const float* rel_rows, const float* rel_scale,
                       int64_t n_pairs, int32_t d, float* score, rgcn_stream_t stream);
 int rgcn_distmult_bwd(const float* emb_h, int64_t ld_h, const float* emb_t, int64_t ld_t,
                       const int64_t* head, const int64_t* tail, const int64_t* rel,
-                      const float* rel_table, const float* rel_rows, const float* g_score,
-                      int64_t n_pairs, int32_t d, float* g_h, int64_t ld_gh, float* g_t, int64_t ld_gt,
+                      const float* rel_table, const float* rel_rows, const float* rel_scale,
+                      const float* g_score, int64_t n_pairs, int32_t d, float* g_h, int64_t ld_gh, float* g_t, int64_t ld_gt,
                       float* g_rel_table, float* g_rel_rows, rgcn_stream_t stream);
 /* flag[0] = 1 when any head/tail is outside [0, n_nodes) or any rel outside [0, n_rel). */
 int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,

@@ -45,8 +45,8 @@ PROTOTYPES = {
     "rgcn_transform_fwd": (C.c_int, [p, i64, i32, p, i64, i32, p, p, p, i32, i64, i32, p, i64, i32, p, sz, p]),
     "rgcn_transform_dgrad": (C.c_int, [p, i64, p, i64, i32, p, i32, p, i32, i64, p, i64, i32, p, sz, p]),
     "rgcn_transform_wgrad": (C.c_int, [p, i64, i32, p, i64, i32, p, i64, p, i64, i32, i64, p, p, p, i32, p, sz, p]),
-    "rgcn_distmult_fwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, i64, i32, p, p]),
-    "rgcn_distmult_bwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, i64, i32, p, i64, p, i64, p, p, p]),
+    "rgcn_distmult_fwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, i64, i32, p, p]),
+    "rgcn_distmult_bwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, p, i64, i32, p, i64, p, i64, p, p, p]),
     "rgcn_check_pairs": (C.c_int, [p, p, p, i64, i64, i32, p, p]),
 }
 

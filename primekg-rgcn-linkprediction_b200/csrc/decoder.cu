@@ -11,7 +11,8 @@ __global__ void __launch_bounds__(256) distmult_fwd_kernel(const float* __restri
                                                            const int64_t* __restrict__ tail,
                                                            const int64_t* __restrict__ rel,
                                                            const float* __restrict__ rel_table,
-                                                           const float* __restrict__ rel_rows, int64_t n_pairs,
+                                                           const float* __restrict__ rel_rows,
+                                                           const float* __restrict__ rel_scale, int64_t n_pairs,
                                                            int32_t d, float* __restrict__ score) {
   const int lane = threadIdx.x & 31;
   const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -21,7 +22,12 @@ __global__ void __launch_bounds__(256) distmult_fwd_kernel(const float* __restri
   const float* r = rel_rows ? rel_rows + p * d : rel_table + rel[p] * d;
   float s = 0.f;
   for (int vi = lane; vi < (d >> 2); vi += 32) {
-    const float4 a = ldg4(h + vi * 4), b = ldg4(r + vi * 4), c = ldg4(t + vi * 4);
+    const float4 a = ldg4(h + vi * 4), c = ldg4(t + vi * 4);
+    float4 b = ldg4(r + vi * 4);
+    if (rel_scale) {   // dropout on the relation row: mask / (1 - p), drawn by the caller
+      const float4 m = ldg4(rel_scale + p * d + vi * 4);
+      b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w;
+    }
     // (h * r) * t, summed in element order inside the lane like torch.sum's pairwise tree is not
     // reproduced bit for bit; the tolerance of the parity tests covers the reduction order
     s += a.x * b.x * c.x;
@@ -40,6 +46,7 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const float* __restri
                                                            const int64_t* __restrict__ rel,
                                                            const float* __restrict__ rel_table,
                                                            const float* __restrict__ rel_rows,
+                                                           const float* __restrict__ rel_scale,
                                                            const float* __restrict__ g_score, int64_t n_pairs,
                                                            int32_t d, float* __restrict__ g_h, int64_t ld_gh,
                                                            float* __restrict__ g_t, int64_t ld_gt,
@@ -54,10 +61,16 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const float* __restri
   const float* r = rel_rows ? rel_rows + p * d : rel_table + rel[p] * d;
   const float g = g_score[p];
   for (int vi = lane; vi < (d >> 2); vi += 32) {
-    const float4 a = ldg4(h + vi * 4), b = ldg4(r + vi * 4), c = ldg4(t + vi * 4);
+    const float4 a = ldg4(h + vi * 4), c = ldg4(t + vi * 4);
+    float4 b = ldg4(r + vi * 4);
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (rel_scale) {
+      m = ldg4(rel_scale + p * d + vi * 4);
+      b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w;
+    }
     const float4 gh = make_float4(g * b.x * c.x, g * b.y * c.y, g * b.z * c.z, g * b.w * c.w);
     const float4 gt = make_float4(g * a.x * b.x, g * a.y * b.y, g * a.z * b.z, g * a.w * b.w);
-    const float4 gr = make_float4(g * a.x * c.x, g * a.y * c.y, g * a.z * c.z, g * a.w * c.w);
+    const float4 gr = make_float4(g * a.x * c.x * m.x, g * a.y * c.y * m.y, g * a.z * c.z * m.z, g * a.w * c.w * m.w);
     // gathered rows may repeat => fp32 atomics; identity rows are written exactly once => plain stores
     if (head) atomicAdd(reinterpret_cast<float4*>(g_h + hi * ld_gh + vi * 4), gh);
     else *reinterpret_cast<float4*>(g_h + hi * ld_gh + vi * 4) = gh;
@@ -91,34 +104,37 @@ static int check_dm(const float* emb_h, int64_t ld_h, const float* emb_t, int64_
   RGCN_CHECK_ARG((((uintptr_t)rel_rows | (uintptr_t)rel_table) & 15) == 0, "distmult: relation rows must be 16-byte aligned");
   return RGCN_OK;
 }
+#define CHECK_SCALE(s) RGCN_CHECK_ARG((((uintptr_t)(s)) & 15) == 0, "distmult: rel_scale must be 16-byte aligned")
 
 extern "C" int rgcn_distmult_fwd(const float* emb_h, int64_t ld_h, const float* emb_t, int64_t ld_t,
                                  const int64_t* head, const int64_t* tail, const int64_t* rel,
-                                 const float* rel_table, const float* rel_rows, int64_t n_pairs, int32_t d,
-                                 float* score, rgcn_stream_t stream) {
+                                 const float* rel_table, const float* rel_rows, const float* rel_scale,
+                                 int64_t n_pairs, int32_t d, float* score, rgcn_stream_t stream) {
   int rc = check_dm(emb_h, ld_h, emb_t, ld_t, rel, rel_table, rel_rows, n_pairs, d);
   if (rc) return rc;
   if (n_pairs == 0) return RGCN_OK;
+  CHECK_SCALE(rel_scale);
   RGCN_CHECK_ARG(score, "distmult_fwd: null output");
   distmult_fwd_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      emb_h, ld_h, emb_t, ld_t, head, tail, rel, rel_table, rel_rows, n_pairs, d, score);
+      emb_h, ld_h, emb_t, ld_t, head, tail, rel, rel_table, rel_rows, rel_scale, n_pairs, d, score);
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
 
 extern "C" int rgcn_distmult_bwd(const float* emb_h, int64_t ld_h, const float* emb_t, int64_t ld_t,
                                  const int64_t* head, const int64_t* tail, const int64_t* rel,
-                                 const float* rel_table, const float* rel_rows, const float* g_score,
-                                 int64_t n_pairs, int32_t d, float* g_h, int64_t ld_gh, float* g_t, int64_t ld_gt,
+                                 const float* rel_table, const float* rel_rows, const float* rel_scale,
+                                 const float* g_score, int64_t n_pairs, int32_t d, float* g_h, int64_t ld_gh, float* g_t, int64_t ld_gt,
                                  float* g_rel_table, float* g_rel_rows, rgcn_stream_t stream) {
   int rc = check_dm(emb_h, ld_h, emb_t, ld_t, rel, rel_table, rel_rows, n_pairs, d);
   if (rc) return rc;
   if (n_pairs == 0) return RGCN_OK;
   RGCN_CHECK_ARG(g_score && g_h && g_t && ld_gh % 4 == 0 && ld_gt % 4 == 0 &&
                  (((uintptr_t)g_h | (uintptr_t)g_t) & 15) == 0, "distmult_bwd: bad gradient buffers");
+  CHECK_SCALE(rel_scale);
   RGCN_CHECK_ARG(!g_rel_table || rel, "distmult_bwd: g_rel_table needs rel");
   distmult_bwd_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      emb_h, ld_h, emb_t, ld_t, head, tail, rel, rel_table, rel_rows, g_score, n_pairs, d, g_h, ld_gh, g_t, ld_gt,
+      emb_h, ld_h, emb_t, ld_t, head, tail, rel, rel_table, rel_rows, rel_scale, g_score, n_pairs, d, g_h, ld_gh, g_t, ld_gt,
       g_rel_table, g_rel_rows);
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;

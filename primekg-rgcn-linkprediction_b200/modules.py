@@ -80,32 +80,32 @@ class _DistMultGather(torch.autograd.Function):
     """score[p] = <emb[head[p]], r_p, emb[tail[p]]> with the row gathers fused into the kernel."""
 
     @staticmethod
-    def forward(ctx, emb, head, tail, rel, rel_table, rel_rows):
-        ctx.save_for_backward(emb, head, tail, rel, rel_table, rel_rows)
-        return ops.distmult_fwd(emb, emb, head, tail, rel, rel_table, rel_rows)
+    def forward(ctx, emb, head, tail, rel, rel_table, rel_rows, rel_scale):
+        ctx.save_for_backward(emb, head, tail, rel, rel_table, rel_rows, rel_scale)
+        return ops.distmult_fwd(emb, emb, head, tail, rel, rel_table, rel_rows, rel_scale)
 
     @staticmethod
     def backward(ctx, g):
-        emb, head, tail, rel, rel_table, rel_rows = ctx.saved_tensors
+        emb, head, tail, rel, rel_table, rel_rows, rel_scale = ctx.saved_tensors
         g_emb, _, g_tab, g_rows = ops.distmult_bwd(emb, emb, head, tail, rel, rel_table, rel_rows, g,
-                                                   ctx.needs_input_grad[4])
-        return (g_emb if ctx.needs_input_grad[0] else None), None, None, None, g_tab, g_rows
+                                                   ctx.needs_input_grad[4], rel_scale)
+        return (g_emb if ctx.needs_input_grad[0] else None), None, None, None, g_tab, g_rows, None
 
 
 class _DistMultRows(torch.autograd.Function):
     """score[p] = <head_emb[p], r_p, tail_emb[p]> on rows the caller already gathered."""
 
     @staticmethod
-    def forward(ctx, head_emb, tail_emb, rel, rel_table, rel_rows):
-        ctx.save_for_backward(head_emb, tail_emb, rel, rel_table, rel_rows)
-        return ops.distmult_fwd(head_emb, tail_emb, None, None, rel, rel_table, rel_rows)
+    def forward(ctx, head_emb, tail_emb, rel, rel_table, rel_rows, rel_scale):
+        ctx.save_for_backward(head_emb, tail_emb, rel, rel_table, rel_rows, rel_scale)
+        return ops.distmult_fwd(head_emb, tail_emb, None, None, rel, rel_table, rel_rows, rel_scale)
 
     @staticmethod
     def backward(ctx, g):
-        head_emb, tail_emb, rel, rel_table, rel_rows = ctx.saved_tensors
+        head_emb, tail_emb, rel, rel_table, rel_rows, rel_scale = ctx.saved_tensors
         g_h, g_t, g_tab, g_rows = ops.distmult_bwd(head_emb, tail_emb, None, None, rel, rel_table, rel_rows, g,
-                                                   ctx.needs_input_grad[3])
-        return g_h, g_t, None, g_tab, g_rows
+                                                   ctx.needs_input_grad[3], rel_scale)
+        return g_h, g_t, None, g_tab, g_rows, None
 
 
 class LinkPredictor(nn.Module):
@@ -123,24 +123,30 @@ class LinkPredictor(nn.Module):
         nn.init.xavier_uniform_(self.relation_embeddings.weight)
 
     def _relation_operand(self, relation_types):
-        """(rel_table, rel_rows): dropout active => rows gathered + dropped by torch's own RNG
-        (reference :207-208), otherwise the kernel reads the table directly."""
-        if self.training and self.dropout.p > 0:
-            return None, self.dropout(self.relation_embeddings(relation_types))
-        return self.relation_embeddings.weight, None
+        """(rel_table, rel_scale).  The kernel gathers relation rows from the table itself; when dropout is
+        active (reference :207-208) the per-pair mask / (1 - p) is drawn from torch's generator, as
+        nn.Dropout does, and applied inside the kernel."""
+        table = self.relation_embeddings.weight
+        p = self.dropout.p
+        if self.training and p > 0:
+            if p >= 1:
+                return table, torch.zeros(relation_types.numel(), table.size(1), device=table.device)
+            scale = torch.empty(relation_types.numel(), table.size(1), device=table.device).bernoulli_(1 - p)
+            return table, scale.div_(1 - p)
+        return table, None
 
     def forward(self, head_embeddings: torch.Tensor, tail_embeddings: torch.Tensor,
                 relation_types: torch.Tensor) -> torch.Tensor:
         _need_cuda(head_embeddings, "LinkPredictor.forward")
-        table, rows = self._relation_operand(relation_types)
-        return _DistMultRows.apply(head_embeddings, tail_embeddings, relation_types, table, rows)
+        table, scale = self._relation_operand(relation_types)
+        return _DistMultRows.apply(head_embeddings, tail_embeddings, relation_types, table, None, scale)
 
     def score_pairs(self, node_embeddings: torch.Tensor, head_indices: torch.Tensor, tail_indices: torch.Tensor,
                     relation_types: torch.Tensor) -> torch.Tensor:
         """Fused form of ``forward(emb[head], emb[tail], rel)`` (reference :325-329)."""
         _need_cuda(node_embeddings, "LinkPredictor.score_pairs")
-        table, rows = self._relation_operand(relation_types)
-        return _DistMultGather.apply(node_embeddings, head_indices, tail_indices, relation_types, table, rows)
+        table, scale = self._relation_operand(relation_types)
+        return _DistMultGather.apply(node_embeddings, head_indices, tail_indices, relation_types, table, None, scale)
 
     def score_all_tails(self, head_embeddings: torch.Tensor, relation_types: torch.Tensor,
                         all_tail_embeddings: torch.Tensor) -> torch.Tensor:

@@ -88,7 +88,7 @@ def _rows(t, name):
 
 
 def distmult_fwd(emb_h: torch.Tensor, emb_t: torch.Tensor, head, tail, rel, rel_table: Optional[torch.Tensor],
-                 rel_rows: Optional[torch.Tensor]) -> torch.Tensor:
+                 rel_rows: Optional[torch.Tensor], rel_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """score[p] = sum_k emb_h[hp, k] * r_p[k] * emb_t[tp, k]; hp = head[p] (or p when head is None)."""
     lib = _lib.load()
     emb_h, emb_t = _f32c(emb_h, "head embeddings"), _f32c(emb_t, "tail embeddings")
@@ -100,14 +100,17 @@ def distmult_fwd(emb_h: torch.Tensor, emb_t: torch.Tensor, head, tail, rel, rel_
     if emb_t.size(1) != d:
         raise ValueError("head and tail embeddings differ in width")
     rel_rows, rel_table = _rows(rel_rows, "rel_rows"), _rows(rel_table, "rel_table")
+    rel_scale = _rows(rel_scale, "rel_scale")
     score = torch.empty(n, dtype=torch.float32, device=emb_h.device)
     _lib.check(lib.rgcn_distmult_fwd(_ptr(emb_h), emb_h.stride(0), _ptr(emb_t), emb_t.stride(0), _ptr(head),
-                                     _ptr(tail), _ptr(rel), _ptr(rel_table), _ptr(rel_rows), n, d, _ptr(score),
+                                     _ptr(tail), _ptr(rel), _ptr(rel_table), _ptr(rel_rows), _ptr(rel_scale), n, d,
+                                     _ptr(score),
                                      _stream(emb_h.device)), "rgcn_distmult_fwd")
     return score
 
 
-def distmult_bwd(emb_h, emb_t, head, tail, rel, rel_table, rel_rows, g_score, need_rel_table_grad: bool):
+def distmult_bwd(emb_h, emb_t, head, tail, rel, rel_table, rel_rows, g_score, need_rel_table_grad: bool,
+                 rel_scale=None):
     """Returns (g_h, g_t, g_rel_table | None, g_rel_rows | None).  With index arrays and emb_h is emb_t the
     two row gradients are accumulated into ONE dense [N, d] buffer (returned as g_h, g_t = None)."""
     lib = _lib.load()
@@ -131,8 +134,10 @@ def distmult_bwd(emb_h, emb_t, head, tail, rel, rel_table, rel_rows, g_score, ne
     rel_rows, rel_table = _rows(rel_rows, "rel_rows"), _rows(rel_table, "rel_table")
     g_rows = torch.empty(n, d, dtype=torch.float32, device=dev) if rel_rows is not None else None
     g_tab = torch.zeros_like(rel_table) if (rel_rows is None and need_rel_table_grad) else None
+    rel_scale = _rows(rel_scale, "rel_scale")
     _lib.check(lib.rgcn_distmult_bwd(_ptr(emb_h), emb_h.stride(0), _ptr(emb_t), emb_t.stride(0), _ptr(head),
-                                     _ptr(tail), _ptr(rel), _ptr(rel_table), _ptr(rel_rows), _ptr(g_score), n, d,
+                                     _ptr(tail), _ptr(rel), _ptr(rel_table), _ptr(rel_rows), _ptr(rel_scale),
+                                     _ptr(g_score), n, d,
                                      _ptr(g_h), g_h.stride(0), _ptr(g_t), g_t.stride(0), _ptr(g_tab), _ptr(g_rows),
                                      _stream(dev)), "rgcn_distmult_bwd")
     return g_h, (None if shared else g_t), g_tab, g_rows
