@@ -77,8 +77,32 @@ struct KStage {
   static constexpr int B_HI = (SPLIT ? 2 : 1) * A_BYTES, B_LO = B_HI + B_BYTES;
 };
 
+constexpr int K_LOADERS = 256;   // 8 loader / epilogue warps
+
+// 4 fp32 -> 4 bf16 hi (+ 4 bf16 lo) packed into 8-byte words
 template <bool SPLIT>
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ void split_store4(const float4& v, uint8_t* hi_ptr, uint8_t* lo_ptr) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+  __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+  uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(hi_ptr) = pk;
+  if (SPLIT) {
+    a = __halves2bfloat162(l0, l1); b = __halves2bfloat162(l2, l3);
+    pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(lo_ptr) = pk;
+  }
+}
+__device__ __forceinline__ void relu_mask4(float4& v, const float4& m) {
+  if (!(m.x > 0.f)) v.x = 0.f;
+  if (!(m.y > 0.f)) v.y = 0.f;
+  if (!(m.z > 0.f)) v.z = 0.f;
+  if (!(m.w > 0.f)) v.w = 0.f;
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(K_LOADERS + 64, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmKParams p) {
   using S = KStage<SPLIT>;
@@ -95,13 +119,13 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
-      mbar_init(&full_bar[s], 128 + 1);     // 128 loader threads + the TMA thread's expect_tx arrive
-      mbar_init(&empty_bar[s], 1);          // one tcgen05.commit
+      mbar_init(&full_bar[s], K_LOADERS + 1);   // loader threads + the TMA thread's expect_tx arrive
+      mbar_init(&empty_bar[s], 1);              // one tcgen05.commit
     }
     mbar_init(&accum_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_b_hi);
     if (SPLIT) tma_prefetch_desc(&tm_b_lo);
   }
@@ -111,65 +135,56 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_con
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp < 4) {
-    // ===================== operand-A loaders =====================
+  if (warp < 8) {
+    // ===================== operand-A loaders (register double buffering: K block kb+1 is in flight
+    // while kb is converted and stored) =====================
     const int c = threadIdx.x & 15;          // float4 index inside the 64-wide K block
-    const int rsub = threadIdx.x >> 4;       // 0..7
+    const int rsub = threadIdx.x >> 4;       // 0..15
+    float4 cur[8], nxt[8], mcur[8], mnxt[8];
+    bool cur_masked = false, nxt_masked = false;
+    auto issue = [&](int kb, float4 (&v)[8], float4 (&mk)[8], bool& masked) {
+      const int k = kb * BK + c * 4;
+      const float* src = nullptr;
+      const float* msk = nullptr;
+      int64_t ld = 0;
+      if (k < p.K1) { src = p.a1 + k; ld = p.lda1; if (p.mask) msk = p.mask + k; }
+      else if (k < p.K1 + p.K2) { src = p.a2 + (k - p.K1); ld = p.lda2; }
+      masked = msk != nullptr;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int64_t row = m0 + it * 16 + rsub;
+        const bool ok = src && row < p.M;
+        v[it] = ok ? ldg4(src + row * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (msk) mk[it] = ok ? ldg4(msk + row * p.ldmask) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    issue(0, cur, mcur, cur_masked);
     for (int kb = 0; kb < p.num_kb; ++kb) {
       const int s = kb % S::STAGES;
       const uint32_t ph = (kb / S::STAGES) & 1;
-      const int k = kb * BK + c * 4;
-      const float* src = nullptr;
-      int64_t ld = 0;
-      const float* msk = nullptr;
-      if (k < p.K1) { src = p.a1 + k; ld = p.lda1; if (p.mask) msk = p.mask + k; }
-      else if (k < p.K1 + p.K2) { src = p.a2 + (k - p.K1); ld = p.lda2; }
-      float4 v[16];
-#pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int64_t row = m0 + it * 8 + rsub;
-        v[it] = (src && row < p.M) ? ldg4(src + row * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (msk) {
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-          const int64_t row = m0 + it * 8 + rsub;
-          if (row < p.M) {
-            const float4 mk = ldg4(msk + row * p.ldmask);
-            if (!(mk.x > 0.f)) v[it].x = 0.f;
-            if (!(mk.y > 0.f)) v[it].y = 0.f;
-            if (!(mk.z > 0.f)) v[it].z = 0.f;
-            if (!(mk.w > 0.f)) v[it].w = 0.f;
-          }
-        }
-      }
+      if (kb + 1 < p.num_kb) issue(kb + 1, nxt, mnxt, nxt_masked);
       mbar_wait(&empty_bar[s], ph ^ 1);      // slot free (passes immediately on the first round)
       uint8_t* st = smem + (size_t)s * S::BYTES;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const uint32_t r = it * 8 + rsub;
+      for (int it = 0; it < 8; ++it) {
+        const uint32_t r = it * 16 + rsub;
         const uint32_t off = sw128_offset(r, c >> 1) + (c & 1) * 8;
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(v[it].x, h0, l0); split_bf16(v[it].y, h1, l1);
-        split_bf16(v[it].z, h2, l2); split_bf16(v[it].w, h3, l3);
-        __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(st + S::A_HI + off) = pk;
-        if (SPLIT) {
-          a = __halves2bfloat162(l0, l1); b = __halves2bfloat162(l2, l3);
-          pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-          *reinterpret_cast<uint2*>(st + S::A_LO + off) = pk;
-        }
+        if (cur_masked) relu_mask4(cur[it], mcur[it]);
+        split_store4<SPLIT>(cur[it], st + S::A_HI + off, st + S::A_LO + off);
       }
       fence_proxy_async();
       mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) { cur[it] = nxt[it]; mcur[it] = mnxt[it]; }
+      cur_masked = nxt_masked;
     }
-    // ===================== epilogue =====================
+    // ===================== epilogue: warps w and w+4 share TMEM lane quadrant w, alternate 32-column chunks ====
     mbar_wait(&accum_bar, 0);
     fence_after_sync();
-    const int64_t row = m0 + warp * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int cc = 0; cc < p.BN; cc += 32) {
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t row = m0 + q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int cc = half * 32; cc < p.BN; cc += 64) {
       uint32_t r[32];
       tmem_ld_32x32(t_lane + cc, r);
       tmem_ld_wait();
@@ -179,20 +194,20 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_con
         for (int j = 0; j < 32; j += 4) {
           const int n = n0 + cc + j;
           if (n < p.N) {
-            float4 q = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
+            float4 qv = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                    __uint_as_float(r[j + 3]));
             if (p.bias) {
               const float4 b = ldg4(p.bias + n);
-              q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+              qv.x += b.x; qv.y += b.y; qv.z += b.z; qv.w += b.w;
             }
-            if (p.relu) { q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f); }
-            *reinterpret_cast<float4*>(o + j) = q;
+            if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
+            *reinterpret_cast<float4*>(o + j) = qv;
           }
         }
       }
     }
     fence_before_sync();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ===================== TMA producer for the weight tiles =====================
     if (lane == 0) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -311,33 +326,30 @@ __global__ void __launch_bounds__(288, 1) gemm_wgrad_kernel(const WgradParams p)
     const bool b_on = (cb * 4 < p.BN);
     const bool b_valid = b_on && nb < p.N;
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % S::STAGES;
-      const uint32_t ph = (kb / S::STAGES) & 1;
+    float4 va[4], vb[8], vm[8], na[4], nbv[8], nm[8];
+    auto issue = [&](int kb, float4 (&xa)[4], float4 (&xb)[8], float4 (&xm)[8]) {
       const int64_t nd0 = node_beg + (int64_t)kb * WG_BK;
-      float4 va[4], vb[8];
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int64_t nd = nd0 + it * 8 + ra;
-        va[it] = (srca && nd < node_end) ? ldg4(srca + nd * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xa[it] = (srca && nd < node_end) ? ldg4(srca + nd * lda) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int64_t nd = nd0 + it * 4 + rb;
-        vb[it] = (b_valid && nd < node_end) ? ldg4(p.g + nd * p.ldg + nb) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = b_valid && nd < node_end;
+        xb[it] = ok ? ldg4(p.g + nd * p.ldg + nb) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.mask) xm[it] = ok ? ldg4(p.mask + nd * p.ldmask + nb) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (p.mask && b_valid) {
+    };
+    if (num_kb > 0) issue(0, va, vb, vm);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % S::STAGES;
+      const uint32_t ph = (kb / S::STAGES) & 1;
+      if (kb + 1 < num_kb) issue(kb + 1, na, nbv, nm);
+      if (p.mask) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int64_t nd = nd0 + it * 4 + rb;
-          if (nd < node_end) {
-            const float4 mk = ldg4(p.mask + nd * p.ldmask + nb);
-            if (!(mk.x > 0.f)) vb[it].x = 0.f;
-            if (!(mk.y > 0.f)) vb[it].y = 0.f;
-            if (!(mk.z > 0.f)) vb[it].z = 0.f;
-            if (!(mk.w > 0.f)) vb[it].w = 0.f;
-          }
-        }
+        for (int it = 0; it < 8; ++it) relu_mask4(vb[it], vm[it]);
       }
       if (m_tile == 0) {
 #pragma unroll
@@ -349,38 +361,22 @@ __global__ void __launch_bounds__(288, 1) gemm_wgrad_kernel(const WgradParams p)
       for (int it = 0; it < 4; ++it) {
         const uint32_t kr = it * 8 + ra;                       // node row inside the stage
         const uint32_t off = (uint32_t)(ca >> 4) * (WG_BK * 128) + sw128_offset(kr, (ca & 15) >> 1) + (ca & 1) * 8;
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(va[it].x, h0, l0); split_bf16(va[it].y, h1, l1);
-        split_bf16(va[it].z, h2, l2); split_bf16(va[it].w, h3, l3);
-        __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-        uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(st + S::A_HI + off) = pk;
-        if (SPLIT) {
-          a = __halves2bfloat162(l0, l1); b = __halves2bfloat162(l2, l3);
-          pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-          *reinterpret_cast<uint2*>(st + S::A_LO + off) = pk;
-        }
+        split_store4<SPLIT>(va[it], st + S::A_HI + off, st + S::A_LO + off);
       }
       if (b_on) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const uint32_t kr = it * 4 + rb;
           const uint32_t off = (uint32_t)(cb >> 4) * (WG_BK * 128) + sw128_offset(kr, (cb & 15) >> 1) + (cb & 1) * 8;
-          __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-          split_bf16(vb[it].x, h0, l0); split_bf16(vb[it].y, h1, l1);
-          split_bf16(vb[it].z, h2, l2); split_bf16(vb[it].w, h3, l3);
-          __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-          *reinterpret_cast<uint2*>(st + S::B_HI + off) = pk;
-          if (SPLIT) {
-            a = __halves2bfloat162(l0, l1); b = __halves2bfloat162(l2, l3);
-            pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-            *reinterpret_cast<uint2*>(st + S::B_LO + off) = pk;
-          }
+          split_store4<SPLIT>(vb[it], st + S::B_HI + off, st + S::B_LO + off);
         }
       }
       fence_proxy_async();
       mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) va[it] = na[it];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) { vb[it] = nbv[it]; vm[it] = nm[it]; }
     }
     // bias gradient partial: fixed-order sum of the 4 node sub-rows sharing a column group
     if (m_tile == 0) bias_red[rb][cb] = colsum;
@@ -544,19 +540,19 @@ static int launch_kmajor(const GemmKParams& p, const __nv_bfloat16* bhi, const _
     const int smem = KStage<true>::STAGES * KStage<true>::BYTES + 1024;
     rc = set_smem(gemm_kmajor_kernel<true>, smem);
     if (rc) return rc;
-    gemm_kmajor_kernel<true><<<grid, 192, smem, st>>>(mhi, mlo, p);
+    gemm_kmajor_kernel<true><<<grid, K_LOADERS + 64, smem, st>>>(mhi, mlo, p);
   } else {
     const int smem = KStage<false>::STAGES * KStage<false>::BYTES + 1024;
     rc = set_smem(gemm_kmajor_kernel<false>, smem);
     if (rc) return rc;
-    gemm_kmajor_kernel<false><<<grid, 192, smem, st>>>(mhi, mlo, p);
+    gemm_kmajor_kernel<false><<<grid, K_LOADERS + 64, smem, st>>>(mhi, mlo, p);
   }
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
 
 static int wgrad_splits(int64_t nodes, int tiles) {
-  int s = (sm_count() + tiles - 1) / tiles;
+  int s = sm_count() / tiles;                                     // one wave: tiles * splits <= #SMs
   const int64_t max_s = (nodes + 4 * WG_BK - 1) / (4 * WG_BK);      // at least 4 stages of work per split
   if (s > max_s) s = (int)max_s;
   if (s > 64) s = 64;

