@@ -79,19 +79,25 @@ struct KStage {
 
 constexpr int K_LOADERS = 256;   // 8 loader / epilogue warps
 
-// 4 fp32 -> 4 bf16 hi (+ 4 bf16 lo) packed into 8-byte words
+// 4 fp32 -> 4 bf16 hi (+ 4 bf16 lo) packed into 8-byte words.  Packed conversions only
+// (cvt.rn.bf16x2.f32 = F2FP on the ALU pipe); the scalar F2F.BF16.F32 runs on the slow conversion pipe and
+// made the loaders the bottleneck of every GEMM.
 template <bool SPLIT>
 __device__ __forceinline__ void split_store4(const float4& v, uint8_t* hi_ptr, uint8_t* lo_ptr) {
-  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1);
-  split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
-  __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-  uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+  __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&h01);
+  pk.y = *reinterpret_cast<uint32_t*>(&h23);
   *reinterpret_cast<uint2*>(hi_ptr) = pk;
   if (SPLIT) {
-    a = __halves2bfloat162(l0, l1); b = __halves2bfloat162(l2, l3);
-    pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(lo_ptr) = pk;
+    // bf16 -> fp32 is a shift / mask of the bit pattern
+    const float hx = __uint_as_float(pk.x << 16), hy = __uint_as_float(pk.x & 0xffff0000u);
+    const float hz = __uint_as_float(pk.y << 16), hw = __uint_as_float(pk.y & 0xffff0000u);
+    __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - hx, v.y - hy), l23 = __floats2bfloat162_rn(v.z - hz, v.w - hw);
+    uint2 pl;
+    pl.x = *reinterpret_cast<uint32_t*>(&l01);
+    pl.y = *reinterpret_cast<uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(lo_ptr) = pl;
   }
 }
 __device__ __forceinline__ void relu_mask4(float4& v, const float4& m) {
@@ -110,6 +116,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[S::STAGES], empty_bar[S::STAGES], accum_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bias[BNMAX];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tile = blockIdx.x, n_tile = blockIdx.y;
@@ -117,6 +124,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_con
   const int n0 = n_tile * p.BN;
   const uint32_t tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
 
+  if (threadIdx.x < BNMAX) {
+    const int n = n0 + threadIdx.x;
+    s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.BN && n < p.N) ? p.bias[n] : 0.f;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
       mbar_init(&full_bar[s], K_LOADERS + 1);   // loader threads + the TMA thread's expect_tx arrive
@@ -178,35 +189,40 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_b_hi, const __grid_con
       for (int it = 0; it < 8; ++it) { cur[it] = nxt[it]; mcur[it] = mnxt[it]; }
       cur_masked = nxt_masked;
     }
-    // ===================== epilogue: warps w and w+4 share TMEM lane quadrant w, alternate 32-column chunks ====
+    // ===================== epilogue =====================
+    // TMEM -> registers (+ bias, ReLU) -> staging tile in the (now idle) operand smem -> coalesced row stores.
+    // Warps w and w+4 share TMEM lane quadrant w and alternate 32-column chunks.
     mbar_wait(&accum_bar, 0);
     fence_after_sync();
     const int q = warp & 3, half = warp >> 2;
-    const int64_t row = m0 + q * 32 + lane;
+    const int pitch = p.BN + 4;                      // floats; +4 keeps the float4 row stores bank-conflict free
+    float* stile = reinterpret_cast<float*>(smem);
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* srow = stile + (size_t)(q * 32 + lane) * pitch;
     for (int cc = half * 32; cc < p.BN; cc += 64) {
       uint32_t r[32];
       tmem_ld_32x32(t_lane + cc, r);
       tmem_ld_wait();
-      if (row < p.M) {
-        float* o = p.out + row * p.ldo + n0 + cc;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + cc + j;
-          if (n < p.N) {
-            float4 qv = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                    __uint_as_float(r[j + 3]));
-            if (p.bias) {
-              const float4 b = ldg4(p.bias + n);
-              qv.x += b.x; qv.y += b.y; qv.z += b.z; qv.w += b.w;
-            }
-            if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
-            *reinterpret_cast<float4*>(o + j) = qv;
-          }
-        }
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(s_bias + cc + j);
+        float4 qv = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
+                                __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
+        if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
+        *reinterpret_cast<float4*>(srow + cc + j) = qv;
       }
     }
     fence_before_sync();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int ncol4 = min(p.BN, p.N - n0) >> 2;      // valid float4 columns of this tile
+    for (int rl = warp; rl < BM; rl += 8) {
+      const int64_t row = m0 + rl;
+      if (row >= p.M) break;
+      const float* src = stile + (size_t)rl * pitch;
+      float* dst = p.out + row * p.ldo + n0;
+      for (int c4 = lane; c4 < ncol4; c4 += 32)
+        *reinterpret_cast<float4*>(dst + c4 * 4) = *reinterpret_cast<const float4*>(src + c4 * 4);
+    }
   } else if (warp == 8) {
     // ===================== TMA producer for the weight tiles =====================
     if (lane == 0) {
