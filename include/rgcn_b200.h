@@ -120,14 +120,16 @@ typedef struct rgcn_csr {
  * One group of d/4 lanes per destination row, 128-bit loads, serial left-to-right fp32 sum inside
  * a segment (= the order of CPU index_add_), no atomics; segments longer than the hub threshold
  * are split over whole thread blocks and reduced in a fixed order.
- *   out_bf16 != 0 : H is written as bf16 (the "bf16-transform" mode), else fp32.
+ *   out_mode 0: H is fp32 [n_rows, ldh].  out_mode 1: H is one bf16 plane (values rounded to bf16, the
+ *   "bf16-transform" mode).  out_mode 2: two bf16 planes H (hi) and H_lo with hi + lo = value to 2^-17 — the
+ *   TMA-loadable operand format of rgcn_transform_* in the fp32 mode.  ldh counts elements of the output type.
  *   comp != NULL (basis decomposition, comp [R, B] fp32): instead of R blocks the kernel writes the
  *   B basis-mixed blocks  Z[i, b*d:(b+1)*d] = sum_r comp[r, b] * h_r[i]   (H is then [n_rows, B*d]).
  * ------------------------------------------------------------------------------------------ */
 size_t rgcn_aggregate_workspace_bytes(const rgcn_csr_t* g, int32_t d);
 int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d,
                        const float* comp, int32_t B,
-                       void* H, int64_t ldh, int32_t out_bf16,
+                       void* H, void* H_lo, int64_t ldh, int32_t out_mode,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -144,30 +146,39 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Relational transform on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM, weight tiles by
- * TMA).  Replaces the R+1 matmuls `h_r @ W_r`, `x @ root` per layer of RGCNConv's loop path
+ * Relational transform on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM, every operand tile
+ * streamed by TMA).  Replaces the R+1 matmuls `h_r @ W_r`, `x @ root` per layer of RGCNConv's loop path
  * (src/models/rgcn.py:123, :128) and their autograd transposes (src/train.py:306), concatenated
- * along K:  A = [A1 | A2] = [H | X]  ([n_rows, K1 + K2]),  W = [W1 ; W2] = [weight.view(R*d_in, d_out) ; root].
- *   fwd   : out = A @ W + bias (, ReLU)                                   [n_rows, d_out]
- *   dgrad : gA  = (gO * [relu_out > 0]) @ W^T                             [n_rows, K1 + K2]
- *   wgrad : [gW1 ; gW2] = A^T @ (gO * [relu_out > 0]),  gbias = column sums of the masked gO
- * relu_out (nullable) is the layer's post-ReLU output, used as the ReLU-backward mask.
- * mode 0 = "fp32": operands split into bf16 hi + lo, three products (error ~1e-5 relative);
- * mode 1 = "bf16": operands rounded to bf16, one product.  fp32 accumulation in both.
- * Everything is deterministic (fixed split-K reduction order).  K1, K2, d_out multiples of 4.
+ * along K:  A = [H | X]  ([n_rows, K1 + K2]),  W = [W1 ; W2] = [weight.view(R*d_in, d_out) ; root].
+ *
+ * Activations are passed as "bf16 planes": row-major bf16 matrices `hi` (value rounded to bf16) and, in
+ * mode 0, `lo` (value - hi rounded to bf16).  rgcn_aggregate_fwd(out_mode 1|2) writes H planes directly;
+ * rgcn_split_planes converts any fp32 matrix, optionally zeroing elements where relu_mask <= 0 (ReLU
+ * backward) and emitting per-block column sums (the bias gradient; rgcn_split_planes_blocks() rows of
+ * `cols` floats).  Planes: base 16-byte aligned, ld (elements) a multiple of 8.
+ *   fwd   : out = A @ W + bias (, ReLU)                       [n_rows, d_out] fp32
+ *   dgrad : gA  = G @ W^T                                     [n_rows, K1 + K2] fp32
+ *   wgrad : [gW1 ; gW2] = A^T @ G ;  gbias = sum of the n_colsum column-sum partials
+ * mode 0 = "fp32": hi*hi + hi*lo + lo*hi (error ~1e-5 relative); mode 1 = "bf16": hi*hi only.
+ * Everything is deterministic (fixed split-K / partial reduction order).  K1, K2, d_out multiples of 4.
  * ------------------------------------------------------------------------------------------ */
-size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K1, int32_t K2, int32_t d_out);
-int rgcn_transform_fwd(const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
+int64_t rgcn_split_planes_blocks(int64_t rows, int32_t cols);
+int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, int64_t rows,
+                      int32_t cols, void* hi, void* lo, int64_t ldp, float* colsum_partial,
+                      rgcn_stream_t stream);
+size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K, int32_t d_out);
+int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t lda, int32_t K1, int32_t K2,
                        const float* W1, const float* W2, const float* bias, int32_t relu,
                        int64_t n_rows, int32_t d_out, float* out, int64_t ldo, int32_t mode,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
-int rgcn_transform_dgrad(const float* gO, int64_t ldg, const float* relu_out, int64_t ld_ro, int32_t d_out,
+int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out,
                          const float* W1, int32_t K1, const float* W2, int32_t K2,
                          int64_t n_rows, float* gA, int64_t ldga, int32_t mode,
                          void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
-int rgcn_transform_wgrad(const float* A1, int64_t lda1, int32_t K1, const float* A2, int64_t lda2, int32_t K2,
-                         const float* gO, int64_t ldg, const float* relu_out, int64_t ld_ro, int32_t d_out,
-                         int64_t n_rows, float* gW1, float* gW2, float* gbias, int32_t mode,
+int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t lda, int32_t K1, int32_t K2,
+                         const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, int64_t n_rows,
+                         const float* colsum_partial, int32_t n_colsum,
+                         float* gW1, float* gW2, float* gbias, int32_t mode,
                          void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -19,45 +19,62 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import dense, ops
+from . import ops
 from .graph import RelGraph, get_graph
+
+
+MODES = ("fp32", "bf16")
 
 
 def default_mode() -> str:
     m = os.environ.get("PRIMEKG_RGCN_MODE", "fp32").lower()
-    if m not in dense.MODES:
-        raise ValueError(f"PRIMEKG_RGCN_MODE must be one of {dense.MODES}, got {m!r}")
+    if m not in MODES:
+        raise ValueError(f"PRIMEKG_RGCN_MODE must be one of {MODES}, got {m!r}")
     return m
 
 
 class _RGCNLayerFn(torch.autograd.Function):
-    """out = [relu]( H(x) @ Wf + x @ root + bias ),  Wf = W.view(R * d_in, d_out)."""
+    """out = [relu]( H(x) @ Wf + x @ root + bias ),  Wf = W.view(R * d_in, d_out).
+
+    Data flow (all on hand-written sm_100a kernels):
+      forward : aggregate_fwd writes H as bf16 planes into A[:, :R*d_in]; split_planes writes x into A[:, R*d_in:];
+                transform_fwd (tcgen05) = A @ [Wf ; root] + bias (, ReLU).
+      backward: split_planes(gO, relu mask) -> G planes + bias-gradient partials; transform_dgrad -> gA;
+                aggregate_bwd over the transposed CSR -> grad x; transform_wgrad (split-K tcgen05) -> grad W, root, bias.
+    """
 
     @staticmethod
     def forward(ctx, x, W, root, bias, graph: RelGraph, relu: bool, mode: str):
         R, d_in, d_out = W.shape
         x = x.contiguous()
-        H = ops.aggregate_fwd(graph, x, out_bf16=False)
-        out = dense.transform_fwd(H, W.reshape(R * d_in, d_out), x, root, bias, relu, mode)
+        K1, K2 = R * d_in, d_in
+        A = ops.alloc_planes(graph.n_dst, K1 + K2, mode, x.device)
+        ops.aggregate_fwd(graph, x, planes=A)
+        ops.split_planes(x, A, col0=K1)
+        out = ops.transform_fwd(A, K1, K2, W.reshape(K1, d_out), root, bias, relu, mode)
         ctx.graph, ctx.relu, ctx.mode = graph, relu, mode
-        ctx.save_for_backward(x, H, W, root, out if relu else None)
+        ctx.save_for_backward(A[0], A[1], W, root, out if relu else None)
         return out
 
     @staticmethod
     def backward(ctx, gO):
-        x, H, W, root, out = ctx.saved_tensors
+        A_hi, A_lo, W, root, out = ctx.saved_tensors
         graph, mode = ctx.graph, ctx.mode
         R, d_in, d_out = W.shape
+        K1, K2 = R * d_in, d_in
         gO = gO.contiguous()
-        Wf = W.reshape(R * d_in, d_out)
+        Wf = W.reshape(K1, d_out)
         need_x, need_W, need_root, need_b = ctx.needs_input_grad[:4]
+        need_w_any = need_W or need_root or need_b
         gx = gW = groot = gb = None
+        # G = gO * [out > 0] as bf16 planes, formed once for both GEMMs; column sums = bias gradient
+        G = ops.alloc_planes(gO.size(0), d_out, mode, gO.device)
+        colsum = ops.split_planes(gO, G, relu_mask=out, colsum=need_w_any)
         if need_x:
-            # ReLU backward is applied inside the loaders (mask = post-ReLU output > 0)
-            gA = dense.transform_dgrad(gO, out, Wf, root, mode)           # [N, (R+1) * d_in]
-            gx = ops.aggregate_bwd(graph, gA, d_in, init=gA[:, R * d_in:])
-        if need_W or need_root or need_b:
-            gWf, groot, gb = dense.transform_wgrad(H, x, gO, out, mode)
+            gA = ops.transform_dgrad(G, d_out, Wf, root, mode)            # [N, (R+1) * d_in]
+            gx = ops.aggregate_bwd(graph, gA, d_in, init=gA[:, K1:])
+        if need_w_any:
+            gWf, groot, gb = ops.transform_wgrad((A_hi, A_lo), K1, K2, G, d_out, colsum, mode)
             gW = gWf.view(R, d_in, d_out)
         return gx, gW, groot, gb, None, None, None
 

@@ -42,8 +42,9 @@ struct AggParams {
   const float* init;         // nullable (MIX_SUM)
   int64_t ld_init;
   void* O;
+  void* O_lo;                // second bf16 plane (out_mode 2)
   int64_t ldo;
-  int32_t out_bf16;
+  int32_t out_mode;          // 0: fp32, 1: bf16 (hi plane only), 2: bf16 hi + lo planes (hi + lo = value to 2^-17)
   float* partials;           // [n_chunks, d]
 };
 
@@ -108,14 +109,25 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(AggParams p) {
 }
 
 __device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int col, const float4& v) {
-  if (p.out_bf16) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&a);
-    pk.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.O) + row * p.ldo + col) = pk;
-  } else {
+  if (p.out_mode == 0) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.O) + row * p.ldo + col) = v;
+    return;
+  }
+  // packed conversions (F2FP); the bf16 planes are the TMA-loadable operand format of the tensor-core kernels
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 hi;
+  hi.x = *reinterpret_cast<uint32_t*>(&a);
+  hi.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.O) + row * p.ldo + col) = hi;
+  if (p.out_mode == 2) {
+    const float hx = __uint_as_float(hi.x << 16), hy = __uint_as_float(hi.x & 0xffff0000u);
+    const float hz = __uint_as_float(hi.y << 16), hw = __uint_as_float(hi.y & 0xffff0000u);
+    a = __floats2bfloat162_rn(v.x - hx, v.y - hy);
+    b = __floats2bfloat162_rn(v.z - hz, v.w - hw);
+    uint2 lo;
+    lo.x = *reinterpret_cast<uint32_t*>(&a);
+    lo.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.O_lo) + row * p.ldo + col) = lo;
   }
 }
 
@@ -302,25 +314,28 @@ extern "C" size_t rgcn_aggregate_workspace_bytes(const rgcn_csr_t* g, int32_t d)
 }
 
 extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d,
-                                  const float* comp, int32_t B, void* H, int64_t ldh, int32_t out_bf16,
+                                  const float* comp, int32_t B, void* H, void* H_lo, int64_t ldh, int32_t out_mode,
                                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
   int rc = check_common(g, X, ldx, d, workspace, workspace_bytes);
   if (rc) return rc;
-  RGCN_CHECK_ARG(H && ((uintptr_t)H & 15) == 0 && ldh % 4 == 0, "aggregate_fwd: output must be 16-byte aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "aggregate_fwd: out_mode must be 0 (fp32), 1 (bf16) or 2 (bf16 hi+lo)");
+  RGCN_CHECK_ARG(H && ((uintptr_t)H & (out_mode ? 7 : 15)) == 0 && ldh % 4 == 0, "aggregate_fwd: output must be aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(out_mode != 2 || (H_lo && ((uintptr_t)H_lo & 7) == 0), "aggregate_fwd: out_mode 2 needs the lo plane");
   RGCN_CHECK_ARG(!comp || (B >= 1), "aggregate_fwd: bad number of bases");
   AggParams p{};
   p.rowptr = g->rowptr; p.idx = g->idx; p.edge_w = g->w;
   p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs;
   p.n_rows = g->n_rows; p.R = g->R;
   p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d;
-  p.O = H; p.ldo = ldh; p.out_bf16 = out_bf16; p.partials = (float*)workspace;
+  p.O = H; p.O_lo = H_lo; p.ldo = ldh; p.out_mode = out_mode; p.partials = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   if (!comp) return dispatch_agg(p, MIX_NONE, g->n_chunks, st);
   // basis blocks are produced kMaxBasis at a time (registers hold B * d/lanes accumulators)
   for (int b0 = 0; b0 < B; b0 += kMaxBasis) {
     AggParams q = p;
     q.comp = comp + b0; q.ldcomp = B; q.B = (B - b0 < kMaxBasis) ? (B - b0) : kMaxBasis;
-    q.O = out_bf16 ? (void*)((__nv_bfloat16*)H + (size_t)b0 * d) : (void*)((float*)H + (size_t)b0 * d);
+    q.O = out_mode ? (void*)((__nv_bfloat16*)H + (size_t)b0 * d) : (void*)((float*)H + (size_t)b0 * d);
+    if (out_mode == 2) q.O_lo = (void*)((__nv_bfloat16*)H_lo + (size_t)b0 * d);
     rc = dispatch_agg(q, MIX_BASIS, b0 == 0 ? g->n_chunks : 0, st);   // chunk partials do not depend on b
     if (rc) return rc;
   }
@@ -341,6 +356,6 @@ extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t
   p.n_rows = gt->n_rows; p.R = gt->R;
   p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d;
   p.init = init; p.ld_init = ld_init; p.B = 1;
-  p.O = gX; p.ldo = ldgx; p.out_bf16 = 0; p.partials = (float*)workspace;
+  p.O = gX; p.ldo = ldgx; p.out_mode = 0; p.partials = (float*)workspace;
   return dispatch_agg(p, MIX_SUM, gt->n_chunks, (cudaStream_t)stream);
 }

@@ -26,9 +26,12 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
-def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False,
-                  comp: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """H[i, r*d:(r+1)*d] = mean_{j in N_r(i)} x[j]  (or the basis-mixed Z when ``comp`` [R, B] is given)."""
+def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False, comp: Optional[torch.Tensor] = None,
+                  planes=None) -> torch.Tensor:
+    """H[i, r*d:(r+1)*d] = mean_{j in N_r(i)} x[j]  (or the basis-mixed Z when ``comp`` [R, B] is given).
+
+    ``planes=(hi, lo_or_None)``: write the result as bf16 planes (the tensor-core operand format) into the first
+    R*d (or B*d) columns of the given row-major bf16 tensors instead of allocating an fp32 / bf16 matrix."""
     lib = _lib.load()
     x = _f32c(x, "x")
     if x.size(0) != g.n_src:
@@ -41,10 +44,17 @@ def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False,
         comp = comp.detach().to(torch.float32).contiguous()
         if comp.size(0) != g.R:
             raise ValueError("comp must have one row per relation")
-    H = torch.empty(g.n_dst, blocks * d, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
     ws = g.fwd.workspace(d)
+    if planes is not None:
+        hi, lo = planes
+        if hi.dtype != torch.bfloat16 or hi.size(0) != g.n_dst or hi.size(1) < blocks * d or hi.stride(1) != 1:
+            raise ValueError("planes must be bf16 [n_dst, >= blocks*d] row-major")
+        H, H_lo, mode = hi, lo, (2 if lo is not None else 1)
+    else:
+        H = torch.empty(g.n_dst, blocks * d, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+        H_lo, mode = None, int(out_bf16)
     _lib.check(lib.rgcn_aggregate_fwd(g.fwd.ref, _ptr(x), x.stride(0), d, _ptr(comp), 0 if comp is None else blocks,
-                                      _ptr(H), H.stride(0), int(out_bf16), _ptr(ws),
+                                      _ptr(H), _ptr(H_lo), H.stride(0), mode, _ptr(ws),
                                       0 if ws is None else ws.numel() * 4, _stream(x.device)), "rgcn_aggregate_fwd")
     return H
 
@@ -171,79 +181,97 @@ def _w2d(w: torch.Tensor, name: str) -> torch.Tensor:
     return w.detach().contiguous()
 
 
-def transform_fwd(A1: torch.Tensor, A2: Optional[torch.Tensor], W1: torch.Tensor, W2: Optional[torch.Tensor],
-                  bias: Optional[torch.Tensor], relu: bool, mode: str) -> torch.Tensor:
-    """out = [A1 | A2] @ [W1 ; W2] + bias (, ReLU) — tcgen05 kernel."""
+def alloc_planes(rows: int, cols: int, mode: str, device):
+    """(hi, lo | None): bf16 row-major [rows, ld] with ld padded to a multiple of 8 (TMA stride alignment)."""
+    ld = (cols + 7) // 8 * 8
+    hi = torch.empty(rows, ld, dtype=torch.bfloat16, device=device)
+    lo = torch.empty(rows, ld, dtype=torch.bfloat16, device=device) if mode == "fp32" else None
+    if ld != cols:
+        hi = hi[:, :cols]
+        lo = None if lo is None else lo[:, :cols]
+    return hi, lo
+
+
+def split_planes(x: torch.Tensor, planes, col0: int = 0, relu_mask: Optional[torch.Tensor] = None,
+                 colsum: bool = False):
+    """Write fp32 ``x`` [rows, cols] into columns [col0, col0+cols) of the bf16 planes (hi [, lo]); optionally zero
+    where relu_mask <= 0 and return the per-block column-sum partials [nblocks, cols] of the masked values."""
     lib = _lib.load()
-    A1 = _f32c(A1, "A1")
-    n, K1 = A1.shape
-    K2 = 0
-    if A2 is not None:
-        A2 = _f32c(A2, "A2")
-        K2 = A2.size(1)
-        W2 = _w2d(W2, "W2")
+    x = _f32c(x, "x")
+    rows, cols = x.shape
+    hi, lo = planes
+    if relu_mask is not None:
+        relu_mask = _f32c(relu_mask, "relu_mask")
+    part = None
+    if colsum:
+        nb = lib.rgcn_split_planes_blocks(rows, cols)
+        part = torch.empty(max(nb, 1), cols, dtype=torch.float32, device=x.device)
+    hi_v = hi[:, col0:col0 + cols]
+    lo_v = None if lo is None else lo[:, col0:col0 + cols]
+    _lib.check(lib.rgcn_split_planes(_ptr(x), x.stride(0), _ptr(relu_mask), 0 if relu_mask is None else relu_mask.stride(0),
+                                     rows, cols, _ptr(hi_v), _ptr(lo_v), hi.stride(0), _ptr(part), _stream(x.device)),
+               "rgcn_split_planes")
+    return part
+
+
+def transform_fwd(planes, K1: int, K2: int, W1: torch.Tensor, W2: Optional[torch.Tensor],
+                  bias: Optional[torch.Tensor], relu: bool, mode: str) -> torch.Tensor:
+    """out = A @ [W1 ; W2] + bias (, ReLU) with A given as bf16 planes [n, K1 + K2] — tcgen05 kernel."""
+    lib = _lib.load()
+    hi, lo = planes
+    n = hi.size(0)
     W1 = _w2d(W1, "W1")
     d_out = W1.size(-1)
-    if W1.numel() != K1 * d_out or (K2 and W2.numel() != K2 * d_out):
+    if W2 is not None:
+        W2 = _w2d(W2, "W2")
+    if W1.numel() != K1 * d_out or (K2 and W2.numel() != K2 * d_out) or hi.size(1) < K1 + K2:
         raise ValueError("weight shapes do not match the operands")
     if bias is not None:
         bias = bias.detach().contiguous()
-    out = torch.empty(n, d_out, dtype=torch.float32, device=A1.device)
-    nb = lib.rgcn_transform_workspace_bytes(n, K1, K2, d_out)
-    ws = _workspace(A1.device, nb)
-    _lib.check(lib.rgcn_transform_fwd(_ptr(A1), A1.stride(0), K1, _ptr(A2), 0 if A2 is None else A2.stride(0), K2,
-                                      _ptr(W1), _ptr(W2), _ptr(bias), int(relu), n, d_out, _ptr(out), out.stride(0),
-                                      _mode_id(mode), _ptr(ws), ws.numel(), _stream(A1.device)), "rgcn_transform_fwd")
+    out = torch.empty(n, d_out, dtype=torch.float32, device=hi.device)
+    nb = lib.rgcn_transform_workspace_bytes(n, K1 + K2, d_out)
+    ws = _workspace(hi.device, nb)
+    _lib.check(lib.rgcn_transform_fwd(_ptr(hi), _ptr(lo), hi.stride(0), K1, K2, _ptr(W1), _ptr(W2), _ptr(bias),
+                                      int(relu), n, d_out, _ptr(out), out.stride(0), _mode_id(mode), _ptr(ws),
+                                      ws.numel(), _stream(hi.device)), "rgcn_transform_fwd")
     return out
 
 
-def transform_dgrad(gO: torch.Tensor, relu_out: Optional[torch.Tensor], W1: torch.Tensor, W2: Optional[torch.Tensor],
-                    mode: str) -> torch.Tensor:
-    """gA = (gO * [relu_out > 0]) @ [W1 ; W2]^T  -> [n, K1 + K2]."""
+def transform_dgrad(g_planes, d_out: int, W1: torch.Tensor, W2: Optional[torch.Tensor], mode: str) -> torch.Tensor:
+    """gA = G @ [W1 ; W2]^T  -> [n, K1 + K2]; G given as bf16 planes [n, d_out]."""
     lib = _lib.load()
-    gO = _f32c(gO, "gO")
-    n, d_out = gO.shape
+    hi, lo = g_planes
+    n = hi.size(0)
     W1 = _w2d(W1, "W1")
     K1 = W1.numel() // d_out
     K2 = 0
     if W2 is not None:
         W2 = _w2d(W2, "W2")
         K2 = W2.numel() // d_out
-    if relu_out is not None:
-        relu_out = _f32c(relu_out, "relu_out")
-    gA = torch.empty(n, K1 + K2, dtype=torch.float32, device=gO.device)
-    nb = lib.rgcn_transform_workspace_bytes(n, K1, K2, d_out)
-    ws = _workspace(gO.device, nb)
-    _lib.check(lib.rgcn_transform_dgrad(_ptr(gO), gO.stride(0), _ptr(relu_out),
-                                        0 if relu_out is None else relu_out.stride(0), d_out, _ptr(W1), K1, _ptr(W2), K2,
-                                        n, _ptr(gA), gA.stride(0), _mode_id(mode), _ptr(ws), ws.numel(),
-                                        _stream(gO.device)), "rgcn_transform_dgrad")
+    gA = torch.empty(n, K1 + K2, dtype=torch.float32, device=hi.device)
+    nb = lib.rgcn_transform_workspace_bytes(n, K1 + K2, d_out)
+    ws = _workspace(hi.device, nb)
+    _lib.check(lib.rgcn_transform_dgrad(_ptr(hi), _ptr(lo), hi.stride(0), d_out, _ptr(W1), K1, _ptr(W2), K2, n,
+                                        _ptr(gA), gA.stride(0), _mode_id(mode), _ptr(ws), ws.numel(),
+                                        _stream(hi.device)), "rgcn_transform_dgrad")
     return gA
 
 
-def transform_wgrad(A1: torch.Tensor, A2: Optional[torch.Tensor], gO: torch.Tensor, relu_out: Optional[torch.Tensor],
-                    mode: str):
-    """(gW1 [K1, d_out], gW2 [K2, d_out] | None, gbias [d_out]) = [A1 | A2]^T @ masked gO, column sums."""
+def transform_wgrad(a_planes, K1: int, K2: int, g_planes, d_out: int, colsum_partial: Optional[torch.Tensor], mode: str):
+    """(gW1 [K1, d_out], gW2 [K2, d_out] | None, gbias [d_out] | None) = A^T @ G, sum of the column-sum partials."""
     lib = _lib.load()
-    A1 = _f32c(A1, "A1")
-    gO = _f32c(gO, "gO")
-    n, K1 = A1.shape
-    d_out = gO.size(1)
-    K2 = 0
-    if A2 is not None:
-        A2 = _f32c(A2, "A2")
-        K2 = A2.size(1)
-    if relu_out is not None:
-        relu_out = _f32c(relu_out, "relu_out")
-    dev = gO.device
+    ahi, alo = a_planes
+    ghi, glo = g_planes
+    n = ahi.size(0)
+    dev = ahi.device
     gW1 = torch.empty(K1, d_out, dtype=torch.float32, device=dev)
     gW2 = torch.empty(K2, d_out, dtype=torch.float32, device=dev) if K2 else None
-    gb = torch.empty(d_out, dtype=torch.float32, device=dev)
-    nb = lib.rgcn_transform_workspace_bytes(n, K1, K2, d_out)
+    gb = torch.empty(d_out, dtype=torch.float32, device=dev) if colsum_partial is not None else None
+    nb = lib.rgcn_transform_workspace_bytes(n, K1 + K2, d_out)
     ws = _workspace(dev, nb)
-    _lib.check(lib.rgcn_transform_wgrad(_ptr(A1), A1.stride(0), K1, _ptr(A2), 0 if A2 is None else A2.stride(0), K2,
-                                        _ptr(gO), gO.stride(0), _ptr(relu_out),
-                                        0 if relu_out is None else relu_out.stride(0), d_out, n, _ptr(gW1), _ptr(gW2),
+    _lib.check(lib.rgcn_transform_wgrad(_ptr(ahi), _ptr(alo), ahi.stride(0), K1, K2, _ptr(ghi), _ptr(glo), ghi.stride(0),
+                                        d_out, n, _ptr(colsum_partial),
+                                        0 if colsum_partial is None else colsum_partial.size(0), _ptr(gW1), _ptr(gW2),
                                         _ptr(gb), _mode_id(mode), _ptr(ws), ws.numel(), _stream(dev)),
                "rgcn_transform_wgrad")
     return gW1, gW2, gb

@@ -1,7 +1,7 @@
-"""GPU tests of the tcgen05 relational-transform kernels against fp64 torch matmuls.
+"""GPU tests of the tcgen05 relational-transform kernels (bf16-plane operands fed by TMA) against fp64 torch matmuls.
 
-Tolerances: mode "fp32" (bf16 hi/lo split, 3 products) — 1e-4 of the output scale, comfortably inside
-BASELINE.json's rtol 1e-4; mode "bf16" — 2e-2."""
+Tolerances: mode "fp32" (bf16 hi/lo planes, 3 products) — 1e-4 of the output scale, inside BASELINE.json's
+rtol 1e-4; mode "bf16" — 2e-2."""
 import pytest
 import torch
 
@@ -11,6 +11,7 @@ DEV = "cuda:0"
 SHAPES = [  # (rows, K1, K2, d_out)
     (300, 48, 16, 32),          # golden-test dims: R=3, d_in=16, d_out=32
     (140, 96, 16, 24),          # d_out not a multiple of 32
+    (100, 36, 12, 20),          # nothing a multiple of 8: padded plane strides
     (1000, 192, 64, 128),       # cfg1 layer 1
     (5000, 384, 128, 128),      # cfg1 layer 2
     (4097, 768, 256, 256),      # cfg2 layer 2, ragged row count
@@ -29,6 +30,32 @@ def ops(lib_built):
     return ops
 
 
+def _planes(ops, mats, mode, relu_mask=None, colsum=False):
+    """fp32 matrices (concatenated along columns) -> bf16 planes."""
+    n = mats[0].size(0)
+    total = sum(m.size(1) for m in mats)
+    P = ops.alloc_planes(n, total, mode, mats[0].device)
+    c0, part = 0, None
+    for m in mats:
+        part = ops.split_planes(m, P, col0=c0, relu_mask=relu_mask, colsum=colsum)
+        c0 += m.size(1)
+    return P, part
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_split_planes(ops, mode):
+    torch.manual_seed(3)
+    x = torch.randn(777, 100, device=DEV) * 3
+    m = torch.randn(777, 100, device=DEV)
+    P, part = _planes(ops, [x], mode, relu_mask=m, colsum=True)
+    want = x * (m > 0)
+    hi = P[0].float()
+    assert torch.equal(P[0], want.to(torch.bfloat16))
+    if mode == "fp32":
+        torch.testing.assert_close(hi + P[1].float(), want, rtol=2 ** -16, atol=1e-30)
+    torch.testing.assert_close(part.double().sum(0), want.double().sum(0), rtol=1e-6, atol=1e-4)
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("relu", [False, True])
@@ -40,14 +67,15 @@ def test_transform_fwd(ops, shape, mode, relu):
     W1 = torch.randn(K1, N, device=DEV) / (K1 + K2) ** 0.5
     W2 = torch.randn(K2, N, device=DEV) / (K1 + K2) ** 0.5 if K2 else None
     b = torch.randn(N, device=DEV)
-    out = ops.transform_fwd(A1, A2, W1, W2, b, relu, mode)
+    A, _ = _planes(ops, [A1] + ([A2] if K2 else []), mode)
+    out = ops.transform_fwd(A, K1, K2, W1, W2, b, relu, mode)
     want = A1.double() @ W1.double() + b.double()
     if K2:
         want = want + A2.double() @ W2.double()
     if relu:
         want = want.clamp(min=0)
     assert _err(out, want) < TOL[mode], (shape, mode, _err(out, want))
-    out2 = ops.transform_fwd(A1, A2, W1, W2, b, relu, mode)
+    out2 = ops.transform_fwd(A, K1, K2, W1, W2, b, relu, mode)
     assert torch.equal(out, out2)
 
 
@@ -61,7 +89,8 @@ def test_transform_dgrad(ops, shape, mode, masked):
     ro = torch.randn(n, N, device=DEV).clamp(min=0) if masked else None
     W1 = torch.randn(K1, N, device=DEV) / N ** 0.5
     W2 = torch.randn(K2, N, device=DEV) / N ** 0.5 if K2 else None
-    gA = ops.transform_dgrad(gO, ro, W1, W2, mode)
+    G, _ = _planes(ops, [gO], mode, relu_mask=ro)
+    gA = ops.transform_dgrad(G, N, W1, W2, mode)
     g = gO.double() * (ro > 0) if masked else gO.double()
     W = torch.cat([W1, W2], 0) if K2 else W1
     want = g @ W.double().t()
@@ -79,11 +108,13 @@ def test_transform_wgrad(ops, shape, mode, masked):
     A2 = torch.randn(n, K2, device=DEV) if K2 else None
     gO = torch.randn(n, N, device=DEV)
     ro = torch.randn(n, N, device=DEV).clamp(min=0) if masked else None
-    gW1, gW2, gb = ops.transform_wgrad(A1, A2, gO, ro, mode)
+    A, _ = _planes(ops, [A1] + ([A2] if K2 else []), mode)
+    G, part = _planes(ops, [gO], mode, relu_mask=ro, colsum=True)
+    gW1, gW2, gb = ops.transform_wgrad(A, K1, K2, G, N, part, mode)
     g = gO.double() * (ro > 0) if masked else gO.double()
     assert _err(gW1, A1.double().t() @ g) < TOL[mode], (shape, mode, "gW1", _err(gW1, A1.double().t() @ g))
     if K2:
         assert _err(gW2, A2.double().t() @ g) < TOL[mode], (shape, mode, "gW2")
     assert _err(gb, g.sum(0)) < 1e-5, (shape, mode, "gbias", _err(gb, g.sum(0)))
-    again = ops.transform_wgrad(A1, A2, gO, ro, mode)
+    again = ops.transform_wgrad(A, K1, K2, G, N, part, mode)
     assert torch.equal(gW1, again[0]) and torch.equal(gb, again[2])          # deterministic split-K
