@@ -65,20 +65,33 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   const int64_t r_end = min(r_beg + rows_per_block, rows);
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rsub < rpp) {
-    for (int64_t r = r_beg + rsub; r < r_end; r += rpp) {
-      float4 v = ldg4(x + r * ldx + c4 * 4);
-      if (mask) {
-        const float4 m = ldg4(mask + r * ldm + c4 * 4);
-        if (!(m.x > 0.f)) v.x = 0.f;
-        if (!(m.y > 0.f)) v.y = 0.f;
-        if (!(m.z > 0.f)) v.z = 0.f;
-        if (!(m.w > 0.f)) v.w = 0.f;
+    constexpr int U = 4;                           // independent rows in flight per thread
+    for (int64_t r0 = r_beg + rsub; r0 < r_end; r0 += (int64_t)U * rpp) {
+      float4 v[U], m[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + (int64_t)u * rpp;
+        const bool ok = r < r_end;
+        v[u] = ok ? ldg4(x + r * ldx + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mask) m[u] = ok ? ldg4(mask + r * ldm + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      add4(cs, v);
-      uint2 h, l;
-      split4(v, h, l);
-      *reinterpret_cast<uint2*>(hi + r * ldp + c4 * 4) = h;
-      if (lo) *reinterpret_cast<uint2*>(lo + r * ldp + c4 * 4) = l;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + (int64_t)u * rpp;
+        if (r < r_end) {
+          if (mask) {
+            if (!(m[u].x > 0.f)) v[u].x = 0.f;
+            if (!(m[u].y > 0.f)) v[u].y = 0.f;
+            if (!(m[u].z > 0.f)) v[u].z = 0.f;
+            if (!(m[u].w > 0.f)) v[u].w = 0.f;
+          }
+          add4(cs, v[u]);
+          uint2 h, l;
+          split4(v[u], h, l);
+          *reinterpret_cast<uint2*>(hi + r * ldp + c4 * 4) = h;
+          if (lo) *reinterpret_cast<uint2*>(lo + r * ldp + c4 * 4) = l;
+        }
+      }
     }
   }
   if (colsum_partial) {
@@ -401,24 +414,46 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   }
 }
 
-// fixed-order reduction of the split partials into gW1 [K1, N], gW2 [K2, N]; of the column-sum partials into g_bias
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int m_pad, int ldp, int K1, int K2,
-                                    int N, float* __restrict__ gw1, float* __restrict__ gw2,
-                                    const float* __restrict__ colsum_partial, int n_colsum, float* __restrict__ gbias) {
-  const int64_t total = (int64_t)(K1 + K2 + 1) * (N >> 2);
+// fixed-order reduction of the split partials into gW1 [K1, N], gW2 [K2, N]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int m_pad,
+                                                           int ldp, int K1, int K2, int N, float* __restrict__ gw1,
+                                                           float* __restrict__ gw2) {
+  const int64_t total = (int64_t)(K1 + K2) * (N >> 2);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int m = (int)(i / (N >> 2)), n = (int)(i % (N >> 2)) * 4;
+    const float* src = partial + (size_t)m * ldp + n;
+    const size_t stride = (size_t)m_pad * ldp;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < K1 + K2) {
-      for (int sp = 0; sp < splits; ++sp)
-        add4(s, *reinterpret_cast<const float4*>(partial + ((size_t)sp * m_pad + m) * ldp + n));
-      float* dst = (m < K1) ? gw1 + (size_t)m * N + n : gw2 + (size_t)(m - K1) * N + n;
-      *reinterpret_cast<float4*>(dst) = s;
-    } else if (gbias && colsum_partial) {
-      for (int sp = 0; sp < n_colsum; ++sp) add4(s, *reinterpret_cast<const float4*>(colsum_partial + (size_t)sp * N + n));
-      *reinterpret_cast<float4*>(gbias + n) = s;
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {          // 4 independent loads in flight, added in split order
+      const float4 a = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
+      const float4 b = *reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * stride);
+      const float4 c = *reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * stride);
+      const float4 d = *reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * stride);
+      add4(s, a); add4(s, b); add4(s, c); add4(s, d);
     }
+    for (; sp < splits; ++sp) add4(s, *reinterpret_cast<const float4*>(src + (size_t)sp * stride));
+    float* dst = (m < K1) ? gw1 + (size_t)m * N + n : gw2 + (size_t)(m - K1) * N + n;
+    *reinterpret_cast<float4*>(dst) = s;
   }
+}
+
+// g_bias[n] = sum over the column-sum partials [n_part, N]: one warp per float4 column, lanes stride over the
+// partials, then a fixed shuffle tree => deterministic
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int n_part, int N,
+                                                            float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int c4 = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c4 >= (N >> 2)) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = lane; p < n_part; p += 32) add4(s, *reinterpret_cast<const float4*>(part + (size_t)p * N + c4 * 4));
+  for (int o = 16; o; o >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+    s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+  }
+  if (lane == 0) *reinterpret_cast<float4*>(out + c4 * 4) = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,8 +565,8 @@ using namespace rgcn;
 extern "C" int64_t rgcn_split_planes_blocks(int64_t rows, int32_t cols) {
   if (rows <= 0 || cols < 4) return 0;
   const int rpp = 256 / (cols / 4) > 0 ? 256 / (cols / 4) : 1;
-  int64_t nb = (rows + 63) / 64;
-  if (nb > 592) nb = 592;
+  int64_t nb = (rows + 31) / 32;
+  if (nb > 1184) nb = 1184;
   const int64_t rpb = ((rows + nb - 1) / nb + rpp - 1) / rpp * rpp;
   return (rows + rpb - 1) / rpb;
 }
@@ -692,9 +727,13 @@ extern "C" int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t 
     }
     RGCN_LAUNCH_CHECK();
   }
-  const int64_t total = (int64_t)(K + 1) * (d_out / 4);
-  wgrad_reduce_kernel<<<grid_cap((total + 255) / 256, 2368), 256, 0, st>>>(
-      p.partial, n_rows > 0 ? splits : 0, m_tiles * BM, t.n_pad, K1, K2, d_out, gW1, gW2, colsum_partial, n_colsum, gbias);
+  const int64_t total = (int64_t)K * (d_out / 4);
+  wgrad_reduce_kernel<<<grid_cap((total + 255) / 256, 4736), 256, 0, st>>>(p.partial, n_rows > 0 ? splits : 0, m_tiles * BM,
+                                                                          t.n_pad, K1, K2, d_out, gW1, gW2);
   RGCN_LAUNCH_CHECK();
+  if (gbias) {
+    colsum_reduce_kernel<<<(unsigned)((d_out / 4 + 7) / 8), 256, 0, st>>>(colsum_partial, n_colsum, d_out, gbias);
+    RGCN_LAUNCH_CHECK();
+  }
   return RGCN_OK;
 }
