@@ -7,8 +7,9 @@ A from-scratch implementation of the one hot path of arnold117/PrimeKG-RGCN-Link
 """
 from .conv import RGCNConv, default_mode
 from .graph import RelGraph, clear_graph_cache, get_graph
+from .graphed import GraphedTrainStep
 from .modules import DrugDiseaseModel, DrugDiseaseRGCN, LinkPredictor
 
 __all__ = ["RGCNConv", "DrugDiseaseRGCN", "LinkPredictor", "DrugDiseaseModel", "RelGraph", "get_graph",
-           "clear_graph_cache", "default_mode"]
+           "clear_graph_cache", "default_mode", "GraphedTrainStep"]
 __version__ = "0.1.0"

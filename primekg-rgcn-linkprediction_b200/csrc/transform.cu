@@ -477,7 +477,20 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 matrix [rows, cols] row-major with leading dimension ld (elements); box = 64 cols x box_rows rows, 128B swizzle;
 // out-of-range elements read as zero
+struct MapKey { const void* base; int64_t rows, cols, ld; int box_rows; };
 static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  // the same planes / weight buffers come back every step: a small thread-local cache skips the driver call
+  constexpr int NC = 32;
+  static thread_local MapKey keys[NC];
+  static thread_local CUtensorMap vals[NC];
+  static thread_local int n_cached = 0, next = 0;
+  for (int i = 0; i < n_cached; ++i) {
+    const MapKey& k = keys[i];
+    if (k.base == base && k.rows == rows && k.cols == cols && k.ld == ld && k.box_rows == box_rows) {
+      *m = vals[i];
+      return RGCN_OK;
+    }
+  }
   EncodeTiledFn enc = encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return RGCN_EUNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -492,6 +505,10 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
               (long long)rows, (long long)cols, (long long)ld, box_rows);
     return RGCN_ECUDA;
   }
+  keys[next] = MapKey{base, rows, cols, ld, box_rows};
+  vals[next] = *m;
+  next = (next + 1) % NC;
+  if (n_cached < NC) ++n_cached;
   return RGCN_OK;
 }
 
@@ -509,9 +526,16 @@ static Tiling tile_n(int N, int gran) {
   return t;
 }
 
+// opt in to > 48 KB dynamic shared memory, once per kernel instantiation and device
 template <typename K>
 static int set_smem(K kernel, int bytes) {
-  RGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  static bool done[64] = {false};
+  int dev = 0;
+  RGCN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    RGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+  }
   return RGCN_OK;
 }
 

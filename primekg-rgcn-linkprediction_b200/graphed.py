@@ -1,0 +1,64 @@
+"""CUDA-graph replay of the hot step (forward + loss + backward) for launch-bound graph sizes.
+
+At the reference's sizes one full-graph step is ~50 kernels of 3-80 us; issued eagerly from Python the host is the
+limiter.  ``GraphedTrainStep`` captures one step — ``model(edge_index, edge_type, heads, tails, rels)`` ->
+``BCEWithLogitsLoss`` -> ``backward()`` (reference src/train.py:291-306) — into a CUDA graph over static input buffers
+and replays it; gradients land in the parameters' ``.grad`` as usual, so the optimiser / clipping code of the caller
+(src/train.py:309-318) stays as it is.  Dropout masks are re-drawn on every replay (torch's graph-safe Philox state).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+class GraphedTrainStep:
+    def __init__(self, model: torch.nn.Module, edge_index: torch.Tensor, edge_type: torch.Tensor, batch_size: int,
+                 loss_fn: Optional[Callable] = None, warmup: int = 3):
+        if not edge_index.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors")
+        dev = edge_index.device
+        self.model, self.edge_index, self.edge_type = model, edge_index, edge_type
+        self.loss_fn = loss_fn or F.binary_cross_entropy_with_logits
+        self.heads = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.tails = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.rels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
+        self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        for p in self.params:                                   # static gradient buffers
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.scores = self._step()
+
+    def _step(self):
+        for p in self.params:
+            p.grad.zero_()
+        scores = self.model(self.edge_index, self.edge_type, self.heads, self.tails, self.rels)
+        loss = self.loss_fn(scores, self.labels)
+        loss.backward()
+        return loss.detach(), scores.detach()
+
+    def load_batch(self, heads, tails, rels, labels, non_blocking: bool = True) -> None:
+        """Copy one batch (host, pinned or device tensors) into the static input buffers."""
+        self.heads.copy_(heads, non_blocking=non_blocking)
+        self.tails.copy_(tails, non_blocking=non_blocking)
+        self.rels.copy_(rels, non_blocking=non_blocking)
+        self.labels.copy_(labels, non_blocking=non_blocking)
+
+    def __call__(self, heads=None, tails=None, rels=None, labels=None) -> torch.Tensor:
+        """Run one step; returns the (static) loss tensor.  With no arguments the buffers are used as they are."""
+        if heads is not None:
+            self.load_batch(heads, tails, rels, labels)
+        self.graph.replay()
+        return self.loss
