@@ -44,15 +44,21 @@ class _RGCNLayerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, W, root, bias, graph: RelGraph, relu: bool, mode: str):
+    def forward(ctx, x_src, x_root, W, root, bias, graph: RelGraph, relu: bool, mode: str):
+        """x_src [n_src, d_in]: rows the edges gather from; x_root [n_dst, d_in]: the rows being updated (self-loop
+        term).  On one GPU they are the same tensor; on a destination-range shard x_src is the all-gathered matrix."""
         R, d_in, d_out = W.shape
-        x = x.contiguous()
+        shared = x_src.data_ptr() == x_root.data_ptr() and x_src.shape == x_root.shape
+        x_src = x_src.contiguous()
+        x_root = x_src if shared else x_root.contiguous()
+        if x_root.size(0) != graph.n_dst:
+            raise ValueError(f"x has {x_root.size(0)} rows, the graph updates {graph.n_dst}")
         K1, K2 = R * d_in, d_in
-        A = ops.alloc_planes(graph.n_dst, K1 + K2, mode, x.device)
-        ops.aggregate_fwd(graph, x, planes=A)
-        ops.split_planes(x, A, col0=K1)
+        A = ops.alloc_planes(graph.n_dst, K1 + K2, mode, x_src.device)
+        ops.aggregate_fwd(graph, x_src, planes=A)
+        ops.split_planes(x_root, A, col0=K1)
         out = ops.transform_fwd(A, K1, K2, W.reshape(K1, d_out), root, bias, relu, mode)
-        ctx.graph, ctx.relu, ctx.mode = graph, relu, mode
+        ctx.graph, ctx.relu, ctx.mode, ctx.shared = graph, relu, mode, shared
         ctx.save_for_backward(A[0], A[1], W, root, out if relu else None)
         return out
 
@@ -64,19 +70,24 @@ class _RGCNLayerFn(torch.autograd.Function):
         K1, K2 = R * d_in, d_in
         gO = gO.contiguous()
         Wf = W.reshape(K1, d_out)
-        need_x, need_W, need_root, need_b = ctx.needs_input_grad[:4]
+        need_src, need_root_x, need_W, need_root, need_b = ctx.needs_input_grad[:5]
         need_w_any = need_W or need_root or need_b
-        gx = gW = groot = gb = None
+        gx_src = gx_root = gW = groot = gb = None
         # G = gO * [out > 0] as bf16 planes, formed once for both GEMMs; column sums = bias gradient
         G = ops.alloc_planes(gO.size(0), d_out, mode, gO.device)
         colsum = ops.split_planes(gO, G, relu_mask=out, colsum=need_w_any)
-        if need_x:
-            gA = ops.transform_dgrad(G, d_out, Wf, root, mode)            # [N, (R+1) * d_in]
-            gx = ops.aggregate_bwd(graph, gA, d_in, init=gA[:, K1:])
+        if need_src or need_root_x:
+            gA = ops.transform_dgrad(G, d_out, Wf, root, mode)            # [n_dst, (R+1) * d_in]
+            if ctx.shared:
+                gx_src = ops.aggregate_bwd(graph, gA, d_in, init=gA[:, K1:])
+            else:
+                if need_src:
+                    gx_src = ops.aggregate_bwd(graph, gA, d_in, init=None)   # full-length partial, reduced by the caller
+                gx_root = gA[:, K1:]
         if need_w_any:
             gWf, groot, gb = ops.transform_wgrad((A_hi, A_lo), K1, K2, G, d_out, colsum, mode)
             gW = gWf.view(R, d_in, d_out)
-        return gx, gW, groot, gb, None, None, None
+        return gx_src, gx_root, gW, groot, gb, None, None, None
 
 
 def _glorot_(t: Optional[torch.Tensor]) -> None:
@@ -123,7 +134,7 @@ class RGCNConv(nn.Module):
             raise ValueError(f"x must be [N, {self.in_channels}]")
         if graph.R != self.num_relations:
             raise ValueError("graph and layer disagree on the number of relations")
-        return _RGCNLayerFn.apply(x, self.relation_weights(), self.root, self.bias, graph, relu,
+        return _RGCNLayerFn.apply(x, x, self.relation_weights(), self.root, self.bias, graph, relu,
                                   self.mode or default_mode())
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_type: torch.Tensor) -> torch.Tensor:

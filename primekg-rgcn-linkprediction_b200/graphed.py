@@ -5,6 +5,9 @@ limiter.  ``GraphedTrainStep`` captures one step — ``model(edge_index, edge_ty
 ``BCEWithLogitsLoss`` -> ``backward()`` (reference src/train.py:291-306) — into a CUDA graph over static input buffers
 and replays it; gradients land in the parameters' ``.grad`` as usual, so the optimiser / clipping code of the caller
 (src/train.py:309-318) stays as it is.  Dropout masks are re-drawn on every replay (torch's graph-safe Philox state).
+
+Construct it before (or after dropping) any eager autograd graph of the same model: a live graph keeps the
+parameters' AccumulateGrad nodes bound to the stream they were created on, which a capture cannot depend on.
 """
 from __future__ import annotations
 

@@ -1,0 +1,69 @@
+"""TEST INFRASTRUCTURE: CPU stand-ins for the C-ABI wrappers in ``ops.py`` so the host-side plumbing above the
+kernels (the partition plan, padded relabelling, collectives with autograd, layer wiring) can be exercised with
+``gloo`` on a machine without a GPU.  Same formulas as oracle/rgcn_ref.py; never imported by the product."""
+import torch
+
+
+class CpuGraph:
+    """Stand-in for graph.RelGraph: keeps the local edge list (src may live in a larger, padded id space)."""
+
+    def __init__(self, src, dst, rel, n_dst, n_src, R):
+        self.src, self.dst, self.rel = src.long(), dst.long(), rel.long()
+        self.n_dst, self.n_src, self.R, self.E = int(n_dst), int(n_src), int(R), int(rel.numel())
+        key = self.dst * R + self.rel
+        self.cnt = torch.bincount(key, minlength=self.n_dst * R).clamp(min=1).to(torch.float32).view(self.n_dst, R)
+
+
+def alloc_planes(rows, cols, mode, device):
+    return torch.zeros(rows, cols), None
+
+
+def aggregate_fwd(g, x, out_bf16=False, comp=None, planes=None):
+    d = x.size(1)
+    H = planes[0] if planes is not None else torch.zeros(g.n_dst, g.R * d)
+    for r in range(g.R):
+        m = g.rel == r
+        s = torch.zeros(g.n_dst, d).index_add_(0, g.dst[m], x[g.src[m]])
+        H[:, r * d:(r + 1) * d] = s / g.cnt[:, r:r + 1]
+    return H
+
+
+def split_planes(x, planes, col0=0, relu_mask=None, colsum=False):
+    v = x if relu_mask is None else x * (relu_mask > 0)
+    planes[0][:, col0:col0 + x.size(1)] = v
+    return v.sum(0, keepdim=True) if colsum else None
+
+
+def transform_fwd(planes, K1, K2, W1, W2, bias, relu, mode):
+    W = W1.reshape(K1, -1) if W2 is None else torch.cat([W1.reshape(K1, -1), W2], 0)
+    out = planes[0][:, :K1 + K2] @ W.detach() + bias.detach()
+    return out.clamp(min=0) if relu else out
+
+
+def transform_dgrad(g_planes, d_out, W1, W2, mode):
+    W = W1.reshape(-1, d_out) if W2 is None else torch.cat([W1.reshape(-1, d_out), W2], 0)
+    return g_planes[0] @ W.detach().t()
+
+
+def transform_wgrad(a_planes, K1, K2, g_planes, d_out, colsum_partial, mode):
+    gW = a_planes[0][:, :K1 + K2].t() @ g_planes[0]
+    return gW[:K1].contiguous(), (gW[K1:].contiguous() if K2 else None), (
+        None if colsum_partial is None else colsum_partial.sum(0))
+
+
+def aggregate_bwd(g, gH, d, init=None):
+    gx = torch.zeros(g.n_src, d)
+    if init is not None:
+        gx[: init.size(0)] += init[:, :d]
+    for r in range(g.R):
+        m = g.rel == r
+        contrib = gH[g.dst[m], r * d:(r + 1) * d] / g.cnt[g.dst[m], r:r + 1]
+        gx.index_add_(0, g.src[m], contrib)
+    return gx
+
+
+def install(monkeypatch_target):
+    """Replace the kernel wrappers in ``ops`` (module object) by the CPU stand-ins."""
+    for name in ("alloc_planes", "aggregate_fwd", "split_planes", "transform_fwd", "transform_dgrad",
+                 "transform_wgrad", "aggregate_bwd"):
+        setattr(monkeypatch_target, name, globals()[name])

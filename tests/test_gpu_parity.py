@@ -411,13 +411,18 @@ def test_graphed_step_matches_eager(pkg):
     m.train()
     ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
     b = [g[k].to(DEV) for k in ("heads", "tails", "rels", "labels")]
-    m.zero_grad()
-    loss = F.binary_cross_entropy_with_logits(m(ei, et, b[0], b[1], b[2]), b[3])
-    loss.backward()
-    want = {k: p.grad.clone() for k, p in m.named_parameters()}
+    def eager():
+        # in its own scope: a live autograd graph would keep the parameters' AccumulateGrad nodes bound to the
+        # default stream, which a later capture on another stream may not depend on
+        m.zero_grad()
+        loss = F.binary_cross_entropy_with_logits(m(ei, et, b[0], b[1], b[2]), b[3])
+        loss.backward()
+        return loss.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    want_loss, want = eager()
     step = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel())
     got_loss = step(*b).clone()
-    torch.testing.assert_close(got_loss, loss.detach(), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(got_loss, want_loss, rtol=1e-6, atol=1e-7)
     for k, p in m.named_parameters():
         if "node_embeddings" in k or "relation" in k:      # decoder scatter uses fp32 atomics on repeated nodes
             torch.testing.assert_close(p.grad, want[k], rtol=1e-4, atol=1e-6)
