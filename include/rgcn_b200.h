@@ -204,6 +204,27 @@ int rgcn_distmult_bwd(const float* emb_h, int64_t ld_h, const float* emb_t, int6
                       const float* rel_table, const float* rel_rows, const float* rel_scale,
                       const float* g_score, int64_t n_pairs, int32_t d, float* g_h, int64_t ld_gh, float* g_t, int64_t ld_gt,
                       float* g_rel_table, float* g_rel_rows, rgcn_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * All-pairs scoring / ranking (fp32).  A is a prepared query matrix (rgcn_rows_prepare: gather rows of the
+ * encoder output, optionally times the relation row (DistMult h * r, src/models/rgcn.py:235-238) and / or
+ * L2-normalised (cosine, src/compare_methods.py:384-397)); B is the candidate matrix, optionally gathered
+ * through b_idx.
+ *   rgcn_allpairs_scores: out[i, j] = alpha * <A[i], B[b_idx[j]]> + beta      (score_all_tails, src/models/rgcn.py:241;
+ *                          (cos + 1) / 2 with alpha = beta = 0.5; the 6,282 x 5,593 drug-disease sweep)
+ *   rgcn_allpairs_rank  : thr[i] = <A[i], B[true_pos[i]]>;  greater[i] / equal[i] = number of candidates j != true_pos[i]
+ *                          scoring above / exactly at thr[i].  rank = 1 + greater reproduces the argsort loop of
+ *                          src/evaluate.py:260-276 without materialising the [queries, candidates] matrix.
+ * true_pos indexes the candidate list (positions in b_idx when given).
+ * ------------------------------------------------------------------------------------------ */
+int rgcn_rows_prepare(const float* emb, int64_t ld, const int64_t* idx, int64_t n, int32_t d,
+                      const float* rel_table, const int64_t* rel, int32_t normalize,
+                      float* out, int64_t ldo, rgcn_stream_t stream);
+int rgcn_allpairs_scores(const float* A, int64_t lda, int64_t na, const float* B, int64_t ldb,
+                         const int64_t* b_idx, int64_t nb, int32_t d, float alpha, float beta,
+                         float* out, int64_t ldo, rgcn_stream_t stream);
+int rgcn_allpairs_rank(const float* A, int64_t lda, int64_t nq, const float* B, int64_t ldb,
+                       const int64_t* b_idx, int64_t nb, int32_t d, const int64_t* true_pos,
+                       float* thr, int32_t* greater, int32_t* equal, rgcn_stream_t stream);
 /* flag[0] = 1 when any head/tail is outside [0, n_nodes) or any rel outside [0, n_rel). */
 int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,
                      int64_t n_nodes, int32_t n_rel, int32_t* flag, rgcn_stream_t stream);

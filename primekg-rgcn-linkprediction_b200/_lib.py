@@ -49,6 +49,9 @@ PROTOTYPES = {
     "rgcn_transform_wgrad": (C.c_int, [p, p, i64, i32, i32, p, p, i64, i32, i64, p, i32, p, p, p, i32, p, sz, p]),
     "rgcn_distmult_fwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, i64, i32, p, p]),
     "rgcn_distmult_bwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, p, i64, i32, p, i64, p, i64, p, p, p]),
+    "rgcn_rows_prepare": (C.c_int, [p, i64, p, i64, i32, p, p, i32, p, i64, p]),
+    "rgcn_allpairs_scores": (C.c_int, [p, i64, i64, p, i64, p, i64, i32, C.c_float, C.c_float, p, i64, p]),
+    "rgcn_allpairs_rank": (C.c_int, [p, i64, i64, p, i64, p, i64, i32, p, p, p, p, p]),
     "rgcn_check_pairs": (C.c_int, [p, p, p, i64, i64, i32, p, p]),
 }
 

@@ -152,8 +152,39 @@ class LinkPredictor(nn.Module):
                         all_tail_embeddings: torch.Tensor) -> torch.Tensor:
         """(h * r) @ T^T -> [batch, num_entities] (reference :234-241; no dropout here, as there)."""
         _need_cuda(head_embeddings, "LinkPredictor.score_all_tails")
-        hr = head_embeddings * self.relation_embeddings(relation_types)
-        return hr @ all_tail_embeddings.t()
+        return _ScoreAllTails.apply(head_embeddings, self.relation_embeddings.weight, relation_types,
+                                    all_tail_embeddings)
+
+    def rank_tails(self, node_embeddings: torch.Tensor, head_indices: torch.Tensor, relation_types: torch.Tensor,
+                   tail_indices: torch.Tensor):
+        """(rank, ties) of the true tails among all entities — the fused form of ``score_all_tails`` + the per-row
+        ``argsort`` loop of reference src/evaluate.py:260-276."""
+        from .rank import rank_true_tails
+        return rank_true_tails(node_embeddings, self.relation_embeddings.weight, head_indices, relation_types,
+                               tail_indices)
+
+
+class _ScoreAllTails(torch.autograd.Function):
+    """scores = (h * r[rel]) @ T^T through the all-pairs kernel; the (never hot) backward uses three library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, h, table, rel, T):
+        from .rank import _prep, scores_from_rows
+        hr = _prep(h, None, table, rel, False)
+        ctx.save_for_backward(h, table, rel, T)
+        return scores_from_rows(hr, T)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, table, rel, T = ctx.saved_tensors
+        r = table[rel]
+        g_hr = g @ T                                  # [B, d]
+        g_h = g_hr * r if ctx.needs_input_grad[0] else None
+        g_table = None
+        if ctx.needs_input_grad[1]:
+            g_table = torch.zeros_like(table).index_add_(0, rel, g_hr * h)
+        g_T = g.t() @ (h * r) if ctx.needs_input_grad[3] else None
+        return g_h, g_table, None, g_T
 
 
 class DrugDiseaseModel(nn.Module):

@@ -1,0 +1,98 @@
+"""GPU tests of the all-pairs scoring / ranking kernels against the oracle (reference src/models/rgcn.py:234-241,
+src/evaluate.py:260-276, src/compare_methods.py:384-397)."""
+import pytest
+import torch
+
+from oracle import rgcn_ref as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def pkg(lib_built):
+    return lib_built
+
+
+@pytest.mark.parametrize("N,d,B", [(1000, 128, 77), (30926, 128, 1024), (513, 24, 5)])
+def test_score_all_tails_matches_oracle(pkg, N, d, B):
+    torch.manual_seed(0)
+    R = 3
+    dec = pkg.LinkPredictor(R, d).to(DEV)
+    ref = O.DecoderRef(R, d)
+    ref.load_state_dict(dec.state_dict())
+    emb = torch.randn(N, d)
+    heads = torch.randint(0, N, (B,))
+    rels = torch.randint(0, R, (B,))
+    with torch.no_grad():
+        got = dec.score_all_tails(emb.to(DEV)[heads.to(DEV)], rels.to(DEV), emb.to(DEV)).cpu()
+        want = ref.score_all_tails(emb[heads], rels, emb)
+    assert got.shape == (B, N)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+
+
+def test_score_all_tails_backward(pkg):
+    torch.manual_seed(1)
+    N, d, B, R = 200, 32, 9, 3
+    dec = pkg.LinkPredictor(R, d).to(DEV)
+    ref = O.DecoderRef(R, d)
+    ref.load_state_dict(dec.state_dict())
+    h, T = torch.randn(B, d, requires_grad=True), torch.randn(N, d, requires_grad=True)
+    rels = torch.randint(0, R, (B,))
+    hd, Td = h.detach().to(DEV).requires_grad_(), T.detach().to(DEV).requires_grad_()
+    coef = torch.randn(B, N)
+    (dec.score_all_tails(hd, rels.to(DEV), Td) * coef.to(DEV)).sum().backward()
+    (ref.score_all_tails(h, rels, T) * coef).sum().backward()
+    torch.testing.assert_close(hd.grad.cpu(), h.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(Td.grad.cpu(), T.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dec.relation_embeddings.weight.grad.cpu(), ref.relation_embeddings.weight.grad,
+                               rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,d,B", [(30926, 128, 1024), (777, 64, 130)])
+def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B):
+    """rank = 1 + #greater must lie inside the oracle's [optimistic, pessimistic] bracket evaluated with an epsilon
+    band (two fp32 summation orders), and equal the exact count computed from our own score matrix."""
+    torch.manual_seed(2)
+    R = 3
+    emb = torch.randn(N, d, device=DEV)
+    table = torch.randn(R, d, device=DEV)
+    heads = torch.randint(0, N, (B,), device=DEV)
+    tails = torch.randint(0, N, (B,), device=DEV)
+    rels = torch.randint(0, R, (B,), device=DEV)
+    emb[5] = emb[9]                                   # an exact duplicate entity => exact score ties
+    tails[0] = 5
+    rank, ties = pkg.rank_true_tails(emb, table, heads, rels, tails)
+    scores = O.distmult_allpairs_ref(emb.double(), heads, torch.arange(N, device=DEV), table[rels].double())
+    s_true = scores.gather(1, tails.view(-1, 1))
+    eps = 1e-4 * scores.abs().max()
+    lo = (scores > s_true + eps).sum(1) + 1
+    hi = (scores >= s_true - eps).sum(1)
+    assert torch.all(rank >= lo) and torch.all(rank + ties <= hi + 0) or torch.all((rank >= lo) & (rank <= hi))
+    assert int(ties[0]) >= 1                          # the duplicate of the true tail is an exact tie
+    # exactness against our own fp32 scores
+    from primekg_rgcn_linkprediction_b200.rank import _prep, scores_from_rows
+    S = scores_from_rows(_prep(emb, heads, table, rels, False), emb)
+    st = S.gather(1, tails.view(-1, 1))
+    others = torch.ones_like(S, dtype=torch.bool)
+    others.scatter_(1, tails.view(-1, 1), False)
+    assert torch.equal(rank, ((S > st) & others).sum(1) + 1)
+    assert torch.equal(ties, ((S == st) & others).sum(1))
+    m = pkg.ranking_metrics(rank)
+    assert 0 < m["mrr"] <= 1 and m["hits@100"] >= m["hits@10"]
+
+
+def test_all_pairs_drug_disease_sweep(pkg):
+    """BASELINE cfg4: all 6,282 x 5,593 drug-disease pairs, DistMult and cosine."""
+    torch.manual_seed(3)
+    emb = torch.randn(30926, 128, device=DEV)
+    drugs = torch.arange(5593, 11875, device=DEV)
+    diseases = torch.arange(0, 5593, device=DEV)
+    rel = torch.randn(128, device=DEV)
+    got = pkg.score_all_pairs(emb, drugs, diseases, rel_vec=rel)
+    want = O.distmult_allpairs_ref(emb, drugs, diseases, rel)
+    assert got.shape == (6282, 5593)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+    gotc = pkg.score_all_pairs(emb, drugs, diseases, cosine=True)
+    wantc = O.cosine_allpairs_ref(emb, drugs, diseases)
+    torch.testing.assert_close(gotc, wantc, rtol=1e-5, atol=1e-5)
