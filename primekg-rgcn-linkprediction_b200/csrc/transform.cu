@@ -526,16 +526,19 @@ static Tiling tile_n(int N, int gran) {
   return t;
 }
 
-// opt in to > 48 KB dynamic shared memory, once per kernel instantiation and device
+// opt in to > 48 KB dynamic shared memory, once per kernel (function pointer) and device
 template <typename K>
 static int set_smem(K kernel, int bytes) {
-  static bool done[64] = {false};
+  struct Seen { const void* fn; int dev; };
+  static Seen seen[64];
+  static int n_seen = 0;
   int dev = 0;
   RGCN_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !done[dev]) {
-    RGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    if (dev >= 0 && dev < 64) done[dev] = true;
-  }
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i].fn == fn && seen[i].dev == dev) return RGCN_OK;
+  RGCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (n_seen < 64) seen[n_seen++] = Seen{fn, dev};
   return RGCN_OK;
 }
 
