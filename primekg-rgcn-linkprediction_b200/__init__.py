@@ -6,11 +6,11 @@ A from-scratch implementation of the one hot path of arnold117/PrimeKG-RGCN-Link
 ``nn.Module`` API.  No CPU fallback: see ``oracle/`` for the CPU restatement used by the tests.
 """
 from .conv import RGCNConv, default_mode
-from .graph import RelGraph, clear_graph_cache, get_graph
+from .graph import RelGraph, clear_graph_cache, get_graph, graph_from_state, graph_state, register_graph
 from .graphed import GraphedTrainStep
 from .rank import rank_true_tails, ranking_metrics, score_all_pairs
 from .modules import DrugDiseaseModel, DrugDiseaseRGCN, LinkPredictor
 
 __all__ = ["RGCNConv", "DrugDiseaseRGCN", "LinkPredictor", "DrugDiseaseModel", "RelGraph", "get_graph",
-           "clear_graph_cache", "default_mode", "GraphedTrainStep", "rank_true_tails", "ranking_metrics", "score_all_pairs"]
+           "clear_graph_cache", "default_mode", "GraphedTrainStep", "graph_state", "graph_from_state", "register_graph", "rank_true_tails", "ranking_metrics", "score_all_pairs"]
 __version__ = "0.1.0"

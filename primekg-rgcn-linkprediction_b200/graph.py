@@ -154,3 +154,41 @@ def get_graph(edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int,
 
 def clear_graph_cache() -> None:
     _CACHE.clear()
+
+
+# ---- on-disk form ---------------------------------------------------------------
+def graph_state(g: RelGraph) -> dict:
+    """Plain dict of CPU tensors / ints with the preprocessed CSR + CSR^T, to be stored next to ``edge_index`` in the
+    reference's ``data/processed/*.pt`` files (its loaders read keys by name and ignore extras: src/train.py:130-135),
+    so later runs skip the sort."""
+    keys = ("rowptr", "col", "perm", "rowptr_t", "row_t", "perm_t", "inv_cnt", "w_t")
+    out = {f"csr_{k}": getattr(g, k).cpu() for k in keys}
+    out.update(csr_n_dst=g.n_dst, csr_n_src=g.n_src, csr_num_relations=g.R, csr_num_edges=g.E,
+               csr_max_seg=g.max_seg, csr_max_seg_t=g.max_seg_t, csr_format=1)
+    return out
+
+
+def graph_from_state(state: dict, device) -> RelGraph:
+    """Rebuild a ``RelGraph`` on ``device`` from ``graph_state`` output (only the hub plan is recomputed)."""
+    if state.get("csr_format") != 1:
+        raise ValueError("unknown CSR format")
+    g = RelGraph.__new__(RelGraph)
+    _lib.check(_lib.load().rgcn_check_device(), "rgcn_check_device")
+    g.n_dst, g.n_src, g.R, g.E = (int(state[k]) for k in ("csr_n_dst", "csr_n_src", "csr_num_relations", "csr_num_edges"))
+    g.device = torch.device(device)
+    for k in ("rowptr", "col", "perm", "rowptr_t", "row_t", "perm_t", "inv_cnt", "w_t"):
+        setattr(g, k, state[f"csr_{k}"].to(g.device).contiguous())
+    if g.rowptr.numel() != g.n_dst * g.R + 1 or g.col.numel() != g.E or int(g.rowptr[-1]) != g.E:
+        raise ValueError("inconsistent CSR state")
+    g.max_seg, g.max_seg_t = int(state["csr_max_seg"]), int(state["csr_max_seg_t"])
+    with torch.cuda.device(g.device):
+        g.fwd = _Orientation(g.rowptr, g.col, None, g.n_dst, g.R, g.E)
+        g.bwd = _Orientation(g.rowptr_t, g.row_t, g.w_t, g.n_src, g.R, g.E)
+    return g
+
+
+def register_graph(edge_index: torch.Tensor, edge_type: torch.Tensor, g: RelGraph) -> None:
+    """Seed the identity cache so ``model(edge_index, edge_type, ...)`` uses a pre-built / loaded graph."""
+    key = (edge_index.data_ptr(), edge_type.data_ptr(), tuple(edge_index.shape), edge_index.stride(),
+           str(edge_index.device), int(g.n_src), int(g.R))
+    _CACHE[key] = (g, weakref.ref(edge_index), weakref.ref(edge_type), edge_index._version, edge_type._version)

@@ -431,3 +431,97 @@ def test_graphed_step_matches_eager(pkg):
     perm = torch.randperm(b[0].numel(), device=DEV)
     l2 = step(b[0][perm], b[1][perm], b[2][perm], b[3][perm]).clone()
     torch.testing.assert_close(l2, got_loss, rtol=1e-5, atol=1e-6)      # same pairs, permuted => same mean loss
+
+
+def test_graph_state_round_trip(pkg, tmp_path):
+    """CSR + CSR^T stored next to edge_index (the reference's loaders ignore extra keys) and reloaded."""
+    ei, et, N, R = graphs()["primekg_100k"]
+    ei, et = ei.to(DEV), et.to(DEV)
+    g = pkg.RelGraph.from_edges(ei, et, N, R)
+    blob = {"edge_index": ei.cpu(), "edge_type": et.cpu(), "num_nodes": N, "num_relations": R, **pkg.graph_state(g)}
+    f = tmp_path / "full_graph.pt"
+    torch.save(blob, f)
+    back = torch.load(f)                                   # weights_only default: plain tensors / ints only
+    g2 = pkg.graph_from_state(back, DEV)
+    for k in ("rowptr", "col", "perm", "rowptr_t", "row_t", "perm_t", "inv_cnt", "w_t"):
+        assert torch.equal(getattr(g, k), getattr(g2, k)), k
+    assert (g2.fwd.n_hubs, g2.fwd.n_chunks, g2.bwd.n_hubs) == (g.fwd.n_hubs, g.fwd.n_chunks, g.bwd.n_hubs)
+    from primekg_rgcn_linkprediction_b200 import ops
+    x = torch.randn(N, 64, device=DEV)
+    assert torch.equal(ops.aggregate_fwd(g, x), ops.aggregate_fwd(g2, x))
+    pkg.clear_graph_cache()
+    pkg.register_graph(ei, et, g2)
+    assert pkg.get_graph(ei, et, N, R) is g2
+
+
+def test_trainer_loop_like_reference(pkg):
+    """The calls src/train.py makes, in its order (NegativeSampler :59-97, forward :291-297, BCEWithLogits :300,
+    backward :306, clip :311-315, Adam :317-318, eval forward :389-395), on our modules: parameters move, the loss
+    falls, and the first steps track the oracle trained the same way (dropout 0, same negatives)."""
+    from primekg_rgcn_linkprediction_b200 import synth
+    kg = synth.primekg_subgraph(60_000, seed=11)
+    torch.manual_seed(0)
+    model = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, 128, dropout=0.0, decoder_dropout=0.0)
+    ref = O.ModelRef(kg.num_nodes, kg.num_relations, 64, 128, 0.0, 0.0)
+    ref.load_state_dict(model.state_dict())
+    model.to(DEV); ref.to(DEV)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    crit = torch.nn.BCEWithLogitsLoss()
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    losses, ref_losses = [], []
+    for it in range(12):
+        sel = torch.randint(0, kg.num_edges, (512,), generator=g, device=DEV)
+        ph, pt, pr = ei[0, sel], ei[1, sel], et[sel]
+        corrupt = torch.rand(512, generator=g, device=DEV) < 0.5
+        rnd = torch.randint(0, kg.num_nodes, (512,), generator=g, device=DEV)
+        heads = torch.cat([ph, torch.where(corrupt, rnd, ph)])
+        tails = torch.cat([pt, torch.where(~corrupt, rnd, pt)])
+        rels = torch.cat([pr, pr])
+        labels = torch.cat([torch.ones(512, device=DEV), torch.zeros(512, device=DEV)])
+        for m, o, acc in ((model, opt, losses), (ref, opt_ref, ref_losses)):
+            m.train()
+            loss = crit(m(ei, et, heads, tails, rels), labels)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            o.step(); o.zero_grad()
+            acc.append(float(loss))
+    assert losses[-1] < losses[0] - 0.05, losses
+    for a, b in zip(losses[:6], ref_losses[:6]):
+        assert abs(a - b) < 2e-3 * max(1.0, abs(b)), (losses, ref_losses)
+    model.eval()
+    with torch.no_grad():
+        s = model(ei, et, heads, tails, rels)
+    assert torch.isfinite(s).all()
+
+
+def test_cfg3_full_size_basis_forward_backward(pkg):
+    """BASELINE cfg3: full-PrimeKG-shaped synthetic KG (129,375 nodes / ~8.1 M edges / 30 relations), basis
+    decomposition B = 8, one layer 64 -> 256 forward + backward against the oracle run on the same device."""
+    from primekg_rgcn_linkprediction_b200 import synth
+    kg = synth.primekg_full()
+    assert kg.num_nodes == 129_375 and kg.num_relations == 30 and kg.num_edges == 8_100_498
+    torch.manual_seed(3)
+    conv = pkg.RGCNConv(64, 256, 30, num_bases=8).to(DEV)
+    ref = O.RGCNConvRef(64, 256, 30, num_bases=8).to(DEV)
+    ref.load_state_dict(conv.state_dict())
+    x = (torch.randn(kg.num_nodes, 64, device=DEV) * 0.5).requires_grad_()
+    xr = x.detach().clone().requires_grad_()
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    coef = torch.randn(kg.num_nodes, 256, device=DEV)
+    out = conv(x, ei, et)
+    (out * coef).sum().backward()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        want = ref(xr, ei, et)
+        (want * coef).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    torch.testing.assert_close(out.detach(), want.detach(), rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+    for got, exp, name in ((x.grad, xr.grad, "x"), (conv.weight.grad, ref.weight.grad, "weight"),
+                           (conv.comp.grad, ref.comp.grad, "comp"), (conv.root.grad, ref.root.grad, "root"),
+                           (conv.bias.grad, ref.bias.grad, "bias")):
+        rel = float((got - exp).norm() / (exp.norm() + 1e-30))
+        assert rel < 1e-4, (name, rel)
