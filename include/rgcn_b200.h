@@ -225,6 +225,16 @@ int rgcn_allpairs_scores(const float* A, int64_t lda, int64_t na, const float* B
 int rgcn_allpairs_rank(const float* A, int64_t lda, int64_t nq, const float* B, int64_t ldb,
                        const int64_t* b_idx, int64_t nb, int32_t d, const int64_t* true_pos,
                        float* thr, int32_t* greater, int32_t* equal, rgcn_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * Fused link-prediction loss.  Replaces nn.BCEWithLogitsLoss (mean) over the batch logits and the
+ * sigmoid > 0.5 accuracy count (src/train.py:139, :300, :321-322):
+ *   loss = mean_i [ max(x,0) - x*y + log1p(exp(-|x|)) ],  n_correct = #{(x_i > 0) == y_i}   (one block, fixed order)
+ *   g_logits[i] = g_loss * (sigmoid(x_i) - y_i) / n
+ * ------------------------------------------------------------------------------------------ */
+int rgcn_bce_logits_fwd(const float* logits, const float* labels, int64_t n, float* loss,
+                        int32_t* n_correct, rgcn_stream_t stream);
+int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, const float* g_loss,
+                        float* g_logits, rgcn_stream_t stream);
 /* flag[0] = 1 when any head/tail is outside [0, n_nodes) or any rel outside [0, n_rel). */
 int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,
                      int64_t n_nodes, int32_t n_rel, int32_t* flag, rgcn_stream_t stream);

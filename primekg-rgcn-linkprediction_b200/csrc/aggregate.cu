@@ -164,6 +164,13 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
     }
   }
 
+  // A row's edges are contiguous in the CSR (sorted by (row, relation)).  The group keeps a window of G edge
+  // indices (and weights) in registers — one coalesced load per G edges — and hands them out by shuffle, so a batch
+  // of U row gathers costs ONE dependent memory latency instead of two (index, then row).
+  const int row_end = __ldg(p.rowptr + key0 + p.R);
+  int wbase = -(1 << 30), my_idx = 0;
+  float my_w = 1.f;
+
   for (int rbase = 0; rbase < p.R; rbase += G) {
     // the group's lanes fetch G consecutive (beg, end) pairs with two coalesced loads
     const int rl = rbase + lane;
@@ -200,11 +207,19 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
         for (int e = beg; e < end; e += U) {
           float4 v[U][VPL];
           float w[U];
+          if (e + U > wbase + G) {               // (re)fill the index window at e; uniform across the group
+            wbase = e;
+            const bool in = e + lane < row_end;
+            my_idx = in ? __ldg(p.idx + e + lane) : 0;
+            if (p.edge_w) my_w = in ? __ldg(p.edge_w + e + lane) : 0.f;
+          }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const bool ok = e + u < end;
-            const int j = ok ? __ldg(p.idx + e + u) : 0;
-            w[u] = (ok && p.edge_w) ? __ldg(p.edge_w + e + u) : 1.f;
+            const int sj = __shfl_sync(gmask, my_idx, (e + u - wbase) & (G - 1), G);
+            const float sw = __shfl_sync(gmask, my_w, (e + u - wbase) & (G - 1), G);
+            const int j = ok ? sj : 0;
+            w[u] = (ok && p.edge_w) ? sw : 1.f;
 #pragma unroll
             for (int k = 0; k < VPL; ++k) {
               const int vi = k * G + lane;

@@ -81,6 +81,48 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const float* __restri
   }
 }
 
+// loss = mean_i [ max(x,0) - x*y + log1p(exp(-|x|)) ]   (= torch BCEWithLogitsLoss, reference src/train.py:139, :300)
+// one block, fixed-order tree => deterministic; also counts sigmoid(x) > 0.5 == y (the accuracy of src/train.py:321-322)
+__global__ void __launch_bounds__(1024) bce_logits_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                              int64_t n, float* __restrict__ loss,
+                                                              int32_t* __restrict__ n_correct) {
+  __shared__ float sl[32];
+  __shared__ int sc[32];
+  float acc = 0.f;
+  int cor = 0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const float v = x[i], t = y[i];
+    acc += fmaxf(v, 0.f) - v * t + log1pf(expf(-fabsf(v)));
+    cor += ((v > 0.f) ? 1.f : 0.f) == t;
+  }
+  for (int o = 16; o; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    cor += __shfl_xor_sync(0xffffffffu, cor, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = acc; sc[threadIdx.x >> 5] = cor; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = sl[threadIdx.x]; cor = sc[threadIdx.x];
+    for (int o = 16; o; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      cor += __shfl_xor_sync(0xffffffffu, cor, o);
+    }
+    if (threadIdx.x == 0) {
+      *loss = acc / (float)n;
+      if (n_correct) *n_correct = cor;
+    }
+  }
+}
+
+// g_x[i] = g_loss * (sigmoid(x_i) - y_i) / n
+__global__ void bce_logits_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n,
+                                      const float* __restrict__ g_loss, float* __restrict__ g_x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = 1.f / (1.f + expf(-x[i]));
+  g_x[i] = (*g_loss) * (s - y[i]) / (float)n;
+}
+
 // 1 when any index is out of range
 __global__ void check_pairs_kernel(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,
                                    int64_t n_nodes, int32_t n_rel, int32_t* flag) {
@@ -146,6 +188,22 @@ extern "C" int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const 
   if (n_pairs == 0) return RGCN_OK;
   check_pairs_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(head, tail, rel, n_pairs,
                                                                                           n_nodes, n_rel, flag);
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_bce_logits_fwd(const float* logits, const float* labels, int64_t n, float* loss, int32_t* n_correct,
+                                   rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n > 0 && logits && labels && loss, "bce_logits_fwd: bad arguments");
+  bce_logits_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, n, loss, n_correct);
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, const float* g_loss,
+                                   float* g_logits, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n > 0 && logits && labels && g_loss && g_logits, "bce_logits_bwd: bad arguments");
+  bce_logits_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, labels, n, g_loss, g_logits);
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

@@ -414,46 +414,57 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   }
 }
 
-// fixed-order reduction of the split partials into gW1 [K1, N], gW2 [K2, N]
+// fixed-order reduction of the split partials into gW1 [K1, N], gW2 [K2, N]: 4 lanes per output float4, lane q adds
+// splits q, q+4, ... in order, then a fixed two-step shuffle combine (deterministic)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int m_pad,
                                                            int ldp, int K1, int K2, int N, float* __restrict__ gw1,
                                                            float* __restrict__ gw2) {
   const int64_t total = (int64_t)(K1 + K2) * (N >> 2);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / (N >> 2)), n = (int)(i % (N >> 2)) * 4;
+  const int q = threadIdx.x & 3;
+  const int64_t stride_i = (int64_t)gridDim.x * (blockDim.x >> 2);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); i < ((total + 7) & ~int64_t(7));
+       i += stride_i) {
+    const bool valid = i < total;
+    const int m = valid ? (int)(i / (N >> 2)) : 0, n = valid ? (int)(i % (N >> 2)) * 4 : 0;
     const float* src = partial + (size_t)m * ldp + n;
     const size_t stride = (size_t)m_pad * ldp;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    int sp = 0;
-    for (; sp + 4 <= splits; sp += 4) {          // 4 independent loads in flight, added in split order
-      const float4 a = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
-      const float4 b = *reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * stride);
-      const float4 c = *reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * stride);
-      const float4 d = *reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * stride);
-      add4(s, a); add4(s, b); add4(s, c); add4(s, d);
+    if (valid)
+      for (int sp = q; sp < splits; sp += 4) add4(s, *reinterpret_cast<const float4*>(src + (size_t)sp * stride));
+    for (int o = 1; o <= 2; o <<= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+      s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+      s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
+      s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
     }
-    for (; sp < splits; ++sp) add4(s, *reinterpret_cast<const float4*>(src + (size_t)sp * stride));
-    float* dst = (m < K1) ? gw1 + (size_t)m * N + n : gw2 + (size_t)(m - K1) * N + n;
-    *reinterpret_cast<float4*>(dst) = s;
+    if (valid && q == 0) {
+      float* dst = (m < K1) ? gw1 + (size_t)m * N + n : gw2 + (size_t)(m - K1) * N + n;
+      *reinterpret_cast<float4*>(dst) = s;
+    }
   }
 }
 
-// g_bias[n] = sum over the column-sum partials [n_part, N]: one warp per float4 column, lanes stride over the
-// partials, then a fixed shuffle tree => deterministic
+// g_bias[n] = sum over the column-sum partials [n_part, N]: one block per float4 column; thread t adds partials
+// t, t+256, ...; fixed shuffle tree inside each warp, then the 8 warp sums in order => deterministic
 __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int n_part, int N,
                                                             float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int c4 = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c4 >= (N >> 2)) return;
+  __shared__ float4 wsum[8];
+  const int c4 = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = lane; p < n_part; p += 32) add4(s, *reinterpret_cast<const float4*>(part + (size_t)p * N + c4 * 4));
+  for (int p = threadIdx.x; p < n_part; p += 256) add4(s, *reinterpret_cast<const float4*>(part + (size_t)p * N + c4 * 4));
   for (int o = 16; o; o >>= 1) {
     s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
     s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
     s.z += __shfl_xor_sync(0xffffffffu, s.z, o);
     s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
   }
-  if (lane == 0) *reinterpret_cast<float4*>(out + c4 * 4) = s;
+  if (lane == 0) wsum[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float4 t = wsum[0];
+    for (int w = 1; w < 8; ++w) add4(t, wsum[w]);
+    *reinterpret_cast<float4*>(out + c4 * 4) = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -755,11 +766,11 @@ extern "C" int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t 
     RGCN_LAUNCH_CHECK();
   }
   const int64_t total = (int64_t)K * (d_out / 4);
-  wgrad_reduce_kernel<<<grid_cap((total + 255) / 256, 4736), 256, 0, st>>>(p.partial, n_rows > 0 ? splits : 0, m_tiles * BM,
+  wgrad_reduce_kernel<<<grid_cap((total + 63) / 64, 4736), 256, 0, st>>>(p.partial, n_rows > 0 ? splits : 0, m_tiles * BM,
                                                                           t.n_pad, K1, K2, d_out, gW1, gW2);
   RGCN_LAUNCH_CHECK();
   if (gbias) {
-    colsum_reduce_kernel<<<(unsigned)((d_out / 4 + 7) / 8), 256, 0, st>>>(colsum_partial, n_colsum, d_out, gbias);
+    colsum_reduce_kernel<<<(unsigned)(d_out / 4), 256, 0, st>>>(colsum_partial, n_colsum, d_out, gbias);
     RGCN_LAUNCH_CHECK();
   }
   return RGCN_OK;

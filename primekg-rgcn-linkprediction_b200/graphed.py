@@ -14,7 +14,8 @@ from __future__ import annotations
 from typing import Callable, Optional
 
 import torch
-import torch.nn.functional as F
+
+from .ops import bce_with_logits
 
 
 class GraphedTrainStep:
@@ -24,7 +25,7 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors")
         dev = edge_index.device
         self.model, self.edge_index, self.edge_type = model, edge_index, edge_type
-        self.loss_fn = loss_fn or F.binary_cross_entropy_with_logits
+        self.loss_fn = loss_fn or bce_with_logits      # fused equivalent of nn.BCEWithLogitsLoss()
         self.heads = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.tails = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.rels = torch.zeros(batch_size, dtype=torch.int64, device=dev)

@@ -275,3 +275,37 @@ def transform_wgrad(a_planes, K1: int, K2: int, g_planes, d_out: int, colsum_par
                                         _ptr(gb), _mode_id(mode), _ptr(ws), ws.numel(), _stream(dev)),
                "rgcn_transform_wgrad")
     return gW1, gW2, gb
+
+
+# ---- fused BCE-with-logits (the loss of reference src/train.py:139, :300) ------------------------------
+class _BCEWithLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lib = _lib.load()
+        logits = logits.contiguous()
+        labels = labels.to(torch.float32).contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        correct = torch.empty((), dtype=torch.int32, device=logits.device)
+        _lib.check(lib.rgcn_bce_logits_fwd(_ptr(logits), _ptr(labels), logits.numel(), _ptr(loss), _ptr(correct),
+                                           _stream(logits.device)), "rgcn_bce_logits_fwd")
+        ctx.save_for_backward(logits, labels)
+        ctx.mark_non_differentiable(correct)
+        return loss, correct
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_correct):
+        lib = _lib.load()
+        logits, labels = ctx.saved_tensors
+        g = torch.empty_like(logits)
+        g_loss = g_loss.to(torch.float32).contiguous()
+        _lib.check(lib.rgcn_bce_logits_bwd(_ptr(logits), _ptr(labels), logits.numel(), _ptr(g_loss), _ptr(g),
+                                           _stream(logits.device)), "rgcn_bce_logits_bwd")
+        return g, None
+
+
+def bce_with_logits(logits: torch.Tensor, labels: torch.Tensor, with_accuracy: bool = False):
+    """Mean binary cross-entropy on logits in one kernel (+ the number of correct sigmoid > 0.5 predictions)."""
+    if not logits.is_cuda or logits.dtype != torch.float32 or logits.dim() != 1:
+        raise ValueError("bce_with_logits expects a 1-D float32 CUDA tensor of logits")
+    loss, correct = _BCEWithLogits.apply(logits, labels)
+    return (loss, correct) if with_accuracy else loss

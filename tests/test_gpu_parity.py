@@ -525,3 +525,18 @@ def test_cfg3_full_size_basis_forward_backward(pkg):
                            (conv.bias.grad, ref.bias.grad, "bias")):
         rel = float((got - exp).norm() / (exp.norm() + 1e-30))
         assert rel < 1e-4, (name, rel)
+
+
+def test_fused_bce_matches_torch(pkg):
+    from primekg_rgcn_linkprediction_b200 import ops
+    torch.manual_seed(8)
+    x = (torch.randn(2048, device=DEV) * 6).requires_grad_()
+    y = (torch.rand(2048, device=DEV) < 0.5).float()
+    xr = x.detach().clone().requires_grad_()
+    loss, correct = ops.bce_with_logits(x, y, with_accuracy=True)
+    (loss * 3.0).backward()
+    ref = F.binary_cross_entropy_with_logits(xr, y)
+    (ref * 3.0).backward()
+    torch.testing.assert_close(loss, ref, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(x.grad, xr.grad, rtol=1e-5, atol=1e-9)
+    assert int(correct) == int(((torch.sigmoid(xr) > 0.5).float() == y).sum())      # reference src/train.py:321-322
