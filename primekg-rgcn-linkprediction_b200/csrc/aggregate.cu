@@ -136,7 +136,8 @@ template <int G, int VPL, int MIX>
 __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
   constexpr int GROUPS = 256 / G;
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
-  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  constexpr int U = U0 < G ? U0 : G;             // a batch never exceeds the G-edge index window
   extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS
   if (MIX == MIX_BASIS) {
     for (int t = threadIdx.x; t < p.R * p.B; t += 256) s_comp[t] = p.comp[(t / p.B) * p.ldcomp + (t % p.B)];
@@ -164,12 +165,13 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
     }
   }
 
-  // A row's edges are contiguous in the CSR (sorted by (row, relation)).  The group keeps a window of G edge
-  // indices (and weights) in registers — one coalesced load per G edges — and hands them out by shuffle, so a batch
-  // of U row gathers costs ONE dependent memory latency instead of two (index, then row).
+  // A row's edges are contiguous in the CSR (sorted by (row, relation)).  The group keeps a window of 2*G edge
+  // indices (and weights) in registers — loaded once per row for rows of up to 2*G edges, with two coalesced loads
+  // issued back to back — and hands them out by shuffle, so a batch of U row gathers costs ONE dependent memory
+  // latency instead of two (index, then row).
   const int row_end = __ldg(p.rowptr + key0 + p.R);
-  int wbase = -(1 << 30), my_idx = 0;
-  float my_w = 1.f;
+  int wbase = -(1 << 30), wi0 = 0, wi1 = 0;
+  float ww0 = 1.f, ww1 = 1.f;
 
   for (int rbase = 0; rbase < p.R; rbase += G) {
     // the group's lanes fetch G consecutive (beg, end) pairs with two coalesced loads
@@ -207,17 +209,23 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
         for (int e = beg; e < end; e += U) {
           float4 v[U][VPL];
           float w[U];
-          if (e + U > wbase + G) {               // (re)fill the index window at e; uniform across the group
+          if (e + U > wbase + 2 * G) {           // (re)fill the index window at e; uniform across the group
             wbase = e;
-            const bool in = e + lane < row_end;
-            my_idx = in ? __ldg(p.idx + e + lane) : 0;
-            if (p.edge_w) my_w = in ? __ldg(p.edge_w + e + lane) : 0.f;
+            const bool in0 = e + lane < row_end, in1 = e + G + lane < row_end;
+            wi0 = in0 ? __ldg(p.idx + e + lane) : 0;
+            wi1 = in1 ? __ldg(p.idx + e + G + lane) : 0;
+            if (p.edge_w) {
+              ww0 = in0 ? __ldg(p.edge_w + e + lane) : 0.f;
+              ww1 = in1 ? __ldg(p.edge_w + e + G + lane) : 0.f;
+            }
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const bool ok = e + u < end;
-            const int sj = __shfl_sync(gmask, my_idx, (e + u - wbase) & (G - 1), G);
-            const float sw = __shfl_sync(gmask, my_w, (e + u - wbase) & (G - 1), G);
+            const int off = e + u - wbase;                       // uniform across the group
+            const int sj = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
+            float sw = 1.f;
+            if (p.edge_w) sw = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
             const int j = ok ? sj : 0;
             w[u] = (ok && p.edge_w) ? sw : 1.f;
 #pragma unroll
