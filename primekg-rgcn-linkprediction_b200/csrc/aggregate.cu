@@ -16,6 +16,8 @@
 // into kHubChunk-edge chunks that whole blocks reduce beforehand (hub_partial_kernel) into a
 // partial buffer; the row kernel then adds the chunk partials in chunk order.  Everything is
 // deterministic: same bits on every run.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace rgcn {
@@ -49,8 +51,8 @@ struct AggParams {
 };
 
 // ---- hub chunks: one block per chunk --------------------------------------------------------
-template <int G, int VPL>
-__global__ void __launch_bounds__(256) hub_partial_kernel(AggParams p) {
+template <int G, int VPL, bool W>
+__global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
   constexpr int GROUPS = 256 / G;
   __shared__ float4 red[GROUPS][G * VPL];
   const int chunk = blockIdx.x;
@@ -72,30 +74,46 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(AggParams p) {
   constexpr int PER = kHubChunk / GROUPS;
   const int g_beg = c_beg + grp * PER, g_end = min(g_beg + PER, c_end);
   float4 acc[VPL];
+  int vcol[VPL];
 #pragma unroll
-  for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* Fb = p.F + (size_t)r * p.src_rel_stride;
-  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
-  for (int e = g_beg; e < g_end; e += U) {
+  for (int k = 0; k < VPL; ++k) {
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int vi = k * G + lane;
+    vcol[k] = vi < nvec ? vi * 4 : 0;
+  }
+  const float* __restrict__ Fb = p.F + (size_t)r * p.src_rel_stride;
+  const int32_t* __restrict__ idx = p.idx;
+  const float* __restrict__ ew = p.edge_w;
+  const int64_t ldf = p.ldf;
+  constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  constexpr int U = U0 < PER ? U0 : PER;
+  int e = g_beg;
+  for (; e + U <= g_end; e += U) {
     float4 v[U][VPL];
     float w[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool ok = e + u < g_end;
-      const int j = ok ? __ldg(p.idx + e + u) : 0;
-      w[u] = (ok && p.edge_w) ? __ldg(p.edge_w + e + u) : 1.f;
+      const int j = __ldg(idx + e + u);
+      if (W) w[u] = __ldg(ew + e + u);
+      const float* __restrict__ rp = Fb + (size_t)j * ldf;
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) {
-        const int vi = k * G + lane;
-        v[u][k] = (ok && vi < nvec) ? ldg4(Fb + (size_t)j * p.ldf + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int k = 0; k < VPL; ++k) v[u][k] = ldg4(rp + vcol[k]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        if (p.edge_w) fma4(acc[k], w[u], v[u][k]); else add4(acc[k], v[u][k]);
+        if (W) fma4(acc[k], w[u], v[u][k]); else add4(acc[k], v[u][k]);
       }
+  }
+  for (; e < g_end; ++e) {
+    const int j = __ldg(idx + e);
+    const float* __restrict__ rp = Fb + (size_t)j * ldf;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const float4 v = ldg4(rp + vcol[k]);
+      if (W) fma4(acc[k], __ldg(ew + e), v); else add4(acc[k], v);
+    }
   }
 #pragma unroll
   for (int k = 0; k < VPL; ++k) red[grp][k * G + lane] = acc[k];
@@ -132,12 +150,15 @@ __device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int c
 }
 
 // ---- rows: one G-lane group per row ----------------------------------------------------------
-template <int G, int VPL, int MIX>
-__global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
+// The inner loop is instruction-issue sensitive (16 B per lane per edge): parameters are hoisted into registers,
+// the edge weights are a template flag, full batches of U edges run without any predicate, inactive lanes of a
+// ragged feature width read column 0 instead of being masked, and only the tail batch is guarded.
+template <int G, int VPL, int MIX, bool W>
+__global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) {
   constexpr int GROUPS = 256 / G;
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
   constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
-  constexpr int U = U0 < G ? U0 : G;             // a batch never exceeds the G-edge index window
+  constexpr int U = U0 < G ? U0 : G;             // a batch never exceeds the index window
   extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS
   if (MIX == MIX_BASIS) {
     for (int t = threadIdx.x; t < p.R * p.B; t += 256) s_comp[t] = p.comp[(t / p.B) * p.ldcomp + (t % p.B)];
@@ -145,10 +166,24 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
   }
   const int lane = threadIdx.x % G, grp = threadIdx.x / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-  const int nvec = p.d >> 2;
   const int64_t row = (int64_t)blockIdx.x * GROUPS + grp;
   if (row >= p.n_rows) return;
-  const int64_t key0 = row * p.R;
+  const int R = p.R, d = p.d, nvec = p.d >> 2;
+  const int64_t key0 = row * R;
+  const int32_t* __restrict__ rowptr = p.rowptr + key0;
+  const int32_t* __restrict__ idx = p.idx;
+  const float* __restrict__ ew = p.edge_w;
+  const float* __restrict__ F = p.F;
+  const int64_t ldf = p.ldf;
+  const int rel_stride = p.src_rel_stride;
+  bool act[VPL];
+  int vcol[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = k * G + lane;
+    act[k] = vi < nvec;
+    vcol[k] = act[k] ? vi * 4 : 0;               // inactive lanes gather column 0; their sums are never stored
+  }
 
   float4 mix[NB][VPL];
   if (MIX != MIX_NONE) {
@@ -158,27 +193,32 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
       for (int k = 0; k < VPL; ++k) mix[b][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (MIX == MIX_SUM && p.init) {
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) {
-        const int vi = k * G + lane;
-        if (vi < nvec) mix[0][k] = ldg4(p.init + row * p.ld_init + vi * 4);
-      }
+      for (int k = 0; k < VPL; ++k) mix[0][k] = ldg4(p.init + row * p.ld_init + vcol[k]);
     }
   }
 
   // A row's edges are contiguous in the CSR (sorted by (row, relation)).  The group keeps a window of 2*G edge
-  // indices (and weights) in registers — loaded once per row for rows of up to 2*G edges, with two coalesced loads
-  // issued back to back — and hands them out by shuffle, so a batch of U row gathers costs ONE dependent memory
-  // latency instead of two (index, then row).
-  const int row_end = __ldg(p.rowptr + key0 + p.R);
+  // indices (and weights) in registers — two coalesced loads issued back to back — and hands them out by shuffle.
+  const int row_end = __ldg(rowptr + R);
   int wbase = -(1 << 30), wi0 = 0, wi1 = 0;
   float ww0 = 1.f, ww1 = 1.f;
+  auto refill = [&](int e) {
+    wbase = e;
+    const bool in0 = e + lane < row_end, in1 = e + G + lane < row_end;
+    wi0 = in0 ? __ldg(idx + e + lane) : 0;
+    wi1 = in1 ? __ldg(idx + e + G + lane) : 0;
+    if (W) {
+      ww0 = in0 ? __ldg(ew + e + lane) : 0.f;
+      ww1 = in1 ? __ldg(ew + e + G + lane) : 0.f;
+    }
+  };
 
-  for (int rbase = 0; rbase < p.R; rbase += G) {
+  for (int rbase = 0; rbase < R; rbase += G) {
     // the group's lanes fetch G consecutive (beg, end) pairs with two coalesced loads
     const int rl = rbase + lane;
-    const int my_beg = (rl < p.R) ? __ldg(p.rowptr + key0 + rl) : 0;
-    const int my_end = (rl < p.R) ? __ldg(p.rowptr + key0 + rl + 1) : 0;
-    const int rcount = min(G, p.R - rbase);
+    const int my_beg = (rl < R) ? __ldg(rowptr + rl) : 0;
+    const int my_end = (rl < R) ? __ldg(rowptr + rl + 1) : 0;
+    const int rcount = min(G, R - rbase);
     for (int rr = 0; rr < rcount; ++rr) {
       const int r = rbase + rr;
       const int beg = __shfl_sync(gmask, my_beg, rr, G);
@@ -199,60 +239,49 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
         const int c0 = __ldg(p.hub_chunk_ptr + lo), c1 = __ldg(p.hub_chunk_ptr + lo + 1);
         for (int c = c0; c < c1; ++c) {
 #pragma unroll
-          for (int k = 0; k < VPL; ++k) {
-            const int vi = k * G + lane;
-            if (vi < nvec) add4(acc[k], reinterpret_cast<const float4*>(p.partials + (size_t)c * p.d)[vi]);
-          }
+          for (int k = 0; k < VPL; ++k) add4(acc[k], *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k]));
         }
       } else if (len > 0) {
-        const float* Fb = p.F + (size_t)r * p.src_rel_stride;
-        for (int e = beg; e < end; e += U) {
-          float4 v[U][VPL];
-          float w[U];
-          if (e + U > wbase + 2 * G) {           // (re)fill the index window at e; uniform across the group
-            wbase = e;
-            const bool in0 = e + lane < row_end, in1 = e + G + lane < row_end;
-            wi0 = in0 ? __ldg(p.idx + e + lane) : 0;
-            wi1 = in1 ? __ldg(p.idx + e + G + lane) : 0;
-            if (p.edge_w) {
-              ww0 = in0 ? __ldg(p.edge_w + e + lane) : 0.f;
-              ww1 = in1 ? __ldg(p.edge_w + e + G + lane) : 0.f;
-            }
+        const float* __restrict__ Fb = F + (size_t)r * rel_stride;
+        // full batches of U edges, then power-of-two remainders: every batch is straight-line code with
+        // unconditional loads, nothing is gathered twice and nothing is masked
+        int e = beg;
+        auto batch = [&](auto ub) {
+          constexpr int UB = decltype(ub)::value;
+          if (e + UB > wbase + 2 * G) refill(e);
+          float4 v[UB][VPL];
+          float w[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int off = e + u - wbase;         // uniform across the group, < 2 * G
+            const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
+            if (W) w[u] = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
+            const float* __restrict__ rp = Fb + (size_t)j * ldf;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) v[u][k] = ldg4(rp + vcol[k]);
           }
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const bool ok = e + u < end;
-            const int off = e + u - wbase;                       // uniform across the group
-            const int sj = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
-            float sw = 1.f;
-            if (p.edge_w) sw = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
-            const int j = ok ? sj : 0;
-            w[u] = (ok && p.edge_w) ? sw : 1.f;
+          for (int u = 0; u < UB; ++u)
 #pragma unroll
             for (int k = 0; k < VPL; ++k) {
-              const int vi = k * G + lane;
-              v[u][k] = (ok && vi < nvec) ? ldg4(Fb + (size_t)j * p.ldf + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (W) fma4(acc[k], w[u], v[u][k]); else add4(acc[k], v[u][k]);
             }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-              if (p.edge_w) fma4(acc[k], w[u], v[u][k]); else add4(acc[k], v[u][k]);
-            }
-        }
+          e += UB;
+        };
+        while (e + U <= end) batch(std::integral_constant<int, U>{});
+        if (U > 4 && e + 4 <= end) batch(std::integral_constant<int, (U > 4 ? 4 : 1)>{});
+        if (U > 2 && e + 2 <= end) batch(std::integral_constant<int, (U > 2 ? 2 : 1)>{});
+        if (e < end) batch(std::integral_constant<int, 1>{});
       }
-      if (!p.edge_w && len > 1) {
+      if (!W && len > 1) {
         const float c = (float)len;   // s / clamp(cnt, 1): a true division, like the reference
 #pragma unroll
         for (int k = 0; k < VPL; ++k) acc[k] = div4(acc[k], c);
       }
       if (MIX == MIX_NONE) {
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const int vi = k * G + lane;
-          if (vi < nvec) store_vec(p, row, r * p.d + vi * 4, acc[k]);
-        }
+        for (int k = 0; k < VPL; ++k)
+          if (act[k]) store_vec(p, row, r * d + vcol[k], acc[k]);
       } else if (MIX == MIX_SUM) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k) add4(mix[0][k], acc[k]);
@@ -273,10 +302,8 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(AggParams p) {
     for (int b = 0; b < NB; ++b) {
       if (b < p.B) {
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const int vi = k * G + lane;
-          if (vi < nvec) store_vec(p, row, b * p.d + vi * 4, mix[b][k]);
-        }
+        for (int k = 0; k < VPL; ++k)
+          if (act[k]) store_vec(p, row, b * d + vcol[k], mix[b][k]);
       }
     }
   }
@@ -286,17 +313,23 @@ template <int G, int VPL>
 static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
   if (n_chunks > 0) {
-    hub_partial_kernel<G, VPL><<<n_chunks, 256, 0, st>>>(p);
+    if (p.edge_w) hub_partial_kernel<G, VPL, true><<<n_chunks, 256, 0, st>>>(p);
+    else hub_partial_kernel<G, VPL, false><<<n_chunks, 256, 0, st>>>(p);
     RGCN_LAUNCH_CHECK();
   }
   if (p.n_rows == 0) return RGCN_OK;
   const unsigned grid = (unsigned)((p.n_rows + GROUPS - 1) / GROUPS);
+  const bool w = p.edge_w != nullptr;
+  const size_t sm = (size_t)p.R * p.B * sizeof(float);
   if (mix == MIX_NONE) {
-    aggregate_rows_kernel<G, VPL, MIX_NONE><<<grid, 256, 0, st>>>(p);
+    if (w) aggregate_rows_kernel<G, VPL, MIX_NONE, true><<<grid, 256, 0, st>>>(p);
+    else aggregate_rows_kernel<G, VPL, MIX_NONE, false><<<grid, 256, 0, st>>>(p);
   } else if (mix == MIX_SUM) {
-    aggregate_rows_kernel<G, VPL, MIX_SUM><<<grid, 256, 0, st>>>(p);
+    if (w) aggregate_rows_kernel<G, VPL, MIX_SUM, true><<<grid, 256, 0, st>>>(p);
+    else aggregate_rows_kernel<G, VPL, MIX_SUM, false><<<grid, 256, 0, st>>>(p);
   } else {
-    aggregate_rows_kernel<G, VPL, MIX_BASIS><<<grid, 256, (size_t)p.R * p.B * sizeof(float), st>>>(p);
+    if (w) aggregate_rows_kernel<G, VPL, MIX_BASIS, true><<<grid, 256, sm, st>>>(p);
+    else aggregate_rows_kernel<G, VPL, MIX_BASIS, false><<<grid, 256, sm, st>>>(p);
   }
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
