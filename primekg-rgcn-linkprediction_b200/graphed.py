@@ -31,9 +31,13 @@ class GraphedTrainStep:
         self.rels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
-        for p in self.params:                                   # static gradient buffers
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
+        # static gradient buffers: views into ONE flat tensor, so zeroing is a single fill and a data-parallel
+        # caller all-reduces ``flat_grad`` in place (every p.grad sees the result)
+        self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -46,8 +50,7 @@ class GraphedTrainStep:
             self.loss, self.scores = self._step()
 
     def _step(self):
-        for p in self.params:
-            p.grad.zero_()
+        self.flat_grad.zero_()
         scores = self.model(self.edge_index, self.edge_type, self.heads, self.tails, self.rels)
         loss = self.loss_fn(scores, self.labels)
         loss.backward()
