@@ -129,55 +129,62 @@ __global__ void split_weights_kernel(const float* __restrict__ w1, int K1, const
 struct GemmKParams {
   int64_t M;
   int N;                                      // valid output columns
-  int BN;                                     // tile width: multiple of 32, <= 256
+  int BN;                                     // tile width: multiple of 32, <= 128
+  int n_tiles;                                // column tiles
   int num_kb;                                 // K blocks of 64 (TMA zero-fills past the true K)
   const float* bias; int relu;
   float* out; int64_t ldo;
 };
 
+constexpr int KBN = 128;                      // N tile of the persistent kernel: two accumulators fit 256 TMEM columns
+constexpr int K_EPI_WARPS = 4;
+constexpr int K_PATCH = 32 * 36 * 4;          // per-warp transpose patch: 32 rows x (32 + 4) floats
+
 template <bool SPLIT>
 struct KStage {
   static constexpr int A_BYTES = BM * 128;              // 128 rows x 64 bf16
-  static constexpr int B_BYTES = BNMAX * 128;
+  static constexpr int B_BYTES = KBN * 128;
   static constexpr int BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = SPLIT ? 2 : 4;
+  static constexpr int STAGES = SPLIT ? 3 : 6;
   static constexpr int A_HI = 0, A_LO = A_BYTES;
   static constexpr int B_HI = (SPLIT ? 2 : 1) * A_BYTES, B_LO = B_HI + B_BYTES;
+  static constexpr int SMEM = STAGES * BYTES + K_EPI_WARPS * K_PATCH + 1024;
 };
 
-constexpr int K_EPI = 256;   // 8 epilogue warps
-
+// Persistent, warp-specialised: CTA c walks tiles c, c + grid, ... (column tile fastest, so neighbouring CTAs share
+// the A rows in L2).  The smem ring and the two TMEM accumulators are continuous across tiles: the MMA warp starts
+// tile i+1 while the epilogue warps drain tile i.
 template <bool SPLIT>
-__global__ void __launch_bounds__(K_EPI + 64, 1)
+__global__ void __launch_bounds__(192, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmKParams p) {
   using S = KStage<SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[S::STAGES], empty_bar[S::STAGES], accum_bar;
+  __shared__ uint64_t full_bar[S::STAGES], empty_bar[S::STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_bias[BNMAX];
+  __shared__ __align__(16) float s_bias[1024];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-  const int64_t m0 = (int64_t)m_tile * BM;
-  const int n0 = n_tile * p.BN;
-  const uint32_t tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  const int64_t m_tiles = (p.M + BM - 1) / BM;
+  const int64_t n_tiles_total = m_tiles * p.n_tiles;
+  const uint32_t acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;     // columns of one accumulator
+  const uint32_t tmem_cols = 2 * acc_cols;
 
-  if (threadIdx.x < BNMAX) {
-    const int n = n0 + threadIdx.x;
-    s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.BN && n < p.N) ? p.bias[n] : 0.f;
-  }
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);               // the TMA thread's arrive.expect_tx
       mbar_init(&empty_bar[s], 1);              // one tcgen05.commit
     }
-    mbar_init(&accum_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);              // tcgen05.commit after the tile's last MMA
+      mbar_init(&tempty_bar[a], K_EPI_WARPS);   // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_b_hi);
     if (SPLIT) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
@@ -188,56 +195,67 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp < 8) {
-    // ===================== epilogue =====================
-    // TMEM -> registers (+ bias, ReLU) -> staging tile in the (now idle) operand smem -> coalesced row stores.
-    // Warps w and w+4 share TMEM lane quadrant w and alternate 32-column chunks.
-    mbar_wait(&accum_bar, 0);
-    fence_after_sync();
-    const int q = warp & 3, half = warp >> 2;
-    const int pitch = p.BN + 4;                      // floats; +4 keeps the float4 row stores bank-conflict free
-    float* stile = reinterpret_cast<float*>(smem);
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* srow = stile + (size_t)(q * 32 + lane) * pitch;
-    for (int cc = half * 32; cc < p.BN; cc += 64) {
-      uint32_t r[32];
-      tmem_ld_32x32(t_lane + cc, r);
-      tmem_ld_wait();
+  if (warp < K_EPI_WARPS) {
+    // ===================== epilogue: warp w owns TMEM lanes 32w .. 32w+31 =====================
+    float* patch = reinterpret_cast<float*>(smem + (size_t)S::STAGES * S::BYTES + (size_t)warp * K_PATCH);
+    int iter = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++iter) {
+      const int64_t m0 = (t / p.n_tiles) * BM;
+      const int n0 = (int)(t % p.n_tiles) * p.BN;
+      const int a = iter & 1;
+      mbar_wait(&tfull_bar[a], (uint32_t)((iter >> 1) & 1));
+      fence_after_sync();
+      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * acc_cols;
+      for (int cc = 0; cc < p.BN; cc += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_lane + cc, r);
+        tmem_ld_wait();
+        // registers (one row per lane) -> patch, + bias / ReLU
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(s_bias + cc + j);
-        float4 qv = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
-                                __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
-        if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
-        *reinterpret_cast<float4*>(srow + cc + j) = qv;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(s_bias + ((n0 + cc + j) & 1023));
+          float4 qv = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
+                                  __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
+          if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
+          *reinterpret_cast<float4*>(patch + lane * 36 + j) = qv;
+        }
+        __syncwarp();
+        // patch -> global: each instruction writes 4 rows x 128 contiguous bytes
+        const int c4 = (lane & 7) * 4;
+        const bool col_ok = n0 + cc + c4 < p.N;
+#pragma unroll
+        for (int rr = 0; rr < 32; rr += 4) {
+          const int rl = rr + (lane >> 3);
+          const int64_t row = m0 + warp * 32 + rl;
+          if (row < p.M && col_ok)
+            *reinterpret_cast<float4*>(p.out + row * p.ldo + n0 + cc + c4) =
+                *reinterpret_cast<const float4*>(patch + rl * 36 + c4);
+        }
+        __syncwarp();
       }
+      fence_before_sync();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);       // accumulator a may be overwritten
     }
-    fence_before_sync();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int ncol4 = min(p.BN, p.N - n0) >> 2;      // valid float4 columns of this tile
-    for (int rl = warp; rl < BM; rl += 8) {
-      const int64_t row = m0 + rl;
-      if (row >= p.M) break;
-      const float* src = stile + (size_t)rl * pitch;
-      float* dst = p.out + row * p.ldo + n0;
-      for (int c4 = lane; c4 < ncol4; c4 += 32)
-        *reinterpret_cast<float4*>(dst + c4 * 4) = *reinterpret_cast<const float4*>(src + c4 * 4);
-    }
-  } else if (warp == 8) {
+  } else if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(BM + p.BN) * 128u * (SPLIT ? 2u : 1u);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);      // slot free (passes immediately on the first round)
-        uint8_t* st = smem + (size_t)s * S::BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        tma_load_2d(st + S::A_HI, &tm_a_hi, &full_bar[s], kb * BK, (int)m0);
-        tma_load_2d(st + S::B_HI, &tm_b_hi, &full_bar[s], kb * BK, n0);
-        if (SPLIT) {
-          tma_load_2d(st + S::A_LO, &tm_a_lo, &full_bar[s], kb * BK, (int)m0);
-          tma_load_2d(st + S::B_LO, &tm_b_lo, &full_bar[s], kb * BK, n0);
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
+        const int m0 = (int)((t / p.n_tiles) * BM);
+        const int n0 = (int)(t % p.n_tiles) * p.BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);      // slot free (passes immediately on the first round)
+          uint8_t* st = smem + (size_t)s * S::BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          tma_load_2d(st + S::A_HI, &tm_a_hi, &full_bar[s], kb * BK, m0);
+          tma_load_2d(st + S::B_HI, &tm_b_hi, &full_bar[s], kb * BK, n0);
+          if (SPLIT) {
+            tma_load_2d(st + S::A_LO, &tm_a_lo, &full_bar[s], kb * BK, m0);
+            tma_load_2d(st + S::B_LO, &tm_b_lo, &full_bar[s], kb * BK, n0);
+          }
         }
       }
     }
@@ -245,28 +263,36 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16(BM, p.BN, 0, 0);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % S::STAGES;
-        const uint32_t ph = (kb / S::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0;
+      int iter = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++iter) {
+        const int a = iter & 1;
+        mbar_wait(&tempty_bar[a], (uint32_t)(((iter >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
         fence_after_sync();
-        const uint32_t base = smem_u32(smem + (size_t)s * S::BYTES);
-        const uint64_t da_hi = smem_desc_sw128(base + S::A_HI, 16, 1024);
-        const uint64_t db_hi = smem_desc_sw128(base + S::B_HI, 16, 1024);
-        const uint64_t da_lo = smem_desc_sw128(base + S::A_LO, 16, 1024);
-        const uint64_t db_lo = smem_desc_sw128(base + S::B_LO, 16, 1024);
+        const uint32_t tacc = tmem_base + (uint32_t)a * acc_cols;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % S::STAGES;
+          const uint32_t ph = (it / S::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          fence_after_sync();
+          const uint32_t base = smem_u32(smem + (size_t)s * S::BYTES);
+          const uint64_t da_hi = smem_desc_sw128(base + S::A_HI, 16, 1024);
+          const uint64_t db_hi = smem_desc_sw128(base + S::B_HI, 16, 1024);
+          const uint64_t da_lo = smem_desc_sw128(base + S::A_LO, 16, 1024);
+          const uint64_t db_lo = smem_desc_sw128(base + S::B_LO, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 16 bf16 = 32 bytes along K inside the swizzle row
-          mma_bf16_ss(tmem_base, da_hi + adv, db_hi + adv, idesc, (kb | k) ? 1u : 0u);
-          if (SPLIT) {
-            mma_bf16_ss(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-            mma_bf16_ss(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 16 bf16 = 32 bytes along K inside the swizzle row
+            mma_bf16_ss(tacc, da_hi + adv, db_hi + adv, idesc, (kb | k) ? 1u : 0u);
+            if (SPLIT) {
+              mma_bf16_ss(tacc, da_hi + adv, db_lo + adv, idesc, 1u);
+              mma_bf16_ss(tacc, da_lo + adv, db_hi + adv, idesc, 1u);
+            }
           }
+          mma_commit(&empty_bar[s]);            // frees the stage once these MMAs have read it
         }
-        mma_commit(&empty_bar[s]);            // frees the stage once these MMAs have read it
+        mma_commit(&tfull_bar[a]);              // this tile's accumulator is complete
       }
-      mma_commit(&accum_bar);                 // accumulator complete
     }
   }
   __syncthreads();
@@ -528,10 +554,10 @@ static unsigned grid_cap(int64_t blocks, int64_t cap) { return (unsigned)(blocks
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 struct Tiling { int n_tiles, BN, n_pad; };
-static Tiling tile_n(int N, int gran) {
+static Tiling tile_n(int N, int gran, int bn_max = BNMAX) {
   Tiling t;
   const int np = round_up(N, gran);
-  t.n_tiles = (np + BNMAX - 1) / BNMAX;
+  t.n_tiles = (np + bn_max - 1) / bn_max;
   t.BN = round_up((np + t.n_tiles - 1) / t.n_tiles, gran);
   t.n_pad = t.n_tiles * t.BN;
   return t;
@@ -559,7 +585,7 @@ static int check_plane(const void* p, int64_t ld, const char* what) {
 }
 
 // out[M, N] = A @ B^T with A planes [M, K] (ld lda) and weight planes [n_pad, k_pad]
-static int launch_kmajor(const GemmKParams& p, const void* a_hi, const void* a_lo, int64_t lda, int K,
+static int launch_kmajor(GemmKParams p, const void* a_hi, const void* a_lo, int64_t lda, int K,
                          const __nv_bfloat16* bhi, const __nv_bfloat16* blo, int n_pad, int k_pad, int n_tiles, bool split,
                          cudaStream_t st) {
   CUtensorMap ahi, alo, mhi, mlo;
@@ -571,17 +597,17 @@ static int launch_kmajor(const GemmKParams& p, const void* a_hi, const void* a_l
   if (rc) return rc;
   rc = make_map(&mlo, split ? blo : bhi, n_pad, k_pad, k_pad, p.BN);
   if (rc) return rc;
-  dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)n_tiles);
+  p.n_tiles = n_tiles;
+  const int64_t tiles = ((p.M + BM - 1) / BM) * n_tiles;
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
   if (split) {
-    const int smem = KStage<true>::STAGES * KStage<true>::BYTES + 1024;
-    rc = set_smem(gemm_kmajor_kernel<true>, smem);
+    rc = set_smem(gemm_kmajor_kernel<true>, KStage<true>::SMEM);
     if (rc) return rc;
-    gemm_kmajor_kernel<true><<<grid, K_EPI + 64, smem, st>>>(ahi, alo, mhi, mlo, p);
+    gemm_kmajor_kernel<true><<<grid, 192, KStage<true>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
   } else {
-    const int smem = KStage<false>::STAGES * KStage<false>::BYTES + 1024;
-    rc = set_smem(gemm_kmajor_kernel<false>, smem);
+    rc = set_smem(gemm_kmajor_kernel<false>, KStage<false>::SMEM);
     if (rc) return rc;
-    gemm_kmajor_kernel<false><<<grid, K_EPI + 64, smem, st>>>(ahi, alo, mhi, mlo, p);
+    gemm_kmajor_kernel<false><<<grid, 192, KStage<false>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
   }
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
@@ -632,8 +658,8 @@ extern "C" int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_
 extern "C" size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K, int32_t d_out) {
   if (n_rows < 0 || K <= 0 || d_out <= 0) return 0;
   // forward: weights^T [n_pad(d_out), k_pad(K)];  dgrad: weights [n_pad(K), k_pad(d_out)];  2 bf16 planes each
-  const size_t fwd = (size_t)tile_n(d_out, 32).n_pad * round_up(K, BK) * 2 * 2;
-  const size_t dgr = (size_t)tile_n(K, 32).n_pad * round_up(d_out, BK) * 2 * 2;
+  const size_t fwd = (size_t)tile_n(d_out, 32, KBN).n_pad * round_up(K, BK) * 2 * 2;
+  const size_t dgr = (size_t)tile_n(K, 32, KBN).n_pad * round_up(d_out, BK) * 2 * 2;
   const Tiling t = tile_n(d_out, 64);
   const int m_tiles = (K + BM - 1) / BM;
   const int splits = wgrad_splits(n_rows, m_tiles * t.n_tiles);
@@ -657,7 +683,8 @@ extern "C" int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t ld
   RGCN_CHECK_ARG(W1 && (K2 == 0 || W2) && (!bias || ((uintptr_t)bias & 3) == 0), "transform_fwd: null weights");
   if (n_rows == 0) return RGCN_OK;
   const int K = K1 + K2, k_pad = round_up(K, BK);
-  const Tiling t = tile_n(d_out, 32);
+  const Tiling t = tile_n(d_out, 32, KBN);
+  RGCN_CHECK_ARG(!bias || d_out <= 1024, "transform_fwd: bias needs d_out <= 1024");
   const size_t plane = (size_t)t.n_pad * k_pad * 2;
   if (!workspace || workspace_bytes < align_up(2 * plane, 256) + 1024) {
     set_error("transform_fwd: workspace too small"); return RGCN_EWORKSPACE;
@@ -693,7 +720,7 @@ extern "C" int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t 
   if (n_rows == 0) return RGCN_OK;
   const int K = K1 + K2;                      // = N of this GEMM
   const int k_pad = round_up(d_out, BK);      // = K of this GEMM
-  const Tiling t = tile_n(K, 32);
+  const Tiling t = tile_n(K, 32, KBN);
   const size_t plane = (size_t)t.n_pad * k_pad * 2;
   if (!workspace || workspace_bytes < align_up(2 * plane, 256) + 1024) {
     set_error("transform_dgrad: workspace too small"); return RGCN_EWORKSPACE;
