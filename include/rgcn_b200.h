@@ -85,7 +85,7 @@ int rgcn_csr_build(const int64_t* src, const int64_t* dst, const int64_t* rel, i
 
 /* ------------------------------------------------------------------------------------------
  * Hub plan (one per CSR orientation, once per graph).  Power-law graphs have (row, relation)
- * segments with 10^4 edges; segments longer than 128 edges are cut into 512-edge chunks that
+ * segments with 10^4 edges; segments longer than 128 edges are cut into 128-edge chunks that
  * whole thread blocks reduce in a fixed order (no atomics).  hub_keys receives the sorted keys of
  * those segments, hub_chunk_ptr the exclusive prefix of their chunk counts (cap_hubs + 1 entries;
  * entries past n_hubs repeat the total).  cap_hubs >= E / 128 + 1 is always enough.

@@ -49,7 +49,7 @@ int sm_count();
 // Hub segments: a (row, relation) segment with more than kHubThreshold edges is cut into
 // chunks of kHubChunk edges that whole thread blocks reduce in a fixed order.
 constexpr int kHubThreshold = 128;
-constexpr int kHubChunk = 512;
+constexpr int kHubChunk = 128;
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }

@@ -8,7 +8,7 @@ HBM layout (all int32 / fp32, contiguous):
     rowptr   [n_dst * R + 1]   col   [E]   perm   [E]        keyed dst * R + rel
     rowptr_t [n_src * R + 1]   row_t [E]   perm_t [E]  w_t [E]   keyed src * R + rel
     inv_cnt  [n_dst * R]       1 / max(|N_r(i)|, 1)
-    hub_keys / hub_chunk_ptr   per orientation (segments > 128 edges, cut into 512-edge chunks)
+    hub_keys / hub_chunk_ptr   per orientation (segments > 128 edges, cut into 128-edge chunks)
 """
 from __future__ import annotations
 
