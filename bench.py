@@ -117,7 +117,7 @@ def algorithmic_bytes(E, N, R, d_in):
 
 
 def time_dominant_kernel(pkg, graph, d, iters, flush, comp=None):
-    """CUDA-event duration of the dominant op (forward / backward aggregation = hub_partial_kernel +
+    """CUDA-event duration of the dominant op (forward / backward aggregation = hub chunks +
     aggregate_rows_kernel, gather width d) on the launching stream, L2 flushed between launches."""
     from primekg_rgcn_linkprediction_b200 import ops
     x = torch.randn(graph.n_src, d, device="cuda")
@@ -270,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("aggregate_rows_fwd_d256_bytes")
-    roofline = {"bound": "hbm", "kernel": "aggregate_rows_kernel + hub_partial_kernel (layer-2 forward gather, d=256)",
+    roofline = {"bound": "hbm", "kernel": "hub_partial_kernel + aggregate_rows_kernel (layer-2 forward gather, d=256)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": fwd_b,
                 "avg_launch_ms": round(kt["aggregate_fwd"], 5),

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 1
+#define RGCN_B200_ABI_VERSION 2
 
 enum {
   RGCN_OK = 0,
@@ -96,6 +96,11 @@ int rgcn_hub_plan(const int32_t* rowptr, int64_t n_keys, int32_t* hub_keys, int3
                   int64_t cap_hubs, int32_t* n_hubs_host, int32_t* n_chunks_host,
                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
+/* Chunk table of a hub plan, one int32[4] entry per chunk: {key of the chunk's segment, first chunk of that segment,
+ * index of the first hub segment of the same row, number of chunks of that row}.  16-byte aligned. */
+int rgcn_hub_chunk_table(const int32_t* hub_keys, const int32_t* hub_chunk_ptr, int32_t n_hubs, int32_t R,
+                         int32_t* chunk_table, rgcn_stream_t stream);
+
 /* One orientation of the relation-keyed CSR as the aggregation kernels consume it. */
 typedef struct rgcn_csr {
   const int32_t* rowptr;        /* [n_rows * R + 1]                                   */
@@ -109,6 +114,7 @@ typedef struct rgcn_csr {
   int32_t reserved_;
   const int32_t* hub_keys;      /* [n_hubs]                                           */
   const int32_t* hub_chunk_ptr; /* [n_hubs + 1]                                       */
+  const int32_t* chunk_table;   /* [n_chunks][4] from rgcn_hub_chunk_table            */
 } rgcn_csr_t;
 
 /* ------------------------------------------------------------------------------------------
@@ -159,17 +165,24 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
  *   fwd   : out = A @ W + bias (, ReLU)                       [n_rows, d_out] fp32
  *   dgrad : gA  = G @ W^T                                     [n_rows, K1 + K2] fp32
  *   wgrad : [gW1 ; gW2] = A^T @ G ;  gbias = sum of the n_colsum column-sum partials
+ * Fused dropout (F.relu + nn.Dropout of src/models/rgcn.py:124-125 in ONE epilogue): with dropout_p > 0 (needs
+ * relu = 1) fwd zeroes each output element with probability p and scales the kept ones by 1 / (1 - p).  The mask is
+ * a counter-based hash of (dropout_seed, *dropout_counter, element index); the device-side counter is advanced by the
+ * call itself, so a captured CUDA graph draws a fresh mask on every replay.  Backward needs no stored mask: the
+ * output is zero exactly where ReLU or dropout killed the element, so rgcn_split_planes(gO, relu_mask = out,
+ * mask_scale = 1 / (1 - p)) yields G (mask_scale multiplies the masked values; pass 1 without dropout).
  * mode 0 = "fp32": hi*hi + hi*lo + lo*hi (error ~1e-5 relative); mode 1 = "bf16": hi*hi only.
  * Everything is deterministic (fixed split-K / partial reduction order).  K1, K2, d_out multiples of 4.
  * ------------------------------------------------------------------------------------------ */
 int64_t rgcn_split_planes_blocks(int64_t rows, int32_t cols);
 int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, int64_t rows,
                       int32_t cols, void* hi, void* lo, int64_t ldp, float* colsum_partial,
-                      rgcn_stream_t stream);
+                      float mask_scale, rgcn_stream_t stream);
 size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K, int32_t d_out);
 int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t lda, int32_t K1, int32_t K2,
                        const float* W1, const float* W2, const float* bias, int32_t relu,
                        int64_t n_rows, int32_t d_out, float* out, int64_t ldo, int32_t mode,
+                       float dropout_p, uint32_t dropout_seed, unsigned long long* dropout_counter,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out,
                          const float* W1, int32_t K1, const float* W2, int32_t K2,

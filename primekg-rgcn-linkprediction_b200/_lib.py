@@ -12,6 +12,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgcn_b200.so")
 
+ABI_VERSION = 2          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
+
 _lock = threading.Lock()
 _lib = None
 
@@ -23,7 +25,7 @@ class CsrStruct(C.Structure):
     """Mirror of ``rgcn_csr_t`` (include/rgcn_b200.h)."""
     _fields_ = [("rowptr", p), ("idx", p), ("w", p), ("n_rows", i64), ("E", i64), ("R", i32),
                 ("n_hubs", i32), ("n_chunks", i32), ("reserved_", i32), ("hub_keys", p),
-                ("hub_chunk_ptr", p)]
+                ("hub_chunk_ptr", p), ("chunk_table", p)]
 
 
 PCSR = C.POINTER(CsrStruct)
@@ -38,13 +40,15 @@ PROTOTYPES = {
     "rgcn_csr_build": (C.c_int, [p, p, p, i64, i64, i64, i32, p, p, p, p, p, p, p, p, p, p, sz, p]),
     "rgcn_hub_plan_workspace_bytes": (sz, [i64, i64]),
     "rgcn_hub_plan": (C.c_int, [p, i64, p, p, i64, C.POINTER(i32), C.POINTER(i32), p, sz, p]),
+    "rgcn_hub_chunk_table": (C.c_int, [p, p, i32, i32, p, p]),
     "rgcn_aggregate_workspace_bytes": (sz, [PCSR, i32]),
     "rgcn_aggregate_fwd": (C.c_int, [PCSR, p, i64, i32, p, i32, p, p, i64, i32, p, sz, p]),
     "rgcn_aggregate_bwd": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, p, sz, p]),
     "rgcn_split_planes_blocks": (i64, [i64, i32]),
-    "rgcn_split_planes": (C.c_int, [p, i64, p, i64, i64, i32, p, p, i64, p, p]),
+    "rgcn_split_planes": (C.c_int, [p, i64, p, i64, i64, i32, p, p, i64, p, C.c_float, p]),
     "rgcn_transform_workspace_bytes": (sz, [i64, i32, i32]),
-    "rgcn_transform_fwd": (C.c_int, [p, p, i64, i32, i32, p, p, p, i32, i64, i32, p, i64, i32, p, sz, p]),
+    "rgcn_transform_fwd": (C.c_int, [p, p, i64, i32, i32, p, p, p, i32, i64, i32, p, i64, i32, C.c_float, C.c_uint32, p,
+                                     p, sz, p]),
     "rgcn_transform_dgrad": (C.c_int, [p, p, i64, i32, p, i32, p, i32, i64, p, i64, i32, p, sz, p]),
     "rgcn_transform_wgrad": (C.c_int, [p, p, i64, i32, i32, p, p, i64, i32, i64, p, i32, p, p, p, i32, p, sz, p]),
     "rgcn_distmult_fwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, i64, i32, p, p]),
@@ -82,7 +86,7 @@ def load():
                 raise RGCNLibraryError(f"{LIB_PATH} does not export {name}; rebuild the library") from e
             fn.restype = res
             fn.argtypes = args
-        if lib.rgcn_abi_version() != 1:
+        if lib.rgcn_abi_version() != ABI_VERSION:
             raise RGCNLibraryError("ABI version mismatch between the Python host side and librgcn_b200.so")
         _lib = lib
     return _lib

@@ -44,7 +44,7 @@ class _RGCNLayerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x_src, x_root, W, root, bias, graph: RelGraph, relu: bool, mode: str):
+    def forward(ctx, x_src, x_root, W, root, bias, graph: RelGraph, relu: bool, mode: str, drop=None):
         """x_src [n_src, d_in]: rows the edges gather from; x_root [n_dst, d_in]: the rows being updated (self-loop
         term).  On one GPU they are the same tensor; on a destination-range shard x_src is the all-gathered matrix."""
         R, d_in, d_out = W.shape
@@ -57,8 +57,10 @@ class _RGCNLayerFn(torch.autograd.Function):
         A = ops.alloc_planes(graph.n_dst, K1 + K2, mode, x_src.device)
         ops.aggregate_fwd(graph, x_src, planes=A)
         ops.split_planes(x_root, A, col0=K1)
-        out = ops.transform_fwd(A, K1, K2, W.reshape(K1, d_out), root, bias, relu, mode)
-        ctx.graph, ctx.relu, ctx.mode, ctx.shared = graph, relu, mode, shared
+        # drop = (p, seed, device counter): ReLU + dropout fused into the GEMM epilogue (reference :124-125)
+        p_drop, seed, ctr = drop if drop is not None else (0.0, 0, None)
+        out = ops.transform_fwd(A, K1, K2, W.reshape(K1, d_out), root, bias, relu, mode, p_drop, seed, ctr)
+        ctx.graph, ctx.relu, ctx.mode, ctx.shared, ctx.p_drop = graph, relu, mode, shared, p_drop
         ctx.save_for_backward(A[0], A[1], W, root, out if relu else None)
         return out
 
@@ -75,7 +77,8 @@ class _RGCNLayerFn(torch.autograd.Function):
         gx_src = gx_root = gW = groot = gb = None
         # G = gO * [out > 0] as bf16 planes, formed once for both GEMMs; column sums = bias gradient
         G = ops.alloc_planes(gO.size(0), d_out, mode, gO.device)
-        colsum = ops.split_planes(gO, G, relu_mask=out, colsum=need_w_any)
+        # out is zero exactly where ReLU or the fused dropout killed the element: one mask serves both
+        colsum = ops.split_planes(gO, G, relu_mask=out, colsum=need_w_any, mask_scale=1.0 / (1.0 - ctx.p_drop))
         if need_src or need_root_x:
             gA = ops.transform_dgrad(G, d_out, Wf, root, mode)            # [n_dst, (R+1) * d_in]
             if ctx.shared:
@@ -87,7 +90,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         if need_w_any:
             gWf, groot, gb = ops.transform_wgrad((A_hi, A_lo), K1, K2, G, d_out, colsum, mode)
             gW = gWf.view(R, d_in, d_out)
-        return gx_src, gx_root, gW, groot, gb, None, None, None
+        return gx_src, gx_root, gW, groot, gb, None, None, None, None
 
 
 def _glorot_(t: Optional[torch.Tensor]) -> None:
@@ -106,6 +109,7 @@ class RGCNConv(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.num_relations, self.num_bases = num_relations, num_bases
         self.mode = mode
+        self._drop_ctr, self._drop_seed = None, 0
         if num_bases is not None:
             self.weight = nn.Parameter(torch.empty(num_bases, in_channels, out_channels))
             self.comp = nn.Parameter(torch.empty(num_relations, num_bases))
@@ -129,13 +133,29 @@ class RGCNConv(nn.Module):
         B = self.weight.size(0)
         return (self.comp @ self.weight.view(B, -1)).view(self.num_relations, self.in_channels, self.out_channels)
 
-    def forward_graph(self, x: torch.Tensor, graph: RelGraph, relu: bool = False) -> torch.Tensor:
+    def dropout_state(self, p: float, device):
+        """(p, seed, counter) for the fused ReLU + dropout epilogue.  The seed is drawn from torch's generator the
+        first time dropout is used (so ``torch.manual_seed`` makes runs repeatable); the device-side counter is
+        advanced by every call, also under CUDA-graph replay."""
+        if not (0.0 <= p < 1.0):
+            raise ValueError("fused dropout needs 0 <= p < 1")
+        ctr = self._drop_ctr
+        if ctr is None or ctr.device != device:
+            self._drop_seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+            ctr = self._drop_ctr = ops.dropout_counter(device)
+        return (float(p), self._drop_seed, ctr)
+
+    def forward_graph(self, x: torch.Tensor, graph: RelGraph, relu: bool = False, dropout_p: float = 0.0) -> torch.Tensor:
+        """``dropout_p`` > 0 (training): ReLU and dropout are applied in the transform's epilogue (needs relu=True)."""
         if x.dim() != 2 or x.size(1) != self.in_channels:
             raise ValueError(f"x must be [N, {self.in_channels}]")
         if graph.R != self.num_relations:
             raise ValueError("graph and layer disagree on the number of relations")
+        if dropout_p > 0.0 and not relu:
+            raise ValueError("the fused dropout follows the fused ReLU; use nn.Dropout for other placements")
+        drop = self.dropout_state(dropout_p, x.device) if dropout_p > 0.0 else None
         return _RGCNLayerFn.apply(x, x, self.relation_weights(), self.root, self.bias, graph, relu,
-                                  self.mode or default_mode())
+                                  self.mode or default_mode(), drop)
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_type: torch.Tensor) -> torch.Tensor:
         if edge_type is None:

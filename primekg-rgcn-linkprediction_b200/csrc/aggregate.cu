@@ -31,6 +31,7 @@ struct AggParams {
   const float* edge_w;       // nullable
   const int32_t* hub_keys;   // sorted keys of hub segments
   const int32_t* hub_chunk_ptr;
+  const int32_t* chunk_table;  // [n_chunks][4]: {segment key, first chunk of the segment, -, -}
   int32_t n_hubs;
   int64_t n_rows;
   int32_t R;
@@ -56,17 +57,12 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
   constexpr int GROUPS = 256 / G;
   __shared__ float4 red[GROUPS][G * VPL];
   const int chunk = blockIdx.x;
-  // which hub does this chunk belong to: last h with hub_chunk_ptr[h] <= chunk
-  int lo = 0, hi = p.n_hubs;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(p.hub_chunk_ptr + mid) <= chunk) lo = mid; else hi = mid;
-  }
-  const int hub = lo;
-  const int key = __ldg(p.hub_keys + hub);
+  // one table load instead of a search through the hub list (a chain of dependent loads in front of every block)
+  const int4 t = __ldg(reinterpret_cast<const int4*>(p.chunk_table) + chunk);
+  const int key = t.x;
   const int r = key % p.R;
   const int seg_beg = __ldg(p.rowptr + key), seg_end = __ldg(p.rowptr + key + 1);
-  const int c_beg = seg_beg + (chunk - __ldg(p.hub_chunk_ptr + hub)) * kHubChunk;
+  const int c_beg = seg_beg + (chunk - t.y) * kHubChunk;
   const int c_end = min(c_beg + kHubChunk, seg_end);
   const int nvec = p.d >> 2;
   const int lane = threadIdx.x % G, grp = threadIdx.x / G;
@@ -237,7 +233,21 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) 
           if (__ldg(p.hub_keys + mid) <= key) lo = mid; else hi = mid;
         }
         const int c0 = __ldg(p.hub_chunk_ptr + lo), c1 = __ldg(p.hub_chunk_ptr + lo + 1);
-        for (int c = c0; c < c1; ++c) {
+        // loads U chunks ahead (a 10^4-edge hub has ~100 partials: one dependent load each would be a long chain),
+        // adds strictly in chunk order
+        int c = c0;
+        for (; c + U <= c1; c += U) {
+          float4 v[U][VPL];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) v[u][k] = *reinterpret_cast<const float4*>(p.partials + (size_t)(c + u) * d + vcol[k]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) add4(acc[k], v[u][k]);
+        }
+        for (; c < c1; ++c) {
 #pragma unroll
           for (int k = 0; k < VPL; ++k) add4(acc[k], *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k]));
         }
@@ -352,7 +362,8 @@ static int check_common(const rgcn_csr_t* g, const float* F, int64_t ldf, int32_
   RGCN_CHECK_ARG(g->R >= 1 && g->n_rows >= 0, "aggregate: bad n_rows/R");
   RGCN_CHECK_ARG(d >= 4 && d <= 1024 && d % 4 == 0, "aggregate: feature width d=%d must be a multiple of 4 in [4,1024]", d);
   RGCN_CHECK_ARG(F && ldf % 4 == 0 && ((uintptr_t)F & 15) == 0, "aggregate: feature matrix must be 16-byte aligned with ld %% 4 == 0");
-  RGCN_CHECK_ARG(g->n_chunks == 0 || (g->hub_keys && g->hub_chunk_ptr && g->n_hubs > 0), "aggregate: hub plan missing");
+  RGCN_CHECK_ARG(g->n_chunks == 0 || (g->hub_keys && g->hub_chunk_ptr && g->n_hubs > 0 && g->chunk_table &&
+                                      ((uintptr_t)g->chunk_table & 15) == 0), "aggregate: hub plan missing");
   if (g->n_chunks > 0 && (!ws || ws_bytes < (size_t)g->n_chunks * d * sizeof(float))) {
     set_error("aggregate: workspace too small (%zu < %zu)", ws_bytes, (size_t)g->n_chunks * d * sizeof(float));
     return RGCN_EWORKSPACE;
@@ -380,7 +391,7 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
   RGCN_CHECK_ARG(!comp || (B >= 1), "aggregate_fwd: bad number of bases");
   AggParams p{};
   p.rowptr = g->rowptr; p.idx = g->idx; p.edge_w = g->w;
-  p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs;
+  p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs; p.chunk_table = g->chunk_table;
   p.n_rows = g->n_rows; p.R = g->R;
   p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d;
   p.O = H; p.O_lo = H_lo; p.ldo = ldh; p.out_mode = out_mode; p.partials = (float*)workspace;
@@ -408,7 +419,7 @@ extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t
   RGCN_CHECK_ARG(gt->w || gt->E == 0, "aggregate_bwd: the transposed CSR needs per-edge weights w_t");
   AggParams p{};
   p.rowptr = gt->rowptr; p.idx = gt->idx; p.edge_w = gt->w;
-  p.hub_keys = gt->hub_keys; p.hub_chunk_ptr = gt->hub_chunk_ptr; p.n_hubs = gt->n_hubs;
+  p.hub_keys = gt->hub_keys; p.hub_chunk_ptr = gt->hub_chunk_ptr; p.n_hubs = gt->n_hubs; p.chunk_table = gt->chunk_table;
   p.n_rows = gt->n_rows; p.R = gt->R;
   p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d;
   p.init = init; p.ld_init = ld_init; p.B = 1;

@@ -145,9 +145,35 @@ __global__ void hub_chunks_kernel(const int32_t* __restrict__ rowptr, const int3
   chunk_cnt[h] = c;
 }
 
+// one thread per hub segment: fills the table entries of its chunks
+__global__ void hub_chunk_table_kernel(const int32_t* __restrict__ hub_keys, const int32_t* __restrict__ chunk_ptr,
+                                       int n_hubs, int R, int4* __restrict__ table) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hubs) return;
+  const int key = hub_keys[h], row = key / R;
+  int first = h, end = h + 1;
+  while (first > 0 && hub_keys[first - 1] / R == row) --first;
+  while (end < n_hubs && hub_keys[end] / R == row) ++end;
+  const int need = chunk_ptr[end] - chunk_ptr[first];
+  const int c0 = chunk_ptr[h], c1 = chunk_ptr[h + 1];
+  for (int c = c0; c < c1; ++c) table[c] = make_int4(key, c0, first, need);
+}
+
 }  // namespace rgcn
 
 using namespace rgcn;
+
+extern "C" int rgcn_hub_chunk_table(const int32_t* hub_keys, const int32_t* hub_chunk_ptr, int32_t n_hubs, int32_t R,
+                                    int32_t* chunk_table, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n_hubs >= 0 && R >= 1, "hub_chunk_table: bad sizes");
+  if (n_hubs == 0) return RGCN_OK;
+  RGCN_CHECK_ARG(hub_keys && hub_chunk_ptr && chunk_table && ((uintptr_t)chunk_table & 15) == 0,
+                 "hub_chunk_table: null or misaligned argument");
+  hub_chunk_table_kernel<<<(unsigned)((n_hubs + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      hub_keys, hub_chunk_ptr, n_hubs, R, reinterpret_cast<int4*>(chunk_table));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
 
 extern "C" size_t rgcn_csr_build_workspace_bytes(int64_t E, int64_t n_dst, int64_t n_src, int32_t R) {
   if (E < 0 || n_dst < 0 || n_src < 0 || R < 1) return 0;

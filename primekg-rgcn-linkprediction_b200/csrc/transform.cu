@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
                                                            const float* __restrict__ mask, int64_t ldm, int64_t rows,
                                                            int cols, __nv_bfloat16* __restrict__ hi,
                                                            __nv_bfloat16* __restrict__ lo, int64_t ldp,
-                                                           float* __restrict__ colsum_partial, int64_t rows_per_block) {
+                                                           float* __restrict__ colsum_partial, int64_t rows_per_block,
+                                                           float scale) {
   __shared__ float4 red[256];
   const int tpr = cols >> 2;                       // threads per row (<= 256)
   const int rpp = 256 / tpr;                       // rows per pass
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
             if (!(m[u].y > 0.f)) v[u].y = 0.f;
             if (!(m[u].z > 0.f)) v[u].z = 0.f;
             if (!(m[u].w > 0.f)) v[u].w = 0.f;
+            v[u] = scale4(v[u], scale);                // 1 / (1 - p) of a fused dropout, else 1
           }
           add4(cs, v[u]);
           uint2 h, l;
@@ -105,10 +107,25 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
-// weights: fp32 [K1 + K2, N] (two row blocks) -> bf16 hi / lo, optionally transposed, zero padded
+// Counter-based dropout: element (row, col) of step `ctr` is kept iff 16 bits of hash(seed, ctr, row * N + col) >= thresh.
+// The same function regenerates the mask anywhere; the backward pass does not even need it (out == 0 where dropped).
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t x) {
+  uint32_t state = x * 747796405u + 2891336453u;
+  uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+  return (word >> 22u) ^ word;
+}
+// key of the 2^32-element block that `elem` lies in; the bits of element e are pcg_hash((uint32_t)e ^ block_key)
+__device__ __forceinline__ uint32_t drop_block_key(uint32_t key, uint64_t elem) {
+  return pcg_hash(key + (uint32_t)(elem >> 32) * 0x9E3779B9u);
+}
+
+// weights: fp32 [K1 + K2, N] (two row blocks) -> bf16 hi / lo, optionally transposed, zero padded.
+// seed_state (nullable): the dropout step counter, advanced here once per layer call (stream-ordered before the GEMM
+// that reads it, and replayed with the CUDA graph, so every step draws a fresh mask without host involvement).
 __global__ void split_weights_kernel(const float* __restrict__ w1, int K1, const float* __restrict__ w2, int K2, int N,
                                      int transpose, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                     int rows_pad, int cols_pad) {
+                                     int rows_pad, int cols_pad, unsigned long long* seed_state) {
+  if (seed_state && blockIdx.x == 0 && threadIdx.x == 0) *seed_state += 1ull;
   // output [rows_pad, cols_pad]; transpose: out[n][k] = W[k][n], else out[k][n] = W[k][n]
   const int64_t total = (int64_t)rows_pad * cols_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -134,6 +151,8 @@ struct GemmKParams {
   int num_kb;                                 // K blocks of 64 (TMA zero-fills past the true K)
   const float* bias; int relu;
   float* out; int64_t ldo;
+  // fused dropout after the ReLU (training): keep iff drop_bits(...) >= drop_thresh, kept values times drop_scale
+  uint32_t drop_thresh; float drop_scale; uint32_t drop_seed; const unsigned long long* drop_ctr;
 };
 
 constexpr int KBN = 128;                      // N tile of the persistent kernel: two accumulators fit 256 TMEM columns
@@ -198,6 +217,11 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   if (warp < K_EPI_WARPS) {
     // ===================== epilogue: warp w owns TMEM lanes 32w .. 32w+31 =====================
     float* patch = reinterpret_cast<float*>(smem + (size_t)S::STAGES * S::BYTES + (size_t)warp * K_PATCH);
+    uint32_t drop_key = 0;
+    if (p.drop_thresh) {
+      const unsigned long long ctr = *p.drop_ctr;
+      drop_key = pcg_hash(p.drop_seed ^ (uint32_t)ctr) + (uint32_t)(ctr >> 32);
+    }
     int iter = 0;
     for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++iter) {
       const int64_t m0 = (t / p.n_tiles) * BM;
@@ -227,9 +251,21 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         for (int rr = 0; rr < 32; rr += 4) {
           const int rl = rr + (lane >> 3);
           const int64_t row = m0 + warp * 32 + rl;
-          if (row < p.M && col_ok)
-            *reinterpret_cast<float4*>(p.out + row * p.ldo + n0 + cc + c4) =
-                *reinterpret_cast<const float4*>(patch + rl * 36 + c4);
+          if (row < p.M && col_ok) {
+            float4 v = *reinterpret_cast<const float4*>(patch + rl * 36 + c4);
+            if (p.drop_thresh) {
+              // N % 4 == 0, so the four elements of one store never straddle a 2^32 block
+              const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + cc + c4);
+              // two hashes per store, 16 random bits per element (p is resolved to 2^-16)
+              const uint32_t bk = drop_block_key(drop_key, e0), e32 = (uint32_t)e0;
+              const uint32_t h0 = pcg_hash(e32 ^ bk), h1 = pcg_hash((e32 + 2) ^ bk);
+              v.x = (h0 & 0xffffu) >= p.drop_thresh ? v.x * p.drop_scale : 0.f;
+              v.y = (h0 >> 16) >= p.drop_thresh ? v.y * p.drop_scale : 0.f;
+              v.z = (h1 & 0xffffu) >= p.drop_thresh ? v.z * p.drop_scale : 0.f;
+              v.w = (h1 >> 16) >= p.drop_thresh ? v.w * p.drop_scale : 0.f;
+            }
+            *reinterpret_cast<float4*>(p.out + row * p.ldo + n0 + cc + c4) = v;
+          }
         }
         __syncwarp();
       }
@@ -637,7 +673,7 @@ extern "C" int64_t rgcn_split_planes_blocks(int64_t rows, int32_t cols) {
 
 extern "C" int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, int64_t rows,
                                  int32_t cols, void* hi, void* lo, int64_t ldp, float* colsum_partial,
-                                 rgcn_stream_t stream) {
+                                 float mask_scale, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(rows >= 0 && cols >= 4 && cols % 4 == 0 && cols <= 1024, "split_planes: cols=%d must be a multiple of 4 in [4, 1024]", cols);
   RGCN_CHECK_ARG(x && ((uintptr_t)x & 15) == 0 && ldx % 4 == 0, "split_planes: x must be 16-byte aligned, ld %% 4 == 0");
   RGCN_CHECK_ARG(!relu_mask || (((uintptr_t)relu_mask & 15) == 0 && ldm % 4 == 0), "split_planes: mask misaligned");
@@ -650,7 +686,7 @@ extern "C" int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_
   const int64_t rows_per_block = ((rows + nb - 1) / nb + rpp - 1) / rpp * rpp;
   split_planes_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(x, ldx, relu_mask, ldm, rows, cols,
                                                                      (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp,
-                                                                     colsum_partial, rows_per_block);
+                                                                     colsum_partial, rows_per_block, mask_scale);
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -671,9 +707,12 @@ extern "C" size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K, int3
 
 extern "C" int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t lda, int32_t K1, int32_t K2, const float* W1,
                                   const float* W2, const float* bias, int32_t relu, int64_t n_rows, int32_t d_out,
-                                  float* out, int64_t ldo, int32_t mode, void* workspace, size_t workspace_bytes,
+                                  float* out, int64_t ldo, int32_t mode, float dropout_p, uint32_t dropout_seed,
+                                  unsigned long long* dropout_counter, void* workspace, size_t workspace_bytes,
                                   rgcn_stream_t stream) {
   RGCN_CHECK_ARG(n_rows >= 0 && K1 > 0 && K2 >= 0 && d_out > 0, "transform_fwd: bad sizes");
+  RGCN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "transform_fwd: dropout_p must be in [0, 1)");
+  RGCN_CHECK_ARG(dropout_p == 0.f || (dropout_counter && relu), "transform_fwd: fused dropout needs relu = 1 and a counter");
   RGCN_CHECK_ARG(K1 % 4 == 0 && K2 % 4 == 0 && d_out % 4 == 0, "transform_fwd: K1, K2, d_out must be multiples of 4");
   RGCN_CHECK_ARG(mode == 0 || mode == 1, "transform_fwd: mode must be 0 (fp32) or 1 (bf16)");
   RGCN_CHECK_ARG(n_rows < (1ll << 31), "transform_fwd: too many rows for one call");
@@ -697,12 +736,19 @@ extern "C" int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t ld
   {
     const int64_t total = (int64_t)t.n_pad * k_pad;
     split_weights_kernel<<<grid_cap((total + 255) / 256, 1184), 256, 0, st>>>(W1, K1, W2, K2, d_out, 1, bhi,
-                                                                              split ? blo : nullptr, t.n_pad, k_pad);
+                                                                              split ? blo : nullptr, t.n_pad, k_pad,
+                                                                              dropout_p > 0.f ? dropout_counter : nullptr);
     RGCN_LAUNCH_CHECK();
   }
   GemmKParams p{};
   p.M = n_rows; p.N = d_out; p.BN = t.BN; p.num_kb = k_pad / BK;
   p.bias = bias; p.relu = relu; p.out = out; p.ldo = ldo;
+  if (dropout_p > 0.f) {
+    const double th = (double)dropout_p * 65536.0 + 0.5;
+    p.drop_thresh = th >= 65535.0 ? 65535u : (th < 1.0 ? 1u : (uint32_t)th);
+    p.drop_scale = 1.f / (1.f - dropout_p);
+    p.drop_seed = dropout_seed; p.drop_ctr = dropout_counter;
+  }
   return launch_kmajor(p, A_hi, A_lo, lda, K, bhi, blo, t.n_pad, k_pad, t.n_tiles, split, st);
 }
 
@@ -733,7 +779,7 @@ extern "C" int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t 
   {
     const int64_t total = (int64_t)t.n_pad * k_pad;
     split_weights_kernel<<<grid_cap((total + 255) / 256, 1184), 256, 0, st>>>(W1, K1, W2, K2, d_out, 0, bhi,
-                                                                              split ? blo : nullptr, t.n_pad, k_pad);
+                                                                              split ? blo : nullptr, t.n_pad, k_pad, nullptr);
     RGCN_LAUNCH_CHECK();
   }
   GemmKParams p{};

@@ -174,8 +174,10 @@ class PartitionedRGCN(nn.Module):
             x_full = AllGatherRows.apply(x)                                  # NCCL all-gather over NVLink
             W = AllReduceGrad.apply(conv.relation_weights())
             root, bias = AllReduceGrad.apply(conv.root), AllReduceGrad.apply(conv.bias)
-            x = _RGCNLayerFn.apply(x_full, x, W, root, bias, self.graph, li != last, conv.mode or default_mode())
-            if li != last:
+            p = self.dropout.p if (self.training and li != last) else 0.0
+            drop = conv.dropout_state(p, x.device) if (0.0 < p < 1.0 and x.is_cuda) else None
+            x = _RGCNLayerFn.apply(x_full, x, W, root, bias, self.graph, li != last, conv.mode or default_mode(), drop)
+            if li != last and p > 0.0 and drop is None:
                 x = self.dropout(x)
         return x
 

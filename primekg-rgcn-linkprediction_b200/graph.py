@@ -8,7 +8,7 @@ HBM layout (all int32 / fp32, contiguous):
     rowptr   [n_dst * R + 1]   col   [E]   perm   [E]        keyed dst * R + rel
     rowptr_t [n_src * R + 1]   row_t [E]   perm_t [E]  w_t [E]   keyed src * R + rel
     inv_cnt  [n_dst * R]       1 / max(|N_r(i)|, 1)
-    hub_keys / hub_chunk_ptr   per orientation (segments > 128 edges, cut into 128-edge chunks)
+    hub_keys / hub_chunk_ptr / chunk_table   per orientation (segments > 128 edges, cut into 128-edge chunks)
 """
 from __future__ import annotations
 
@@ -36,12 +36,12 @@ class _Orientation:
     def __init__(self, rowptr, idx, w, n_rows, R, E):
         self.rowptr, self.idx, self.w = rowptr, idx, w
         self.n_rows, self.R, self.E = int(n_rows), int(R), int(E)
-        self.hub_keys = self.hub_chunk_ptr = None
+        self.hub_keys = self.hub_chunk_ptr = self.chunk_table = None
         self.n_hubs = self.n_chunks = 0
         self._plan_hubs()
         self.struct = _lib.CsrStruct(
             _ptr(rowptr), _ptr(idx), _ptr(w), self.n_rows, self.E, self.R, self.n_hubs, self.n_chunks, 0,
-            _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr))
+            _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr), _ptr(self.chunk_table))
         self.ref = C.byref(self.struct)
         self._ws = {}
 
@@ -61,6 +61,9 @@ class _Orientation:
         if self.n_hubs:
             self.hub_keys = hub_keys[: self.n_hubs].clone()
             self.hub_chunk_ptr = chunk_ptr[: self.n_hubs + 1].clone()
+            self.chunk_table = torch.empty(self.n_chunks, 4, dtype=torch.int32, device=dev)
+            _lib.check(lib.rgcn_hub_chunk_table(_ptr(self.hub_keys), _ptr(self.hub_chunk_ptr), self.n_hubs, self.R,
+                                                _ptr(self.chunk_table), _stream(dev)), "rgcn_hub_chunk_table")
 
     def workspace(self, d: int) -> Optional[torch.Tensor]:
         """Chunk-partial buffer for feature width d (kept; sized n_chunks * d floats)."""

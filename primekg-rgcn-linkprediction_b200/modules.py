@@ -67,8 +67,10 @@ class DrugDiseaseRGCN(nn.Module):
         layers = list(self._layers())
         for li, conv in enumerate(layers):
             last = li == len(layers) - 1
-            x = conv.forward_graph(x, graph, relu=not last)      # ReLU fused into the layer epilogue
-            if not last:
+            # ReLU and (in training) dropout live in the layer's GEMM epilogue; p == 1 keeps nn.Dropout's all-zero output
+            p = self.dropout.p if (self.training and not last) else 0.0
+            x = conv.forward_graph(x, graph, relu=not last, dropout_p=p if p < 1.0 else 0.0)
+            if not last and p >= 1.0:
                 x = self.dropout(x)
         return x
 

@@ -193,9 +193,10 @@ def alloc_planes(rows: int, cols: int, mode: str, device):
 
 
 def split_planes(x: torch.Tensor, planes, col0: int = 0, relu_mask: Optional[torch.Tensor] = None,
-                 colsum: bool = False):
+                 colsum: bool = False, mask_scale: float = 1.0):
     """Write fp32 ``x`` [rows, cols] into columns [col0, col0+cols) of the bf16 planes (hi [, lo]); optionally zero
-    where relu_mask <= 0 and return the per-block column-sum partials [nblocks, cols] of the masked values."""
+    where relu_mask <= 0 (and multiply the rest by ``mask_scale``, the 1 / (1 - p) of a fused dropout) and return the
+    per-block column-sum partials [nblocks, cols] of the masked values."""
     lib = _lib.load()
     x = _f32c(x, "x")
     rows, cols = x.shape
@@ -209,14 +210,21 @@ def split_planes(x: torch.Tensor, planes, col0: int = 0, relu_mask: Optional[tor
     hi_v = hi[:, col0:col0 + cols]
     lo_v = None if lo is None else lo[:, col0:col0 + cols]
     _lib.check(lib.rgcn_split_planes(_ptr(x), x.stride(0), _ptr(relu_mask), 0 if relu_mask is None else relu_mask.stride(0),
-                                     rows, cols, _ptr(hi_v), _ptr(lo_v), hi.stride(0), _ptr(part), _stream(x.device)),
+                                     rows, cols, _ptr(hi_v), _ptr(lo_v), hi.stride(0), _ptr(part), float(mask_scale),
+                                     _stream(x.device)),
                "rgcn_split_planes")
     return part
 
 
+def dropout_counter(device) -> torch.Tensor:
+    """Device-side step counter of the fused dropout (uint64 stored as int64 [1]); advanced by every layer call."""
+    return torch.zeros(1, dtype=torch.int64, device=device)
+
+
 def transform_fwd(planes, K1: int, K2: int, W1: torch.Tensor, W2: Optional[torch.Tensor],
-                  bias: Optional[torch.Tensor], relu: bool, mode: str) -> torch.Tensor:
-    """out = A @ [W1 ; W2] + bias (, ReLU) with A given as bf16 planes [n, K1 + K2] — tcgen05 kernel."""
+                  bias: Optional[torch.Tensor], relu: bool, mode: str, dropout_p: float = 0.0,
+                  dropout_seed: int = 0, dropout_ctr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = A @ [W1 ; W2] + bias (, ReLU (, dropout)) with A given as bf16 planes [n, K1 + K2] — tcgen05 kernel."""
     lib = _lib.load()
     hi, lo = planes
     n = hi.size(0)
@@ -232,8 +240,9 @@ def transform_fwd(planes, K1: int, K2: int, W1: torch.Tensor, W2: Optional[torch
     nb = lib.rgcn_transform_workspace_bytes(n, K1 + K2, d_out)
     ws = _workspace(hi.device, nb)
     _lib.check(lib.rgcn_transform_fwd(_ptr(hi), _ptr(lo), hi.stride(0), K1, K2, _ptr(W1), _ptr(W2), _ptr(bias),
-                                      int(relu), n, d_out, _ptr(out), out.stride(0), _mode_id(mode), _ptr(ws),
-                                      ws.numel(), _stream(hi.device)), "rgcn_transform_fwd")
+                                      int(relu), n, d_out, _ptr(out), out.stride(0), _mode_id(mode), float(dropout_p),
+                                      int(dropout_seed) & 0xFFFFFFFF, _ptr(dropout_ctr if dropout_p > 0 else None),
+                                      _ptr(ws), ws.numel(), _stream(hi.device)), "rgcn_transform_fwd")
     return out
 
 

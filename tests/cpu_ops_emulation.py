@@ -28,13 +28,14 @@ def aggregate_fwd(g, x, out_bf16=False, comp=None, planes=None):
     return H
 
 
-def split_planes(x, planes, col0=0, relu_mask=None, colsum=False):
-    v = x if relu_mask is None else x * (relu_mask > 0)
+def split_planes(x, planes, col0=0, relu_mask=None, colsum=False, mask_scale=1.0):
+    v = x if relu_mask is None else x * (relu_mask > 0) * mask_scale
     planes[0][:, col0:col0 + x.size(1)] = v
     return v.sum(0, keepdim=True) if colsum else None
 
 
-def transform_fwd(planes, K1, K2, W1, W2, bias, relu, mode):
+def transform_fwd(planes, K1, K2, W1, W2, bias, relu, mode, dropout_p=0.0, dropout_seed=0, dropout_ctr=None):
+    assert dropout_p == 0.0, "the CPU stand-in has no fused dropout"
     W = W1.reshape(K1, -1) if W2 is None else torch.cat([W1.reshape(K1, -1), W2], 0)
     out = planes[0][:, :K1 + K2] @ W.detach() + bias.detach()
     return out.clamp(min=0) if relu else out

@@ -540,3 +540,108 @@ def test_fused_bce_matches_torch(pkg):
     torch.testing.assert_close(loss, ref, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(x.grad, xr.grad, rtol=1e-5, atol=1e-9)
     assert int(correct) == int(((torch.sigmoid(xr) > 0.5).float() == y).sum())      # reference src/train.py:321-322
+
+
+# ------------------------------------------------------------------------------------------------
+# fused ReLU + dropout epilogue (reference F.relu + nn.Dropout, src/models/rgcn.py:124-125)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [0.5, 0.1])
+def test_fused_dropout_layer(pkg, p):
+    """Train-mode layer with the dropout in the GEMM epilogue: every element is either 0 or the no-dropout value
+    / (1 - p); the kept fraction is 1 - p; the gradient is the no-dropout gradient of the same masked function; a
+    second call draws a different mask."""
+    from primekg_rgcn_linkprediction_b200 import synth
+    from primekg_rgcn_linkprediction_b200.conv import RGCNConv
+    from primekg_rgcn_linkprediction_b200.graph import get_graph
+    torch.manual_seed(3)
+    kg = synth.uniform_kg(3000, 40_000, 3, seed=11)
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    conv = RGCNConv(64, 128, 3).to(DEV)
+    x = torch.randn(3000, 64, device=DEV, requires_grad=True)
+    graph = get_graph(ei, et, 3000, 3)
+    base = conv.forward_graph(x, graph, relu=True).detach()
+    out = conv.forward_graph(x, graph, relu=True, dropout_p=p)
+    kept = out != 0
+    pos = base > 0
+    assert not (kept & ~pos).any()                                   # nothing appears where ReLU gave 0
+    frac = float((kept & pos).sum()) / float(pos.sum())
+    assert abs(frac - (1 - p)) < 0.01, frac
+    torch.testing.assert_close(out[kept], base[kept] / (1 - p), rtol=1e-6, atol=0)
+    # backward: same as differentiating relu(z) * mask / (1 - p) with the mask held fixed
+    coef = torch.randn_like(out)
+    (out * coef).sum().backward()
+    gx, gw = x.grad.clone(), conv.weight.grad.clone()
+    x.grad = None
+    conv.zero_grad()
+    base2 = conv.forward_graph(x, graph, relu=True)
+    (base2 * coef * kept / (1 - p)).sum().backward()
+    torch.testing.assert_close(gx, x.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(gw, conv.weight.grad, rtol=1e-4, atol=1e-4)
+    out2 = conv.forward_graph(x, graph, relu=True, dropout_p=p).detach()
+    assert ((out2 != 0) != kept).float().mean() > 0.05              # fresh mask per call
+    # columns are not correlated with rows: every column keeps about 1 - p of its positives
+    col_frac = (kept & pos).float().sum(0) / pos.float().sum(0).clamp(min=1)
+    assert float((col_frac - (1 - p)).abs().max()) < 0.08
+
+
+def test_fused_dropout_changes_under_graph_replay(pkg):
+    """The device-side dropout counter advances inside the captured graph: two replays give different masks."""
+    from primekg_rgcn_linkprediction_b200 import synth
+    from primekg_rgcn_linkprediction_b200.graphed import GraphedTrainStep
+    torch.manual_seed(1)
+    kg = synth.primekg_subgraph(20_000, seed=5)
+    model = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, 128, dropout=0.5, decoder_dropout=0.0).to(DEV)
+    model.train()
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    B = 256
+    step = GraphedTrainStep(model, ei, et, B)
+    heads = torch.randint(0, kg.num_nodes, (B,), device=DEV)
+    tails = torch.randint(0, kg.num_nodes, (B,), device=DEV)
+    rels = torch.randint(0, kg.num_relations, (B,), device=DEV)
+    labels = (torch.rand(B, device=DEV) > 0.5).float()
+    l1 = float(step(heads, tails, rels, labels))
+    s1 = step.scores.clone()
+    l2 = float(step(heads, tails, rels, labels))
+    s2 = step.scores.clone()
+    assert l1 == l1 and l2 == l2
+    assert not torch.equal(s1, s2)
+    model.eval()                                                      # eval: no dropout, deterministic
+    with torch.no_grad():
+        a = model(ei, et, heads, tails, rels)
+        b = model(ei, et, heads, tails, rels)
+    assert torch.equal(a, b)
+
+
+def test_hub_rows_mixed_modes(pkg):
+    """Graph where several relations of the same rows are hubs (> 128 edges) next to short segments: the row pass
+    skips what needs chunk partials and the hub-row pass fills it in, for all three mixing modes."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    from primekg_rgcn_linkprediction_b200.graph import RelGraph
+    g = torch.Generator().manual_seed(7)
+    N, R, E = 600, 4, 30_000
+    src = torch.randint(0, N, (E,), generator=g)
+    dst = torch.randint(0, N, (E,), generator=g)
+    rel = torch.randint(0, R, (E,), generator=g)
+    dst[: E // 2] = torch.randint(0, 5, (E // 2,), generator=g)       # rows 0..4: every relation a hub (~750 edges)
+    src[E // 2: E // 2 + 4000] = 7                                     # node 7: hub in the transposed CSR
+    dst[-300:] = 9
+    rel[-300:] = 2                                                    # row 9: one hub relation, three short ones
+    graph = RelGraph(src.to(DEV), dst.to(DEV), rel.to(DEV), N, N, R)
+    assert graph.fwd.n_hubs >= 21 and graph.bwd.n_hubs >= 1
+    for d in (8, 64, 256):
+        x = torch.randn(N, d, generator=g)
+        H = ops.aggregate_fwd(graph, x.to(DEV)).cpu()
+        Href = _means_ref(x, torch.stack([src, dst]), rel, N, R)
+        torch.testing.assert_close(H, Href, rtol=1e-5, atol=1e-5)
+        comp = torch.randn(R, 3, generator=g)
+        Z = ops.aggregate_fwd(graph, x.to(DEV), comp=comp.to(DEV)).cpu()
+        Zref = torch.einsum("rb,nrd->nbd", comp, Href.reshape(N, R, d)).reshape(N, 3 * d)
+        torch.testing.assert_close(Z, Zref, rtol=1e-4, atol=1e-4)
+        gH = torch.randn(N, R * d, generator=g)
+        init = torch.randn(N, d, generator=g)
+        gx = ops.aggregate_bwd(graph, gH.to(DEV), d, init=init.to(DEV)).cpu()
+        cnt = torch.bincount(dst * R + rel, minlength=N * R).clamp(min=1).float()
+        contrib = gH.reshape(N, R, d)[dst, rel] / cnt[dst * R + rel][:, None]
+        gref = init.clone().index_add_(0, src, contrib)
+        torch.testing.assert_close(gx, gref, rtol=1e-4, atol=1e-4)
+        assert torch.equal(ops.aggregate_fwd(graph, x.to(DEV)).cpu(), H)                            # same bits again

@@ -26,7 +26,7 @@ def test_library_exports_every_header_symbol(lib_built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rgcn_b200.h but not exported"
     assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
-    assert _lib.load().rgcn_abi_version() == 1
+    assert _lib.load().rgcn_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_argument_errors_without_gpu(lib_built):
@@ -46,7 +46,7 @@ def test_library_argument_errors_without_gpu(lib_built):
 def test_csr_struct_matches_header_layout():
     from primekg_rgcn_linkprediction_b200 import _lib
     # 3 pointers, 2 int64, 4 int32, 2 pointers
-    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 2 * 8 + 4 * 4 + 2 * 8
+    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 2 * 8 + 4 * 4 + 3 * 8
     assert _lib.CsrStruct.hub_keys.offset == 56
 
 
