@@ -226,7 +226,7 @@ def run_ours(args, rank, world, local_rank):
         p.grad = None
 
     # ---- the same step captured once into a CUDA graph (GraphedTrainStep) ----
-    gstep = pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel())
+    gstep = pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel(), flat_grads=world > 1)
     gstep.load_batch(*d_batch)
 
     def allreduce_flat():

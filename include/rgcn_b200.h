@@ -50,6 +50,9 @@ int rgcn_abi_version(void);
 int rgcn_last_error(char* buf, size_t buf_len);
 /* 0 when the current device is compute capability 10.x, RGCN_EUNSUPPORTED otherwise. */
 int rgcn_check_device(void);
+/* Lets kernels of the current device load / store memory of `peer_device` (needed once per peer when the peer
+ * buffers were mapped with CUDA IPC; a no-op for the device itself or when already enabled). */
+int rgcn_enable_peer_access(int32_t peer_device);
 /* Number of kernels of this library launched so far by this process (all threads). */
 int64_t rgcn_launch_count(void);
 
@@ -171,6 +174,11 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
  * call itself, so a captured CUDA graph draws a fresh mask on every replay.  Backward needs no stored mask: the
  * output is zero exactly where ReLU or dropout killed the element, so rgcn_split_planes(gO, relu_mask = out,
  * mask_scale = 1 / (1 - p)) yields G (mask_scale multiplies the masked values; pass 1 without dropout).
+ * Fused all-gather (destination-range partition over the GPUs of one NVSwitch domain): peer_out_host is a HOST array
+ * of n_peer (<= 8) device pointers to feature buffers [*, peer_ld] that live in other GPUs' memory and are mapped
+ * into this process (CUDA IPC / symmetric memory).  fwd's epilogue stores every finished tile into `out` AND into
+ * rows peer_row0 + i of each peer buffer, so the transfer of the layer's output overlaps its own GEMM tile by tile
+ * and the next layer's all-gather disappears; the caller only has to put a cross-GPU barrier before the next read.
  * mode 0 = "fp32": hi*hi + hi*lo + lo*hi (error ~1e-5 relative); mode 1 = "bf16": hi*hi only.
  * Everything is deterministic (fixed split-K / partial reduction order).  K1, K2, d_out multiples of 4.
  * ------------------------------------------------------------------------------------------ */
@@ -183,6 +191,7 @@ int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t lda, int32_t 
                        const float* W1, const float* W2, const float* bias, int32_t relu,
                        int64_t n_rows, int32_t d_out, float* out, int64_t ldo, int32_t mode,
                        float dropout_p, uint32_t dropout_seed, unsigned long long* dropout_counter,
+                       float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out,
                          const float* W1, int32_t K1, const float* W2, int32_t K2,
@@ -193,6 +202,25 @@ int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t lda, int32_
                          const float* colsum_partial, int32_t n_colsum,
                          float* gW1, float* gW2, float* gbias, int32_t mode,
                          void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-memory exchange kernels of the destination-range partitioned path (graphs too large for one GPU; the
+ * reference is single-device, this is the scale-out of src/models/rgcn.py:123-128 and of its autograd backward).
+ * All `*_host` arguments are HOST arrays of DEVICE pointers into buffers of the n GPUs of one NVSwitch domain,
+ * peer-mapped into this process; entry q belongs to rank q.  No collective library call is involved: the caller
+ * places a cross-GPU barrier between a producer and its consumers.
+ *   rgcn_p2p_push_rows    : dst_q[row0 + i, :] = src[i, :] for every q  (all-gather by push of this rank's shard)
+ *   rgcn_p2p_reduce_split : v[i, :] = extra[i, :] + sum_q part_q[row0 + i, :]  in rank order (deterministic reduce-
+ *                           scatter by pull), then optionally zeroed where relu_mask <= 0 and scaled by mask_scale,
+ *                           written as fp32 `out` and / or as bf16 planes hi (, lo) with the same column-sum partials
+ *                           as rgcn_split_planes (rgcn_split_planes_blocks(rows, cols) rows of `cols` floats).
+ * ------------------------------------------------------------------------------------------ */
+int rgcn_p2p_push_rows(const float* src, int64_t ld_src, int64_t rows, int32_t cols,
+                       float* const* dst_host, int32_t n_dst, int64_t row0, int64_t ld_dst, rgcn_stream_t stream);
+int rgcn_p2p_reduce_split(const float* const* part_host, int32_t n_part, int64_t row0, int64_t ld_part,
+                          const float* extra, int64_t ld_extra, const float* relu_mask, int64_t ldm, float mask_scale,
+                          int64_t rows, int32_t cols, float* out, int64_t ldo, void* hi, void* lo, int64_t ldp,
+                          float* colsum_partial, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * DistMult decoder.  Replaces node_embeddings[head], [tail] (src/models/rgcn.py:325-326) +

@@ -36,6 +36,7 @@ PROTOTYPES = {
     "rgcn_last_error": (C.c_int, [C.c_char_p, sz]),
     "rgcn_check_device": (C.c_int, []),
     "rgcn_launch_count": (i64, []),
+    "rgcn_enable_peer_access": (C.c_int, [i32]),
     "rgcn_csr_build_workspace_bytes": (sz, [i64, i64, i64, i32]),
     "rgcn_csr_build": (C.c_int, [p, p, p, i64, i64, i64, i32, p, p, p, p, p, p, p, p, p, p, sz, p]),
     "rgcn_hub_plan_workspace_bytes": (sz, [i64, i64]),
@@ -48,7 +49,9 @@ PROTOTYPES = {
     "rgcn_split_planes": (C.c_int, [p, i64, p, i64, i64, i32, p, p, i64, p, C.c_float, p]),
     "rgcn_transform_workspace_bytes": (sz, [i64, i32, i32]),
     "rgcn_transform_fwd": (C.c_int, [p, p, i64, i32, i32, p, p, p, i32, i64, i32, p, i64, i32, C.c_float, C.c_uint32, p,
-                                     p, sz, p]),
+                                     p, i32, i64, i64, p, sz, p]),
+    "rgcn_p2p_push_rows": (C.c_int, [p, i64, i64, i32, p, i32, i64, i64, p]),
+    "rgcn_p2p_reduce_split": (C.c_int, [p, i32, i64, i64, p, i64, p, i64, C.c_float, i64, i32, p, i64, p, p, i64, p, p]),
     "rgcn_transform_dgrad": (C.c_int, [p, p, i64, i32, p, i32, p, i32, i64, p, i64, i32, p, sz, p]),
     "rgcn_transform_wgrad": (C.c_int, [p, p, i64, i32, i32, p, p, i64, i32, i64, p, i32, p, p, p, i32, p, sz, p]),
     "rgcn_distmult_fwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, i64, i32, p, p]),

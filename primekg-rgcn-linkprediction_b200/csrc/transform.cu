@@ -34,6 +34,7 @@ constexpr int BM = 128;         // UMMA M
 constexpr int BK = 64;          // K per stage for K-major operands (= one 128-byte swizzle row of bf16)
 constexpr int BNMAX = 256;      // UMMA N max = TMEM columns per accumulator
 constexpr int WG_BK = 32;       // nodes per stage in the weight-gradient kernel
+constexpr int kMaxPeers = 8;    // GPUs of one NVSwitch domain the fused all-gather epilogue can address
 
 // ------------------------------------------------------------------------------------------------
 // fp32 -> bf16 planes
@@ -153,6 +154,9 @@ struct GemmKParams {
   float* out; int64_t ldo;
   // fused dropout after the ReLU (training): keep iff drop_bits(...) >= drop_thresh, kept values times drop_scale
   uint32_t drop_thresh; float drop_scale; uint32_t drop_seed; const unsigned long long* drop_ctr;
+  // fused all-gather: every output tile is also stored into the same-shaped slot (rows peer_row0 ...) of up to
+  // kMaxPeers feature buffers that live in OTHER GPUs' memory (peer-mapped, NVLink stores issued by the epilogue)
+  float* peer_out[kMaxPeers]; int n_peer; int64_t peer_row0; int64_t peer_ld;
 };
 
 constexpr int KBN = 128;                      // N tile of the persistent kernel: two accumulators fit 256 TMEM columns
@@ -265,6 +269,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               v.w = (h1 >> 16) >= p.drop_thresh ? v.w * p.drop_scale : 0.f;
             }
             *reinterpret_cast<float4*>(p.out + row * p.ldo + n0 + cc + c4) = v;
+            for (int q = 0; q < p.n_peer; ++q)
+              *reinterpret_cast<float4*>(p.peer_out[q] + (p.peer_row0 + row) * p.peer_ld + n0 + cc + c4) = v;
           }
         }
         __syncwarp();
@@ -478,12 +484,22 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
 
 // fixed-order reduction of the split partials into gW1 [K1, N], gW2 [K2, N]: 4 lanes per output float4, lane q adds
 // splits q, q+4, ... in order, then a fixed two-step shuffle combine (deterministic)
+__device__ __forceinline__ void colsum_reduce_block(const float* __restrict__ part, int n_part, int N, int c4,
+                                                    float* __restrict__ out);
+
+// The last N / 4 blocks of the launch reduce the bias-gradient column sums instead (one launch for both).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int m_pad,
                                                            int ldp, int K1, int K2, int N, float* __restrict__ gw1,
-                                                           float* __restrict__ gw2) {
+                                                           float* __restrict__ gw2, int main_blocks,
+                                                           const float* __restrict__ colsum_part, int n_colsum,
+                                                           float* __restrict__ gbias) {
+  if ((int)blockIdx.x >= main_blocks) {
+    colsum_reduce_block(colsum_part, n_colsum, N, blockIdx.x - main_blocks, gbias);
+    return;
+  }
   const int64_t total = (int64_t)(K1 + K2) * (N >> 2);
   const int q = threadIdx.x & 3;
-  const int64_t stride_i = (int64_t)gridDim.x * (blockDim.x >> 2);
+  const int64_t stride_i = (int64_t)main_blocks * (blockDim.x >> 2);
   for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); i < ((total + 7) & ~int64_t(7));
        i += stride_i) {
     const bool valid = i < total;
@@ -508,10 +524,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 // g_bias[n] = sum over the column-sum partials [n_part, N]: one block per float4 column; thread t adds partials
 // t, t+256, ...; fixed shuffle tree inside each warp, then the 8 warp sums in order => deterministic
-__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int n_part, int N,
-                                                            float* __restrict__ out) {
+__device__ __forceinline__ void colsum_reduce_block(const float* __restrict__ part, int n_part, int N, int c4,
+                                                    float* __restrict__ out) {
   __shared__ float4 wsum[8];
-  const int c4 = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = threadIdx.x; p < n_part; p += 256) add4(s, *reinterpret_cast<const float4*>(part + (size_t)p * N + c4 * 4));
   for (int o = 16; o; o >>= 1) {
@@ -708,8 +724,11 @@ extern "C" size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K, int3
 extern "C" int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t lda, int32_t K1, int32_t K2, const float* W1,
                                   const float* W2, const float* bias, int32_t relu, int64_t n_rows, int32_t d_out,
                                   float* out, int64_t ldo, int32_t mode, float dropout_p, uint32_t dropout_seed,
-                                  unsigned long long* dropout_counter, void* workspace, size_t workspace_bytes,
+                                  unsigned long long* dropout_counter, float* const* peer_out_host, int32_t n_peer,
+                                  int64_t peer_row0, int64_t peer_ld, void* workspace, size_t workspace_bytes,
                                   rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n_peer >= 0 && n_peer <= kMaxPeers && (n_peer == 0 || (peer_out_host && peer_ld % 4 == 0 && peer_row0 >= 0)),
+                 "transform_fwd: bad peer outputs (at most %d, ld %% 4 == 0)", kMaxPeers);
   RGCN_CHECK_ARG(n_rows >= 0 && K1 > 0 && K2 >= 0 && d_out > 0, "transform_fwd: bad sizes");
   RGCN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "transform_fwd: dropout_p must be in [0, 1)");
   RGCN_CHECK_ARG(dropout_p == 0.f || (dropout_counter && relu), "transform_fwd: fused dropout needs relu = 1 and a counter");
@@ -748,6 +767,11 @@ extern "C" int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t ld
     p.drop_thresh = th >= 65535.0 ? 65535u : (th < 1.0 ? 1u : (uint32_t)th);
     p.drop_scale = 1.f / (1.f - dropout_p);
     p.drop_seed = dropout_seed; p.drop_ctr = dropout_counter;
+  }
+  p.n_peer = n_peer; p.peer_row0 = peer_row0; p.peer_ld = peer_ld;
+  for (int q = 0; q < n_peer; ++q) {
+    RGCN_CHECK_ARG(peer_out_host[q] && ((uintptr_t)peer_out_host[q] & 15) == 0, "transform_fwd: peer output %d is null or misaligned", q);
+    p.peer_out[q] = peer_out_host[q];
   }
   return launch_kmajor(p, A_hi, A_lo, lda, K, bhi, blo, t.n_pad, k_pad, t.n_tiles, split, st);
 }
@@ -839,12 +863,10 @@ extern "C" int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t 
     RGCN_LAUNCH_CHECK();
   }
   const int64_t total = (int64_t)K * (d_out / 4);
-  wgrad_reduce_kernel<<<grid_cap((total + 63) / 64, 4736), 256, 0, st>>>(p.partial, n_rows > 0 ? splits : 0, m_tiles * BM,
-                                                                          t.n_pad, K1, K2, d_out, gW1, gW2);
+  const unsigned main_blocks = grid_cap((total + 63) / 64, 4736);
+  wgrad_reduce_kernel<<<main_blocks + (gbias ? (unsigned)(d_out / 4) : 0u), 256, 0, st>>>(
+      p.partial, n_rows > 0 ? splits : 0, m_tiles * BM, t.n_pad, K1, K2, d_out, gW1, gW2, (int)main_blocks,
+      colsum_partial, n_colsum, gbias);
   RGCN_LAUNCH_CHECK();
-  if (gbias) {
-    colsum_reduce_kernel<<<(unsigned)(d_out / 4), 256, 0, st>>>(colsum_partial, n_colsum, d_out, gbias);
-    RGCN_LAUNCH_CHECK();
-  }
   return RGCN_OK;
 }

@@ -1,0 +1,191 @@
+"""Destination-range partitioned RGCN whose exchange steps are done by OUR kernels over peer-mapped memory
+(NVLink loads / stores) instead of collective-library calls — the fused form of ``dist.py``.
+
+Per layer, forward (rank p owns rows [lo_p, hi_p), padded to ``max_n``):
+
+    X_full (all rows, this rank's copy)  --aggregate-->  H  --tcgen05 transform, epilogue stores each finished
+    tile into the row slot of EVERY rank's next X_full over NVLink-->  [barrier]
+
+so the all-gather of the next layer's input is the transform's own epilogue and overlaps its MMA main loop tile by
+tile; only a device-side barrier separates the layers.  Backward:
+
+    [barrier]  pull this rank's rows of every rank's full-length partial grad-X over NVLink, sum in RANK ORDER,
+    add the local root-term gradient, apply the ReLU / dropout mask and emit the bf16 planes G + bias-gradient
+    partials (one kernel = reduce-scatter + mask + operand conversion)  ->  dgrad  ->  transposed-CSR gather into
+    this rank's partial buffer  ->  wgrad
+
+Weight gradients are all-reduced once per step as one flat NCCL call (plumbing).  Two halves of one peer buffer
+alternate between layers; the per-layer barrier is what makes the reuse safe (a rank can only be one layer ahead).
+Everything is deterministic: fixed reduction orders everywhere, no atomics.
+
+The NCCL form in ``dist.py`` (all-gather / reduce-scatter / all-reduce with autograd) stays as the baseline this
+is measured against and as the form the CPU (gloo) tests exercise.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from .conv import default_mode
+from .dist import PartitionPlan, PartitionedRGCN
+from .peer import PeerBuffer
+
+
+class _Exchange:
+    """The two peer buffers (features forward, partial gradients backward), each cut into two halves."""
+
+    def __init__(self, plan: PartitionPlan, rank: int, dims: List[int], device: torch.device):
+        self.rank, self.world = rank, plan.world
+        self.n_total = plan.world * plan.max_n
+        self.max_n = plan.max_n
+        self.row0 = rank * plan.max_n
+        self.half = self.n_total * max(dims)               # floats per half
+        self.half = (self.half + 63) // 64 * 64
+        self.x = PeerBuffer(2 * self.half * 4, device)
+        self.g = PeerBuffer(2 * self.half * 4, device)
+
+    def x_view(self, k: int, d: int) -> torch.Tensor:
+        return self.x.view(self.n_total, d, (k % 2) * self.half)
+
+    def g_view(self, k: int, d: int) -> torch.Tensor:
+        return self.g.view(self.n_total, d, (k % 2) * self.half)
+
+    def x_ptrs(self, k: int) -> List[int]:
+        return self.x.peer_ptrs((k % 2) * self.half)
+
+    def g_ptrs(self, k: int) -> List[int]:
+        return self.g.peer_ptrs((k % 2) * self.half)
+
+
+class _FusedEncoderFn(torch.autograd.Function):
+    """(table shard, W_1, root_1, bias_1, ..., W_L, root_L, bias_L) -> all ranks' final embeddings [P * max_n, H]
+    (this rank's copy; rows in padded id order).  Its gradient is the full-length PARTIAL gradient of this rank."""
+
+    @staticmethod
+    def forward(ctx, ex: _Exchange, graph, mode: str, drops, x0, *params):
+        L = len(params) // 3
+        n, row0 = ex.max_n, ex.row0
+        x0 = x0.contiguous()
+        ops.p2p_push_rows(x0, ex.x_ptrs(0), row0, x0.size(1))
+        ex.x.barrier()
+        saved, outs = [], []
+        for l in range(L):
+            W, root, bias = params[3 * l: 3 * l + 3]
+            R, d_in, d_out = W.shape
+            K1, K2 = R * d_in, d_in
+            x_full = ex.x_view(l, d_in)
+            A = ops.alloc_planes(n, K1 + K2, mode, x0.device)
+            ops.aggregate_fwd(graph, x_full, planes=A)
+            ops.split_planes(x_full[row0:row0 + n], A, col0=K1)
+            p_drop, seed, ctr = drops[l] if drops[l] is not None else (0.0, 0, None)
+            last = l == L - 1
+            out = ops.transform_fwd(A, K1, K2, W.reshape(K1, d_out), root, bias, not last, mode, p_drop, seed, ctr,
+                                    peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out)
+            ex.x.barrier()
+            saved += [A[0], A[1], W, root]
+            outs.append(None if last else out)          # post-ReLU/dropout output = the backward mask
+        ctx.ex, ctx.graph, ctx.mode, ctx.L = ex, graph, mode, L
+        ctx.p_drops = [d[0] if d is not None else 0.0 for d in drops]
+        ctx.d0 = x0.size(1)
+        ctx.save_for_backward(*saved, *[o for o in outs if o is not None])
+        d_last = params[3 * (L - 1)].shape[2]
+        return ex.x_view(L, d_last)
+
+    @staticmethod
+    def backward(ctx, g_full):
+        ex, graph, mode, L = ctx.ex, ctx.graph, ctx.mode, ctx.L
+        n, row0 = ex.max_n, ex.row0
+        t = ctx.saved_tensors
+        masks = list(t[4 * L:])
+        dev = g_full.device
+        d_last = t[4 * (L - 1) + 2].shape[2]
+        ex.g_view(L, d_last).copy_(g_full)              # this rank's partial gradient of ALL rows, peer visible
+        ex.g.barrier()
+        extra = None
+        grads = [None] * (3 * L)
+        for l in range(L - 1, -1, -1):
+            A_hi, A_lo, W, root = t[4 * l: 4 * l + 4]
+            R, d_in, d_out = W.shape
+            K1, K2 = R * d_in, d_in
+            mask = masks[l] if l < L - 1 else None
+            G = ops.alloc_planes(n, d_out, mode, dev)
+            # reduce-scatter by pull + root-term gradient + ReLU/dropout mask + operand conversion, one kernel
+            _, colsum = ops.p2p_reduce_split(ex.g_ptrs(l + 1), row0, d_out, n, d_out, dev, extra=extra, relu_mask=mask,
+                                             mask_scale=1.0 / (1.0 - ctx.p_drops[l]), planes=G, colsum=True)
+            Wf = W.reshape(K1, d_out)
+            gA = ops.transform_dgrad(G, d_out, Wf, root, mode)
+            ops.aggregate_bwd(graph, gA, d_in, init=None, out=ex.g_view(l, d_in))
+            extra = gA[:, K1:]
+            gWf, groot, gb = ops.transform_wgrad((A_hi, A_lo), K1, K2, G, d_out, colsum, mode)
+            grads[3 * l: 3 * l + 3] = [gWf.view(R, d_in, d_out), groot, gb]
+            ex.g.barrier()
+        gx0, _ = ops.p2p_reduce_split(ex.g_ptrs(0), row0, ctx.d0, n, ctx.d0, dev, extra=extra, want_fp32=True)
+        # replicated weights: one flat all-reduce (sum) for all layers
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        off = 0
+        for i, g in enumerate(grads):
+            grads[i] = flat[off: off + g.numel()].view_as(g)
+            off += g.numel()
+        return (None, None, None, None, gx0, *grads)
+
+
+class FusedPartitionedRGCN(PartitionedRGCN):
+    """``PartitionedRGCN`` (same parameters, same plan, same graph shard) with the peer-memory exchange.
+    ``forward()`` returns ALL ranks' output rows ``[P * max_n, hidden]`` (padded id order) — the final all-gather is
+    the last transform's epilogue too."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._ex: Optional[_Exchange] = None
+
+    def _exchange(self) -> _Exchange:
+        if self._ex is None:
+            dims = [self.convs[0].in_channels] + [c.out_channels for c in self.convs]
+            self._ex = _Exchange(self.plan, self.rank, dims, self.node_embeddings.device)
+        return self._ex
+
+    def forward(self) -> torch.Tensor:
+        if not self.node_embeddings.is_cuda:
+            raise RuntimeError("FusedPartitionedRGCN needs CUDA devices with peer access; dist.PartitionedRGCN is the "
+                               "collective-library form")
+        last = len(self.convs) - 1
+        params, drops = [], []
+        for li, conv in enumerate(self.convs):
+            params += [conv.relation_weights(), conv.root, conv.bias]
+            p = self.dropout.p if (self.training and li != last) else 0.0
+            if p >= 1.0:
+                raise ValueError("fused dropout needs p < 1")
+            drops.append(conv.dropout_state(p, self.node_embeddings.device) if p > 0.0 else None)
+        mode = self.convs[0].mode or default_mode()
+        return _FusedEncoderFn.apply(self._exchange(), self.graph, mode, drops, self.node_embeddings, *params)
+
+
+class FusedPartitionedModel(nn.Module):
+    """Encoder shard with peer-memory exchange + replicated DistMult decoder; the interface of ``dist.PartitionedModel``."""
+
+    def __init__(self, plan: PartitionPlan, rank: int, num_relations: int, embedding_dim: int = 64,
+                 hidden_dim: int = 128, dropout: float = 0.5, decoder_dropout: float = 0.0,
+                 num_bases: Optional[int] = None, num_layers: int = 2, seed: int = 42):
+        super().__init__()
+        from .modules import LinkPredictor
+        self.plan = plan
+        self.encoder = FusedPartitionedRGCN(plan, rank, num_relations, embedding_dim, hidden_dim, dropout, num_bases,
+                                            num_layers, seed)
+        state = torch.random.get_rng_state()
+        torch.manual_seed(seed + 12345)                       # identical decoder on every rank
+        self.decoder = LinkPredictor(num_relations, hidden_dim, decoder_dropout)
+        torch.random.set_rng_state(state)
+
+    def forward(self, heads: torch.Tensor, tails: torch.Tensor, rels: torch.Tensor) -> torch.Tensor:
+        emb = self.encoder()                                  # [P * max_n, hidden], padded id order
+        return self.decoder.score_pairs(emb, self.plan.to_padded(heads), self.plan.to_padded(tails), rels)
+
+    def allreduce_decoder_grads(self) -> None:
+        for p in self.decoder.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)

@@ -3,8 +3,9 @@
 At the reference's sizes one full-graph step is ~50 kernels of 3-80 us; issued eagerly from Python the host is the
 limiter.  ``GraphedTrainStep`` captures one step — ``model(edge_index, edge_type, heads, tails, rels)`` ->
 ``BCEWithLogitsLoss`` -> ``backward()`` (reference src/train.py:291-306) — into a CUDA graph over static input buffers
-and replays it; gradients land in the parameters' ``.grad`` as usual, so the optimiser / clipping code of the caller
-(src/train.py:309-318) stays as it is.  Dropout masks are re-drawn on every replay (torch's graph-safe Philox state).
+and replays it; gradients land in the parameters' ``.grad`` as usual (each replay OVERWRITES them: the step owns the
+buffers, so gradient accumulation over several batches needs ``flat_grads=True`` and a caller-side sum), so the
+optimiser / clipping code of the caller (src/train.py:309-318) stays as it is.  Dropout masks are re-drawn on every replay (torch's graph-safe Philox state).
 
 Construct it before (or after dropping) any eager autograd graph of the same model: a live graph keeps the
 parameters' AccumulateGrad nodes bound to the stream they were created on, which a capture cannot depend on.
@@ -20,7 +21,7 @@ from .ops import bce_with_logits
 
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, edge_index: torch.Tensor, edge_type: torch.Tensor, batch_size: int,
-                 loss_fn: Optional[Callable] = None, warmup: int = 3):
+                 loss_fn: Optional[Callable] = None, warmup: int = 3, flat_grads: bool = False):
         if not edge_index.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors")
         dev = edge_index.device
@@ -31,13 +32,20 @@ class GraphedTrainStep:
         self.rels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
-        # static gradient buffers: views into ONE flat tensor, so zeroing is a single fill and a data-parallel
-        # caller all-reduces ``flat_grad`` in place (every p.grad sees the result)
-        self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.flat_grad = None
+        if flat_grads:
+            # static gradient buffers: views into ONE flat tensor, so zeroing is a single fill and a data-parallel
+            # caller all-reduces ``flat_grad`` in place (every p.grad sees the result); costs one accumulate per tensor
+            self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+            off = 0
+            for p in self.params:
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        else:
+            # the kernels' own output buffers (static inside the captured graph) become p.grad: no zero fill and
+            # no accumulate kernels
+            for p in self.params:
+                p.grad = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -48,13 +56,22 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.scores = self._step()
+        self._bind_grads()
 
     def _step(self):
-        self.flat_grad.zero_()
         scores = self.model(self.edge_index, self.edge_type, self.heads, self.tails, self.rels)
         loss = self.loss_fn(scores, self.labels)
-        loss.backward()
+        if self.flat_grad is not None:
+            self.flat_grad.zero_()
+            loss.backward()
+        else:
+            self._grads = torch.autograd.grad(loss, self.params, allow_unused=True)
         return loss.detach(), scores.detach()
+
+    def _bind_grads(self) -> None:
+        if self.flat_grad is None:
+            for p, g in zip(self.params, self._grads):
+                p.grad = g
 
     def load_batch(self, heads, tails, rels, labels, non_blocking: bool = True) -> None:
         """Copy one batch (host, pinned or device tensors) into the static input buffers."""
@@ -68,4 +85,5 @@ class GraphedTrainStep:
         if heads is not None:
             self.load_batch(heads, tails, rels, labels)
         self.graph.replay()
+        self._bind_grads()          # (a caller may have set .grad to None, e.g. optimizer.zero_grad())
         return self.loss

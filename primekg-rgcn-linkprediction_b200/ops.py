@@ -59,8 +59,10 @@ def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False, comp: Op
     return H
 
 
-def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """gX[j] = init[j] + sum_r sum_{(j->i, r)} gH[i, r*d:(r+1)*d] / max(|N_r(i)|, 1)  over the transposed CSR."""
+def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gX[j] = init[j] + sum_r sum_{(j->i, r)} gH[i, r*d:(r+1)*d] / max(|N_r(i)|, 1)  over the transposed CSR.
+    ``out``: write into this [n_src, d] fp32 tensor (e.g. a peer-visible buffer) instead of allocating."""
     lib = _lib.load()
     gH = _f32c(gH, "gH")
     if gH.size(0) != g.n_dst or gH.size(1) < g.R * d:
@@ -69,7 +71,12 @@ def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Te
         init = _f32c(init, "init")
         if init.size(0) != g.n_src or init.size(1) < d:
             raise ValueError("init must be [n_src, >= d]")
-    gX = torch.empty(g.n_src, d, dtype=torch.float32, device=gH.device)
+    if out is None:
+        gX = torch.empty(g.n_src, d, dtype=torch.float32, device=gH.device)
+    else:
+        gX = out
+        if gX.dtype != torch.float32 or gX.shape != (g.n_src, d) or gX.stride(1) != 1 or gX.stride(0) % 4:
+            raise ValueError("out must be a row-major float32 [n_src, d] tensor")
     ws = g.bwd.workspace(d)
     _lib.check(lib.rgcn_aggregate_bwd(g.bwd.ref, _ptr(gH), gH.stride(0), d, _ptr(init),
                                       0 if init is None else init.stride(0), _ptr(gX), gX.stride(0), _ptr(ws),
@@ -221,10 +228,18 @@ def dropout_counter(device) -> torch.Tensor:
     return torch.zeros(1, dtype=torch.int64, device=device)
 
 
+def _ptr_array(ptrs):
+    """HOST array of device pointers (the ``*_host`` arguments of the C ABI)."""
+    return (C.c_void_p * len(ptrs))(*[int(a) for a in ptrs])
+
+
 def transform_fwd(planes, K1: int, K2: int, W1: torch.Tensor, W2: Optional[torch.Tensor],
                   bias: Optional[torch.Tensor], relu: bool, mode: str, dropout_p: float = 0.0,
-                  dropout_seed: int = 0, dropout_ctr: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = A @ [W1 ; W2] + bias (, ReLU (, dropout)) with A given as bf16 planes [n, K1 + K2] — tcgen05 kernel."""
+                  dropout_seed: int = 0, dropout_ctr: Optional[torch.Tensor] = None, peer_out=None,
+                  peer_row0: int = 0, peer_ld: int = 0) -> torch.Tensor:
+    """out = A @ [W1 ; W2] + bias (, ReLU (, dropout)) with A given as bf16 planes [n, K1 + K2] — tcgen05 kernel.
+    ``peer_out``: device pointers of other GPUs' (peer-mapped) feature buffers [*, peer_ld]; the epilogue also stores
+    every tile into rows ``peer_row0 + i`` of each of them (fused all-gather)."""
     lib = _lib.load()
     hi, lo = planes
     n = hi.size(0)
@@ -242,6 +257,8 @@ def transform_fwd(planes, K1: int, K2: int, W1: torch.Tensor, W2: Optional[torch
     _lib.check(lib.rgcn_transform_fwd(_ptr(hi), _ptr(lo), hi.stride(0), K1, K2, _ptr(W1), _ptr(W2), _ptr(bias),
                                       int(relu), n, d_out, _ptr(out), out.stride(0), _mode_id(mode), float(dropout_p),
                                       int(dropout_seed) & 0xFFFFFFFF, _ptr(dropout_ctr if dropout_p > 0 else None),
+                                      _ptr_array(peer_out) if peer_out else None, len(peer_out) if peer_out else 0,
+                                      int(peer_row0), int(peer_ld),
                                       _ptr(ws), ws.numel(), _stream(hi.device)), "rgcn_transform_fwd")
     return out
 
@@ -284,6 +301,39 @@ def transform_wgrad(a_planes, K1: int, K2: int, g_planes, d_out: int, colsum_par
                                         _ptr(gb), _mode_id(mode), _ptr(ws), ws.numel(), _stream(dev)),
                "rgcn_transform_wgrad")
     return gW1, gW2, gb
+
+
+# ---- peer-memory exchange (destination-range partition over the GPUs of one NVSwitch domain) -----------
+def p2p_push_rows(src: torch.Tensor, dst_ptrs, row0: int, ld_dst: int) -> None:
+    """dst_q[row0 + i, :] = src[i, :] for every peer-mapped destination buffer (all-gather by push)."""
+    lib = _lib.load()
+    src = _f32c(src, "src")
+    _lib.check(lib.rgcn_p2p_push_rows(_ptr(src), src.stride(0), src.size(0), src.size(1), _ptr_array(dst_ptrs),
+                                      len(dst_ptrs), int(row0), int(ld_dst), _stream(src.device)), "rgcn_p2p_push_rows")
+
+
+def p2p_reduce_split(part_ptrs, row0: int, ld_part: int, rows: int, cols: int, device,
+                     extra: Optional[torch.Tensor] = None, relu_mask: Optional[torch.Tensor] = None,
+                     mask_scale: float = 1.0, want_fp32: bool = False, planes=None, colsum: bool = False):
+    """v = extra + sum_q part_q[row0 : row0 + rows] (rank order), masked like ``split_planes``; returns
+    (fp32 tensor | None, column-sum partials | None) and fills ``planes`` when given (reduce-scatter by pull)."""
+    lib = _lib.load()
+    if extra is not None:
+        extra = _f32c(extra, "extra")
+    if relu_mask is not None:
+        relu_mask = _f32c(relu_mask, "relu_mask")
+    out = torch.empty(rows, cols, dtype=torch.float32, device=device) if want_fp32 else None
+    hi, lo = planes if planes is not None else (None, None)
+    part = None
+    if colsum:
+        nb = lib.rgcn_split_planes_blocks(rows, cols)
+        part = torch.empty(max(nb, 1), cols, dtype=torch.float32, device=device)
+    _lib.check(lib.rgcn_p2p_reduce_split(_ptr_array(part_ptrs), len(part_ptrs), int(row0), int(ld_part), _ptr(extra),
+                                         0 if extra is None else extra.stride(0), _ptr(relu_mask),
+                                         0 if relu_mask is None else relu_mask.stride(0), float(mask_scale), rows, cols,
+                                         _ptr(out), cols, _ptr(hi), _ptr(lo), 0 if hi is None else hi.stride(0),
+                                         _ptr(part), _stream(device)), "rgcn_p2p_reduce_split")
+    return out, part
 
 
 # ---- fused BCE-with-logits (the loss of reference src/train.py:139, :300) ------------------------------

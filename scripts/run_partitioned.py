@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", action="store_true", help="compare with the single-GPU model on rank 0")
     ap.add_argument("--mode", default="fp32")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "fused"],
+                    help="nccl: all-gather / reduce-scatter calls (dist.py); fused: our kernels over peer memory (dist_fused.py)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
@@ -39,8 +41,10 @@ def main():
     kg = synth.scaled_kg(args.nodes, args.edges, args.relations, seed=42, device=dev)     # same graph on every rank
     ei, et = kg.edge_index, kg.edge_type
     plan = D.plan_partition(ei[1], kg.num_nodes, world)
-    model = D.PartitionedModel(plan, rank, args.relations, args.embedding, args.hidden, dropout=0.0,
-                               decoder_dropout=0.0, num_layers=args.layers, seed=42).to(dev)
+    from primekg_rgcn_linkprediction_b200 import dist_fused as DF
+    cls = DF.FusedPartitionedModel if args.exchange == "fused" else D.PartitionedModel
+    model = cls(plan, rank, args.relations, args.embedding, args.hidden, dropout=0.0,
+                decoder_dropout=0.0, num_layers=args.layers, seed=42).to(dev)
     model.encoder.build_graph(ei, et)
     model.train()
     B = 2048
@@ -109,7 +113,9 @@ def main():
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        report.update({"ms_per_step": float(t), "edges_per_sec": int(et.numel()) / (float(t) * 1e-3), "mode": args.mode})
+        report.update({"ms_per_step": float(t), "edges_per_sec": int(et.numel()) / (float(t) * 1e-3), "mode": args.mode,
+                       "exchange": args.exchange,
+                       "peer_memory": getattr(getattr(model.encoder, "_ex", None), "x", None) and model.encoder._ex.x.kind})
         print(json.dumps(report), flush=True)
     dist.destroy_process_group()
 

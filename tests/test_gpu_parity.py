@@ -403,7 +403,8 @@ def test_full_size_properties(pkg, cfg2):
                                rtol=1e-6, atol=1e-2)
 
 
-def test_graphed_step_matches_eager(pkg):
+@pytest.mark.parametrize("flat", [False, True])
+def test_graphed_step_matches_eager(pkg, flat):
     """GraphedTrainStep replays the same kernels: loss and every gradient equal the eager step bit for bit
     (dropout off so both draw nothing), and a second batch through the static buffers works."""
     g = load_golden("small_full")
@@ -420,7 +421,8 @@ def test_graphed_step_matches_eager(pkg):
         return loss.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}
 
     want_loss, want = eager()
-    step = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel())
+    step = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel(), flat_grads=flat)
+    assert (step.flat_grad is not None) == flat
     got_loss = step(*b).clone()
     torch.testing.assert_close(got_loss, want_loss, rtol=1e-6, atol=1e-7)
     for k, p in m.named_parameters():
