@@ -50,9 +50,6 @@ int rgcn_abi_version(void);
 int rgcn_last_error(char* buf, size_t buf_len);
 /* 0 when the current device is compute capability 10.x, RGCN_EUNSUPPORTED otherwise. */
 int rgcn_check_device(void);
-/* Lets kernels of the current device load / store memory of `peer_device` (needed once per peer when the peer
- * buffers were mapped with CUDA IPC; a no-op for the device itself or when already enabled). */
-int rgcn_enable_peer_access(int32_t peer_device);
 /* Number of kernels of this library launched so far by this process (all threads). */
 int64_t rgcn_launch_count(void);
 

@@ -36,7 +36,6 @@ PROTOTYPES = {
     "rgcn_last_error": (C.c_int, [C.c_char_p, sz]),
     "rgcn_check_device": (C.c_int, []),
     "rgcn_launch_count": (i64, []),
-    "rgcn_enable_peer_access": (C.c_int, [i32]),
     "rgcn_csr_build_workspace_bytes": (sz, [i64, i64, i64, i32]),
     "rgcn_csr_build": (C.c_int, [p, p, p, i64, i64, i64, i32, p, p, p, p, p, p, p, p, p, p, sz, p]),
     "rgcn_hub_plan_workspace_bytes": (sz, [i64, i64]),

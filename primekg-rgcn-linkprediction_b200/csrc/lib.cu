@@ -61,18 +61,3 @@ extern "C" int rgcn_check_device(void) {
   }
   return RGCN_OK;
 }
-
-extern "C" int rgcn_enable_peer_access(int32_t peer_device) {
-  int dev = 0, can = 0;
-  RGCN_CUDA(cudaGetDevice(&dev));
-  if (peer_device == dev) return RGCN_OK;
-  RGCN_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
-  if (!can) {
-    rgcn::set_error("device %d cannot access peer device %d (no NVLink / P2P path)", dev, peer_device);
-    return RGCN_EUNSUPPORTED;
-  }
-  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
-  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return RGCN_OK; }
-  RGCN_CUDA(e);
-  return RGCN_OK;
-}
