@@ -131,12 +131,22 @@ typedef struct rgcn_csr {
  *   TMA-loadable operand format of rgcn_transform_* in the fp32 mode.  ldh counts elements of the output type.
  *   comp != NULL (basis decomposition, comp [R, B] fp32): instead of R blocks the kernel writes the
  *   B basis-mixed blocks  Z[i, b*d:(b+1)*d] = sum_r comp[r, b] * h_r[i]   (H is then [n_rows, B*d]).
+ *   With a weighted CSR (g->w != NULL, i.e. the transposed orientation) h_r is the weighted SUM instead of
+ *   the mean: called on the transposed CSR with X = the masked output gradient this is the mirrored
+ *   backward of the basis form,  T_b[j] = sum_r comp[r, b] * sum_{e in seg_t(j, r)} w_t[e] * G[row_t[e]].
+ *   dot_p != NULL (needs comp, B <= 8): additionally  gc[r, b] = sum_i <h_r[i], dot_p[i, b*d:(b+1)*d]>, the
+ *   gradient of comp when dot_p = X @ [V_1 .. V_B]; written as rgcn_aggregate_blocks(g, d) partial rows of
+ *   R*B floats into gc_partial, to be summed with rgcn_reduce_partials (fixed order).
  * ------------------------------------------------------------------------------------------ */
 size_t rgcn_aggregate_workspace_bytes(const rgcn_csr_t* g, int32_t d);
+int64_t rgcn_aggregate_blocks(const rgcn_csr_t* g, int32_t d);
 int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d,
                        const float* comp, int32_t B,
                        void* H, void* H_lo, int64_t ldh, int32_t out_mode,
+                       const float* dot_p, int64_t ld_dot_p, float* gc_partial,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+/* out[c] = sum over the n_part rows of part[., n_cols] in a fixed order (deterministic). */
+int rgcn_reduce_partials(const float* part, int64_t n_part, int32_t n_cols, float* out, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Neighbourhood aggregation, backward (grad-X).  Replaces autograd's backward of the gather /
@@ -161,7 +171,7 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
  * mode 0, `lo` (value - hi rounded to bf16).  rgcn_aggregate_fwd(out_mode 1|2) writes H planes directly;
  * rgcn_split_planes converts any fp32 matrix, optionally zeroing elements where relu_mask <= 0 (ReLU
  * backward) and emitting per-block column sums (the bias gradient; rgcn_split_planes_blocks() rows of
- * `cols` floats).  Planes: base 16-byte aligned, ld (elements) a multiple of 8.
+ * `cols` floats) and / or the masked values themselves as fp32 (out_f32, nullable).  Planes: base 16-byte aligned, ld (elements) a multiple of 8.
  *   fwd   : out = A @ W + bias (, ReLU)                       [n_rows, d_out] fp32
  *   dgrad : gA  = G @ W^T                                     [n_rows, K1 + K2] fp32
  *   wgrad : [gW1 ; gW2] = A^T @ G ;  gbias = sum of the n_colsum column-sum partials
@@ -182,7 +192,7 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
 int64_t rgcn_split_planes_blocks(int64_t rows, int32_t cols);
 int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, int64_t rows,
                       int32_t cols, void* hi, void* lo, int64_t ldp, float* colsum_partial,
-                      float mask_scale, rgcn_stream_t stream);
+                      float mask_scale, float* out_f32, int64_t ld_f32, rgcn_stream_t stream);
 size_t rgcn_transform_workspace_bytes(int64_t n_rows, int32_t K, int32_t d_out);
 int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t lda, int32_t K1, int32_t K2,
                        const float* W1, const float* W2, const float* bias, int32_t relu,

@@ -39,6 +39,8 @@ struct AggParams {
   int64_t ldf;
   int32_t src_rel_stride;    // column offset per relation inside a gathered row (0 forward, d backward)
   int32_t d;
+  int32_t block_stride;      // columns between consecutive relation / basis blocks of the output (= d unless the
+                             // feature columns are processed in slices)
   const float* comp;         // [R, ldcomp] (MIX_BASIS)
   int32_t ldcomp;
   int32_t B;
@@ -49,6 +51,11 @@ struct AggParams {
   int64_t ldo;
   int32_t out_mode;          // 0: fp32, 1: bf16 (hi plane only), 2: bf16 hi + lo planes (hi + lo = value to 2^-17)
   float* partials;           // [n_chunks, d]
+  // MIX_BASIS side output (gradient of the basis coefficients): gc[r, b] += <h(i, r), dotP[i, b*d : (b+1)*d]>,
+  // written as one [R * B] partial per block, reduced afterwards in block order
+  const float* dotP;         // nullable, [n_rows, B * d]
+  int64_t ld_dotP;
+  float* gc_partial;         // [gridDim.x, R * B]
 };
 
 // ---- hub chunks: one block per chunk --------------------------------------------------------
@@ -155,15 +162,21 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) 
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
   constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   constexpr int U = U0 < G ? U0 : G;             // a batch never exceeds the index window
-  extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS
+  extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS, then [GROUPS][R * B] coefficient-gradient sums
+  const bool with_gc = MIX == MIX_BASIS && p.dotP != nullptr;
+  float* s_gc = s_comp + p.R * p.B;
   if (MIX == MIX_BASIS) {
     for (int t = threadIdx.x; t < p.R * p.B; t += 256) s_comp[t] = p.comp[(t / p.B) * p.ldcomp + (t % p.B)];
+    if (with_gc)
+      for (int t = threadIdx.x; t < GROUPS * p.R * p.B; t += 256) s_gc[t] = 0.f;
     __syncthreads();
   }
   const int lane = threadIdx.x % G, grp = threadIdx.x / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   const int64_t row = (int64_t)blockIdx.x * GROUPS + grp;
-  if (row >= p.n_rows) return;
+  if (row >= p.n_rows) {
+    if (!with_gc) return;
+  } else {
   const int R = p.R, d = p.d, nvec = p.d >> 2;
   const int64_t key0 = row * R;
   const int32_t* __restrict__ rowptr = p.rowptr + key0;
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) 
       if (MIX == MIX_NONE) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
-          if (act[k]) store_vec(p, row, r * d + vcol[k], acc[k]);
+          if (act[k]) store_vec(p, row, r * p.block_stride + vcol[k], acc[k]);
       } else if (MIX == MIX_SUM) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k) add4(mix[0][k], acc[k]);
@@ -304,6 +317,27 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) 
             for (int k = 0; k < VPL; ++k) fma4(mix[b][k], c, acc[k]);
           }
         }
+        if (with_gc) {
+          // <h(i, r), P_b[i]> for every basis b: lane-partial dots, one fixed butterfly per b, lane 0 accumulates
+          const float* __restrict__ Pr = p.dotP + row * p.ld_dotP;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            if (b < p.B) {
+              float dot = 0.f;
+#pragma unroll
+              for (int k = 0; k < VPL; ++k) {
+                if (act[k]) {
+                  const float4 q = ldg4(Pr + (size_t)b * p.block_stride + vcol[k]);
+                  dot = fmaf(acc[k].x, q.x, dot); dot = fmaf(acc[k].y, q.y, dot);
+                  dot = fmaf(acc[k].z, q.z, dot); dot = fmaf(acc[k].w, q.w, dot);
+                }
+              }
+#pragma unroll
+              for (int o = G >> 1; o; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o, G);
+              if (lane == 0) s_gc[(grp * R + r) * p.B + b] += dot;
+            }
+          }
+        }
       }
     }
   }
@@ -313,8 +347,19 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) 
       if (b < p.B) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
-          if (act[k]) store_vec(p, row, b * d + vcol[k], mix[b][k]);
+          if (act[k]) store_vec(p, row, b * p.block_stride + vcol[k], mix[b][k]);
       }
+    }
+  }
+  }  // row < n_rows
+  if (with_gc) {
+    // the block's partial = its groups' sums in group order (deterministic)
+    __syncthreads();
+    const int RB = p.R * p.B;
+    for (int t = threadIdx.x; t < RB; t += 256) {
+      float sum = s_gc[t];
+      for (int g = 1; g < GROUPS; ++g) sum += s_gc[g * RB + t];
+      p.gc_partial[(size_t)blockIdx.x * RB + t] = sum;
     }
   }
 }
@@ -330,7 +375,7 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
   if (p.n_rows == 0) return RGCN_OK;
   const unsigned grid = (unsigned)((p.n_rows + GROUPS - 1) / GROUPS);
   const bool w = p.edge_w != nullptr;
-  const size_t sm = (size_t)p.R * p.B * sizeof(float);
+  const size_t sm = (size_t)p.R * p.B * sizeof(float) * (p.dotP ? 1 + GROUPS : 1);
   if (mix == MIX_NONE) {
     if (w) aggregate_rows_kernel<G, VPL, MIX_NONE, true><<<grid, 256, 0, st>>>(p);
     else aggregate_rows_kernel<G, VPL, MIX_NONE, false><<<grid, 256, 0, st>>>(p);
@@ -380,11 +425,32 @@ extern "C" size_t rgcn_aggregate_workspace_bytes(const rgcn_csr_t* g, int32_t d)
   return align_up((size_t)g->n_chunks * (size_t)d * sizeof(float), 256);
 }
 
+// The basis-mixing walk keeps B accumulators per lane; beyond kBasisSlice feature columns it runs once per column
+// slice (one 128-bit vector per lane and basis) so that the register allocation still leaves several blocks per SM.
+constexpr int kBasisSlice = 128;
+
+static int64_t agg_blocks(int64_t n_rows, int d) {
+  const int nvec = d >> 2;
+  const int G = nvec <= 4 ? 4 : nvec <= 8 ? 8 : nvec <= 16 ? 16 : 32;
+  const int groups = 256 / G;
+  return (n_rows + groups - 1) / groups;
+}
+
+extern "C" int64_t rgcn_aggregate_blocks(const rgcn_csr_t* g, int32_t d) {
+  if (!g || d < 4) return 0;
+  int64_t total = 0;
+  for (int c0 = 0; c0 < d; c0 += kBasisSlice) total += agg_blocks(g->n_rows, d - c0 < kBasisSlice ? d - c0 : kBasisSlice);
+  return total;
+}
+
 extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d,
                                   const float* comp, int32_t B, void* H, void* H_lo, int64_t ldh, int32_t out_mode,
+                                  const float* dot_p, int64_t ld_dot_p, float* gc_partial,
                                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
   int rc = check_common(g, X, ldx, d, workspace, workspace_bytes);
   if (rc) return rc;
+  RGCN_CHECK_ARG(!dot_p || (comp && B <= kMaxBasis && gc_partial && ((uintptr_t)dot_p & 15) == 0 && ld_dot_p % 4 == 0),
+                 "aggregate_fwd: the coefficient-gradient side output needs comp, B <= %d, aligned P and a partial buffer", kMaxBasis);
   RGCN_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "aggregate_fwd: out_mode must be 0 (fp32), 1 (bf16) or 2 (bf16 hi+lo)");
   RGCN_CHECK_ARG(H && ((uintptr_t)H & (out_mode ? 7 : 15)) == 0 && ldh % 4 == 0, "aggregate_fwd: output must be aligned with ld %% 4 == 0");
   RGCN_CHECK_ARG(out_mode != 2 || (H_lo && ((uintptr_t)H_lo & 7) == 0), "aggregate_fwd: out_mode 2 needs the lo plane");
@@ -393,18 +459,32 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
   p.rowptr = g->rowptr; p.idx = g->idx; p.edge_w = g->w;
   p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs; p.chunk_table = g->chunk_table;
   p.n_rows = g->n_rows; p.R = g->R;
-  p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d;
+  p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d; p.block_stride = d;
   p.O = H; p.O_lo = H_lo; p.ldo = ldh; p.out_mode = out_mode; p.partials = (float*)workspace;
+  p.dotP = dot_p; p.ld_dotP = ld_dot_p; p.gc_partial = gc_partial;
   cudaStream_t st = (cudaStream_t)stream;
   if (!comp) return dispatch_agg(p, MIX_NONE, g->n_chunks, st);
-  // basis blocks are produced kMaxBasis at a time (registers hold B * d/lanes accumulators)
+  // basis blocks are produced kMaxBasis at a time (registers hold the B accumulators), feature columns in slices
+  // of kBasisSlice; every (basis group, slice) launch has its own region of the partial buffers
+  int64_t gc_row = 0;
   for (int b0 = 0; b0 < B; b0 += kMaxBasis) {
-    AggParams q = p;
-    q.comp = comp + b0; q.ldcomp = B; q.B = (B - b0 < kMaxBasis) ? (B - b0) : kMaxBasis;
-    q.O = out_mode ? (void*)((__nv_bfloat16*)H + (size_t)b0 * d) : (void*)((float*)H + (size_t)b0 * d);
-    if (out_mode == 2) q.O_lo = (void*)((__nv_bfloat16*)H_lo + (size_t)b0 * d);
-    rc = dispatch_agg(q, MIX_BASIS, b0 == 0 ? g->n_chunks : 0, st);   // chunk partials do not depend on b
-    if (rc) return rc;
+    for (int c0 = 0; c0 < d; c0 += kBasisSlice) {
+      const int dc = d - c0 < kBasisSlice ? d - c0 : kBasisSlice;
+      AggParams q = p;
+      q.comp = comp + b0; q.ldcomp = B; q.B = (B - b0 < kMaxBasis) ? (B - b0) : kMaxBasis;
+      q.F = X + c0; q.d = dc;
+      const size_t off = (size_t)b0 * d + c0;
+      q.O = out_mode ? (void*)((__nv_bfloat16*)H + off) : (void*)((float*)H + off);
+      if (out_mode == 2) q.O_lo = (void*)((__nv_bfloat16*)H_lo + off);
+      q.partials = (float*)workspace + (size_t)g->n_chunks * c0;
+      if (dot_p) {
+        q.dotP = dot_p + c0;
+        q.gc_partial = gc_partial + (size_t)gc_row * g->R * B;
+        gc_row += agg_blocks(g->n_rows, dc);
+      }
+      rc = dispatch_agg(q, MIX_BASIS, g->n_chunks, st);   // (chunk partials are simply reduced again per basis group)
+      if (rc) return rc;
+    }
   }
   return RGCN_OK;
 }
@@ -421,7 +501,7 @@ extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t
   p.rowptr = gt->rowptr; p.idx = gt->idx; p.edge_w = gt->w;
   p.hub_keys = gt->hub_keys; p.hub_chunk_ptr = gt->hub_chunk_ptr; p.n_hubs = gt->n_hubs; p.chunk_table = gt->chunk_table;
   p.n_rows = gt->n_rows; p.R = gt->R;
-  p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d;
+  p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d; p.block_stride = d;
   p.init = init; p.ld_init = ld_init; p.B = 1;
   p.O = gX; p.ldo = ldgx; p.out_mode = 0; p.partials = (float*)workspace;
   return dispatch_agg(p, MIX_SUM, gt->n_chunks, (cudaStream_t)stream);

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
                                                            int cols, __nv_bfloat16* __restrict__ hi,
                                                            __nv_bfloat16* __restrict__ lo, int64_t ldp,
                                                            float* __restrict__ colsum_partial, int64_t rows_per_block,
-                                                           float scale) {
+                                                           float scale, float* __restrict__ out_f32, int64_t ldf) {
   __shared__ float4 red[256];
   const int tpr = cols >> 2;                       // threads per row (<= 256)
   const int rpp = 256 / tpr;                       // rows per pass
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
             v[u] = scale4(v[u], scale);                // 1 / (1 - p) of a fused dropout, else 1
           }
           add4(cs, v[u]);
+          if (out_f32) *reinterpret_cast<float4*>(out_f32 + r * ldf + c4 * 4) = v[u];
           uint2 h, l;
           split4(v[u], h, l);
           *reinterpret_cast<uint2*>(hi + r * ldp + c4 * 4) = h;
@@ -160,8 +161,9 @@ struct GemmKParams {
 };
 
 constexpr int KBN = 128;                      // N tile of the persistent kernel: two accumulators fit 256 TMEM columns
-constexpr int K_EPI_WARPS = 4;
-constexpr int K_PATCH = 32 * 36 * 4;          // per-warp transpose patch: 32 rows x (32 + 4) floats
+constexpr int K_EPI_WARPS = 8;                // two warps per TMEM lane quarter, each draining half of the tile's columns
+constexpr int K_PATCH = 32 * 20 * 4;          // per-warp transpose patch: 32 rows x (16 + 4) floats
+constexpr int K_THREADS = (K_EPI_WARPS + 2) * 32;
 
 template <bool SPLIT>
 struct KStage {
@@ -178,7 +180,7 @@ struct KStage {
 // the A rows in L2).  The smem ring and the two TMEM accumulators are continuous across tiles: the MMA warp starts
 // tile i+1 while the epilogue warps drain tile i.
 template <bool SPLIT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(K_THREADS, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmKParams p) {
@@ -207,7 +209,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == K_EPI_WARPS && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_b_hi);
     if (SPLIT) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
@@ -219,7 +221,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp < K_EPI_WARPS) {
-    // ===================== epilogue: warp w owns TMEM lanes 32w .. 32w+31 =====================
+    // ===================== epilogue: warp w drains TMEM lanes 32 (w % 4) .. +31 (the quarter a warp may address),
+    // columns [half * BN / 2, (half + 1) * BN / 2) with half = w / 4, in sub-chunks of 16 columns ===============
+    const int quarter = warp & 3, half = warp >> 2;
+    const int c_lo = half * (p.BN >> 1), c_hi = c_lo + (p.BN >> 1);
     float* patch = reinterpret_cast<float*>(smem + (size_t)S::STAGES * S::BYTES + (size_t)warp * K_PATCH);
     uint32_t drop_key = 0;
     if (p.drop_thresh) {
@@ -233,30 +238,30 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const int a = iter & 1;
       mbar_wait(&tfull_bar[a], (uint32_t)((iter >> 1) & 1));
       fence_after_sync();
-      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)a * acc_cols;
-      for (int cc = 0; cc < p.BN; cc += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_lane + cc, r);
+      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
+      for (int cc = c_lo; cc < c_hi; cc += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(t_lane + cc, r);
         tmem_ld_wait();
         // registers (one row per lane) -> patch, + bias / ReLU
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 16; j += 4) {
           const float4 b = *reinterpret_cast<const float4*>(s_bias + ((n0 + cc + j) & 1023));
           float4 qv = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
                                   __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
           if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
-          *reinterpret_cast<float4*>(patch + lane * 36 + j) = qv;
+          *reinterpret_cast<float4*>(patch + lane * 20 + j) = qv;
         }
         __syncwarp();
-        // patch -> global: each instruction writes 4 rows x 128 contiguous bytes
-        const int c4 = (lane & 7) * 4;
+        // patch -> global: each instruction writes 8 rows x 64 contiguous bytes
+        const int c4 = (lane & 3) * 4;
         const bool col_ok = n0 + cc + c4 < p.N;
 #pragma unroll
-        for (int rr = 0; rr < 32; rr += 4) {
-          const int rl = rr + (lane >> 3);
-          const int64_t row = m0 + warp * 32 + rl;
+        for (int rr = 0; rr < 32; rr += 8) {
+          const int rl = rr + (lane >> 2);
+          const int64_t row = m0 + quarter * 32 + rl;
           if (row < p.M && col_ok) {
-            float4 v = *reinterpret_cast<const float4*>(patch + rl * 36 + c4);
+            float4 v = *reinterpret_cast<const float4*>(patch + rl * 20 + c4);
             if (p.drop_thresh) {
               // N % 4 == 0, so the four elements of one store never straddle a 2^32 block
               const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + cc + c4);
@@ -278,7 +283,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       fence_before_sync();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);       // accumulator a may be overwritten
     }
-  } else if (warp == 4) {
+  } else if (warp == K_EPI_WARPS) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(BM + p.BN) * 128u * (SPLIT ? 2u : 1u);
@@ -545,6 +550,11 @@ __device__ __forceinline__ void colsum_reduce_block(const float* __restrict__ pa
   }
 }
 
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int n_part, int N,
+                                                              float* __restrict__ out) {
+  colsum_reduce_block(part, n_part, N, blockIdx.x, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -655,11 +665,11 @@ static int launch_kmajor(GemmKParams p, const void* a_hi, const void* a_lo, int6
   if (split) {
     rc = set_smem(gemm_kmajor_kernel<true>, KStage<true>::SMEM);
     if (rc) return rc;
-    gemm_kmajor_kernel<true><<<grid, 192, KStage<true>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
+    gemm_kmajor_kernel<true><<<grid, K_THREADS, KStage<true>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
   } else {
     rc = set_smem(gemm_kmajor_kernel<false>, KStage<false>::SMEM);
     if (rc) return rc;
-    gemm_kmajor_kernel<false><<<grid, 192, KStage<false>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
+    gemm_kmajor_kernel<false><<<grid, K_THREADS, KStage<false>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
   }
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
@@ -687,9 +697,19 @@ extern "C" int64_t rgcn_split_planes_blocks(int64_t rows, int32_t cols) {
   return (rows + rpb - 1) / rpb;
 }
 
+extern "C" int rgcn_reduce_partials(const float* part, int64_t n_part, int32_t n_cols, float* out, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(part && out && n_part >= 0 && n_part < (1ll << 31) && n_cols >= 4 && n_cols % 4 == 0,
+                 "reduce_partials: n_cols must be a positive multiple of 4");
+  RGCN_CHECK_ARG(((uintptr_t)part & 15) == 0 && ((uintptr_t)out & 15) == 0, "reduce_partials: buffers must be 16-byte aligned");
+  reduce_partials_kernel<<<(unsigned)(n_cols / 4), 256, 0, (cudaStream_t)stream>>>(part, (int)n_part, n_cols, out);
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
 extern "C" int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_mask, int64_t ldm, int64_t rows,
                                  int32_t cols, void* hi, void* lo, int64_t ldp, float* colsum_partial,
-                                 float mask_scale, rgcn_stream_t stream) {
+                                 float mask_scale, float* out_f32, int64_t ld_f32, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(!out_f32 || (((uintptr_t)out_f32 & 15) == 0 && ld_f32 % 4 == 0), "split_planes: fp32 output misaligned");
   RGCN_CHECK_ARG(rows >= 0 && cols >= 4 && cols % 4 == 0 && cols <= 1024, "split_planes: cols=%d must be a multiple of 4 in [4, 1024]", cols);
   RGCN_CHECK_ARG(x && ((uintptr_t)x & 15) == 0 && ldx % 4 == 0, "split_planes: x must be 16-byte aligned, ld %% 4 == 0");
   RGCN_CHECK_ARG(!relu_mask || (((uintptr_t)relu_mask & 15) == 0 && ldm % 4 == 0), "split_planes: mask misaligned");
@@ -702,7 +722,8 @@ extern "C" int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_
   const int64_t rows_per_block = ((rows + nb - 1) / nb + rpp - 1) / rpp * rpp;
   split_planes_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(x, ldx, relu_mask, ldm, rows, cols,
                                                                      (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp,
-                                                                     colsum_partial, rows_per_block, mask_scale);
+                                                                     colsum_partial, rows_per_block, mask_scale,
+                                                                     out_f32, ld_f32);
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

@@ -27,15 +27,20 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False, comp: Optional[torch.Tensor] = None,
-                  planes=None) -> torch.Tensor:
+                  planes=None, transposed: bool = False, dot_p: Optional[torch.Tensor] = None):
     """H[i, r*d:(r+1)*d] = mean_{j in N_r(i)} x[j]  (or the basis-mixed Z when ``comp`` [R, B] is given).
 
     ``planes=(hi, lo_or_None)``: write the result as bf16 planes (the tensor-core operand format) into the first
-    R*d (or B*d) columns of the given row-major bf16 tensors instead of allocating an fp32 / bf16 matrix."""
+    R*d (or B*d) columns of the given row-major bf16 tensors instead of allocating an fp32 / bf16 matrix.
+    ``transposed``: walk the (src, rel) CSR with its 1/count edge weights instead — with ``comp`` and x = the masked
+    output gradient this is the mirrored backward of the basis form.  ``dot_p`` [rows, B*d] (needs ``comp``):
+    also return gc[r, b] = sum_i <h_r[i], dot_p[i, b]> (the gradient of ``comp``) -> (H, gc)."""
     lib = _lib.load()
     x = _f32c(x, "x")
-    if x.size(0) != g.n_src:
-        raise ValueError(f"x has {x.size(0)} rows, the graph gathers from {g.n_src}")
+    ori = g.bwd if transposed else g.fwd
+    n_in, n_out = (g.n_dst, g.n_src) if transposed else (g.n_src, g.n_dst)
+    if x.size(0) != n_in:
+        raise ValueError(f"x has {x.size(0)} rows, the graph gathers from {n_in}")
     d = x.size(1)
     if d % 4 != 0 or d > 1024:
         raise ValueError("feature width must be a multiple of 4 and at most 1024")
@@ -44,19 +49,45 @@ def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False, comp: Op
         comp = comp.detach().to(torch.float32).contiguous()
         if comp.size(0) != g.R:
             raise ValueError("comp must have one row per relation")
-    ws = g.fwd.workspace(d)
+    ws = ori.workspace(d)
     if planes is not None:
         hi, lo = planes
-        if hi.dtype != torch.bfloat16 or hi.size(0) != g.n_dst or hi.size(1) < blocks * d or hi.stride(1) != 1:
-            raise ValueError("planes must be bf16 [n_dst, >= blocks*d] row-major")
+        if hi.dtype != torch.bfloat16 or hi.size(0) != n_out or hi.size(1) < blocks * d or hi.stride(1) != 1:
+            raise ValueError("planes must be bf16 [rows, >= blocks*d] row-major")
         H, H_lo, mode = hi, lo, (2 if lo is not None else 1)
     else:
-        H = torch.empty(g.n_dst, blocks * d, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+        H = torch.empty(n_out, blocks * d, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
         H_lo, mode = None, int(out_bf16)
-    _lib.check(lib.rgcn_aggregate_fwd(g.fwd.ref, _ptr(x), x.stride(0), d, _ptr(comp), 0 if comp is None else blocks,
-                                      _ptr(H), _ptr(H_lo), H.stride(0), mode, _ptr(ws),
+    gc_part = None
+    if dot_p is not None:
+        if comp is None:
+            raise ValueError("dot_p needs comp")
+        dot_p = _f32c(dot_p, "dot_p")
+        if dot_p.size(0) != n_out or dot_p.size(1) < blocks * d:
+            raise ValueError("dot_p must be [rows, >= B*d]")
+        nb = lib.rgcn_aggregate_blocks(ori.ref, d)
+        gc_part = torch.empty(max(nb, 1), g.R * blocks, dtype=torch.float32, device=x.device)
+    _lib.check(lib.rgcn_aggregate_fwd(ori.ref, _ptr(x), x.stride(0), d, _ptr(comp), 0 if comp is None else blocks,
+                                      _ptr(H), _ptr(H_lo), H.stride(0), mode, _ptr(dot_p),
+                                      0 if dot_p is None else dot_p.stride(0), _ptr(gc_part), _ptr(ws),
                                       0 if ws is None else ws.numel() * 4, _stream(x.device)), "rgcn_aggregate_fwd")
-    return H
+    if dot_p is None:
+        return H
+    return H, reduce_partials(gc_part).view(g.R, blocks)
+
+
+def reduce_partials(part: torch.Tensor) -> torch.Tensor:
+    """Column sums of a [n_part, n_cols] fp32 partial buffer in a fixed order (n_cols padded to a multiple of 4)."""
+    lib = _lib.load()
+    n, c = part.shape
+    if c % 4:
+        pad = torch.zeros(n, (c + 3) // 4 * 4, dtype=torch.float32, device=part.device)
+        pad[:, :c] = part
+        part = pad
+    out = torch.empty(part.size(1), dtype=torch.float32, device=part.device)
+    _lib.check(lib.rgcn_reduce_partials(_ptr(part), n, part.size(1), _ptr(out), _stream(part.device)),
+               "rgcn_reduce_partials")
+    return out[:c]
 
 
 def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Tensor] = None,
@@ -200,7 +231,7 @@ def alloc_planes(rows: int, cols: int, mode: str, device):
 
 
 def split_planes(x: torch.Tensor, planes, col0: int = 0, relu_mask: Optional[torch.Tensor] = None,
-                 colsum: bool = False, mask_scale: float = 1.0):
+                 colsum: bool = False, mask_scale: float = 1.0, out_f32: Optional[torch.Tensor] = None):
     """Write fp32 ``x`` [rows, cols] into columns [col0, col0+cols) of the bf16 planes (hi [, lo]); optionally zero
     where relu_mask <= 0 (and multiply the rest by ``mask_scale``, the 1 / (1 - p) of a fused dropout) and return the
     per-block column-sum partials [nblocks, cols] of the masked values."""
@@ -218,7 +249,7 @@ def split_planes(x: torch.Tensor, planes, col0: int = 0, relu_mask: Optional[tor
     lo_v = None if lo is None else lo[:, col0:col0 + cols]
     _lib.check(lib.rgcn_split_planes(_ptr(x), x.stride(0), _ptr(relu_mask), 0 if relu_mask is None else relu_mask.stride(0),
                                      rows, cols, _ptr(hi_v), _ptr(lo_v), hi.stride(0), _ptr(part), float(mask_scale),
-                                     _stream(x.device)),
+                                     _ptr(out_f32), 0 if out_f32 is None else out_f32.stride(0), _stream(x.device)),
                "rgcn_split_planes")
     return part
 

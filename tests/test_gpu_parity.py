@@ -647,3 +647,78 @@ def test_hub_rows_mixed_modes(pkg):
         gref = init.clone().index_add_(0, src, contrib)
         torch.testing.assert_close(gx, gref, rtol=1e-4, atol=1e-4)
         assert torch.equal(ops.aggregate_fwd(graph, x.to(DEV)).cpu(), H)                            # same bits again
+
+
+# ------------------------------------------------------------------------------------------------
+# basis decomposition in the B-accumulator (Z) form
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [(64, 64), (128, 64), (64, 256), (256, 256)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_basis_z_form_layer(pkg, dims, mode, monkeypatch):
+    """The Z form (relations mixed in the aggregation, K = (B+1) d_in, mirrored backward with the coefficient
+    gradient as a side output) against the oracle's materialised-W_r loop, on a hub-heavy graph, with ReLU."""
+    from primekg_rgcn_linkprediction_b200 import synth
+    from primekg_rgcn_linkprediction_b200.conv import _RGCNBasisLayerFn  # noqa: F401  (the form under test)
+    monkeypatch.setenv("PRIMEKG_RGCN_BASIS_FORM", "z")
+    d_in, d_out = dims
+    kg = synth.primekg_subgraph(20_000, seed=9)
+    R, B = kg.num_relations, 2
+    torch.manual_seed(4)
+    conv = pkg.RGCNConv(d_in, d_out, R, num_bases=B, mode=mode).to(DEV)
+    ref = O.RGCNConvRef(d_in, d_out, R, num_bases=B).to(DEV)
+    ref.load_state_dict(conv.state_dict())
+    with torch.no_grad():
+        conv.bias.normal_(); ref.bias.copy_(conv.bias)
+    x = (torch.randn(kg.num_nodes, d_in, device=DEV) * 0.5).requires_grad_()
+    xr = x.detach().clone().requires_grad_()
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    from primekg_rgcn_linkprediction_b200.graph import get_graph
+    graph = get_graph(ei, et, kg.num_nodes, R)
+    assert conv._use_z_form(graph) and graph.bwd.n_hubs > 0 and graph.fwd.n_hubs > 0
+    coef = torch.randn(kg.num_nodes, d_out, device=DEV)
+    out = conv.forward_graph(x, graph, relu=True)
+    (out * coef).sum().backward()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        pre = ref(xr, ei, et)
+        # the ReLU mask is taken from the product's output: an element within rounding distance of zero may fall on
+        # either side, and one flipped element out of 10^6 already shows up at 1e-3 in the gradient norm
+        want = pre * (out.detach() > 0)
+        (want * coef).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    torch.testing.assert_close(out.detach(), torch.relu(pre.detach()), rtol=tol, atol=tol * float(want.abs().max()))
+    for got, exp, name in ((x.grad, xr.grad, "x"), (conv.weight.grad, ref.weight.grad, "weight"),
+                           (conv.comp.grad, ref.comp.grad, "comp"), (conv.root.grad, ref.root.grad, "root"),
+                           (conv.bias.grad, ref.bias.grad, "bias")):
+        rel = float((got - exp).norm() / (exp.norm() + 1e-30))
+        assert rel < (2e-4 if mode == "fp32" else 3e-2), (name, rel)
+    # deterministic
+    x.grad = None
+    conv.zero_grad()
+    out2 = conv.forward_graph(x, graph, relu=True)
+    (out2 * coef).sum().backward()
+    assert torch.equal(out, out2)
+
+
+def test_basis_forms_agree_r30(pkg, monkeypatch):
+    """30 relations / 8 bases: the Z form and the materialised-W_r form of the same layer give the same numbers."""
+    from primekg_rgcn_linkprediction_b200 import synth
+    kg = synth.uniform_kg(5000, 60_000, 30, seed=2)
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    torch.manual_seed(6)
+    conv = pkg.RGCNConv(128, 128, 30, num_bases=8).to(DEV)
+    x0 = torch.randn(5000, 128, device=DEV)
+    coef = torch.randn(5000, 128, device=DEV)
+    res = {}
+    for form in ("w", "z"):
+        monkeypatch.setenv("PRIMEKG_RGCN_BASIS_FORM", form)
+        x = x0.clone().requires_grad_()
+        conv.zero_grad()
+        out = conv(x, ei, et)
+        (out * coef).sum().backward()
+        res[form] = (out.detach(), x.grad, conv.weight.grad.clone(), conv.comp.grad.clone(), conv.root.grad.clone())
+    for a, b in zip(res["w"], res["z"]):
+        assert float((a - b).norm() / (a.norm() + 1e-30)) < 1e-4
