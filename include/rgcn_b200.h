@@ -85,15 +85,16 @@ int rgcn_csr_build(const int64_t* src, const int64_t* dst, const int64_t* rel, i
 
 /* ------------------------------------------------------------------------------------------
  * Hub plan (one per CSR orientation, once per graph).  Power-law graphs have (row, relation)
- * segments with 10^4 edges; segments longer than 128 edges are cut into 128-edge chunks that
- * whole thread blocks reduce in a fixed order (no atomics).  hub_keys receives the sorted keys of
+ * segments with 10^4 edges; segments longer than hub_threshold edges are cut into 128-edge chunks that
+ * whole thread blocks reduce in a fixed order (no atomics).  The threshold bounds the longest serial walk
+ * of one lane group, i.e. the critical path of the row kernel (64 is the default of the Python layer).  hub_keys receives the sorted keys of
  * those segments, hub_chunk_ptr the exclusive prefix of their chunk counts (cap_hubs + 1 entries;
- * entries past n_hubs repeat the total).  cap_hubs >= E / 128 + 1 is always enough.
+ * entries past n_hubs repeat the total).  cap_hubs >= E / hub_threshold + 1 is always enough.
  * SYNCHRONISES the stream: the two counts are returned to the host.
  * ------------------------------------------------------------------------------------------ */
 size_t rgcn_hub_plan_workspace_bytes(int64_t n_keys, int64_t cap_hubs);
-int rgcn_hub_plan(const int32_t* rowptr, int64_t n_keys, int32_t* hub_keys, int32_t* hub_chunk_ptr,
-                  int64_t cap_hubs, int32_t* n_hubs_host, int32_t* n_chunks_host,
+int rgcn_hub_plan(const int32_t* rowptr, int64_t n_keys, int32_t hub_threshold, int32_t* hub_keys,
+                  int32_t* hub_chunk_ptr, int64_t cap_hubs, int32_t* n_hubs_host, int32_t* n_chunks_host,
                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* Chunk table of a hub plan, one int32[4] entry per chunk: {key of the chunk's segment, first chunk of that segment,
@@ -111,10 +112,12 @@ typedef struct rgcn_csr {
   int32_t R;
   int32_t n_hubs;
   int32_t n_chunks;
-  int32_t reserved_;
+  int32_t hub_threshold;        /* the threshold the hub plan was made with            */
   const int32_t* hub_keys;      /* [n_hubs]                                           */
   const int32_t* hub_chunk_ptr; /* [n_hubs + 1]                                       */
   const int32_t* chunk_table;   /* [n_chunks][4] from rgcn_hub_chunk_table            */
+  const int32_t* row_order;     /* [n_rows] or NULL: a permutation of the rows, the order in which the lane
+                                   groups take them (by decreasing edge count: balanced blocks, long walks first) */
 } rgcn_csr_t;
 
 /* ------------------------------------------------------------------------------------------

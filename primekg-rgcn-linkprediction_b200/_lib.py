@@ -24,8 +24,8 @@ i32, i64, sz = C.c_int32, C.c_int64, C.c_size_t
 class CsrStruct(C.Structure):
     """Mirror of ``rgcn_csr_t`` (include/rgcn_b200.h)."""
     _fields_ = [("rowptr", p), ("idx", p), ("w", p), ("n_rows", i64), ("E", i64), ("R", i32),
-                ("n_hubs", i32), ("n_chunks", i32), ("reserved_", i32), ("hub_keys", p),
-                ("hub_chunk_ptr", p), ("chunk_table", p)]
+                ("n_hubs", i32), ("n_chunks", i32), ("hub_threshold", i32), ("hub_keys", p),
+                ("hub_chunk_ptr", p), ("chunk_table", p), ("row_order", p)]
 
 
 PCSR = C.POINTER(CsrStruct)
@@ -39,7 +39,7 @@ PROTOTYPES = {
     "rgcn_csr_build_workspace_bytes": (sz, [i64, i64, i64, i32]),
     "rgcn_csr_build": (C.c_int, [p, p, p, i64, i64, i64, i32, p, p, p, p, p, p, p, p, p, p, sz, p]),
     "rgcn_hub_plan_workspace_bytes": (sz, [i64, i64]),
-    "rgcn_hub_plan": (C.c_int, [p, i64, p, p, i64, C.POINTER(i32), C.POINTER(i32), p, sz, p]),
+    "rgcn_hub_plan": (C.c_int, [p, i64, i32, p, p, i64, C.POINTER(i32), C.POINTER(i32), p, sz, p]),
     "rgcn_hub_chunk_table": (C.c_int, [p, p, i32, i32, p, p]),
     "rgcn_aggregate_workspace_bytes": (sz, [PCSR, i32]),
     "rgcn_aggregate_blocks": (i64, [PCSR, i32]),

@@ -32,6 +32,8 @@ struct AggParams {
   const int32_t* hub_keys;   // sorted keys of hub segments
   const int32_t* hub_chunk_ptr;
   const int32_t* chunk_table;  // [n_chunks][4]: {segment key, first chunk of the segment, -, -}
+  const int32_t* row_order;    // nullable: rows in the order the groups take them (longest first)
+  int32_t hub_threshold;
   int32_t n_hubs;
   int64_t n_rows;
   int32_t R;
@@ -173,10 +175,12 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) 
   }
   const int lane = threadIdx.x % G, grp = threadIdx.x / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-  const int64_t row = (int64_t)blockIdx.x * GROUPS + grp;
+  int64_t row = (int64_t)blockIdx.x * GROUPS + grp;
   if (row >= p.n_rows) {
     if (!with_gc) return;
   } else {
+  // longest rows first: neighbouring groups get rows of similar length and the long walks start at time zero
+  if (p.row_order) row = __ldg(p.row_order + row);
   const int R = p.R, d = p.d, nvec = p.d >> 2;
   const int64_t key0 = row * R;
   const int32_t* __restrict__ rowptr = p.rowptr + key0;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) 
       float4 acc[VPL];
 #pragma unroll
       for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (len > kHubThreshold) {
+      if (len > p.hub_threshold) {
         // hub: add the chunk partials in chunk order
         const int key = (int)(key0 + r);
         int lo = 0, hi = p.n_hubs;
@@ -405,6 +409,7 @@ static int check_common(const rgcn_csr_t* g, const float* F, int64_t ldf, int32_
                         size_t ws_bytes) {
   RGCN_CHECK_ARG(g && g->rowptr && (g->idx || g->E == 0), "aggregate: null CSR arrays");
   RGCN_CHECK_ARG(g->R >= 1 && g->n_rows >= 0, "aggregate: bad n_rows/R");
+  RGCN_CHECK_ARG(g->hub_threshold >= 1, "aggregate: hub_threshold must be the (positive) threshold the hub plan was made with");
   RGCN_CHECK_ARG(d >= 4 && d <= 1024 && d % 4 == 0, "aggregate: feature width d=%d must be a multiple of 4 in [4,1024]", d);
   RGCN_CHECK_ARG(F && ldf % 4 == 0 && ((uintptr_t)F & 15) == 0, "aggregate: feature matrix must be 16-byte aligned with ld %% 4 == 0");
   RGCN_CHECK_ARG(g->n_chunks == 0 || (g->hub_keys && g->hub_chunk_ptr && g->n_hubs > 0 && g->chunk_table &&
@@ -458,6 +463,7 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
   AggParams p{};
   p.rowptr = g->rowptr; p.idx = g->idx; p.edge_w = g->w;
   p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs; p.chunk_table = g->chunk_table;
+  p.row_order = g->row_order; p.hub_threshold = g->hub_threshold;
   p.n_rows = g->n_rows; p.R = g->R;
   p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d; p.block_stride = d;
   p.O = H; p.O_lo = H_lo; p.ldo = ldh; p.out_mode = out_mode; p.partials = (float*)workspace;
@@ -500,6 +506,7 @@ extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t
   AggParams p{};
   p.rowptr = gt->rowptr; p.idx = gt->idx; p.edge_w = gt->w;
   p.hub_keys = gt->hub_keys; p.hub_chunk_ptr = gt->hub_chunk_ptr; p.n_hubs = gt->n_hubs; p.chunk_table = gt->chunk_table;
+  p.row_order = gt->row_order; p.hub_threshold = gt->hub_threshold;
   p.n_rows = gt->n_rows; p.R = gt->R;
   p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d; p.block_stride = d;
   p.init = init; p.ld_init = ld_init; p.B = 1;

@@ -130,7 +130,8 @@ static int build_one(const int64_t* major, const int64_t* minor, const int64_t* 
 // ---- hub plan ---------------------------------------------------------------------------------
 struct IsHub {
   const int32_t* rowptr;
-  __device__ bool operator()(int32_t k) const { return rowptr[k + 1] - rowptr[k] > kHubThreshold; }
+  int threshold;
+  __device__ bool operator()(int32_t k) const { return rowptr[k + 1] - rowptr[k] > threshold; }
 };
 
 __global__ void hub_chunks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ hub_keys,
@@ -223,15 +224,16 @@ extern "C" int rgcn_csr_build(const int64_t* src, const int64_t* dst, const int6
 extern "C" size_t rgcn_hub_plan_workspace_bytes(int64_t n_keys, int64_t cap_hubs) {
   size_t sel = 0, scan = 0;
   cub::CountingInputIterator<int32_t> it(0);
-  IsHub pred{nullptr};
+  IsHub pred{nullptr, kHubThreshold};
   cub::DeviceSelect::If(nullptr, sel, it, (int32_t*)nullptr, (int32_t*)nullptr, (int)n_keys, pred);
   cub::DeviceScan::ExclusiveSum(nullptr, scan, (int32_t*)nullptr, (int32_t*)nullptr, (int)(cap_hubs + 1));
   return align_up(sel > scan ? sel : scan, 256) + 512;
 }
 
-extern "C" int rgcn_hub_plan(const int32_t* rowptr, int64_t n_keys, int32_t* hub_keys, int32_t* hub_chunk_ptr,
-                             int64_t cap_hubs, int32_t* n_hubs_host, int32_t* n_chunks_host, void* workspace,
-                             size_t workspace_bytes, rgcn_stream_t stream) {
+extern "C" int rgcn_hub_plan(const int32_t* rowptr, int64_t n_keys, int32_t hub_threshold, int32_t* hub_keys,
+                             int32_t* hub_chunk_ptr, int64_t cap_hubs, int32_t* n_hubs_host, int32_t* n_chunks_host,
+                             void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(hub_threshold >= 1, "hub_plan: hub_threshold must be positive");
   RGCN_CHECK_ARG(rowptr && hub_keys && hub_chunk_ptr && n_hubs_host && n_chunks_host, "hub_plan: null argument");
   RGCN_CHECK_ARG(n_keys >= 0 && n_keys < (1ll << 31) - 1 && cap_hubs >= 0, "hub_plan: bad sizes");
   const size_t need = rgcn_hub_plan_workspace_bytes(n_keys, cap_hubs);
@@ -245,7 +247,7 @@ extern "C" int rgcn_hub_plan(const int32_t* rowptr, int64_t n_keys, int32_t* hub
   char* tmp = ws + 256;
   size_t tmp_bytes = need - 512;
   cub::CountingInputIterator<int32_t> it(0);
-  IsHub pred{rowptr};
+  IsHub pred{rowptr, hub_threshold};
   RGCN_CUDA(cudaMemsetAsync(d_n, 0, sizeof(int32_t), st));
   if (n_keys > 0 && cap_hubs > 0) {
     // keys come out in increasing order (DeviceSelect keeps the input order)

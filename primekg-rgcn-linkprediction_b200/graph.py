@@ -8,11 +8,13 @@ HBM layout (all int32 / fp32, contiguous):
     rowptr   [n_dst * R + 1]   col   [E]   perm   [E]        keyed dst * R + rel
     rowptr_t [n_src * R + 1]   row_t [E]   perm_t [E]  w_t [E]   keyed src * R + rel
     inv_cnt  [n_dst * R]       1 / max(|N_r(i)|, 1)
-    hub_keys / hub_chunk_ptr / chunk_table   per orientation (segments > 128 edges, cut into 128-edge chunks)
+    hub_keys / hub_chunk_ptr / chunk_table   per orientation (segments > hub_threshold() edges, cut into 128-edge chunks)
+    row_order [n_rows]         rows by decreasing edge count, the order the lane groups take them
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from collections import OrderedDict
 from typing import Optional
@@ -30,32 +32,53 @@ def _stream(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def hub_threshold() -> int:
+    """Segments longer than this go through the chunk path (``PRIMEKG_RGCN_HUB_THRESHOLD``).  Measured on the B200
+    (cfg2 / cfg3 aggregation, profiles/r1_agg_threshold_order_ab.txt): 128 beats 64 and 32 — the chunk path costs
+    more than the shorter serial walks save."""
+    t = int(os.environ.get("PRIMEKG_RGCN_HUB_THRESHOLD", "128"))
+    if t < 1:
+        raise ValueError("PRIMEKG_RGCN_HUB_THRESHOLD must be positive")
+    return t
+
+
 class _Orientation:
     """One CSR orientation + its hub plan, and the ``rgcn_csr_t`` handed to the kernels."""
 
     def __init__(self, rowptr, idx, w, n_rows, R, E):
         self.rowptr, self.idx, self.w = rowptr, idx, w
         self.n_rows, self.R, self.E = int(n_rows), int(R), int(E)
-        self.hub_keys = self.hub_chunk_ptr = self.chunk_table = None
+        self.hub_keys = self.hub_chunk_ptr = self.chunk_table = self.row_order = None
         self.n_hubs = self.n_chunks = 0
+        self.threshold = hub_threshold()
         self._plan_hubs()
+        order = os.environ.get("PRIMEKG_RGCN_ROW_ORDER", "auto")
+        if order not in ("auto", "degree", "none"):
+            raise ValueError("PRIMEKG_RGCN_ROW_ORDER must be auto, degree or none")
+        # measured: +6-8 % on the L2-resident cfg2 aggregation, -3 % on cfg3 whose feature matrix does not fit the L2
+        # (index order keeps neighbouring rows' gathers close) => by default only for graphs up to 64 k rows
+        if self.n_rows > 1 and (order == "degree" or (order == "auto" and self.n_rows <= 65536)):
+            # rows by decreasing edge count (stable): blocks get rows of similar length, the longest walks start first
+            ends = rowptr[self.R::self.R]
+            deg = ends - rowptr[:-1:self.R][: ends.numel()]
+            self.row_order = torch.argsort(deg, descending=True, stable=True).to(torch.int32).contiguous()
         self.struct = _lib.CsrStruct(
-            _ptr(rowptr), _ptr(idx), _ptr(w), self.n_rows, self.E, self.R, self.n_hubs, self.n_chunks, 0,
-            _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr), _ptr(self.chunk_table))
+            _ptr(rowptr), _ptr(idx), _ptr(w), self.n_rows, self.E, self.R, self.n_hubs, self.n_chunks, self.threshold,
+            _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr), _ptr(self.chunk_table), _ptr(self.row_order))
         self.ref = C.byref(self.struct)
         self._ws = {}
 
     def _plan_hubs(self):
         lib = _lib.load()
         dev = self.rowptr.device
-        cap = self.E // 128 + 1
+        cap = self.E // self.threshold + 1
         n_keys = self.n_rows * self.R
         hub_keys = torch.empty(cap, dtype=torch.int32, device=dev)
         chunk_ptr = torch.empty(cap + 1, dtype=torch.int32, device=dev)
         ws_bytes = lib.rgcn_hub_plan_workspace_bytes(n_keys, cap)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         nh, nc = C.c_int32(0), C.c_int32(0)
-        _lib.check(lib.rgcn_hub_plan(_ptr(self.rowptr), n_keys, _ptr(hub_keys), _ptr(chunk_ptr), cap,
+        _lib.check(lib.rgcn_hub_plan(_ptr(self.rowptr), n_keys, self.threshold, _ptr(hub_keys), _ptr(chunk_ptr), cap,
                                      C.byref(nh), C.byref(nc), _ptr(ws), ws_bytes, _stream(dev)), "rgcn_hub_plan")
         self.n_hubs, self.n_chunks = int(nh.value), int(nc.value)
         if self.n_hubs:

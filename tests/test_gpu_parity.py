@@ -127,7 +127,7 @@ def test_aggregate_fwd(pkg, name, d):
     torch.testing.assert_close(H, want, rtol=1e-5, atol=1e-5)
     # segments below the hub threshold are summed serially in original edge order => identical bits
     cnt = (g.rowptr[1:] - g.rowptr[:-1]).cpu().view(N, R)
-    small = (cnt <= 128)[:, :, None].expand(N, R, d).reshape(N, R * d)
+    small = (cnt <= g.fwd.threshold)[:, :, None].expand(N, R, d).reshape(N, R * d)
     assert torch.equal(H[small], want[small])
     Hb = ops.aggregate_fwd(g, x.to(DEV), out_bf16=True).cpu()
     assert torch.equal(Hb, H.to(torch.bfloat16))

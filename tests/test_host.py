@@ -46,7 +46,7 @@ def test_library_argument_errors_without_gpu(lib_built):
 def test_csr_struct_matches_header_layout():
     from primekg_rgcn_linkprediction_b200 import _lib
     # 3 pointers, 2 int64, 4 int32, 2 pointers
-    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 2 * 8 + 4 * 4 + 3 * 8
+    assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 2 * 8 + 4 * 4 + 4 * 8
     assert _lib.CsrStruct.hub_keys.offset == 56
 
 
