@@ -430,8 +430,10 @@ extern "C" size_t rgcn_aggregate_workspace_bytes(const rgcn_csr_t* g, int32_t d)
   return align_up((size_t)g->n_chunks * (size_t)d * sizeof(float), 256);
 }
 
-// The basis-mixing walk keeps B accumulators per lane; beyond kBasisSlice feature columns it runs once per column
-// slice (one 128-bit vector per lane and basis) so that the register allocation still leaves several blocks per SM.
+// The basis-mixing walk keeps B accumulators per lane.  With the coefficient-gradient side output it runs once per
+// slice of kBasisSlice feature columns (one 128-bit vector per lane and basis): measured on cfg3, d = 256, that walk is
+// faster in two slices (2 x 1.35 ms) than in one with 150 registers, while the plain mixing walk is faster unsliced
+// (1.04 ms against 2 x 0.78 ms).
 constexpr int kBasisSlice = 128;
 
 static int64_t agg_blocks(int64_t n_rows, int d) {
@@ -441,6 +443,7 @@ static int64_t agg_blocks(int64_t n_rows, int d) {
   return (n_rows + groups - 1) / groups;
 }
 
+// rows of R * B floats the coefficient-gradient side output of rgcn_aggregate_fwd writes
 extern "C" int64_t rgcn_aggregate_blocks(const rgcn_csr_t* g, int32_t d) {
   if (!g || d < 4) return 0;
   int64_t total = 0;
@@ -473,9 +476,10 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
   // basis blocks are produced kMaxBasis at a time (registers hold the B accumulators), feature columns in slices
   // of kBasisSlice; every (basis group, slice) launch has its own region of the partial buffers
   int64_t gc_row = 0;
+  const int slice = dot_p ? kBasisSlice : d;
   for (int b0 = 0; b0 < B; b0 += kMaxBasis) {
-    for (int c0 = 0; c0 < d; c0 += kBasisSlice) {
-      const int dc = d - c0 < kBasisSlice ? d - c0 : kBasisSlice;
+    for (int c0 = 0; c0 < d; c0 += slice) {
+      const int dc = d - c0 < slice ? d - c0 : slice;
       AggParams q = p;
       q.comp = comp + b0; q.ldcomp = B; q.B = (B - b0 < kMaxBasis) ? (B - b0) : kMaxBasis;
       q.F = X + c0; q.d = dc;
