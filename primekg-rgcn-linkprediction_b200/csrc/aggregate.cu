@@ -158,8 +158,17 @@ __device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int c
 // The inner loop is instruction-issue sensitive (16 B per lane per edge): parameters are hoisted into registers,
 // the edge weights are a template flag, full batches of U edges run without any predicate, inactive lanes of a
 // ragged feature width read column 0 instead of being masked, and only the tail batch is guarded.
+// resident blocks per SM the register allocation aims at: the walk is latency bound, occupancy is its throughput
+constexpr int agg_min_blocks(int G, int vpl, int mix, bool w) {
+  // measured on the B200 (scripts/bench_agg.py, scripts/bench_cfg.py cfg1 / cfg2)
+  if (mix == MIX_BASIS || vpl > 2) return 1;
+  if (vpl == 2) return (mix == MIX_NONE && !w) ? 5 : 4;          // d = 256: forward 48 registers, backward 64
+  if (G == 32) return mix == MIX_NONE ? 6 : 5;                    // d = 128
+  return (mix == MIX_SUM && w) ? 3 : 4;                           // d <= 64
+}
+
 template <int G, int VPL, int MIX, bool W>
-__global__ void __launch_bounds__(256) aggregate_rows_kernel(const AggParams p) {
+__global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate_rows_kernel(const AggParams p) {
   constexpr int GROUPS = 256 / G;
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
   constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
