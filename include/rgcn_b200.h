@@ -214,6 +214,49 @@ int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t lda, int32_
                          void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * One layer per call.  rgcn_layer_fwd = rgcn_aggregate_fwd (into the H columns of the operand planes) +
+ * rgcn_split_planes (x into the last d_in columns) + rgcn_transform_fwd: everything `RGCNConv.forward` does at
+ * src/models/rgcn.py:123 / :128 (+ the ReLU / dropout of :124-125 when asked).  rgcn_layer_bwd = rgcn_split_planes
+ * (G = g_out * mask) + rgcn_transform_dgrad + rgcn_aggregate_bwd + rgcn_transform_wgrad: its autograd backward
+ * (src/train.py:306).  Same kernels, same results as the separate calls; one foreign call instead of 5-7, which is
+ * what bounds the step when the reference's unmodified loop drives the modules eagerly from Python.
+ * weight is [R * d_in, d_out] row-major (RGCNConv.weight viewed 2-D), modes / dropout / peers as in rgcn_transform_fwd.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct rgcn_layer_fwd_args {
+  const rgcn_csr_t* csr;                    /* (dst, relation) orientation                                   */
+  const float* x_src; int64_t ld_x_src;     /* [n_src, d_in] rows the edges gather from                      */
+  const float* x_root; int64_t ld_x_root;   /* [n_dst, d_in] rows being updated (== x_src on one GPU)        */
+  int32_t d_in, d_out, relu, mode;
+  const float* weight; const float* root; const float* bias;
+  float dropout_p; uint32_t dropout_seed; unsigned long long* dropout_counter;
+  void* A_hi; void* A_lo; int64_t lda;      /* out: operand planes [n_dst, >= (R+1) d_in], kept for backward */
+  float* out; int64_t ldo;                  /* out: [n_dst, d_out]                                           */
+  float* const* peer_out_host; int32_t n_peer; int64_t peer_row0, peer_ld;
+  void* agg_workspace; size_t agg_workspace_bytes;     /* rgcn_aggregate_workspace_bytes(csr, d_in)           */
+  void* gemm_workspace; size_t gemm_workspace_bytes;   /* rgcn_transform_workspace_bytes(n_dst, (R+1) d_in, d_out) */
+} rgcn_layer_fwd_args;
+
+typedef struct rgcn_layer_bwd_args {
+  const rgcn_csr_t* csr_t;                  /* (src, relation) orientation with edge weights                 */
+  const float* g_out; int64_t ld_g_out;     /* [n_dst, d_out]                                                */
+  const float* relu_mask; int64_t ld_mask; float mask_scale;   /* layer output (NULL: no ReLU), 1 / (1 - p)  */
+  int64_t n_dst; int32_t d_in, d_out, mode, add_root_term;
+  const float* weight; const float* root;
+  const void* A_hi; const void* A_lo; int64_t lda;             /* planes saved by rgcn_layer_fwd             */
+  void* G_hi; void* G_lo; int64_t ldg;      /* scratch planes [n_dst, d_out]                                 */
+  float* colsum_partial;                    /* scratch [rgcn_split_planes_blocks(n_dst, d_out), d_out]       */
+  float* gA; int64_t ld_gA;                 /* scratch [n_dst, (R+1) d_in]; NULL: no input gradient wanted   */
+  float* g_x; int64_t ld_g_x;               /* out [n_src, d_in] (NULL: only gA is wanted); with add_root_term the
+                                               root-term gradient gA[:, R d_in:] is added (one-GPU case)       */
+  float* g_weight; float* g_root; float* g_bias;               /* out, NULL: not wanted                      */
+  void* agg_workspace; size_t agg_workspace_bytes;
+  void* gemm_workspace; size_t gemm_workspace_bytes;
+} rgcn_layer_bwd_args;
+
+int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream);
+int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Peer-memory exchange kernels of the destination-range partitioned path (graphs too large for one GPU; the
  * reference is single-device, this is the scale-out of src/models/rgcn.py:123-128 and of its autograd backward).
  * All `*_host` arguments are HOST arrays of DEVICE pointers into buffers of the n GPUs of one NVSwitch domain,

@@ -29,6 +29,28 @@ class CsrStruct(C.Structure):
 
 
 PCSR = C.POINTER(CsrStruct)
+f32, u32, u64 = C.c_float, C.c_uint32, C.c_uint64
+
+
+class LayerFwdArgs(C.Structure):
+    """Mirror of ``rgcn_layer_fwd_args`` (include/rgcn_b200.h)."""
+    _fields_ = [("csr", PCSR), ("x_src", p), ("ld_x_src", i64), ("x_root", p), ("ld_x_root", i64),
+                ("d_in", i32), ("d_out", i32), ("relu", i32), ("mode", i32),
+                ("weight", p), ("root", p), ("bias", p),
+                ("dropout_p", f32), ("dropout_seed", u32), ("dropout_counter", p),
+                ("A_hi", p), ("A_lo", p), ("lda", i64), ("out", p), ("ldo", i64),
+                ("peer_out_host", p), ("n_peer", i32), ("peer_row0", i64), ("peer_ld", i64),
+                ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz)]
+
+
+class LayerBwdArgs(C.Structure):
+    """Mirror of ``rgcn_layer_bwd_args`` (include/rgcn_b200.h)."""
+    _fields_ = [("csr_t", PCSR), ("g_out", p), ("ld_g_out", i64), ("relu_mask", p), ("ld_mask", i64), ("mask_scale", f32),
+                ("n_dst", i64), ("d_in", i32), ("d_out", i32), ("mode", i32), ("add_root_term", i32),
+                ("weight", p), ("root", p), ("A_hi", p), ("A_lo", p), ("lda", i64),
+                ("G_hi", p), ("G_lo", p), ("ldg", i64), ("colsum_partial", p), ("gA", p), ("ld_gA", i64),
+                ("g_x", p), ("ld_g_x", i64), ("g_weight", p), ("g_root", p), ("g_bias", p),
+                ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz)]
 
 # name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
 PROTOTYPES = {
@@ -51,6 +73,8 @@ PROTOTYPES = {
     "rgcn_transform_workspace_bytes": (sz, [i64, i32, i32]),
     "rgcn_transform_fwd": (C.c_int, [p, p, i64, i32, i32, p, p, p, i32, i64, i32, p, i64, i32, C.c_float, C.c_uint32, p,
                                      p, i32, i64, i64, p, sz, p]),
+    "rgcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), p]),
+    "rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), p]),
     "rgcn_p2p_push_rows": (C.c_int, [p, i64, i64, i32, p, i32, i64, i64, p]),
     "rgcn_p2p_reduce_split": (C.c_int, [p, i32, i64, i64, p, i64, p, i64, C.c_float, i64, i32, p, i64, p, p, i64, p, p]),
     "rgcn_transform_dgrad": (C.c_int, [p, p, i64, i32, p, i32, p, i32, i64, p, i64, i32, p, sz, p]),

@@ -53,13 +53,9 @@ class _RGCNLayerFn(torch.autograd.Function):
         x_root = x_src if shared else x_root.contiguous()
         if x_root.size(0) != graph.n_dst:
             raise ValueError(f"x has {x_root.size(0)} rows, the graph updates {graph.n_dst}")
-        K1, K2 = R * d_in, d_in
-        A = ops.alloc_planes(graph.n_dst, K1 + K2, mode, x_src.device)
-        ops.aggregate_fwd(graph, x_src, planes=A)
-        ops.split_planes(x_root, A, col0=K1)
         # drop = (p, seed, device counter): ReLU + dropout fused into the GEMM epilogue (reference :124-125)
         p_drop, seed, ctr = drop if drop is not None else (0.0, 0, None)
-        out = ops.transform_fwd(A, K1, K2, W.reshape(K1, d_out), root, bias, relu, mode, p_drop, seed, ctr)
+        out, A = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr)
         ctx.graph, ctx.relu, ctx.mode, ctx.shared, ctx.p_drop = graph, relu, mode, shared, p_drop
         ctx.save_for_backward(A[0], A[1], W, root, out if relu else None)
         return out
@@ -69,27 +65,22 @@ class _RGCNLayerFn(torch.autograd.Function):
         A_hi, A_lo, W, root, out = ctx.saved_tensors
         graph, mode = ctx.graph, ctx.mode
         R, d_in, d_out = W.shape
-        K1, K2 = R * d_in, d_in
-        gO = gO.contiguous()
-        Wf = W.reshape(K1, d_out)
+        K1 = R * d_in
         need_src, need_root_x, need_W, need_root, need_b = ctx.needs_input_grad[:5]
         need_w_any = need_W or need_root or need_b
-        gx_src = gx_root = gW = groot = gb = None
-        # G = gO * [out > 0] as bf16 planes, formed once for both GEMMs; column sums = bias gradient
-        G = ops.alloc_planes(gO.size(0), d_out, mode, gO.device)
+        need_x = need_src or need_root_x
         # out is zero exactly where ReLU or the fused dropout killed the element: one mask serves both
-        colsum = ops.split_planes(gO, G, relu_mask=out, colsum=need_w_any, mask_scale=1.0 / (1.0 - ctx.p_drop))
-        if need_src or need_root_x:
-            gA = ops.transform_dgrad(G, d_out, Wf, root, mode)            # [n_dst, (R+1) * d_in]
+        gx, gA, gWf, groot, gb = ops.layer_bwd(
+            graph, gO.contiguous(), out, 1.0 / (1.0 - ctx.p_drop), (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
+            need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any)
+        gx_src = gx_root = None
+        if need_x:
             if ctx.shared:
-                gx_src = ops.aggregate_bwd(graph, gA, d_in, init=gA[:, K1:])
+                gx_src = gx
             else:
-                if need_src:
-                    gx_src = ops.aggregate_bwd(graph, gA, d_in, init=None)   # full-length partial, reduced by the caller
+                gx_src = gx if need_src else None             # full-length partial, reduced by the caller
                 gx_root = gA[:, K1:]
-        if need_w_any:
-            gWf, groot, gb = ops.transform_wgrad((A_hi, A_lo), K1, K2, G, d_out, colsum, mode)
-            gW = gWf.view(R, d_in, d_out)
+        gW = gWf.view(R, d_in, d_out) if gWf is not None else None
         return gx_src, gx_root, gW, groot, gb, None, None, None, None
 
 

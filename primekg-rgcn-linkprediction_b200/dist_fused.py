@@ -78,13 +78,11 @@ class _FusedEncoderFn(torch.autograd.Function):
             R, d_in, d_out = W.shape
             K1, K2 = R * d_in, d_in
             x_full = ex.x_view(l, d_in)
-            A = ops.alloc_planes(n, K1 + K2, mode, x0.device)
-            ops.aggregate_fwd(graph, x_full, planes=A)
-            ops.split_planes(x_full[row0:row0 + n], A, col0=K1)
             p_drop, seed, ctr = drops[l] if drops[l] is not None else (0.0, 0, None)
             last = l == L - 1
-            out = ops.transform_fwd(A, K1, K2, W.reshape(K1, d_out), root, bias, not last, mode, p_drop, seed, ctr,
-                                    peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out)
+            # aggregate -> planes -> transform whose epilogue also stores every tile into all ranks' next buffer
+            out, A = ops.layer_fwd(graph, x_full, x_full[row0:row0 + n], W.reshape(K1, d_out), root, bias, not last, mode,
+                                   p_drop, seed, ctr, peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out)
             ex.x.barrier()
             saved += [A[0], A[1], W, root]
             outs.append(None if last else out)          # post-ReLU/dropout output = the backward mask

@@ -66,6 +66,7 @@ class _Orientation:
             _ptr(rowptr), _ptr(idx), _ptr(w), self.n_rows, self.E, self.R, self.n_hubs, self.n_chunks, self.threshold,
             _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr), _ptr(self.chunk_table), _ptr(self.row_order))
         self.ref = C.byref(self.struct)
+        self.ptr = C.pointer(self.struct)          # for struct fields of type POINTER(rgcn_csr_t)
         self._ws = {}
 
     def _plan_hubs(self):

@@ -334,6 +334,98 @@ def transform_wgrad(a_planes, K1: int, K2: int, g_planes, d_out: int, colsum_par
     return gW1, gW2, gb
 
 
+# ---- one layer per foreign call ---------------------------------------------------------------------
+_WS_BYTES = {}
+
+
+def _gemm_workspace(device, n: int, K: int, d_out: int) -> torch.Tensor:
+    key = (n, K, d_out)
+    nb = _WS_BYTES.get(key)
+    if nb is None:
+        nb = _WS_BYTES[key] = int(_lib.load().rgcn_transform_workspace_bytes(n, K, d_out))
+    return _workspace(device, nb)
+
+
+def _dp(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch.Tensor, root: torch.Tensor,
+              bias: torch.Tensor, relu: bool, mode: str, dropout_p: float = 0.0, dropout_seed: int = 0,
+              dropout_ctr: Optional[torch.Tensor] = None, peer_out=None, peer_row0: int = 0, peer_ld: int = 0):
+    """aggregate -> operand planes -> tensor-core transform of one layer in ONE C call (``rgcn_layer_fwd``).
+    Returns (out [n_dst, d_out], (A_hi, A_lo | None))."""
+    lib = _lib.load()
+    x_src = _f32c(x_src, "x")
+    x_root = x_src if x_root is x_src else _f32c(x_root, "x_root")
+    if x_src.size(0) != g.n_src or x_root.size(0) != g.n_dst:
+        raise ValueError(f"x has {x_src.size(0)} / {x_root.size(0)} rows, the graph gathers from {g.n_src} and updates {g.n_dst}")
+    d_in = x_src.size(1)
+    if d_in % 4 or d_in > 1024:
+        raise ValueError("feature width must be a multiple of 4 and at most 1024")
+    W2d, root = _w2d(W2d, "weight"), _w2d(root, "root")
+    bias = bias.detach().contiguous()
+    d_out = W2d.size(-1)
+    K = (g.R + 1) * d_in
+    if W2d.numel() != g.R * d_in * d_out or root.numel() != d_in * d_out:
+        raise ValueError("weight shapes do not match the operands")
+    dev = x_src.device
+    A = alloc_planes(g.n_dst, K, mode, dev)
+    out = torch.empty(g.n_dst, d_out, dtype=torch.float32, device=dev)
+    aws = g.fwd.workspace(d_in)
+    gws = _gemm_workspace(dev, g.n_dst, K, d_out)
+    peers = _ptr_array(peer_out) if peer_out else None
+    args = _lib.LayerFwdArgs(
+        g.fwd.ptr, x_src.data_ptr(), x_src.stride(0), x_root.data_ptr(), x_root.stride(0), d_in, d_out, int(relu),
+        _mode_id(mode), W2d.data_ptr(), root.data_ptr(), bias.data_ptr(), float(dropout_p), int(dropout_seed) & 0xFFFFFFFF,
+        _dp(dropout_ctr) if dropout_p > 0 else None, A[0].data_ptr(), _dp(A[1]), A[0].stride(0), out.data_ptr(),
+        out.stride(0), C.cast(peers, C.c_void_p) if peers is not None else None, len(peer_out) if peer_out else 0,
+        int(peer_row0), int(peer_ld), _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel())
+    _lib.check(lib.rgcn_layer_fwd(C.byref(args), _stream(dev)), "rgcn_layer_fwd")
+    return out, A
+
+
+def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], mask_scale: float, planes, W2d: torch.Tensor,
+              root: torch.Tensor, d_in: int, mode: str, need_x: bool, add_root_term: bool, need_w: bool, need_b: bool,
+              gx_out: Optional[torch.Tensor] = None):
+    """split(gO, mask) -> dgrad -> transposed gather -> wgrad of one layer in ONE C call (``rgcn_layer_bwd``).
+    Returns (g_x | None, gA | None, gW2d | None, g_root | None, g_bias | None); ``gA[:, R*d_in:]`` is the root-term
+    gradient (already inside g_x when ``add_root_term``)."""
+    lib = _lib.load()
+    gO = _f32c(gO, "gO")
+    if relu_mask is not None:
+        relu_mask = _f32c(relu_mask, "relu_mask")
+    W2d, root = _w2d(W2d, "weight"), _w2d(root, "root")
+    n, d_out = gO.shape
+    if n != g.n_dst:
+        raise ValueError("gO must have one row per destination")
+    K1 = g.R * d_in
+    K = K1 + d_in
+    dev = gO.device
+    A_hi, A_lo = planes
+    G = alloc_planes(n, d_out, mode, dev)
+    colsum = None
+    if need_b:
+        colsum = torch.empty(max(int(lib.rgcn_split_planes_blocks(n, d_out)), 1), d_out, dtype=torch.float32, device=dev)
+    gA = torch.empty(n, K, dtype=torch.float32, device=dev) if need_x else None
+    gx = None
+    if need_x:
+        gx = gx_out if gx_out is not None else torch.empty(g.n_src, d_in, dtype=torch.float32, device=dev)
+    gW = torch.empty(K1, d_out, dtype=torch.float32, device=dev) if need_w else None
+    groot = torch.empty(d_in, d_out, dtype=torch.float32, device=dev) if need_w else None
+    gb = torch.empty(d_out, dtype=torch.float32, device=dev) if (need_w and need_b) else None
+    aws = g.bwd.workspace(d_in)
+    gws = _gemm_workspace(dev, n, K, d_out)
+    args = _lib.LayerBwdArgs(
+        g.bwd.ptr, gO.data_ptr(), gO.stride(0), _dp(relu_mask), 0 if relu_mask is None else relu_mask.stride(0),
+        float(mask_scale), n, d_in, d_out, _mode_id(mode), int(add_root_term), W2d.data_ptr(), root.data_ptr(),
+        A_hi.data_ptr(), _dp(A_lo), A_hi.stride(0), G[0].data_ptr(), _dp(G[1]), G[0].stride(0), _dp(colsum if gb is not None else None),
+        _dp(gA), 0 if gA is None else gA.stride(0), _dp(gx), 0 if gx is None else gx.stride(0), _dp(gW), _dp(groot), _dp(gb),
+        _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel())
+    _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
+    return gx, gA, gW, groot, gb
+
+
 # ---- peer-memory exchange (destination-range partition over the GPUs of one NVSwitch domain) -----------
 def p2p_push_rows(src: torch.Tensor, dst_ptrs, row0: int, ld_dst: int) -> None:
     """dst_q[row0 + i, :] = src[i, :] for every peer-mapped destination buffer (all-gather by push)."""

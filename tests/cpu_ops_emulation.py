@@ -63,8 +63,34 @@ def aggregate_bwd(g, gH, d, init=None):
     return gx
 
 
+def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, dropout_seed=0, dropout_ctr=None,
+              peer_out=None, peer_row0=0, peer_ld=0):
+    assert dropout_p == 0.0 and not peer_out
+    d_in = x_src.size(1)
+    K1 = g.R * d_in
+    A = alloc_planes(g.n_dst, K1 + d_in, mode, None)
+    aggregate_fwd(g, x_src.detach(), planes=A)
+    split_planes(x_root.detach(), A, col0=K1)
+    return transform_fwd(A, K1, d_in, W2d, root, bias, relu, mode), A
+
+
+def layer_bwd(g, gO, relu_mask, mask_scale, planes, W2d, root, d_in, mode, need_x, add_root_term, need_w, need_b,
+              gx_out=None):
+    d_out = gO.size(1)
+    K1 = g.R * d_in
+    G = alloc_planes(gO.size(0), d_out, mode, None)
+    colsum = split_planes(gO, G, relu_mask=relu_mask, colsum=True, mask_scale=mask_scale)
+    gx = gA = gW = groot = gb = None
+    if need_x:
+        gA = transform_dgrad(G, d_out, W2d, root, mode)
+        gx = aggregate_bwd(g, gA, d_in, init=gA[:, K1:] if add_root_term else None)
+    if need_w:
+        gW, groot, gb = transform_wgrad(planes, K1, d_in, G, d_out, colsum if need_b else None, mode)
+    return gx, gA, gW, groot, gb
+
+
 def install(monkeypatch_target):
     """Replace the kernel wrappers in ``ops`` (module object) by the CPU stand-ins."""
     for name in ("alloc_planes", "aggregate_fwd", "split_planes", "transform_fwd", "transform_dgrad",
-                 "transform_wgrad", "aggregate_bwd"):
+                 "transform_wgrad", "aggregate_bwd", "layer_fwd", "layer_bwd"):
         setattr(monkeypatch_target, name, globals()[name])
