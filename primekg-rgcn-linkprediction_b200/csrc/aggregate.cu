@@ -63,6 +63,7 @@ struct AggParams {
 // ---- hub chunks: one block per chunk --------------------------------------------------------
 template <int G, int VPL, bool W>
 __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
+  pdl_enter();
   constexpr int GROUPS = 256 / G;
   __shared__ float4 red[GROUPS][G * VPL];
   const int chunk = blockIdx.x;
@@ -169,6 +170,7 @@ constexpr int agg_min_blocks(int G, int vpl, int mix, bool w) {
 
 template <int G, int VPL, int MIX, bool W>
 __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate_rows_kernel(const AggParams p) {
+  pdl_enter();
   constexpr int GROUPS = 256 / G;
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
   constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
@@ -381,8 +383,8 @@ template <int G, int VPL>
 static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
   if (n_chunks > 0) {
-    if (p.edge_w) hub_partial_kernel<G, VPL, true><<<n_chunks, 256, 0, st>>>(p);
-    else hub_partial_kernel<G, VPL, false><<<n_chunks, 256, 0, st>>>(p);
+    if (p.edge_w) RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, true>, dim3(n_chunks), dim3(256), 0, st, p));
+    else RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, false>, dim3(n_chunks), dim3(256), 0, st, p));
     RGCN_LAUNCH_CHECK();
   }
   if (p.n_rows == 0) return RGCN_OK;
@@ -390,14 +392,14 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
   const bool w = p.edge_w != nullptr;
   const size_t sm = (size_t)p.R * p.B * sizeof(float) * (p.dotP ? 1 + GROUPS : 1);
   if (mix == MIX_NONE) {
-    if (w) aggregate_rows_kernel<G, VPL, MIX_NONE, true><<<grid, 256, 0, st>>>(p);
-    else aggregate_rows_kernel<G, VPL, MIX_NONE, false><<<grid, 256, 0, st>>>(p);
+    if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, true>, dim3(grid), dim3(256), 0, st, p));
+    else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, false>, dim3(grid), dim3(256), 0, st, p));
   } else if (mix == MIX_SUM) {
-    if (w) aggregate_rows_kernel<G, VPL, MIX_SUM, true><<<grid, 256, 0, st>>>(p);
-    else aggregate_rows_kernel<G, VPL, MIX_SUM, false><<<grid, 256, 0, st>>>(p);
+    if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true>, dim3(grid), dim3(256), 0, st, p));
+    else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, false>, dim3(grid), dim3(256), 0, st, p));
   } else {
-    if (w) aggregate_rows_kernel<G, VPL, MIX_BASIS, true><<<grid, 256, sm, st>>>(p);
-    else aggregate_rows_kernel<G, VPL, MIX_BASIS, false><<<grid, 256, sm, st>>>(p);
+    if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_BASIS, true>, dim3(grid), dim3(256), sm, st, p));
+    else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_BASIS, false>, dim3(grid), dim3(256), sm, st, p));
   }
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;

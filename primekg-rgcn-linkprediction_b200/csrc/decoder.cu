@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) distmult_fwd_kernel(const float* __restri
                                                            const float* __restrict__ rel_rows,
                                                            const float* __restrict__ rel_scale, int64_t n_pairs,
                                                            int32_t d, float* __restrict__ score) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (p >= n_pairs) return;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const float* __restri
                                                            float* __restrict__ g_t, int64_t ld_gt,
                                                            float* __restrict__ g_rel_table,
                                                            float* __restrict__ g_rel_rows) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (p >= n_pairs) return;
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const float* __restri
 __global__ void __launch_bounds__(1024) bce_logits_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                               int64_t n, float* __restrict__ loss,
                                                               int32_t* __restrict__ n_correct) {
+  pdl_enter();
   __shared__ float sl[32];
   __shared__ int sc[32];
   float acc = 0.f;
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(1024) bce_logits_fwd_kernel(const float* __res
 // g_x[i] = g_loss * (sigmoid(x_i) - y_i) / n
 __global__ void bce_logits_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n,
                                       const float* __restrict__ g_loss, float* __restrict__ g_x) {
+  pdl_enter();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float s = 1.f / (1.f + expf(-x[i]));
@@ -157,8 +161,8 @@ extern "C" int rgcn_distmult_fwd(const float* emb_h, int64_t ld_h, const float* 
   if (n_pairs == 0) return RGCN_OK;
   CHECK_SCALE(rel_scale);
   RGCN_CHECK_ARG(score, "distmult_fwd: null output");
-  distmult_fwd_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      emb_h, ld_h, emb_t, ld_t, head, tail, rel, rel_table, rel_rows, rel_scale, n_pairs, d, score);
+  RGCN_CUDA(launch_pdl(distmult_fwd_kernel, dim3((unsigned)((n_pairs + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 
+      emb_h, ld_h, emb_t, ld_t, head, tail, rel, rel_table, rel_rows, rel_scale, n_pairs, d, score));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -175,9 +179,9 @@ extern "C" int rgcn_distmult_bwd(const float* emb_h, int64_t ld_h, const float* 
                  (((uintptr_t)g_h | (uintptr_t)g_t) & 15) == 0, "distmult_bwd: bad gradient buffers");
   CHECK_SCALE(rel_scale);
   RGCN_CHECK_ARG(!g_rel_table || rel, "distmult_bwd: g_rel_table needs rel");
-  distmult_bwd_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+  RGCN_CUDA(launch_pdl(distmult_bwd_kernel, dim3((unsigned)((n_pairs + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, 
       emb_h, ld_h, emb_t, ld_t, head, tail, rel, rel_table, rel_rows, rel_scale, g_score, n_pairs, d, g_h, ld_gh, g_t, ld_gt,
-      g_rel_table, g_rel_rows);
+      g_rel_table, g_rel_rows));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -195,7 +199,7 @@ extern "C" int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const 
 extern "C" int rgcn_bce_logits_fwd(const float* logits, const float* labels, int64_t n, float* loss, int32_t* n_correct,
                                    rgcn_stream_t stream) {
   RGCN_CHECK_ARG(n > 0 && logits && labels && loss, "bce_logits_fwd: bad arguments");
-  bce_logits_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, labels, n, loss, n_correct);
+  RGCN_CUDA(launch_pdl(bce_logits_fwd_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, logits, labels, n, loss, n_correct));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -203,7 +207,7 @@ extern "C" int rgcn_bce_logits_fwd(const float* logits, const float* labels, int
 extern "C" int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, const float* g_loss,
                                    float* g_logits, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(n > 0 && logits && labels && g_loss && g_logits, "bce_logits_bwd: bad arguments");
-  bce_logits_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logits, labels, n, g_loss, g_logits);
+  RGCN_CUDA(launch_pdl(bce_logits_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, logits, labels, n, g_loss, g_logits));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

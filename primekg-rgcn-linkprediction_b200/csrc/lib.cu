@@ -1,5 +1,6 @@
 // Library-level entry points: ABI version, thread-local error text, device check.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,6 +22,15 @@ void set_error(const char* fmt, ...) {
 static unsigned long long g_launches = 0;
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RGCN_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 int sm_count() {
   static int cached[64] = {0};

@@ -26,6 +26,7 @@ struct ConstPeerPtrs {
 __global__ void __launch_bounds__(256) push_rows_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows,
                                                         int cols, PeerPtrs dst, int n_dst, int64_t row0,
                                                         int64_t ld_dst) {
+  pdl_enter();
   const int c4n = cols >> 2;
   const int64_t total = rows * c4n;
   constexpr int U = 4;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) reduce_split_kernel(ConstPeerPtrs part, i
                                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                            int64_t ldp, float* __restrict__ colsum_partial,
                                                            int64_t rows_per_block) {
+  pdl_enter();
   __shared__ float4 red[256];
   const int tpr = cols >> 2;                       // threads per row (<= 256)
   const int rpp = 256 / tpr;                       // rows per pass
@@ -150,7 +152,7 @@ extern "C" int rgcn_p2p_push_rows(const float* src, int64_t ld_src, int64_t rows
   int64_t blocks = (total + 256 * 4 - 1) / (256 * 4);
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  push_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows, cols, d, n_dst, row0, ld_dst);
+  RGCN_CUDA(launch_pdl(push_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, src, ld_src, rows, cols, d, n_dst, row0, ld_dst));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -178,9 +180,9 @@ extern "C" int rgcn_p2p_reduce_split(const float* const* part_host, int32_t n_pa
   const int64_t nb = rgcn_split_planes_blocks(rows, cols);
   const int rpp = 256 / (cols / 4) > 0 ? 256 / (cols / 4) : 1;
   const int64_t rows_per_block = ((rows + nb - 1) / nb + rpp - 1) / rpp * rpp;
-  reduce_split_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
+  RGCN_CUDA(launch_pdl(reduce_split_kernel, dim3((unsigned)nb), dim3(256), 0, (cudaStream_t)stream, 
       pp, n_part, row0, ld_part, extra, ld_extra, relu_mask, ldm, mask_scale, rows, cols, out, ldo, (__nv_bfloat16*)hi,
-      (__nv_bfloat16*)lo, ldp, colsum_partial, rows_per_block);
+      (__nv_bfloat16*)lo, ldp, colsum_partial, rows_per_block));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
                                                            __nv_bfloat16* __restrict__ lo, int64_t ldp,
                                                            float* __restrict__ colsum_partial, int64_t rows_per_block,
                                                            float scale, float* __restrict__ out_f32, int64_t ldf) {
+  pdl_enter();
   __shared__ float4 red[256];
   const int tpr = cols >> 2;                       // threads per row (<= 256)
   const int rpp = 256 / tpr;                       // rows per pass
@@ -127,6 +128,7 @@ __device__ __forceinline__ uint32_t drop_block_key(uint32_t key, uint64_t elem) 
 __global__ void split_weights_kernel(const float* __restrict__ w1, int K1, const float* __restrict__ w2, int K2, int N,
                                      int transpose, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                      int rows_pad, int cols_pad, unsigned long long* seed_state) {
+  pdl_enter();
   if (seed_state && blockIdx.x == 0 && threadIdx.x == 0) *seed_state += 1ull;
   // output [rows_pad, cols_pad]; transpose: out[n][k] = W[k][n], else out[k][n] = W[k][n]
   const int64_t total = (int64_t)rows_pad * cols_pad;
@@ -197,7 +199,6 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const uint32_t acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;     // columns of one accumulator
   const uint32_t tmem_cols = 2 * acc_cols;
 
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);               // the TMA thread's arrive.expect_tx
@@ -219,6 +220,11 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
+  // everything above is independent of the predecessor's data: barriers, TMEM, descriptor prefetch
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  __syncthreads();
 
   if (warp < K_EPI_WARPS) {
     // ===================== epilogue: warp w drains TMEM lanes 32 (w % 4) .. +31 (the quarter a warp may address),
@@ -408,6 +414,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_cons
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp < 4) {
     // ===================== epilogue: TMEM -> partial buffer (warp w owns TMEM lanes 32w..32w+31) ==========
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            float* __restrict__ gw2, int main_blocks,
                                                            const float* __restrict__ colsum_part, int n_colsum,
                                                            float* __restrict__ gbias) {
+  pdl_enter();
   if ((int)blockIdx.x >= main_blocks) {
     colsum_reduce_block(colsum_part, n_colsum, N, blockIdx.x - main_blocks, gbias);
     return;
@@ -552,6 +561,7 @@ __device__ __forceinline__ void colsum_reduce_block(const float* __restrict__ pa
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int n_part, int N,
                                                               float* __restrict__ out) {
+  pdl_enter();
   colsum_reduce_block(part, n_part, N, blockIdx.x, out);
 }
 
@@ -665,11 +675,11 @@ static int launch_kmajor(GemmKParams p, const void* a_hi, const void* a_lo, int6
   if (split) {
     rc = set_smem(gemm_kmajor_kernel<true>, KStage<true>::SMEM);
     if (rc) return rc;
-    gemm_kmajor_kernel<true><<<grid, K_THREADS, KStage<true>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
+    RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<true>, dim3(grid), dim3(K_THREADS), KStage<true>::SMEM, st, ahi, alo, mhi, mlo, p));
   } else {
     rc = set_smem(gemm_kmajor_kernel<false>, KStage<false>::SMEM);
     if (rc) return rc;
-    gemm_kmajor_kernel<false><<<grid, K_THREADS, KStage<false>::SMEM, st>>>(ahi, alo, mhi, mlo, p);
+    RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<false>, dim3(grid), dim3(K_THREADS), KStage<false>::SMEM, st, ahi, alo, mhi, mlo, p));
   }
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
@@ -701,7 +711,7 @@ extern "C" int rgcn_reduce_partials(const float* part, int64_t n_part, int32_t n
   RGCN_CHECK_ARG(part && out && n_part >= 0 && n_part < (1ll << 31) && n_cols >= 4 && n_cols % 4 == 0,
                  "reduce_partials: n_cols must be a positive multiple of 4");
   RGCN_CHECK_ARG(((uintptr_t)part & 15) == 0 && ((uintptr_t)out & 15) == 0, "reduce_partials: buffers must be 16-byte aligned");
-  reduce_partials_kernel<<<(unsigned)(n_cols / 4), 256, 0, (cudaStream_t)stream>>>(part, (int)n_part, n_cols, out);
+  RGCN_CUDA(launch_pdl(reduce_partials_kernel, dim3((unsigned)(n_cols / 4)), dim3(256), 0, (cudaStream_t)stream, part, (int)n_part, n_cols, out));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -720,10 +730,10 @@ extern "C" int rgcn_split_planes(const float* x, int64_t ldx, const float* relu_
   const int64_t nb = rgcn_split_planes_blocks(rows, cols);
   const int rpp = 256 / (cols / 4) > 0 ? 256 / (cols / 4) : 1;
   const int64_t rows_per_block = ((rows + nb - 1) / nb + rpp - 1) / rpp * rpp;
-  split_planes_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(x, ldx, relu_mask, ldm, rows, cols,
+  RGCN_CUDA(launch_pdl(split_planes_kernel, dim3((unsigned)nb), dim3(256), 0, (cudaStream_t)stream, x, ldx, relu_mask, ldm, rows, cols,
                                                                      (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp,
                                                                      colsum_partial, rows_per_block, mask_scale,
-                                                                     out_f32, ld_f32);
+                                                                     out_f32, ld_f32));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -775,9 +785,9 @@ extern "C" int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t ld
   const bool split = mode == 0;
   {
     const int64_t total = (int64_t)t.n_pad * k_pad;
-    split_weights_kernel<<<grid_cap((total + 255) / 256, 1184), 256, 0, st>>>(W1, K1, W2, K2, d_out, 1, bhi,
+    RGCN_CUDA(launch_pdl(split_weights_kernel, dim3(grid_cap((total + 255) / 256, 1184)), dim3(256), 0, st, W1, K1, W2, K2, d_out, 1, bhi,
                                                                               split ? blo : nullptr, t.n_pad, k_pad,
-                                                                              dropout_p > 0.f ? dropout_counter : nullptr);
+                                                                              dropout_p > 0.f ? dropout_counter : nullptr));
     RGCN_LAUNCH_CHECK();
   }
   GemmKParams p{};
@@ -823,8 +833,8 @@ extern "C" int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t 
   const bool split = mode == 0;
   {
     const int64_t total = (int64_t)t.n_pad * k_pad;
-    split_weights_kernel<<<grid_cap((total + 255) / 256, 1184), 256, 0, st>>>(W1, K1, W2, K2, d_out, 0, bhi,
-                                                                              split ? blo : nullptr, t.n_pad, k_pad, nullptr);
+    RGCN_CUDA(launch_pdl(split_weights_kernel, dim3(grid_cap((total + 255) / 256, 1184)), dim3(256), 0, st, W1, K1, W2, K2, d_out, 0, bhi,
+                                                                              split ? blo : nullptr, t.n_pad, k_pad, nullptr));
     RGCN_LAUNCH_CHECK();
   }
   GemmKParams p{};
@@ -875,19 +885,19 @@ extern "C" int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t 
     if (split) {
       const int smem = WStage<true>::STAGES * WStage<true>::BYTES + 1024;
       rc = set_smem(gemm_wgrad_kernel<true>, smem); if (rc) return rc;
-      gemm_wgrad_kernel<true><<<grid, 192, smem, st>>>(ahi, alo, ghi, glo, p);
+      RGCN_CUDA(launch_pdl(gemm_wgrad_kernel<true>, dim3(grid), dim3(192), smem, st, ahi, alo, ghi, glo, p));
     } else {
       const int smem = WStage<false>::STAGES * WStage<false>::BYTES + 1024;
       rc = set_smem(gemm_wgrad_kernel<false>, smem); if (rc) return rc;
-      gemm_wgrad_kernel<false><<<grid, 192, smem, st>>>(ahi, alo, ghi, glo, p);
+      RGCN_CUDA(launch_pdl(gemm_wgrad_kernel<false>, dim3(grid), dim3(192), smem, st, ahi, alo, ghi, glo, p));
     }
     RGCN_LAUNCH_CHECK();
   }
   const int64_t total = (int64_t)K * (d_out / 4);
   const unsigned main_blocks = grid_cap((total + 63) / 64, 4736);
-  wgrad_reduce_kernel<<<main_blocks + (gbias ? (unsigned)(d_out / 4) : 0u), 256, 0, st>>>(
+  RGCN_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(main_blocks + (gbias ? (unsigned)(d_out / 4) : 0u)), dim3(256), 0, st, 
       p.partial, n_rows > 0 ? splits : 0, m_tiles * BM, t.n_pad, K1, K2, d_out, gW1, gW2, (int)main_blocks,
-      colsum_partial, n_colsum, gbias);
+      colsum_partial, n_colsum, gbias));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
