@@ -137,6 +137,8 @@ typedef struct rgcn_csr {
  *   With a weighted CSR (g->w != NULL, i.e. the transposed orientation) h_r is the weighted SUM instead of
  *   the mean: called on the transposed CSR with X = the masked output gradient this is the mirrored
  *   backward of the basis form,  T_b[j] = sum_r comp[r, b] * sum_{e in seg_t(j, r)} w_t[e] * G[row_t[e]].
+ *   x_root != NULL (unmixed form only): row i of x_root [n_rows, d] is appended as block R of output row i, so the
+ *   transform operand [H | X] (self-loop term last) is complete after this one kernel (H must be R+1 blocks wide).
  *   dot_p != NULL (needs comp, B <= 8): additionally  gc[r, b] = sum_i <h_r[i], dot_p[i, b*d:(b+1)*d]>, the
  *   gradient of comp when dot_p = X @ [V_1 .. V_B]; written as rgcn_aggregate_blocks(g, d) partial rows of
  *   R*B floats into gc_partial, to be summed with rgcn_reduce_partials (fixed order).
@@ -147,6 +149,7 @@ int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t
                        const float* comp, int32_t B,
                        void* H, void* H_lo, int64_t ldh, int32_t out_mode,
                        const float* dot_p, int64_t ld_dot_p, float* gc_partial,
+                       const float* x_root, int64_t ld_x_root,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 /* out[c] = sum over the n_part rows of part[., n_cols] in a fixed order (deterministic). */
 int rgcn_reduce_partials(const float* part, int64_t n_part, int32_t n_cols, float* out, rgcn_stream_t stream);
@@ -214,8 +217,8 @@ int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t lda, int32_
                          void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * One layer per call.  rgcn_layer_fwd = rgcn_aggregate_fwd (into the H columns of the operand planes) +
- * rgcn_split_planes (x into the last d_in columns) + rgcn_transform_fwd: everything `RGCNConv.forward` does at
+ * One layer per call.  rgcn_layer_fwd = rgcn_aggregate_fwd (H into the first R blocks of the operand planes, x_root
+ * appended as the last block by the same kernel) + rgcn_transform_fwd: everything `RGCNConv.forward` does at
  * src/models/rgcn.py:123 / :128 (+ the ReLU / dropout of :124-125 when asked).  rgcn_layer_bwd = rgcn_split_planes
  * (G = g_out * mask) + rgcn_transform_dgrad + rgcn_aggregate_bwd + rgcn_transform_wgrad: its autograd backward
  * (src/train.py:306).  Same kernels, same results as the separate calls; one foreign call instead of 5-7, which is

@@ -65,7 +65,7 @@ PROTOTYPES = {
     "rgcn_hub_chunk_table": (C.c_int, [p, p, i32, i32, p, p]),
     "rgcn_aggregate_workspace_bytes": (sz, [PCSR, i32]),
     "rgcn_aggregate_blocks": (i64, [PCSR, i32]),
-    "rgcn_aggregate_fwd": (C.c_int, [PCSR, p, i64, i32, p, i32, p, p, i64, i32, p, i64, p, p, sz, p]),
+    "rgcn_aggregate_fwd": (C.c_int, [PCSR, p, i64, i32, p, i32, p, p, i64, i32, p, i64, p, p, i64, p, sz, p]),
     "rgcn_reduce_partials": (C.c_int, [p, i64, i32, p, p]),
     "rgcn_aggregate_bwd": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, p, sz, p]),
     "rgcn_split_planes_blocks": (i64, [i64, i32]),

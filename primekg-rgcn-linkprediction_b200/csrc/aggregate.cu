@@ -48,6 +48,8 @@ struct AggParams {
   int32_t B;
   const float* init;         // nullable (MIX_SUM)
   int64_t ld_init;
+  const float* root_rows;    // nullable (MIX_NONE): row i of this matrix is appended as block R of output row i — the
+  int64_t ld_root;           // self-loop operand [H | X] of the transform is then complete after one kernel
   void* O;
   void* O_lo;                // second bf16 plane (out_mode 2)
   int64_t ldo;
@@ -209,6 +211,11 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
     vcol[k] = act[k] ? vi * 4 : 0;               // inactive lanes gather column 0; their sums are never stored
   }
 
+  if (MIX == MIX_NONE && p.root_rows) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (act[k]) store_vec(p, row, R * p.block_stride + vcol[k], ldg4(p.root_rows + row * p.ld_root + vcol[k]));
+  }
   float4 mix[NB][VPL];
   if (MIX != MIX_NONE) {
 #pragma unroll
@@ -465,9 +472,12 @@ extern "C" int64_t rgcn_aggregate_blocks(const rgcn_csr_t* g, int32_t d) {
 extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d,
                                   const float* comp, int32_t B, void* H, void* H_lo, int64_t ldh, int32_t out_mode,
                                   const float* dot_p, int64_t ld_dot_p, float* gc_partial,
+                                  const float* x_root, int64_t ld_x_root,
                                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
   int rc = check_common(g, X, ldx, d, workspace, workspace_bytes);
   if (rc) return rc;
+  RGCN_CHECK_ARG(!x_root || (!comp && ((uintptr_t)x_root & 15) == 0 && ld_x_root % 4 == 0),
+                 "aggregate_fwd: x_root (appended self-loop block) needs the unmixed form and 16-byte aligned rows");
   RGCN_CHECK_ARG(!dot_p || (comp && B <= kMaxBasis && gc_partial && ((uintptr_t)dot_p & 15) == 0 && ld_dot_p % 4 == 0),
                  "aggregate_fwd: the coefficient-gradient side output needs comp, B <= %d, aligned P and a partial buffer", kMaxBasis);
   RGCN_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "aggregate_fwd: out_mode must be 0 (fp32), 1 (bf16) or 2 (bf16 hi+lo)");
@@ -482,6 +492,7 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
   p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d; p.block_stride = d;
   p.O = H; p.O_lo = H_lo; p.ldo = ldh; p.out_mode = out_mode; p.partials = (float*)workspace;
   p.dotP = dot_p; p.ld_dotP = ld_dot_p; p.gc_partial = gc_partial;
+  p.root_rows = x_root; p.ld_root = ld_x_root;
   cudaStream_t st = (cudaStream_t)stream;
   if (!comp) return dispatch_agg(p, MIX_NONE, g->n_chunks, st);
   // basis blocks are produced kMaxBasis at a time (registers hold the B accumulators), feature columns in slices

@@ -14,12 +14,10 @@ extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream
   const int out_mode = a->mode == 0 ? 2 : 1;
   RGCN_CHECK_ARG(a->mode == 0 || a->mode == 1, "layer_fwd: mode must be 0 (fp32) or 1 (bf16)");
   RGCN_CHECK_ARG(a->A_hi && (a->mode == 1 || a->A_lo) && a->lda >= K1 + K2, "layer_fwd: operand planes missing or too narrow");
+  // the row walk also appends x_root[i] as the last block of row i: the operand [H | X] in one kernel
   int rc = rgcn_aggregate_fwd(a->csr, a->x_src, a->ld_x_src, a->d_in, nullptr, 0, a->A_hi, a->mode == 0 ? a->A_lo : nullptr,
-                              a->lda, out_mode, nullptr, 0, nullptr, a->agg_workspace, a->agg_workspace_bytes, stream);
-  if (rc) return rc;
-  rc = rgcn_split_planes(a->x_root, a->ld_x_root, nullptr, 0, a->csr->n_rows, a->d_in,
-                         (__nv_bfloat16*)a->A_hi + K1, a->mode == 0 ? (void*)((__nv_bfloat16*)a->A_lo + K1) : nullptr, a->lda,
-                         nullptr, 1.f, nullptr, 0, stream);
+                              a->lda, out_mode, nullptr, 0, nullptr, a->x_root, a->ld_x_root, a->agg_workspace,
+                              a->agg_workspace_bytes, stream);
   if (rc) return rc;
   return rgcn_transform_fwd(a->A_hi, a->A_lo, a->lda, K1, K2, a->weight, a->root, a->bias, a->relu, a->csr->n_rows, a->d_out,
                             a->out, a->ldo, a->mode, a->dropout_p, a->dropout_seed, a->dropout_counter, a->peer_out_host,

@@ -27,14 +27,17 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False, comp: Optional[torch.Tensor] = None,
-                  planes=None, transposed: bool = False, dot_p: Optional[torch.Tensor] = None):
+                  planes=None, transposed: bool = False, dot_p: Optional[torch.Tensor] = None,
+                  x_root: Optional[torch.Tensor] = None):
     """H[i, r*d:(r+1)*d] = mean_{j in N_r(i)} x[j]  (or the basis-mixed Z when ``comp`` [R, B] is given).
 
     ``planes=(hi, lo_or_None)``: write the result as bf16 planes (the tensor-core operand format) into the first
     R*d (or B*d) columns of the given row-major bf16 tensors instead of allocating an fp32 / bf16 matrix.
     ``transposed``: walk the (src, rel) CSR with its 1/count edge weights instead — with ``comp`` and x = the masked
     output gradient this is the mirrored backward of the basis form.  ``dot_p`` [rows, B*d] (needs ``comp``):
-    also return gc[r, b] = sum_i <h_r[i], dot_p[i, b]> (the gradient of ``comp``) -> (H, gc)."""
+    also return gc[r, b] = sum_i <h_r[i], dot_p[i, b]> (the gradient of ``comp``) -> (H, gc).
+    ``x_root`` [rows, d] (unmixed form, needs ``planes`` / an output R+1 blocks wide): appended as block R of every
+    output row — the operand [H | X] of the transform in one kernel."""
     lib = _lib.load()
     x = _f32c(x, "x")
     ori = g.bwd if transposed else g.fwd
@@ -58,6 +61,10 @@ def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False, comp: Op
     else:
         H = torch.empty(n_out, blocks * d, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
         H_lo, mode = None, int(out_bf16)
+    if x_root is not None:
+        x_root = _f32c(x_root, "x_root")
+        if comp is not None or x_root.size(0) != n_out or x_root.size(1) != d or H.size(1) < (blocks + 1) * d:
+            raise ValueError("x_root needs the unmixed form, [rows, d] and an output of R+1 blocks")
     gc_part = None
     if dot_p is not None:
         if comp is None:
@@ -69,7 +76,8 @@ def aggregate_fwd(g: RelGraph, x: torch.Tensor, out_bf16: bool = False, comp: Op
         gc_part = torch.empty(max(nb, 1), g.R * blocks, dtype=torch.float32, device=x.device)
     _lib.check(lib.rgcn_aggregate_fwd(ori.ref, _ptr(x), x.stride(0), d, _ptr(comp), 0 if comp is None else blocks,
                                       _ptr(H), _ptr(H_lo), H.stride(0), mode, _ptr(dot_p),
-                                      0 if dot_p is None else dot_p.stride(0), _ptr(gc_part), _ptr(ws),
+                                      0 if dot_p is None else dot_p.stride(0), _ptr(gc_part), _ptr(x_root),
+                                      0 if x_root is None else x_root.stride(0), _ptr(ws),
                                       0 if ws is None else ws.numel() * 4, _stream(x.device)), "rgcn_aggregate_fwd")
     if dot_p is None:
         return H

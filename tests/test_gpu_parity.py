@@ -154,6 +154,22 @@ def test_aggregate_bwd(pkg, name, d):
     assert torch.equal(got, got2)                            # deterministic: no atomics
 
 
+def test_aggregate_appends_root_rows(pkg):
+    """x_root appended as the last block by the row walk = the separate split_planes call, bit for bit."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()["primekg_100k"]
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    torch.manual_seed(5)
+    for d in (64, 256, 100):
+        x = torch.randn(N, d, device=DEV)
+        A = ops.alloc_planes(N, (R + 1) * d, "fp32", DEV)
+        B = ops.alloc_planes(N, (R + 1) * d, "fp32", DEV)
+        ops.aggregate_fwd(g, x, planes=A, x_root=x)
+        ops.aggregate_fwd(g, x, planes=B)
+        ops.split_planes(x, B, col0=R * d)
+        assert torch.equal(A[0], B[0]) and torch.equal(A[1], B[1])
+
+
 def test_aggregate_basis_mix(pkg):
     from primekg_rgcn_linkprediction_b200 import ops
     ei, et, N, R = graphs()["uniform_r30"]

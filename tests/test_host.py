@@ -37,7 +37,7 @@ def test_library_argument_errors_without_gpu(lib_built):
                             None, 0, None)
     assert rc == 1 and "negative" in _lib.last_error()
     g = _lib.CsrStruct()
-    rc = lib.rgcn_aggregate_fwd(ctypes.byref(g), None, 0, 6, None, 0, None, None, 0, 0, None, 0, None, None, 0, None)
+    rc = lib.rgcn_aggregate_fwd(ctypes.byref(g), None, 0, 6, None, 0, None, None, 0, 0, None, 0, None, None, 0, None, 0, None)
     assert rc == 1
     with pytest.raises(_lib.RGCNLibraryError):
         _lib.check(rc, "rgcn_aggregate_fwd")
