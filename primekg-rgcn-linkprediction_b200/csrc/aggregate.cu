@@ -16,6 +16,8 @@
 // into kHubChunk-edge chunks that whole blocks reduce beforehand (hub_partial_kernel) into a
 // partial buffer; the row kernel then adds the chunk partials in chunk order.  Everything is
 // deterministic: same bits on every run.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -34,6 +36,7 @@ struct AggParams {
   const int32_t* chunk_table;  // [n_chunks][4]: {segment key, first chunk of the segment, -, -}
   const int32_t* row_order;    // nullable: rows in the order the groups take them (longest first)
   int32_t hub_threshold;
+  int32_t skip_hubs;           // the row walk leaves hub segments out (hub_finish_kernel adds them afterwards)
   int32_t n_hubs;
   int64_t n_rows;
   int32_t R;
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
       const int end = __shfl_sync(gmask, my_end, rr, G);
       const int len = end - beg;
       if (len == 0 && MIX != MIX_NONE) continue;
+      if (MIX != MIX_BASIS && p.skip_hubs && len > p.hub_threshold) continue;   // added by hub_finish_kernel
       float4 acc[VPL];
 #pragma unroll
       for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -386,9 +390,139 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
   }
 }
 
+// ---- hub finish: one G-lane group per hub ROW (led by the row's first hub segment) -------------------------
+// Runs after hub_partial_kernel (chunk partials) and after the row walk (which skipped the hub segments): sums each
+// hub segment's partials in chunk order and writes its block (MIX_NONE) or adds the row's hub segments to the row the
+// walk already wrote (MIX_SUM).  Fixed order everywhere: deterministic.
+template <int G, int VPL, int MIX, bool W>
+__global__ void __launch_bounds__(256) hub_finish_kernel(const AggParams p) {
+  pdl_enter();
+  constexpr int GROUPS = 256 / G;
+  const int lane = threadIdx.x % G;
+  const int h0 = blockIdx.x * GROUPS + threadIdx.x / G;
+  if (h0 >= p.n_hubs) return;
+  const int R = p.R, d = p.d, nvec = p.d >> 2;
+  const int key0 = __ldg(p.hub_keys + h0);
+  const int64_t row = key0 / R;
+  if (h0 > 0 && __ldg(p.hub_keys + h0 - 1) / R == row) return;      // not the row's first hub segment
+  bool act[VPL];
+  int vcol[VPL];
+  float4 total[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = k * G + lane;
+    act[k] = vi < nvec;
+    vcol[k] = act[k] ? vi * 4 : 0;
+    total[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+  for (int h = h0; h < p.n_hubs; ++h) {
+    const int key = __ldg(p.hub_keys + h);
+    if (key / R != row) break;
+    const int r = key - (int)row * R;
+    float4 acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c0 = __ldg(p.hub_chunk_ptr + h), c1 = __ldg(p.hub_chunk_ptr + h + 1);
+    int c = c0;
+    for (; c + U <= c1; c += U) {                    // loads U chunks ahead, adds strictly in chunk order
+      float4 v[U][VPL];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) v[u][k] = *reinterpret_cast<const float4*>(p.partials + (size_t)(c + u) * d + vcol[k]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) add4(acc[k], v[u][k]);
+    }
+    for (; c < c1; ++c) {
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) add4(acc[k], *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k]));
+    }
+    if (!W) {
+      const float len = (float)(__ldg(p.rowptr + key + 1) - __ldg(p.rowptr + key));
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) acc[k] = div4(acc[k], len);
+    }
+    if (MIX == MIX_NONE) {
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        if (act[k]) store_vec(p, row, r * p.block_stride + vcol[k], acc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) add4(total[k], acc[k]);
+    }
+  }
+  if (MIX == MIX_SUM) {
+    float* o = reinterpret_cast<float*>(p.O) + row * p.ldo;      // fp32 output (checked by the host)
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (act[k]) {
+        float4 cur = *reinterpret_cast<const float4*>(o + vcol[k]);
+        add4(cur, total[k]);
+        *reinterpret_cast<float4*>(o + vcol[k]) = cur;
+      }
+    }
+  }
+}
+
+// side stream + events for the fork / join of the hub pass (one set per device, created on first use)
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static ForkJoin* fork_join() {
+  static ForkJoin fj[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  ForkJoin& f = fj[dev];
+  if (!f.side) {
+    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &f;
+}
+// Opt-in (RGCN_OVERLAP_HUBS=1).  Measured on the B200 it LOSES against the plain order hub pass -> row walk
+// (cfg2 d = 256 forward 93 vs 75 us, step 0.595 vs 0.533 ms): the two latency-bound kernels slow each other down and
+// the finish kernel adds a serial tail, so the default stays the single-stream order.
+static bool overlap_hubs_enabled() {
+  const char* e = getenv("RGCN_OVERLAP_HUBS");
+  return e && e[0] == '1';
+}
+
+template <int G, int VPL, int MIX, bool W>
+static int launch_agg_overlapped(AggParams p, int n_chunks, cudaStream_t st) {
+  // hub chunks on a side stream, concurrently with the row walk (which skips the hub segments); then the finish
+  // kernel.  Inside a stream capture the fork / join becomes two parallel branches of the graph.
+  constexpr int GROUPS = 256 / G;
+  ForkJoin* fj = fork_join();
+  if (!fj) { set_error("aggregate: could not create the side stream for the hub pass"); return RGCN_ECUDA; }
+  p.skip_hubs = 1;
+  RGCN_CUDA(cudaEventRecord(fj->fork, st));
+  RGCN_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+  hub_partial_kernel<G, VPL, W><<<n_chunks, 256, 0, fj->side>>>(p);
+  RGCN_LAUNCH_CHECK();
+  RGCN_CUDA(cudaEventRecord(fj->join, fj->side));
+  const unsigned grid = (unsigned)((p.n_rows + GROUPS - 1) / GROUPS);
+  RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX, W>, dim3(grid), dim3(256), 0, st, p));
+  RGCN_LAUNCH_CHECK();
+  RGCN_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
+  hub_finish_kernel<G, VPL, MIX, W><<<(unsigned)((p.n_hubs + GROUPS - 1) / GROUPS), 256, 0, st>>>(p);
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
 template <int G, int VPL>
 static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
+  if (n_chunks > 0 && p.n_rows > 0 && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
+    const bool w = p.edge_w != nullptr;
+    if (mix == MIX_NONE)
+      return w ? launch_agg_overlapped<G, VPL, MIX_NONE, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_NONE, false>(p, n_chunks, st);
+    return w ? launch_agg_overlapped<G, VPL, MIX_SUM, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_SUM, false>(p, n_chunks, st);
+  }
   if (n_chunks > 0) {
     if (p.edge_w) RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, true>, dim3(n_chunks), dim3(256), 0, st, p));
     else RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, false>, dim3(n_chunks), dim3(256), 0, st, p));

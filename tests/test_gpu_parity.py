@@ -630,7 +630,13 @@ def test_fused_dropout_changes_under_graph_replay(pkg):
     assert torch.equal(a, b)
 
 
-def test_hub_rows_mixed_modes(pkg):
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_hub_rows_mixed_modes(pkg, overlap, monkeypatch):
+    monkeypatch.setenv("RGCN_OVERLAP_HUBS", overlap)     # "1": hub chunks on a side stream + finish kernel (opt-in)
+    _hub_rows_mixed_modes(pkg)
+
+
+def _hub_rows_mixed_modes(pkg):
     """Graph where several relations of the same rows are hubs (> 128 edges) next to short segments: the row pass
     skips what needs chunk partials and the hub-row pass fills it in, for all three mixing modes."""
     from primekg_rgcn_linkprediction_b200 import ops
