@@ -12,6 +12,7 @@ parameters at the defaults (reference results/results.json:29).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -48,10 +49,19 @@ class DrugDiseaseRGCN(nn.Module):
             self.extra_convs = nn.ModuleList(
                 RGCNConv(hidden_dim, hidden_dim, num_relations, num_bases=num_bases) for _ in range(num_layers - 2))
         self.dropout = nn.Dropout(dropout)
+        self._eval_cache = None
         self._init_embeddings()
 
     def _init_embeddings(self) -> None:
         nn.init.xavier_uniform_(self.node_embeddings.weight)
+
+    def _eval_key(self, graph):
+        """Identity of an eval-mode encoding: the graph object and every parameter's storage + in-place version
+        (optimizer steps, ``load_state_dict`` and ``.to()`` all change one of them)."""
+        ps = tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
+        modes = tuple(c.mode for c in self._layers())
+        return (id(graph), graph.E, ps, modes, os.environ.get("PRIMEKG_RGCN_MODE", ""),
+                os.environ.get("PRIMEKG_RGCN_BASIS_FORM", ""))
 
     def _layers(self):
         yield self.conv1
@@ -64,6 +74,15 @@ class DrugDiseaseRGCN(nn.Module):
         x = self.node_embeddings.weight if node_indices is None else self.node_embeddings(node_indices)
         _need_cuda(x, "DrugDiseaseRGCN.forward")
         graph = get_graph(edge_index, edge_type, x.size(0), self.num_relations)
+        # The reference's ranking evaluation re-encodes the full graph for every batch of test edges with unchanged
+        # weights (src/evaluate.py:251-254: 16 identical passes per evaluation).  In eval mode without autograd the
+        # result is a pure function of (graph, parameters): keep the last one and hand it back while neither changed.
+        cacheable = not self.training and not torch.is_grad_enabled() and node_indices is None
+        if cacheable:
+            key = self._eval_key(graph)
+            hit = self._eval_cache
+            if hit is not None and hit[0] == key and hit[1]._version == hit[2]:
+                return hit[1]
         layers = list(self._layers())
         for li, conv in enumerate(layers):
             last = li == len(layers) - 1
@@ -72,6 +91,8 @@ class DrugDiseaseRGCN(nn.Module):
             x = conv.forward_graph(x, graph, relu=not last, dropout_p=p if p < 1.0 else 0.0)
             if not last and p >= 1.0:
                 x = self.dropout(x)
+        if cacheable:
+            self._eval_cache = (key, x, x._version)
         return x
 
     def get_node_embeddings(self, node_indices: torch.Tensor) -> torch.Tensor:

@@ -744,3 +744,36 @@ def test_basis_forms_agree_r30(pkg, monkeypatch):
         res[form] = (out.detach(), x.grad, conv.weight.grad.clone(), conv.comp.grad.clone(), conv.root.grad.clone())
     for a, b in zip(res["w"], res["z"]):
         assert float((a - b).norm() / (a.norm() + 1e-30)) < 1e-4
+
+
+def test_eval_encoder_output_is_cached(pkg):
+    """evaluate.py re-encodes the full graph once per batch of test edges (reference src/evaluate.py:251-254); in eval
+    mode under no_grad the second call launches nothing, and any parameter change or a train-mode call recomputes."""
+    from primekg_rgcn_linkprediction_b200 import _lib
+    g = load_golden("small_full")
+    m = _product_model(pkg, g)
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    lib = _lib.load()
+    m.eval()
+    with torch.no_grad():
+        a = m.encoder(ei, et)
+        n0 = lib.rgcn_launch_count()
+        b = m.encoder(ei, et)
+        assert lib.rgcn_launch_count() == n0 and b is a            # served from the cache
+        c = m.get_embeddings(ei, et)
+        assert lib.rgcn_launch_count() == n0 and torch.equal(c, a)
+        m.encoder.conv1.root.mul_(1.5)                             # in-place parameter change (an optimizer step)
+        d = m.encoder(ei, et)
+        assert lib.rgcn_launch_count() > n0 and not torch.equal(d, a)
+        n1 = lib.rgcn_launch_count()
+        d.add_(1.0)                                                # a caller scribbles on the returned tensor
+        e = m.encoder(ei, et)
+        assert lib.rgcn_launch_count() > n1 and not torch.equal(e, d)
+    n2 = lib.rgcn_launch_count()
+    f = m.encoder(ei, et)                                          # autograd on: never cached
+    assert lib.rgcn_launch_count() > n2 and f.requires_grad
+    m.train()
+    with torch.no_grad():
+        n3 = lib.rgcn_launch_count()
+        m.encoder(ei, et)
+        assert lib.rgcn_launch_count() > n3
