@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 2
+#define RGCN_B200_ABI_VERSION 3
 
 enum {
   RGCN_OK = 0,
@@ -166,6 +166,14 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
                        const float* init, int64_t ld_init,
                        float* gX, int64_t ldgx,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+/* Same walk over a ROW-SPARSE gH: gH_rows holds only the listed rows (see rgcn_rows_compact), slot[i] is the compact
+ * row of node i or zero_row (an all-zero row of gH_rows / init_rows) for every other node; init_rows is indexed through
+ * slot as well.  Edges whose gathered row is absent are skipped — they would add exact zeros — so the result equals
+ * rgcn_aggregate_bwd on the dense matrix bit for bit. */
+int rgcn_aggregate_bwd_rows(const rgcn_csr_t* gt, const float* gH_rows, int64_t ldg, int32_t d,
+                            const int32_t* slot, int32_t zero_row, const float* init_rows, int64_t ld_init,
+                            float* gX, int64_t ldgx,
+                            void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Relational transform on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM, every operand tile
@@ -254,7 +262,27 @@ typedef struct rgcn_layer_bwd_args {
   float* g_weight; float* g_root; float* g_bias;               /* out, NULL: not wanted                      */
   void* agg_workspace; size_t agg_workspace_bytes;
   void* gemm_workspace; size_t gemm_workspace_bytes;
+  /* Row-sparse form (rows != NULL): the caller guarantees that g_out is zero outside the listed rows — the 2 * batch
+   * (head, tail) rows the link-prediction loss reads from the encoder output, src/models/rgcn.py:325-326, so this is the
+   * backward of the LAST layer in the reference's training step (src/train.py:291-306).  With m_c =
+   * rgcn_rows_compact_size(n_list) the scratch shapes become: G planes [m_c, d_out], gA [m_c + 1, (R+1) d_in] (row m_c
+   * is the zero row), colsum_partial [rgcn_rows_compact_blocks(n_list), d_out], gemm workspace for m_c rows; relu_mask
+   * must be NULL and add_root_term set.  Results equal the dense form (absent rows only ever add exact zeros). */
+  const int64_t* rows; int64_t n_list;      /* device list of node ids, duplicates allowed                    */
+  int32_t* slot;                            /* scratch [n_dst]                                                */
+  void* Ac_hi; void* Ac_lo; int64_t ldac;   /* scratch planes [m_c, (R+1) d_in] (weight gradient wanted)      */
 } rgcn_layer_bwd_args;
+
+/* Compaction step of the row-sparse backward (csrc/rowsparse.cu), also callable on its own:
+ * slot[i] = first position of node i in rows[0 .. n_list) or m_c; G planes row c = g_out[rows[c]] when slot[rows[c]] == c
+ * else zeros; Ac planes likewise from A (optional); colsum_partial = per-block column sums of the G rows (optional);
+ * zero_row[0 .. zero_cols) is cleared (optional: the zero row of the dgrad output). */
+int64_t rgcn_rows_compact_size(int64_t n_list);       /* m_c = n_list rounded up to a multiple of 128 */
+int64_t rgcn_rows_compact_blocks(int64_t n_list);     /* rows of colsum_partial                       */
+int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_nodes, int32_t* slot,
+                      const float* g_out, int64_t ld_g_out, int32_t d_out, void* G_hi, void* G_lo, int64_t ldg,
+                      const void* A_hi, const void* A_lo, int64_t lda, int32_t K, void* Ac_hi, void* Ac_lo,
+                      int64_t ldac, float* colsum_partial, float* zero_row, int32_t zero_cols, rgcn_stream_t stream);
 
 int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream);
 int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream);

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgcn_b200.so")
 
-ABI_VERSION = 2          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
+ABI_VERSION = 3          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
 
 _lock = threading.Lock()
 _lib = None
@@ -50,7 +50,8 @@ class LayerBwdArgs(C.Structure):
                 ("weight", p), ("root", p), ("A_hi", p), ("A_lo", p), ("lda", i64),
                 ("G_hi", p), ("G_lo", p), ("ldg", i64), ("colsum_partial", p), ("gA", p), ("ld_gA", i64),
                 ("g_x", p), ("ld_g_x", i64), ("g_weight", p), ("g_root", p), ("g_bias", p),
-                ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz)]
+                ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
+                ("rows", p), ("n_list", i64), ("slot", p), ("Ac_hi", p), ("Ac_lo", p), ("ldac", i64)]
 
 # name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
 PROTOTYPES = {
@@ -68,6 +69,10 @@ PROTOTYPES = {
     "rgcn_aggregate_fwd": (C.c_int, [PCSR, p, i64, i32, p, i32, p, p, i64, i32, p, i64, p, p, i64, p, sz, p]),
     "rgcn_reduce_partials": (C.c_int, [p, i64, i32, p, p]),
     "rgcn_aggregate_bwd": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, p, sz, p]),
+    "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, p, sz, p]),
+    "rgcn_rows_compact_size": (i64, [i64]),
+    "rgcn_rows_compact_blocks": (i64, [i64]),
+    "rgcn_rows_compact": (C.c_int, [p, i64, i64, p, p, i64, i32, p, p, i64, p, p, i64, i32, p, p, i64, p, p, i32, p]),
     "rgcn_split_planes_blocks": (i64, [i64, i32]),
     "rgcn_split_planes": (C.c_int, [p, i64, p, i64, i64, i32, p, p, i64, p, C.c_float, p, i64, p]),
     "rgcn_transform_workspace_bytes": (sz, [i64, i32, i32]),

@@ -19,7 +19,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, rowsparse
 from .graph import RelGraph, get_graph
 
 
@@ -69,10 +69,14 @@ class _RGCNLayerFn(torch.autograd.Function):
         need_src, need_root_x, need_W, need_root, need_b = ctx.needs_input_grad[:5]
         need_w_any = need_W or need_root or need_b
         need_x = need_src or need_root_x
+        # gO zero outside a short, announced row list (the decoder's backward, rowsparse.py): compact backward
+        rows = None
+        if out is None and ctx.shared and graph.n_src == graph.n_dst:
+            rows = rowsparse.claim(gO)
         # out is zero exactly where ReLU or the fused dropout killed the element: one mask serves both
         gx, gA, gWf, groot, gb = ops.layer_bwd(
             graph, gO.contiguous(), out, 1.0 / (1.0 - ctx.p_drop), (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
-            need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any)
+            need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any, rows=rows)
         gx_src = gx_root = None
         if need_x:
             if ctx.shared:

@@ -63,10 +63,16 @@ struct AggParams {
   const float* dotP;         // nullable, [n_rows, B * d]
   int64_t ld_dotP;
   float* gc_partial;         // [gridDim.x, R * B]
+  // Row-sparse gathered matrix (backward of a layer whose output gradient is zero outside a short row list, e.g. the
+  // 2 * batch rows a link-prediction loss touches): F holds only the listed rows, slot[j] is the compact row of node j
+  // or zero_row (an all-zero row of F) for every other node.  Absent edges are skipped; since they would add exact
+  // zeros, the result equals the dense walk bit for bit.
+  const int32_t* slot;       // nullable, [number of gatherable nodes]
+  int32_t zero_row;
 };
 
 // ---- hub chunks: one block per chunk --------------------------------------------------------
-template <int G, int VPL, bool W>
+template <int G, int VPL, bool W, bool SLOT = false>
 __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
   pdl_enter();
   constexpr int GROUPS = 256 / G;
@@ -102,13 +108,22 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
   for (; e + U <= g_end; e += U) {
     float4 v[U][VPL];
     float w[U];
+    int js[U];
+    bool any = !SLOT;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = __ldg(idx + e + u);
+      js[u] = __ldg(idx + e + u);
+      if (SLOT) { js[u] = __ldg(p.slot + js[u]); any |= js[u] != p.zero_row; }
+    }
+    if (!any) continue;                            // (group-uniform) every edge of the batch points at a zero row
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = js[u];
       if (W) w[u] = __ldg(ew + e + u);
       const float* __restrict__ rp = Fb + (size_t)j * ldf;
+      const bool on = !SLOT || j != p.zero_row;
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) v[u][k] = ldg4(rp + vcol[k]);
+      for (int k = 0; k < VPL; ++k) v[u][k] = on ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -118,7 +133,8 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
       }
   }
   for (; e < g_end; ++e) {
-    const int j = __ldg(idx + e);
+    int j = __ldg(idx + e);
+    if (SLOT) { j = __ldg(p.slot + j); if (j == p.zero_row) continue; }
     const float* __restrict__ rp = Fb + (size_t)j * ldf;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
@@ -173,7 +189,7 @@ constexpr int agg_min_blocks(int G, int vpl, int mix, bool w) {
   return (mix == MIX_SUM && w) ? 3 : 4;                           // d <= 64
 }
 
-template <int G, int VPL, int MIX, bool W>
+template <int G, int VPL, int MIX, bool W, bool SLOT = false>
 __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate_rows_kernel(const AggParams p) {
   pdl_enter();
   constexpr int GROUPS = 256 / G;
@@ -226,8 +242,9 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
 #pragma unroll
       for (int k = 0; k < VPL; ++k) mix[b][k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (MIX == MIX_SUM && p.init) {
+      const int64_t irow = SLOT ? (int64_t)__ldg(p.slot + row) : row;      // compact row of this node (or the zero row)
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) mix[0][k] = ldg4(p.init + row * p.ld_init + vcol[k]);
+      for (int k = 0; k < VPL; ++k) mix[0][k] = ldg4(p.init + irow * p.ld_init + vcol[k]);
     }
   }
 
@@ -236,11 +253,20 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
   const int row_end = __ldg(rowptr + R);
   int wbase = -(1 << 30), wi0 = 0, wi1 = 0;
   float ww0 = 1.f, ww1 = 1.f;
+  unsigned long long present = 0ull;     // SLOT: bit o = edge wbase + o of the window gathers a listed row
   auto refill = [&](int e) {
     wbase = e;
     const bool in0 = e + lane < row_end, in1 = e + G + lane < row_end;
     wi0 = in0 ? __ldg(idx + e + lane) : 0;
     wi1 = in1 ? __ldg(idx + e + G + lane) : 0;
+    if (SLOT) {
+      wi0 = in0 ? __ldg(p.slot + wi0) : p.zero_row;
+      wi1 = in1 ? __ldg(p.slot + wi1) : p.zero_row;
+      const int sh = (G == 32) ? 0 : (int)((threadIdx.x & 31) / G * G);
+      const unsigned b0 = (__ballot_sync(gmask, wi0 != p.zero_row) & gmask) >> sh;
+      const unsigned b1 = (__ballot_sync(gmask, wi1 != p.zero_row) & gmask) >> sh;
+      present = ((unsigned long long)b1 << G) | (unsigned long long)b0;
+    }
     if (W) {
       ww0 = in0 ? __ldg(ew + e + lane) : 0.f;
       ww1 = in1 ? __ldg(ew + e + G + lane) : 0.f;
@@ -289,6 +315,38 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
         for (; c < c1; ++c) {
 #pragma unroll
           for (int k = 0; k < VPL; ++k) add4(acc[k], *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k]));
+        }
+      } else if (SLOT && len > 0) {
+        // only the edges whose gathered row is listed (set bits of the window mask), U at a time, in edge order
+        const float* __restrict__ Fb = F + (size_t)r * rel_stride;
+        int e = beg;
+        while (e < end) {
+          if (e >= wbase + 2 * G) refill(e);
+          const int o0 = e - wbase;
+          const int lim = min(end - wbase, 2 * G);
+          unsigned long long m = present >> o0;
+          if (lim - o0 < 64) m &= (1ull << (lim - o0)) - 1ull;
+          while (m) {
+            float4 v[U][VPL];
+            float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const bool on = m != 0ull;
+              const int off = o0 + (on ? __ffsll((long long)m) - 1 : 0);
+              m &= m - 1ull;
+              const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
+              const float wv = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
+              w[u] = on ? wv : 0.f;
+              const float* __restrict__ rp = Fb + (size_t)j * ldf;
+#pragma unroll
+              for (int k = 0; k < VPL; ++k) v[u][k] = on ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int k = 0; k < VPL; ++k) fma4(acc[k], w[u], v[u][k]);
+          }
+          e = wbase + lim;
         }
       } else if (len > 0) {
         const float* __restrict__ Fb = F + (size_t)r * rel_stride;
@@ -517,11 +575,24 @@ static int launch_agg_overlapped(AggParams p, int n_chunks, cudaStream_t st) {
 template <int G, int VPL>
 static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
-  if (n_chunks > 0 && p.n_rows > 0 && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
+  if (!p.slot && n_chunks > 0 && p.n_rows > 0 && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
     const bool w = p.edge_w != nullptr;
     if (mix == MIX_NONE)
       return w ? launch_agg_overlapped<G, VPL, MIX_NONE, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_NONE, false>(p, n_chunks, st);
     return w ? launch_agg_overlapped<G, VPL, MIX_SUM, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_SUM, false>(p, n_chunks, st);
+  }
+  if (p.slot) {
+    // row-sparse gather: backward form only (summed relations, weighted edges)
+    if (mix != MIX_SUM || !p.edge_w) { set_error("aggregate: the row-sparse gather serves the backward walk only"); return RGCN_EINVAL; }
+    if (n_chunks > 0) {
+      RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, true, true>, dim3(n_chunks), dim3(256), 0, st, p));
+      RGCN_LAUNCH_CHECK();
+    }
+    if (p.n_rows == 0) return RGCN_OK;
+    RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true>, dim3((unsigned)((p.n_rows + GROUPS - 1) / GROUPS)),
+                         dim3(256), 0, st, p));
+    RGCN_LAUNCH_CHECK();
+    return RGCN_OK;
   }
   if (n_chunks > 0) {
     if (p.edge_w) RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, true>, dim3(n_chunks), dim3(256), 0, st, p));
@@ -655,9 +726,27 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
   return RGCN_OK;
 }
 
+static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,
+                              int32_t zero_row, const float* init, int64_t ld_init, float* gX, int64_t ldgx,
+                              void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
 extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
                                   const float* init, int64_t ld_init, float* gX, int64_t ldgx,
                                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+  return aggregate_bwd_impl(gt, gH, ldg, d, nullptr, 0, init, ld_init, gX, ldgx, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rgcn_aggregate_bwd_rows(const rgcn_csr_t* gt, const float* gH_rows, int64_t ldg, int32_t d,
+                                       const int32_t* slot, int32_t zero_row, const float* init_rows, int64_t ld_init,
+                                       float* gX, int64_t ldgx, void* workspace, size_t workspace_bytes,
+                                       rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(slot && zero_row >= 0, "aggregate_bwd_rows: slot map and zero row are required");
+  return aggregate_bwd_impl(gt, gH_rows, ldg, d, slot, zero_row, init_rows, ld_init, gX, ldgx, workspace, workspace_bytes, stream);
+}
+
+static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,
+                              int32_t zero_row, const float* init, int64_t ld_init, float* gX, int64_t ldgx,
+                              void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
   int rc = check_common(gt, gH, ldg, d, workspace, workspace_bytes);
   if (rc) return rc;
   RGCN_CHECK_ARG(gX && ((uintptr_t)gX & 15) == 0 && ldgx % 4 == 0, "aggregate_bwd: output must be 16-byte aligned with ld %% 4 == 0");
@@ -671,5 +760,6 @@ extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t
   p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d; p.block_stride = d;
   p.init = init; p.ld_init = ld_init; p.B = 1;
   p.O = gX; p.ldo = ldgx; p.out_mode = 0; p.partials = (float*)workspace;
+  p.slot = slot; p.zero_row = zero_row;
   return dispatch_agg(p, MIX_SUM, gt->n_chunks, (cudaStream_t)stream);
 }

@@ -24,6 +24,42 @@ extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream
                             a->n_peer, a->peer_row0, a->peer_ld, a->gemm_workspace, a->gemm_workspace_bytes, stream);
 }
 
+// g_out is zero outside the listed rows (csrc/rowsparse.cu): compact, then the same four steps over m_c rows
+static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
+  const int R = a->csr_t->R;
+  const int K1 = R * a->d_in, K2 = a->d_in, K = K1 + K2;
+  const bool need_w = a->g_weight != nullptr;
+  const int64_t m_c = rgcn_rows_compact_size(a->n_list);
+  RGCN_CHECK_ARG(a->n_list > 0 && a->slot, "layer_bwd: the row-sparse form needs a row list and the slot scratch");
+  RGCN_CHECK_ARG(!a->relu_mask, "layer_bwd: the row-sparse form serves a layer without ReLU (the last one)");
+  RGCN_CHECK_ARG(!a->gA || a->add_root_term || !a->g_x, "layer_bwd: the row-sparse form is the one-GPU form (root term added)");
+  RGCN_CHECK_ARG(!need_w || (a->Ac_hi && (a->mode == 1 || a->Ac_lo)), "layer_bwd: compact operand planes missing");
+  int rc = rgcn_rows_compact(a->rows, a->n_list, a->n_dst, a->slot, a->g_out, a->ld_g_out, a->d_out, a->G_hi,
+                             a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->A_hi, a->mode == 0 ? a->A_lo : nullptr, a->lda, K,
+                             need_w ? a->Ac_hi : nullptr, (need_w && a->mode == 0) ? a->Ac_lo : nullptr, a->ldac,
+                             a->g_bias ? a->colsum_partial : nullptr, a->gA ? a->gA + m_c * a->ld_gA : nullptr, a->gA ? K : 0,
+                             stream);
+  if (rc) return rc;
+  if (a->gA) {
+    rc = rgcn_transform_dgrad(a->G_hi, a->G_lo, a->ldg, a->d_out, a->weight, K1, a->root, K2, m_c, a->gA, a->ld_gA,
+                              a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
+    if (rc) return rc;
+    if (a->g_x) {
+      rc = rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c, a->gA + K1, a->ld_gA, a->g_x,
+                                   a->ld_g_x, a->agg_workspace, a->agg_workspace_bytes, stream);
+      if (rc) return rc;
+    }
+  }
+  if (need_w) {
+    rc = rgcn_transform_wgrad(a->Ac_hi, a->Ac_lo, a->ldac, K1, K2, a->G_hi, a->G_lo, a->ldg, a->d_out, m_c,
+                              a->g_bias ? a->colsum_partial : nullptr,
+                              a->g_bias ? (int32_t)rgcn_rows_compact_blocks(a->n_list) : 0, a->g_weight, a->g_root,
+                              a->g_bias, a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  return RGCN_OK;
+}
+
 extern "C" int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(a && a->csr_t, "layer_bwd: null arguments");
   const int R = a->csr_t->R;
@@ -33,6 +69,7 @@ extern "C" int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream
   const bool need_w = a->g_weight != nullptr;
   RGCN_CHECK_ARG(!need_w || (a->g_root && a->A_hi && (a->mode == 1 || a->A_lo)), "layer_bwd: weight gradient needs g_root and the saved planes");
   RGCN_CHECK_ARG(!a->g_bias || (need_w && a->colsum_partial), "layer_bwd: g_bias needs the weight gradient and colsum_partial");
+  if (a->rows) return layer_bwd_rows(a, stream);
   // G = g_out * [mask > 0] * mask_scale as planes, column sums = bias gradient
   int rc = rgcn_split_planes(a->g_out, a->ld_g_out, a->relu_mask, a->ld_mask, a->n_dst, a->d_out, a->G_hi,
                              a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->g_bias ? a->colsum_partial : nullptr,

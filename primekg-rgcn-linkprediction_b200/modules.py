@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import rowsparse
 from .conv import RGCNConv
 from .graph import get_graph
 
@@ -112,7 +113,11 @@ class _DistMultGather(torch.autograd.Function):
         emb, head, tail, rel, rel_table, rel_rows, rel_scale = ctx.saved_tensors
         g_emb, _, g_tab, g_rows = ops.distmult_bwd(emb, emb, head, tail, rel, rel_table, rel_rows, g,
                                                    ctx.needs_input_grad[4], rel_scale)
-        return (g_emb if ctx.needs_input_grad[0] else None), None, None, None, g_tab, g_rows, None
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, g_tab, g_rows, None
+        # g_emb is zero outside the head / tail rows: tell the last encoder layer (rowsparse.py)
+        rowsparse.announce(g_emb, torch.cat([head.reshape(-1), tail.reshape(-1)]).to(torch.int64))
+        return g_emb, None, None, None, g_tab, g_rows, None
 
 
 class _DistMultRows(torch.autograd.Function):

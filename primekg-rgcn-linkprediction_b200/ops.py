@@ -99,16 +99,24 @@ def reduce_partials(part: torch.Tensor) -> torch.Tensor:
 
 
 def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, slot: Optional[torch.Tensor] = None,
+                  zero_row: int = -1) -> torch.Tensor:
     """gX[j] = init[j] + sum_r sum_{(j->i, r)} gH[i, r*d:(r+1)*d] / max(|N_r(i)|, 1)  over the transposed CSR.
-    ``out``: write into this [n_src, d] fp32 tensor (e.g. a peer-visible buffer) instead of allocating."""
+    ``out``: write into this [n_src, d] fp32 tensor (e.g. a peer-visible buffer) instead of allocating.
+    ``slot`` (int32 [n_dst]) + ``zero_row``: gH (and init) hold only the listed rows; node i lives in row slot[i], every
+    other node maps to the all-zero row ``zero_row`` (``rgcn_aggregate_bwd_rows``)."""
     lib = _lib.load()
     gH = _f32c(gH, "gH")
-    if gH.size(0) != g.n_dst or gH.size(1) < g.R * d:
+    rows_form = slot is not None
+    if rows_form:
+        if slot.dtype != torch.int32 or slot.numel() != g.n_dst or not (0 <= zero_row < gH.size(0)) or g.n_src != g.n_dst:
+            raise ValueError("slot must be int32 [n_dst] and zero_row a row of gH")
+        slot = slot.contiguous()
+    if (not rows_form and gH.size(0) != g.n_dst) or gH.size(1) < g.R * d:
         raise ValueError("gH must be [n_dst, >= R*d]")
     if init is not None:
         init = _f32c(init, "init")
-        if init.size(0) != g.n_src or init.size(1) < d:
+        if init.size(0) != (gH.size(0) if rows_form else g.n_src) or init.size(1) < d:
             raise ValueError("init must be [n_src, >= d]")
     if out is None:
         gX = torch.empty(g.n_src, d, dtype=torch.float32, device=gH.device)
@@ -117,6 +125,12 @@ def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Te
         if gX.dtype != torch.float32 or gX.shape != (g.n_src, d) or gX.stride(1) != 1 or gX.stride(0) % 4:
             raise ValueError("out must be a row-major float32 [n_src, d] tensor")
     ws = g.bwd.workspace(d)
+    if rows_form:
+        _lib.check(lib.rgcn_aggregate_bwd_rows(g.bwd.ref, _ptr(gH), gH.stride(0), d, _ptr(slot), int(zero_row), _ptr(init),
+                                               0 if init is None else init.stride(0), _ptr(gX), gX.stride(0), _ptr(ws),
+                                               0 if ws is None else ws.numel() * 4, _stream(gH.device)),
+                   "rgcn_aggregate_bwd_rows")
+        return gX
     _lib.check(lib.rgcn_aggregate_bwd(g.bwd.ref, _ptr(gH), gH.stride(0), d, _ptr(init),
                                       0 if init is None else init.stride(0), _ptr(gX), gX.stride(0), _ptr(ws),
                                       0 if ws is None else ws.numel() * 4, _stream(gH.device)), "rgcn_aggregate_bwd")
@@ -395,10 +409,12 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
 
 def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], mask_scale: float, planes, W2d: torch.Tensor,
               root: torch.Tensor, d_in: int, mode: str, need_x: bool, add_root_term: bool, need_w: bool, need_b: bool,
-              gx_out: Optional[torch.Tensor] = None):
+              gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None):
     """split(gO, mask) -> dgrad -> transposed gather -> wgrad of one layer in ONE C call (``rgcn_layer_bwd``).
     Returns (g_x | None, gA | None, gW2d | None, g_root | None, g_bias | None); ``gA[:, R*d_in:]`` is the root-term
-    gradient (already inside g_x when ``add_root_term``)."""
+    gradient (already inside g_x when ``add_root_term``).
+    ``rows`` (int64 device list, duplicates allowed): the caller guarantees gO is zero outside these rows; the backward
+    then runs on the compacted rows (csrc/rowsparse.cu) with the same results, and gA comes back compact (``None`` here)."""
     lib = _lib.load()
     gO = _f32c(gO, "gO")
     if relu_mask is not None:
@@ -411,27 +427,40 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
     K = K1 + d_in
     dev = gO.device
     A_hi, A_lo = planes
-    G = alloc_planes(n, d_out, mode, dev)
+    sparse = rows is not None
+    if sparse:
+        if relu_mask is not None or not add_root_term or g.n_src != g.n_dst:
+            raise ValueError("the row-sparse backward serves an unpartitioned layer without ReLU")
+        rows = _idx(rows, "rows").reshape(-1)
+        m = int(lib.rgcn_rows_compact_size(rows.numel()))
+    else:
+        m = n
+    G = alloc_planes(m, d_out, mode, dev)
     colsum = None
     if need_b:
-        colsum = torch.empty(max(int(lib.rgcn_split_planes_blocks(n, d_out)), 1), d_out, dtype=torch.float32, device=dev)
-    gA = torch.empty(n, K, dtype=torch.float32, device=dev) if need_x else None
+        nb = lib.rgcn_rows_compact_blocks(rows.numel()) if sparse else lib.rgcn_split_planes_blocks(n, d_out)
+        colsum = torch.empty(max(int(nb), 1), d_out, dtype=torch.float32, device=dev)
+    gA = torch.empty(m + (1 if sparse else 0), K, dtype=torch.float32, device=dev) if need_x else None
     gx = None
     if need_x:
         gx = gx_out if gx_out is not None else torch.empty(g.n_src, d_in, dtype=torch.float32, device=dev)
     gW = torch.empty(K1, d_out, dtype=torch.float32, device=dev) if need_w else None
     groot = torch.empty(d_in, d_out, dtype=torch.float32, device=dev) if need_w else None
     gb = torch.empty(d_out, dtype=torch.float32, device=dev) if (need_w and need_b) else None
+    slot = torch.empty(n, dtype=torch.int32, device=dev) if sparse else None
+    Ac = alloc_planes(m, K, mode, dev) if (sparse and need_w) else (None, None)
     aws = g.bwd.workspace(d_in)
-    gws = _gemm_workspace(dev, n, K, d_out)
+    gws = _gemm_workspace(dev, m, K, d_out)
     args = _lib.LayerBwdArgs(
         g.bwd.ptr, gO.data_ptr(), gO.stride(0), _dp(relu_mask), 0 if relu_mask is None else relu_mask.stride(0),
         float(mask_scale), n, d_in, d_out, _mode_id(mode), int(add_root_term), W2d.data_ptr(), root.data_ptr(),
         A_hi.data_ptr(), _dp(A_lo), A_hi.stride(0), G[0].data_ptr(), _dp(G[1]), G[0].stride(0), _dp(colsum if gb is not None else None),
         _dp(gA), 0 if gA is None else gA.stride(0), _dp(gx), 0 if gx is None else gx.stride(0), _dp(gW), _dp(groot), _dp(gb),
-        _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel())
+        _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel(),
+        _dp(rows), 0 if rows is None else rows.numel(), _dp(slot), _dp(Ac[0]), _dp(Ac[1]),
+        0 if Ac[0] is None else Ac[0].stride(0))
     _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
-    return gx, gA, gW, groot, gb
+    return gx, (None if sparse else gA), gW, groot, gb
 
 
 # ---- peer-memory exchange (destination-range partition over the GPUs of one NVSwitch domain) -----------

@@ -1,0 +1,54 @@
+"""Row-sparse output gradients: the hand-over between the decoder's backward and the last encoder layer's backward.
+
+The training step of the reference (src/train.py:291-306) reads only ``node_embeddings[head]`` / ``[tail]`` of the
+encoder output (src/models/rgcn.py:325-326), so the gradient autograd hands to the last ``RGCNConv`` is an ``[N, d]``
+matrix that is zero outside <= 2 * batch rows.  ``_DistMultGather.backward`` still returns that dense matrix (autograd's
+contract; the engine may add other contributions to it), and *announces* here which rows it wrote.  The layer's backward
+takes the row-sparse path (csrc/rowsparse.cu) only if the tensor it receives is that very buffer, unmodified: same
+storage, same shape, same in-place version.  Anything else — another consumer of the embeddings whose gradient the
+engine added, a hook that rewrote it — fails the check and the dense path runs.  ``PRIMEKG_RGCN_SPARSE_BWD=0`` turns
+the hand-over off.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+MAX_FRACTION = 0.5     # longer row lists (relative to the node count) take the dense backward
+stats = {"claimed": 0, "declined": 0}      # how often the last layer took the compact / the dense backward
+_announced = None      # (dense gradient tensor, its _version when announced, int64 device list of the rows written)
+
+
+def enabled() -> bool:
+    return os.environ.get("PRIMEKG_RGCN_SPARSE_BWD", "1") != "0"
+
+
+def announce(dense: torch.Tensor, rows: torch.Tensor) -> None:
+    """``dense`` is zero outside ``rows`` (duplicates allowed).  Holding the tensor keeps its storage from being reused
+    while the announcement stands, which is what makes the pointer comparison in ``claim`` sound."""
+    global _announced
+    _announced = (dense, dense._version, rows) if enabled() else None
+
+
+def claim(grad: torch.Tensor) -> Optional[torch.Tensor]:
+    """The announced row list if ``grad`` is the announced buffer, untouched, and short enough to pay off; else None.
+    An announcement is consumed by the first claim attempt."""
+    global _announced
+    a, _announced = _announced, None
+    if a is None:
+        return None
+    dense, version, rows = a
+    same = (grad.data_ptr() == dense.data_ptr() and grad.shape == dense.shape and grad.stride() == dense.stride()
+            and grad.dtype == dense.dtype and grad._version == version and dense._version == version)
+    if not same or rows.numel() == 0 or rows.numel() > MAX_FRACTION * grad.size(0):
+        stats["declined"] += 1
+        return None
+    stats["claimed"] += 1
+    return rows
+
+
+def clear() -> None:
+    global _announced
+    _announced = None

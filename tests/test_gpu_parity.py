@@ -777,3 +777,142 @@ def test_eval_encoder_output_is_cached(pkg):
         n3 = lib.rgcn_launch_count()
         m.encoder(ei, et)
         assert lib.rgcn_launch_count() > n3
+
+
+# ------------------------------------------------------------------------------------------------
+# row-sparse output gradient of the last layer (csrc/rowsparse.cu)
+@pytest.mark.parametrize("name", ["uniform_small", "uniform_r30", "primekg_100k", "val_fixture", "ragged"])
+@pytest.mark.parametrize("d", [16, 64, 128, 256])
+def test_aggregate_bwd_rows_equals_dense_bitwise(pkg, name, d):
+    """gH zero outside a row list (with duplicates): the walk that skips the absent edges returns the dense walk's bits,
+    hub segments included."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()[name]
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    gen = torch.Generator().manual_seed(5)
+    n_list = max(2, N // 8)
+    rows = torch.randint(0, N, (n_list,), generator=gen)
+    rows[1] = rows[0]                                                   # a duplicate
+    if ei.numel():
+        rows[2 % n_list] = int(torch.bincount(ei[1], minlength=N).argmax())   # the biggest hub is listed
+    uniq = torch.unique(rows)
+    m_c = (n_list + 127) // 128 * 128
+    K = (R + 1) * d
+    dense = torch.zeros(N, K)
+    dense[uniq] = torch.randn(uniq.numel(), K, generator=gen)
+    slot = torch.full((N,), m_c, dtype=torch.int32)
+    compact = torch.zeros(m_c + 1, K)
+    for c in range(n_list - 1, -1, -1):                                 # first position wins
+        slot[rows[c]] = c
+    for i in uniq.tolist():
+        compact[slot[i]] = dense[i]
+    dd, cd = dense.to(DEV), compact.to(DEV)
+    want = ops.aggregate_bwd(g, dd, d, init=dd[:, R * d:])
+    got = ops.aggregate_bwd(g, cd, d, init=cd[:, R * d:], slot=slot.to(DEV), zero_row=m_c)
+    assert torch.equal(got, want)
+
+
+def _step_grads(pkg, g, sparse, monkeypatch, extra_consumer=False, mode="fp32"):
+    from primekg_rgcn_linkprediction_b200 import rowsparse
+    monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_BWD", "1" if sparse else "0")
+    monkeypatch.setattr(rowsparse, "MAX_FRACTION", 1e9)      # the fixture graphs are small: list longer than N / 2
+    rowsparse.clear()
+    rowsparse.stats.update(claimed=0, declined=0)
+    m = _product_model(pkg, g, mode)
+    m.train()
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    if extra_consumer:
+        emb = m.encoder(ei, et)
+        scores = m.decoder.score_pairs(emb, g["heads"].to(DEV), g["tails"].to(DEV), g["rels"].to(DEV))
+        loss = F.binary_cross_entropy_with_logits(scores, g["labels"].to(DEV)) + 1e-3 * emb.square().mean()
+    else:
+        scores = m(ei, et, g["heads"].to(DEV), g["tails"].to(DEV), g["rels"].to(DEV))
+        loss = F.binary_cross_entropy_with_logits(scores, g["labels"].to(DEV))
+    loss.backward()
+    return {k: p.grad.clone() for k, p in m.named_parameters()}, dict(rowsparse.stats)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,d_in,d_out", [("uniform_r30", 64, 128), ("primekg_100k", 256, 256), ("val_fixture", 64, 64)])
+def test_layer_bwd_rows_equals_dense(pkg, name, d_in, d_out, mode):
+    """One layer's backward on a row-sparse output gradient, compact form against dense form on the SAME gO: the input
+    gradient bit for bit (dgrad rows and the walk do not depend on the other rows), the weight gradients up to the
+    summation order of the split-K reduction."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()[name]
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(N, d_in, generator=gen).to(DEV)
+    W = (torch.randn(R * d_in, d_out, generator=gen) / d_in ** 0.5).to(DEV)
+    root = (torch.randn(d_in, d_out, generator=gen) / d_in ** 0.5).to(DEV)
+    bias = torch.zeros(d_out, device=DEV)
+    _, A = ops.layer_fwd(g, x, x, W, root, bias, False, mode)
+    n_list = min(4096, N // 4)
+    rows = torch.randint(0, N, (n_list,), generator=gen)
+    rows[1::7] = rows[0]                                               # duplicates
+    rows[3] = int(torch.bincount(ei[1], minlength=N).argmax())          # a hub
+    gO = torch.zeros(N, d_out)
+    uniq = torch.unique(rows)
+    gO[uniq] = torch.randn(uniq.numel(), d_out, generator=gen)
+    gO = gO.to(DEV)
+    dense = ops.layer_bwd(g, gO, None, 1.0, A, W, root, d_in, mode, True, True, True, True)
+    comp = ops.layer_bwd(g, gO, None, 1.0, A, W, root, d_in, mode, True, True, True, True, rows=rows.to(DEV))
+    assert torch.equal(comp[0], dense[0])                               # g_x
+    assert comp[1] is None
+    for a, b, what in zip(comp[2:], dense[2:], ("g_weight", "g_root", "g_bias")):
+        scale = float(b.abs().max()) + 1e-30
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * scale, msg=lambda s: f"{what}: {s}")
+    only_x = ops.layer_bwd(g, gO, None, 1.0, A, W, root, d_in, mode, True, True, False, False, rows=rows.to(DEV))
+    assert torch.equal(only_x[0], dense[0]) and only_x[2] is None
+
+
+def _close_by_scale(a, b, what, rtol=1e-4, atol=2e-5):
+    scale = float(b.abs().max()) + 1e-30
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol * scale, msg=lambda s: f"{what}: {s}")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_sparse_last_layer_backward_equals_dense(pkg, monkeypatch, mode):
+    """The loss reads 2 * batch rows of the encoder output (reference src/models/rgcn.py:325-326): the compact backward of
+    the last layer must give the dense backward's gradients.  (Not compared bitwise here: the decoder's backward adds the
+    rows of repeated nodes with fp32 atomics, so gO itself differs in the last bit between two runs.)"""
+    g = load_golden("small_full")
+    dense, st0 = _step_grads(pkg, g, False, monkeypatch, mode=mode)
+    sparse, st1 = _step_grads(pkg, g, True, monkeypatch, mode=mode)
+    assert st0 == {"claimed": 0, "declined": 0} and st1 == {"claimed": 1, "declined": 0}
+    for k in dense:
+        _close_by_scale(sparse[k], dense[k], k)
+    if mode == "fp32":
+        for k, want in g["grads"].items():                               # and the reference's goldens
+            _close_by_scale(sparse[k].cpu(), want, k, rtol=1e-3)
+
+
+def test_sparse_backward_declines_when_gradient_is_not_row_sparse(pkg, monkeypatch):
+    """A second consumer of the embeddings makes autograd add a dense contribution: the announcement must not be
+    honoured, and the gradients must equal those of the run with the hand-over switched off."""
+    g = load_golden("small_full")
+    dense, _ = _step_grads(pkg, g, False, monkeypatch, extra_consumer=True)
+    guarded, st = _step_grads(pkg, g, True, monkeypatch, extra_consumer=True)
+    assert st["claimed"] == 0
+    for k in dense:
+        _close_by_scale(guarded[k], dense[k], k)
+
+
+def test_sparse_backward_full_size_cfg2(pkg, cfg2, monkeypatch):
+    """cfg2 at full size (849,456 edges, hubs of 10^4 edges, 4,096 listed rows with duplicates)."""
+    from primekg_rgcn_linkprediction_b200 import rowsparse
+    kg, (heads, tails, rels, labels) = cfg2
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    b = [t.to(DEV) for t in (heads, tails, rels, labels)]
+    res = {}
+    for sparse in (False, True):
+        monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_BWD", "1" if sparse else "0")
+        rowsparse.stats.update(claimed=0, declined=0)
+        torch.manual_seed(42)
+        m = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, 256, dropout=0.0, decoder_dropout=0.0).to(DEV).train()
+        F.binary_cross_entropy_with_logits(m(ei, et, b[0], b[1], b[2]), b[3]).backward()
+        assert rowsparse.stats["claimed"] == int(sparse)
+        res[sparse] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for k in res[False]:
+        rel = float((res[True][k] - res[False][k]).norm() / (res[False][k].norm() + 1e-30))
+        assert rel < 1e-5, f"{k}: relative Frobenius difference {rel:.3e}"

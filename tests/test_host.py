@@ -26,7 +26,7 @@ def test_library_exports_every_header_symbol(lib_built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rgcn_b200.h but not exported"
     assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
-    assert _lib.load().rgcn_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.load().rgcn_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_library_argument_errors_without_gpu(lib_built):
@@ -48,6 +48,27 @@ def test_csr_struct_matches_header_layout():
     # 3 pointers, 2 int64, 4 int32, 2 pointers
     assert ctypes.sizeof(_lib.CsrStruct) == 3 * 8 + 2 * 8 + 4 * 4 + 4 * 8
     assert _lib.CsrStruct.hub_keys.offset == 56
+
+
+def test_arg_structs_match_header_layout(tmp_path):
+    """The header is plain C: compile it with gcc and compare sizeof / offsetof with the ctypes mirrors."""
+    import shutil
+    import subprocess
+    from primekg_rgcn_linkprediction_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rgcn_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(rgcn_csr_t), sizeof(rgcn_layer_fwd_args),'
+                   'sizeof(rgcn_layer_bwd_args), offsetof(rgcn_layer_bwd_args, rows), offsetof(rgcn_layer_bwd_args, ldac),'
+                   'offsetof(rgcn_layer_fwd_args, gemm_workspace_bytes));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(t) for t in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.CsrStruct), ctypes.sizeof(_lib.LayerFwdArgs), ctypes.sizeof(_lib.LayerBwdArgs),
+            _lib.LayerBwdArgs.rows.offset, _lib.LayerBwdArgs.ldac.offset, _lib.LayerFwdArgs.gemm_workspace_bytes.offset]
+    assert got == want
 
 
 def test_module_surface_and_state_dict(lib_built):
