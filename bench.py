@@ -262,6 +262,28 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_value = world * kg.num_edges / (timed(e2e_graphed, args.steps) * 1e-3)
 
+    # ---- the same graphed step with the row-sparse hand-over off: the last layer's backward over all N rows, i.e.
+    #      the dense formulation SURVEY.md §8d's byte counts describe (same gradients, see tests) ----
+    sparse_env = os.environ.get("PRIMEKG_RGCN_SPARSE_BWD")
+    dense_ms = None
+    if sparse_env != "0":
+        os.environ["PRIMEKG_RGCN_SPARSE_BWD"] = "0"
+        try:
+            del gstep
+            for p in params:
+                p.grad = None
+            gdense = pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel())
+            gdense.load_batch(*d_batch)
+            for _ in range(3):
+                gdense(); allreduce_grads()
+            barrier()
+            dense_ms = timed(lambda: (gdense(), allreduce_grads()), args.steps)
+        finally:
+            if sparse_env is None:
+                del os.environ["PRIMEKG_RGCN_SPARSE_BWD"]
+            else:
+                os.environ["PRIMEKG_RGCN_SPARSE_BWD"] = sparse_env
+
     if rank != 0:
         return None
     # ---- roofline of the dominant kernel ----
@@ -313,7 +335,11 @@ def run_ours(args, rank, world, local_rank):
            "config": {"workload": WORKLOAD, "mode": args.mode, "l2": "flushed between steps (512 MiB write)",
                       "parallelism": "single GPU" if world == 1 else f"dp{world} replicas, grads all-reduced (one coalesced NCCL call)",
                       "timing": "CUDA events per step on the launching stream, max over ranks",
-                      "step": "one CUDA-graph replay of forward + BCE loss + backward (GraphedTrainStep)"},
+                      "step": "one CUDA-graph replay of forward + BCE loss + backward (GraphedTrainStep)",
+                      "last_layer_backward": ("dense over all N rows (PRIMEKG_RGCN_SPARSE_BWD=0)" if sparse_env == "0" else
+                                              "row-sparse: on the 2*batch rows of the encoder output the loss reads "
+                                              "(reference src/models/rgcn.py:325-326); identical gradients, "
+                                              "tests/test_gpu_parity.py::test_layer_bwd_rows_equals_dense")},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                    "api": "GraphedTrainStep(model, edge_index, edge_type)(heads, tails, rels, labels)",
                    "eager_module_api_value": e2e_eager_value,
@@ -321,6 +347,10 @@ def run_ours(args, rank, world, local_rank):
                            "the graph and the model stay device-resident as in reference src/train.py:122-135; "
                            "eager_module_api_value = the unmodified reference call model(...); loss; backward()"},
            "eager_ms_per_step": eager_ms,
+           "dense_last_layer_bwd": (None if dense_ms is None else
+                                    {"ms_per_step": dense_ms, "value": world * kg.num_edges / (dense_ms * 1e-3), "unit": UNIT,
+                                     "note": "same graphed step with the last layer's backward over all N rows "
+                                             "(PRIMEKG_RGCN_SPARSE_BWD=0)"}),
            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
            "wall_s_timed_region": t_wall, "clocks": clocks, "roofline": roofline}
     return out

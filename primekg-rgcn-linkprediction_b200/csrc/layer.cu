@@ -5,7 +5,80 @@
 // reference's unmodified training loop drives the modules eagerly (no CUDA graph).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 using namespace rgcn;
+
+// The weight-gradient contraction (tensor pipe) and the transposed walk (L2 / latency bound) of one layer's backward
+// both depend only on G and on the dgrad output respectively, not on each other: the wgrad runs on a side stream while
+// the main stream walks the graph, forked AFTER the dgrad launch (so the dgrad, which the walk waits for, gets the SMs
+// first) and joined before the call returns.  Inside a stream capture the fork / join becomes two branches of the graph.
+// Default: only while the stream is being captured into a CUDA graph — an eagerly driven step is bound by the host, and
+// the four extra event calls per layer only add to that.  RGCN_OVERLAP_WGRAD=0 never forks, =1 always does.
+namespace {
+struct SideStream {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static SideStream ss[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& f = ss[dev];
+  if (!f.side) {
+    if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &f;
+}
+bool overlap_wgrad(cudaStream_t st) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RGCN_OVERLAP_WGRAD");
+    v = !e ? 2 : (e[0] == '0' ? 0 : 1);
+  }
+  if (v != 2) return v != 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+}
+}  // namespace
+
+// dgrad -> [fork: wgrad on the side stream] -> transposed walk -> join.  `m` rows of G / A; `walk` launches the gather.
+template <typename Walk>
+static int dgrad_walk_wgrad(const rgcn_layer_bwd_args* a, int64_t m, const void* A_hi, const void* A_lo, int64_t lda,
+                            int32_t n_colsum, Walk walk, rgcn_stream_t stream) {
+  const int R = a->csr_t->R;
+  const int K1 = R * a->d_in, K2 = a->d_in;
+  const bool need_w = a->g_weight != nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (a->gA) {
+    rc = rgcn_transform_dgrad(a->G_hi, a->G_lo, a->ldg, a->d_out, a->weight, K1, a->root, K2, m, a->gA, a->ld_gA,
+                              a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  SideStream* ss = (need_w && a->gA && a->g_x && overlap_wgrad(st)) ? side_stream() : nullptr;
+  cudaStream_t wst = st;
+  if (ss) {
+    RGCN_CUDA(cudaEventRecord(ss->fork, st));
+    RGCN_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+    wst = ss->side;
+  }
+  if (need_w) {
+    rc = rgcn_transform_wgrad(A_hi, A_lo, lda, K1, K2, a->G_hi, a->G_lo, a->ldg, a->d_out, m,
+                              a->g_bias ? a->colsum_partial : nullptr, a->g_bias ? n_colsum : 0, a->g_weight, a->g_root,
+                              a->g_bias, a->mode, a->gemm_workspace, a->gemm_workspace_bytes, (rgcn_stream_t)wst);
+    if (rc) return rc;
+  }
+  if (ss) RGCN_CUDA(cudaEventRecord(ss->join, ss->side));
+  if (a->gA && a->g_x) {
+    rc = walk();
+    if (rc) return rc;
+  }
+  if (ss) RGCN_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
+  return RGCN_OK;
+}
 
 extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(a && a->csr, "layer_fwd: null arguments");
@@ -40,24 +113,10 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
                              a->g_bias ? a->colsum_partial : nullptr, a->gA ? a->gA + m_c * a->ld_gA : nullptr, a->gA ? K : 0,
                              stream);
   if (rc) return rc;
-  if (a->gA) {
-    rc = rgcn_transform_dgrad(a->G_hi, a->G_lo, a->ldg, a->d_out, a->weight, K1, a->root, K2, m_c, a->gA, a->ld_gA,
-                              a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
-    if (rc) return rc;
-    if (a->g_x) {
-      rc = rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c, a->gA + K1, a->ld_gA, a->g_x,
+  return dgrad_walk_wgrad(a, m_c, a->Ac_hi, a->Ac_lo, a->ldac, (int32_t)rgcn_rows_compact_blocks(a->n_list), [&]() {
+    return rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c, a->gA + K1, a->ld_gA, a->g_x,
                                    a->ld_g_x, a->agg_workspace, a->agg_workspace_bytes, stream);
-      if (rc) return rc;
-    }
-  }
-  if (need_w) {
-    rc = rgcn_transform_wgrad(a->Ac_hi, a->Ac_lo, a->ldac, K1, K2, a->G_hi, a->G_lo, a->ldg, a->d_out, m_c,
-                              a->g_bias ? a->colsum_partial : nullptr,
-                              a->g_bias ? (int32_t)rgcn_rows_compact_blocks(a->n_list) : 0, a->g_weight, a->g_root,
-                              a->g_bias, a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
-    if (rc) return rc;
-  }
-  return RGCN_OK;
+  }, stream);
 }
 
 extern "C" int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
@@ -75,22 +134,8 @@ extern "C" int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream
                              a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->g_bias ? a->colsum_partial : nullptr,
                              a->mask_scale, nullptr, 0, stream);
   if (rc) return rc;
-  if (a->gA) {
-    rc = rgcn_transform_dgrad(a->G_hi, a->G_lo, a->ldg, a->d_out, a->weight, K1, a->root, K2, a->n_dst, a->gA, a->ld_gA,
-                              a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
-    if (rc) return rc;
-    if (a->g_x) {
-      rc = rgcn_aggregate_bwd(a->csr_t, a->gA, a->ld_gA, a->d_in, a->add_root_term ? a->gA + K1 : nullptr, a->ld_gA, a->g_x,
+  return dgrad_walk_wgrad(a, a->n_dst, a->A_hi, a->A_lo, a->lda, (int32_t)rgcn_split_planes_blocks(a->n_dst, a->d_out), [&]() {
+    return rgcn_aggregate_bwd(a->csr_t, a->gA, a->ld_gA, a->d_in, a->add_root_term ? a->gA + K1 : nullptr, a->ld_gA, a->g_x,
                               a->ld_g_x, a->agg_workspace, a->agg_workspace_bytes, stream);
-      if (rc) return rc;
-    }
-  }
-  if (need_w) {
-    rc = rgcn_transform_wgrad(a->A_hi, a->A_lo, a->lda, K1, K2, a->G_hi, a->G_lo, a->ldg, a->d_out, a->n_dst,
-                              a->g_bias ? a->colsum_partial : nullptr,
-                              a->g_bias ? (int32_t)rgcn_split_planes_blocks(a->n_dst, a->d_out) : 0, a->g_weight, a->g_root,
-                              a->g_bias, a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
-    if (rc) return rc;
-  }
-  return RGCN_OK;
+  }, stream);
 }
