@@ -360,6 +360,32 @@ int rgcn_bce_logits_fwd(const float* logits, const float* labels, int64_t n, flo
                         int32_t* n_correct, rgcn_stream_t stream);
 int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, const float* g_loss,
                         float* g_logits, rgcn_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * Fused tail of the training step (the caller-side code of src/train.py:276-300, :321-322 around the model call).
+ *   rgcn_link_batch    : NegativeSampler.sample (src/train.py:59-97) + the pos/neg concatenation and labels of :281-288:
+ *                        out[0 .. n_pos) = positives (label 1), out[n_pos + i*num_neg + k] = positive i with its head
+ *                        (probability 1/2) or else its tail replaced by a uniform node (label 0).  Counter-based RNG
+ *                        (seed, device counter advanced by the call): fresh negatives on every CUDA-graph replay.
+ *   rgcn_link_loss_fwd : scores (src/models/rgcn.py:325-329, relation dropout of :207-208 by counter-based mask),
+ *                        loss = mean BCE-with-logits (src/train.py:139, :300) and the count of correct sigmoid > 0.5
+ *                        predictions (:321-322) in ONE kernel; `state` receives the dropout counter value used.
+ *   rgcn_link_loss_bwd : d loss / d emb scattered into the dense, pre-zeroed g_emb [N, d]; d loss / d rel_table (optional,
+ *                        pre-zeroed; n_rel = its row count, used to pre-reduce the block's pairs in shared memory).
+ *                        workspace: rgcn_link_loss_workspace_bytes(n_pairs), ZEROED once before first use.
+ * ------------------------------------------------------------------------------------------ */
+int rgcn_link_batch(const int64_t* pos_head, const int64_t* pos_tail, const int64_t* pos_rel, int64_t n_pos,
+                    int32_t num_neg, int64_t num_nodes, uint32_t seed, unsigned long long* counter,
+                    int64_t* heads, int64_t* tails, int64_t* rels, float* labels, rgcn_stream_t stream);
+size_t rgcn_link_loss_workspace_bytes(int64_t n_pairs);
+int rgcn_link_loss_fwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
+                       const float* rel_table, const float* labels, int64_t n_pairs, int32_t d, float dropout_p,
+                       uint32_t seed, unsigned long long* counter, unsigned long long* state, float* score,
+                       float* loss, int32_t* n_correct, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+int rgcn_link_loss_bwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
+                       const float* rel_table, const float* labels, const float* score, const float* g_loss,
+                       int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed, const unsigned long long* state,
+                       float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, rgcn_stream_t stream);
+
 /* flag[0] = 1 when any head/tail is outside [0, n_nodes) or any rel outside [0, n_rel). */
 int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,
                      int64_t n_nodes, int32_t n_rel, int32_t* flag, rgcn_stream_t stream);

@@ -196,6 +196,10 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
   constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   constexpr int U = U0 < G ? U0 : G;             // a batch never exceeds the index window
+#ifndef RGCN_TAILPRED_MAX_VPL
+#define RGCN_TAILPRED_MAX_VPL 1
+#endif
+  constexpr bool TAILPRED = MIX != MIX_BASIS && VPL <= RGCN_TAILPRED_MAX_VPL;
   extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS, then [GROUPS][R * B] coefficient-gradient sums
   const bool with_gc = MIX == MIX_BASIS && p.dotP != nullptr;
   float* s_gc = s_comp + p.R * p.B;
@@ -376,9 +380,36 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
           e += UB;
         };
         while (e + U <= end) batch(std::integral_constant<int, U>{});
-        if (U > 4 && e + 4 <= end) batch(std::integral_constant<int, (U > 4 ? 4 : 1)>{});
-        if (U > 2 && e + 2 <= end) batch(std::integral_constant<int, (U > 2 ? 2 : 1)>{});
-        if (e < end) batch(std::integral_constant<int, 1>{});
+        if (TAILPRED) {
+          // narrow rows are latency bound: ONE predicated batch for the < U remaining edges instead of up to three
+          // dependent power-of-two batches (masked edges add exact zeros, the order of the sum is unchanged)
+          if (e < end) {
+            if (e + U > wbase + 2 * G) refill(e);
+            const int n = end - e;
+            float4 v[U][VPL];
+            float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int off = e + u - wbase;
+              const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
+              if (W) w[u] = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
+              const float* __restrict__ rp = Fb + (size_t)j * ldf;
+#pragma unroll
+              for (int k = 0; k < VPL; ++k) v[u][k] = (u < n) ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int k = 0; k < VPL; ++k) {
+                if (W) fma4(acc[k], (u < n) ? w[u] : 0.f, v[u][k]); else add4(acc[k], v[u][k]);
+              }
+            e = end;
+          }
+        } else {
+          if (U > 4 && e + 4 <= end) batch(std::integral_constant<int, (U > 4 ? 4 : 1)>{});
+          if (U > 2 && e + 2 <= end) batch(std::integral_constant<int, (U > 2 ? 2 : 1)>{});
+          if (e < end) batch(std::integral_constant<int, 1>{});
+        }
       }
       if (!W && len > 1) {
         const float c = (float)len;   // s / clamp(cnt, 1): a true division, like the reference

@@ -127,6 +127,194 @@ __global__ void bce_logits_bwd_kernel(const float* __restrict__ x, const float* 
   g_x[i] = (*g_loss) * (s - y[i]) / (float)n;
 }
 
+// ---- fused training-step tail: sampler, and DistMult + BCE-with-logits + accuracy in one pair ----
+__device__ __forceinline__ uint32_t pcg32(uint32_t x) {
+  uint32_t state = x * 747796405u + 2891336453u;
+  uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+  return (word >> 22u) ^ word;
+}
+// two independent 32-bit draws for item i of step `ctr`
+__device__ __forceinline__ uint2 draw2(uint32_t seed, unsigned long long ctr, uint32_t i) {
+  const uint32_t k = pcg32(seed ^ (uint32_t)ctr) + (uint32_t)(ctr >> 32) * 0x9E3779B9u;
+  const uint32_t a = pcg32(i ^ k);
+  return make_uint2(a, pcg32(a + 0x85EBCA6Bu + i));
+}
+
+// Negative sampling of reference src/train.py:59-97 + the concatenation / labels of :281-288 on device: out[0 .. n_pos)
+// = the positives (label 1); out[n_pos + i * num_neg + k] = positive i with its head (probability 1/2) or else its
+// tail replaced by a uniform node (label 0).  One block: every thread reads the step counter, then thread 0 advances
+// it — a captured graph draws fresh negatives on every replay.
+__global__ void __launch_bounds__(1024) link_batch_kernel(const int64_t* __restrict__ ph, const int64_t* __restrict__ pt,
+                                                          const int64_t* __restrict__ pr, int64_t n_pos, int32_t num_neg,
+                                                          int64_t num_nodes, uint32_t seed, unsigned long long* ctr,
+                                                          int64_t* __restrict__ heads, int64_t* __restrict__ tails,
+                                                          int64_t* __restrict__ rels, float* __restrict__ labels) {
+  pdl_enter();
+  const unsigned long long c = *ctr;
+  __syncthreads();
+  if (threadIdx.x == 0) *ctr = c + 1ull;
+  const int64_t n_neg = n_pos * num_neg;
+  for (int64_t i = threadIdx.x; i < n_pos + n_neg; i += 1024) {
+    if (i < n_pos) {
+      heads[i] = ph[i]; tails[i] = pt[i]; rels[i] = pr[i]; labels[i] = 1.f;
+    } else {
+      const int64_t q = (i - n_pos) / num_neg;
+      const uint2 r = draw2(seed, c, (uint32_t)(i - n_pos));
+      const bool corrupt_head = (r.x >> 31) != 0u;
+      // uniform in [0, num_nodes): multiply-shift of a 32-bit draw (bias < num_nodes / 2^32)
+      const int64_t ent = (int64_t)(((unsigned long long)r.y * (unsigned long long)num_nodes) >> 32);
+      heads[i] = corrupt_head ? ent : ph[q];
+      tails[i] = corrupt_head ? pt[q] : ent;
+      rels[i] = pr[q]; labels[i] = 0.f;
+    }
+  }
+}
+
+// keep-mask of the decoder's dropout on the relation row (reference src/models/rgcn.py:207-208): 16 hash bits per
+// element of pair p; returns the four multipliers (0 or 1 / (1 - p)) of float4 number vi of the row
+__device__ __forceinline__ float4 rel_drop4(uint32_t key, int64_t p, int d, int vi, uint32_t thresh, float scale) {
+  const uint32_t e = (uint32_t)(p * d + vi * 4);
+  const uint32_t h0 = pcg32(e ^ key), h1 = pcg32((e + 2u) ^ key);
+  return make_float4((h0 & 0xffffu) >= thresh ? scale : 0.f, (h0 >> 16) >= thresh ? scale : 0.f,
+                     (h1 & 0xffffu) >= thresh ? scale : 0.f, (h1 >> 16) >= thresh ? scale : 0.f);
+}
+
+struct LinkLossParams {
+  const float* emb; int64_t ld;
+  const int64_t* head; const int64_t* tail; const int64_t* rel;
+  const float* rel_table; const float* labels;
+  int64_t n_pairs; int32_t d;
+  uint32_t drop_thresh; float drop_scale; uint32_t seed;     // drop_thresh == 0: no dropout
+  unsigned long long* ctr;           // dropout step counter (forward: read by all, advanced by the last block)
+  unsigned long long* state;         // forward: out, the counter value used; backward: in
+  float* score; float* loss; int32_t* n_correct;
+  float* part_loss; int32_t* part_correct; unsigned int* ticket;   // [gridDim.x], [gridDim.x], [1] (zero before launch)
+};
+
+// scores, mean BCE-with-logits loss and the number of correct sigmoid > 0.5 predictions (src/train.py:300, :321-322)
+// in ONE kernel: a warp per pair, per-block partials, the last block to finish reduces them in block order.
+__global__ void __launch_bounds__(256) link_loss_fwd_kernel(const LinkLossParams q) {
+  pdl_enter();
+  __shared__ float s_l[8];
+  __shared__ int s_c[8];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t p = (int64_t)blockIdx.x * 8 + warp;
+  const unsigned long long c = q.drop_thresh ? *q.ctr : 0ull;
+  const uint32_t key = pcg32(q.seed ^ (uint32_t)c) + (uint32_t)(c >> 32) * 0x9E3779B9u;
+  float l = 0.f;
+  int ok = 0;
+  if (p < q.n_pairs) {
+    const float* h = q.emb + q.head[p] * q.ld;
+    const float* t = q.emb + q.tail[p] * q.ld;
+    const float* r = q.rel_table + q.rel[p] * q.d;
+    float s = 0.f;
+    for (int vi = lane; vi < (q.d >> 2); vi += 32) {
+      const float4 a = ldg4(h + vi * 4), cc = ldg4(t + vi * 4);
+      float4 b = ldg4(r + vi * 4);
+      if (q.drop_thresh) {
+        const float4 m = rel_drop4(key, p, q.d, vi, q.drop_thresh, q.drop_scale);
+        b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w;
+      }
+      s += a.x * b.x * cc.x; s += a.y * b.y * cc.y; s += a.z * b.z * cc.z; s += a.w * b.w * cc.w;
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float y = q.labels[p];
+    l = fmaxf(s, 0.f) - s * y + log1pf(expf(-fabsf(s)));
+    ok = (((s > 0.f) ? 1.f : 0.f) == y) ? 1 : 0;
+    if (lane == 0) q.score[p] = s;
+  }
+  if (lane == 0) { s_l[warp] = l; s_c[warp] = ok; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bl = 0.f; int bc = 0;
+    for (int w = 0; w < 8; ++w) { bl += s_l[w]; bc += s_c[w]; }
+    q.part_loss[blockIdx.x] = bl; q.part_correct[blockIdx.x] = bc;
+    __threadfence();
+    s_last = atomicAdd(q.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last block: every block has read the counter and published its partial
+  __threadfence();
+  float acc = 0.f; int cor = 0;
+  if (threadIdx.x < 32) {
+    // fixed order: lane-strided partials, then a fixed butterfly => same bits on every run
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 32) {
+      acc += *((volatile float*)q.part_loss + b);
+      cor += *((volatile int*)q.part_correct + b);
+    }
+    for (int o = 16; o; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      cor += __shfl_xor_sync(0xffffffffu, cor, o);
+    }
+    if (threadIdx.x == 0) {
+      *q.loss = acc / (float)q.n_pairs;
+      if (q.n_correct) *q.n_correct = cor;
+      *q.ticket = 0u;                               // ready for the next launch (graph replay)
+      if (q.state) *q.state = c;
+      if (q.drop_thresh) *q.ctr = c + 1ull;
+    }
+  }
+}
+
+// g_score[p] = g_loss * (sigmoid(s_p) - y_p) / n folded into the DistMult backward: node-row gradients scattered into
+// the dense [N, d] buffer (zeroed by the caller), relation-table gradient accumulated
+__global__ void __launch_bounds__(256) link_loss_bwd_kernel(const LinkLossParams q, const float* __restrict__ g_loss,
+                                                            float* __restrict__ g_emb, int64_t ld_g,
+                                                            float* __restrict__ g_rel_table, int32_t n_rel_smem) {
+  pdl_enter();
+  // the relation table has few rows that every pair hits: the block's 8 pairs are pre-reduced in shared memory
+  // (n_rel_smem rows, 0 = table too large: straight global atomics) and flushed with one atomic per touched element
+  extern __shared__ float s_tab[];
+  const int lane = threadIdx.x & 31;
+  const int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const bool tab_smem = g_rel_table && n_rel_smem > 0;
+  if (tab_smem) {
+    for (int i = threadIdx.x; i < n_rel_smem * q.d; i += 256) s_tab[i] = 0.f;
+    __syncthreads();
+  }
+  if (p < q.n_pairs) {
+    const unsigned long long c = q.drop_thresh ? *q.state : 0ull;
+    const uint32_t key = pcg32(q.seed ^ (uint32_t)c) + (uint32_t)(c >> 32) * 0x9E3779B9u;
+    const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
+    const float* h = q.emb + hi * q.ld;
+    const float* t = q.emb + ti * q.ld;
+    const float* r = q.rel_table + ri * q.d;
+    const float s = q.score[p];
+    const float g = (*g_loss) * (1.f / (1.f + expf(-s)) - q.labels[p]) / (float)q.n_pairs;
+    for (int vi = lane; vi < (q.d >> 2); vi += 32) {
+      const float4 a = ldg4(h + vi * 4), cc = ldg4(t + vi * 4);
+      float4 b = ldg4(r + vi * 4);
+      float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (q.drop_thresh) {
+        m = rel_drop4(key, p, q.d, vi, q.drop_thresh, q.drop_scale);
+        b.x *= m.x; b.y *= m.y; b.z *= m.z; b.w *= m.w;
+      }
+      const float4 gh = make_float4(g * b.x * cc.x, g * b.y * cc.y, g * b.z * cc.z, g * b.w * cc.w);
+      const float4 gt = make_float4(g * a.x * b.x, g * a.y * b.y, g * a.z * b.z, g * a.w * b.w);
+      atomicAdd(reinterpret_cast<float4*>(g_emb + hi * ld_g + vi * 4), gh);
+      atomicAdd(reinterpret_cast<float4*>(g_emb + ti * ld_g + vi * 4), gt);
+      if (g_rel_table) {
+        const float4 gr = make_float4(g * a.x * cc.x * m.x, g * a.y * cc.y * m.y, g * a.z * cc.z * m.z, g * a.w * cc.w * m.w);
+        if (tab_smem) {
+          float* dst = s_tab + ri * q.d + vi * 4;
+          atomicAdd(dst, gr.x); atomicAdd(dst + 1, gr.y); atomicAdd(dst + 2, gr.z); atomicAdd(dst + 3, gr.w);
+        } else {
+          atomicAdd(reinterpret_cast<float4*>(g_rel_table + ri * q.d + vi * 4), gr);
+        }
+      }
+    }
+  }
+  if (tab_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_rel_smem * (q.d >> 2); i += 256) {
+      const float4 v = *reinterpret_cast<const float4*>(s_tab + i * 4);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(g_rel_table) + i, v);
+    }
+  }
+}
+
 // 1 when any index is out of range
 __global__ void check_pairs_kernel(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,
                                    int64_t n_nodes, int32_t n_rel, int32_t* flag) {
@@ -208,6 +396,83 @@ extern "C" int rgcn_bce_logits_bwd(const float* logits, const float* labels, int
                                    float* g_logits, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(n > 0 && logits && labels && g_loss && g_logits, "bce_logits_bwd: bad arguments");
   RGCN_CUDA(launch_pdl(bce_logits_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, logits, labels, n, g_loss, g_logits));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_link_batch(const int64_t* pos_head, const int64_t* pos_tail, const int64_t* pos_rel, int64_t n_pos,
+                               int32_t num_neg, int64_t num_nodes, uint32_t seed, unsigned long long* counter,
+                               int64_t* heads, int64_t* tails, int64_t* rels, float* labels, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n_pos >= 0 && num_neg >= 0 && num_nodes > 0 && num_nodes < (1ll << 32), "link_batch: bad sizes");
+  RGCN_CHECK_ARG(n_pos == 0 || (pos_head && pos_tail && pos_rel && heads && tails && rels && labels && counter),
+                 "link_batch: null argument");
+  if (n_pos == 0) return RGCN_OK;
+  RGCN_CUDA(launch_pdl(link_batch_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, pos_head, pos_tail, pos_rel, n_pos,
+                       num_neg, num_nodes, seed, counter, heads, tails, rels, labels));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+static int fill_link_params(LinkLossParams& q, const float* emb, int64_t ld, const int64_t* head, const int64_t* tail,
+                            const int64_t* rel, const float* rel_table, const float* labels, int64_t n_pairs, int32_t d,
+                            float dropout_p, uint32_t seed) {
+  RGCN_CHECK_ARG(n_pairs > 0 && d >= 4 && d % 4 == 0, "link_loss: n_pairs must be positive and d a multiple of 4");
+  RGCN_CHECK_ARG(emb && head && tail && rel && rel_table && labels, "link_loss: null argument");
+  RGCN_CHECK_ARG(ld % 4 == 0 && (((uintptr_t)emb | (uintptr_t)rel_table) & 15) == 0, "link_loss: rows must be 16-byte aligned");
+  RGCN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "link_loss: dropout_p must be in [0, 1)");
+  RGCN_CHECK_ARG(n_pairs * (int64_t)d < (1ll << 32), "link_loss: batch too large for the 32-bit dropout index");
+  q.emb = emb; q.ld = ld; q.head = head; q.tail = tail; q.rel = rel; q.rel_table = rel_table; q.labels = labels;
+  q.n_pairs = n_pairs; q.d = d; q.seed = seed;
+  q.drop_thresh = 0; q.drop_scale = 1.f;
+  if (dropout_p > 0.f) {
+    const double th = (double)dropout_p * 65536.0 + 0.5;
+    q.drop_thresh = th < 1.0 ? 1u : (uint32_t)th;
+    q.drop_scale = 1.f / (1.f - dropout_p);
+  }
+  return RGCN_OK;
+}
+
+extern "C" size_t rgcn_link_loss_workspace_bytes(int64_t n_pairs) {
+  const size_t blocks = (size_t)((n_pairs + 7) / 8);
+  return align_up(blocks * 8 + 16, 256);
+}
+
+extern "C" int rgcn_link_loss_fwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
+                                  const float* rel_table, const float* labels, int64_t n_pairs, int32_t d, float dropout_p,
+                                  uint32_t seed, unsigned long long* counter, unsigned long long* state, float* score,
+                                  float* loss, int32_t* n_correct, void* workspace, size_t workspace_bytes,
+                                  rgcn_stream_t stream) {
+  LinkLossParams q{};
+  int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed);
+  if (rc) return rc;
+  RGCN_CHECK_ARG(score && loss, "link_loss_fwd: null outputs");
+  RGCN_CHECK_ARG(dropout_p == 0.f || (counter && state), "link_loss_fwd: dropout needs the counter and a state slot");
+  const size_t blocks = (size_t)((n_pairs + 7) / 8);
+  if (!workspace || workspace_bytes < rgcn_link_loss_workspace_bytes(n_pairs)) {
+    set_error("link_loss_fwd: workspace too small"); return RGCN_EWORKSPACE;
+  }
+  q.ctr = counter; q.state = state; q.score = score; q.loss = loss; q.n_correct = n_correct;
+  q.part_loss = (float*)workspace; q.part_correct = (int32_t*)((char*)workspace + blocks * 4);
+  q.ticket = (unsigned int*)((char*)workspace + blocks * 8);
+  RGCN_CUDA(launch_pdl(link_loss_fwd_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, q));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_link_loss_bwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
+                                  const float* rel_table, const float* labels, const float* score, const float* g_loss,
+                                  int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed, const unsigned long long* state,
+                                  float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, rgcn_stream_t stream) {
+  LinkLossParams q{};
+  int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed);
+  if (rc) return rc;
+  RGCN_CHECK_ARG(score && g_loss && g_emb && ld_g % 4 == 0 && ((uintptr_t)g_emb & 15) == 0, "link_loss_bwd: bad buffers");
+  RGCN_CHECK_ARG(dropout_p == 0.f || state, "link_loss_bwd: dropout needs the state the forward wrote");
+  RGCN_CHECK_ARG(!g_rel_table || ((uintptr_t)g_rel_table & 15) == 0, "link_loss_bwd: g_rel_table misaligned");
+  q.state = const_cast<unsigned long long*>(state); q.score = const_cast<float*>(score);
+  const int32_t n_rel_smem = (g_rel_table && n_rel > 0 && (size_t)n_rel * d * 4 <= 40 * 1024) ? n_rel : 0;
+  RGCN_CUDA(launch_pdl(link_loss_bwd_kernel, dim3((unsigned)((n_pairs + 7) / 8)), dim3(256), (size_t)n_rel_smem * d * 4,
+                       (cudaStream_t)stream, q, g_loss, g_emb, ld_g, g_rel_table, n_rel_smem));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

@@ -20,27 +20,32 @@ struct SideStream {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-SideStream* side_stream() {
+// `create` = false while a capture is in progress: creating streams / events there could invalidate the capture, so the
+// objects are made by the first eager call (GraphedTrainStep warms up eagerly before it captures)
+SideStream* side_stream(bool create) {
   static SideStream ss[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream& f = ss[dev];
-  if (!f.side) {
+  if (!f.join) {
+    if (!create) return nullptr;
     if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
   return &f;
 }
-bool overlap_wgrad(cudaStream_t st) {
+SideStream* overlap_wgrad(cudaStream_t st) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RGCN_OVERLAP_WGRAD");
     v = !e ? 2 : (e[0] == '0' ? 0 : 1);
   }
-  if (v != 2) return v != 0;
+  if (v == 0) return nullptr;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+  const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+  SideStream* ss = side_stream(!capturing);
+  return (v == 1 || capturing) ? ss : nullptr;
 }
 }  // namespace
 
@@ -58,7 +63,7 @@ static int dgrad_walk_wgrad(const rgcn_layer_bwd_args* a, int64_t m, const void*
                               a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
     if (rc) return rc;
   }
-  SideStream* ss = (need_w && a->gA && a->g_x && overlap_wgrad(st)) ? side_stream() : nullptr;
+  SideStream* ss = (need_w && a->gA && a->g_x) ? overlap_wgrad(st) : nullptr;
   cudaStream_t wst = st;
   if (ss) {
     RGCN_CUDA(cudaEventRecord(ss->fork, st));

@@ -27,6 +27,9 @@ class GraphedTrainStep:
         dev = edge_index.device
         self.model, self.edge_index, self.edge_type = model, edge_index, edge_type
         self.loss_fn = loss_fn or bce_with_logits      # fused equivalent of nn.BCEWithLogitsLoss()
+        # default loss + a model that offers it: decoder, loss and accuracy in one kernel pair (model.link_loss)
+        self.fused_loss = loss_fn is None and hasattr(model, "link_loss")
+        self.correct = None
         self.heads = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.tails = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.rels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
@@ -59,8 +62,12 @@ class GraphedTrainStep:
         self._bind_grads()
 
     def _step(self):
-        scores = self.model(self.edge_index, self.edge_type, self.heads, self.tails, self.rels)
-        loss = self.loss_fn(scores, self.labels)
+        if self.fused_loss:
+            loss, scores, self.correct = self.model.link_loss(self.edge_index, self.edge_type, self.heads, self.tails,
+                                                              self.rels, self.labels)
+        else:
+            scores = self.model(self.edge_index, self.edge_type, self.heads, self.tails, self.rels)
+            loss = self.loss_fn(scores, self.labels)
         if self.flat_grad is not None:
             self.flat_grad.zero_()
             loss.backward()

@@ -183,6 +183,28 @@ class LinkPredictor(nn.Module):
         return _ScoreAllTails.apply(head_embeddings, self.relation_embeddings.weight, relation_types,
                                     all_tail_embeddings)
 
+    def _dropout_rng(self, device):
+        """(seed, device counter) of the fused loss's relation dropout; the seed comes from torch's generator on first use."""
+        st = getattr(self, "_drop_rng", None)
+        if st is None or st[1].device != device:
+            st = self._drop_rng = (int(torch.randint(0, 2 ** 31 - 1, (1,)).item()), ops.rng_counter(device))
+        return st
+
+    def link_loss(self, node_embeddings: torch.Tensor, head_indices: torch.Tensor, tail_indices: torch.Tensor,
+                  relation_types: torch.Tensor, labels: torch.Tensor):
+        """(loss, scores, n_correct): ``score_pairs`` + ``BCEWithLogitsLoss`` + the sigmoid > 0.5 accuracy count of the
+        reference's training step (src/train.py:291-300, :321-322) in one kernel pair; both extra outputs are device
+        tensors, so a caller can log them without the two ``.item()`` syncs per step."""
+        _need_cuda(node_embeddings, "LinkPredictor.link_loss")
+        p = self.dropout.p if self.training else 0.0
+        if p >= 1.0:
+            scores = self.score_pairs(node_embeddings, head_indices, tail_indices, relation_types)
+            loss, correct = ops.bce_with_logits(scores, labels, with_accuracy=True)
+            return loss, scores, correct
+        seed, ctr = self._dropout_rng(node_embeddings.device) if p > 0 else (0, None)
+        return ops.link_loss(node_embeddings, self.relation_embeddings.weight, head_indices, tail_indices, relation_types,
+                             labels, p, seed, ctr)
+
     def rank_tails(self, node_embeddings: torch.Tensor, head_indices: torch.Tensor, relation_types: torch.Tensor,
                    tail_indices: torch.Tensor):
         """(rank, ties) of the true tails among all entities — the fused form of ``score_all_tails`` + the per-row
@@ -233,6 +255,12 @@ class DrugDiseaseModel(nn.Module):
     def forward(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:
         node_embeddings = self.encoder(edge_index, edge_type)
         return self.decoder.score_pairs(node_embeddings, head_indices, tail_indices, relation_types)
+
+    def link_loss(self, edge_index, edge_type, head_indices, tail_indices, relation_types, labels):
+        """Encoder + fused decoder / loss / accuracy: the whole of src/train.py:291-300 and :321-322 -> (loss, scores,
+        n_correct), all on the device."""
+        node_embeddings = self.encoder(edge_index, edge_type)
+        return self.decoder.link_loss(node_embeddings, head_indices, tail_indices, relation_types, labels)
 
     def predict(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:
         self.eval()

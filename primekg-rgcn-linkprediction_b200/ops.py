@@ -528,3 +528,101 @@ def bce_with_logits(logits: torch.Tensor, labels: torch.Tensor, with_accuracy: b
         raise ValueError("bce_with_logits expects a 1-D float32 CUDA tensor of logits")
     loss, correct = _BCEWithLogits.apply(logits, labels)
     return (loss, correct) if with_accuracy else loss
+
+
+# ---- fused tail of the training step (reference src/train.py:276-300, :321-322) --------------------
+def rng_counter(device) -> torch.Tensor:
+    """Device-side step counter of a counter-based RNG stream (uint64 stored as int64 [1])."""
+    return torch.zeros(1, dtype=torch.int64, device=device)
+
+
+def link_batch(pos_head: torch.Tensor, pos_tail: torch.Tensor, pos_rel: torch.Tensor, num_nodes: int, num_neg: int,
+               seed: int, counter: torch.Tensor, out=None):
+    """(heads, tails, rels, labels) = positives followed by ``num_neg`` corruptions each (``rgcn_link_batch``).
+    ``out``: four preallocated tensors (e.g. the static buffers of a captured step)."""
+    lib = _lib.load()
+    ph, pt, pr = _idx(pos_head, "pos_head"), _idx(pos_tail, "pos_tail"), _idx(pos_rel, "pos_rel")
+    n = ph.numel()
+    tot = n * (1 + num_neg)
+    dev = ph.device
+    if out is None:
+        out = (torch.empty(tot, dtype=torch.int64, device=dev), torch.empty(tot, dtype=torch.int64, device=dev),
+               torch.empty(tot, dtype=torch.int64, device=dev), torch.empty(tot, dtype=torch.float32, device=dev))
+    h, t, r, y = out
+    if not (h.numel() == t.numel() == r.numel() == y.numel() == tot and h.dtype == t.dtype == r.dtype == torch.int64
+            and y.dtype == torch.float32 and all(x.is_contiguous() for x in out)):
+        raise ValueError("out must be (int64, int64, int64, float32) contiguous tensors of n_pos * (1 + num_neg) entries")
+    _lib.check(lib.rgcn_link_batch(_ptr(ph), _ptr(pt), _ptr(pr), n, int(num_neg), int(num_nodes), int(seed) & 0xFFFFFFFF,
+                                   _ptr(counter), _ptr(h), _ptr(t), _ptr(r), _ptr(y), _stream(dev)), "rgcn_link_batch")
+    return out
+
+
+_LINK_WS = {}
+
+
+def _link_workspace(device, n_pairs: int) -> torch.Tensor:
+    """Zero-initialised partial / ticket buffer of the fused loss kernel (the kernel leaves the ticket at zero)."""
+    key = (str(device), int(n_pairs))      # calls are stream-ordered per device in this package
+    ws = _LINK_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().rgcn_link_loss_workspace_bytes(n_pairs)), dtype=torch.uint8, device=device)
+        _LINK_WS[key] = ws
+    return ws
+
+
+class _LinkLoss(torch.autograd.Function):
+    """(loss, scores, n_correct) = BCEWithLogits(DistMult(emb[head], rel_table[rel] (dropout), emb[tail]), labels)."""
+
+    @staticmethod
+    def forward(ctx, emb, rel_table, head, tail, rel, labels, p_drop, seed, counter):
+        lib = _lib.load()
+        emb = _f32c(emb, "node embeddings")
+        rel_table = _f32c(rel_table, "relation table").contiguous()
+        head, tail, rel = _idx(head, "head"), _idx(tail, "tail"), _idx(rel, "rel")
+        labels = labels.to(torch.float32).contiguous()
+        n, d, dev = head.numel(), emb.size(1), emb.device
+        if rel_table.size(1) != d or not (tail.numel() == rel.numel() == labels.numel() == n):
+            raise ValueError("link_loss: shapes disagree")
+        score = torch.empty(n, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        correct = torch.empty((), dtype=torch.int32, device=dev)
+        state = torch.empty(1, dtype=torch.int64, device=dev) if p_drop > 0 else None
+        ws = _link_workspace(dev, n)
+        _lib.check(lib.rgcn_link_loss_fwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
+                                          _ptr(labels), n, d, float(p_drop), int(seed) & 0xFFFFFFFF,
+                                          _ptr(counter if p_drop > 0 else None), _ptr(state), _ptr(score), _ptr(loss),
+                                          _ptr(correct), _ptr(ws), ws.numel(), _stream(dev)), "rgcn_link_loss_fwd")
+        ctx.save_for_backward(emb, rel_table, head, tail, rel, labels, score, state)
+        ctx.p_drop, ctx.seed = float(p_drop), int(seed)
+        ctx.mark_non_differentiable(score, correct)
+        ctx.set_materialize_grads(False)          # no zero-filled gradients for the two non-differentiable outputs
+        return loss, score, correct
+
+    @staticmethod
+    def backward(ctx, g_loss, _gs, _gc):
+        from . import rowsparse
+        lib = _lib.load()
+        emb, rel_table, head, tail, rel, labels, score, state = ctx.saved_tensors
+        dev = emb.device
+        if g_loss is None:
+            return (None,) * 9
+        g_loss = g_loss.to(torch.float32).contiguous()
+        g_emb = torch.zeros_like(emb, memory_format=torch.contiguous_format)
+        g_tab = torch.zeros_like(rel_table) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.rgcn_link_loss_bwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
+                                          _ptr(labels), _ptr(score), _ptr(g_loss), head.numel(), emb.size(1), ctx.p_drop,
+                                          ctx.seed & 0xFFFFFFFF, _ptr(state), _ptr(g_emb), g_emb.stride(0), _ptr(g_tab),
+                                          rel_table.size(0), _stream(dev)), "rgcn_link_loss_bwd")
+        if not ctx.needs_input_grad[0]:
+            return None, g_tab, None, None, None, None, None, None, None
+        rowsparse.announce(g_emb, torch.cat([head, tail]))     # zero outside the head / tail rows
+        return g_emb, g_tab, None, None, None, None, None, None, None
+
+
+def link_loss(emb, rel_table, head, tail, rel, labels, p_drop: float = 0.0, seed: int = 0, counter=None):
+    """Fused decoder + loss of the training step; returns (loss, scores, n_correct)."""
+    if not emb.is_cuda:
+        raise RuntimeError("link_loss needs CUDA tensors: there is no CPU implementation of this path")
+    if p_drop > 0 and counter is None:
+        raise ValueError("link_loss: dropout needs a device counter (ops.rng_counter)")
+    return _LinkLoss.apply(emb, rel_table, head, tail, rel, labels, float(p_drop), int(seed), counter)

@@ -916,3 +916,114 @@ def test_sparse_backward_full_size_cfg2(pkg, cfg2, monkeypatch):
     for k in res[False]:
         rel = float((res[True][k] - res[False][k]).norm() / (res[False][k].norm() + 1e-30))
         assert rel < 1e-5, f"{k}: relative Frobenius difference {rel:.3e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# fused tail of the training step: sampler, decoder + loss + accuracy in one kernel pair
+def test_link_loss_matches_unfused_step(pkg):
+    """model.link_loss == model(...) -> BCEWithLogitsLoss -> sigmoid > 0.5 accuracy (reference src/train.py:291-300,
+    :321-322) and the oracle's goldens; gradients equal those of the unfused step."""
+    g = load_golden("small_full")
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    b = [g[k].to(DEV) for k in ("heads", "tails", "rels", "labels")]
+    m = _product_model(pkg, g)
+    m.train()
+    s0 = m(ei, et, b[0], b[1], b[2])
+    l0 = F.binary_cross_entropy_with_logits(s0, b[3])
+    l0.backward()
+    want = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad()
+    loss, scores, correct = m.link_loss(ei, et, *b)
+    loss.backward()
+    torch.testing.assert_close(scores, s0.detach(), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(loss.detach(), l0.detach(), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(loss.detach().cpu(), g["loss"], rtol=1e-4, atol=1e-5)
+    assert int(correct) == int(((torch.sigmoid(s0) > 0.5).float() == b[3]).sum())
+    for k, p in m.named_parameters():
+        _close_by_scale(p.grad, want[k], k, rtol=1e-4, atol=1e-5)
+    # deterministic loss: the block partials are reduced in a fixed order
+    l2, _, _ = m.link_loss(ei, et, *b)
+    assert torch.equal(l2.detach(), loss.detach())
+
+
+def test_link_loss_dropout_mask_is_shared_by_forward_and_backward(pkg):
+    """Relation dropout of reference src/models/rgcn.py:207-208 by counter-based mask.  With all-ones embeddings and
+    relation table, score[p] = (kept elements of pair p) / (1 - p): the keep rate is read off the scores, and
+    sum_k dL/dtable[r, k] = sum_{p: rel = r} g_p * score_p holds only if the backward regenerates the same mask."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    n, d, R, N, p = 4096, 256, 3, 500, 0.25
+    gen = torch.Generator().manual_seed(3)
+    emb = torch.ones(N, d, device=DEV, requires_grad=True)
+    table = torch.ones(R, d, device=DEV, requires_grad=True)
+    h = torch.randint(0, N, (n,), generator=gen).to(DEV)
+    t = torch.randint(0, N, (n,), generator=gen).to(DEV)
+    r = torch.randint(0, R, (n,), generator=gen).to(DEV)
+    y = (torch.rand(n, generator=gen) < 0.5).float().to(DEV)
+    ctr = ops.rng_counter(DEV)
+    loss, s, _ = ops.link_loss(emb, table, h, t, r, y, p, 1234, ctr)
+    assert int(ctr) == 1
+    kept = s * (1 - p) / d
+    assert abs(float(kept.mean()) - (1 - p)) < 0.01 and float(kept.std()) > 0.0
+    assert float((s * (1 - p) - (s * (1 - p)).round()).abs().max()) < 1e-2    # each element is 0 or 1 / (1 - p)
+    loss.backward()
+    g = (torch.sigmoid(s) - y) / n
+    want = torch.zeros(R, device=DEV).index_add_(0, r, g * s)
+    torch.testing.assert_close(table.grad.sum(1), want, rtol=1e-4, atol=1e-6)
+    # next call: counter advanced => another mask
+    _, s2, _ = ops.link_loss(emb, table, h, t, r, y, p, 1234, ctr)
+    assert int(ctr) == 2 and not torch.equal(s2, s)
+    # no dropout: plain DistMult
+    _, s3, _ = ops.link_loss(emb, table, h, t, r, y, 0.0, 0, None)
+    assert torch.equal(s3, torch.full_like(s3, float(d)))
+
+
+def test_negative_sampler_properties(pkg):
+    """Device-side NegativeSampler (reference src/train.py:59-97, :281-288): layout, labels, exactly-one-end corruption,
+    range, rates; fresh draws per call and per CUDA-graph replay."""
+    N, n, k = 30926, 1024, 3
+    gen = torch.Generator().manual_seed(9)
+    ph = torch.randint(0, N, (n,), generator=gen).to(DEV)
+    pt = torch.randint(0, N, (n,), generator=gen).to(DEV)
+    pr = torch.randint(0, 3, (n,), generator=gen).to(DEV)
+    torch.manual_seed(0)
+    smp = pkg.NegativeSampler(N, k)
+    H, T, Rr, Y = smp.batch(ph, pt, pr)
+    assert H.numel() == n * (1 + k) and torch.equal(H[:n], ph) and torch.equal(T[:n], pt) and torch.equal(Rr[:n], pr)
+    assert torch.equal(Y, torch.cat([torch.ones(n), torch.zeros(n * k)]).to(DEV))
+    rh, rt = ph.repeat_interleave(k), pt.repeat_interleave(k)
+    assert torch.equal(Rr[n:], pr.repeat_interleave(k))
+    keep_h, keep_t = H[n:] == rh, T[n:] == rt
+    assert bool((keep_h | keep_t).all())                               # never both ends replaced
+    assert int(H.min()) >= 0 and int(H.max()) < N and int(T.min()) >= 0 and int(T.max()) < N
+    frac_head = float((~keep_h).float().mean())
+    assert 0.45 < frac_head < 0.55
+    ent = torch.where(~keep_h, H[n:], T[n:]).double()
+    assert abs(float(ent.mean()) / N - 0.5) < 0.03 and float(ent.std()) / N > 0.25
+    nh, nt, nr = smp.sample(ph, pt, pr)                                # reference interface, next counter value
+    assert nh.numel() == n * k and not torch.equal(nh, H[n:])
+    # graph replay draws fresh negatives
+    out = tuple(torch.empty_like(x) for x in (H, T, Rr, Y))
+    smp.batch(ph, pt, pr, out=out)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            smp.batch(ph, pt, pr, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    gr.replay(); a = out[0].clone()
+    gr.replay(); b2 = out[0].clone()
+    assert not torch.equal(a, b2)
+
+
+def test_graphed_step_uses_fused_loss_and_reports_accuracy(pkg):
+    g = load_golden("small_full")
+    m = _product_model(pkg, g)
+    m.train()
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    b = [g[k].to(DEV) for k in ("heads", "tails", "rels", "labels")]
+    step = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel())
+    assert step.fused_loss
+    loss = step(*b)
+    torch.testing.assert_close(loss.cpu(), g["loss"], rtol=1e-4, atol=1e-5)
+    assert int(step.correct) == int(((g["scores"] > 0).float() == g["labels"]).sum())
