@@ -162,9 +162,20 @@ int rgcn_reduce_partials(const float* part, int64_t n_part, int32_t n_cols, floa
  *   gX[j, :] = init[j, :] + sum_r sum_{e in seg_t(j, r)} w_t[e] * gH[row_t[e], r*d : (r+1)*d]
  * `init` (may be NULL) carries the root/self-loop term gO @ root^T.
  * ------------------------------------------------------------------------------------------ */
+/* Optional second output of the backward walk: gX once more, masked for the layer UPSTREAM of this one —
+ * v = mask > 0 ? gX * scale : 0, mask = that layer's ReLU / dropout output (src/models/rgcn.py:124-125), scale its
+ * 1 / (1 - p) — written as the bf16 operand planes (hi [, lo]) its backward GEMMs read, with the per-block column sums of
+ * v (its bias gradient, [rgcn_aggregate_row_blocks(gt, d), d]).  Replaces that layer's rgcn_split_planes pass. */
+typedef struct rgcn_masked_planes_out {
+  const float* mask; int64_t ld_mask; float scale;
+  void* hi; void* lo; int64_t ldp;          /* lo == NULL: hi plane only (bf16 mode) */
+  float* colsum_partial;                    /* nullable */
+} rgcn_masked_planes_out;
+int64_t rgcn_aggregate_row_blocks(const rgcn_csr_t* g, int32_t d);
+
 int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
                        const float* init, int64_t ld_init,
-                       float* gX, int64_t ldgx,
+                       float* gX, int64_t ldgx, const rgcn_masked_planes_out* masked_planes,
                        void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 /* Same walk over a ROW-SPARSE gH: gH_rows holds only the listed rows (see rgcn_rows_compact), slot[i] is the compact
  * row of node i or zero_row (an all-zero row of gH_rows / init_rows) for every other node; init_rows is indexed through
@@ -172,7 +183,7 @@ int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32
  * rgcn_aggregate_bwd on the dense matrix bit for bit. */
 int rgcn_aggregate_bwd_rows(const rgcn_csr_t* gt, const float* gH_rows, int64_t ldg, int32_t d,
                             const int32_t* slot, int32_t zero_row, const float* init_rows, int64_t ld_init,
-                            float* gX, int64_t ldgx,
+                            float* gX, int64_t ldgx, const rgcn_masked_planes_out* masked_planes,
                             void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -271,6 +282,12 @@ typedef struct rgcn_layer_bwd_args {
   const int64_t* rows; int64_t n_list;      /* device list of node ids, duplicates allowed                    */
   int32_t* slot;                            /* scratch [n_dst]                                                */
   void* Ac_hi; void* Ac_lo; int64_t ldac;   /* scratch planes [m_c, (R+1) d_in] (weight gradient wanted)      */
+  /* Cross-layer hand-over of the masked output gradient (both optional):
+   * next_G   : the walk also writes g_x masked for the upstream layer as that layer's G planes (see above);
+   * g_ready  : G_hi / G_lo / colsum_partial (n_colsum_ready rows) ALREADY hold this layer's masked output gradient —
+   *            written by the downstream layer's next_G — so the rgcn_split_planes pass over g_out is skipped. */
+  const rgcn_masked_planes_out* next_G;
+  int32_t g_ready; int32_t n_colsum_ready;
 } rgcn_layer_bwd_args;
 
 /* Compaction step of the row-sparse backward (csrc/rowsparse.cu), also callable on its own:

@@ -43,6 +43,11 @@ class LayerFwdArgs(C.Structure):
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz)]
 
 
+class MaskedPlanesOut(C.Structure):
+    """Mirror of ``rgcn_masked_planes_out`` (include/rgcn_b200.h)."""
+    _fields_ = [("mask", p), ("ld_mask", i64), ("scale", f32), ("hi", p), ("lo", p), ("ldp", i64), ("colsum_partial", p)]
+
+
 class LayerBwdArgs(C.Structure):
     """Mirror of ``rgcn_layer_bwd_args`` (include/rgcn_b200.h)."""
     _fields_ = [("csr_t", PCSR), ("g_out", p), ("ld_g_out", i64), ("relu_mask", p), ("ld_mask", i64), ("mask_scale", f32),
@@ -51,7 +56,8 @@ class LayerBwdArgs(C.Structure):
                 ("G_hi", p), ("G_lo", p), ("ldg", i64), ("colsum_partial", p), ("gA", p), ("ld_gA", i64),
                 ("g_x", p), ("ld_g_x", i64), ("g_weight", p), ("g_root", p), ("g_bias", p),
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
-                ("rows", p), ("n_list", i64), ("slot", p), ("Ac_hi", p), ("Ac_lo", p), ("ldac", i64)]
+                ("rows", p), ("n_list", i64), ("slot", p), ("Ac_hi", p), ("Ac_lo", p), ("ldac", i64),
+                ("next_G", C.POINTER(MaskedPlanesOut)), ("g_ready", i32), ("n_colsum_ready", i32)]
 
 # name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
 PROTOTYPES = {
@@ -68,8 +74,9 @@ PROTOTYPES = {
     "rgcn_aggregate_blocks": (i64, [PCSR, i32]),
     "rgcn_aggregate_fwd": (C.c_int, [PCSR, p, i64, i32, p, i32, p, p, i64, i32, p, i64, p, p, i64, p, sz, p]),
     "rgcn_reduce_partials": (C.c_int, [p, i64, i32, p, p]),
-    "rgcn_aggregate_bwd": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, p, sz, p]),
-    "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, p, sz, p]),
+    "rgcn_aggregate_bwd": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
+    "rgcn_aggregate_row_blocks": (i64, [PCSR, i32]),
+    "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
     "rgcn_rows_compact_size": (i64, [i64]),
     "rgcn_rows_compact_blocks": (i64, [i64]),
     "rgcn_rows_compact": (C.c_int, [p, i64, i64, p, p, i64, i32, p, p, i64, p, p, i64, i32, p, p, i64, p, p, i32, p]),

@@ -44,7 +44,7 @@ class _RGCNLayerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x_src, x_root, W, root, bias, graph: RelGraph, relu: bool, mode: str, drop=None):
+    def forward(ctx, x_src, x_root, W, root, bias, graph: RelGraph, relu: bool, mode: str, drop=None, in_mask_scale=None):
         """x_src [n_src, d_in]: rows the edges gather from; x_root [n_dst, d_in]: the rows being updated (self-loop
         term).  On one GPU they are the same tensor; on a destination-range shard x_src is the all-gathered matrix."""
         R, d_in, d_out = W.shape
@@ -57,12 +57,15 @@ class _RGCNLayerFn(torch.autograd.Function):
         p_drop, seed, ctr = drop if drop is not None else (0.0, 0, None)
         out, A = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr)
         ctx.graph, ctx.relu, ctx.mode, ctx.shared, ctx.p_drop = graph, relu, mode, shared, p_drop
-        ctx.save_for_backward(A[0], A[1], W, root, out if relu else None)
+        # in_mask_scale: x is the fused ReLU (+ dropout) output of the layer upstream, whose backward will want this
+        # layer's input gradient masked by x > 0 and scaled — the backward walk can write that directly (rowsparse.py)
+        ctx.in_mask_scale = in_mask_scale if (shared and in_mask_scale is not None) else None
+        ctx.save_for_backward(A[0], A[1], W, root, out if relu else None, x_src if ctx.in_mask_scale is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, gO):
-        A_hi, A_lo, W, root, out = ctx.saved_tensors
+        A_hi, A_lo, W, root, out, x_in = ctx.saved_tensors
         graph, mode = ctx.graph, ctx.mode
         R, d_in, d_out = W.shape
         K1 = R * d_in
@@ -74,9 +77,17 @@ class _RGCNLayerFn(torch.autograd.Function):
         if out is None and ctx.shared and graph.n_src == graph.n_dst:
             rows = rowsparse.claim(gO)
         # out is zero exactly where ReLU or the fused dropout killed the element: one mask serves both
-        gx, gA, gWf, groot, gb = ops.layer_bwd(
-            graph, gO.contiguous(), out, 1.0 / (1.0 - ctx.p_drop), (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
-            need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any, rows=rows)
+        mask_scale = 1.0 / (1.0 - ctx.p_drop)
+        # the downstream layer's walk may have left this layer's masked output gradient as planes already
+        g_ready = rowsparse.claim_planes(gO, out, mask_scale, mode) if (out is not None and rows is None) else None
+        next_mask = (x_in, ctx.in_mask_scale) if (x_in is not None and need_x and rowsparse.planes_enabled()) else None
+        res = ops.layer_bwd(
+            graph, gO.contiguous(), out, mask_scale, (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
+            need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any, rows=rows, g_ready=g_ready,
+            next_mask=next_mask)
+        gx, gA, gWf, groot, gb = res[:5]
+        if next_mask is not None:
+            rowsparse.announce_planes(gx, x_in, ctx.in_mask_scale, mode, res[5])
         gx_src = gx_root = None
         if need_x:
             if ctx.shared:
@@ -85,7 +96,7 @@ class _RGCNLayerFn(torch.autograd.Function):
                 gx_src = gx if need_src else None             # full-length partial, reduced by the caller
                 gx_root = gA[:, K1:]
         gW = gWf.view(R, d_in, d_out) if gWf is not None else None
-        return gx_src, gx_root, gW, groot, gb, None, None, None, None
+        return gx_src, gx_root, gW, groot, gb, None, None, None, None, None
 
 
 class _RGCNBasisLayerFn(torch.autograd.Function):
@@ -210,8 +221,10 @@ class RGCNConv(nn.Module):
             ctr = self._drop_ctr = ops.dropout_counter(device)
         return (float(p), self._drop_seed, ctr)
 
-    def forward_graph(self, x: torch.Tensor, graph: RelGraph, relu: bool = False, dropout_p: float = 0.0) -> torch.Tensor:
-        """``dropout_p`` > 0 (training): ReLU and dropout are applied in the transform's epilogue (needs relu=True)."""
+    def forward_graph(self, x: torch.Tensor, graph: RelGraph, relu: bool = False, dropout_p: float = 0.0,
+                      in_mask_scale: Optional[float] = None) -> torch.Tensor:
+        """``dropout_p`` > 0 (training): ReLU and dropout are applied in the transform's epilogue (needs relu=True).
+        ``in_mask_scale``: ``x`` is the fused ReLU / dropout output of the previous layer (whose 1 / (1 - p) this is)."""
         if x.dim() != 2 or x.size(1) != self.in_channels:
             raise ValueError(f"x must be [N, {self.in_channels}]")
         if graph.R != self.num_relations:
@@ -223,7 +236,7 @@ class RGCNConv(nn.Module):
             return _RGCNBasisLayerFn.apply(x, self.weight, self.comp, self.root, self.bias, graph, relu,
                                            self.mode or default_mode(), drop)
         return _RGCNLayerFn.apply(x, x, self.relation_weights(), self.root, self.bias, graph, relu,
-                                  self.mode or default_mode(), drop)
+                                  self.mode or default_mode(), drop, in_mask_scale)
 
     def _use_z_form(self, graph: RelGraph) -> bool:
         """B-accumulator form of the basis decomposition (``PRIMEKG_RGCN_BASIS_FORM=z``).  It halves the layer's

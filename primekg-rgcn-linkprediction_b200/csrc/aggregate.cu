@@ -69,6 +69,12 @@ struct AggParams {
   // zeros, the result equals the dense walk bit for bit.
   const int32_t* slot;       // nullable, [number of gatherable nodes]
   int32_t zero_row;
+  // MIX_SUM second output (nullable): the result masked for the layer UPSTREAM — v = (mask > 0 ? O * mp_scale : 0) with
+  // mask = that layer's ReLU / dropout output — written as the bf16 operand planes its backward GEMMs read, plus the
+  // per-block column sums (its bias gradient).  Saves the separate conversion pass over O.
+  const float* mp_mask; int64_t ld_mp_mask; float mp_scale;
+  void* mp_hi; void* mp_lo; int64_t ld_mp;
+  float* mp_colsum;          // nullable, [gridDim.x, d]
 };
 
 // ---- hub chunks: one block per chunk --------------------------------------------------------
@@ -153,9 +159,10 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
   }
 }
 
-__device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int col, const float4& v) {
-  if (p.out_mode == 0) {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.O) + row * p.ldo + col) = v;
+__device__ __forceinline__ void store_vec_to(void* O, void* O_lo, int64_t ldo, int out_mode, int64_t row, int col,
+                                             const float4& v) {
+  if (out_mode == 0) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(O) + row * ldo + col) = v;
     return;
   }
   // packed conversions (F2FP); the bf16 planes are the TMA-loadable operand format of the tensor-core kernels
@@ -163,8 +170,8 @@ __device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int c
   uint2 hi;
   hi.x = *reinterpret_cast<uint32_t*>(&a);
   hi.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.O) + row * p.ldo + col) = hi;
-  if (p.out_mode == 2) {
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(O) + row * ldo + col) = hi;
+  if (out_mode == 2) {
     const float hx = __uint_as_float(hi.x << 16), hy = __uint_as_float(hi.x & 0xffff0000u);
     const float hz = __uint_as_float(hi.y << 16), hw = __uint_as_float(hi.y & 0xffff0000u);
     a = __floats2bfloat162_rn(v.x - hx, v.y - hy);
@@ -172,8 +179,11 @@ __device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int c
     uint2 lo;
     lo.x = *reinterpret_cast<uint32_t*>(&a);
     lo.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.O_lo) + row * p.ldo + col) = lo;
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(O_lo) + row * ldo + col) = lo;
   }
+}
+__device__ __forceinline__ void store_vec(const AggParams& p, int64_t row, int col, const float4& v) {
+  store_vec_to(p.O, p.O_lo, p.ldo, p.out_mode, row, col, v);
 }
 
 // ---- rows: one G-lane group per row ----------------------------------------------------------
@@ -189,8 +199,10 @@ constexpr int agg_min_blocks(int G, int vpl, int mix, bool w) {
   return (mix == MIX_SUM && w) ? 3 : 4;                           // d <= 64
 }
 
-template <int G, int VPL, int MIX, bool W, bool SLOT = false>
-__global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate_rows_kernel(const AggParams p) {
+// MP: the masked-planes second output (MIX_SUM only) is compiled in; one resident block less buys it the registers
+template <int G, int VPL, int MIX, bool W, bool SLOT = false, bool MP = false>
+__global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W) - ((MP && agg_min_blocks(G, VPL, MIX, W) > 1) ? 1 : 0))
+aggregate_rows_kernel(const AggParams p) {
   pdl_enter();
   constexpr int GROUPS = 256 / G;
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
@@ -202,6 +214,7 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
   constexpr bool TAILPRED = MIX != MIX_BASIS && VPL <= RGCN_TAILPRED_MAX_VPL;
   extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS, then [GROUPS][R * B] coefficient-gradient sums
   const bool with_gc = MIX == MIX_BASIS && p.dotP != nullptr;
+  const bool with_cs = MP && MIX == MIX_SUM && p.mp_colsum != nullptr;       // s_comp then holds [GROUPS][d] column-sum rows
   float* s_gc = s_comp + p.R * p.B;
   if (MIX == MIX_BASIS) {
     for (int t = threadIdx.x; t < p.R * p.B; t += 256) s_comp[t] = p.comp[(t / p.B) * p.ldcomp + (t % p.B)];
@@ -213,7 +226,9 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   int64_t row = (int64_t)blockIdx.x * GROUPS + grp;
   if (row >= p.n_rows) {
-    if (!with_gc) return;
+    if (!with_gc && !with_cs) return;
+    if (with_cs)
+      for (int t = lane; t < p.d; t += G) s_comp[grp * p.d + t] = 0.f;
   } else {
   // longest rows first: neighbouring groups get rows of similar length and the long walks start at time zero
   if (p.row_order) row = __ldg(p.row_order + row);
@@ -465,8 +480,33 @@ __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W)) aggregate
           if (act[k]) store_vec(p, row, b * p.block_stride + vcol[k], mix[b][k]);
       }
     }
+    if (MP && MIX == MIX_SUM && p.mp_hi) {
+      // the same row once more, masked and scaled, as the upstream layer's G planes (+ column sums)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (act[k]) {
+          const float4 m = ldg4(p.mp_mask + row * p.ld_mp_mask + vcol[k]);
+          float4 v = scale4(mix[0][k], p.mp_scale);
+          if (!(m.x > 0.f)) v.x = 0.f;
+          if (!(m.y > 0.f)) v.y = 0.f;
+          if (!(m.z > 0.f)) v.z = 0.f;
+          if (!(m.w > 0.f)) v.w = 0.f;
+          store_vec_to(p.mp_hi, p.mp_lo, p.ld_mp, p.mp_lo ? 2 : 1, row, vcol[k], v);
+          if (with_cs) *reinterpret_cast<float4*>(s_comp + grp * d + vcol[k]) = v;
+        }
+      }
+    }
   }
   }  // row < n_rows
+  if (with_cs) {
+    // the block's column sums = its groups' rows in group order (deterministic)
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.d; t += 256) {
+      float sum = s_comp[t];
+      for (int g = 1; g < GROUPS; ++g) sum += s_comp[g * p.d + t];
+      p.mp_colsum[(size_t)blockIdx.x * p.d + t] = sum;
+    }
+  }
   if (with_gc) {
     // the block's partial = its groups' sums in group order (deterministic)
     __syncthreads();
@@ -606,7 +646,7 @@ static int launch_agg_overlapped(AggParams p, int n_chunks, cudaStream_t st) {
 template <int G, int VPL>
 static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
-  if (!p.slot && n_chunks > 0 && p.n_rows > 0 && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
+  if (!p.slot && !p.mp_hi && n_chunks > 0 && p.n_rows > 0 && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
     const bool w = p.edge_w != nullptr;
     if (mix == MIX_NONE)
       return w ? launch_agg_overlapped<G, VPL, MIX_NONE, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_NONE, false>(p, n_chunks, st);
@@ -620,8 +660,10 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
       RGCN_LAUNCH_CHECK();
     }
     if (p.n_rows == 0) return RGCN_OK;
-    RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true>, dim3((unsigned)((p.n_rows + GROUPS - 1) / GROUPS)),
-                         dim3(256), 0, st, p));
+    const dim3 sgrid((unsigned)((p.n_rows + GROUPS - 1) / GROUPS));
+    if (p.mp_hi) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true, true>, sgrid, dim3(256),
+                                      p.mp_colsum ? (size_t)GROUPS * p.d * sizeof(float) : 0, st, p));
+    else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true>, sgrid, dim3(256), 0, st, p));
     RGCN_LAUNCH_CHECK();
     return RGCN_OK;
   }
@@ -638,7 +680,11 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
     if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, true>, dim3(grid), dim3(256), 0, st, p));
     else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, false>, dim3(grid), dim3(256), 0, st, p));
   } else if (mix == MIX_SUM) {
-    if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true>, dim3(grid), dim3(256), 0, st, p));
+    if (p.mp_hi) {
+      if (!w) { set_error("aggregate: the masked-planes output serves the weighted (backward) walk"); return RGCN_EINVAL; }
+      RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, false, true>, dim3(grid), dim3(256),
+                           p.mp_colsum ? (size_t)GROUPS * p.d * sizeof(float) : 0, st, p));
+    } else if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true>, dim3(grid), dim3(256), 0, st, p));
     else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, false>, dim3(grid), dim3(256), 0, st, p));
   } else {
     if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_BASIS, true>, dim3(grid), dim3(256), sm, st, p));
@@ -759,27 +805,38 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
 
 static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,
                               int32_t zero_row, const float* init, int64_t ld_init, float* gX, int64_t ldgx,
-                              void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+                              const rgcn_masked_planes_out* mp, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
+// grid of the (unmixed / summed) row walk = rows of the column-sum partials of rgcn_masked_planes_out
+extern "C" int64_t rgcn_aggregate_row_blocks(const rgcn_csr_t* g, int32_t d) {
+  if (!g || d < 4) return 0;
+  return agg_blocks(g->n_rows, d);
+}
 
 extern "C" int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
                                   const float* init, int64_t ld_init, float* gX, int64_t ldgx,
+                                  const rgcn_masked_planes_out* mp,
                                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
-  return aggregate_bwd_impl(gt, gH, ldg, d, nullptr, 0, init, ld_init, gX, ldgx, workspace, workspace_bytes, stream);
+  return aggregate_bwd_impl(gt, gH, ldg, d, nullptr, 0, init, ld_init, gX, ldgx, mp, workspace, workspace_bytes, stream);
 }
 
 extern "C" int rgcn_aggregate_bwd_rows(const rgcn_csr_t* gt, const float* gH_rows, int64_t ldg, int32_t d,
                                        const int32_t* slot, int32_t zero_row, const float* init_rows, int64_t ld_init,
-                                       float* gX, int64_t ldgx, void* workspace, size_t workspace_bytes,
-                                       rgcn_stream_t stream) {
+                                       float* gX, int64_t ldgx, const rgcn_masked_planes_out* mp,
+                                       void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(slot && zero_row >= 0, "aggregate_bwd_rows: slot map and zero row are required");
-  return aggregate_bwd_impl(gt, gH_rows, ldg, d, slot, zero_row, init_rows, ld_init, gX, ldgx, workspace, workspace_bytes, stream);
+  return aggregate_bwd_impl(gt, gH_rows, ldg, d, slot, zero_row, init_rows, ld_init, gX, ldgx, mp, workspace, workspace_bytes, stream);
 }
 
 static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,
                               int32_t zero_row, const float* init, int64_t ld_init, float* gX, int64_t ldgx,
-                              void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+                              const rgcn_masked_planes_out* mp, void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
   int rc = check_common(gt, gH, ldg, d, workspace, workspace_bytes);
   if (rc) return rc;
+  RGCN_CHECK_ARG(!mp || (mp->mask && mp->hi && ((uintptr_t)mp->mask & 15) == 0 && mp->ld_mask % 4 == 0 &&
+                         ((uintptr_t)mp->hi & 7) == 0 && (!mp->lo || ((uintptr_t)mp->lo & 7) == 0) && mp->ldp % 4 == 0 &&
+                         (!mp->colsum_partial || ((uintptr_t)mp->colsum_partial & 15) == 0)),
+                 "aggregate_bwd: masked-planes output needs a 16-byte aligned mask and 8-byte aligned planes");
   RGCN_CHECK_ARG(gX && ((uintptr_t)gX & 15) == 0 && ldgx % 4 == 0, "aggregate_bwd: output must be 16-byte aligned with ld %% 4 == 0");
   RGCN_CHECK_ARG(!init || (((uintptr_t)init & 15) == 0 && ld_init % 4 == 0), "aggregate_bwd: init must be 16-byte aligned with ld %% 4 == 0");
   RGCN_CHECK_ARG(gt->w || gt->E == 0, "aggregate_bwd: the transposed CSR needs per-edge weights w_t");
@@ -792,5 +849,9 @@ static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg
   p.init = init; p.ld_init = ld_init; p.B = 1;
   p.O = gX; p.ldo = ldgx; p.out_mode = 0; p.partials = (float*)workspace;
   p.slot = slot; p.zero_row = zero_row;
+  if (mp) {
+    p.mp_mask = mp->mask; p.ld_mp_mask = mp->ld_mask; p.mp_scale = mp->scale;
+    p.mp_hi = mp->hi; p.mp_lo = mp->lo; p.ld_mp = mp->ldp; p.mp_colsum = mp->colsum_partial;
+  }
   return dispatch_agg(p, MIX_SUM, gt->n_chunks, (cudaStream_t)stream);
 }

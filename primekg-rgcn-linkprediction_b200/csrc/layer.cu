@@ -109,7 +109,7 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
   const bool need_w = a->g_weight != nullptr;
   const int64_t m_c = rgcn_rows_compact_size(a->n_list);
   RGCN_CHECK_ARG(a->n_list > 0 && a->slot, "layer_bwd: the row-sparse form needs a row list and the slot scratch");
-  RGCN_CHECK_ARG(!a->relu_mask, "layer_bwd: the row-sparse form serves a layer without ReLU (the last one)");
+  RGCN_CHECK_ARG(!a->relu_mask && !a->g_ready, "layer_bwd: the row-sparse form serves a layer without ReLU (the last one)");
   RGCN_CHECK_ARG(!a->gA || a->add_root_term || !a->g_x, "layer_bwd: the row-sparse form is the one-GPU form (root term added)");
   RGCN_CHECK_ARG(!need_w || (a->Ac_hi && (a->mode == 1 || a->Ac_lo)), "layer_bwd: compact operand planes missing");
   int rc = rgcn_rows_compact(a->rows, a->n_list, a->n_dst, a->slot, a->g_out, a->ld_g_out, a->d_out, a->G_hi,
@@ -120,7 +120,7 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
   if (rc) return rc;
   return dgrad_walk_wgrad(a, m_c, a->Ac_hi, a->Ac_lo, a->ldac, (int32_t)rgcn_rows_compact_blocks(a->n_list), [&]() {
     return rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c, a->gA + K1, a->ld_gA, a->g_x,
-                                   a->ld_g_x, a->agg_workspace, a->agg_workspace_bytes, stream);
+                                   a->ld_g_x, a->next_G, a->agg_workspace, a->agg_workspace_bytes, stream);
   }, stream);
 }
 
@@ -134,13 +134,18 @@ extern "C" int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream
   RGCN_CHECK_ARG(!need_w || (a->g_root && a->A_hi && (a->mode == 1 || a->A_lo)), "layer_bwd: weight gradient needs g_root and the saved planes");
   RGCN_CHECK_ARG(!a->g_bias || (need_w && a->colsum_partial), "layer_bwd: g_bias needs the weight gradient and colsum_partial");
   if (a->rows) return layer_bwd_rows(a, stream);
-  // G = g_out * [mask > 0] * mask_scale as planes, column sums = bias gradient
-  int rc = rgcn_split_planes(a->g_out, a->ld_g_out, a->relu_mask, a->ld_mask, a->n_dst, a->d_out, a->G_hi,
-                             a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->g_bias ? a->colsum_partial : nullptr,
-                             a->mask_scale, nullptr, 0, stream);
-  if (rc) return rc;
-  return dgrad_walk_wgrad(a, a->n_dst, a->A_hi, a->A_lo, a->lda, (int32_t)rgcn_split_planes_blocks(a->n_dst, a->d_out), [&]() {
+  // G = g_out * [mask > 0] * mask_scale as planes, column sums = bias gradient — unless the downstream layer's walk
+  // has written them already (g_ready)
+  int32_t n_colsum = a->n_colsum_ready;
+  if (!a->g_ready) {
+    int rc = rgcn_split_planes(a->g_out, a->ld_g_out, a->relu_mask, a->ld_mask, a->n_dst, a->d_out, a->G_hi,
+                               a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->g_bias ? a->colsum_partial : nullptr,
+                               a->mask_scale, nullptr, 0, stream);
+    if (rc) return rc;
+    n_colsum = (int32_t)rgcn_split_planes_blocks(a->n_dst, a->d_out);
+  }
+  return dgrad_walk_wgrad(a, a->n_dst, a->A_hi, a->A_lo, a->lda, n_colsum, [&]() {
     return rgcn_aggregate_bwd(a->csr_t, a->gA, a->ld_gA, a->d_in, a->add_root_term ? a->gA + K1 : nullptr, a->ld_gA, a->g_x,
-                              a->ld_g_x, a->agg_workspace, a->agg_workspace_bytes, stream);
+                              a->ld_g_x, a->next_G, a->agg_workspace, a->agg_workspace_bytes, stream);
   }, stream);
 }

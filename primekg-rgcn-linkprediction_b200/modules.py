@@ -85,11 +85,13 @@ class DrugDiseaseRGCN(nn.Module):
             if hit is not None and hit[0] == key and hit[1]._version == hit[2]:
                 return hit[1]
         layers = list(self._layers())
+        in_scale = None         # 1 / (1 - p) of the fused ReLU / dropout that produced x (None: x is not such an output)
         for li, conv in enumerate(layers):
             last = li == len(layers) - 1
             # ReLU and (in training) dropout live in the layer's GEMM epilogue; p == 1 keeps nn.Dropout's all-zero output
             p = self.dropout.p if (self.training and not last) else 0.0
-            x = conv.forward_graph(x, graph, relu=not last, dropout_p=p if p < 1.0 else 0.0)
+            x = conv.forward_graph(x, graph, relu=not last, dropout_p=p if p < 1.0 else 0.0, in_mask_scale=in_scale)
+            in_scale = 1.0 / (1.0 - p) if (not last and p < 1.0) else None
             if not last and p >= 1.0:
                 x = self.dropout(x)
         if cacheable:

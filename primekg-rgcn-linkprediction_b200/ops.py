@@ -100,11 +100,13 @@ def reduce_partials(part: torch.Tensor) -> torch.Tensor:
 
 def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None, slot: Optional[torch.Tensor] = None,
-                  zero_row: int = -1) -> torch.Tensor:
+                  zero_row: int = -1, masked=None) -> torch.Tensor:
     """gX[j] = init[j] + sum_r sum_{(j->i, r)} gH[i, r*d:(r+1)*d] / max(|N_r(i)|, 1)  over the transposed CSR.
     ``out``: write into this [n_src, d] fp32 tensor (e.g. a peer-visible buffer) instead of allocating.
     ``slot`` (int32 [n_dst]) + ``zero_row``: gH (and init) hold only the listed rows; node i lives in row slot[i], every
-    other node maps to the all-zero row ``zero_row`` (``rgcn_aggregate_bwd_rows``)."""
+    other node maps to the all-zero row ``zero_row`` (``rgcn_aggregate_bwd_rows``).
+    ``masked`` = (mask [n_src, d], scale, (hi, lo | None), colsum | None): second output, gX masked / scaled as bf16
+    planes + per-block column sums (``rgcn_masked_planes_out``)."""
     lib = _lib.load()
     gH = _f32c(gH, "gH")
     rows_form = slot is not None
@@ -125,16 +127,27 @@ def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Te
         if gX.dtype != torch.float32 or gX.shape != (g.n_src, d) or gX.stride(1) != 1 or gX.stride(0) % 4:
             raise ValueError("out must be a row-major float32 [n_src, d] tensor")
     ws = g.bwd.workspace(d)
+    mp = None if masked is None else C.byref(masked_planes_struct(*masked))
     if rows_form:
         _lib.check(lib.rgcn_aggregate_bwd_rows(g.bwd.ref, _ptr(gH), gH.stride(0), d, _ptr(slot), int(zero_row), _ptr(init),
-                                               0 if init is None else init.stride(0), _ptr(gX), gX.stride(0), _ptr(ws),
+                                               0 if init is None else init.stride(0), _ptr(gX), gX.stride(0), mp, _ptr(ws),
                                                0 if ws is None else ws.numel() * 4, _stream(gH.device)),
                    "rgcn_aggregate_bwd_rows")
         return gX
     _lib.check(lib.rgcn_aggregate_bwd(g.bwd.ref, _ptr(gH), gH.stride(0), d, _ptr(init),
-                                      0 if init is None else init.stride(0), _ptr(gX), gX.stride(0), _ptr(ws),
+                                      0 if init is None else init.stride(0), _ptr(gX), gX.stride(0), mp, _ptr(ws),
                                       0 if ws is None else ws.numel() * 4, _stream(gH.device)), "rgcn_aggregate_bwd")
     return gX
+
+
+def masked_planes_struct(mask: torch.Tensor, scale: float, planes, colsum: Optional[torch.Tensor]):
+    """``rgcn_masked_planes_out`` for (mask, scale, (hi, lo | None), colsum | None); the tensors must outlive the call."""
+    if _f32c(mask, "mask") is not mask:
+        raise ValueError("mask must be a 16-byte aligned row-major float32 matrix")
+    hi, lo = planes
+    if hi.dtype != torch.bfloat16 or hi.stride(1) != 1 or hi.shape[0] != mask.shape[0] or hi.shape[1] < mask.shape[1]:
+        raise ValueError("masked planes must be bf16 row-major [rows, >= d]")
+    return _lib.MaskedPlanesOut(mask.data_ptr(), mask.stride(0), float(scale), hi.data_ptr(), _dp(lo), hi.stride(0), _dp(colsum))
 
 
 def _idx(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -409,12 +422,15 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
 
 def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], mask_scale: float, planes, W2d: torch.Tensor,
               root: torch.Tensor, d_in: int, mode: str, need_x: bool, add_root_term: bool, need_w: bool, need_b: bool,
-              gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None):
+              gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None, g_ready=None, next_mask=None):
     """split(gO, mask) -> dgrad -> transposed gather -> wgrad of one layer in ONE C call (``rgcn_layer_bwd``).
     Returns (g_x | None, gA | None, gW2d | None, g_root | None, g_bias | None); ``gA[:, R*d_in:]`` is the root-term
     gradient (already inside g_x when ``add_root_term``).
     ``rows`` (int64 device list, duplicates allowed): the caller guarantees gO is zero outside these rows; the backward
-    then runs on the compacted rows (csrc/rowsparse.cu) with the same results, and gA comes back compact (``None`` here)."""
+    then runs on the compacted rows (csrc/rowsparse.cu) with the same results, and gA comes back compact (``None`` here).
+    ``g_ready`` = ((G_hi, G_lo | None), colsum [n, d_out]): this layer's masked output gradient as planes, already written
+    by the downstream layer (skips the split pass).  ``next_mask`` = (mask [n_src, d_in], scale): also produce g_x masked
+    for the upstream layer; the result gains a sixth entry ((hi, lo | None), colsum)."""
     lib = _lib.load()
     gO = _f32c(gO, "gO")
     if relu_mask is not None:
@@ -435,9 +451,16 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         m = int(lib.rgcn_rows_compact_size(rows.numel()))
     else:
         m = n
-    G = alloc_planes(m, d_out, mode, dev)
+    if g_ready is not None:
+        if sparse or g_ready[0][0].shape != (n, d_out) or (mode == "fp32") != (g_ready[0][1] is not None):
+            raise ValueError("g_ready does not match this layer")
+        G, colsum_ready = g_ready
+    else:
+        G = alloc_planes(m, d_out, mode, dev)
     colsum = None
-    if need_b:
+    if g_ready is not None:
+        colsum = colsum_ready
+    elif need_b:
         nb = lib.rgcn_rows_compact_blocks(rows.numel()) if sparse else lib.rgcn_split_planes_blocks(n, d_out)
         colsum = torch.empty(max(int(nb), 1), d_out, dtype=torch.float32, device=dev)
     gA = torch.empty(m + (1 if sparse else 0), K, dtype=torch.float32, device=dev) if need_x else None
@@ -449,17 +472,31 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
     gb = torch.empty(d_out, dtype=torch.float32, device=dev) if (need_w and need_b) else None
     slot = torch.empty(n, dtype=torch.int32, device=dev) if sparse else None
     Ac = alloc_planes(m, K, mode, dev) if (sparse and need_w) else (None, None)
+    nxt = nxt_struct = None
+    if next_mask is not None and need_x:
+        nmask, nscale = next_mask
+        if nmask.shape != (g.n_src, d_in):
+            raise ValueError("next_mask must be [n_src, d_in]")
+        nplanes = alloc_planes(g.n_src, d_in, mode, dev)
+        ncs = torch.empty(max(int(lib.rgcn_aggregate_row_blocks(g.bwd.ref, d_in)), 1), d_in, dtype=torch.float32, device=dev)
+        nxt = (nplanes, ncs)
+        nxt_struct = masked_planes_struct(nmask, nscale, nplanes, ncs)
     aws = g.bwd.workspace(d_in)
     gws = _gemm_workspace(dev, m, K, d_out)
     args = _lib.LayerBwdArgs(
         g.bwd.ptr, gO.data_ptr(), gO.stride(0), _dp(relu_mask), 0 if relu_mask is None else relu_mask.stride(0),
         float(mask_scale), n, d_in, d_out, _mode_id(mode), int(add_root_term), W2d.data_ptr(), root.data_ptr(),
-        A_hi.data_ptr(), _dp(A_lo), A_hi.stride(0), G[0].data_ptr(), _dp(G[1]), G[0].stride(0), _dp(colsum if gb is not None else None),
+        A_hi.data_ptr(), _dp(A_lo), A_hi.stride(0), G[0].data_ptr(), _dp(G[1]), G[0].stride(0),
+        _dp(colsum if (gb is not None and colsum is not None) else None),
         _dp(gA), 0 if gA is None else gA.stride(0), _dp(gx), 0 if gx is None else gx.stride(0), _dp(gW), _dp(groot), _dp(gb),
         _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel(),
         _dp(rows), 0 if rows is None else rows.numel(), _dp(slot), _dp(Ac[0]), _dp(Ac[1]),
-        0 if Ac[0] is None else Ac[0].stride(0))
+        0 if Ac[0] is None else Ac[0].stride(0),
+        C.pointer(nxt_struct) if nxt_struct is not None else None, int(g_ready is not None),
+        0 if g_ready is None else colsum.size(0))
     _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
+    if next_mask is not None:
+        return gx, (None if sparse else gA), gW, groot, gb, nxt
     return gx, (None if sparse else gA), gW, groot, gb
 
 

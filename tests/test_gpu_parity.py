@@ -1027,3 +1027,74 @@ def test_graphed_step_uses_fused_loss_and_reports_accuracy(pkg):
     loss = step(*b)
     torch.testing.assert_close(loss.cpu(), g["loss"], rtol=1e-4, atol=1e-5)
     assert int(step.correct) == int(((g["scores"] > 0).float() == g["labels"]).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+# cross-layer hand-over: the backward walk writes the upstream layer's masked G planes itself
+@pytest.mark.parametrize("name,d", [("primekg_100k", 256), ("uniform_r30", 64), ("val_fixture", 128), ("ragged", 16)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("slot_form", [False, True])
+def test_walk_writes_masked_planes(pkg, name, d, mode, slot_form):
+    """Second output of rgcn_aggregate_bwd[_rows] == rgcn_split_planes(gX, relu_mask, scale) on the walk's own result:
+    planes bit for bit, column sums up to the order of the partial rows."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()[name]
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    gen = torch.Generator().manual_seed(21)
+    K = (R + 1) * d
+    mask = (torch.randn(N, d, generator=gen).clamp_min(0.0)).to(DEV)            # ~half zeros, like a ReLU output
+    scale = 1.0 / (1.0 - 0.3)
+    kw = {}
+    if slot_form:
+        n_list = max(2, N // 6)
+        rows = torch.randint(0, N, (n_list,), generator=gen)
+        m_c = (n_list + 127) // 128 * 128
+        slot = torch.full((N,), m_c, dtype=torch.int32)
+        for c in range(n_list - 1, -1, -1):
+            slot[rows[c]] = c
+        gA = torch.zeros(m_c + 1, K)
+        uniq = torch.unique(rows)
+        gA[slot[uniq].long()] = torch.randn(uniq.numel(), K, generator=gen)
+        kw = dict(slot=slot.to(DEV), zero_row=m_c)
+    else:
+        gA = torch.randn(N, K, generator=gen)
+    gA = gA.to(DEV)
+    planes = ops.alloc_planes(N, d, mode, DEV)
+    ncs = torch.empty(int(pkg._lib.load().rgcn_aggregate_row_blocks(g.bwd.ref, d)) or 1, d, device=DEV)
+    gx = ops.aggregate_bwd(g, gA, d, init=gA[:, R * d:], masked=(mask, scale, planes, ncs), **kw)
+    want_gx = ops.aggregate_bwd(g, gA, d, init=gA[:, R * d:], **kw)
+    assert torch.equal(gx, want_gx)
+    ref = ops.alloc_planes(N, d, mode, DEV)
+    cs = ops.split_planes(gx, ref, relu_mask=mask, colsum=True, mask_scale=scale)
+    assert torch.equal(planes[0], ref[0])
+    if mode == "fp32":
+        assert torch.equal(planes[1], ref[1])
+    a, b = ncs.sum(0), cs.sum(0)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-4 * float(b.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.5])
+def test_cross_layer_planes_handover_equals_separate_pass(pkg, monkeypatch, p_drop):
+    """Two-layer model, training step: with the hand-overs on, layer 1's backward takes the planes layer 2's walk wrote
+    (claimed == 1) and every gradient equals the run with the hand-overs off."""
+    from primekg_rgcn_linkprediction_b200 import rowsparse
+    g = load_golden("small_full")
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    b = [g[k].to(DEV) for k in ("heads", "tails", "rels", "labels")]
+    res = {}
+    for on in (False, True):
+        monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_BWD", "1" if on else "0")
+        monkeypatch.setenv("PRIMEKG_RGCN_PLANES_HANDOVER", "1")          # opt-in (measured slower on cfg2)
+        monkeypatch.setattr(rowsparse, "MAX_FRACTION", 1e9)
+        rowsparse.clear()
+        rowsparse.plane_stats.update(claimed=0, declined=0)
+        torch.manual_seed(77)                                            # same dropout seed in both runs
+        m = pkg.DrugDiseaseModel(g["num_nodes"], g["num_relations"], g["embedding_dim"], g["hidden_dim"], dropout=p_drop,
+                                 decoder_dropout=0.0, num_bases=g["num_bases"])
+        m.load_state_dict(g["state_dict"], strict=True)
+        m.to(DEV).train()
+        F.binary_cross_entropy_with_logits(m(ei, et, b[0], b[1], b[2]), b[3]).backward()
+        assert rowsparse.plane_stats["claimed"] == int(on)
+        res[on] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for k in res[False]:
+        _close_by_scale(res[True][k], res[False][k], k)
