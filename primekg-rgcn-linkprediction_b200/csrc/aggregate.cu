@@ -519,266 +519,6 @@ aggregate_rows_kernel(const AggParams p) {
   }
 }
 
-// ---- rows, software-pipelined: one G-lane group walks kPipeRows consecutive rows (of the row order) -----------------
-// The plain row kernel exposes a chain of dependent loads per row — row order -> rowptr -> edge indices (-> slot) ->
-// feature rows — and a PrimeKG row has ~27 edges, so most of a group's life is spent waiting on the first three.  Here
-// the group keeps three rows in flight: while it gathers the feature rows of row A, the index window of row B and the
-// rowptr block of row C are already on their way (issued one iteration earlier), so per row only the feature loads are
-// exposed.  Same arithmetic in the same order as aggregate_rows_kernel (bit-identical results); unmixed and summed
-// forms only, R <= G (one rowptr block per row).
-constexpr int pipe_min_blocks(int G, int vpl, int mix, bool w) {
-  if (vpl > 2) return 1;
-  if (vpl == 2) return (mix == MIX_NONE && !w) ? 4 : 3;
-  return 3;
-}
-
-template <int G, int VPL, int MIX, bool W, bool SLOT, int RPG>
-__global__ void __launch_bounds__(256, pipe_min_blocks(G, VPL, MIX, W)) aggregate_rows_pipe_kernel(const AggParams p) {
-  pdl_enter();
-  constexpr int GROUPS = 256 / G;
-  constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
-  constexpr int U = U0 < G ? U0 : G;
-  constexpr bool TAILPRED = VPL <= RGCN_TAILPRED_MAX_VPL;
-  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-  const int sh = (G == 32) ? 0 : (int)((threadIdx.x & 31) / G * G);
-  // group `gid` takes rows gid, gid + n_groups, gid + 2 n_groups, ... of the (longest-first) row order: every group
-  // gets one row of each length class, so the groups finish together
-  const int64_t gid = (int64_t)blockIdx.x * GROUPS + grp;
-  const int64_t n_groups = (int64_t)gridDim.x * GROUPS;
-  if (gid >= p.n_rows) return;
-  const int n_mine = (int)min((int64_t)RPG, (p.n_rows - gid + n_groups - 1) / n_groups);
-  const int R = p.R, d = p.d, nvec = p.d >> 2;
-  const int32_t* __restrict__ idx = p.idx;
-  const float* __restrict__ ew = p.edge_w;
-  const float* __restrict__ F = p.F;
-  const int64_t ldf = p.ldf;
-  const int rel_stride = p.src_rel_stride;
-  bool act[VPL];
-  int vcol[VPL];
-#pragma unroll
-  for (int k = 0; k < VPL; ++k) {
-    const int vi = k * G + lane;
-    act[k] = vi < nvec;
-    vcol[k] = act[k] ? vi * 4 : 0;
-  }
-  // the group's row ids, one per lane (RPG <= G), handed out by shuffle
-  int my_rid = 0;
-  if (lane < n_mine) my_rid = p.row_order ? __ldg(p.row_order + gid + lane * n_groups) : (int)(gid + lane * n_groups);
-
-  // pipeline state.  A = the row being gathered, B = next (rowptr arrived, index window in flight), C = after that
-  // (row id known, rowptr in flight)
-  int a_row = 0, a_beg = 0, a_end = 0, a_rend = 0;            // (beg, end) of relation `lane`, end of the row
-  int wbase = 0, wi0 = 0, wi1 = 0;
-  float ww0 = 1.f, ww1 = 1.f;
-  unsigned long long present = 0ull;
-  int b_row = 0, b_beg = 0, b_end = 0, b_rend = 0, b_rbeg = 0;
-  int bw0 = 0, bw1 = 0;
-  float bf0 = 1.f, bf1 = 1.f;
-  int c_row = 0, c_beg = 0, c_end = 0;
-
-  auto load_rowptr = [&](int row, int& beg, int& end) {
-    const int32_t* __restrict__ rp = p.rowptr + (int64_t)row * R;
-    beg = (lane < R) ? __ldg(rp + lane) : 0;
-    end = (lane < R) ? __ldg(rp + lane + 1) : 0;
-  };
-  // first two windows' worth of indices (and weights) of a row: raw loads only, the slot translation follows later
-  auto load_window = [&](int e, int row_end, int& i0, int& i1, float& f0, float& f1) {
-    const bool in0 = e + lane < row_end, in1 = e + G + lane < row_end;
-    i0 = in0 ? __ldg(idx + e + lane) : -1;
-    i1 = in1 ? __ldg(idx + e + G + lane) : -1;
-    if (W) {
-      f0 = in0 ? __ldg(ew + e + lane) : 0.f;
-      f1 = in1 ? __ldg(ew + e + G + lane) : 0.f;
-    }
-  };
-  // window of the CURRENT row from raw indices: slot translation + presence mask (SLOT), -1 -> harmless row 0
-  auto adopt_window = [&](int e, int i0, int i1, float f0, float f1) {
-    wbase = e;
-    if (SLOT) {
-      wi0 = i0 >= 0 ? __ldg(p.slot + i0) : p.zero_row;
-      wi1 = i1 >= 0 ? __ldg(p.slot + i1) : p.zero_row;
-      const unsigned m0 = (__ballot_sync(gmask, wi0 != p.zero_row) & gmask) >> sh;
-      const unsigned m1 = (__ballot_sync(gmask, wi1 != p.zero_row) & gmask) >> sh;
-      present = ((unsigned long long)m1 << G) | (unsigned long long)m0;
-    } else {
-      wi0 = i0 < 0 ? 0 : i0;
-      wi1 = i1 < 0 ? 0 : i1;
-    }
-    ww0 = f0; ww1 = f1;
-  };
-  auto refill = [&](int e) {
-    int i0, i1; float f0 = 0.f, f1 = 0.f;
-    load_window(e, a_rend, i0, i1, f0, f1);
-    adopt_window(e, i0, i1, f0, f1);
-  };
-
-  // prologue: rowptr(A) -> window(A), rowptr(B); rowptr(C) is issued by the first iteration
-  a_row = __shfl_sync(gmask, my_rid, 0, G);
-  load_rowptr(a_row, a_beg, a_end);
-  if (n_mine > 1) { b_row = __shfl_sync(gmask, my_rid, 1, G); load_rowptr(b_row, b_beg, b_end); }
-  a_rend = __shfl_sync(gmask, a_end, R - 1, G);
-  {
-    const int e0 = __shfl_sync(gmask, a_beg, 0, G);
-    int i0, i1; float f0 = 0.f, f1 = 0.f;
-    load_window(e0, a_rend, i0, i1, f0, f1);
-    adopt_window(e0, i0, i1, f0, f1);
-  }
-
-  for (int it = 0; it < n_mine; ++it) {
-    const int64_t row = a_row;
-    // ---- issue the loads of the rows behind this one --------------------------------------------------------
-    const bool has_b = it + 1 < n_mine, has_c = it + 2 < n_mine;
-    if (has_b) {
-      b_rend = __shfl_sync(gmask, b_end, R - 1, G);
-      b_rbeg = __shfl_sync(gmask, b_beg, 0, G);
-      load_window(b_rbeg, b_rend, bw0, bw1, bf0, bf1);
-    }
-    if (has_c) {
-      c_row = __shfl_sync(gmask, my_rid, it + 2, G);
-      load_rowptr(c_row, c_beg, c_end);
-    }
-    // ---- row A ------------------------------------------------------------------------------------------------
-    if (MIX == MIX_NONE && p.root_rows) {
-#pragma unroll
-      for (int k = 0; k < VPL; ++k)
-        if (act[k]) store_vec(p, row, R * p.block_stride + vcol[k], ldg4(p.root_rows + row * p.ld_root + vcol[k]));
-    }
-    float4 mix[VPL];
-    if (MIX == MIX_SUM) {
-#pragma unroll
-      for (int k = 0; k < VPL; ++k) mix[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.init) {
-        const int64_t irow = SLOT ? (int64_t)__ldg(p.slot + row) : row;
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) mix[k] = ldg4(p.init + irow * p.ld_init + vcol[k]);
-      }
-    }
-    for (int r = 0; r < R; ++r) {
-      const int beg = __shfl_sync(gmask, a_beg, r, G);
-      const int end = __shfl_sync(gmask, a_end, r, G);
-      const int len = end - beg;
-      if (len == 0 && MIX != MIX_NONE) continue;
-      float4 acc[VPL];
-#pragma unroll
-      for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (len > p.hub_threshold) {
-        const int key = (int)(row * R + r);
-        int lo = 0, hi = p.n_hubs;
-        while (hi - lo > 1) {
-          int mid = (lo + hi) >> 1;
-          if (__ldg(p.hub_keys + mid) <= key) lo = mid; else hi = mid;
-        }
-        const int c0 = __ldg(p.hub_chunk_ptr + lo), c1 = __ldg(p.hub_chunk_ptr + lo + 1);
-        int c = c0;
-        for (; c + U <= c1; c += U) {
-          float4 v[U][VPL];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) v[u][k] = *reinterpret_cast<const float4*>(p.partials + (size_t)(c + u) * d + vcol[k]);
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) add4(acc[k], v[u][k]);
-        }
-        for (; c < c1; ++c) {
-#pragma unroll
-          for (int k = 0; k < VPL; ++k) add4(acc[k], *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k]));
-        }
-      } else if (SLOT && len > 0) {
-        const float* __restrict__ Fb = F + (size_t)r * rel_stride;
-        int e = beg;
-        while (e < end) {
-          if (e >= wbase + 2 * G) refill(e);
-          const int o0 = e - wbase;
-          const int lim = min(end - wbase, 2 * G);
-          unsigned long long m = present >> o0;
-          if (lim - o0 < 64) m &= (1ull << (lim - o0)) - 1ull;
-          while (m) {
-            float4 v[U][VPL];
-            float w[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const bool on = m != 0ull;
-              const int off = o0 + (on ? __ffsll((long long)m) - 1 : 0);
-              m &= m - 1ull;
-              const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
-              const float wv = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
-              w[u] = on ? wv : 0.f;
-              const float* __restrict__ rp = Fb + (size_t)j * ldf;
-#pragma unroll
-              for (int k = 0; k < VPL; ++k) v[u][k] = on ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-              for (int k = 0; k < VPL; ++k) fma4(acc[k], w[u], v[u][k]);
-          }
-          e = wbase + lim;
-        }
-      } else if (len > 0) {
-        const float* __restrict__ Fb = F + (size_t)r * rel_stride;
-        int e = beg;
-        auto batch = [&](auto ub, int n) {
-          constexpr int UB = decltype(ub)::value;
-          if (e + UB > wbase + 2 * G) refill(e);
-          float4 v[UB][VPL];
-          float w[UB];
-#pragma unroll
-          for (int u = 0; u < UB; ++u) {
-            const int off = e + u - wbase;
-            const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
-            if (W) w[u] = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
-            const float* __restrict__ rp = Fb + (size_t)j * ldf;
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) v[u][k] = (u < n) ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < UB; ++u)
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-              if (W) fma4(acc[k], (u < n) ? w[u] : 0.f, v[u][k]); else add4(acc[k], v[u][k]);
-            }
-          e += (n < UB) ? n : UB;
-        };
-        while (e + U <= end) batch(std::integral_constant<int, U>{}, U);
-        if (TAILPRED) {
-          if (e < end) batch(std::integral_constant<int, U>{}, end - e);
-        } else {
-          if (U > 4 && e + 4 <= end) batch(std::integral_constant<int, (U > 4 ? 4 : 1)>{}, 4);
-          if (U > 2 && e + 2 <= end) batch(std::integral_constant<int, (U > 2 ? 2 : 1)>{}, 2);
-          if (e < end) batch(std::integral_constant<int, 1>{}, 1);
-        }
-      }
-      if (!W && len > 1) {
-        const float c = (float)len;
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) acc[k] = div4(acc[k], c);
-      }
-      if (MIX == MIX_NONE) {
-#pragma unroll
-        for (int k = 0; k < VPL; ++k)
-          if (act[k]) store_vec(p, row, r * p.block_stride + vcol[k], acc[k]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) add4(mix[k], acc[k]);
-      }
-    }
-    if (MIX == MIX_SUM) {
-#pragma unroll
-      for (int k = 0; k < VPL; ++k)
-        if (act[k]) store_vec(p, row, vcol[k], mix[k]);
-    }
-    // ---- rotate: B becomes the current row (its window has arrived by now), C moves up --------------------------
-    if (has_b) {
-      a_row = b_row; a_beg = b_beg; a_end = b_end; a_rend = b_rend;
-      adopt_window(b_rbeg, bw0, bw1, bf0, bf1);
-      b_row = c_row; b_beg = c_beg; b_end = c_end;
-    }
-  }
-}
-
 // ---- hub finish: one G-lane group per hub ROW (led by the row's first hub segment) -------------------------
 // Runs after hub_partial_kernel (chunk partials) and after the row walk (which skipped the hub segments): sums each
 // hub segment's partials in chunk order and writes its block (MIX_NONE) or adds the row's hub segments to the row the
@@ -903,30 +643,6 @@ static int launch_agg_overlapped(AggParams p, int n_chunks, cudaStream_t st) {
   return RGCN_OK;
 }
 
-// rows per group of the pipelined walk (0 = plain kernel); RGCN_AGG_PIPE overrides (0 .. 8)
-static int pipe_rows(int G, int vpl) {
-  static int env = -2;
-  if (env == -2) {
-    const char* e = getenv("RGCN_AGG_PIPE");
-    env = e ? atoi(e) : -1;
-    if (env > 8) env = 8;
-  }
-  if (env >= 0) return env;
-  (void)G; (void)vpl;
-  return 0;       // measured slower on the B200 at every depth (cfg2 d = 64 / 256: 40 / 75 us plain, 45 / 85 us with 2 rows)
-}
-
-template <int G, int VPL, int MIX, bool W, bool SLOT>
-static int launch_pipe(const AggParams& p, int rpg, cudaStream_t st) {
-  constexpr int GROUPS = 256 / G;
-  const unsigned grid = (unsigned)((p.n_rows + (int64_t)GROUPS * rpg - 1) / ((int64_t)GROUPS * rpg));
-  if (rpg <= 2) RGCN_CUDA(launch_pdl(aggregate_rows_pipe_kernel<G, VPL, MIX, W, SLOT, 2>, dim3(grid), dim3(256), 0, st, p));
-  else if (rpg <= 4) RGCN_CUDA(launch_pdl(aggregate_rows_pipe_kernel<G, VPL, MIX, W, SLOT, (G >= 4 ? 4 : 2)>, dim3(grid), dim3(256), 0, st, p));
-  else RGCN_CUDA(launch_pdl(aggregate_rows_pipe_kernel<G, VPL, MIX, W, SLOT, (G >= 8 ? 8 : 4)>, dim3(grid), dim3(256), 0, st, p));
-  RGCN_LAUNCH_CHECK();
-  return RGCN_OK;
-}
-
 template <int G, int VPL>
 static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
@@ -944,10 +660,6 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
       RGCN_LAUNCH_CHECK();
     }
     if (p.n_rows == 0) return RGCN_OK;
-    {
-      const int rpg = (p.R <= G && !p.mp_hi) ? pipe_rows(G, VPL) : 0;
-      if (rpg >= 2) return launch_pipe<G, VPL, MIX_SUM, true, true>(p, rpg > 4 ? (G >= 8 ? 8 : 4) : (rpg > 2 ? 4 : 2), st);
-    }
     const dim3 sgrid((unsigned)((p.n_rows + GROUPS - 1) / GROUPS));
     if (p.mp_hi) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true, true>, sgrid, dim3(256),
                                       p.mp_colsum ? (size_t)GROUPS * p.d * sizeof(float) : 0, st, p));
@@ -963,14 +675,6 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
   if (p.n_rows == 0) return RGCN_OK;
   const unsigned grid = (unsigned)((p.n_rows + GROUPS - 1) / GROUPS);
   const bool w = p.edge_w != nullptr;
-  if (mix != MIX_BASIS && p.R <= G && !p.mp_hi && !p.skip_hubs) {
-    int rpg = pipe_rows(G, VPL);
-    if (rpg >= 2) {
-      rpg = rpg > 4 ? (G >= 8 ? 8 : 4) : (rpg > 2 ? 4 : 2);
-      if (mix == MIX_NONE) return w ? launch_pipe<G, VPL, MIX_NONE, true, false>(p, rpg, st) : launch_pipe<G, VPL, MIX_NONE, false, false>(p, rpg, st);
-      return w ? launch_pipe<G, VPL, MIX_SUM, true, false>(p, rpg, st) : launch_pipe<G, VPL, MIX_SUM, false, false>(p, rpg, st);
-    }
-  }
   const size_t sm = (size_t)p.R * p.B * sizeof(float) * (p.dotP ? 1 + GROUPS : 1);
   if (mix == MIX_NONE) {
     if (w) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, true>, dim3(grid), dim3(256), 0, st, p));

@@ -81,9 +81,32 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+// Packed fp32 arithmetic of sm_100 (add.f32x2 / fma.f32x2 -> FADD2 / FFMA2: two IEEE round-to-nearest results per
+// instruction, bit-identical to the scalar forms).  The gather loops are instruction-issue sensitive (16 B per lane per
+// edge): the accumulate of one 128-bit vector is 2 instructions instead of 4.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+  unsigned long long a0 = pack2(a.x, a.y), a1 = pack2(a.z, a.w);
+  const unsigned long long b0 = pack2(b.x, b.y), b1 = pack2(b.z, b.w);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(b0));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(b1));
+  unpack2(a0, a.x, a.y);
+  unpack2(a1, a.z, a.w);
+}
 __device__ __forceinline__ void fma4(float4& a, float w, const float4& b) {
-  a.x = fmaf(w, b.x, a.x); a.y = fmaf(w, b.y, a.y); a.z = fmaf(w, b.z, a.z); a.w = fmaf(w, b.w, a.w);
+  unsigned long long a0 = pack2(a.x, a.y), a1 = pack2(a.z, a.w);
+  const unsigned long long b0 = pack2(b.x, b.y), b1 = pack2(b.z, b.w), ww = pack2(w, w);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(ww), "l"(b0));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(ww), "l"(b1));
+  unpack2(a0, a.x, a.y);
+  unpack2(a1, a.z, a.w);
 }
 __device__ __forceinline__ float4 scale4(const float4& a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ float4 div4(const float4& a, float s) { return make_float4(a.x / s, a.y / s, a.z / s, a.w / s); }
