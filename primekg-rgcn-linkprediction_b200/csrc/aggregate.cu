@@ -336,34 +336,54 @@ aggregate_rows_kernel(const AggParams p) {
           for (int k = 0; k < VPL; ++k) add4(acc[k], *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k]));
         }
       } else if (SLOT && len > 0) {
-        // only the edges whose gathered row is listed (set bits of the window mask), U at a time, in edge order
+        // only the edges whose gathered row is listed, in edge order: the window's presence mask is walked bit by bit,
+        // one 32-bit half at a time (G <= 32), batches of 4 — or 2 when no more bits are left, since a segment of a
+        // PrimeKG row has two or three listed edges on average and every unrolled slot costs issue cycles
         const float* __restrict__ Fb = F + (size_t)r * rel_stride;
         int e = beg;
-        while (e < end) {
-          if (e >= wbase + 2 * G) refill(e);
-          const int o0 = e - wbase;
-          const int lim = min(end - wbase, 2 * G);
-          unsigned long long m = present >> o0;
-          if (lim - o0 < 64) m &= (1ull << (lim - o0)) - 1ull;
-          while (m) {
-            float4 v[U][VPL];
-            float w[U];
+        auto run = [&](unsigned m, int wsel, int obase) {
+          auto batch = [&](auto ub) {
+            constexpr int UB = decltype(ub)::value;
+            float4 v[UB][VPL];
+            float w[UB];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const bool on = m != 0ull;
-              const int off = o0 + (on ? __ffsll((long long)m) - 1 : 0);
-              m &= m - 1ull;
-              const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
-              const float wv = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
+            for (int u = 0; u < UB; ++u) {
+              const bool on = m != 0u;
+              const int off = on ? __ffs((int)m) - 1 : obase;
+              m &= m - 1u;
+              const int j = __shfl_sync(gmask, wsel ? wi1 : wi0, off, G);
+              const float wv = __shfl_sync(gmask, wsel ? ww1 : ww0, off, G);
               w[u] = on ? wv : 0.f;
               const float* __restrict__ rp = Fb + (size_t)j * ldf;
 #pragma unroll
               for (int k = 0; k < VPL; ++k) v[u][k] = on ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < UB; ++u)
 #pragma unroll
               for (int k = 0; k < VPL; ++k) fma4(acc[k], w[u], v[u][k]);
+          };
+          while (m) {
+            if (U >= 4 && __popc(m) > 2) batch(std::integral_constant<int, (U >= 4 ? 4 : 2)>{});
+            else batch(std::integral_constant<int, 2>{});
+          }
+        };
+        while (e < end) {
+          if (e >= wbase + 2 * G) refill(e);
+          const int o0 = e - wbase;                       // < 2 G
+          const int lim = min(end - wbase, 2 * G);
+          const unsigned full = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+          if (o0 < G) {
+            const int hi = min(lim, G);
+            unsigned m = ((unsigned)present & full) >> o0 << o0;
+            if (hi < G) m &= (1u << hi) - 1u;
+            run(m, 0, o0);
+          }
+          if (lim > G) {
+            const int lo = max(o0 - G, 0), hi = lim - G;
+            unsigned m = ((unsigned)(present >> G) & full) >> lo << lo;
+            if (hi < G) m &= (1u << hi) - 1u;
+            run(m, 1, lo);
           }
           e = wbase + lim;
         }
