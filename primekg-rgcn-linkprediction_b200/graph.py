@@ -28,8 +28,22 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _stream_id(device) -> int:
+    """torch's current stream on ``device`` as a raw handle (the direct binding is several times cheaper than building a
+    ``torch.cuda.Stream`` object; the eager step makes ~10 such calls and is bound by the host)."""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+        return int(_raw_stream(idx))
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
 def _stream(device) -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return C.c_void_p(_stream_id(device))
 
 
 def hub_threshold() -> int:

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .graph import RelGraph, _ptr, _stream
+from .graph import RelGraph, _ptr, _stream, _stream_id
 
 
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -232,7 +232,7 @@ _WS = {}
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
     """Per-device scratch reused by every transform call (all calls are ordered on one stream)."""
-    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    key = (device, _stream_id(device))
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
