@@ -1098,3 +1098,82 @@ def test_cross_layer_planes_handover_equals_separate_pass(pkg, monkeypatch, p_dr
         res[on] = {k: p.grad.clone() for k, p in m.named_parameters()}
     for k in res[False]:
         _close_by_scale(res[True][k], res[False][k], k)
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases of the row-sparse backward and the fused step tail
+@pytest.mark.parametrize("case", ["single_row", "all_duplicates", "every_node", "n_129", "isolated_rows"])
+def test_layer_bwd_rows_edge_cases(pkg, case):
+    """Row lists of awkward shapes: one entry, one node repeated, every node listed (nothing to skip), a length just past
+    a multiple of 128, rows without any edge."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R = graphs()["uniform_r30" if case != "isolated_rows" else "ragged"]
+    d_in, d_out = 64, 128
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(N, d_in, generator=gen).to(DEV)
+    W = (torch.randn(R * d_in, d_out, generator=gen) / 8).to(DEV)
+    root = (torch.randn(d_in, d_out, generator=gen) / 8).to(DEV)
+    _, A = ops.layer_fwd(g, x, x, W, root, torch.zeros(d_out, device=DEV), False, "fp32")
+    rows = {"single_row": torch.tensor([N // 2]), "all_duplicates": torch.full((300,), 7),
+            "every_node": torch.randperm(N, generator=gen), "n_129": torch.randint(0, N, (129,), generator=gen),
+            "isolated_rows": torch.tensor([4, 5, 7, 8, 4])}[case]
+    gO = torch.zeros(N, d_out)
+    uniq = torch.unique(rows)
+    gO[uniq] = torch.randn(uniq.numel(), d_out, generator=gen)
+    gO = gO.to(DEV)
+    dense = ops.layer_bwd(g, gO, None, 1.0, A, W, root, d_in, "fp32", True, True, True, True)
+    comp = ops.layer_bwd(g, gO, None, 1.0, A, W, root, d_in, "fp32", True, True, True, True, rows=rows.to(DEV))
+    assert torch.equal(comp[0], dense[0])
+    for a, b, what in zip(comp[2:], dense[2:], ("g_weight", "g_root", "g_bias")):
+        _close_by_scale(a, b, what)
+
+
+def test_sparse_backward_three_layers_and_long_lists(pkg, monkeypatch):
+    """num_layers = 3 (the extension pattern of the reference's guide): only the last layer takes the compact backward;
+    a row list longer than MAX_FRACTION * N falls back to the dense one.  Gradients equal the hand-over-off run."""
+    from primekg_rgcn_linkprediction_b200 import rowsparse, synth
+    kg = synth.uniform_kg(4000, 60_000, 5, seed=8)
+    heads, tails, rels, labels = synth.link_batch(kg, 256, seed=8)
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    b = [t.to(DEV) for t in (heads, tails, rels, labels)]
+    res = {}
+    for tag, env, frac in (("off", "0", 0.5), ("on", "1", 0.5), ("too_long", "1", 0.01)):
+        monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_BWD", env)
+        monkeypatch.setattr(rowsparse, "MAX_FRACTION", frac)
+        rowsparse.clear()
+        rowsparse.stats.update(claimed=0, declined=0)
+        torch.manual_seed(3)
+        m = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 32, 64, dropout=0.0, decoder_dropout=0.0,
+                                 num_layers=3).to(DEV).train()
+        F.binary_cross_entropy_with_logits(m(ei, et, b[0], b[1], b[2]), b[3]).backward()
+        assert rowsparse.stats == {"off": dict(claimed=0, declined=0), "on": dict(claimed=1, declined=0),
+                                   "too_long": dict(claimed=0, declined=1)}[tag]
+        res[tag] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    for tag in ("on", "too_long"):
+        for k in res["off"]:
+            _close_by_scale(res[tag][k], res["off"][k], f"{tag}/{k}")
+
+
+def test_negative_sampler_edge_cases(pkg):
+    """num_neg_samples = 0 (positives only), a single positive, and the reference's default of one negative each."""
+    ph = torch.tensor([3, 1, 4], device=DEV); pt = torch.tensor([1, 5, 9], device=DEV); pr = torch.tensor([0, 1, 2], device=DEV)
+    h, t, r, y = pkg.NegativeSampler(10, 0).batch(ph, pt, pr)
+    assert torch.equal(h, ph) and torch.equal(t, pt) and torch.equal(r, pr) and torch.equal(y, torch.ones(3, device=DEV))
+    h, t, r, y = pkg.NegativeSampler(10, 1).batch(ph[:1], pt[:1], pr[:1])
+    assert h.numel() == 2 and y.tolist() == [1.0, 0.0] and int(r[1]) == 0
+    assert (int(h[1]) == 3) != (int(t[1]) == 1) or (int(h[1]) == 3 and int(t[1]) == 1)   # at most one end replaced
+    with pytest.raises(RuntimeError):
+        pkg.NegativeSampler(10, 1).batch(ph.cpu(), pt.cpu(), pr.cpu())                    # no CPU path
+
+
+def test_link_loss_rejects_bad_input(pkg):
+    from primekg_rgcn_linkprediction_b200 import ops
+    emb = torch.randn(10, 8, device=DEV); table = torch.randn(2, 8, device=DEV)
+    idx = torch.zeros(4, dtype=torch.int64, device=DEV); y = torch.zeros(4, device=DEV)
+    with pytest.raises(ValueError):
+        ops.link_loss(emb, table, idx, idx[:3], idx, y)                                  # ragged batch
+    with pytest.raises(ValueError):
+        ops.link_loss(emb, table, idx, idx, idx, y, p_drop=0.5)                          # dropout without a counter
+    with pytest.raises(RuntimeError):
+        ops.link_loss(emb.cpu(), table.cpu(), idx.cpu(), idx.cpu(), idx.cpu(), y.cpu())  # no CPU path
