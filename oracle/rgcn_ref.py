@@ -228,6 +228,27 @@ def train_step_ref(model, edge_index, edge_type, heads, tails, rels, labels):
     return loss.detach(), scores.detach()
 
 
+def negative_batch_ref(pos_head, pos_tail, pos_rel, num_nodes: int, num_neg: int = 1, generator=None):
+    """The mini-batch the reference's loop assembles: ``NegativeSampler.sample`` (src/train.py:59-97: repeat_interleave,
+    corrupt the head where rand < 0.5 else the tail, replacement uniform over all nodes) followed by the concatenation
+    and labels of src/train.py:281-288.  Returns (heads, tails, rels, labels).  The device sampler draws from another
+    random stream, so parity with this restatement is distributional (layout, rates, ranges), not element-wise."""
+    n = pos_head.numel()
+    nh, nt, nr = (t.repeat_interleave(num_neg) for t in (pos_head, pos_tail, pos_rel))
+    total = n * num_neg
+    corrupt_head = torch.rand(total, generator=generator) < 0.5
+    ent = torch.randint(0, num_nodes, (total,), generator=generator)
+    nh = torch.where(corrupt_head, ent, nh)
+    nt = torch.where(~corrupt_head, ent, nt)
+    labels = torch.cat([torch.ones(n), torch.zeros(total)])
+    return torch.cat([pos_head, nh]), torch.cat([pos_tail, nt]), torch.cat([pos_rel, nr]), labels
+
+
+def accuracy_count_ref(scores: torch.Tensor, labels: torch.Tensor) -> int:
+    """Number of correct predictions as counted at src/train.py:321-322."""
+    return int(((torch.sigmoid(scores) > 0.5).float() == labels).sum().item())
+
+
 # ----------------------------------------------------------------------------------
 # Ranking / all-pairs scoring (cfg4 and the evaluate.py inner loop)
 # ----------------------------------------------------------------------------------

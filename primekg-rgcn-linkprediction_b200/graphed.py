@@ -21,7 +21,11 @@ from .ops import bce_with_logits
 
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, edge_index: torch.Tensor, edge_type: torch.Tensor, batch_size: int,
-                 loss_fn: Optional[Callable] = None, warmup: int = 3, flat_grads: bool = False):
+                 loss_fn: Optional[Callable] = None, warmup: int = 3, flat_grads: bool = False, sampler=None):
+        """``sampler`` (a ``NegativeSampler``): the captured step starts from ``batch_size / (1 + num_neg_samples)``
+        POSITIVE edges and draws the negatives, the concatenation and the labels on the device inside the graph
+        (reference src/train.py:276-288) — ``step.run_positives(pos_head, pos_tail, pos_rel)``; fresh negatives on every
+        replay."""
         if not edge_index.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors")
         dev = edge_index.device
@@ -34,6 +38,14 @@ class GraphedTrainStep:
         self.tails = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.rels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
         self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+        self.sampler = sampler
+        if sampler is not None:
+            if batch_size % (1 + sampler.num_neg_samples):
+                raise ValueError("batch_size must be n_pos * (1 + num_neg_samples)")
+            n_pos = batch_size // (1 + sampler.num_neg_samples)
+            self.pos_heads = torch.zeros(n_pos, dtype=torch.int64, device=dev)
+            self.pos_tails = torch.zeros(n_pos, dtype=torch.int64, device=dev)
+            self.pos_rels = torch.zeros(n_pos, dtype=torch.int64, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat_grad = None
         if flat_grads:
@@ -62,6 +74,9 @@ class GraphedTrainStep:
         self._bind_grads()
 
     def _step(self):
+        if self.sampler is not None:
+            self.sampler.batch(self.pos_heads, self.pos_tails, self.pos_rels,
+                               out=(self.heads, self.tails, self.rels, self.labels))
         if self.fused_loss:
             loss, scores, self.correct = self.model.link_loss(self.edge_index, self.edge_type, self.heads, self.tails,
                                                               self.rels, self.labels)
@@ -87,9 +102,22 @@ class GraphedTrainStep:
         self.rels.copy_(rels, non_blocking=non_blocking)
         self.labels.copy_(labels, non_blocking=non_blocking)
 
+    def run_positives(self, pos_heads, pos_tails, pos_rels, non_blocking: bool = True) -> torch.Tensor:
+        """One step from positive edges only (needs ``sampler``): negatives, labels, forward, loss, backward in the graph."""
+        if self.sampler is None:
+            raise RuntimeError("run_positives needs a GraphedTrainStep built with sampler=NegativeSampler(...)")
+        self.pos_heads.copy_(pos_heads, non_blocking=non_blocking)
+        self.pos_tails.copy_(pos_tails, non_blocking=non_blocking)
+        self.pos_rels.copy_(pos_rels, non_blocking=non_blocking)
+        self.graph.replay()
+        self._bind_grads()
+        return self.loss
+
     def __call__(self, heads=None, tails=None, rels=None, labels=None) -> torch.Tensor:
         """Run one step; returns the (static) loss tensor.  With no arguments the buffers are used as they are."""
         if heads is not None:
+            if self.sampler is not None:
+                raise RuntimeError("this step draws its own negatives: call run_positives(pos_heads, pos_tails, pos_rels)")
             self.load_batch(heads, tails, rels, labels)
         self.graph.replay()
         self._bind_grads()          # (a caller may have set .grad to None, e.g. optimizer.zero_grad())

@@ -1177,3 +1177,26 @@ def test_link_loss_rejects_bad_input(pkg):
         ops.link_loss(emb, table, idx, idx, idx, y, p_drop=0.5)                          # dropout without a counter
     with pytest.raises(RuntimeError):
         ops.link_loss(emb.cpu(), table.cpu(), idx.cpu(), idx.cpu(), idx.cpu(), y.cpu())  # no CPU path
+
+
+def test_graphed_step_with_device_sampler(pkg):
+    """The whole of src/train.py:276-306 as one CUDA graph: positives in, negatives drawn on the device per replay."""
+    g = load_golden("small_full")
+    m = _product_model(pkg, g)
+    m.train()
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    n_pos = 16
+    ph, pt, pr = ei[0, :n_pos].clone(), ei[1, :n_pos].clone(), et[:n_pos].clone()
+    torch.manual_seed(1)
+    smp = pkg.NegativeSampler(g["num_nodes"], 1)
+    step = pkg.GraphedTrainStep(m, ei, et, batch_size=2 * n_pos, sampler=smp)
+    l1 = float(step.run_positives(ph, pt, pr)); neg1 = (step.heads[n_pos:].clone(), step.tails[n_pos:].clone())
+    l2 = float(step.run_positives(ph, pt, pr)); neg2 = (step.heads[n_pos:].clone(), step.tails[n_pos:].clone())
+    assert torch.equal(step.heads[:n_pos], ph) and torch.equal(step.labels, torch.cat([torch.ones(n_pos), torch.zeros(n_pos)]).to(DEV))
+    assert not (torch.equal(neg1[0], neg2[0]) and torch.equal(neg1[1], neg2[1]))            # fresh negatives per replay
+    assert l1 == l1 and l2 == l2 and all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # the replayed step equals the eager step on the batch it drew
+    want = F.binary_cross_entropy_with_logits(m(ei, et, step.heads, step.tails, step.rels), step.labels)
+    torch.testing.assert_close(torch.tensor(l2), want.detach().cpu(), rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        step(ph, pt, pr, step.labels)

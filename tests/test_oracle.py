@@ -146,3 +146,18 @@ def test_rank_oracle_brackets_argsort_rank():
         order = torch.argsort(s[i], descending=True)
         rank = int((order == true[i]).nonzero()[0]) + 1
         assert int(opt[i]) <= rank <= int(pes[i])
+
+
+def test_negative_batch_oracle_layout_and_rates():
+    """The restated sampler + batch assembly (reference src/train.py:59-97, :281-288): the properties the device sampler
+    is tested for on the GPU."""
+    g = torch.Generator().manual_seed(0)
+    N, n, k = 1000, 4096, 2
+    ph, pt, pr = torch.randint(0, N, (n,), generator=g), torch.randint(0, N, (n,), generator=g), torch.randint(0, 3, (n,), generator=g)
+    h, t, r, y = O.negative_batch_ref(ph, pt, pr, N, k, generator=g)
+    assert torch.equal(h[:n], ph) and torch.equal(t[:n], pt) and torch.equal(r, torch.cat([pr, pr.repeat_interleave(k)]))
+    assert y.tolist() == [1.0] * n + [0.0] * (n * k)
+    keep_h, keep_t = h[n:] == ph.repeat_interleave(k), t[n:] == pt.repeat_interleave(k)
+    assert bool((keep_h | keep_t).all())
+    assert 0.47 < float((~keep_h).float().mean()) < 0.53
+    assert O.accuracy_count_ref(torch.tensor([2.0, -1.0, 0.5]), torch.tensor([1.0, 0.0, 0.0])) == 2
