@@ -239,12 +239,11 @@ def run_ours(args, rank, world, local_rank):
     def allreduce_graphed():
         if world > 1:
             # the step's own gradient buffers (no flat copy, no accumulate kernels): ONE coalesced NCCL all-reduce
-            # over all of them, then one multi-tensor scale
+            # over all of them
             grads = [p.grad for p in params]
             with dist._coalescing_manager(device=dev):
                 for g in grads:
-                    dist.all_reduce(g)
-            torch._foreach_mul_(grads, 1.0 / world)
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG)      # NCCL averages in the reduction: no scaling pass
 
     allreduce_grads = allreduce_graphed     # noqa: F811
     for _ in range(max(args.warmup, 3)):
