@@ -418,15 +418,18 @@ aggregate_rows_kernel(const AggParams p) {
         };
         while (e + U <= end) batch(std::integral_constant<int, U>{});
         if (TAILPRED) {
-          // narrow rows are latency bound: ONE predicated batch for the < U remaining edges instead of up to three
-          // dependent power-of-two batches (masked edges add exact zeros, the order of the sum is unchanged)
-          if (e < end) {
-            if (e + U > wbase + 2 * G) refill(e);
+          // narrow rows: ONE predicated batch for the < U remaining edges instead of up to three dependent
+          // power-of-two batches, of the smallest width (1, 2, 4, U) that holds them — a graph with many relations has
+          // mostly one- and two-edge segments, and every unrolled slot costs issue cycles.  Masked edges add exact
+          // zeros, the order of the sum is unchanged.
+          auto tail = [&](auto ub) {
+            constexpr int UB = decltype(ub)::value;
+            if (e + UB > wbase + 2 * G) refill(e);
             const int n = end - e;
-            float4 v[U][VPL];
-            float w[U];
+            float4 v[UB][VPL];
+            float w[UB];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < UB; ++u) {
               const int off = e + u - wbase;
               const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
               if (W) w[u] = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
@@ -435,13 +438,18 @@ aggregate_rows_kernel(const AggParams p) {
               for (int k = 0; k < VPL; ++k) v[u][k] = (u < n) ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < UB; ++u)
 #pragma unroll
               for (int k = 0; k < VPL; ++k) {
                 if (W) fma4(acc[k], (u < n) ? w[u] : 0.f, v[u][k]); else add4(acc[k], v[u][k]);
               }
             e = end;
-          }
+          };
+          const int n_left = end - e;
+          if (n_left == 1) batch(std::integral_constant<int, 1>{});
+          else if (n_left == 2) batch(std::integral_constant<int, (U >= 2 ? 2 : 1)>{});
+          else if (n_left > 0 && n_left <= 4 && U > 4) tail(std::integral_constant<int, (U > 4 ? 4 : 1)>{});
+          else if (n_left > 0) tail(std::integral_constant<int, U>{});
         } else {
           if (U > 4 && e + 4 <= end) batch(std::integral_constant<int, (U > 4 ? 4 : 1)>{});
           if (U > 2 && e + 2 <= end) batch(std::integral_constant<int, (U > 2 ? 2 : 1)>{});
