@@ -367,6 +367,11 @@ int rgcn_allpairs_scores(const float* A, int64_t lda, int64_t na, const float* B
 int rgcn_allpairs_rank(const float* A, int64_t lda, int64_t nq, const float* B, int64_t ldb,
                        const int64_t* b_idx, int64_t nb, int32_t d, const int64_t* true_pos,
                        float* thr, int32_t* greater, int32_t* equal, rgcn_stream_t stream);
+/* The same two counts from a MATERIALISED score block scores[nq, ld] (first n_cand columns; e.g. produced on the tensor
+ * cores by rgcn_transform_dgrad(A' planes, candidate rows)): the threshold is scores[i, true_pos[i]], the true tail is
+ * excluded by index.  thr (optional) receives the thresholds. */
+int rgcn_rank_count(const float* scores, int64_t ld, int64_t nq, int64_t n_cand, const int64_t* true_pos,
+                    float* thr, int32_t* greater, int32_t* equal, rgcn_stream_t stream);
 /* ------------------------------------------------------------------------------------------
  * Fused link-prediction loss.  Replaces nn.BCEWithLogitsLoss (mean) over the batch logits and the
  * sigmoid > 0.5 accuracy count (src/train.py:139, :300, :321-322):

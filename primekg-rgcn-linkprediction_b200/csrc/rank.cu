@@ -200,3 +200,49 @@ extern "C" int rgcn_allpairs_rank(const float* A, int64_t lda, int64_t nq, const
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
+
+// ---- rank from a materialised score block (the tensor-core path) ---------------------------------------------------
+// greater[i] = #{j != t_i : s[i, j] > s[i, t_i]}, equal[i] = #{j != t_i : s[i, j] == s[i, t_i]} over the first n_cand
+// columns of row i; the threshold is read from the same matrix, the true tail is excluded by INDEX, so there are no
+// self-comparison artefacts whatever the accumulation order of the GEMM that produced the scores.
+namespace rgcn {
+__global__ void __launch_bounds__(256) rank_count_kernel(const float* __restrict__ s, int64_t ld, int64_t nq, int64_t n_cand,
+                                                         const int64_t* __restrict__ true_pos, float* __restrict__ thr,
+                                                         int32_t* __restrict__ greater, int32_t* __restrict__ equal) {
+  pdl_enter();
+  __shared__ int sg[8], se[8];
+  const int64_t i = blockIdx.x;
+  if (i >= nq) return;
+  const float* __restrict__ row = s + i * ld;
+  const int64_t t = true_pos[i];
+  const float th = row[t];
+  int g = 0, e = 0;
+  for (int64_t j = threadIdx.x; j < n_cand; j += 256) {
+    const float v = row[j];
+    if (j != t) { g += v > th; e += v == th; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    g += __shfl_xor_sync(0xffffffffu, g, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = g; se[threadIdx.x >> 5] = e; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { g += sg[w]; e += se[w]; }
+    greater[i] = g; equal[i] = e;
+    if (thr) thr[i] = th;
+  }
+}
+}  // namespace rgcn
+
+extern "C" int rgcn_rank_count(const float* scores, int64_t ld, int64_t nq, int64_t n_cand, const int64_t* true_pos,
+                               float* thr, int32_t* greater, int32_t* equal, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(nq >= 0 && n_cand > 0 && ld >= n_cand, "rank_count: bad sizes");
+  RGCN_CHECK_ARG(nq == 0 || (scores && true_pos && greater && equal), "rank_count: null argument");
+  if (nq == 0) return RGCN_OK;
+  RGCN_CUDA(launch_pdl(rgcn::rank_count_kernel, dim3((unsigned)nq), dim3(256), 0, (cudaStream_t)stream, scores, ld, nq, n_cand,
+                       true_pos, thr, greater, equal));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+

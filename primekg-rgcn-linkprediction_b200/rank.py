@@ -3,7 +3,15 @@
 * ``score_all_pairs``  — DistMult ``(h * r) @ T^T`` (reference src/models/rgcn.py:234-241) or cosine ``(cos + 1) / 2``
   (src/compare_methods.py:384-397; src/medical_validation.py:222-239) over index lists, gathers fused.
 * ``rank_true_tails``  — 1-indexed rank of the true tail among all candidates, the quantity the Python loop at
-  src/evaluate.py:266-276 extracts with one ``argsort`` per row, computed without the [batch, N] score matrix.
+  src/evaluate.py:266-276 extracts with one ``argsort`` per row.
+
+Both are a dense contraction ``A' @ B^T`` over the feature width and run on the tensor cores by default (``method="tc"``):
+the prepared query rows become bf16 hi / lo operand planes and the candidate rows the K-major "weight" operand of the
+tcgen05 kernel behind ``rgcn_transform_dgrad`` (three bf16 products with fp32 accumulation, 3-7e-6 relative error — the
+fp32 mode of the encoder).  ``alpha`` / ``beta`` ride along as one extra K column, so the cosine rescale costs nothing.
+The ranking counts come from the score block itself (``rgcn_rank_count``), a block of queries at a time.
+``method="simt"`` keeps the fp32 FMA tile kernels of ``csrc/rank.cu`` (every output accumulated in ascending k order with
+``fmaf``; they never materialise the [queries, candidates] block when ranking).
 """
 from __future__ import annotations
 
@@ -13,6 +21,8 @@ import torch
 
 from . import _lib
 from .graph import _ptr, _stream
+
+_RANK_BLOCK = 2048       # queries ranked per score block of the tensor-core path (2048 x 30,926 fp32 = 253 MB)
 
 
 def _prep(emb: torch.Tensor, idx: Optional[torch.Tensor], rel_table: Optional[torch.Tensor],
@@ -36,8 +46,43 @@ def _prep(emb: torch.Tensor, idx: Optional[torch.Tensor], rel_table: Optional[to
     return out
 
 
+def _tc_block(A: torch.Tensor, Bext: torch.Tensor, alpha: float, beta: float) -> torch.Tensor:
+    """[rows(A), rows(Bext)] = alpha * A @ Bext[:, :d]^T + beta on the tensor cores.  ``Bext`` is the candidate operand
+    from ``_tc_candidates`` ([nb_pad, d + 8] when alpha / beta ride along, else [nb_pad, d])."""
+    from . import ops
+    d = A.size(1)
+    dk = Bext.size(1)
+    if dk != d:
+        Ae = torch.zeros(A.size(0), dk, dtype=torch.float32, device=A.device)
+        torch.mul(A, alpha, out=Ae[:, :d])
+        Ae[:, d] = 1.0
+        A = Ae
+    planes = ops.alloc_planes(A.size(0), dk, "fp32", A.device)
+    ops.split_planes(A, planes)
+    return ops.transform_dgrad(planes, dk, Bext, None, "fp32")
+
+
+def _tc_candidates(B: torch.Tensor, b_idx: Optional[torch.Tensor], alpha: float, beta: float) -> torch.Tensor:
+    """Candidate rows as the K-major operand: gathered, padded to a multiple of 8 rows with zeros and — when the scores
+    are to be rescaled — widened by 8 columns of which the first holds ``beta`` (it meets the constant 1 of the queries)."""
+    nb = B.size(0) if b_idx is None else b_idx.numel()
+    d = B.size(1)
+    ext = alpha != 1.0 or beta != 0.0
+    Be = torch.zeros((nb + 7) // 8 * 8, d + (8 if ext else 0), dtype=torch.float32, device=B.device)
+    if b_idx is None:
+        Be[:nb, :d] = B
+    else:
+        lib = _lib.load()
+        view = Be[:nb, :d]
+        _lib.check(lib.rgcn_rows_prepare(_ptr(B), B.stride(0), _ptr(b_idx), nb, d, None, None, 0, _ptr(view), Be.stride(0),
+                                         _stream(B.device)), "rgcn_rows_prepare")
+    if ext:
+        Be[:nb, d] = beta
+    return Be
+
+
 def scores_from_rows(A: torch.Tensor, B: torch.Tensor, b_idx: Optional[torch.Tensor] = None, alpha: float = 1.0,
-                     beta: float = 0.0) -> torch.Tensor:
+                     beta: float = 0.0, method: str = "tc") -> torch.Tensor:
     """out[i, j] = alpha * <A[i], B[b_idx[j]]> + beta  (fp32, fused gather of the candidate rows)."""
     lib = _lib.load()
     A = A.detach().to(torch.float32).contiguous()
@@ -46,6 +91,11 @@ def scores_from_rows(A: torch.Tensor, B: torch.Tensor, b_idx: Optional[torch.Ten
         B = B.contiguous()
     b_idx = None if b_idx is None else b_idx.to(torch.int64).contiguous()
     nb = B.size(0) if b_idx is None else b_idx.numel()
+    if method == "tc" and A.size(0) > 0 and nb > 0 and A.size(1) % 4 == 0:
+        out = _tc_block(A, _tc_candidates(B, b_idx, alpha, beta), alpha, beta)
+        return out[:, :nb]
+    if method not in ("tc", "simt"):
+        raise ValueError("method must be 'tc' (tensor cores) or 'simt' (fp32 FMA tiles)")
     out = torch.empty(A.size(0), nb, dtype=torch.float32, device=A.device)
     _lib.check(lib.rgcn_allpairs_scores(_ptr(A), A.stride(0), A.size(0), _ptr(B), B.stride(0), _ptr(b_idx), nb,
                                         A.size(1), alpha, beta, _ptr(out), out.stride(0), _stream(A.device)),
@@ -54,22 +104,22 @@ def scores_from_rows(A: torch.Tensor, B: torch.Tensor, b_idx: Optional[torch.Ten
 
 
 def score_all_pairs(emb: torch.Tensor, a_idx: torch.Tensor, b_idx: torch.Tensor,
-                    rel_vec: Optional[torch.Tensor] = None, cosine: bool = False) -> torch.Tensor:
+                    rel_vec: Optional[torch.Tensor] = None, cosine: bool = False, method: str = "tc") -> torch.Tensor:
     """[len(a_idx), len(b_idx)] scores.  DistMult: (emb[a] * rel_vec) . emb[b];  cosine: (cos(emb[a], emb[b]) + 1) / 2."""
     if cosine:
         A = _prep(emb, a_idx, None, None, True)
         Bn = _prep(emb, b_idx, None, None, True)
-        return scores_from_rows(A, Bn, None, 0.5, 0.5)
+        return scores_from_rows(A, Bn, None, 0.5, 0.5, method=method)
     if rel_vec is not None:
         table = rel_vec.reshape(1, -1)
         A = _prep(emb, a_idx, table, torch.zeros(a_idx.numel(), dtype=torch.int64, device=emb.device), False)
     else:
         A = _prep(emb, a_idx, None, None, False)
-    return scores_from_rows(A, emb, b_idx)
+    return scores_from_rows(A, emb, b_idx, method=method)
 
 
 def rank_true_tails(emb: torch.Tensor, rel_table: torch.Tensor, heads: torch.Tensor, rels: torch.Tensor,
-                    tails: torch.Tensor, candidates: Optional[torch.Tensor] = None
+                    tails: torch.Tensor, candidates: Optional[torch.Tensor] = None, method: str = "tc"
                     ) -> Tuple[torch.Tensor, torch.Tensor]:
     """(rank, ties): rank[i] = 1 + #{candidates scoring strictly above the true tail} (int64, 1-indexed like
     src/evaluate.py:274); ties[i] = #{other candidates with exactly the true tail's score}.  ``candidates`` = index list
@@ -83,9 +133,19 @@ def rank_true_tails(emb: torch.Tensor, rel_table: torch.Tensor, heads: torch.Ten
     nb = B.size(0) if cand is None else cand.numel()
     nq = A.size(0)
     tails = tails.to(torch.int64).contiguous()
-    thr = torch.empty(nq, dtype=torch.float32, device=A.device)
     greater = torch.empty(nq, dtype=torch.int32, device=A.device)
     equal = torch.empty(nq, dtype=torch.int32, device=A.device)
+    if method == "tc" and nq > 0 and nb > 0 and A.size(1) % 4 == 0:
+        Bext = _tc_candidates(B, cand, 1.0, 0.0)
+        for q0 in range(0, nq, _RANK_BLOCK):
+            q1 = min(q0 + _RANK_BLOCK, nq)
+            S = _tc_block(A[q0:q1], Bext, 1.0, 0.0)
+            _lib.check(lib.rgcn_rank_count(_ptr(S), S.stride(0), q1 - q0, nb, _ptr(tails[q0:q1]), None, _ptr(greater[q0:q1]),
+                                           _ptr(equal[q0:q1]), _stream(A.device)), "rgcn_rank_count")
+        return greater.to(torch.int64) + 1, equal.to(torch.int64)
+    if method not in ("tc", "simt"):
+        raise ValueError("method must be 'tc' (tensor cores) or 'simt' (fp32 FMA tiles)")
+    thr = torch.empty(nq, dtype=torch.float32, device=A.device)
     _lib.check(lib.rgcn_allpairs_rank(_ptr(A), A.stride(0), nq, _ptr(B), B.stride(0), _ptr(cand), nb, A.size(1),
                                       _ptr(tails), _ptr(thr), _ptr(greater), _ptr(equal), _stream(A.device)),
                "rgcn_allpairs_rank")

@@ -49,8 +49,9 @@ def test_score_all_tails_backward(pkg):
                                rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("N,d,B", [(30926, 128, 1024), (777, 64, 130)])
-def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B):
+@pytest.mark.parametrize("method", ["tc", "simt"])
+@pytest.mark.parametrize("N,d,B", [(30926, 128, 1024), (777, 64, 130), (30926, 256, 2500)])
+def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B, method):
     """rank = 1 + #greater must lie inside the oracle's [optimistic, pessimistic] bracket evaluated with an epsilon
     band (two fp32 summation orders), and equal the exact count computed from our own score matrix."""
     torch.manual_seed(2)
@@ -62,7 +63,7 @@ def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B):
     rels = torch.randint(0, R, (B,), device=DEV)
     emb[5] = emb[9]                                   # an exact duplicate entity => exact score ties
     tails[0] = 5
-    rank, ties = pkg.rank_true_tails(emb, table, heads, rels, tails)
+    rank, ties = pkg.rank_true_tails(emb, table, heads, rels, tails, method=method)
     scores = O.distmult_allpairs_ref(emb.double(), heads, torch.arange(N, device=DEV), table[rels].double())
     s_true = scores.gather(1, tails.view(-1, 1))
     eps = 1e-4 * scores.abs().max()
@@ -72,7 +73,7 @@ def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B):
     assert int(ties[0]) >= 1                          # the duplicate of the true tail is an exact tie
     # exactness against our own fp32 scores
     from primekg_rgcn_linkprediction_b200.rank import _prep, scores_from_rows
-    S = scores_from_rows(_prep(emb, heads, table, rels, False), emb)
+    S = scores_from_rows(_prep(emb, heads, table, rels, False), emb, method=method)
     st = S.gather(1, tails.view(-1, 1))
     others = torch.ones_like(S, dtype=torch.bool)
     others.scatter_(1, tails.view(-1, 1), False)
@@ -82,17 +83,19 @@ def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B):
     assert 0 < m["mrr"] <= 1 and m["hits@100"] >= m["hits@10"]
 
 
-def test_all_pairs_drug_disease_sweep(pkg):
-    """BASELINE cfg4: all 6,282 x 5,593 drug-disease pairs, DistMult and cosine."""
+@pytest.mark.parametrize("method", ["tc", "simt"])
+def test_all_pairs_drug_disease_sweep(pkg, method):
+    """BASELINE cfg4: all 6,282 x 5,593 drug-disease pairs, DistMult and cosine; on the tensor cores (three bf16 products,
+    fp32 accumulation) and through the fp32 FMA tiles."""
     torch.manual_seed(3)
     emb = torch.randn(30926, 128, device=DEV)
     drugs = torch.arange(5593, 11875, device=DEV)
     diseases = torch.arange(0, 5593, device=DEV)
     rel = torch.randn(128, device=DEV)
-    got = pkg.score_all_pairs(emb, drugs, diseases, rel_vec=rel)
+    got = pkg.score_all_pairs(emb, drugs, diseases, rel_vec=rel, method=method)
     want = O.distmult_allpairs_ref(emb, drugs, diseases, rel)
     assert got.shape == (6282, 5593)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
-    gotc = pkg.score_all_pairs(emb, drugs, diseases, cosine=True)
+    gotc = pkg.score_all_pairs(emb, drugs, diseases, cosine=True, method=method)
     wantc = O.cosine_allpairs_ref(emb, drugs, diseases)
-    torch.testing.assert_close(gotc, wantc, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gotc, wantc, rtol=1e-5, atol=1e-5 if method == "simt" else 2e-5)
