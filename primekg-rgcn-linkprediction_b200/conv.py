@@ -60,6 +60,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         # in_mask_scale: x is the fused ReLU (+ dropout) output of the layer upstream, whose backward will want this
         # layer's input gradient masked by x > 0 and scaled — the backward walk can write that directly (rowsparse.py)
         ctx.in_mask_scale = in_mask_scale if (shared and in_mask_scale is not None) else None
+        ctx.x_is_param = bool(shared and x_src.is_leaf and x_src.requires_grad)     # e.g. the embedding table
         ctx.save_for_backward(A[0], A[1], W, root, out if relu else None, x_src if ctx.in_mask_scale is not None else None)
         return out
 
@@ -84,7 +85,8 @@ class _RGCNLayerFn(torch.autograd.Function):
         res = ops.layer_bwd(
             graph, gO.contiguous(), out, mask_scale, (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
             need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any, rows=rows, g_ready=g_ready,
-            next_mask=next_mask)
+            next_mask=next_mask,
+            gx_out=ops.param_grad(graph.n_src, d_in, device=gO.device) if (need_x and ctx.x_is_param) else None)
         gx, gA, gWf, groot, gb = res[:5]
         if next_mask is not None:
             rowsparse.announce_planes(gx, x_in, ctx.in_mask_scale, mode, res[5])

@@ -48,7 +48,15 @@ class GraphedTrainStep:
             self.pos_rels = torch.zeros(n_pos, dtype=torch.int64, device=dev)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat_grad = None
-        if flat_grads:
+        self.arena = None
+        if flat_grads == "arena":
+            # the backward kernels write the parameter gradients straight into one flat buffer (ops.GradArena): no zero
+            # fill, no accumulate kernels, and ONE tensor to all-reduce
+            from . import ops
+            self.arena = ops.GradArena(sum((p.numel() + 63) // 64 * 64 for p in self.params), dev)
+            for p in self.params:
+                p.grad = None
+        elif flat_grads:
             # static gradient buffers: views into ONE flat tensor, so zeroing is a single fill and a data-parallel
             # caller all-reduces ``flat_grad`` in place (every p.grad sees the result); costs one accumulate per tensor
             self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
@@ -72,8 +80,24 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss, self.scores = self._step()
         self._bind_grads()
+        if self.arena is not None:
+            lo, hi = self.arena.buf.data_ptr(), self.arena.buf.data_ptr() + self.arena.buf.numel() * 4
+            if all(g is not None and lo <= g.data_ptr() < hi for g in self._grads):
+                self.flat_grad = self.arena.used        # every parameter gradient lives inside: all-reduce this one tensor
+            # else (e.g. basis layers, whose gradients autograd assembles): p.grad are ordinary tensors, flat_grad stays None
 
     def _step(self):
+        if self.arena is not None:
+            from . import ops
+            self.arena.reset()
+            ops.set_grad_arena(self.arena)
+            try:
+                return self._step_body()
+            finally:
+                ops.set_grad_arena(None)
+        return self._step_body()
+
+    def _step_body(self):
         if self.sampler is not None:
             self.sampler.batch(self.pos_heads, self.pos_tails, self.pos_rels,
                                out=(self.heads, self.tails, self.rels, self.labels))
@@ -83,7 +107,7 @@ class GraphedTrainStep:
         else:
             scores = self.model(self.edge_index, self.edge_type, self.heads, self.tails, self.rels)
             loss = self.loss_fn(scores, self.labels)
-        if self.flat_grad is not None:
+        if self.flat_grad is not None and self.arena is None:
             self.flat_grad.zero_()
             loss.backward()
         else:
@@ -91,7 +115,7 @@ class GraphedTrainStep:
         return loss.detach(), scores.detach()
 
     def _bind_grads(self) -> None:
-        if self.flat_grad is None:
+        if self.flat_grad is None or self.arena is not None:
             for p, g in zip(self.params, self._grads):
                 p.grad = g
 

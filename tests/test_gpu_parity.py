@@ -1200,3 +1200,36 @@ def test_graphed_step_with_device_sampler(pkg):
     torch.testing.assert_close(torch.tensor(l2), want.detach().cpu(), rtol=1e-5, atol=1e-6)
     with pytest.raises(RuntimeError):
         step(ph, pt, pr, step.labels)
+
+
+def test_graphed_step_grad_arena(pkg):
+    """flat_grads="arena": every parameter gradient is a slice of one flat buffer (what a data-parallel caller
+    all-reduces in one call) and equals the plain graphed step's gradient."""
+    g = load_golden("small_full")
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    b = [g[k].to(DEV) for k in ("heads", "tails", "rels", "labels")]
+    m = _product_model(pkg, g)
+    m.train()
+    plain = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel())
+    plain(*b)
+    want = {k: p.grad.clone() for k, p in m.named_parameters()}
+    step = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel(), flat_grads="arena")
+    assert step.flat_grad is not None
+    loss = step(*b)
+    torch.testing.assert_close(loss.cpu(), g["loss"], rtol=1e-4, atol=1e-5)
+    lo, hi = step.flat_grad.data_ptr(), step.flat_grad.data_ptr() + step.flat_grad.numel() * 4
+    for k, p in m.named_parameters():
+        assert lo <= p.grad.data_ptr() < hi, k
+        _close_by_scale(p.grad, want[k], k, rtol=1e-4, atol=1e-5)
+    # an in-place all-reduce stand-in on the flat tensor is seen by every p.grad
+    before = m.encoder.conv1.root.grad.clone()
+    step.flat_grad.mul_(2.0)
+    assert torch.equal(m.encoder.conv1.root.grad, before * 2.0)
+    # basis layers: autograd assembles weight / comp gradients itself -> no flat tensor, ordinary gradients
+    gb = load_golden("small_basis")
+    mb = _product_model(pkg, gb)
+    mb.train()
+    sb = pkg.GraphedTrainStep(mb, gb["edge_index"].to(DEV), gb["edge_type"].to(DEV), batch_size=gb["heads"].numel(),
+                              flat_grads="arena")
+    sb(*[gb[k].to(DEV) for k in ("heads", "tails", "rels", "labels")])
+    assert sb.flat_grad is None and all(p.grad is not None for p in mb.parameters())
