@@ -153,3 +153,66 @@ def test_synthetic_full_kg_shape():
     kg = synth.primekg_full(num_directed_edges=200_000)
     assert kg.num_nodes == 129_375 and kg.num_relations == 30 and kg.num_edges == 200_000
     assert int(kg.edge_type.max()) == 29 and int(kg.edge_index.max()) < 129_375
+
+
+def test_rowsparse_handover_guards(lib_built, monkeypatch):
+    """Host logic of the row-sparse hand-over (rowsparse.py), on CPU tensors: the announcement is honoured only for the very
+    buffer that was announced, untouched, and is consumed by the first claim."""
+    from primekg_rgcn_linkprediction_b200 import rowsparse
+    monkeypatch.delenv("PRIMEKG_RGCN_SPARSE_BWD", raising=False)
+    rowsparse.clear()
+    rowsparse.stats.update(claimed=0, declined=0)
+    dense = torch.zeros(100, 8)
+    rows = torch.tensor([3, 7, 3])
+    rowsparse.announce(dense, rows)
+    assert rowsparse.claim(dense) is rows and rowsparse.claim(dense) is None          # consumed
+    rowsparse.announce(dense, rows)
+    assert rowsparse.claim(dense.clone()) is None                                      # another buffer (engine summed a copy)
+    rowsparse.announce(dense, rows)
+    dense.add_(1.0)                                                                    # in-place accumulation bumps the version
+    assert rowsparse.claim(dense) is None
+    rowsparse.announce(dense, rows)
+    assert rowsparse.claim(dense[:50]) is None                                         # same storage, other shape
+    rowsparse.announce(dense, torch.arange(60))                                        # longer than MAX_FRACTION * N
+    assert rowsparse.claim(dense) is None
+    assert rowsparse.stats["claimed"] == 1 and rowsparse.stats["declined"] == 4
+    monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_BWD", "0")
+    rowsparse.announce(dense, rows)
+    assert rowsparse.claim(dense) is None                                              # switched off: nothing announced
+    # second hand-over (masked planes): off by default, keyed on the mask tensor, scale and mode
+    monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_BWD", "1")
+    mask = torch.ones(100, 8)
+    rowsparse.announce_planes(dense, mask, 2.0, "fp32", "payload")
+    assert rowsparse.claim_planes(dense, mask, 2.0, "fp32") is None                    # opt-in only
+    monkeypatch.setenv("PRIMEKG_RGCN_PLANES_HANDOVER", "1")
+    rowsparse.announce_planes(dense, mask, 2.0, "fp32", "payload")
+    assert rowsparse.claim_planes(dense, mask, 2.0, "fp32") == "payload"
+    rowsparse.announce_planes(dense, mask, 2.0, "fp32", "payload")
+    assert rowsparse.claim_planes(dense, mask.clone(), 2.0, "fp32") is None            # another mask tensor
+    rowsparse.announce_planes(dense, mask, 2.0, "fp32", "payload")
+    assert rowsparse.claim_planes(dense, mask, 1.0, "fp32") is None                    # another dropout scale
+    rowsparse.clear()
+
+
+def test_grad_arena_slices(lib_built):
+    """ops.GradArena: call-order slices of one flat buffer, 256-byte aligned, reset per step, overflow falls back."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    arena = ops.GradArena(64 * 4, "cpu")
+    a = arena.take(3, 5)
+    b = arena.take(64)
+    assert a.shape == (3, 5) and a.data_ptr() == arena.buf.data_ptr() and b.data_ptr() == arena.buf.data_ptr() + 64 * 4
+    assert arena.used.numel() == 128
+    assert arena.take(200) is None and arena.used.numel() == 128                        # too large: the caller allocates
+    arena.reset()
+    a2 = arena.take(3, 5)
+    assert a2.data_ptr() == a.data_ptr()                                               # same slices every step
+    ops.set_grad_arena(arena)
+    try:
+        arena.reset()
+        g = ops.param_grad(4, 4, device=torch.device("cpu"))
+        assert g.data_ptr() == arena.buf.data_ptr()
+        big = ops.param_grad(1000, device=torch.device("cpu"))
+        assert not (arena.buf.data_ptr() <= big.data_ptr() < arena.buf.data_ptr() + arena.buf.numel() * 4)
+    finally:
+        ops.set_grad_arena(None)
+    assert ops.param_grad(4, device=torch.device("cpu")).data_ptr() != arena.buf.data_ptr()
