@@ -236,6 +236,17 @@ int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t lda, int32_
                          void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Basis decomposition of the relation weights, RGCNConv(num_bases = B) (plumbed at src/models/rgcn.py:58, :76, :84):
+ *   rgcn_basis_combine     : W[r, :] = sum_b comp[r, b] * V[b, :]          (PyG: (comp @ weight.view(B, -1)).view(R, in, out))
+ *   rgcn_basis_combine_bwd : g_V[b, :] = sum_r comp[r, b] * gW[r, :],  g_comp[r, b] = <gW[r, :], V[b, :]>   (either may be NULL)
+ * comp [R, B], V / g_V [B, in_out], W / gW [R, in_out], all row-major fp32; R, B <= 64 (g_comp: B <= 16).
+ * ------------------------------------------------------------------------------------------ */
+int rgcn_basis_combine(const float* comp, const float* V, int32_t R, int32_t B, int64_t in_out, float* W,
+                       rgcn_stream_t stream);
+int rgcn_basis_combine_bwd(const float* comp, const float* V, const float* gW, int32_t R, int32_t B, int64_t in_out,
+                           float* g_V, float* g_comp, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * One layer per call.  rgcn_layer_fwd = rgcn_aggregate_fwd (H into the first R blocks of the operand planes, x_root
  * appended as the last block by the same kernel) + rgcn_transform_fwd: everything `RGCNConv.forward` does at
  * src/models/rgcn.py:123 / :128 (+ the ReLU / dropout of :124-125 when asked).  rgcn_layer_bwd = rgcn_split_planes

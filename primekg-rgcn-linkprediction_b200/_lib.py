@@ -85,6 +85,8 @@ PROTOTYPES = {
     "rgcn_transform_workspace_bytes": (sz, [i64, i32, i32]),
     "rgcn_transform_fwd": (C.c_int, [p, p, i64, i32, i32, p, p, p, i32, i64, i32, p, i64, i32, C.c_float, C.c_uint32, p,
                                      p, i32, i64, i64, p, sz, p]),
+    "rgcn_basis_combine": (C.c_int, [p, p, i32, i32, i64, p, p]),
+    "rgcn_basis_combine_bwd": (C.c_int, [p, p, p, i32, i32, i64, p, p, p]),
     "rgcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), p]),
     "rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), p]),
     "rgcn_p2p_push_rows": (C.c_int, [p, i64, i64, i32, p, i32, i64, i64, p]),

@@ -713,3 +713,41 @@ def link_loss(emb, rel_table, head, tail, rel, labels, p_drop: float = 0.0, seed
     if p_drop > 0 and counter is None:
         raise ValueError("link_loss: dropout needs a device counter (ops.rng_counter)")
     return _LinkLoss.apply(emb, rel_table, head, tail, rel, labels, float(p_drop), int(seed), counter)
+
+
+# ---- basis decomposition of the relation weights (RGCNConv(num_bases = B)) -------------------------------------------
+class _BasisCombine(torch.autograd.Function):
+    """W[r] = sum_b comp[r, b] V[b]  ([R, in, out] from comp [R, B] and V [B, in, out]) and its backward, on our kernels
+    (``rgcn_basis_combine`` / ``_bwd``) instead of a library matmul."""
+
+    @staticmethod
+    def forward(ctx, comp, V):
+        lib = _lib.load()
+        comp_c = comp.detach().to(torch.float32).contiguous()
+        V_c = V.detach().to(torch.float32).contiguous()
+        R, B = comp_c.shape
+        io = V_c[0].numel()
+        W = torch.empty(R, *V_c.shape[1:], dtype=torch.float32, device=V.device)
+        _lib.check(lib.rgcn_basis_combine(_ptr(comp_c), _ptr(V_c), R, B, io, _ptr(W), _stream(V.device)), "rgcn_basis_combine")
+        ctx.save_for_backward(comp_c, V_c)
+        return W
+
+    @staticmethod
+    def backward(ctx, gW):
+        lib = _lib.load()
+        comp, V = ctx.saved_tensors
+        R, B = comp.shape
+        gW = gW.to(torch.float32).contiguous()
+        g_comp = param_grad(R, B, device=V.device) if ctx.needs_input_grad[0] else None
+        g_V = param_grad(*V.shape, device=V.device) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.rgcn_basis_combine_bwd(_ptr(comp), _ptr(V), _ptr(gW), R, B, V[0].numel(), _ptr(g_V), _ptr(g_comp),
+                                              _stream(V.device)), "rgcn_basis_combine_bwd")
+        return g_comp, g_V
+
+
+def basis_combine(comp: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
+    if not V.is_cuda:
+        raise RuntimeError("basis_combine needs CUDA tensors: there is no CPU implementation of this path")
+    if comp.size(0) > 64 or comp.size(1) > 16 or V[0].numel() % 4:
+        raise ValueError("basis_combine handles up to 64 relations, 16 bases and in * out a multiple of 4")
+    return _BasisCombine.apply(comp, V)
