@@ -137,8 +137,10 @@ def rank_true_tails(emb: torch.Tensor, rel_table: torch.Tensor, heads: torch.Ten
     equal = torch.empty(nq, dtype=torch.int32, device=A.device)
     if method == "tc" and nq > 0 and nb > 0 and A.size(1) % 4 == 0:
         Bext = _tc_candidates(B, cand, 1.0, 0.0)
-        for q0 in range(0, nq, _RANK_BLOCK):
-            q1 = min(q0 + _RANK_BLOCK, nq)
+        # queries per score block: at most _RANK_BLOCK, and at most ~1 GiB of scores for very large candidate sets
+        qb = max(128, min(_RANK_BLOCK, (1 << 28) // max(Bext.size(0), 1) // 128 * 128))
+        for q0 in range(0, nq, qb):
+            q1 = min(q0 + qb, nq)
             S = _tc_block(A[q0:q1], Bext, 1.0, 0.0)
             _lib.check(lib.rgcn_rank_count(_ptr(S), S.stride(0), q1 - q0, nb, _ptr(tails[q0:q1]), None, _ptr(greater[q0:q1]),
                                            _ptr(equal[q0:q1]), _stream(A.device)), "rgcn_rank_count")
