@@ -34,10 +34,13 @@ class GraphedTrainStep:
         # default loss + a model that offers it: decoder, loss and accuracy in one kernel pair (model.link_loss)
         self.fused_loss = loss_fn is None and hasattr(model, "link_loss")
         self.correct = None
-        self.heads = torch.zeros(batch_size, dtype=torch.int64, device=dev)
-        self.tails = torch.zeros(batch_size, dtype=torch.int64, device=dev)
-        self.rels = torch.zeros(batch_size, dtype=torch.int64, device=dev)
-        self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+        # the static input buffers are views of ONE int64 [4, B] block (heads, tails, rels; row 3 holds the float32
+        # labels in its first 4 B bytes), so a caller that keeps its batch packed the same way in pinned host memory
+        # (``pack_batch``) pays one host-to-device copy per step instead of four (``load_packed``)
+        self.batch_size = batch_size
+        self.batch_buf = torch.zeros(4, batch_size, dtype=torch.int64, device=dev)
+        self.heads, self.tails, self.rels = self.batch_buf[0], self.batch_buf[1], self.batch_buf[2]
+        self.labels = self.batch_buf[3].view(torch.float32)[:batch_size]
         self.sampler = sampler
         if sampler is not None:
             if batch_size % (1 + sampler.num_neg_samples):
@@ -125,6 +128,33 @@ class GraphedTrainStep:
         self.tails.copy_(tails, non_blocking=non_blocking)
         self.rels.copy_(rels, non_blocking=non_blocking)
         self.labels.copy_(labels, non_blocking=non_blocking)
+
+    @staticmethod
+    def pack_batch(heads, tails, rels, labels, pin: bool = True) -> torch.Tensor:
+        """One int64 [4, B] host tensor in the layout of the step's input block (pinned by default)."""
+        b = heads.numel()
+        out = torch.empty(4, b, dtype=torch.int64)
+        if pin and torch.cuda.is_available():
+            out = out.pin_memory()
+        out[0].copy_(heads); out[1].copy_(tails); out[2].copy_(rels)
+        out[3].zero_()
+        out[3].view(torch.float32)[:b].copy_(labels)
+        return out
+
+    def load_packed(self, packed: torch.Tensor, non_blocking: bool = True) -> None:
+        """Copy a ``pack_batch`` block (host or device) into the static input buffers: one copy."""
+        if packed.shape != self.batch_buf.shape or packed.dtype != torch.int64:
+            raise ValueError(f"packed batch must be int64 {tuple(self.batch_buf.shape)}")
+        self.batch_buf.copy_(packed, non_blocking=non_blocking)
+
+    def run_packed(self, packed: torch.Tensor) -> torch.Tensor:
+        """One step from a ``pack_batch`` block."""
+        if self.sampler is not None:
+            raise RuntimeError("this step draws its own negatives: call run_positives(pos_heads, pos_tails, pos_rels)")
+        self.load_packed(packed)
+        self.graph.replay()
+        self._bind_grads()
+        return self.loss
 
     def run_positives(self, pos_heads, pos_tails, pos_rels, non_blocking: bool = True) -> torch.Tensor:
         """One step from positive edges only (needs ``sampler``): negatives, labels, forward, loss, backward in the graph."""

@@ -1256,3 +1256,25 @@ def test_basis_combine_matches_matmul(pkg, R, B, din, dout):
     comp.grad = None; V.grad = None
     (ops.basis_combine(comp, V) * coef).sum().backward()
     assert torch.equal(comp.grad, g1)
+
+
+def test_graphed_step_packed_batch(pkg):
+    """One pinned [4, B] block per step (heads, tails, rels, labels bits) == the four separate copies."""
+    g = load_golden("small_full")
+    m = _product_model(pkg, g)
+    m.train()
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    b = [g[k] for k in ("heads", "tails", "rels", "labels")]
+    step = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel())
+    l_sep = step(*[t.to(DEV) for t in b]).clone()
+    grads = {k: p.grad.clone() for k, p in m.named_parameters()}
+    packed = pkg.GraphedTrainStep.pack_batch(*b)
+    assert packed.is_pinned() and packed.shape == (4, b[0].numel())
+    step.heads.zero_(); step.labels.zero_()
+    l_packed = step.run_packed(packed).clone()
+    assert torch.equal(step.heads.cpu(), b[0]) and torch.equal(step.labels.cpu(), b[3])
+    torch.testing.assert_close(l_packed, l_sep, rtol=1e-6, atol=1e-7)
+    for k, p in m.named_parameters():
+        _close_by_scale(p.grad, grads[k], k, rtol=1e-4, atol=1e-5)
+    with pytest.raises(ValueError):
+        step.load_packed(packed[:3])
