@@ -21,8 +21,16 @@ from .ops import bce_with_logits
 
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, edge_index: torch.Tensor, edge_type: torch.Tensor, batch_size: int,
-                 loss_fn: Optional[Callable] = None, warmup: int = 3, flat_grads: bool = False, sampler=None):
-        """``sampler`` (a ``NegativeSampler``): the captured step starts from ``batch_size / (1 + num_neg_samples)``
+                 loss_fn: Optional[Callable] = None, warmup: int = 3, flat_grads: bool = False, sampler=None,
+                 host_io: bool = False):
+        """``host_io``: the captured graph starts with the host-to-device copy of the batch from a pinned staging block
+        (``self.host_batch``, int64 [4, B] in ``pack_batch`` layout) and ends with the device-to-host copy of the loss
+        and the correct-count into pinned memory (``self.host_loss``, ``self.host_correct``): one graph launch per step
+        is the whole host-side work.  Fill ``host_batch`` (``step.host_batch.copy_(packed)``), call ``replay_host()``,
+        synchronise, read ``host_loss``; do not rewrite ``host_batch`` before the previous replay has consumed it
+        (the reference's loop reads ``loss.item()`` every step, src/train.py:322, which is such a synchronisation).
+
+        ``sampler`` (a ``NegativeSampler``): the captured step starts from ``batch_size / (1 + num_neg_samples)``
         POSITIVE edges and draws the negatives, the concatenation and the labels on the device inside the graph
         (reference src/train.py:276-288) — ``step.run_positives(pos_head, pos_tail, pos_rel)``; fresh negatives on every
         replay."""
@@ -41,6 +49,11 @@ class GraphedTrainStep:
         self.batch_buf = torch.zeros(4, batch_size, dtype=torch.int64, device=dev)
         self.heads, self.tails, self.rels = self.batch_buf[0], self.batch_buf[1], self.batch_buf[2]
         self.labels = self.batch_buf[3].view(torch.float32)[:batch_size]
+        self.host_io = bool(host_io)
+        if self.host_io:
+            self.host_batch = torch.zeros(4, batch_size, dtype=torch.int64).pin_memory()
+            self.host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.host_correct = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.sampler = sampler
         if sampler is not None:
             if batch_size % (1 + sampler.num_neg_samples):
@@ -101,6 +114,16 @@ class GraphedTrainStep:
         return self._step_body()
 
     def _step_body(self):
+        if self.host_io:
+            self.batch_buf.copy_(self.host_batch, non_blocking=True)          # a memcpy node of the captured graph
+        out = self._step_compute()
+        if self.host_io:
+            self.host_loss.copy_(out[0].reshape(1), non_blocking=True)
+            if self.correct is not None:
+                self.host_correct.copy_(self.correct.reshape(1), non_blocking=True)
+        return out
+
+    def _step_compute(self):
         if self.sampler is not None:
             self.sampler.batch(self.pos_heads, self.pos_tails, self.pos_rels,
                                out=(self.heads, self.tails, self.rels, self.labels))
@@ -155,6 +178,15 @@ class GraphedTrainStep:
         self.graph.replay()
         self._bind_grads()
         return self.loss
+
+    def replay_host(self) -> torch.Tensor:
+        """``host_io`` step: batch from ``host_batch``, results into ``host_loss`` / ``host_correct`` — one graph launch.
+        Returns the pinned loss tensor (valid after a synchronisation)."""
+        if not self.host_io:
+            raise RuntimeError("replay_host needs a GraphedTrainStep built with host_io=True")
+        self.graph.replay()
+        self._bind_grads()
+        return self.host_loss
 
     def run_positives(self, pos_heads, pos_tails, pos_rels, non_blocking: bool = True) -> torch.Tensor:
         """One step from positive edges only (needs ``sampler``): negatives, labels, forward, loss, backward in the graph."""

@@ -1278,3 +1278,28 @@ def test_graphed_step_packed_batch(pkg):
         _close_by_scale(p.grad, grads[k], k, rtol=1e-4, atol=1e-5)
     with pytest.raises(ValueError):
         step.load_packed(packed[:3])
+
+
+def test_graphed_step_host_io(pkg):
+    """host_io=True: the batch's H2D copy and the loss's D2H copy are nodes of the captured graph."""
+    g = load_golden("small_full")
+    m = _product_model(pkg, g)
+    m.train()
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    b = [g[k] for k in ("heads", "tails", "rels", "labels")]
+    step = pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel(), host_io=True)
+    step.host_batch.copy_(pkg.GraphedTrainStep.pack_batch(*b, pin=False))
+    out = step.replay_host()
+    torch.cuda.synchronize()
+    assert out is step.host_loss and out.is_pinned()
+    torch.testing.assert_close(step.host_loss[0], g["loss"], rtol=1e-4, atol=1e-5)
+    assert int(step.host_correct) == int(((g["scores"] > 0).float() == g["labels"]).sum())
+    for k, want in g["grads"].items():
+        _close_by_scale(dict(m.named_parameters())[k].grad.cpu(), want, k, rtol=1e-3)
+    # another batch through the same staging block
+    perm = torch.randperm(b[0].numel())
+    step.host_batch.copy_(pkg.GraphedTrainStep.pack_batch(*[t[perm] for t in b], pin=False))
+    step.replay_host(); torch.cuda.synchronize()
+    torch.testing.assert_close(step.host_loss[0], g["loss"], rtol=1e-4, atol=1e-5)
+    with pytest.raises(RuntimeError):
+        pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel()).replay_host()
