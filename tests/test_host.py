@@ -216,3 +216,15 @@ def test_grad_arena_slices(lib_built):
     finally:
         ops.set_grad_arena(None)
     assert ops.param_grad(4, device=torch.device("cpu")).data_ptr() != arena.buf.data_ptr()
+
+
+def test_integration_doc_lists_every_abi_symbol():
+    """INTEGRATION.md is the maintainer-facing map of the C ABI: every entry point of the header must appear in it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "rgcn_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    syms = sorted(set(re.findall(r"\b(rgcn_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(syms) >= 40
+    missing = [s for s in syms if s not in doc]
+    assert not missing, f"not documented in INTEGRATION.md: {missing}"
