@@ -404,6 +404,9 @@ int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, con
  *                        predictions (:321-322) in ONE kernel; `state` receives the dropout counter value used.
  *   rgcn_link_loss_bwd : d loss / d emb scattered into the dense, pre-zeroed g_emb [N, d]; d loss / d rel_table (optional,
  *                        pre-zeroed; n_rel = its row count, used to pre-reduce the block's pairs in shared memory).
+ *                        Scores-only form (LinkPredictor.score_pairs with the same counter-based relation dropout):
+ *                        labels = loss = NULL in the forward; g_score [n_pairs] = the incoming gradient of the scores
+ *                        in the backward (labels, score, g_loss then unused).
  *                        workspace: rgcn_link_loss_workspace_bytes(n_pairs), ZEROED once before first use.
  * ------------------------------------------------------------------------------------------ */
 int rgcn_link_batch(const int64_t* pos_head, const int64_t* pos_tail, const int64_t* pos_rel, int64_t n_pos,
@@ -416,6 +419,7 @@ int rgcn_link_loss_fwd(const float* emb, int64_t ld, const int64_t* head, const 
                        float* loss, int32_t* n_correct, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 int rgcn_link_loss_bwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
                        const float* rel_table, const float* labels, const float* score, const float* g_loss,
+                       const float* g_score,
                        int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed, const unsigned long long* state,
                        float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, rgcn_stream_t stream);
 

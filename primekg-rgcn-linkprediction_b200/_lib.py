@@ -104,7 +104,7 @@ PROTOTYPES = {
     "rgcn_link_batch": (C.c_int, [p, p, p, i64, i32, i64, u32, p, p, p, p, p, p]),
     "rgcn_link_loss_workspace_bytes": (sz, [i64]),
     "rgcn_link_loss_fwd": (C.c_int, [p, i64, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, p, p, p, p, sz, p]),
-    "rgcn_link_loss_bwd": (C.c_int, [p, i64, p, p, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, i64, p, i32, p]),
+    "rgcn_link_loss_bwd": (C.c_int, [p, i64, p, p, p, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, i64, p, i32, p]),
     "rgcn_check_pairs": (C.c_int, [p, p, p, i64, i64, i32, p, p]),
 }
 

@@ -219,9 +219,11 @@ __global__ void __launch_bounds__(256) link_loss_fwd_kernel(const LinkLossParams
       s += a.x * b.x * cc.x; s += a.y * b.y * cc.y; s += a.z * b.z * cc.z; s += a.w * b.w * cc.w;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float y = q.labels[p];
-    l = fmaxf(s, 0.f) - s * y + log1pf(expf(-fabsf(s)));
-    ok = (((s > 0.f) ? 1.f : 0.f) == y) ? 1 : 0;
+    if (q.labels) {                                  // NULL: scores only (LinkPredictor.score_pairs)
+      const float y = q.labels[p];
+      l = fmaxf(s, 0.f) - s * y + log1pf(expf(-fabsf(s)));
+      ok = (((s > 0.f) ? 1.f : 0.f) == y) ? 1 : 0;
+    }
     if (lane == 0) q.score[p] = s;
   }
   if (lane == 0) { s_l[warp] = l; s_c[warp] = ok; }
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(256) link_loss_fwd_kernel(const LinkLossParams
       cor += __shfl_xor_sync(0xffffffffu, cor, o);
     }
     if (threadIdx.x == 0) {
-      *q.loss = acc / (float)q.n_pairs;
+      if (q.loss) *q.loss = acc / (float)q.n_pairs;
       if (q.n_correct) *q.n_correct = cor;
       *q.ticket = 0u;                               // ready for the next launch (graph replay)
       if (q.state) *q.state = c;
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(256) link_loss_fwd_kernel(const LinkLossParams
 // g_score[p] = g_loss * (sigmoid(s_p) - y_p) / n folded into the DistMult backward: node-row gradients scattered into
 // the dense [N, d] buffer (zeroed by the caller), relation-table gradient accumulated
 __global__ void __launch_bounds__(256) link_loss_bwd_kernel(const LinkLossParams q, const float* __restrict__ g_loss,
+                                                            const float* __restrict__ g_score,
                                                             float* __restrict__ g_emb, int64_t ld_g,
                                                             float* __restrict__ g_rel_table, int32_t n_rel_smem) {
   pdl_enter();
@@ -281,8 +284,13 @@ __global__ void __launch_bounds__(256) link_loss_bwd_kernel(const LinkLossParams
     const float* h = q.emb + hi * q.ld;
     const float* t = q.emb + ti * q.ld;
     const float* r = q.rel_table + ri * q.d;
-    const float s = q.score[p];
-    const float g = (*g_loss) * (1.f / (1.f + expf(-s)) - q.labels[p]) / (float)q.n_pairs;
+    float g;
+    if (g_score) {
+      g = g_score[p];                                // scores-only form: the incoming gradient of score[p]
+    } else {
+      const float s = q.score[p];
+      g = (*g_loss) * (1.f / (1.f + expf(-s)) - q.labels[p]) / (float)q.n_pairs;
+    }
     for (int vi = lane; vi < (q.d >> 2); vi += 32) {
       const float4 a = ldg4(h + vi * 4), cc = ldg4(t + vi * 4);
       float4 b = ldg4(r + vi * 4);
@@ -417,7 +425,7 @@ static int fill_link_params(LinkLossParams& q, const float* emb, int64_t ld, con
                             const int64_t* rel, const float* rel_table, const float* labels, int64_t n_pairs, int32_t d,
                             float dropout_p, uint32_t seed) {
   RGCN_CHECK_ARG(n_pairs > 0 && d >= 4 && d % 4 == 0, "link_loss: n_pairs must be positive and d a multiple of 4");
-  RGCN_CHECK_ARG(emb && head && tail && rel && rel_table && labels, "link_loss: null argument");
+  RGCN_CHECK_ARG(emb && head && tail && rel && rel_table, "link_loss: null argument");
   RGCN_CHECK_ARG(ld % 4 == 0 && (((uintptr_t)emb | (uintptr_t)rel_table) & 15) == 0, "link_loss: rows must be 16-byte aligned");
   RGCN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "link_loss: dropout_p must be in [0, 1)");
   RGCN_CHECK_ARG(n_pairs * (int64_t)d < (1ll << 32), "link_loss: batch too large for the 32-bit dropout index");
@@ -445,7 +453,7 @@ extern "C" int rgcn_link_loss_fwd(const float* emb, int64_t ld, const int64_t* h
   LinkLossParams q{};
   int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed);
   if (rc) return rc;
-  RGCN_CHECK_ARG(score && loss, "link_loss_fwd: null outputs");
+  RGCN_CHECK_ARG(score && (loss || !labels), "link_loss_fwd: null outputs");
   RGCN_CHECK_ARG(dropout_p == 0.f || (counter && state), "link_loss_fwd: dropout needs the counter and a state slot");
   const size_t blocks = (size_t)((n_pairs + 7) / 8);
   if (!workspace || workspace_bytes < rgcn_link_loss_workspace_bytes(n_pairs)) {
@@ -461,18 +469,20 @@ extern "C" int rgcn_link_loss_fwd(const float* emb, int64_t ld, const int64_t* h
 
 extern "C" int rgcn_link_loss_bwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
                                   const float* rel_table, const float* labels, const float* score, const float* g_loss,
+                                  const float* g_score,
                                   int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed, const unsigned long long* state,
                                   float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, rgcn_stream_t stream) {
   LinkLossParams q{};
   int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed);
   if (rc) return rc;
-  RGCN_CHECK_ARG(score && g_loss && g_emb && ld_g % 4 == 0 && ((uintptr_t)g_emb & 15) == 0, "link_loss_bwd: bad buffers");
+  RGCN_CHECK_ARG(g_emb && ld_g % 4 == 0 && ((uintptr_t)g_emb & 15) == 0, "link_loss_bwd: bad buffers");
+  RGCN_CHECK_ARG(g_score || (score && g_loss && labels), "link_loss_bwd: need g_score, or score + labels + g_loss");
   RGCN_CHECK_ARG(dropout_p == 0.f || state, "link_loss_bwd: dropout needs the state the forward wrote");
   RGCN_CHECK_ARG(!g_rel_table || ((uintptr_t)g_rel_table & 15) == 0, "link_loss_bwd: g_rel_table misaligned");
   q.state = const_cast<unsigned long long*>(state); q.score = const_cast<float*>(score);
   const int32_t n_rel_smem = (g_rel_table && n_rel > 0 && (size_t)n_rel * d * 4 <= 40 * 1024) ? n_rel : 0;
   RGCN_CUDA(launch_pdl(link_loss_bwd_kernel, dim3((unsigned)((n_pairs + 7) / 8)), dim3(256), (size_t)n_rel_smem * d * 4,
-                       (cudaStream_t)stream, q, g_loss, g_emb, ld_g, g_rel_table, n_rel_smem));
+                       (cudaStream_t)stream, q, g_loss, g_score, g_emb, ld_g, g_rel_table, n_rel_smem));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

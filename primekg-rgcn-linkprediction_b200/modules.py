@@ -175,8 +175,14 @@ class LinkPredictor(nn.Module):
                     relation_types: torch.Tensor) -> torch.Tensor:
         """Fused form of ``forward(emb[head], emb[tail], rel)`` (reference :325-329)."""
         _need_cuda(node_embeddings, "LinkPredictor.score_pairs")
-        table, scale = self._relation_operand(relation_types)
-        return _DistMultGather.apply(node_embeddings, head_indices, tail_indices, relation_types, table, None, scale)
+        p = self.dropout.p if self.training else 0.0
+        if p >= 1.0:
+            table, scale = self._relation_operand(relation_types)
+            return _DistMultGather.apply(node_embeddings, head_indices, tail_indices, relation_types, table, None, scale)
+        # the fused kernels' scores-only form: relation dropout by counter-based mask (no mask tensor, no extra launches)
+        seed, ctr = self._dropout_rng(node_embeddings.device) if p > 0 else (0, None)
+        return ops.pair_scores(node_embeddings, self.relation_embeddings.weight, head_indices, tail_indices,
+                               relation_types, p, seed, ctr)
 
     def score_all_tails(self, head_embeddings: torch.Tensor, relation_types: torch.Tensor,
                         all_tail_embeddings: torch.Tensor) -> torch.Tensor:

@@ -697,7 +697,7 @@ class _LinkLoss(torch.autograd.Function):
             g_tab = param_grad(*rel_table.shape, device=dev)
             g_tab.zero_()
         _lib.check(lib.rgcn_link_loss_bwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
-                                          _ptr(labels), _ptr(score), _ptr(g_loss), head.numel(), emb.size(1), ctx.p_drop,
+                                          _ptr(labels), _ptr(score), _ptr(g_loss), None, head.numel(), emb.size(1), ctx.p_drop,
                                           ctx.seed & 0xFFFFFFFF, _ptr(state), _ptr(g_emb), g_emb.stride(0), _ptr(g_tab),
                                           rel_table.size(0), _stream(dev)), "rgcn_link_loss_bwd")
         if not ctx.needs_input_grad[0]:
@@ -751,3 +751,60 @@ def basis_combine(comp: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
     if comp.size(0) > 64 or comp.size(1) > 16 or V[0].numel() % 4:
         raise ValueError("basis_combine handles up to 64 relations, 16 bases and in * out a multiple of 4")
     return _BasisCombine.apply(comp, V)
+
+
+class _PairScores(torch.autograd.Function):
+    """scores[p] = <emb[head[p]], dropout(rel_table[rel[p]]), emb[tail[p]]> — ``LinkPredictor.score_pairs`` on the fused
+    kernels' scores-only form: the relation dropout (reference src/models/rgcn.py:207-208) is the counter-based mask the
+    backward regenerates, so no mask tensor and no ``bernoulli`` / ``div`` launches."""
+
+    @staticmethod
+    def forward(ctx, emb, rel_table, head, tail, rel, p_drop, seed, counter):
+        lib = _lib.load()
+        emb = _f32c(emb, "node embeddings")
+        rel_table = _f32c(rel_table, "relation table").contiguous()
+        head, tail, rel = _idx(head, "head"), _idx(tail, "tail"), _idx(rel, "rel")
+        n, d, dev = head.numel(), emb.size(1), emb.device
+        if rel_table.size(1) != d or not (tail.numel() == rel.numel() == n):
+            raise ValueError("score_pairs: shapes disagree")
+        score = torch.empty(n, dtype=torch.float32, device=dev)
+        state = torch.empty(1, dtype=torch.int64, device=dev) if p_drop > 0 else None
+        if n:
+            ws = _link_workspace(dev, n)
+            _lib.check(lib.rgcn_link_loss_fwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
+                                              None, n, d, float(p_drop), int(seed) & 0xFFFFFFFF,
+                                              _ptr(counter if p_drop > 0 else None), _ptr(state), _ptr(score), None, None,
+                                              _ptr(ws), ws.numel(), _stream(dev)), "rgcn_link_loss_fwd")
+        ctx.save_for_backward(emb, rel_table, head, tail, rel, state)
+        ctx.p_drop, ctx.seed = float(p_drop), int(seed)
+        return score
+
+    @staticmethod
+    def backward(ctx, g_score):
+        from . import rowsparse
+        lib = _lib.load()
+        emb, rel_table, head, tail, rel, state = ctx.saved_tensors
+        dev = emb.device
+        g_score = g_score.to(torch.float32).contiguous()
+        g_emb = torch.zeros_like(emb, memory_format=torch.contiguous_format)
+        g_tab = None
+        if ctx.needs_input_grad[1]:
+            g_tab = param_grad(*rel_table.shape, device=dev)
+            g_tab.zero_()
+        if head.numel():
+            _lib.check(lib.rgcn_link_loss_bwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
+                                              None, None, None, _ptr(g_score), head.numel(), emb.size(1), ctx.p_drop,
+                                              ctx.seed & 0xFFFFFFFF, _ptr(state), _ptr(g_emb), g_emb.stride(0), _ptr(g_tab),
+                                              rel_table.size(0), _stream(dev)), "rgcn_link_loss_bwd")
+        if not ctx.needs_input_grad[0]:
+            return None, g_tab, None, None, None, None, None, None
+        rowsparse.announce(g_emb, torch.cat([head, tail]))     # zero outside the head / tail rows
+        return g_emb, g_tab, None, None, None, None, None, None
+
+
+def pair_scores(emb, rel_table, head, tail, rel, p_drop: float = 0.0, seed: int = 0, counter=None) -> torch.Tensor:
+    if not emb.is_cuda:
+        raise RuntimeError("score_pairs needs CUDA tensors: there is no CPU implementation of this path")
+    if p_drop > 0 and counter is None:
+        raise ValueError("pair_scores: dropout needs a device counter (ops.rng_counter)")
+    return _PairScores.apply(emb, rel_table, head, tail, rel, float(p_drop), int(seed), counter)
