@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 3
+#define RGCN_B200_ABI_VERSION 4
 
 enum {
   RGCN_OK = 0,
@@ -299,18 +299,22 @@ typedef struct rgcn_layer_bwd_args {
    *            written by the downstream layer's next_G — so the rgcn_split_planes pass over g_out is skipped. */
   const rgcn_masked_planes_out* next_G;
   int32_t g_ready; int32_t n_colsum_ready;
+  int32_t slot_ready;                       /* row-sparse form: `slot` already holds the map for `rows` (written by
+                                               rgcn_link_loss_bwd_rows for this very list): skip building it        */
 } rgcn_layer_bwd_args;
 
 /* Compaction step of the row-sparse backward (csrc/rowsparse.cu), also callable on its own:
  * slot[i] = first position of node i in rows[0 .. n_list) or m_c; G planes row c = g_out[rows[c]] when slot[rows[c]] == c
  * else zeros; Ac planes likewise from A (optional); colsum_partial = per-block column sums of the G rows (optional);
- * zero_row[0 .. zero_cols) is cleared (optional: the zero row of the dgrad output). */
+ * zero_row[0 .. zero_cols) is cleared (optional: the zero row of the dgrad output).  slot_ready != 0: `slot` was built
+ * for this list already (rgcn_link_loss_bwd_rows) and is used as it is. */
 int64_t rgcn_rows_compact_size(int64_t n_list);       /* m_c = n_list rounded up to a multiple of 128 */
 int64_t rgcn_rows_compact_blocks(int64_t n_list);     /* rows of colsum_partial                       */
 int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_nodes, int32_t* slot,
                       const float* g_out, int64_t ld_g_out, int32_t d_out, void* G_hi, void* G_lo, int64_t ldg,
                       const void* A_hi, const void* A_lo, int64_t lda, int32_t K, void* Ac_hi, void* Ac_lo,
-                      int64_t ldac, float* colsum_partial, float* zero_row, int32_t zero_cols, rgcn_stream_t stream);
+                      int64_t ldac, float* colsum_partial, float* zero_row, int32_t zero_cols, int32_t slot_ready,
+                      rgcn_stream_t stream);
 
 int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream);
 int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream);
@@ -408,6 +412,17 @@ int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, con
  *                        labels = loss = NULL in the forward; g_score [n_pairs] = the incoming gradient of the scores
  *                        in the backward (labels, score, g_loss then unused).
  *                        workspace: rgcn_link_loss_workspace_bytes(n_pairs), ZEROED once before first use.
+ *                        (fp32 atomics on repeated rows: the sum order differs from run to run.)
+ *   rgcn_link_loss_bwd_rows : the DETERMINISTIC form of the same backward, and the one the modules use.  No floating-point
+ *                        atomics: slot[i] (int32 [n_nodes], out) = first position of node i in rows (int64 [2 n_pairs],
+ *                        out: the heads then the tails) or rgcn_rows_compact_size(2 n_pairs) when nobody lists it; the
+ *                        owner position's warp adds all contributions to the node in ascending position order and
+ *                        every row of g_emb [n_nodes, d] is written exactly once (no pre-zeroing).  g_rel_table =
+ *                        fixed-order sum of per-32-pair partials (workspace: rgcn_link_bwd_rows_workspace_bytes).
+ *                        slot / rows are exactly what rgcn_layer_bwd's row-sparse form wants (slot_ready = 1).
+ *   Index range: with n_nodes > 0 a pair whose head / tail is outside [0, n_nodes) or whose relation is outside
+ *                        [0, n_rel) is skipped — NaN score and loss, no gradient — and bit 0 of *status (nullable) is
+ *                        set; the reference's nn.Embedding raises a device-side assert at the same place.
  * ------------------------------------------------------------------------------------------ */
 int rgcn_link_batch(const int64_t* pos_head, const int64_t* pos_tail, const int64_t* pos_rel, int64_t n_pos,
                     int32_t num_neg, int64_t num_nodes, uint32_t seed, unsigned long long* counter,
@@ -416,12 +431,21 @@ size_t rgcn_link_loss_workspace_bytes(int64_t n_pairs);
 int rgcn_link_loss_fwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
                        const float* rel_table, const float* labels, int64_t n_pairs, int32_t d, float dropout_p,
                        uint32_t seed, unsigned long long* counter, unsigned long long* state, float* score,
-                       float* loss, int32_t* n_correct, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+                       float* loss, int32_t* n_correct, int64_t n_nodes, int32_t n_rel, int32_t* status,
+                       void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 int rgcn_link_loss_bwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
                        const float* rel_table, const float* labels, const float* score, const float* g_loss,
                        const float* g_score,
                        int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed, const unsigned long long* state,
-                       float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, rgcn_stream_t stream);
+                       float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, int64_t n_nodes,
+                       rgcn_stream_t stream);
+size_t rgcn_link_bwd_rows_workspace_bytes(int64_t n_pairs, int32_t n_rel, int32_t d);
+int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
+                            const float* rel_table, const float* labels, const float* score, const float* g_loss,
+                            const float* g_score, int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed,
+                            const unsigned long long* state, int64_t n_nodes, int32_t n_rel, float* g_emb, int64_t ld_g,
+                            float* g_rel_table, int32_t* slot, int64_t* rows, int32_t* status, void* workspace,
+                            size_t workspace_bytes, rgcn_stream_t stream);
 
 /* flag[0] = 1 when any head/tail is outside [0, n_nodes) or any rel outside [0, n_rel). */
 int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgcn_b200.so")
 
-ABI_VERSION = 3          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
+ABI_VERSION = 4          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
 
 _lock = threading.Lock()
 _lib = None
@@ -57,7 +57,7 @@ class LayerBwdArgs(C.Structure):
                 ("g_x", p), ("ld_g_x", i64), ("g_weight", p), ("g_root", p), ("g_bias", p),
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
                 ("rows", p), ("n_list", i64), ("slot", p), ("Ac_hi", p), ("Ac_lo", p), ("ldac", i64),
-                ("next_G", C.POINTER(MaskedPlanesOut)), ("g_ready", i32), ("n_colsum_ready", i32)]
+                ("next_G", C.POINTER(MaskedPlanesOut)), ("g_ready", i32), ("n_colsum_ready", i32), ("slot_ready", i32)]
 
 # name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
 PROTOTYPES = {
@@ -79,7 +79,7 @@ PROTOTYPES = {
     "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
     "rgcn_rows_compact_size": (i64, [i64]),
     "rgcn_rows_compact_blocks": (i64, [i64]),
-    "rgcn_rows_compact": (C.c_int, [p, i64, i64, p, p, i64, i32, p, p, i64, p, p, i64, i32, p, p, i64, p, p, i32, p]),
+    "rgcn_rows_compact": (C.c_int, [p, i64, i64, p, p, i64, i32, p, p, i64, p, p, i64, i32, p, p, i64, p, p, i32, i32, p]),
     "rgcn_split_planes_blocks": (i64, [i64, i32]),
     "rgcn_split_planes": (C.c_int, [p, i64, p, i64, i64, i32, p, p, i64, p, C.c_float, p, i64, p]),
     "rgcn_transform_workspace_bytes": (sz, [i64, i32, i32]),
@@ -103,8 +103,11 @@ PROTOTYPES = {
     "rgcn_bce_logits_bwd": (C.c_int, [p, p, i64, p, p, p]),
     "rgcn_link_batch": (C.c_int, [p, p, p, i64, i32, i64, u32, p, p, p, p, p, p]),
     "rgcn_link_loss_workspace_bytes": (sz, [i64]),
-    "rgcn_link_loss_fwd": (C.c_int, [p, i64, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, p, p, p, p, sz, p]),
-    "rgcn_link_loss_bwd": (C.c_int, [p, i64, p, p, p, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, i64, p, i32, p]),
+    "rgcn_link_loss_fwd": (C.c_int, [p, i64, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, p, p, p, i64, i32, p, p, sz, p]),
+    "rgcn_link_loss_bwd": (C.c_int, [p, i64, p, p, p, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, i64, p, i32, i64, p]),
+    "rgcn_link_bwd_rows_workspace_bytes": (sz, [i64, i32, i32]),
+    "rgcn_link_loss_bwd_rows": (C.c_int, [p, i64, p, p, p, p, p, p, p, p, i64, i32, C.c_float, u32, p, i64, i32, p, i64, p,
+                                          p, p, p, p, sz, p]),
     "rgcn_check_pairs": (C.c_int, [p, p, p, i64, i64, i32, p, p]),
 }
 

@@ -74,9 +74,11 @@ class _RGCNLayerFn(torch.autograd.Function):
         need_w_any = need_W or need_root or need_b
         need_x = need_src or need_root_x
         # gO zero outside a short, announced row list (the decoder's backward, rowsparse.py): compact backward
-        rows = None
+        rows = slot = None
         if out is None and ctx.shared and graph.n_src == graph.n_dst:
-            rows = rowsparse.claim(gO)
+            claimed = rowsparse.claim(gO)
+            if claimed is not None:
+                rows, slot = claimed
         # out is zero exactly where ReLU or the fused dropout killed the element: one mask serves both
         mask_scale = 1.0 / (1.0 - ctx.p_drop)
         # the downstream layer's walk may have left this layer's masked output gradient as planes already
@@ -85,7 +87,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         res = ops.layer_bwd(
             graph, gO.contiguous(), out, mask_scale, (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
             need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any, rows=rows, g_ready=g_ready,
-            next_mask=next_mask,
+            next_mask=next_mask, slot=slot,
             gx_out=ops.param_grad(graph.n_src, d_in, device=gO.device) if (need_x and ctx.x_is_param) else None)
         gx, gA, gWf, groot, gb = res[:5]
         if next_mask is not None:

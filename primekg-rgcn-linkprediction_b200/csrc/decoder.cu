@@ -189,7 +189,15 @@ struct LinkLossParams {
   unsigned long long* state;         // forward: out, the counter value used; backward: in
   float* score; float* loss; int32_t* n_correct;
   float* part_loss; int32_t* part_correct; unsigned int* ticket;   // [gridDim.x], [gridDim.x], [1] (zero before launch)
+  // index range (n_nodes <= 0: unchecked).  A pair with an out-of-range head / tail / relation is SKIPPED — its score
+  // and the loss become NaN, it contributes no gradient — and bit 0 of *status is set (the reference's nn.Embedding
+  // raises a device assert there; here the caller polls the flag, see ops.raise_on_bad_pairs)
+  int64_t n_nodes; int32_t n_rel; int32_t* status;
 };
+
+__device__ __forceinline__ bool pair_ok(const LinkLossParams& q, int64_t hi, int64_t ti, int64_t ri) {
+  return q.n_nodes <= 0 || (hi >= 0 && hi < q.n_nodes && ti >= 0 && ti < q.n_nodes && ri >= 0 && ri < (int64_t)q.n_rel);
+}
 
 // scores, mean BCE-with-logits loss and the number of correct sigmoid > 0.5 predictions (src/train.py:300, :321-322)
 // in ONE kernel: a warp per pair, per-block partials, the last block to finish reduces them in block order.
@@ -205,9 +213,11 @@ __global__ void __launch_bounds__(256) link_loss_fwd_kernel(const LinkLossParams
   float l = 0.f;
   int ok = 0;
   if (p < q.n_pairs) {
-    const float* h = q.emb + q.head[p] * q.ld;
-    const float* t = q.emb + q.tail[p] * q.ld;
-    const float* r = q.rel_table + q.rel[p] * q.d;
+    const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
+    const bool in_range = pair_ok(q, hi, ti, ri);
+    const float* h = q.emb + (in_range ? hi : 0) * q.ld;
+    const float* t = q.emb + (in_range ? ti : 0) * q.ld;
+    const float* r = q.rel_table + (in_range ? ri : 0) * q.d;
     float s = 0.f;
     for (int vi = lane; vi < (q.d >> 2); vi += 32) {
       const float4 a = ldg4(h + vi * 4), cc = ldg4(t + vi * 4);
@@ -219,6 +229,10 @@ __global__ void __launch_bounds__(256) link_loss_fwd_kernel(const LinkLossParams
       s += a.x * b.x * cc.x; s += a.y * b.y * cc.y; s += a.z * b.z * cc.z; s += a.w * b.w * cc.w;
     }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (!in_range) {
+      s = __int_as_float(0x7fc00000);                // NaN: visible in the scores and in the loss
+      if (lane == 0 && q.status) atomicOr(q.status, 1);
+    }
     if (q.labels) {                                  // NULL: scores only (LinkPredictor.score_pairs)
       const float y = q.labels[p];
       l = fmaxf(s, 0.f) - s * y + log1pf(expf(-fabsf(s)));
@@ -281,9 +295,10 @@ __global__ void __launch_bounds__(256) link_loss_bwd_kernel(const LinkLossParams
     const unsigned long long c = q.drop_thresh ? *q.state : 0ull;
     const uint32_t key = pcg32(q.seed ^ (uint32_t)c) + (uint32_t)(c >> 32) * 0x9E3779B9u;
     const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
-    const float* h = q.emb + hi * q.ld;
-    const float* t = q.emb + ti * q.ld;
-    const float* r = q.rel_table + ri * q.d;
+    const bool in_range = pair_ok(q, hi, ti, ri);
+    const float* h = q.emb + (in_range ? hi : 0) * q.ld;
+    const float* t = q.emb + (in_range ? ti : 0) * q.ld;
+    const float* r = q.rel_table + (in_range ? ri : 0) * q.d;
     float g;
     if (g_score) {
       g = g_score[p];                                // scores-only form: the incoming gradient of score[p]
@@ -291,7 +306,7 @@ __global__ void __launch_bounds__(256) link_loss_bwd_kernel(const LinkLossParams
       const float s = q.score[p];
       g = (*g_loss) * (1.f / (1.f + expf(-s)) - q.labels[p]) / (float)q.n_pairs;
     }
-    for (int vi = lane; vi < (q.d >> 2); vi += 32) {
+    for (int vi = lane; in_range && vi < (q.d >> 2); vi += 32) {
       const float4 a = ldg4(h + vi * 4), cc = ldg4(t + vi * 4);
       float4 b = ldg4(r + vi * 4);
       float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -320,6 +335,152 @@ __global__ void __launch_bounds__(256) link_loss_bwd_kernel(const LinkLossParams
       const float4 v = *reinterpret_cast<const float4*>(s_tab + i * 4);
       if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(g_rel_table) + i, v);
     }
+  }
+}
+
+
+// ---- deterministic backward of the fused decoder (no atomics on floating-point data) --------------------------------
+// The 2 n gathered rows (positions 0 .. n-1 = the heads, n .. 2n-1 = the tails) repeat: a hub gene is the head or tail
+// of many pairs of a batch.  Instead of fp32 atomics (whose order differs from run to run) every listed node gets ONE
+// owner — the first position that lists it, slot[node], found with an integer atomicMin — and the owner's warp adds
+// the contributions of all positions listing the node in ascending position order.  Every row of the dense [N, d]
+// gradient is written exactly once (rows nobody lists are zero-filled by the same launch), so the buffer needs no
+// memset, and `slot` / `rows` are handed to the last encoder layer's row-sparse backward (csrc/rowsparse.cu) as they are.
+// The relation-table gradient is reduced the same way: per-chunk partials in pair order, then a fixed-order column sum.
+__global__ void __launch_bounds__(256) link_rows_kernel(const LinkLossParams q, int64_t* __restrict__ rows,
+                                                        int32_t* __restrict__ slot) {
+  pdl_enter();
+  const int64_t pos = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (pos >= 2 * q.n_pairs) return;
+  const int64_t p = pos < q.n_pairs ? pos : pos - q.n_pairs;
+  const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
+  if (!pair_ok(q, hi, ti, ri)) {
+    rows[pos] = 0;                                   // a valid row id that this position never owns
+    if (q.status) atomicOr(q.status, 1);
+    return;
+  }
+  const int64_t node = pos < q.n_pairs ? hi : ti;
+  rows[pos] = node;
+  atomicMin(slot + node, (int32_t)pos);
+}
+
+struct LinkBwdRows {
+  const float* g_loss; const float* g_score;
+  float* g_emb; int64_t ld_g; int64_t n_rows;       // [n_rows, d]
+  const int32_t* slot; const int64_t* rows; int32_t unlisted;
+  float* tab_partial;                               // [n_tab_blocks, n_rel * d], nullable
+  int32_t n_owner_blocks, n_zero_blocks, n_tab_blocks;
+};
+constexpr int kLinkZeroRows = 64;                    // rows per zero-fill block
+constexpr int kLinkTabPairs = 32;                    // pairs per relation-table partial
+
+__device__ __forceinline__ float link_pair_grad(const LinkLossParams& q, const LinkBwdRows& b, int64_t p) {
+  if (b.g_score) return b.g_score[p];
+  const float s = q.score[p];
+  return (*b.g_loss) * (1.f / (1.f + expf(-s)) - q.labels[p]) / (float)q.n_pairs;
+}
+
+__global__ void __launch_bounds__(256) link_bwd_rows_kernel(const LinkLossParams q, const LinkBwdRows b) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = q.d >> 2;
+  const int64_t n = q.n_pairs, n2 = 2 * q.n_pairs;
+  const unsigned long long c = q.drop_thresh ? *q.state : 0ull;
+  const uint32_t key = pcg32(q.seed ^ (uint32_t)c) + (uint32_t)(c >> 32) * 0x9E3779B9u;
+  int blk = blockIdx.x;
+  if (blk < b.n_owner_blocks) {
+    // ---- one warp per position; only the node's first position (its owner) works ----
+    const int64_t pos = (int64_t)blk * 8 + warp;
+    if (pos >= n2) return;
+    const int64_t v = b.rows[pos];
+    if (__ldg(b.slot + v) != (int32_t)pos) return;
+    for (int v0 = 0; v0 < nv; v0 += 64) {            // column passes of two 128-bit vectors per lane
+      const int vi0 = v0 + lane, vi1 = v0 + 32 + lane;
+      const bool on0 = vi0 < nv, on1 = vi1 < nv;
+      float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+      for (int64_t base = pos & ~int64_t(31); base < n2; base += 32) {
+        const int64_t pp = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, pp >= pos && pp < n2 && b.rows[pp] == v);
+        while (m) {                                  // ascending position order: the order of the sum is fixed
+          const int bit = __ffs((int)m) - 1;
+          m &= m - 1u;
+          const int64_t qq = base + bit;
+          const bool is_head = qq < n;
+          const int64_t p = is_head ? qq : qq - n;
+          const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
+          if (!pair_ok(q, hi, ti, ri)) continue;     // (an invalid pair parks its positions on row 0)
+          const float g = link_pair_grad(q, b, p);
+          const float* __restrict__ other = q.emb + (is_head ? ti : hi) * q.ld;
+          const float* __restrict__ r = q.rel_table + ri * q.d;
+          if (on0) {
+            const float4 o = ldg4(other + vi0 * 4);
+            float4 w = ldg4(r + vi0 * 4);
+            if (q.drop_thresh) {
+              const float4 mk = rel_drop4(key, p, q.d, vi0, q.drop_thresh, q.drop_scale);
+              w.x *= mk.x; w.y *= mk.y; w.z *= mk.z; w.w *= mk.w;
+            }
+            acc0.x += g * w.x * o.x; acc0.y += g * w.y * o.y; acc0.z += g * w.z * o.z; acc0.w += g * w.w * o.w;
+          }
+          if (on1) {
+            const float4 o = ldg4(other + vi1 * 4);
+            float4 w = ldg4(r + vi1 * 4);
+            if (q.drop_thresh) {
+              const float4 mk = rel_drop4(key, p, q.d, vi1, q.drop_thresh, q.drop_scale);
+              w.x *= mk.x; w.y *= mk.y; w.z *= mk.z; w.w *= mk.w;
+            }
+            acc1.x += g * w.x * o.x; acc1.y += g * w.y * o.y; acc1.z += g * w.z * o.z; acc1.w += g * w.w * o.w;
+          }
+        }
+      }
+      if (on0) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + vi0 * 4) = acc0;
+      if (on1) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + vi1 * 4) = acc1;
+    }
+    return;
+  }
+  blk -= b.n_owner_blocks;
+  if (blk < b.n_zero_blocks) {
+    // ---- rows nobody lists: zeros ----
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < kLinkZeroRows / 8; ++k) {
+      const int64_t row = (int64_t)blk * kLinkZeroRows + k * 8 + warp;
+      if (row < b.n_rows && __ldg(b.slot + row) == b.unlisted)
+        for (int vi = lane; vi < nv; vi += 32) *reinterpret_cast<float4*>(b.g_emb + row * b.ld_g + vi * 4) = z;
+    }
+    return;
+  }
+  blk -= b.n_zero_blocks;
+  // ---- relation-table gradient: partial of kLinkTabPairs consecutive pairs, summed in pair order ----
+  __shared__ float s_g[kLinkTabPairs];
+  __shared__ int s_r[kLinkTabPairs];
+  __shared__ long long s_h[kLinkTabPairs], s_t[kLinkTabPairs];
+  const int64_t p0 = (int64_t)blk * kLinkTabPairs;
+  if (threadIdx.x < kLinkTabPairs) {
+    const int64_t p = p0 + threadIdx.x;
+    int r = -1;
+    float g = 0.f;
+    long long hi = 0, ti = 0;
+    if (p < n) {
+      hi = q.head[p]; ti = q.tail[p];
+      const int64_t ri = q.rel[p];
+      if (pair_ok(q, hi, ti, ri)) { r = (int)ri; g = link_pair_grad(q, b, p); }
+    }
+    s_g[threadIdx.x] = g; s_r[threadIdx.x] = r; s_h[threadIdx.x] = hi; s_t[threadIdx.x] = ti;
+  }
+  __syncthreads();
+  float* __restrict__ part = b.tab_partial + (size_t)blk * q.n_rel * q.d;
+  for (int o = threadIdx.x; o < q.n_rel * nv; o += 256) {
+    const int r = o / nv, vi = o % nv;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < kLinkTabPairs; ++k) {
+      if (s_r[k] != r) continue;
+      const float4 a = ldg4(q.emb + s_h[k] * q.ld + vi * 4), cc = ldg4(q.emb + s_t[k] * q.ld + vi * 4);
+      float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (q.drop_thresh) mk = rel_drop4(key, p0 + k, q.d, vi, q.drop_thresh, q.drop_scale);
+      const float g = s_g[k];
+      acc.x += g * a.x * cc.x * mk.x; acc.y += g * a.y * cc.y * mk.y;
+      acc.z += g * a.z * cc.z * mk.z; acc.w += g * a.w * cc.w * mk.w;
+    }
+    *reinterpret_cast<float4*>(part + (size_t)r * q.d + vi * 4) = acc;
   }
 }
 
@@ -423,7 +584,7 @@ extern "C" int rgcn_link_batch(const int64_t* pos_head, const int64_t* pos_tail,
 
 static int fill_link_params(LinkLossParams& q, const float* emb, int64_t ld, const int64_t* head, const int64_t* tail,
                             const int64_t* rel, const float* rel_table, const float* labels, int64_t n_pairs, int32_t d,
-                            float dropout_p, uint32_t seed) {
+                            float dropout_p, uint32_t seed, int64_t n_nodes, int32_t n_rel, int32_t* status) {
   RGCN_CHECK_ARG(n_pairs > 0 && d >= 4 && d % 4 == 0, "link_loss: n_pairs must be positive and d a multiple of 4");
   RGCN_CHECK_ARG(emb && head && tail && rel && rel_table, "link_loss: null argument");
   RGCN_CHECK_ARG(ld % 4 == 0 && (((uintptr_t)emb | (uintptr_t)rel_table) & 15) == 0, "link_loss: rows must be 16-byte aligned");
@@ -431,6 +592,7 @@ static int fill_link_params(LinkLossParams& q, const float* emb, int64_t ld, con
   RGCN_CHECK_ARG(n_pairs * (int64_t)d < (1ll << 32), "link_loss: batch too large for the 32-bit dropout index");
   q.emb = emb; q.ld = ld; q.head = head; q.tail = tail; q.rel = rel; q.rel_table = rel_table; q.labels = labels;
   q.n_pairs = n_pairs; q.d = d; q.seed = seed;
+  q.n_nodes = n_nodes; q.n_rel = n_rel; q.status = status;
   q.drop_thresh = 0; q.drop_scale = 1.f;
   if (dropout_p > 0.f) {
     const double th = (double)dropout_p * 65536.0 + 0.5;
@@ -448,10 +610,10 @@ extern "C" size_t rgcn_link_loss_workspace_bytes(int64_t n_pairs) {
 extern "C" int rgcn_link_loss_fwd(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail, const int64_t* rel,
                                   const float* rel_table, const float* labels, int64_t n_pairs, int32_t d, float dropout_p,
                                   uint32_t seed, unsigned long long* counter, unsigned long long* state, float* score,
-                                  float* loss, int32_t* n_correct, void* workspace, size_t workspace_bytes,
-                                  rgcn_stream_t stream) {
+                                  float* loss, int32_t* n_correct, int64_t n_nodes, int32_t n_rel, int32_t* status,
+                                  void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
   LinkLossParams q{};
-  int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed);
+  int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed, n_nodes, n_rel, status);
   if (rc) return rc;
   RGCN_CHECK_ARG(score && (loss || !labels), "link_loss_fwd: null outputs");
   RGCN_CHECK_ARG(dropout_p == 0.f || (counter && state), "link_loss_fwd: dropout needs the counter and a state slot");
@@ -471,9 +633,10 @@ extern "C" int rgcn_link_loss_bwd(const float* emb, int64_t ld, const int64_t* h
                                   const float* rel_table, const float* labels, const float* score, const float* g_loss,
                                   const float* g_score,
                                   int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed, const unsigned long long* state,
-                                  float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, rgcn_stream_t stream) {
+                                  float* g_emb, int64_t ld_g, float* g_rel_table, int32_t n_rel, int64_t n_nodes,
+                                  rgcn_stream_t stream) {
   LinkLossParams q{};
-  int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed);
+  int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed, n_nodes, n_rel, nullptr);
   if (rc) return rc;
   RGCN_CHECK_ARG(g_emb && ld_g % 4 == 0 && ((uintptr_t)g_emb & 15) == 0, "link_loss_bwd: bad buffers");
   RGCN_CHECK_ARG(g_score || (score && g_loss && labels), "link_loss_bwd: need g_score, or score + labels + g_loss");
@@ -484,5 +647,62 @@ extern "C" int rgcn_link_loss_bwd(const float* emb, int64_t ld, const int64_t* h
   RGCN_CUDA(launch_pdl(link_loss_bwd_kernel, dim3((unsigned)((n_pairs + 7) / 8)), dim3(256), (size_t)n_rel_smem * d * 4,
                        (cudaStream_t)stream, q, g_loss, g_score, g_emb, ld_g, g_rel_table, n_rel_smem));
   RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+// ---- deterministic form of the backward (link_rows_kernel / link_bwd_rows_kernel above) ----
+namespace rgcn {
+__global__ void __launch_bounds__(256) link_slot_fill_kernel(int32_t* __restrict__ slot, int64_t n, int32_t unlisted) {
+  pdl_enter();
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) slot[i] = unlisted;
+}
+}
+
+extern "C" size_t rgcn_link_bwd_rows_workspace_bytes(int64_t n_pairs, int32_t n_rel, int32_t d) {
+  if (n_pairs <= 0 || n_rel <= 0 || d <= 0) return 256;
+  const size_t chunks = (size_t)((n_pairs + kLinkTabPairs - 1) / kLinkTabPairs);
+  return align_up(chunks * (size_t)n_rel * (size_t)d * sizeof(float), 256) + 256;
+}
+
+extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail,
+                                       const int64_t* rel, const float* rel_table, const float* labels, const float* score,
+                                       const float* g_loss, const float* g_score, int64_t n_pairs, int32_t d,
+                                       float dropout_p, uint32_t seed, const unsigned long long* state, int64_t n_nodes,
+                                       int32_t n_rel, float* g_emb, int64_t ld_g, float* g_rel_table, int32_t* slot,
+                                       int64_t* rows, int32_t* status, void* workspace, size_t workspace_bytes,
+                                       rgcn_stream_t stream) {
+  LinkLossParams q{};
+  int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed, n_nodes, n_rel, status);
+  if (rc) return rc;
+  RGCN_CHECK_ARG(n_nodes > 0 && n_nodes < (1ll << 31) && n_rel > 0 && 2 * n_pairs < (1ll << 30), "link_loss_bwd_rows: bad sizes");
+  RGCN_CHECK_ARG(g_emb && ld_g % 4 == 0 && ((uintptr_t)g_emb & 15) == 0 && slot && rows, "link_loss_bwd_rows: bad buffers");
+  RGCN_CHECK_ARG(g_score || (score && g_loss && labels), "link_loss_bwd_rows: need g_score, or score + labels + g_loss");
+  RGCN_CHECK_ARG(dropout_p == 0.f || state, "link_loss_bwd_rows: dropout needs the state the forward wrote");
+  RGCN_CHECK_ARG(!g_rel_table || ((uintptr_t)g_rel_table & 15) == 0, "link_loss_bwd_rows: g_rel_table misaligned");
+  if (g_rel_table && (!workspace || workspace_bytes < rgcn_link_bwd_rows_workspace_bytes(n_pairs, n_rel, d))) {
+    set_error("link_loss_bwd_rows: workspace too small"); return RGCN_EWORKSPACE;
+  }
+  q.state = const_cast<unsigned long long*>(state); q.score = const_cast<float*>(score);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t m_c = (int32_t)rgcn_rows_compact_size(2 * n_pairs);
+  RGCN_CUDA(launch_pdl(link_slot_fill_kernel, dim3((unsigned)((n_nodes + 255) / 256)), dim3(256), 0, st, slot, n_nodes, m_c));
+  RGCN_LAUNCH_CHECK();
+  RGCN_CUDA(launch_pdl(link_rows_kernel, dim3((unsigned)((2 * n_pairs + 255) / 256)), dim3(256), 0, st, q, rows, slot));
+  RGCN_LAUNCH_CHECK();
+  LinkBwdRows b{};
+  b.g_loss = g_loss; b.g_score = g_score; b.g_emb = g_emb; b.ld_g = ld_g; b.n_rows = n_nodes;
+  b.slot = slot; b.rows = rows; b.unlisted = m_c;
+  b.n_owner_blocks = (int32_t)((2 * n_pairs + 7) / 8);
+  b.n_zero_blocks = (int32_t)((n_nodes + kLinkZeroRows - 1) / kLinkZeroRows);
+  b.n_tab_blocks = g_rel_table ? (int32_t)((n_pairs + kLinkTabPairs - 1) / kLinkTabPairs) : 0;
+  b.tab_partial = g_rel_table ? (float*)align_up((size_t)workspace, 16) : nullptr;
+  RGCN_CUDA(launch_pdl(link_bwd_rows_kernel, dim3((unsigned)(b.n_owner_blocks + b.n_zero_blocks + b.n_tab_blocks)), dim3(256),
+                       0, st, q, b));
+  RGCN_LAUNCH_CHECK();
+  if (g_rel_table) {
+    rc = rgcn_reduce_partials(b.tab_partial, b.n_tab_blocks, n_rel * d, g_rel_table, stream);    // fixed order
+    if (rc) return rc;
+  }
   return RGCN_OK;
 }

@@ -116,7 +116,7 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
                              a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->A_hi, a->mode == 0 ? a->A_lo : nullptr, a->lda, K,
                              need_w ? a->Ac_hi : nullptr, (need_w && a->mode == 0) ? a->Ac_lo : nullptr, a->ldac,
                              a->g_bias ? a->colsum_partial : nullptr, a->gA ? a->gA + m_c * a->ld_gA : nullptr, a->gA ? K : 0,
-                             stream);
+                             a->slot_ready, stream);
   if (rc) return rc;
   return dgrad_walk_wgrad(a, m_c, a->Ac_hi, a->Ac_lo, a->ldac, (int32_t)rgcn_rows_compact_blocks(a->n_list), [&]() {
     return rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c, a->gA + K1, a->ld_gA, a->g_x,

@@ -56,12 +56,15 @@ struct CompactParams {
   const __nv_bfloat16* A_hi; const __nv_bfloat16* A_lo; int64_t lda; int32_t K;      // K % 4 == 0
   __nv_bfloat16* Ac_hi; __nv_bfloat16* Ac_lo; int64_t ldac;                          // nullable: no weight gradient
   float* colsum_partial;                                                              // nullable, [gridDim.x, d_out]
+  float* zero_row; int32_t zero_cols;                                                 // nullable: cleared by block 0
 };
 
 __global__ void __launch_bounds__(256) rows_compact_kernel(const CompactParams p) {
   pdl_enter();
   extern __shared__ float4 s_cs[];                // [8][d_out / 4]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (p.zero_row && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < p.zero_cols; i += 256) p.zero_row[i] = 0.f;
   const int nv = p.d_out >> 2, nk = p.K >> 2;     // float4 of G per row, 8-byte groups of 4 bf16 per plane row
   const int c = blockIdx.x * kRowsPerBlock + warp;
   int64_t node = -1;
@@ -135,7 +138,7 @@ extern "C" int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_
                                  const float* g_out, int64_t ld_g_out, int32_t d_out, void* G_hi, void* G_lo, int64_t ldg,
                                  const void* A_hi, const void* A_lo, int64_t lda, int32_t K, void* Ac_hi, void* Ac_lo,
                                  int64_t ldac, float* colsum_partial, float* zero_row, int32_t zero_cols,
-                                 rgcn_stream_t stream) {
+                                 int32_t slot_ready, rgcn_stream_t stream) {
   const int64_t m_c = rgcn_rows_compact_size(n_list);
   RGCN_CHECK_ARG(rows && n_list > 0 && n_nodes > 0 && slot && m_c < (1ll << 30), "rows_compact: bad row list");
   RGCN_CHECK_ARG(g_out && ((uintptr_t)g_out & 15) == 0 && ld_g_out % 4 == 0 && d_out >= 4 && d_out % 4 == 0 && d_out <= 1024,
@@ -146,12 +149,14 @@ extern "C" int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_
                             (!Ac_lo || (A_lo && (((uintptr_t)A_lo | (uintptr_t)Ac_lo) & 7) == 0))),
                  "rows_compact: operand planes must be 8-byte aligned with K, ld %% 4 == 0");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t n_fill = (zero_row && zero_cols > n_nodes) ? zero_cols : n_nodes;
-  RGCN_CUDA(launch_pdl(rows_slot_fill_kernel, dim3((unsigned)((n_fill + 255) / 256)), dim3(256), 0, st, slot, n_nodes,
-                       (int32_t)m_c, zero_row, zero_cols));
-  RGCN_LAUNCH_CHECK();
-  RGCN_CUDA(launch_pdl(rows_slot_min_kernel, dim3((unsigned)((n_list + 255) / 256)), dim3(256), 0, st, rows, n_list, slot));
-  RGCN_LAUNCH_CHECK();
+  if (!slot_ready) {
+    // (slot_ready: the decoder's deterministic backward, rgcn_link_loss_bwd_rows, has built slot for this very list)
+    RGCN_CUDA(launch_pdl(rows_slot_fill_kernel, dim3((unsigned)((n_nodes + 255) / 256)), dim3(256), 0, st, slot, n_nodes,
+                         (int32_t)m_c, (float*)nullptr, 0));
+    RGCN_LAUNCH_CHECK();
+    RGCN_CUDA(launch_pdl(rows_slot_min_kernel, dim3((unsigned)((n_list + 255) / 256)), dim3(256), 0, st, rows, n_list, slot));
+    RGCN_LAUNCH_CHECK();
+  }
   CompactParams p{};
   p.rows = rows; p.n_list = n_list; p.slot = slot; p.m_c = (int32_t)m_c;
   p.g_out = g_out; p.ld_g_out = ld_g_out; p.d_out = d_out;
@@ -159,6 +164,7 @@ extern "C" int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_
   p.A_hi = (const __nv_bfloat16*)A_hi; p.A_lo = (const __nv_bfloat16*)A_lo; p.lda = lda; p.K = K;
   p.Ac_hi = (__nv_bfloat16*)Ac_hi; p.Ac_lo = (__nv_bfloat16*)Ac_lo; p.ldac = ldac;
   p.colsum_partial = colsum_partial;
+  p.zero_row = zero_row; p.zero_cols = zero_cols;
   const size_t smem = (size_t)8 * (d_out / 4) * sizeof(float4);
   RGCN_CUDA(launch_pdl(rows_compact_kernel, dim3((unsigned)rgcn_rows_compact_blocks(n_list)), dim3(256), smem, st, p));
   RGCN_LAUNCH_CHECK();

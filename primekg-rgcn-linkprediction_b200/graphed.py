@@ -5,7 +5,9 @@ limiter.  ``GraphedTrainStep`` captures one step — ``model(edge_index, edge_ty
 ``BCEWithLogitsLoss`` -> ``backward()`` (reference src/train.py:291-306) — into a CUDA graph over static input buffers
 and replays it; gradients land in the parameters' ``.grad`` as usual (each replay OVERWRITES them: the step owns the
 buffers, so gradient accumulation over several batches needs ``flat_grads=True`` and a caller-side sum), so the
-optimiser / clipping code of the caller (src/train.py:309-318) stays as it is.  Dropout masks are re-drawn on every replay (torch's graph-safe Philox state).
+optimiser / clipping code of the caller (src/train.py:309-318) stays as it is.  Dropout masks are re-drawn on every replay: the fused dropout is a counter-based hash of (seed, device-side
+step counter, element index) and the counter is advanced by a kernel of the captured step itself (csrc/transform.cu,
+csrc/decoder.cu; statistical quality: tests/test_gpu_parity.py::test_fused_dropout_hash_statistics).
 
 Construct it before (or after dropping) any eager autograd graph of the same model: a live graph keeps the
 parameters' AccumulateGrad nodes bound to the stream they were created on, which a capture cannot depend on.
@@ -92,6 +94,8 @@ class GraphedTrainStep:
                 self._step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from . import ops as _ops
+        _ops.raise_on_bad_pairs(dev)                     # an out-of-range index in the warm-up batch surfaces here
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.scores = self._step()

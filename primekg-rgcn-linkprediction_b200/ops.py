@@ -469,12 +469,14 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
 
 def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], mask_scale: float, planes, W2d: torch.Tensor,
               root: torch.Tensor, d_in: int, mode: str, need_x: bool, add_root_term: bool, need_w: bool, need_b: bool,
-              gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None, g_ready=None, next_mask=None):
+              gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None, g_ready=None, next_mask=None,
+              slot: Optional[torch.Tensor] = None):
     """split(gO, mask) -> dgrad -> transposed gather -> wgrad of one layer in ONE C call (``rgcn_layer_bwd``).
     Returns (g_x | None, gA | None, gW2d | None, g_root | None, g_bias | None); ``gA[:, R*d_in:]`` is the root-term
     gradient (already inside g_x when ``add_root_term``).
     ``rows`` (int64 device list, duplicates allowed): the caller guarantees gO is zero outside these rows; the backward
     then runs on the compacted rows (csrc/rowsparse.cu) with the same results, and gA comes back compact (``None`` here).
+    ``slot`` (int32 [n]): the node -> first-position map of ``rows``, already built by the decoder's backward.
     ``g_ready`` = ((G_hi, G_lo | None), colsum [n, d_out]): this layer's masked output gradient as planes, already written
     by the downstream layer (skips the split pass).  ``next_mask`` = (mask [n_src, d_in], scale): also produce g_x masked
     for the upstream layer; the result gains a sixth entry ((hi, lo | None), colsum)."""
@@ -517,7 +519,11 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
     gW = param_grad(K1, d_out, device=dev) if need_w else None
     groot = param_grad(d_in, d_out, device=dev) if need_w else None
     gb = param_grad(d_out, device=dev) if (need_w and need_b) else None
-    slot = torch.empty(n, dtype=torch.int32, device=dev) if sparse else None
+    slot_ready = bool(sparse and slot is not None)
+    if slot_ready and (slot.dtype != torch.int32 or slot.numel() != n or not slot.is_contiguous()):
+        raise ValueError("slot must be a contiguous int32 [n_dst] tensor")
+    if not slot_ready:
+        slot = torch.empty(n, dtype=torch.int32, device=dev) if sparse else None
     Ac = alloc_planes(m, K, mode, dev) if (sparse and need_w) else (None, None)
     nxt = nxt_struct = None
     if next_mask is not None and need_x:
@@ -540,7 +546,7 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         _dp(rows), 0 if rows is None else rows.numel(), _dp(slot), _dp(Ac[0]), _dp(Ac[1]),
         0 if Ac[0] is None else Ac[0].stride(0),
         C.pointer(nxt_struct) if nxt_struct is not None else None, int(g_ready is not None),
-        0 if g_ready is None else colsum.size(0))
+        0 if g_ready is None else colsum.size(0), int(slot_ready))
     _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
     if next_mask is not None:
         return gx, (None if sparse else gA), gW, groot, gb, nxt
@@ -642,16 +648,72 @@ def link_batch(pos_head: torch.Tensor, pos_tail: torch.Tensor, pos_rel: torch.Te
 
 
 _LINK_WS = {}
+_PAIR_STATUS = {}
 
 
 def _link_workspace(device, n_pairs: int) -> torch.Tensor:
-    """Zero-initialised partial / ticket buffer of the fused loss kernel (the kernel leaves the ticket at zero)."""
-    key = (str(device), int(n_pairs))      # calls are stream-ordered per device in this package
+    """Zero-initialised partial / ticket buffer of the fused loss kernel (the kernel leaves the ticket at zero).
+    One buffer per (device, STREAM, batch size): two streams issuing the same batch size never share a ticket."""
+    key = (str(device), _stream_id(device), int(n_pairs))
     ws = _LINK_WS.get(key)
     if ws is None:
         ws = torch.zeros(int(_lib.load().rgcn_link_loss_workspace_bytes(n_pairs)), dtype=torch.uint8, device=device)
         _LINK_WS[key] = ws
     return ws
+
+
+def pair_status(device) -> torch.Tensor:
+    """Device flag (int32 [1]) the fused decoder kernels set when they meet an out-of-range head / tail / relation index
+    (the pair is skipped: NaN score and loss, no gradient).  Polled by ``raise_on_bad_pairs``."""
+    key = str(device)
+    st = _PAIR_STATUS.get(key)
+    if st is None:
+        st = _PAIR_STATUS[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return st
+
+
+def raise_on_bad_pairs(device=None) -> None:
+    """Raise IndexError if any fused decoder call since the last check met an out-of-range index (synchronises).  The
+    reference's ``node_embeddings[idx]`` / ``nn.Embedding`` raise a device-side assert in the same situation; here the
+    kernels skip the pair and the check is lazy: ``GraphedTrainStep`` polls after its warm-up steps, the modules poll on
+    every call when ``PRIMEKG_RGCN_CHECK_PAIRS=1``, and a NaN loss is the always-visible symptom."""
+    for key, st in list(_PAIR_STATUS.items()):
+        if device is not None and key != str(device):
+            continue
+        if int(st.item()):
+            st.zero_()
+            raise IndexError("head / tail / relation index out of range in a link-prediction batch "
+                             "(the offending pairs were skipped: NaN score, no gradient)")
+
+
+def _check_pairs_now() -> bool:
+    import os
+    return os.environ.get("PRIMEKG_RGCN_CHECK_PAIRS", "0") == "1"
+
+
+def _link_bwd(ctx_p_drop, ctx_seed, emb, rel_table, head, tail, rel, labels, score, state, g_loss, g_score, need_emb,
+              need_tab):
+    """Deterministic backward of the fused decoder (``rgcn_link_loss_bwd_rows``): returns (g_emb | None, g_tab | None)
+    and announces the row list + slot map to the last encoder layer's row-sparse backward."""
+    from . import rowsparse
+    lib = _lib.load()
+    dev = emb.device
+    n, d, n_nodes, n_rel = head.numel(), emb.size(1), emb.size(0), rel_table.size(0)
+    g_emb = torch.empty(n_nodes, d, dtype=torch.float32, device=dev)        # every row written exactly once by the kernel
+    g_tab = param_grad(*rel_table.shape, device=dev) if need_tab else None
+    slot = torch.empty(n_nodes, dtype=torch.int32, device=dev)
+    rows = torch.empty(2 * n, dtype=torch.int64, device=dev)
+    nb = int(lib.rgcn_link_bwd_rows_workspace_bytes(n, n_rel, d)) if need_tab else 0
+    ws = _workspace(dev, nb) if need_tab else None
+    _lib.check(lib.rgcn_link_loss_bwd_rows(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
+                                           _ptr(labels), _ptr(score), _ptr(g_loss), _ptr(g_score), n, d, ctx_p_drop,
+                                           ctx_seed & 0xFFFFFFFF, _ptr(state), n_nodes, n_rel, _ptr(g_emb), g_emb.stride(0),
+                                           _ptr(g_tab), _ptr(slot), _ptr(rows), _ptr(pair_status(dev)), _ptr(ws),
+                                           0 if ws is None else ws.numel(), _stream(dev)), "rgcn_link_loss_bwd_rows")
+    if not need_emb:
+        return None, g_tab
+    rowsparse.announce(g_emb, rows, slot)                   # zero outside the head / tail rows
+    return g_emb, g_tab
 
 
 class _LinkLoss(torch.autograd.Function):
@@ -675,7 +737,10 @@ class _LinkLoss(torch.autograd.Function):
         _lib.check(lib.rgcn_link_loss_fwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
                                           _ptr(labels), n, d, float(p_drop), int(seed) & 0xFFFFFFFF,
                                           _ptr(counter if p_drop > 0 else None), _ptr(state), _ptr(score), _ptr(loss),
-                                          _ptr(correct), _ptr(ws), ws.numel(), _stream(dev)), "rgcn_link_loss_fwd")
+                                          _ptr(correct), emb.size(0), rel_table.size(0), _ptr(pair_status(dev)),
+                                          _ptr(ws), ws.numel(), _stream(dev)), "rgcn_link_loss_fwd")
+        if _check_pairs_now():
+            raise_on_bad_pairs(dev)
         ctx.save_for_backward(emb, rel_table, head, tail, rel, labels, score, state)
         ctx.p_drop, ctx.seed = float(p_drop), int(seed)
         ctx.mark_non_differentiable(score, correct)
@@ -684,25 +749,12 @@ class _LinkLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _gs, _gc):
-        from . import rowsparse
-        lib = _lib.load()
         emb, rel_table, head, tail, rel, labels, score, state = ctx.saved_tensors
-        dev = emb.device
         if g_loss is None:
             return (None,) * 9
         g_loss = g_loss.to(torch.float32).contiguous()
-        g_emb = torch.zeros_like(emb, memory_format=torch.contiguous_format)
-        g_tab = None
-        if ctx.needs_input_grad[1]:
-            g_tab = param_grad(*rel_table.shape, device=dev)
-            g_tab.zero_()
-        _lib.check(lib.rgcn_link_loss_bwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
-                                          _ptr(labels), _ptr(score), _ptr(g_loss), None, head.numel(), emb.size(1), ctx.p_drop,
-                                          ctx.seed & 0xFFFFFFFF, _ptr(state), _ptr(g_emb), g_emb.stride(0), _ptr(g_tab),
-                                          rel_table.size(0), _stream(dev)), "rgcn_link_loss_bwd")
-        if not ctx.needs_input_grad[0]:
-            return None, g_tab, None, None, None, None, None, None, None
-        rowsparse.announce(g_emb, torch.cat([head, tail]))     # zero outside the head / tail rows
+        g_emb, g_tab = _link_bwd(ctx.p_drop, ctx.seed, emb, rel_table, head, tail, rel, labels, score, state, g_loss, None,
+                                 ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return g_emb, g_tab, None, None, None, None, None, None, None
 
 
@@ -774,31 +826,23 @@ class _PairScores(torch.autograd.Function):
             _lib.check(lib.rgcn_link_loss_fwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
                                               None, n, d, float(p_drop), int(seed) & 0xFFFFFFFF,
                                               _ptr(counter if p_drop > 0 else None), _ptr(state), _ptr(score), None, None,
+                                              emb.size(0), rel_table.size(0), _ptr(pair_status(dev)),
                                               _ptr(ws), ws.numel(), _stream(dev)), "rgcn_link_loss_fwd")
+            if _check_pairs_now():
+                raise_on_bad_pairs(dev)
         ctx.save_for_backward(emb, rel_table, head, tail, rel, state)
         ctx.p_drop, ctx.seed = float(p_drop), int(seed)
         return score
 
     @staticmethod
     def backward(ctx, g_score):
-        from . import rowsparse
-        lib = _lib.load()
         emb, rel_table, head, tail, rel, state = ctx.saved_tensors
-        dev = emb.device
         g_score = g_score.to(torch.float32).contiguous()
-        g_emb = torch.zeros_like(emb, memory_format=torch.contiguous_format)
-        g_tab = None
-        if ctx.needs_input_grad[1]:
-            g_tab = param_grad(*rel_table.shape, device=dev)
-            g_tab.zero_()
-        if head.numel():
-            _lib.check(lib.rgcn_link_loss_bwd(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
-                                              None, None, None, _ptr(g_score), head.numel(), emb.size(1), ctx.p_drop,
-                                              ctx.seed & 0xFFFFFFFF, _ptr(state), _ptr(g_emb), g_emb.stride(0), _ptr(g_tab),
-                                              rel_table.size(0), _stream(dev)), "rgcn_link_loss_bwd")
-        if not ctx.needs_input_grad[0]:
-            return None, g_tab, None, None, None, None, None, None
-        rowsparse.announce(g_emb, torch.cat([head, tail]))     # zero outside the head / tail rows
+        if head.numel() == 0:
+            return (torch.zeros_like(emb) if ctx.needs_input_grad[0] else None,
+                    torch.zeros_like(rel_table) if ctx.needs_input_grad[1] else None, None, None, None, None, None, None)
+        g_emb, g_tab = _link_bwd(ctx.p_drop, ctx.seed, emb, rel_table, head, tail, rel, None, None, state, None, g_score,
+                                 ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return g_emb, g_tab, None, None, None, None, None, None
 
 

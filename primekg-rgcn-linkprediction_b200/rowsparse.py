@@ -18,7 +18,8 @@ import torch
 
 MAX_FRACTION = 0.5     # longer row lists (relative to the node count) take the dense backward
 stats = {"claimed": 0, "declined": 0}      # how often the last layer took the compact / the dense backward
-_announced = None      # (dense gradient tensor, its _version when announced, int64 device list of the rows written)
+_announced = None      # (dense gradient tensor, its _version when announced, int64 device list of the rows written,
+                       #  int32 node -> first-position map of that list | None)
 
 
 def enabled() -> bool:
@@ -32,28 +33,29 @@ def planes_enabled() -> bool:
     return enabled() and os.environ.get("PRIMEKG_RGCN_PLANES_HANDOVER", "0") == "1"
 
 
-def announce(dense: torch.Tensor, rows: torch.Tensor) -> None:
+def announce(dense: torch.Tensor, rows: torch.Tensor, slot: Optional[torch.Tensor] = None) -> None:
     """``dense`` is zero outside ``rows`` (duplicates allowed).  Holding the tensor keeps its storage from being reused
-    while the announcement stands, which is what makes the pointer comparison in ``claim`` sound."""
+    while the announcement stands, which is what makes the pointer comparison in ``claim`` sound.  ``slot``: the
+    node -> first-position map of ``rows`` when the announcer has built it (``rgcn_link_loss_bwd_rows``)."""
     global _announced
-    _announced = (dense, dense._version, rows) if enabled() else None
+    _announced = (dense, dense._version, rows, slot) if enabled() else None
 
 
-def claim(grad: torch.Tensor) -> Optional[torch.Tensor]:
-    """The announced row list if ``grad`` is the announced buffer, untouched, and short enough to pay off; else None.
+def claim(grad: torch.Tensor):
+    """(rows, slot | None) if ``grad`` is the announced buffer, untouched, and short enough to pay off; else None.
     An announcement is consumed by the first claim attempt."""
     global _announced
     a, _announced = _announced, None
     if a is None:
         return None
-    dense, version, rows = a
+    dense, version, rows, slot = a
     same = (grad.data_ptr() == dense.data_ptr() and grad.shape == dense.shape and grad.stride() == dense.stride()
             and grad.dtype == dense.dtype and grad._version == version and dense._version == version)
     if not same or rows.numel() == 0 or rows.numel() > MAX_FRACTION * grad.size(0):
         stats["declined"] += 1
         return None
     stats["claimed"] += 1
-    return rows
+    return rows, slot
 
 
 # ---- second hand-over: a layer's backward walk has already written its input gradient, masked for the layer upstream,

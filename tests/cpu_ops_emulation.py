@@ -75,7 +75,7 @@ def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, drop
 
 
 def layer_bwd(g, gO, relu_mask, mask_scale, planes, W2d, root, d_in, mode, need_x, add_root_term, need_w, need_b,
-              gx_out=None, rows=None, g_ready=None, next_mask=None):
+              gx_out=None, rows=None, g_ready=None, next_mask=None, slot=None):
     assert g_ready is None and next_mask is None
     d_out = gO.size(1)
     K1 = g.R * d_in

@@ -395,6 +395,189 @@ def test_full_size_step_against_oracle_on_device(pkg, cfg2, mode):
             torch.testing.assert_close(p.grad, q.grad, rtol=1e-2, atol=1e-2 * scale, msg=lambda t: f"{mode}/{k}: {t}")
 
 
+
+def test_full_size_gradients_with_matched_relu_pattern(pkg, cfg2):
+    """Why ``test_full_size_step_against_oracle_on_device`` holds the gradients only in norm: with 7.9 M hidden
+    activations a few ReLU inputs sit within rounding distance of zero and their 0 / 1 derivative differs between two
+    correct fp32 evaluation orders.  SHOWN here, not asserted: (1) the activation patterns of the two implementations
+    differ ONLY at elements whose oracle pre-activation is below 2e-5 * max|z| (the forward's rounding band);
+    (2) once the oracle differentiates through OUR pattern (h = z * [ours > 0]) every gradient agrees element-wise
+    at rtol 1e-3 — the bar of the small golden fixtures — with an absolute floor of 1e-4 of the tensor's scale."""
+    kg, (heads, tails, rels, labels) = cfg2
+    torch.manual_seed(42)
+    m = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, 256, dropout=0.0, decoder_dropout=0.0)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if "conv" in k and not k.endswith("bias"):
+                p.mul_(4.0)
+    ref = O.ModelRef(kg.num_nodes, kg.num_relations, 64, 256, 0.0, 0.0)
+    ref.load_state_dict(m.state_dict())
+    for c in (m.encoder.conv1, m.encoder.conv2):
+        c.mode = "fp32"
+    m.to(DEV).train(); ref.to(DEV).train()
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    b = [t.to(DEV) for t in (heads, tails, rels, labels)]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        s = m(ei, et, b[0], b[1], b[2])
+        F.binary_cross_entropy_with_logits(s, b[3]).backward()
+        with torch.no_grad():
+            graph = pkg.get_graph(ei, et, kg.num_nodes, kg.num_relations)
+            ours_on = m.encoder.conv1.forward_graph(m.encoder.node_embeddings.weight, graph, relu=True) > 0
+        enc = ref.encoder
+        z1 = enc.conv1(enc.node_embeddings.weight, ei, et)
+        flips = ours_on != (z1 > 0)
+        band = 2e-5 * float(z1.detach().abs().max())
+        n_flip = int(flips.sum())
+        assert n_flip < 1e-3 * z1.numel(), n_flip
+        if n_flip:
+            worst = float(z1.detach().abs()[flips].max())
+            assert worst < band, f"{n_flip} ReLU flips, the largest at |z| = {worst:.3e} (band {band:.3e})"
+        h = z1 * ours_on.to(z1.dtype)                      # relu(z1) up to the band; derivative = OUR pattern
+        emb = enc.conv2(h, ei, et)
+        rs = ref.decoder(emb[b[0]], emb[b[1]], b[2])
+        F.binary_cross_entropy_with_logits(rs, b[3]).backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    torch.testing.assert_close(s.detach(), rs.detach(), rtol=1e-4, atol=1e-5 * max(1.0, float(rs.abs().max())))
+    for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        scale = float(q.grad.abs().max()) + 1e-30
+        torch.testing.assert_close(p.grad, q.grad, rtol=1e-3, atol=1e-4 * scale,
+                                   msg=lambda t: f"{k} ({n_flip} pattern flips inside the band): {t}")
+
+
+@pytest.mark.parametrize("decoder_dropout", [0.0, 0.1])
+def test_step_is_bitwise_deterministic(pkg, cfg2, decoder_dropout):
+    """determinism end to end.  Two runs of the same step (hub-heavy batch: repeated head / tail nodes; the
+    decoder's backward sums them in position order, csrc/decoder.cu link_bwd_rows_kernel) give bit-identical gradients
+    for EVERY parameter, the embedding table and the relation table included."""
+    kg, (heads, tails, rels, labels) = cfg2
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    b = [t.to(DEV) for t in (heads, tails, rels, labels)]
+    assert torch.unique(torch.cat([b[0], b[1]])).numel() < 2 * b[0].numel()          # the batch does repeat nodes
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(7)
+        m = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, 256, dropout=0.0,
+                                 decoder_dropout=decoder_dropout).to(DEV)
+        m.train()
+        s = m(ei, et, b[0], b[1], b[2])
+        F.binary_cross_entropy_with_logits(s, b[3]).backward()
+        loss2, _, _ = m.link_loss(ei, et, b[0], b[1], b[2], b[3])
+        g2 = torch.autograd.grad(loss2, [m.encoder.node_embeddings.weight, m.decoder.relation_embeddings.weight])
+        runs.append(({k: p.grad.clone() for k, p in m.named_parameters()}, [g.clone() for g in g2]))
+    for k in runs[0][0]:
+        assert torch.equal(runs[0][0][k], runs[1][0][k]), k
+    for a, c in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, c)
+
+
+def test_decoder_backward_rows_matches_reference_formula(pkg):
+    """The deterministic decoder backward against autograd of the plain formula (repeated nodes, self pairs h == t,
+    a relation nobody uses, d not a multiple of 128)."""
+    torch.manual_seed(11)
+    N, d, R, B = 50, 72, 4, 300
+    emb = torch.randn(N, d, device=DEV, requires_grad=True)
+    dec = pkg.LinkPredictor(R, d).to(DEV)
+    heads = torch.randint(0, 12, (B,), device=DEV)                  # 12 nodes only: every node repeats many times
+    tails = torch.randint(0, N, (B,), device=DEV)
+    tails[:20] = heads[:20]                                          # self pairs
+    rels = torch.randint(0, R - 1, (B,), device=DEV)                 # relation R-1 unused: its gradient row is exactly 0
+    coef = torch.randn(B, device=DEV)
+    s = dec.score_pairs(emb, heads, tails, rels)
+    (s * coef).sum().backward()
+    e2 = emb.detach().clone().requires_grad_()
+    t2 = dec.relation_embeddings.weight.detach().clone().requires_grad_()
+    s2 = (e2[heads] * t2[rels] * e2[tails]).sum(1)
+    (s2 * coef).sum().backward()
+    torch.testing.assert_close(s.detach(), s2.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(emb.grad, e2.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dec.relation_embeddings.weight.grad, t2.grad, rtol=1e-4, atol=1e-4)
+    assert float(dec.relation_embeddings.weight.grad[R - 1].abs().sum()) == 0.0
+    assert float(emb.grad[torch.tensor([i for i in range(N) if i not in set(heads.tolist()) | set(tails.tolist())],
+                                       device=DEV, dtype=torch.long)].abs().sum()) == 0.0
+
+
+def test_out_of_range_pair_is_skipped_and_flagged(pkg):
+    """The reference's ``node_embeddings[idx]`` raises a device assert on a bad index; the fused decoder skips the pair
+    (NaN score, no gradient, no out-of-bounds access) and ``ops.raise_on_bad_pairs`` reports it."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    torch.manual_seed(12)
+    N, d, R, B = 40, 64, 3, 16
+    emb = torch.randn(N, d, device=DEV, requires_grad=True)
+    dec = pkg.LinkPredictor(R, d).to(DEV)
+    heads = torch.randint(0, N, (B,), device=DEV)
+    tails = torch.randint(0, N, (B,), device=DEV)
+    rels = torch.randint(0, R, (B,), device=DEV)
+    ops.raise_on_bad_pairs(emb.device)                               # clean slate
+    good = dec.score_pairs(emb, heads, tails, rels).detach()
+    ops.raise_on_bad_pairs(emb.device)                               # nothing to report
+    bad_h, bad_r = heads.clone(), rels.clone()
+    bad_h[3] = N + 5
+    bad_r[7] = -1
+    s = dec.score_pairs(emb, bad_h, tails, bad_r)
+    assert torch.isnan(s[3]) and torch.isnan(s[7])
+    keep = torch.ones(B, dtype=torch.bool, device=DEV)
+    keep[3] = keep[7] = False
+    torch.testing.assert_close(s.detach()[keep], good[keep], rtol=0, atol=0)
+    torch.nan_to_num(s, nan=0.0).sum().backward()
+    assert torch.isfinite(emb.grad).all() and torch.isfinite(dec.relation_embeddings.weight.grad).all()
+    e2 = emb.detach().clone().requires_grad_()
+    (e2[heads[keep]] * dec.relation_embeddings.weight.detach()[rels[keep]] * e2[tails[keep]]).sum().backward()
+    torch.testing.assert_close(emb.grad, e2.grad, rtol=1e-4, atol=1e-5)          # the two bad pairs left no trace
+    with pytest.raises(IndexError):
+        ops.raise_on_bad_pairs(emb.device)
+    ops.raise_on_bad_pairs(emb.device)                               # the flag is cleared by the report
+
+
+def test_fused_dropout_hash_statistics(pkg):
+    """The fused dropout draws its mask from a counter-based hash (csrc/transform.cu), not from torch's Philox stream;
+    what a dropout mask needs is tested here on 2.6 M elements per step: keep rate, independence of neighbouring elements
+    along rows and columns (2 x 2 chi-square, 1 degree of freedom), no serial correlation at lags 1..4 in memory order,
+    independence between consecutive steps, and 16-bit resolution of p."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    n, K, d_out = 20_000, 8, 128
+    A = torch.zeros(n, K, device=DEV)
+    planes = ops.alloc_planes(n, K, "bf16", A.device)
+    ops.split_planes(A, planes)
+    W = torch.zeros(K, d_out, device=DEV)
+    bias = torch.ones(d_out, device=DEV)
+    ctr = ops.dropout_counter(A.device)
+
+    def mask(p, seed):
+        out = ops.transform_fwd(planes, K, 0, W, None, bias, True, "bf16", p, seed, ctr)       # = 1 / (1 - p) where kept
+        return out > 0
+
+    def chi2(a, c):                                       # 2 x 2 contingency of two boolean tensors
+        a, c = a.reshape(-1).double(), c.reshape(-1).double()
+        nn_ = a.numel()
+        o = torch.stack([(a * c).sum(), (a * (1 - c)).sum(), ((1 - a) * c).sum(), ((1 - a) * (1 - c)).sum()])
+        pa, pc = a.mean(), c.mean()
+        e = nn_ * torch.stack([pa * pc, pa * (1 - pc), (1 - pa) * pc, (1 - pa) * (1 - pc)])
+        return float(((o - e) ** 2 / e).sum())
+
+    for p in (0.5, 0.1, 0.9):
+        m0, m1 = mask(p, 1234), mask(p, 1234)              # consecutive steps of one stream
+        tot = m0.numel()
+        sd = (p * (1 - p) / tot) ** 0.5
+        assert abs(float(m0.float().mean()) - (1 - p)) < 5 * sd + 2.0 ** -16
+        assert chi2(m0[:, :-1], m0[:, 1:]) < 20.0          # chi-square(1): P(> 20) ~ 8e-6
+        assert chi2(m0[:-1, :], m0[1:, :]) < 20.0
+        assert chi2(m0, m1) < 20.0
+        flat = m0.reshape(-1).double() - (1 - p)
+        for lag in (1, 2, 3, 4):
+            rho = float((flat[:-lag] * flat[lag:]).mean() / (p * (1 - p)))
+            assert abs(rho) < 5.0 / tot ** 0.5, (p, lag, rho)
+        assert (m0 != m1).any()
+        assert (mask(p, 99) != mask(p, 1234)).any()        # another seed, another stream
+    # per-row and per-column keep counts are binomial: the largest z-score over 20,000 rows stays below 6
+    m = mask(0.5, 5)
+    z_rows = (m.double().sum(1) - 0.5 * d_out) / (0.25 * d_out) ** 0.5
+    z_cols = (m.double().sum(0) - 0.5 * n) / (0.25 * n) ** 0.5
+    assert float(z_rows.abs().max()) < 6.0 and float(z_cols.abs().max()) < 6.0
+
+
 def test_full_size_properties(pkg, cfg2):
     """Size-independent properties at 849,456 edges: linearity of the aggregation, the count-weighted
     checksum  sum_i cnt(i, r) * H_r[i] = sum_{e of type r} x[src[e]], and adjointness <agg(x), g> = <x, agg^T(g)>."""
@@ -874,8 +1057,7 @@ def _close_by_scale(a, b, what, rtol=1e-4, atol=2e-5):
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_sparse_last_layer_backward_equals_dense(pkg, monkeypatch, mode):
     """The loss reads 2 * batch rows of the encoder output (reference src/models/rgcn.py:325-326): the compact backward of
-    the last layer must give the dense backward's gradients.  (Not compared bitwise here: the decoder's backward adds the
-    rows of repeated nodes with fp32 atomics, so gO itself differs in the last bit between two runs.)"""
+    the last layer must give the dense backward's gradients."""
     g = load_golden("small_full")
     dense, st0 = _step_grads(pkg, g, False, monkeypatch, mode=mode)
     sparse, st1 = _step_grads(pkg, g, True, monkeypatch, mode=mode)

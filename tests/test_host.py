@@ -26,7 +26,7 @@ def test_library_exports_every_header_symbol(lib_built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rgcn_b200.h but not exported"
     assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
-    assert _lib.load().rgcn_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.load().rgcn_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_library_argument_errors_without_gpu(lib_built):
@@ -165,7 +165,8 @@ def test_rowsparse_handover_guards(lib_built, monkeypatch):
     dense = torch.zeros(100, 8)
     rows = torch.tensor([3, 7, 3])
     rowsparse.announce(dense, rows)
-    assert rowsparse.claim(dense) is rows and rowsparse.claim(dense) is None          # consumed
+    got = rowsparse.claim(dense)
+    assert got[0] is rows and got[1] is None and rowsparse.claim(dense) is None         # consumed
     rowsparse.announce(dense, rows)
     assert rowsparse.claim(dense.clone()) is None                                      # another buffer (engine summed a copy)
     rowsparse.announce(dense, rows)
