@@ -177,7 +177,8 @@ def _glorot_(t: Optional[torch.Tensor]) -> None:
     # torch_geometric.nn.inits.glorot: fans are the LAST TWO dims (not nn.init.xavier_uniform_'s)
     if t is not None:
         a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
-        t.data.uniform_(-a, a)
+        with torch.no_grad():
+            t.uniform_(-a, a)               # (not t.data.uniform_: in-place writes must bump the version counter)
 
 
 class RGCNConv(nn.Module):
@@ -204,7 +205,8 @@ class RGCNConv(nn.Module):
         _glorot_(self.weight)
         _glorot_(self.comp)
         _glorot_(self.root)
-        self.bias.data.zero_()
+        with torch.no_grad():
+            self.bias.zero_()
 
     def relation_weights(self) -> torch.Tensor:
         """[R, d_in, d_out]; with bases W_r = sum_b comp[r, b] V_b (differentiable)."""

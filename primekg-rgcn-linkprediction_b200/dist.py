@@ -149,7 +149,8 @@ class PartitionedRGCN(nn.Module):
             for prm in (conv.weight, conv.comp, conv.root):
                 if prm is not None:
                     a = (6.0 / (prm.size(-2) + prm.size(-1))) ** 0.5
-                    prm.data.copy_((torch.rand(prm.shape, generator=g) * 2 - 1) * a)
+                    with torch.no_grad():
+                        prm.copy_((torch.rand(prm.shape, generator=g) * 2 - 1) * a)
         # the shard's rows of the Xavier-initialised table; padding rows are zero and never gathered
         table = torch.zeros(plan.max_n, embedding_dim)
         a = (6.0 / (sum(plan.size(p) for p in range(plan.world)) + embedding_dim)) ** 0.5

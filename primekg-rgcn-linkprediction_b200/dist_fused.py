@@ -16,6 +16,9 @@ tile; only a device-side barrier separates the layers.  Backward:
 
 Weight gradients are all-reduced once per step as one flat NCCL call (plumbing).  Two halves of one peer buffer
 alternate between layers; the per-layer barrier is what makes the reuse safe (a rank can only be one layer ahead).
+The encoder's OUTPUT lives in a third, dedicated region and every forward starts with a barrier, so a fast rank can
+never overwrite what a slow rank's decoder is still reading (forward-only loops included).  The output is valid until
+the next forward; only one forward may be outstanding per backward (checked: ``_Exchange.generation``).
 Everything is deterministic: fixed reduction orders everywhere, no atomics.
 
 The NCCL form in ``dist.py`` (all-gather / reduce-scatter / all-reduce with autograd) stays as the baseline this
@@ -45,17 +48,24 @@ class _Exchange:
         self.row0 = rank * plan.max_n
         self.half = self.n_total * max(dims)               # floats per half
         self.half = (self.half + 63) // 64 * 64
-        self.x = PeerBuffer(2 * self.half * 4, device)
+        # features: two halves that alternate between the layers + a DEDICATED region for the encoder's output, so the
+        # tensor a forward returns is never a buffer the next forward's initial push stores into
+        self.x = PeerBuffer(3 * self.half * 4, device)
         self.g = PeerBuffer(2 * self.half * 4, device)
+        self.n_layers = len(dims) - 1
+        self.generation = 0                                # bumped by every forward; a backward checks it is the latest
+
+    def _x_off(self, k: int) -> int:
+        return 2 * self.half if k == self.n_layers else (k % 2) * self.half
 
     def x_view(self, k: int, d: int) -> torch.Tensor:
-        return self.x.view(self.n_total, d, (k % 2) * self.half)
+        return self.x.view(self.n_total, d, self._x_off(k))
 
     def g_view(self, k: int, d: int) -> torch.Tensor:
         return self.g.view(self.n_total, d, (k % 2) * self.half)
 
     def x_ptrs(self, k: int) -> List[int]:
-        return self.x.peer_ptrs((k % 2) * self.half)
+        return self.x.peer_ptrs(self._x_off(k))
 
     def g_ptrs(self, k: int) -> List[int]:
         return self.g.peer_ptrs((k % 2) * self.half)
@@ -70,6 +80,13 @@ class _FusedEncoderFn(torch.autograd.Function):
         L = len(params) // 3
         n, row0 = ex.max_n, ex.row0
         x0 = x0.contiguous()
+        if L != ex.n_layers:
+            raise ValueError("the exchange buffers were sized for another number of layers")
+        ex.generation += 1
+        # every rank must be done with the PREVIOUS call's buffers (its decoder reading the output region, its last layer
+        # reading half (L-1) % 2) before anybody stores into them again: in training the backward's barriers imply it, in
+        # forward-only loops (evaluation) nothing else does
+        ex.x.barrier()
         ops.p2p_push_rows(x0, ex.x_ptrs(0), row0, x0.size(1))
         ex.x.barrier()
         saved, outs = [], []
@@ -87,6 +104,7 @@ class _FusedEncoderFn(torch.autograd.Function):
             saved += [A[0], A[1], W, root]
             outs.append(None if last else out)          # post-ReLU/dropout output = the backward mask
         ctx.ex, ctx.graph, ctx.mode, ctx.L = ex, graph, mode, L
+        ctx.generation = ex.generation
         ctx.p_drops = [d[0] if d is not None else 0.0 for d in drops]
         ctx.d0 = x0.size(1)
         ctx.save_for_backward(*saved, *[o for o in outs if o is not None])
@@ -96,6 +114,11 @@ class _FusedEncoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_full):
         ex, graph, mode, L = ctx.ex, ctx.graph, ctx.mode, ctx.L
+        if ctx.generation != ex.generation:
+            # the returned embeddings (saved by the decoder for ITS backward) live in the peer buffer and a later forward
+            # has rewritten them through raw pointers, which autograd's version counters cannot see
+            raise RuntimeError("FusedPartitionedRGCN: backward of a forward that is no longer the latest one; only one "
+                               "forward may be outstanding per backward (clone the output to keep it across forwards)")
         n, row0 = ex.max_n, ex.row0
         t = ctx.saved_tensors
         masks = list(t[4 * L:])

@@ -56,13 +56,31 @@ class DrugDiseaseRGCN(nn.Module):
     def _init_embeddings(self) -> None:
         nn.init.xavier_uniform_(self.node_embeddings.weight)
 
-    def _eval_key(self, graph):
-        """Identity of an eval-mode encoding: the graph object and every parameter's storage + in-place version
-        (optimizer steps, ``load_state_dict`` and ``.to()`` all change one of them)."""
+    def _eval_key(self):
+        """Identity of an eval-mode encoding besides the graph object: every parameter's storage + in-place version
+        (optimizer steps, ``load_state_dict`` and ``.to()`` all change one of them).  Writes that bypass the version
+        counter (``p.data`` tricks, raw-pointer or graph-replayed updates) are covered by the cache's LIFETIME instead:
+        it is dropped by every ``train()`` / ``eval()`` switch, ``.to()`` / ``_apply``, ``load_state_dict`` and
+        ``invalidate_eval_cache()``, so it only ever spans one evaluation phase."""
         ps = tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
         modes = tuple(c.mode for c in self._layers())
-        return (id(graph), graph.E, ps, modes, os.environ.get("PRIMEKG_RGCN_MODE", ""),
-                os.environ.get("PRIMEKG_RGCN_BASIS_FORM", ""))
+        return (ps, modes, os.environ.get("PRIMEKG_RGCN_MODE", ""), os.environ.get("PRIMEKG_RGCN_BASIS_FORM", ""))
+
+    def invalidate_eval_cache(self) -> None:
+        """Forget the cached eval-mode encoding (call after changing parameters behind autograd's back)."""
+        self._eval_cache = None
+
+    def train(self, mode: bool = True):
+        self._eval_cache = None                  # also frees the [N, hidden] tensor for the training epochs
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._eval_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._eval_cache = None
+        return super().load_state_dict(*args, **kwargs)
 
     def _layers(self):
         yield self.conv1
@@ -80,10 +98,10 @@ class DrugDiseaseRGCN(nn.Module):
         # result is a pure function of (graph, parameters): keep the last one and hand it back while neither changed.
         cacheable = not self.training and not torch.is_grad_enabled() and node_indices is None
         if cacheable:
-            key = self._eval_key(graph)
-            hit = self._eval_cache
-            if hit is not None and hit[0] == key and hit[1]._version == hit[2]:
-                return hit[1]
+            key = self._eval_key()
+            hit = self._eval_cache          # (key, graph — a strong reference, so its id can never be recycled —, x, version)
+            if hit is not None and hit[1] is graph and hit[0] == key and hit[2]._version == hit[3]:
+                return hit[2]
         layers = list(self._layers())
         in_scale = None         # 1 / (1 - p) of the fused ReLU / dropout that produced x (None: x is not such an output)
         for li, conv in enumerate(layers):
@@ -95,7 +113,7 @@ class DrugDiseaseRGCN(nn.Module):
             if not last and p >= 1.0:
                 x = self.dropout(x)
         if cacheable:
-            self._eval_cache = (key, x, x._version)
+            self._eval_cache = (key, graph, x, x._version)
         return x
 
     def get_node_embeddings(self, node_indices: torch.Tensor) -> torch.Tensor:

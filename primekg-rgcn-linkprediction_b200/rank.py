@@ -154,10 +154,27 @@ def rank_true_tails(emb: torch.Tensor, rel_table: torch.Tensor, heads: torch.Ten
     return greater.to(torch.int64) + 1, equal.to(torch.int64)
 
 
-def ranking_metrics(ranks: torch.Tensor, k_values=(1, 3, 10, 50, 100)) -> dict:
-    """MRR / mean / median rank / Hits@K as assembled at src/evaluate.py:278-291."""
+def ranking_metrics(ranks: torch.Tensor, k_values=(1, 3, 10, 50, 100), ties: Optional[torch.Tensor] = None,
+                    tie_policy: str = "optimistic") -> dict:
+    """MRR / mean / median rank / Hits@K as assembled at src/evaluate.py:278-291.
+
+    ``median_rank`` is numpy's median (the MEAN of the two middle order statistics for an even count, as
+    ``np.median(ranks)`` at src/evaluate.py:283; ``torch.median`` would return the lower one).
+    Ties: ``rank_true_tails`` returns the OPTIMISTIC rank 1 + #{strictly greater}; the reference's position in an
+    unstable ``argsort`` is arbitrary inside [rank, rank + ties].  ``tie_policy="mean"`` (needs ``ties``) reports the
+    expected rank rank + ties / 2 instead, ``"pessimistic"`` rank + ties."""
     r = ranks.to(torch.float64)
-    out = {"mrr": float((1.0 / r).mean()), "mean_rank": float(r.mean()), "median_rank": float(r.median())}
+    if tie_policy != "optimistic":
+        if ties is None:
+            raise ValueError("tie_policy needs the tie counts returned by rank_true_tails")
+        if tie_policy == "mean":
+            r = r + ties.to(torch.float64) / 2
+        elif tie_policy == "pessimistic":
+            r = r + ties.to(torch.float64)
+        else:
+            raise ValueError("tie_policy must be optimistic, mean or pessimistic")
+    out = {"mrr": float((1.0 / r).mean()), "mean_rank": float(r.mean()),
+           "median_rank": float(torch.quantile(r, 0.5)) if r.numel() else float("nan"), "tie_policy": tie_policy}
     for k in k_values:
-        out[f"hits@{k}"] = float((ranks <= k).double().mean())
+        out[f"hits@{k}"] = float((r <= k).double().mean())
     return out

@@ -960,6 +960,27 @@ def test_eval_encoder_output_is_cached(pkg):
         n3 = lib.rgcn_launch_count()
         m.encoder(ei, et)
         assert lib.rgcn_launch_count() > n3
+    # writes that bypass the version counter (p.data, raw pointers, replayed graphs) are covered by the cache's lifetime:
+    # every train() / eval() switch, .to(), load_state_dict and invalidate_eval_cache() drops it
+    m.eval()
+    with torch.no_grad():
+        a = m.encoder(ei, et)
+        assert m.encoder._eval_cache is not None and m.encoder._eval_cache[1] is not None     # holds the graph itself
+        m.encoder.conv2.root.data.mul_(1.25)                       # no version bump
+        m.train(); m.eval()                                        # what a training epoch between two validations does
+        assert m.encoder._eval_cache is None
+        b = m.encoder(ei, et)
+        assert not torch.equal(a, b)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m.encoder(ei, et)
+        m.load_state_dict(sd)
+        assert m.encoder._eval_cache is None
+        m.encoder(ei, et)
+        m.encoder.invalidate_eval_cache()
+        assert m.encoder._eval_cache is None
+        m.encoder(ei, et)
+        m.to(DEV)
+        assert m.encoder._eval_cache is None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -229,3 +229,18 @@ def test_integration_doc_lists_every_abi_symbol():
     assert len(syms) >= 40
     missing = [s for s in syms if s not in doc]
     assert not missing, f"not documented in INTEGRATION.md: {missing}"
+
+
+def test_ranking_metrics_median_is_numpys(lib_built):
+    """src/evaluate.py:283 uses np.median: the MEAN of the two middle values for an even count."""
+    import numpy as np
+    from primekg_rgcn_linkprediction_b200 import ranking_metrics
+    ranks = torch.tensor([1, 2, 10, 400, 7, 3])
+    m = ranking_metrics(ranks, k_values=(1, 3, 10))
+    assert m["median_rank"] == float(np.median(ranks.numpy())) == 5.0
+    assert abs(m["mrr"] - float(np.mean(1.0 / ranks.numpy()))) < 1e-12 and m["hits@3"] == 0.5
+    ties = torch.tensor([0, 2, 0, 0, 0, 1])
+    mean = ranking_metrics(ranks, k_values=(3,), ties=ties, tie_policy="mean")
+    assert mean["mean_rank"] == float((ranks.double() + ties.double() / 2).mean()) and mean["hits@3"] == 1 / 3
+    with pytest.raises(ValueError):
+        ranking_metrics(ranks, tie_policy="mean")
