@@ -65,13 +65,18 @@ def aggregate_bwd(g, gH, d, init=None):
 
 def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, dropout_seed=0, dropout_ctr=None,
               peer_out=None, peer_row0=0, peer_ld=0):
-    assert dropout_p == 0.0 and not peer_out
+    assert not peer_out
     d_in = x_src.size(1)
     K1 = g.R * d_in
     A = alloc_planes(g.n_dst, K1 + d_in, mode, None)
     aggregate_fwd(g, x_src.detach(), planes=A)
     split_planes(x_root.detach(), A, col0=K1)
-    return transform_fwd(A, K1, d_in, W2d, root, bias, relu, mode), A
+    out = transform_fwd(A, K1, d_in, W2d, root, bias, relu, mode)
+    if dropout_p > 0.0:
+        # the fused ReLU + dropout epilogue: zero with probability p, the rest times 1 / (1 - p); the backward needs no
+        # mask tensor (the output is zero exactly where ReLU or dropout killed the element)
+        out = out * torch.bernoulli(torch.full_like(out, 1.0 - dropout_p)) / (1.0 - dropout_p)
+    return out, A
 
 
 def layer_bwd(g, gO, relu_mask, mask_scale, planes, W2d, root, d_in, mode, need_x, add_root_term, need_w, need_b,
@@ -88,6 +93,65 @@ def layer_bwd(g, gO, relu_mask, mask_scale, planes, W2d, root, d_in, mode, need_
     if need_w:
         gW, groot, gb = transform_wgrad(planes, K1, d_in, G, d_out, colsum if need_b else None, mode)
     return gx, gA, gW, groot, gb
+
+
+# ---- the rest of the product's kernel entry points, for running the WHOLE module trio on a CPU-only machine ----------
+_GRAPHS = {}
+
+
+def get_graph(edge_index, edge_type, num_nodes, num_relations):
+    if edge_type is None:
+        raise ValueError("edge_type is required")
+    key = (edge_index.data_ptr(), edge_type.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes))
+    g = _GRAPHS.get(key)
+    if g is None:
+        if edge_index.numel() and (int(edge_index.min()) < 0 or int(edge_index.max()) >= num_nodes):
+            raise IndexError("graph has out-of-range node index")
+        if len(_GRAPHS) > 8:
+            _GRAPHS.clear()
+        g = _GRAPHS[key] = CpuGraph(edge_index[0], edge_index[1], edge_type, num_nodes, num_nodes, num_relations)
+        g._keep = (edge_index, edge_type)
+    return g
+
+
+def pair_scores(emb, rel_table, head, tail, rel, p_drop=0.0, seed=0, counter=None):
+    r = rel_table[rel]
+    if p_drop > 0.0:
+        r = torch.nn.functional.dropout(r, p_drop, True)
+    return (emb[head] * r * emb[tail]).sum(1)
+
+
+def link_loss(emb, rel_table, head, tail, rel, labels, p_drop=0.0, seed=0, counter=None):
+    s = pair_scores(emb, rel_table, head, tail, rel, p_drop)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(s, labels)
+    return loss, s.detach(), ((s.detach() > 0).float() == labels).sum().to(torch.int32)
+
+
+def rank_prep(emb, idx, rel_table, rel, normalize):
+    a = emb.detach() if idx is None else emb.detach()[idx]
+    if rel is not None:
+        a = a * rel_table.detach()[rel]
+    return a / a.norm(dim=1, keepdim=True) if normalize else a
+
+
+def scores_from_rows(A, B, b_idx=None, alpha=1.0, beta=0.0, method="tc"):
+    Bm = B.detach() if b_idx is None else B.detach()[b_idx]
+    return alpha * (A.detach() @ Bm.t()) + beta
+
+
+def install_full(monkeypatch, pkg):
+    """Patch EVERY device entry point the module trio reaches (``ops``, the graph cache, the CUDA guards, the all-pairs
+    helpers) with the CPU stand-ins, through ``monkeypatch`` so the patches are undone after the test."""
+    from primekg_rgcn_linkprediction_b200 import conv, graph, modules, ops, rank
+    for name in ("alloc_planes", "aggregate_fwd", "split_planes", "transform_fwd", "transform_dgrad",
+                 "transform_wgrad", "aggregate_bwd", "layer_fwd", "layer_bwd", "pair_scores", "link_loss"):
+        monkeypatch.setattr(ops, name, globals()[name])
+    for mod in (graph, conv, modules):
+        monkeypatch.setattr(mod, "get_graph", get_graph)
+    monkeypatch.setattr(modules, "_need_cuda", lambda t, what: None)
+    monkeypatch.setattr(rank, "_prep", rank_prep)
+    monkeypatch.setattr(rank, "scores_from_rows", scores_from_rows)
+    _GRAPHS.clear()
 
 
 def install(monkeypatch_target):

@@ -117,56 +117,3 @@ def test_only_one_forward_may_be_outstanding(pg):
         s1.sum().backward()
     s2.sum().backward()
     assert model.encoder.node_embeddings.grad is not None
-
-
-def _two_rank_worker(rank, port, ret):
-    import sys
-    from conftest import ROOT
-    sys.path.insert(0, ROOT)
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=dev)
-    try:
-        import primekg_rgcn_linkprediction_b200 as pkg
-        from primekg_rgcn_linkprediction_b200 import dist as D
-        from primekg_rgcn_linkprediction_b200 import dist_fused as DF
-        from primekg_rgcn_linkprediction_b200 import synth
-        N, R = 20_000, 3
-        kg = synth.uniform_kg(N, 400_000, R, seed=4)
-        ei, et = kg.edge_index.to(dev), kg.edge_type.to(dev)
-        plan = D.plan_partition(ei[1], N, 2)
-        model = DF.FusedPartitionedModel(plan, rank, R, 64, 128, dropout=0.0, num_layers=2, seed=5).to(dev)
-        model.encoder.build_graph(ei, et)
-        model.eval()
-        with torch.no_grad():
-            out1 = model.encoder()
-            if rank == 0:
-                torch.cuda._sleep(200_000_000)          # ~0.1 s: rank 0's consumer of out1 lags behind rank 1
-            kept = out1.clone()                          # the "decoder" reading the first output
-            model.encoder.node_embeddings.mul_(2.0)      # the second forward pushes other values
-            out2 = model.encoder()
-            again = out2.clone()
-            model.encoder.node_embeddings.mul_(0.5)
-            out3 = model.encoder().clone()
-        torch.cuda.synchronize()
-        ok = bool(torch.equal(kept, out3)) and not bool(torch.equal(kept, again))
-        ret[rank] = ok
-    finally:
-        dist.destroy_process_group()
-
-
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_forward_only_loop_with_skewed_ranks_two_gpus(lib_built):
-    """a fast rank must not store the next forward's rows into a buffer a slow rank is still reading."""
-    import torch.multiprocessing as mp
-    if dist.is_initialized():
-        pytest.skip("a process group is already active in this process")
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    ret = mp.get_context("spawn").Manager().dict()
-    mp.spawn(_two_rank_worker, args=(port, ret), nprocs=2, join=True)
-    assert ret.get(0) is True and ret.get(1) is True

@@ -1,0 +1,127 @@
+"""GPU half of the "reference scripts run unchanged" check.  tests/test_reference_scripts.py runs the reference's own
+src/train.py + src/evaluate.py on the drop-in (CPU box) and records every model-API call they make
+(tests/golden/ref_call_sequence.json, generator tests/golden/make_ref_calls.py).  Here that SAME call sequence — same
+order, same shapes, same train / eval and grad modes, same optimizer and clipping calls, same state-dict round trip —
+is replayed against the real sm_100a kernels, side by side with the oracle (stock torch ops on the same device),
+comparing every output the scripts consume.  Dropout is 0 on both sides (the masks come from different generators)."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ref_harness as H
+from conftest import GOLDEN
+from oracle import rgcn_ref as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_replay_reference_call_sequence(lib_built):
+    pkg = lib_built
+    doc = json.load(open(os.path.join(GOLDEN, "ref_call_sequence.json")))
+    assert doc["data"] == H.DATA
+    train, val, test, full, _ = H.build_splits(doc["data"])
+    N, R = doc["model"]["num_nodes"], doc["model"]["num_relations"]
+    d_e, d_h = doc["model"]["embedding_dim"], doc["model"]["hidden_dim"]
+    graphs = {"train": train, "full": full}
+    dev_graphs = {k: (g["edge_index"].to(DEV), g["edge_type"].to(DEV)) for k, g in graphs.items()}
+
+    def make_pair():
+        ours = pkg.DrugDiseaseModel(N, R, d_e, d_h, dropout=0.0, decoder_dropout=0.0)
+        ref = O.ModelRef(N, R, d_e, d_h, 0.0, 0.0)
+        return ours, ref
+
+    torch.manual_seed(42)
+    ours, ref = make_pair()
+    ref.load_state_dict(ours.state_dict())
+    ours.to(DEV); ref.to(DEV)
+    assert sum(p.numel() for p in ours.parameters()) == doc["model"]["num_parameters"]
+    opt_o = opt_r = None
+    g = torch.Generator().manual_seed(7)
+    last = None                     # (scores_ours, scores_ref, labels)
+    emb = None                      # (ours, ref) encoder outputs of the last encoder.forward
+    sd = None
+    n_checked = 0
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for c in doc["calls"]:
+            op = c["op"]
+            if op == "model.forward":
+                ei, et = dev_graphs[c["graph"]]
+                B = c["pairs"]
+                heads = torch.randint(0, N, (B,), generator=g).to(DEV)
+                tails = torch.randint(0, N, (B,), generator=g).to(DEV)
+                rels = torch.randint(0, R, (B,), generator=g).to(DEV)
+                labels = torch.cat([torch.ones(B - B // 2), torch.zeros(B // 2)]).to(DEV)
+                ours.train(c["training"]); ref.train(c["training"])
+                with torch.set_grad_enabled(c["grad"]):
+                    so = ours(ei, et, heads, tails, rels)
+                    sr = ref(ei, et, heads, tails, rels)
+                assert so.requires_grad == c["grad"]
+                smax = float(sr.detach().abs().max())
+                torch.testing.assert_close(so.detach(), sr.detach(), rtol=2e-3, atol=2e-3 * max(smax, 1e-3))
+                last = (so, sr, labels)
+                n_checked += 1
+            elif op == "backward":
+                lo = F.binary_cross_entropy_with_logits(last[0], last[2])
+                lr_ = F.binary_cross_entropy_with_logits(last[1], last[2])
+                torch.testing.assert_close(lo.detach(), lr_.detach(), rtol=1e-3, atol=1e-5)
+                lo.backward(); lr_.backward()
+            elif op == "clip_grad_norm_":
+                no = torch.nn.utils.clip_grad_norm_(ours.parameters(), c["max_norm"])
+                nr = torch.nn.utils.clip_grad_norm_(ref.parameters(), c["max_norm"])
+                torch.testing.assert_close(no, nr, rtol=2e-3, atol=1e-7)
+            elif op == "optimizer.step":
+                if opt_o is None:
+                    cls = getattr(torch.optim, c["optimizer"])
+                    opt_o = cls(ours.parameters(), lr=c["lr"], weight_decay=c["weight_decay"])
+                    opt_r = cls(ref.parameters(), lr=c["lr"], weight_decay=c["weight_decay"])
+                opt_o.step(); opt_r.step()
+                opt_o.zero_grad(); opt_r.zero_grad()                       # src/train.py:312
+            elif op == "state_dict":
+                sd = {k: v.detach().clone() for k, v in ours.state_dict().items()}
+                assert list(sd) == list(ref.state_dict())
+            elif op == "load_state_dict":
+                sd_r = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+                ours, ref = make_pair()                                    # evaluate.py load_model: fresh model, load, .to(), eval()
+                ours.load_state_dict({k: v.cpu() for k, v in sd.items()})
+                ref.load_state_dict({k: v.cpu() for k, v in sd_r.items()})
+                ours.to(DEV).eval(); ref.to(DEV).eval()
+            elif op == "encoder.forward":
+                ei, et = dev_graphs[c["graph"]]
+                ours.train(c["training"]); ref.train(c["training"])
+                with torch.set_grad_enabled(c["grad"]):
+                    emb = (ours.encoder(ei, et), ref.encoder(ei, et))
+                emax = float(emb[1].abs().max())
+                torch.testing.assert_close(emb[0], emb[1], rtol=2e-3, atol=2e-3 * emax)
+                n_checked += 1
+            elif op == "decoder.score_all_tails":
+                h = torch.randint(0, N, (c["heads"],), generator=g).to(DEV)
+                r = torch.randint(0, R, (c["heads"],), generator=g).to(DEV)
+                t = torch.randint(0, N, (c["heads"],), generator=g).to(DEV)
+                with torch.no_grad():
+                    so = ours.decoder.score_all_tails(emb[0][h], r, emb[0])
+                    sr = ref.decoder.score_all_tails(emb[1][h], r, emb[1])
+                    assert so.shape == (c["heads"], c["tails"])
+                    torch.testing.assert_close(so, sr, rtol=2e-3, atol=2e-3 * float(sr.abs().max()))
+                    # the per-row argsort loop of src/evaluate.py:266-276 against the fused ranking on the same embeddings
+                    rank, ties = ours.decoder.rank_tails(emb[0], h, r, t)
+                    for i in range(0, c["heads"], 37):
+                        order = torch.argsort(so[i], descending=True)
+                        pos = int((order == t[i]).nonzero(as_tuple=True)[0].item()) + 1
+                        assert int(rank[i]) <= pos <= int(rank[i]) + int(ties[i])
+                n_checked += 1
+            elif op == "decoder.forward":
+                pass                                                       # (nested inside model.forward in the reference)
+            else:
+                raise AssertionError(f"unknown recorded op {op}")
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+    assert n_checked >= 20 and opt_o is not None
+    # after the whole sequence (10 Adam steps) the two parameter sets still agree
+    for (k, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(p.detach(), q.detach(), rtol=1e-2, atol=2e-3 * float(q.abs().max()), msg=lambda s: f"{k}: {s}")
