@@ -1,24 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the RGCN message-passing hot path (BASELINE.json metric: full-batch RGCN fwd+bwd
-edges/sec; aggregation GB/s against the measured HBM peak).
+edges/sec; aggregation GB/s against the measured roofs of the box; transforms against the tensor peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode fp32|bf16] [--quick]
 
 One *step* = train-mode ``DrugDiseaseModel.forward`` on the full graph + BCEWithLogits + ``backward()``
 (reference src/train.py:291-306; optimiser, clipping and sampling excluded).
-Workload at every N: cfg2 of BASELINE.json — the synthetic PrimeKG-shaped graph (30,926 nodes /
+Headline workload at every N: cfg2 of BASELINE.json — the synthetic PrimeKG-shaped graph (30,926 nodes /
 849,456 directed edges / 3 relations), 2-layer RGCN 64 -> 256 -> 256, batch 1,024 positives + 1,024
-negatives, dropout 0.5 / decoder dropout 0.1, seed 42.  N > 1: data-parallel replicas — every rank holds
-the graph and the model, processes its own mini-batch and the parameter gradients are all-reduced over
-NCCL inside the timed step (weak scaling: N * E edges per step).
+negatives, dropout 0.5 / decoder dropout 0.1, seed 42.  cfg1-4 fit one GPU, so N > 1 runs data-parallel
+replicas for ``value`` (weak scaling: N * E edges per step); the node-range PARTITIONED path of north_star
+config 5 is measured next to it at every N under ``partitioned`` (a cfg5-shaped graph sized per GPU:
+1.25 M nodes / 50 M edges / 30 relations / 3 layers per rank => 10 M / 400 M at N = 8).
 
-Prints ONE JSON line (rank 0).  See the module docstring of the contract in DESIGN.md §Measurement.
+Prints ONE JSON line (rank 0).  Contract and every figure's definition: DESIGN.md §5.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import socket
 import statistics
 import subprocess
 import sys
@@ -37,14 +39,30 @@ WORKLOAD = ("cfg2: synthetic PrimeKG-shaped KG 30,926 nodes / 849,456 edges / 3 
             "2-layer RGCN 64->256->256, batch 1024+1024, fwd+loss+bwd")
 METRIC = "rgcn_fwd_bwd_edges_per_sec"
 UNIT = "edges/s"
+PARITY = ("operator restated, not PyG-pinned (torch_geometric is not installable here): RGCNConv checked against the "
+          "restated loop path + a dense-adjacency re-derivation + fp64 gradcheck; everything around it pinned to the "
+          "unmodified reference model file (tests/golden)")
+# algorithmic bytes of one cfg2 step in the reference's (dense) formulation
+CFG2_STEP_BYTES = 2_406.3e6
+PART = dict(nodes_per_gpu=1_250_000, edges_per_gpu=50_000_000, relations=30, layers=3, embedding=64, hidden=128, batch=2048)
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1650.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -63,7 +81,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=open(self.path, "w"),
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -71,7 +89,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return None
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -95,25 +113,18 @@ class ClockSampler:
             pass
         if not sm:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "window": "sampled every 20 ms from a 0.4 s pre-roll of the same graph replays through the timed region"}
 
 
 # ---------------------------------------------------------------------------------------------
-# workload
+# workload + timing helpers
 # ---------------------------------------------------------------------------------------------
 def make_workload(rank: int):
     from primekg_rgcn_linkprediction_b200 import synth
     kg = synth.primekg_subgraph(CFG["num_edges"], seed=CFG["seed"])
     batch = synth.link_batch(kg, CFG["batch_pos"], seed=CFG["seed"] + 1000 * rank)   # a different mini-batch per rank
     return kg, batch
-
-
-def l2_cap(achieved_gbs, clocks):
-    mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    peak = 6300.0 * mhz * 1e6 / 1e9
-    return {"peak": round(peak, 1), "unit": "GB/s", "frac": round(achieved_gbs / peak, 4),
-            "source": "6300 B/clk (B300_MICROARCH.md, LTS throughput cap) x %.0f MHz" % mhz}
 
 
 def algorithmic_bytes(E, N, R, d_in):
@@ -123,28 +134,409 @@ def algorithmic_bytes(E, N, R, d_in):
     return fwd, bwd
 
 
-def time_dominant_kernel(pkg, graph, d, iters, flush, comp=None):
-    """CUDA-event duration of the dominant op (forward / backward aggregation = hub chunks +
-    aggregate_rows_kernel, gather width d) on the launching stream, L2 flushed between launches."""
+class Flusher:
+    def __init__(self, dev):
+        self.buf = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def __call__(self):
+        self.buf.fill_(1.0)            # 512 MiB write > 126 MB L2
+
+
+def event_time(fn, iters, flush=None, warm=3):
+    """Mean CUDA-event duration (ms) of ``fn`` on the launching stream; ``flush`` runs before every timed call."""
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.mean(ts)
+
+
+def time_aggregation(graph, d, iters, flush, comp=None):
     from primekg_rgcn_linkprediction_b200 import ops
     x = torch.randn(graph.n_src, d, device="cuda")
     gA = torch.randn(graph.n_dst, (graph.R + 1) * d, device="cuda")
+    return {"aggregate_fwd": event_time(lambda: ops.aggregate_fwd(graph, x, comp=comp), iters, flush),
+            "aggregate_bwd": event_time(lambda: ops.aggregate_bwd(graph, gA, d, init=gA[:, graph.R * d:]), iters, flush)}
+
+
+def ncu_record(name):
+    """Per-launch DRAM / L2 bytes of the dominant kernel from the committed ncu capture of this round (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(name)
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+# roofline block
+# ---------------------------------------------------------------------------------------------
+def roofline_block(pkg, kg, ei, et, flush, clocks, iters):
+    """Three measured rates for the dominant kernel (layer-2 forward aggregation, gather width 256):
+    gathered (algorithmic) GB/s, the L2 gather ceiling MEASURED on this box by rgcn_probe_gather over the same index
+    array, and the DRAM rate from the committed ncu capture; ``frac`` = achieved / the roof that binds (the L2 for cfg2,
+    whose 31.7 MB of features are L2 resident).  Plus a genuinely DRAM-bound gather, the tensor-pipe fraction of the
+    layer-2 forward GEMM and the whole-step HBM fraction on the dense-backward line."""
+    from primekg_rgcn_linkprediction_b200 import ops, synth
+    peaks, peak_src = measured_peaks()
+    hbm = float(peaks["hbm_gbs"])
+    graph = pkg.get_graph(ei, et, kg.num_nodes, kg.num_relations)
+    d2 = CFG["hidden_dim"]
+    kt = time_aggregation(graph, d2, iters, flush)
+    fwd_b, bwd_b = algorithmic_bytes(kg.num_edges, kg.num_nodes, kg.num_relations, d2)
+    achieved = fwd_b / (kt["aggregate_fwd"] * 1e-3) / 1e9
+
+    # ---- L2 gather ceiling, measured here: same table size, same source-index array, nothing but the loads ----
+    table = torch.randn(kg.num_nodes, d2, device="cuda")
+    col = graph.col
+    gathered = col.numel() * d2 * 4
+    probe = {}
+    for bps in (2, 4, 8):
+        ms = event_time(lambda: ops.probe_gather(table, col, blocks_per_sm=bps), iters, flush)
+        probe[f"csr_order_{bps}_blocks_per_sm"] = round(gathered / (ms * 1e-3) / 1e9, 1)
+    uni = torch.randint(0, kg.num_nodes, (col.numel(),), device="cuda", dtype=torch.int32)
+    ms = event_time(lambda: ops.probe_gather(table, uni, blocks_per_sm=8), iters, flush)
+    probe["uniform_random_rows_8_blocks_per_sm"] = round(gathered / (ms * 1e-3) / 1e9, 1)
+    ms = event_time(lambda: ops.probe_gather(table, None, n_idx=col.numel(), blocks_per_sm=8), iters, flush)
+    probe["streaming_read_8_blocks_per_sm"] = round(gathered / (ms * 1e-3) / 1e9, 1)
+    l2_peak = max(probe.values())
+    ncu = ncu_record("aggregate_rows_fwd_d256") or {}
+    dram_bytes = ncu.get("dram_bytes")
+    dram_gbs = None if not dram_bytes else dram_bytes / (kt["aggregate_fwd"] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "binding_roof": "l2 (the gather working set is L2 resident: 31.7 MB of features < 126 MB)",
+            "kernel": "hub_partial_kernel + aggregate_rows_kernel (layer-2 forward gather, d=256)",
+            "achieved": round(achieved, 1), "peak": round(l2_peak, 1), "unit": "GB/s", "frac": round(achieved / l2_peak, 4),
+            "peak_source": "L2-resident row gather MEASURED in this run (rgcn_probe_gather: the aggregation's access pattern "
+                           "alone; best of the variants in l2_probe)",
+            "traffic": dram_bytes, "traffic_source": ncu.get("source"),
+            "algorithmic_bytes_per_launch": fwd_b, "avg_launch_ms": round(kt["aggregate_fwd"], 5),
+            "rates": {"gathered_algorithmic_gbs": round(achieved, 1), "l2_probe_peak_gbs": round(l2_peak, 1),
+                      "lts_t_bytes_gbs_ncu": (None if not ncu.get("lts_t_bytes") else
+                                              round(ncu["lts_t_bytes"] / (ncu["ncu_time_us"] * 1e-6) / 1e9, 1)),
+                      "dram_gbs": None if dram_gbs is None else round(dram_gbs, 1),
+                      "hbm_peak_gbs": hbm, "hbm_peak_source": peak_src,
+                      "frac_of_hbm_peak_dram_level": None if dram_gbs is None else round(dram_gbs / hbm, 4),
+                      "frac_of_hbm_peak_algorithmic": round(achieved / hbm, 4),
+                      "note": "algorithmic / HBM peak exceeds 1 because every source row is gathered ~27x out of the L2; "
+                              "the DRAM-level fraction is what the HBM sees"},
+            "l2_probe": probe,
+            "bwd": {"achieved": round(bwd_b / (kt["aggregate_bwd"] * 1e-3) / 1e9, 1),
+                    "avg_launch_ms": round(kt["aggregate_bwd"], 5), "algorithmic_bytes_per_launch": bwd_b,
+                    "frac": round(bwd_b / (kt["aggregate_bwd"] * 1e-3) / 1e9 / l2_peak, 4)}}
+    del table, uni
+
+    # ---- layer-1 gather (d = 64): the narrow-row walk against its own measured ceiling ----
+    try:
+        d1 = CFG["embedding_dim"]
+        k1 = time_aggregation(graph, d1, iters, flush)
+        f1, b1 = algorithmic_bytes(kg.num_edges, kg.num_nodes, kg.num_relations, d1)
+        t1 = torch.randn(kg.num_nodes, d1, device="cuda")
+        p1 = max(col.numel() * d1 * 4 / (event_time(lambda: ops.probe_gather(t1, col, blocks_per_sm=b), iters, flush) * 1e-3) / 1e9
+                 for b in (4, 8))
+        roof["d64"] = {"fwd_achieved": round(f1 / (k1["aggregate_fwd"] * 1e-3) / 1e9, 1),
+                       "bwd_achieved": round(b1 / (k1["aggregate_bwd"] * 1e-3) / 1e9, 1),
+                       "l2_probe_peak": round(p1, 1), "fwd_frac": round(f1 / (k1["aggregate_fwd"] * 1e-3) / 1e9 / p1, 4),
+                       "unit": "GB/s", "fwd_ms": round(k1["aggregate_fwd"], 5), "bwd_ms": round(k1["aggregate_bwd"], 5)}
+        del t1
+    except Exception as ex:  # pragma: no cover
+        roof["d64"] = {"error": repr(ex)[:200]}
+
+    # ---- a genuinely DRAM-bound gather: cfg5-shard shape, uniform sources, 2 GB of features, d = 128 ----
+    try:
+        n_big, e_big, r_big, d_big = 4_000_000, 64_000_000, 30, 128
+        big = synth.scaled_kg(n_big, e_big, r_big, seed=7, power=1.0, device="cuda")
+        gb = pkg.RelGraph.from_edges(big.edge_index, big.edge_type, n_big, r_big)
+        del big
+        xb = torch.randn(n_big, d_big, device="cuda")
+        ms_f = event_time(lambda: ops.aggregate_fwd(gb, xb, out_bf16=True), 3, None, warm=1)
+        fb, _ = algorithmic_bytes(e_big, n_big, r_big, d_big)
+        out_b = n_big * r_big * d_big * 2
+        ms_p = event_time(lambda: ops.probe_gather(xb, gb.col, blocks_per_sm=8), 3, None, warm=1)
+        a_f = fb / (ms_f * 1e-3) / 1e9
+        ncu_b = ncu_record("aggregate_rows_fwd_hbm_case") or {}
+        roof["hbm_bound_case"] = {
+            "workload": "cfg5-shard-shaped gather: 4,000,000 nodes / 64,000,000 edges / 30 relations, uniform sources, "
+                        "d = 128 (2.05 GB of fp32 features, 16x the L2), output as bf16 rows",
+            "bound": "hbm", "achieved": round(a_f, 1), "peak": hbm, "unit": "GB/s", "frac": round(a_f / hbm, 4),
+            "achieved_incl_output_write": round((fb + out_b) / (ms_f * 1e-3) / 1e9, 1),
+            "frac_incl_output_write": round((fb + out_b) / (ms_f * 1e-3) / 1e9 / hbm, 4),
+            "algorithmic_bytes_per_launch": fb, "output_bytes_per_launch": out_b, "avg_launch_ms": round(ms_f, 4),
+            "probe_gather_same_indices_gbs": round(e_big * d_big * 4 / (ms_p * 1e-3) / 1e9, 1),
+            "traffic": ncu_b.get("dram_bytes"), "traffic_source": ncu_b.get("source")}
+        del gb, xb
+        torch.cuda.empty_cache()
+    except Exception as ex:  # pragma: no cover
+        roof["hbm_bound_case"] = {"error": repr(ex)[:200]}
+
+    # ---- tensor roofline: the layer-2 forward transform alone (M = N nodes, K = (R+1) d, N = d_out) ----
+    try:
+        K = (kg.num_relations + 1) * d2
+        A = torch.randn(kg.num_nodes, K, device="cuda")
+        W = torch.randn(K, d2, device="cuda") * 0.05
+        bias = torch.zeros(d2, device="cuda")
+        tens = {}
+        for mode, prods in (("fp32", 3), ("bf16", 1)):
+            planes = ops.alloc_planes(kg.num_nodes, K, mode, A.device)
+            ops.split_planes(A, planes)
+            ms = event_time(lambda: ops.transform_fwd(planes, K, 0, W, None, bias, True, mode), iters, flush)
+            alg = 2.0 * kg.num_nodes * K * d2
+            tens[mode] = {"avg_launch_ms": round(ms, 5), "algorithmic_tflops": round(alg / (ms * 1e-3) / 1e12, 1),
+                          "executed_bf16_tflops": round(prods * alg / (ms * 1e-3) / 1e12, 1), "mma_products": prods,
+                          "note": "includes the weight-plane conversion kernel of the call"}
+        mode = "fp32"
+        roof["tensor"] = {"bound": "tensor", "kernel": "gemm_kmajor_kernel<SPLIT> (layer-2 forward transform, 30,926 x 1,024 x 256)",
+                          "achieved": tens[mode]["executed_bf16_tflops"], "peak": float(peaks["bf16_tflops"]),
+                          "peak_sustained": float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])),
+                          "unit": "TFLOP/s", "frac": round(tens[mode]["executed_bf16_tflops"] / float(peaks["bf16_tflops"]), 4),
+                          "peak_source": peak_src + " (burst figure: the kernel is timed alone)",
+                          "tensor_pipe_active_pct_ncu": (ncu_record("gemm_fwd_layer2") or {}).get("tensor_pipe_active_pct"),
+                          "modes": tens}
+        del A, W, planes
+    except Exception as ex:  # pragma: no cover
+        roof["tensor"] = {"error": repr(ex)[:200]}
+    return roof
+
+
+# ---------------------------------------------------------------------------------------------
+# the other configs of BASELINE.json as one-liners (N = 1 only)
+# ---------------------------------------------------------------------------------------------
+def graphed_step_ms(pkg, kg, hidden, bases, mode, dev, flush, steps=10, batch_pos=1024):
+    from primekg_rgcn_linkprediction_b200 import synth
+    heads, tails, rels, labels = synth.link_batch(kg, batch_pos)
+    torch.manual_seed(CFG["seed"])
+    model = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, hidden, dropout=0.5, decoder_dropout=0.1,
+                                 num_bases=bases).to(dev)
+    for c in (model.encoder.conv1, model.encoder.conv2):
+        c.mode = mode
+    model.train()
+    ei, et = kg.edge_index.to(dev), kg.edge_type.to(dev)
+    step = pkg.GraphedTrainStep(model, ei, et, batch_size=2 * batch_pos)
+    step.load_batch(heads.to(dev), tails.to(dev), rels.to(dev), labels.to(dev))
+    ms = event_time(step, steps, flush)
+    loss = float(step.loss)
+    del step, model
+    return ms, loss
+
+
+def other_configs(pkg, dev, flush, mode):
+    from primekg_rgcn_linkprediction_b200 import synth
     out = {}
-    for name, fn in (("aggregate_fwd", lambda: ops.aggregate_fwd(graph, x, comp=comp)),
-                     ("aggregate_bwd", lambda: ops.aggregate_bwd(graph, gA, d, init=gA[:, graph.R * d:]))):
-        for _ in range(3):
-            fn()
-        ts = []
-        for _ in range(iters):
-            flush()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            b.synchronize()
-            ts.append(a.elapsed_time(b))
-        out[name] = statistics.mean(ts)
+    try:
+        kg = synth.primekg_subgraph(CFG["num_edges"], seed=CFG["seed"])
+        ms, loss = graphed_step_ms(pkg, kg, 128, None, mode, dev, flush)
+        out["cfg1"] = {"workload": "30,926 nodes / 849,456 edges / 3 rel, 64->128->128 (src/train.py defaults), batch 1024+1024",
+                       "ms_per_step": round(ms, 4), "edges_per_s": kg.num_edges / (ms * 1e-3), "loss": loss}
+    except Exception as ex:  # pragma: no cover
+        out["cfg1"] = {"error": repr(ex)[:200]}
+    try:
+        kg = synth.primekg_full()
+        ms, loss = graphed_step_ms(pkg, kg, 256, 8, mode, dev, flush, steps=5)
+        out["cfg3"] = {"workload": "129,375 nodes / 8,100,498 edges / 30 rel, num_bases = 8, 64->256->256, batch 1024+1024",
+                       "ms_per_step": round(ms, 4), "edges_per_s": kg.num_edges / (ms * 1e-3), "loss": loss,
+                       "hbm_floor_ms_survey_8d": 3.35}
+        del kg
+        torch.cuda.empty_cache()
+    except Exception as ex:  # pragma: no cover
+        out["cfg3"] = {"error": repr(ex)[:200]}
+    try:
+        d = CFG["hidden_dim"]
+        torch.manual_seed(3)
+        emb = torch.randn(30926, d, device=dev)
+        drugs = torch.arange(5593, 11875, device=dev)
+        diseases = torch.arange(0, 5593, device=dev)
+        rel = torch.randn(d, device=dev)
+        table = torch.randn(3, d, device=dev)
+        nq = 15372
+        heads = torch.randint(0, 30926, (nq,), device=dev)
+        tails = torch.randint(0, 30926, (nq,), device=dev)
+        rels = torch.zeros(nq, dtype=torch.int64, device=dev)
+        pairs = drugs.numel() * diseases.numel()
+        c4 = {"workload": "all 6,282 x 5,593 drug-disease pairs, d = 256; ranking of 15,372 test edges against 30,926 entities"}
+        ms = event_time(lambda: pkg.score_all_pairs(emb, drugs, diseases, rel_vec=rel), 5, flush)
+        c4["distmult_all_pairs"] = {"ms": round(ms, 4), "pairs_per_s": pairs / (ms * 1e-3)}
+        ms = event_time(lambda: pkg.score_all_pairs(emb, drugs, diseases, cosine=True), 5, flush)
+        c4["cosine_all_pairs"] = {"ms": round(ms, 4), "pairs_per_s": pairs / (ms * 1e-3)}
+        if hasattr(pkg, "topk_all_pairs"):
+            ms = event_time(lambda: pkg.topk_all_pairs(emb, drugs, diseases, k=10, cosine=True), 5, flush)
+            c4["cosine_top10_fused"] = {"ms": round(ms, 4), "pairs_per_s": pairs / (ms * 1e-3)}
+        ms = event_time(lambda: pkg.rank_true_tails(emb, table, heads, rels, tails), 3, flush, warm=1)
+        c4["rank_15372_vs_30926"] = {"ms": round(ms, 4), "pairs_per_s": nq * 30926 / (ms * 1e-3)}
+        out["cfg4"] = c4
+    except Exception as ex:  # pragma: no cover
+        out["cfg4"] = {"error": repr(ex)[:200]}
     return out
 
 
+def library_gpu_baseline(kg, batch, dev, steps=5):
+    """The "library Blackwell path" (SURVEY.md §8d): the restated reference (oracle/rgcn_ref.py — what
+    PyG's loop path does) on the SAME B200 through stock torch CUDA ops (ATen index_select / index_add_ + cuBLAS)."""
+    from oracle import rgcn_ref
+    heads, tails, rels, labels = [t.to(dev) for t in batch]
+    torch.manual_seed(CFG["seed"])
+    model = rgcn_ref.ModelRef(kg.num_nodes, kg.num_relations, CFG["embedding_dim"], CFG["hidden_dim"], CFG["dropout"],
+                              CFG["decoder_dropout"]).to(dev)
+    model.train()
+    ei, et = kg.edge_index.to(dev), kg.edge_type.to(dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        rgcn_ref.train_step_ref(model, ei, et, heads, tails, rels, labels)
+
+    ms = event_time(step, steps, None, warm=3)
+    return {"value": kg.num_edges / (ms * 1e-3), "unit": UNIT, "ms_per_step": round(ms, 4), "device": "same B200",
+            "kind": "oracle port through stock torch CUDA ops (ATen gather / index_add_ atomics + cuBLAS fp32), eager, "
+                    "torch.backends.cuda.matmul.allow_tf32 = %s" % torch.backends.cuda.matmul.allow_tf32}
+
+
+# ---------------------------------------------------------------------------------------------
+# node-range partitioned path (north_star config 5), measured at every N
+# ---------------------------------------------------------------------------------------------
+def partitioned_record(rank, world, dev, steps=5, warmup=2):
+    """Destination-range partition of a cfg5-shaped graph sized per GPU (weak scaling).  Both exchange forms are timed:
+    our kernels over peer-mapped memory (dist_fused.py, the product path) and NCCL all-gather / reduce-scatter (dist.py).
+    Timing: CUDA events per step, barrier + synchronize on both sides, max over ranks."""
+    import torch.distributed as dist
+    import primekg_rgcn_linkprediction_b200 as pkg
+    from primekg_rgcn_linkprediction_b200 import dist as D
+    from primekg_rgcn_linkprediction_b200 import dist_fused as DF
+    from primekg_rgcn_linkprediction_b200 import synth
+    nodes, edges = PART["nodes_per_gpu"] * world, PART["edges_per_gpu"] * world
+    R, L, d_e, d_h, B = PART["relations"], PART["layers"], PART["embedding"], PART["hidden"], PART["batch"]
+    rec = {"workload": f"cfg5-shaped synthetic KG sized per GPU: {nodes:,} nodes / {edges:,} edges / {R} relations, "
+                       f"{L}-layer RGCN {d_e}->{d_h} x {L}, batch {B}, fwd+loss+bwd, fp32 mode",
+           "scaling": "weak", "n_gpus": world, "nodes": nodes, "edges": edges}
+
+    def build(exchange, plan, graph):
+        cls = DF.FusedPartitionedModel if exchange == "fused" else D.PartitionedModel
+        m = cls(plan, rank, R, d_e, d_h, dropout=0.0, decoder_dropout=0.0, num_layers=L, seed=42).to(dev)
+        m.encoder.set_graph(graph)
+        m.train()
+        return m
+
+    def make_step(model, n_nodes):
+        g = torch.Generator(device=dev).manual_seed(7)
+        heads = torch.randint(0, n_nodes, (B,), generator=g, device=dev)
+        tails = torch.randint(0, n_nodes, (B,), generator=g, device=dev)
+        rels = torch.randint(0, R, (B,), generator=g, device=dev)
+        labels = (torch.rand(B, generator=g, device=dev) < 0.5).float()
+        sl = slice(rank * B // world, (rank + 1) * B // world)
+
+        def step():
+            for p in model.parameters():
+                p.grad = None
+            s = model(heads[sl], tails[sl], rels[sl])
+            loss = F.binary_cross_entropy_with_logits(s, labels[sl], reduction="sum") / B
+            loss.backward()
+            model.allreduce_decoder_grads()
+            return loss.detach(), s.detach()
+        return step, (heads, tails, rels, labels, sl)
+
+    def timed(step):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); step(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- equals-single-GPU check at a small size (N > 1: the split must reproduce the one-GPU model) ----
+    if world > 1:
+        try:
+            n_s, e_s = 200_000, 4_000_000
+            kg = synth.scaled_kg(n_s, e_s, R, seed=42, device=dev)
+            plan = D.plan_partition(kg.edge_index[1], n_s, world)
+            src, dst, rel = D.local_edges(kg.edge_index, kg.edge_type, plan, rank)
+            graph = pkg.RelGraph(src, dst, rel, plan.max_n, world * plan.max_n, R)
+            model = build("fused", plan, graph)
+            step, (heads, tails, rels, labels, sl) = make_step(model, n_s)
+            loss, scores = step()
+            total = loss.clone()
+            dist.all_reduce(total)
+            shards = [torch.zeros_like(model.encoder.node_embeddings.data) for _ in range(world)]
+            dist.all_gather(shards, model.encoder.node_embeddings.data)
+            gsh = [torch.zeros_like(model.encoder.node_embeddings.grad) for _ in range(world)]
+            dist.all_gather(gsh, model.encoder.node_embeddings.grad)
+            if rank == 0:
+                ref = pkg.DrugDiseaseModel(n_s, R, d_e, d_h, dropout=0.0, decoder_dropout=0.0, num_layers=L).to(dev)
+                with torch.no_grad():
+                    ref.encoder.node_embeddings.weight.copy_(torch.cat([shards[p][: plan.size(p)] for p in range(world)]))
+                    for mine, theirs in zip(model.encoder.convs, ref.encoder._layers()):
+                        theirs.weight.copy_(mine.weight); theirs.root.copy_(mine.root); theirs.bias.copy_(mine.bias)
+                    ref.decoder.relation_embeddings.weight.copy_(model.decoder.relation_embeddings.weight)
+                ref.train()
+                rs = ref(kg.edge_index, kg.edge_type, heads, tails, rels)
+                rl = F.binary_cross_entropy_with_logits(rs, labels)
+                rl.backward()
+                gg = torch.cat([gsh[p][: plan.size(p)] for p in range(world)])
+                want = ref.encoder.node_embeddings.weight.grad
+                rec["equals_single_gpu"] = {
+                    "graph": f"{n_s:,} nodes / {e_s:,} edges / {R} relations / {L} layers",
+                    "loss_abs_err": abs(float(rl) - float(total)), "score_max_abs_err": float((rs[sl] - scores).abs().max()),
+                    "emb_grad_rel_fro": float((gg - want).norm() / (want.norm() + 1e-30)),
+                    "w_grad_rel_fro_max": max(float((m.weight.grad - t.weight.grad).norm() / (t.weight.grad.norm() + 1e-30))
+                                              for m, t in zip(model.encoder.convs, ref.encoder._layers()))}
+                e = rec["equals_single_gpu"]
+                e["ok"] = bool(e["loss_abs_err"] < 1e-5 and e["score_max_abs_err"] < 1e-4 and e["emb_grad_rel_fro"] < 1e-3
+                               and e["w_grad_rel_fro_max"] < 1e-3)
+                del ref
+            del model, graph, kg, step
+            torch.cuda.empty_cache()
+            dist.barrier()
+        except Exception as ex:  # pragma: no cover
+            rec["equals_single_gpu"] = {"error": repr(ex)[:300]}
+
+    # ---- the timed graph: every rank generates the same edge list on its device, keeps its destination range ----
+    kg = synth.scaled_kg(nodes, edges, R, seed=42, device=dev)
+    plan = D.plan_partition(kg.edge_index[1], nodes, world)
+    src, dst, rel = D.local_edges(kg.edge_index, kg.edge_type, plan, rank)
+    del kg
+    torch.cuda.empty_cache()
+    graph = pkg.RelGraph(src, dst, rel, plan.max_n, world * plan.max_n, R)
+    local_edges = int(rel.numel())
+    del src, dst, rel
+    rec["max_shard_rows"] = plan.max_n
+    rec["local_edges_rank0"] = local_edges
+    dims = [d_e] + [d_h] * L
+    # forward: every rank receives the other ranks' rows of each layer's input and of the output; backward: the transpose
+    fwd_in = (world - 1) * plan.max_n * 4 * sum(dims)
+    rec["exchange_bytes_per_gpu_per_step"] = {"forward_received": fwd_in, "backward_pulled": (world - 1) * plan.max_n * 4 * sum(dims),
+                                              "weight_grad_allreduce": 4 * sum((R + 1) * dims[i] * dims[i + 1] + dims[i + 1] for i in range(L))}
+    for exchange in ("fused", "nccl"):
+        try:
+            model = build(exchange, plan, graph)
+            step, _ = make_step(model, nodes)
+            ms = timed(step)
+            rec["ms_per_step" if exchange == "fused" else "nccl_exchange_ms_per_step"] = ms
+            if exchange == "fused":
+                rec["value"] = edges / (ms * 1e-3)
+                rec["unit"] = UNIT
+                rec["exchange"] = "our kernels over peer-mapped memory (all-gather = the transform's epilogue stores, " \
+                                  "reduce-scatter = rank-ordered pull fused with mask + operand conversion)"
+            del model, step
+            torch.cuda.empty_cache()
+        except Exception as ex:  # pragma: no cover
+            rec[exchange + "_error"] = repr(ex)[:300]
+    if "ms_per_step" in rec and "nccl_exchange_ms_per_step" in rec:
+        rec["fused_vs_nccl_speedup"] = rec["nccl_exchange_ms_per_step"] / rec["ms_per_step"]
+    rec["max_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
+    rec["ceiling_survey_8d_edges_per_s"] = 2.4e9 * world
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------
+# the headline step
+# ---------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import primekg_rgcn_linkprediction_b200 as pkg
     from primekg_rgcn_linkprediction_b200 import _lib
@@ -162,11 +554,7 @@ def run_ours(args, rank, world, local_rank):
     model.train()
     ei, et = kg.edge_index.to(dev), kg.edge_type.to(dev)
     params = [p for p in model.parameters()]
-    flush_buf = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-
-    def flush():
-        flush_buf.fill_(1.0)            # 512 MiB write > 126 MB L2
-
+    flush = Flusher(dev)
     d_batch = [t.to(dev) for t in (heads, tails, rels, labels)]
 
     def eager_step(b):
@@ -217,7 +605,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     eager_ms = timed(lambda: (eager_step(d_batch), allreduce_grads()), args.steps)
     pinned = [t.pin_memory() for t in (heads, tails, rels, labels)]
-    h2d = sum(t.numel() * t.element_size() for t in pinned)
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def e2e_eager():
@@ -234,7 +621,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the same step captured once into a CUDA graph (GraphedTrainStep) ----
     # N > 1: the backward kernels write every parameter gradient into ONE flat buffer (ops.GradArena), so the replicas
-    # exchange a single tensor (one NCCL all-reduce: 63-70 us for the 9.2 MB against 107-124 us as a coalesced group)
+    # exchange a single tensor
     gstep = pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel(), flat_grads="arena" if world > 1 else False)
     gstep.load_batch(*d_batch)
     flat_holder = [gstep.flat_grad]
@@ -256,6 +643,12 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     if rank == 0:
         sampler.start()
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.4:            # pre-roll: the sampler sees the same kernel mix under load
+        for _ in range(20):
+            gstep(); allreduce_grads()
+        torch.cuda.synchronize()
+    barrier()
     t_wall0 = time.perf_counter()
     ms_per_step = timed(lambda: (gstep(), allreduce_grads()), args.steps)
     t_wall = time.perf_counter() - t_wall0
@@ -263,8 +656,6 @@ def run_ours(args, rank, world, local_rank):
     value = world * kg.num_edges / (ms_per_step * 1e-3)
 
     # ---- end to end: batch in pinned host memory, H2D of the step's inputs and D2H of the loss inside ----
-    # the step with its host I/O captured: H2D of the batch (one pinned int64 [4, B] block) as the graph's first node,
-    # D2H of the loss (+ correct count) as its last — one graph launch per step is all the host does
     packed = pkg.GraphedTrainStep.pack_batch(heads, tails, rels, labels)
     h2d_packed = packed.numel() * packed.element_size()
     for p in params:
@@ -305,63 +696,49 @@ def run_ours(args, rank, world, local_rank):
                 gdense(); allreduce_grads()
             barrier()
             dense_ms = timed(lambda: (gdense(), allreduce_grads()), args.steps)
+            del gdense
         finally:
             if sparse_env is None:
                 del os.environ["PRIMEKG_RGCN_SPARSE_BWD"]
             else:
                 os.environ["PRIMEKG_RGCN_SPARSE_BWD"] = sparse_env
+    flat_holder[0] = None
+    for p in params:
+        p.grad = None
+
+    # ---- the partitioned path (north_star config 5), every N, every rank ----
+    part = None
+    if not args.no_partitioned:
+        try:
+            if world == 1 and not dist.is_initialized():
+                s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ["MASTER_PORT"] = str(port)
+                dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+            torch.cuda.empty_cache()
+            part = partitioned_record(rank, world, dev, steps=3 if args.quick else 5)
+        except Exception as ex:  # pragma: no cover
+            part = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return None
-    # ---- roofline of the dominant kernel ----
-    graph = pkg.get_graph(ei, et, kg.num_nodes, kg.num_relations)
-    d2 = CFG["hidden_dim"]
-    kt = time_dominant_kernel(pkg, graph, d2, max(5, min(args.steps, 20)), flush)
-    fwd_b, bwd_b = algorithmic_bytes(kg.num_edges, kg.num_nodes, kg.num_relations, d2)
-    peak, peak_src = measured_peaks()
-    achieved = fwd_b / (kt["aggregate_fwd"] * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("aggregate_rows_fwd_d256_bytes")
-    roofline = {"bound": "hbm", "kernel": "hub_partial_kernel + aggregate_rows_kernel (layer-2 forward gather, d=256)",
-                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": fwd_b,
-                "avg_launch_ms": round(kt["aggregate_fwd"], 5),
-                "bwd": {"achieved": round(bwd_b / (kt["aggregate_bwd"] * 1e-3) / 1e9, 1),
-                        "avg_launch_ms": round(kt["aggregate_bwd"], 5), "algorithmic_bytes_per_launch": bwd_b},
-                "note": "cfg2 working set is L2-resident (features 31.7 MB < 126 MB L2): algorithmic GB/s may exceed the HBM peak",
-                # the bound that binds on this working set: the L2 slices' throughput cap, ~6300 B/clk full chip
-                # (B300_MICROARCH.md, 'LTS throughput cap'; same LTS count on B200) at the SM clock sampled in this run
-                "l2_cap": l2_cap(achieved, clocks)}
-    # the same kernel where the gather working set exceeds L2 (cfg3-sized graph: 129,375 x 256 fp32 = 132 MB):
-    # there the HBM roofline is the binding one
-    hbm_case = None
-    try:
-        from primekg_rgcn_linkprediction_b200 import synth
-        big = synth.primekg_full()
-        gb = pkg.RelGraph.from_edges(big.edge_index.to(dev), big.edge_type.to(dev), big.num_nodes, big.num_relations)
-        comp = torch.randn(big.num_relations, 8, device=dev)            # cfg3 uses basis decomposition, B = 8
-        kb_ = time_dominant_kernel(pkg, gb, d2, 5, flush, comp=comp)
-        fb, bb = algorithmic_bytes(big.num_edges, big.num_nodes, big.num_relations, d2)
-        out_bytes = big.num_nodes * 8 * d2 * 4                           # the basis-mixed output write, not in SURVEY's figure
-        hbm_case = {"workload": "cfg3-shaped KG 129,375 nodes / 8,100,498 edges / 30 relations, gather width 256",
-                    "fwd": {"achieved": round(fb / (kb_["aggregate_fwd"] * 1e-3) / 1e9, 1),
-                            "avg_launch_ms": round(kb_["aggregate_fwd"], 4), "algorithmic_bytes_per_launch": fb,
-                            "output_bytes_not_counted": out_bytes},
-                    "bwd": {"achieved": round(bb / (kb_["aggregate_bwd"] * 1e-3) / 1e9, 1),
-                            "avg_launch_ms": round(kb_["aggregate_bwd"], 4), "algorithmic_bytes_per_launch": bb},
-                    "peak": peak, "unit": "GB/s"}
-        hbm_case["fwd"]["frac"] = round(hbm_case["fwd"]["achieved"] / peak, 4)
-        hbm_case["bwd"]["frac"] = round(hbm_case["bwd"]["achieved"] / peak, 4)
-        del gb, big
-    except Exception as ex:  # pragma: no cover
-        hbm_case = {"error": repr(ex)[:200]}
-    roofline["hbm_bound_case"] = hbm_case
+    peaks, peak_src = measured_peaks()
+    hbm = float(peaks["hbm_gbs"])
+    roofline = roofline_block(pkg, kg, ei, et, flush, clocks, max(5, min(args.steps, 20)))
+    step_dense = dense_ms if dense_ms is not None else ms_per_step
+    roofline["whole_step"] = {
+        "algorithmic_bytes_survey_8d": CFG2_STEP_BYTES,
+        "dense_backward_ms": dense_ms, "frac_of_hbm_peak_dense_backward": round(CFG2_STEP_BYTES / (step_dense * 1e-3) / 1e9 / hbm, 4),
+        "row_sparse_backward_ms": ms_per_step,
+        "note": "SURVEY §8d's bytes describe the dense last-layer backward, so the fraction is quoted on that line; the "
+                "timed default step skips the zero rows of the last layer's output gradient (bit-identical input gradient)"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32" if args.mode == "fp32" else "bf16-transform/f32-accumulate",
-           "data": "synthetic",
+           "vs_baseline": None,
+           "dtype": ("bf16x3-split / f32-accumulate (operands as bf16 hi + lo planes, three tensor-core products, ~17 mantissa "
+                     "bits; gathers, means, loss in f32)" if args.mode == "fp32" else "bf16-transform / f32-accumulate"),
+           "data": "synthetic", "parity": PARITY,
            "config": {"workload": WORKLOAD, "mode": args.mode, "l2": "flushed between steps (512 MiB write)",
                       "parallelism": "single GPU" if world == 1 else f"dp{world} replicas, parameter gradients written into one flat buffer and all-reduced in one NCCL call",
                       "timing": "CUDA events per step on the launching stream, max over ranks",
@@ -383,7 +760,13 @@ def run_ours(args, rank, world, local_rank):
                                      "note": "same graphed step with the last layer's backward over all N rows "
                                              "(PRIMEKG_RGCN_SPARSE_BWD=0)"}),
            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-           "wall_s_timed_region": t_wall, "clocks": clocks, "roofline": roofline}
+           "wall_s_timed_region": t_wall, "clocks": clocks, "roofline": roofline, "partitioned": part}
+    if world == 1 and not args.quick:
+        out["configs"] = other_configs(pkg, dev, flush, args.mode)
+        try:
+            out["library_gpu_baseline"] = library_gpu_baseline(kg, (heads, tails, rels, labels), dev)
+        except Exception as ex:  # pragma: no cover
+            out["library_gpu_baseline"] = {"error": repr(ex)[:200]}
     return out
 
 
@@ -429,9 +812,10 @@ def run_reference(args):
     value, cores, sample, ms = cpu_reference_steps(args.steps, args.warmup, budget_s=150.0)
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "mode": "fp32", "device": "host CPU"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "parity": PARITY,
+            "config": {"workload": WORKLOAD, "mode": "fp32", "device": "host CPU: " + cpu_model()},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "cpu_model": cpu_model()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "PyG is not installable here; this is the restated reference path (oracle/rgcn_ref.py) in "
                     "PyTorch on the host cores"}
@@ -445,6 +829,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("PRIMEKG_RGCN_MODE", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the node-range partitioned record")
+    ap.add_argument("--quick", action="store_true", help="headline + roofline only (no other configs, no library baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -470,10 +856,14 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, ms = cpu_reference_steps(3, 1, budget_s=25.0)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                                   "ms_per_step": ms}
+                                   "ms_per_step": ms, "cpu_model": cpu_model()}
+            if not args.quick:
+                v1, _, sample1, ms1 = cpu_reference_steps(2, 1, budget_s=12.0, threads=1)
+                out["cpu_baseline"]["one_thread"] = {"value": v1, "unit": UNIT, "cores": 1, "sample": sample1, "ms_per_step": ms1}
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
+    if dist.is_initialized():
+        if world > 1:
+            dist.barrier()
         dist.destroy_process_group()
     return 0
 

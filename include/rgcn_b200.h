@@ -54,6 +54,17 @@ int rgcn_check_device(void);
 int64_t rgcn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Measurement aid (no reference counterpart): the row-gather access pattern of the aggregation with everything else
+ * removed, so that bench.py can MEASURE, on the box it runs on, what the L2 (table smaller than the L2) or the HBM
+ * (larger table) delivers for that pattern — the denominators of the roofline block.  Sums table[idx[i], 0:d] over
+ * i in [0, n_idx) (idx == NULL: rows i % n_rows in order, a streaming read) with sm_count * blocks_per_sm blocks;
+ * sink: rgcn_probe_gather_sink_floats(blocks_per_sm) floats of scratch.  Bytes moved = n_idx * d * 4.
+ * ------------------------------------------------------------------------------------------ */
+int64_t rgcn_probe_gather_sink_floats(int32_t blocks_per_sm);
+int rgcn_probe_gather(const float* table, int64_t ld, int64_t n_rows, int32_t d, const int32_t* idx, int64_t n_idx,
+                      int32_t blocks_per_sm, float* sink, rgcn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Graph preprocessing.  Replaces, once per graph, the per-relation boolean masks
  * `edge_index[:, edge_type == r]` that RGCNConv evaluates on every call
  * (call sites src/models/rgcn.py:123, :128; input format src/preprocess.py:240-261).

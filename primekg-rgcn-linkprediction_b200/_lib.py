@@ -65,6 +65,8 @@ PROTOTYPES = {
     "rgcn_last_error": (C.c_int, [C.c_char_p, sz]),
     "rgcn_check_device": (C.c_int, []),
     "rgcn_launch_count": (i64, []),
+    "rgcn_probe_gather_sink_floats": (i64, [i32]),
+    "rgcn_probe_gather": (C.c_int, [p, i64, i64, i32, p, i64, i32, p, p]),
     "rgcn_csr_build_workspace_bytes": (sz, [i64, i64, i64, i32]),
     "rgcn_csr_build": (C.c_int, [p, p, p, i64, i64, i64, i32, p, p, p, p, p, p, p, p, p, p, sz, p]),
     "rgcn_hub_plan_workspace_bytes": (sz, [i64, i64]),

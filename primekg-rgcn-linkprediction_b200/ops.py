@@ -852,3 +852,18 @@ def pair_scores(emb, rel_table, head, tail, rel, p_drop: float = 0.0, seed: int 
     if p_drop > 0 and counter is None:
         raise ValueError("pair_scores: dropout needs a device counter (ops.rng_counter)")
     return _PairScores.apply(emb, rel_table, head, tail, rel, float(p_drop), int(seed), counter)
+
+
+# ---- measurement aid ---------------------------------------------------------------------------------------------------
+def probe_gather(table: torch.Tensor, idx: Optional[torch.Tensor], n_idx: Optional[int] = None, blocks_per_sm: int = 4) -> None:
+    """The aggregation's row-gather pattern alone (``rgcn_probe_gather``): sums ``table[idx[i]]`` (``idx`` int32, or rows
+    in order when None) — bench.py times it to measure the L2 / HBM gather ceilings on the box it runs on."""
+    lib = _lib.load()
+    table = _f32c(table, "table")
+    if idx is not None and (idx.dtype != torch.int32 or not idx.is_contiguous()):
+        raise ValueError("idx must be a contiguous int32 tensor")
+    n = int(idx.numel() if idx is not None else (n_idx or table.size(0)))
+    sink = _workspace(table.device, int(lib.rgcn_probe_gather_sink_floats(blocks_per_sm)) * 4 + 64)
+    sp = (sink.data_ptr() + 15) // 16 * 16
+    _lib.check(lib.rgcn_probe_gather(_ptr(table), table.stride(0), table.size(0), table.size(1), _ptr(idx), n,
+                                     int(blocks_per_sm), C.c_void_p(sp), _stream(table.device)), "rgcn_probe_gather")

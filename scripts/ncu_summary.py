@@ -15,6 +15,10 @@ KEEP = {
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+    "lts__t_bytes.sum": "lts_t_bytes",
+    "lts__t_sectors_srcunit_tex.sum": "lts_sectors_from_tex",
+    "lts__t_sectors_srcunit_tex_op_read.sum": "lts_sectors_from_tex_read",
+    "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum": "l1_global_load_bytes",
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
     "launch__registers_per_thread": "regs",
     "launch__grid_size": "grid",
