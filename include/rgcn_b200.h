@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 4
+#define RGCN_B200_ABI_VERSION 5
 
 enum {
   RGCN_OK = 0,
@@ -129,6 +129,9 @@ typedef struct rgcn_csr {
   const int32_t* chunk_table;   /* [n_chunks][4] from rgcn_hub_chunk_table            */
   const int32_t* row_order;     /* [n_rows] or NULL: a permutation of the rows, the order in which the lane
                                    groups take them (by decreasing edge count: balanced blocks, long walks first) */
+  int64_t order_chunk_rows;     /* 0: row_order sorts all rows globally; c > 0: it sorts inside consecutive blocks of c
+                                   rows (positions [k c, (k+1) c) hold exactly the rows [k c, (k+1) c)), so the walk can be
+                                   launched block by block and pipelined with the transform of the finished rows */
 } rgcn_csr_t;
 
 /* ------------------------------------------------------------------------------------------
@@ -183,6 +186,13 @@ typedef struct rgcn_masked_planes_out {
   float* colsum_partial;                    /* nullable */
 } rgcn_masked_planes_out;
 int64_t rgcn_aggregate_row_blocks(const rgcn_csr_t* g, int32_t d);
+/* Row-range form of the unmixed forward walk (comp == NULL form of rgcn_aggregate_fwd): only the positions
+ * [row_begin, row_end) of the walk order; hub_pass = 0 when an earlier call of the same layer has already reduced the hub
+ * chunks into `workspace` (an empty range with hub_pass = 1 runs the hub pass alone).  With a row order the range must
+ * consist of whole order chunks (order_chunk_rows).  rgcn_layer_fwd pipelines these calls with the transform. */
+int rgcn_aggregate_fwd_rows(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d, void* H, void* H_lo, int64_t ldh,
+                            int32_t out_mode, const float* x_root, int64_t ld_x_root, int64_t row_begin, int64_t row_end,
+                            int32_t hub_pass, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
                        const float* init, int64_t ld_init,
@@ -278,6 +288,14 @@ typedef struct rgcn_layer_fwd_args {
   float* const* peer_out_host; int32_t n_peer; int64_t peer_row0, peer_ld;
   void* agg_workspace; size_t agg_workspace_bytes;     /* rgcn_aggregate_workspace_bytes(csr, d_in)           */
   void* gemm_workspace; size_t gemm_workspace_bytes;   /* rgcn_transform_workspace_bytes(n_dst, (R+1) d_in, d_out) */
+  /* Optional (NULL: the weights are converted into gemm_workspace on every call, forward and dgrad each): persistent
+   * buffer of rgcn_weight_planes_bytes((R+1) d_in, d_out) bytes, 256-byte aligned.  The call converts [weight; root] into
+   * it ONCE (rgcn_prepare_weights), reads it as the MN-major operand of the transform, and rgcn_layer_bwd reads the same
+   * buffer for its dgrad.  With it the call may also PIPELINE: the walk of row chunk c + 1 runs on `stream` while the
+   * transform of chunk c (and, in the partitioned path, its peer stores = the all-gather) runs on an internal side
+   * stream, joined before the call returns.  pipeline: 0 = the library decides (while the stream is being captured, or
+   * from 200,000 rows; RGCN_PIPELINE=0/1 overrides), 1 = never, 2 = always. */
+  void* w_planes; size_t w_planes_bytes; int32_t pipeline;
 } rgcn_layer_fwd_args;
 
 typedef struct rgcn_layer_bwd_args {
@@ -312,6 +330,7 @@ typedef struct rgcn_layer_bwd_args {
   int32_t g_ready; int32_t n_colsum_ready;
   int32_t slot_ready;                       /* row-sparse form: `slot` already holds the map for `rows` (written by
                                                rgcn_link_loss_bwd_rows for this very list): skip building it        */
+  const void* w_planes;                     /* optional: the weight planes rgcn_layer_fwd prepared (dgrad reads them) */
 } rgcn_layer_bwd_args;
 
 /* Compaction step of the row-sparse backward (csrc/rowsparse.cu), also callable on its own:
@@ -326,6 +345,23 @@ int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_nodes, int3
                       const void* A_hi, const void* A_lo, int64_t lda, int32_t K, void* Ac_hi, void* Ac_lo,
                       int64_t ldac, float* colsum_partial, float* zero_row, int32_t zero_cols, int32_t slot_ready,
                       rgcn_stream_t stream);
+
+/* Weights converted once per layer call: bf16 hi (, lo) planes of the row-major [K1 + K2, d_out] block [W1; W2] exactly
+ * as PyTorch stores it (row stride padded to a multiple of 8).  rgcn_transform_fwd_w reads them as the MN-major B operand
+ * of the tcgen05 kernel (no transposed copy), rgcn_transform_dgrad_w as the K-major one; otherwise they are
+ * rgcn_transform_fwd / rgcn_transform_dgrad.  dropout_counter (nullable) is advanced by the conversion kernel, as the
+ * conversion inside rgcn_transform_fwd does.  row_offset: row of the layer's output that row 0 of this call is (the
+ * fused dropout hashes the GLOBAL element index, so row-chunked calls of one layer draw one consistent mask). */
+size_t rgcn_weight_planes_bytes(int32_t K, int32_t d_out);
+int rgcn_prepare_weights(const float* W1, int32_t K1, const float* W2, int32_t K2, int32_t d_out, int32_t mode,
+                         void* w_planes, unsigned long long* dropout_counter, rgcn_stream_t stream);
+int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t lda, int32_t K, const void* w_planes,
+                         const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
+                         int32_t mode, float dropout_p, uint32_t dropout_seed, const unsigned long long* dropout_counter,
+                         int64_t row_offset, float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
+                         rgcn_stream_t stream);
+int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const void* w_planes, int32_t K,
+                           int64_t n_rows, float* gA, int64_t ldga, int32_t mode, rgcn_stream_t stream);
 
 int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream);
 int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream);

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgcn_b200.so")
 
-ABI_VERSION = 4          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
+ABI_VERSION = 5          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
 
 _lock = threading.Lock()
 _lib = None
@@ -25,7 +25,7 @@ class CsrStruct(C.Structure):
     """Mirror of ``rgcn_csr_t`` (include/rgcn_b200.h)."""
     _fields_ = [("rowptr", p), ("idx", p), ("w", p), ("n_rows", i64), ("E", i64), ("R", i32),
                 ("n_hubs", i32), ("n_chunks", i32), ("hub_threshold", i32), ("hub_keys", p),
-                ("hub_chunk_ptr", p), ("chunk_table", p), ("row_order", p)]
+                ("hub_chunk_ptr", p), ("chunk_table", p), ("row_order", p), ("order_chunk_rows", i64)]
 
 
 PCSR = C.POINTER(CsrStruct)
@@ -40,7 +40,8 @@ class LayerFwdArgs(C.Structure):
                 ("dropout_p", f32), ("dropout_seed", u32), ("dropout_counter", p),
                 ("A_hi", p), ("A_lo", p), ("lda", i64), ("out", p), ("ldo", i64),
                 ("peer_out_host", p), ("n_peer", i32), ("peer_row0", i64), ("peer_ld", i64),
-                ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz)]
+                ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
+                ("w_planes", p), ("w_planes_bytes", sz), ("pipeline", i32)]
 
 
 class MaskedPlanesOut(C.Structure):
@@ -57,7 +58,8 @@ class LayerBwdArgs(C.Structure):
                 ("g_x", p), ("ld_g_x", i64), ("g_weight", p), ("g_root", p), ("g_bias", p),
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
                 ("rows", p), ("n_list", i64), ("slot", p), ("Ac_hi", p), ("Ac_lo", p), ("ldac", i64),
-                ("next_G", C.POINTER(MaskedPlanesOut)), ("g_ready", i32), ("n_colsum_ready", i32), ("slot_ready", i32)]
+                ("next_G", C.POINTER(MaskedPlanesOut)), ("g_ready", i32), ("n_colsum_ready", i32), ("slot_ready", i32),
+                ("w_planes", p)]
 
 # name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
 PROTOTYPES = {
@@ -78,6 +80,12 @@ PROTOTYPES = {
     "rgcn_reduce_partials": (C.c_int, [p, i64, i32, p, p]),
     "rgcn_aggregate_bwd": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
     "rgcn_aggregate_row_blocks": (i64, [PCSR, i32]),
+    "rgcn_aggregate_fwd_rows": (C.c_int, [PCSR, p, i64, i32, p, p, i64, i32, p, i64, i64, i64, i32, p, sz, p]),
+    "rgcn_weight_planes_bytes": (sz, [i32, i32]),
+    "rgcn_prepare_weights": (C.c_int, [p, i32, p, i32, i32, i32, p, p, p]),
+    "rgcn_transform_fwd_w": (C.c_int, [p, p, i64, i32, p, p, i32, i64, i32, p, i64, i32, C.c_float, C.c_uint32, p, i64,
+                                       p, i32, i64, i64, p]),
+    "rgcn_transform_dgrad_w": (C.c_int, [p, p, i64, i32, p, i32, i64, p, i64, i32, p]),
     "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
     "rgcn_rows_compact_size": (i64, [i64]),
     "rgcn_rows_compact_blocks": (i64, [i64]),

@@ -55,8 +55,9 @@ class _RGCNLayerFn(torch.autograd.Function):
             raise ValueError(f"x has {x_root.size(0)} rows, the graph updates {graph.n_dst}")
         # drop = (p, seed, device counter): ReLU + dropout fused into the GEMM epilogue (reference :124-125)
         p_drop, seed, ctr = drop if drop is not None else (0.0, 0, None)
-        out, A = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr)
+        out, A, wp = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr)
         ctx.graph, ctx.relu, ctx.mode, ctx.shared, ctx.p_drop = graph, relu, mode, shared, p_drop
+        ctx.w_planes = wp               # the weights as bf16 planes (converted once): the backward's dgrad reads them
         # in_mask_scale: x is the fused ReLU (+ dropout) output of the layer upstream, whose backward will want this
         # layer's input gradient masked by x > 0 and scaled — the backward walk can write that directly (rowsparse.py)
         ctx.in_mask_scale = in_mask_scale if (shared and in_mask_scale is not None) else None
@@ -87,7 +88,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         res = ops.layer_bwd(
             graph, gO.contiguous(), out, mask_scale, (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
             need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any, rows=rows, g_ready=g_ready,
-            next_mask=next_mask, slot=slot,
+            next_mask=next_mask, slot=slot, w_planes=ctx.w_planes,
             gx_out=ops.param_grad(graph.n_src, d_in, device=gO.device) if (need_x and ctx.x_is_param) else None)
         gx, gA, gWf, groot, gb = res[:5]
         if next_mask is not None:

@@ -42,6 +42,9 @@ struct AggParams {
   int32_t skip_hubs;           // the row walk leaves hub segments out (hub_finish_kernel adds them afterwards)
   int32_t n_hubs;
   int64_t n_rows;
+  int32_t range_mode;          // 0: the launch walks all rows; 1: positions [row_begin, row_end) of the row order only
+  int64_t row_begin, row_end;
+  int32_t no_hub_pass;         // the chunk partials are already in `partials` (an earlier launch of the same call made them)
   int32_t R;
   const float* F;            // gathered feature matrix
   int64_t ldf;
@@ -226,8 +229,8 @@ aggregate_rows_kernel(const AggParams p) {
   }
   const int lane = threadIdx.x % G, grp = threadIdx.x / G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-  int64_t row = (int64_t)blockIdx.x * GROUPS + grp;
-  if (row >= p.n_rows) {
+  int64_t row = p.row_begin + (int64_t)blockIdx.x * GROUPS + grp;
+  if (row >= p.row_end) {
     if (!with_gc && !with_cs) return;
     if (with_cs)
       for (int t = lane; t < p.d; t += G) s_comp[grp * p.d + t] = 0.f;
@@ -653,6 +656,7 @@ static bool overlap_hubs_enabled() {
 
 template <int G, int VPL, int MIX, bool W>
 static int launch_agg_overlapped(AggParams p, int n_chunks, cudaStream_t st) {
+  if (!p.range_mode) { p.row_begin = 0; p.row_end = p.n_rows; }
   // hub chunks on a side stream, concurrently with the row walk (which skips the hub segments); then the finish
   // kernel.  Inside a stream capture the fork / join becomes two parallel branches of the graph.
   constexpr int GROUPS = 256 / G;
@@ -674,9 +678,13 @@ static int launch_agg_overlapped(AggParams p, int n_chunks, cudaStream_t st) {
 }
 
 template <int G, int VPL>
-static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st) {
+static int launch_agg(const AggParams& p_in, int mix, int n_chunks, cudaStream_t st) {
   constexpr int GROUPS = 256 / G;
-  if (!p.slot && !p.mp_hi && n_chunks > 0 && p.n_rows > 0 && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
+  AggParams p = p_in;
+  if (!p.range_mode) { p.row_begin = 0; p.row_end = p.n_rows; }
+  if (p.no_hub_pass) n_chunks = 0;
+  const int64_t n_walk = p.row_end - p.row_begin;
+  if (!p.slot && !p.mp_hi && n_chunks > 0 && p.n_rows > 0 && n_walk == p.n_rows && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
     const bool w = p.edge_w != nullptr;
     if (mix == MIX_NONE)
       return w ? launch_agg_overlapped<G, VPL, MIX_NONE, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_NONE, false>(p, n_chunks, st);
@@ -689,8 +697,8 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
       RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, true, true>, dim3(n_chunks), dim3(256), 0, st, p));
       RGCN_LAUNCH_CHECK();
     }
-    if (p.n_rows == 0) return RGCN_OK;
-    const dim3 sgrid((unsigned)((p.n_rows + GROUPS - 1) / GROUPS));
+    if (n_walk <= 0) return RGCN_OK;
+    const dim3 sgrid((unsigned)((n_walk + GROUPS - 1) / GROUPS));
     if (p.mp_hi) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true, true>, sgrid, dim3(256),
                                       p.mp_colsum ? (size_t)GROUPS * p.d * sizeof(float) : 0, st, p));
     else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true>, sgrid, dim3(256), 0, st, p));
@@ -702,8 +710,8 @@ static int launch_agg(const AggParams& p, int mix, int n_chunks, cudaStream_t st
     else RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, false>, dim3(n_chunks), dim3(256), 0, st, p));
     RGCN_LAUNCH_CHECK();
   }
-  if (p.n_rows == 0) return RGCN_OK;
-  const unsigned grid = (unsigned)((p.n_rows + GROUPS - 1) / GROUPS);
+  if (n_walk <= 0) return RGCN_OK;
+  const unsigned grid = (unsigned)((n_walk + GROUPS - 1) / GROUPS);
   const bool w = p.edge_w != nullptr;
   const size_t sm = (size_t)p.R * p.B * sizeof(float) * (p.dotP ? 1 + GROUPS : 1);
   if (mix == MIX_NONE) {
@@ -831,6 +839,38 @@ extern "C" int rgcn_aggregate_fwd(const rgcn_csr_t* g, const float* X, int64_t l
     }
   }
   return RGCN_OK;
+}
+
+// Row-range form of the (unmixed) forward walk: positions [row_begin, row_end) of the walk order only; hub_pass = 0 when
+// an earlier call of the same layer has already reduced the hub chunks into `workspace`.  rgcn_layer_fwd uses it to
+// pipeline the walk of row chunk c + 1 with the transform of chunk c.
+extern "C" int rgcn_aggregate_fwd_rows(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d, void* H, void* H_lo,
+                                       int64_t ldh, int32_t out_mode, const float* x_root, int64_t ld_x_root,
+                                       int64_t row_begin, int64_t row_end, int32_t hub_pass, void* workspace,
+                                       size_t workspace_bytes, rgcn_stream_t stream) {
+  int rc = check_common(g, X, ldx, d, workspace, workspace_bytes);
+  if (rc) return rc;
+  RGCN_CHECK_ARG(!x_root || (((uintptr_t)x_root & 15) == 0 && ld_x_root % 4 == 0), "aggregate_fwd_rows: x_root misaligned");
+  RGCN_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "aggregate_fwd_rows: out_mode must be 0 (fp32), 1 (bf16) or 2 (bf16 hi+lo)");
+  RGCN_CHECK_ARG(H && ((uintptr_t)H & (out_mode ? 7 : 15)) == 0 && ldh % 4 == 0, "aggregate_fwd_rows: output must be aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(out_mode != 2 || (H_lo && ((uintptr_t)H_lo & 7) == 0), "aggregate_fwd_rows: out_mode 2 needs the lo plane");
+  RGCN_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= g->n_rows, "aggregate_fwd_rows: bad row range");
+  RGCN_CHECK_ARG(!g->row_order || g->order_chunk_rows == 0 ||
+                 ((row_begin % g->order_chunk_rows == 0) && (row_end % g->order_chunk_rows == 0 || row_end == g->n_rows)),
+                 "aggregate_fwd_rows: with a chunk-wise row order the range must consist of whole order chunks");
+  RGCN_CHECK_ARG(!g->row_order || g->order_chunk_rows > 0 || (row_begin == 0 && row_end == g->n_rows),
+                 "aggregate_fwd_rows: a global row order cannot be walked in ranges");
+  AggParams p{};
+  p.rowptr = g->rowptr; p.idx = g->idx; p.edge_w = g->w;
+  p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs; p.chunk_table = g->chunk_table;
+  p.row_order = g->row_order; p.hub_threshold = g->hub_threshold;
+  p.n_rows = g->n_rows; p.R = g->R;
+  p.F = X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d; p.block_stride = d;
+  p.O = H; p.O_lo = H_lo; p.ldo = ldh; p.out_mode = out_mode; p.partials = (float*)workspace;
+  p.root_rows = x_root; p.ld_root = ld_x_root;
+  p.range_mode = 1; p.row_begin = row_begin; p.row_end = row_end; p.no_hub_pass = hub_pass ? 0 : 1;
+  if (row_end == row_begin && !hub_pass) return RGCN_OK;            // (an empty range with hub_pass = the hub pass alone)
+  return dispatch_agg(p, MIX_NONE, g->n_chunks, (cudaStream_t)stream);
 }
 
 static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,

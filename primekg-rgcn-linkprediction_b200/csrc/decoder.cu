@@ -370,9 +370,11 @@ struct LinkBwdRows {
   const int32_t* slot; const int64_t* rows; int32_t unlisted;
   float* tab_partial;                               // [n_tab_blocks, n_rel * d], nullable
   int32_t n_owner_blocks, n_zero_blocks, n_tab_blocks;
+  int32_t rows_in_smem;                             // the launch has 2 n ints of dynamic shared memory for the position list
 };
 constexpr int kLinkZeroRows = 64;                    // rows per zero-fill block
-constexpr int kLinkTabPairs = 32;                    // pairs per relation-table partial
+constexpr int kLinkTabPairs = 32;
+constexpr int kLinkList = 64;                       // positions of one node collected before they are added                    // pairs per relation-table partial
 
 __device__ __forceinline__ float link_pair_grad(const LinkLossParams& q, const LinkBwdRows& b, int64_t p) {
   if (b.g_score) return b.g_score[p];
@@ -380,8 +382,9 @@ __device__ __forceinline__ float link_pair_grad(const LinkLossParams& q, const L
   return (*b.g_loss) * (1.f / (1.f + expf(-s)) - q.labels[p]) / (float)q.n_pairs;
 }
 
-__global__ void __launch_bounds__(256) link_bwd_rows_kernel(const LinkLossParams q, const LinkBwdRows b) {
+__global__ void __launch_bounds__(256, 2) link_bwd_rows_kernel(const LinkLossParams q, const LinkBwdRows b) {
   pdl_enter();
+  extern __shared__ int s_rows[];                    // [2 n] node of every position (owner blocks, when it fits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = q.d >> 2;
   const int64_t n = q.n_pairs, n2 = 2 * q.n_pairs;
@@ -390,48 +393,102 @@ __global__ void __launch_bounds__(256) link_bwd_rows_kernel(const LinkLossParams
   int blk = blockIdx.x;
   if (blk < b.n_owner_blocks) {
     // ---- one warp per position; only the node's first position (its owner) works ----
+    // the owner scans the position list for its node: from shared memory (one coalesced copy per block) — a scan from
+    // global memory is a chain of 2 n / 32 exposed load latencies per warp (measured: 50 us for n = 2,048)
+    if (b.rows_in_smem) {
+      for (int64_t i = threadIdx.x; i < n2; i += 256) s_rows[i] = (int)b.rows[i];
+      __syncthreads();
+    }
     const int64_t pos = (int64_t)blk * 8 + warp;
     if (pos >= n2) return;
     const int64_t v = b.rows[pos];
     if (__ldg(b.slot + v) != (int32_t)pos) return;
+    // A hub gene heads or tails dozens of pairs of one batch: adding them one after the other would be a chain of
+    // dependent load latencies (pair indices -> partner row).  So: (1) scan, collecting the positions that list this node
+    // in ascending order into a per-warp list; (2) one lane per listed position fetches the pair's indices and its
+    // score gradient — all at once; (3) the partner rows are loaded four ahead and added strictly in list order.
+    __shared__ int s_list[8][kLinkList];
+    int* list = s_list[warp];
     for (int v0 = 0; v0 < nv; v0 += 64) {            // column passes of two 128-bit vectors per lane
       const int vi0 = v0 + lane, vi1 = v0 + 32 + lane;
       const bool on0 = vi0 < nv, on1 = vi1 < nv;
       float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-      for (int64_t base = pos & ~int64_t(31); base < n2; base += 32) {
-        const int64_t pp = base + lane;
-        unsigned m = __ballot_sync(0xffffffffu, pp >= pos && pp < n2 && b.rows[pp] == v);
-        while (m) {                                  // ascending position order: the order of the sum is fixed
-          const int bit = __ffs((int)m) - 1;
-          m &= m - 1u;
-          const int64_t qq = base + bit;
-          const bool is_head = qq < n;
-          const int64_t p = is_head ? qq : qq - n;
-          const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
-          if (!pair_ok(q, hi, ti, ri)) continue;     // (an invalid pair parks its positions on row 0)
-          const float g = link_pair_grad(q, b, p);
-          const float* __restrict__ other = q.emb + (is_head ? ti : hi) * q.ld;
-          const float* __restrict__ r = q.rel_table + ri * q.d;
-          if (on0) {
-            const float4 o = ldg4(other + vi0 * 4);
-            float4 w = ldg4(r + vi0 * 4);
-            if (q.drop_thresh) {
-              const float4 mk = rel_drop4(key, p, q.d, vi0, q.drop_thresh, q.drop_scale);
-              w.x *= mk.x; w.y *= mk.y; w.z *= mk.z; w.w *= mk.w;
+      auto flush = [&](int count) {
+        __syncwarp();
+        for (int e0 = 0; e0 < count; e0 += 32) {
+          const int e = e0 + lane;
+          int m_other = 0, m_rel = 0, m_pair = 0;
+          float m_g = 0.f;                           // 0 for an invalid pair or a lane past the list: contributes exact zeros
+          if (e < count) {
+            const int64_t qq = list[e];
+            const bool is_head = qq < n;
+            const int64_t p = is_head ? qq : qq - n;
+            const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
+            if (pair_ok(q, hi, ti, ri)) {            // (an invalid pair parks its positions on row 0)
+              m_other = (int)(is_head ? ti : hi); m_rel = (int)ri; m_pair = (int)p;
+              m_g = link_pair_grad(q, b, p);
             }
-            acc0.x += g * w.x * o.x; acc0.y += g * w.y * o.y; acc0.z += g * w.z * o.z; acc0.w += g * w.w * o.w;
           }
-          if (on1) {
-            const float4 o = ldg4(other + vi1 * 4);
-            float4 w = ldg4(r + vi1 * 4);
-            if (q.drop_thresh) {
-              const float4 mk = rel_drop4(key, p, q.d, vi1, q.drop_thresh, q.drop_scale);
-              w.x *= mk.x; w.y *= mk.y; w.z *= mk.z; w.w *= mk.w;
+          const int nb = min(32, count - e0);
+          for (int j = 0; j < nb; j += 4) {
+            float4 o0[4], w0[4], o1[4], w1[4];
+            float g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int src = min(j + u, 31);
+              const int oth = __shfl_sync(0xffffffffu, m_other, src);
+              const int ri = __shfl_sync(0xffffffffu, m_rel, src);
+              const int pr = __shfl_sync(0xffffffffu, m_pair, src);
+              g[u] = (j + u < nb) ? __shfl_sync(0xffffffffu, m_g, src) : 0.f;
+              const float* __restrict__ other = q.emb + (int64_t)oth * q.ld;
+              const float* __restrict__ r = q.rel_table + (int64_t)ri * q.d;
+              if (on0) {
+                o0[u] = ldg4(other + vi0 * 4);
+                w0[u] = ldg4(r + vi0 * 4);
+                if (q.drop_thresh) {
+                  const float4 mk = rel_drop4(key, pr, q.d, vi0, q.drop_thresh, q.drop_scale);
+                  w0[u].x *= mk.x; w0[u].y *= mk.y; w0[u].z *= mk.z; w0[u].w *= mk.w;
+                }
+              }
+              if (on1) {
+                o1[u] = ldg4(other + vi1 * 4);
+                w1[u] = ldg4(r + vi1 * 4);
+                if (q.drop_thresh) {
+                  const float4 mk = rel_drop4(key, pr, q.d, vi1, q.drop_thresh, q.drop_scale);
+                  w1[u].x *= mk.x; w1[u].y *= mk.y; w1[u].z *= mk.z; w1[u].w *= mk.w;
+                }
+              }
             }
-            acc1.x += g * w.x * o.x; acc1.y += g * w.y * o.y; acc1.z += g * w.z * o.z; acc1.w += g * w.w * o.w;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {            // list order = ascending position: the order of the sum is fixed
+              if (j + u < nb) {
+                if (on0) {
+                  acc0.x += g[u] * w0[u].x * o0[u].x; acc0.y += g[u] * w0[u].y * o0[u].y;
+                  acc0.z += g[u] * w0[u].z * o0[u].z; acc0.w += g[u] * w0[u].w * o0[u].w;
+                }
+                if (on1) {
+                  acc1.x += g[u] * w1[u].x * o1[u].x; acc1.y += g[u] * w1[u].y * o1[u].y;
+                  acc1.z += g[u] * w1[u].z * o1[u].z; acc1.w += g[u] * w1[u].w * o1[u].w;
+                }
+              }
+            }
           }
         }
+        __syncwarp();
+      };
+      int cnt = 0;
+      for (int64_t base = pos & ~int64_t(31); base < n2; base += 32) {
+        const int64_t pp = base + lane;
+        bool match = false;
+        if (pp >= pos && pp < n2) match = (b.rows_in_smem ? (int64_t)s_rows[pp] : b.rows[pp]) == v;
+        const unsigned m = __ballot_sync(0xffffffffu, match);
+        if (!m) continue;
+        const int k = __popc(m);
+        if (cnt + k > kLinkList) { flush(cnt); cnt = 0; }
+        if (match) list[cnt + __popc(m & ((1u << lane) - 1u))] = (int)pp;
+        cnt += k;
       }
+      flush(cnt);
       if (on0) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + vi0 * 4) = acc0;
       if (on1) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + vi1 * 4) = acc1;
     }
@@ -697,8 +754,20 @@ extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64
   b.n_zero_blocks = (int32_t)((n_nodes + kLinkZeroRows - 1) / kLinkZeroRows);
   b.n_tab_blocks = g_rel_table ? (int32_t)((n_pairs + kLinkTabPairs - 1) / kLinkTabPairs) : 0;
   b.tab_partial = g_rel_table ? (float*)align_up((size_t)workspace, 16) : nullptr;
+  size_t smem = (size_t)(2 * n_pairs) * sizeof(int);
+  b.rows_in_smem = smem <= 200 * 1024 ? 1 : 0;       // (larger batches scan the list in global memory)
+  if (!b.rows_in_smem) smem = 0;
+  if (smem > 48 * 1024) {
+    static size_t granted[64] = {0};
+    int dev = 0;
+    RGCN_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && granted[dev] < smem) {
+      RGCN_CUDA(cudaFuncSetAttribute(link_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      granted[dev] = 200 * 1024;
+    }
+  }
   RGCN_CUDA(launch_pdl(link_bwd_rows_kernel, dim3((unsigned)(b.n_owner_blocks + b.n_zero_blocks + b.n_tab_blocks)), dim3(256),
-                       0, st, q, b));
+                       smem, st, q, b));
   RGCN_LAUNCH_CHECK();
   if (g_rel_table) {
     rc = rgcn_reduce_partials(b.tab_partial, b.n_tab_blocks, n_rel * d, g_rel_table, stream);    // fixed order

@@ -59,8 +59,11 @@ static int dgrad_walk_wgrad(const rgcn_layer_bwd_args* a, int64_t m, const void*
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (a->gA) {
-    rc = rgcn_transform_dgrad(a->G_hi, a->G_lo, a->ldg, a->d_out, a->weight, K1, a->root, K2, m, a->gA, a->ld_gA,
-                              a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
+    if (a->w_planes)
+      rc = rgcn_transform_dgrad_w(a->G_hi, a->G_lo, a->ldg, a->d_out, a->w_planes, K1 + K2, m, a->gA, a->ld_gA, a->mode, stream);
+    else
+      rc = rgcn_transform_dgrad(a->G_hi, a->G_lo, a->ldg, a->d_out, a->weight, K1, a->root, K2, m, a->gA, a->ld_gA,
+                                a->mode, a->gemm_workspace, a->gemm_workspace_bytes, stream);
     if (rc) return rc;
   }
   SideStream* ss = (need_w && a->gA && a->g_x) ? overlap_wgrad(st) : nullptr;
@@ -85,21 +88,101 @@ static int dgrad_walk_wgrad(const rgcn_layer_bwd_args* a, int64_t m, const void*
   return RGCN_OK;
 }
 
+// ---- forward: the walk of row chunk c + 1 under the transform of chunk c --------------------------------------------
+// The walk is bound by L2 / HBM gathers, the transform by the tensor pipe and (in the partitioned path) by the NVLink
+// stores of its epilogue: run on two streams they overlap instead of adding up.  The hub chunks are reduced once, up
+// front; the weights are converted once (rgcn_prepare_weights) and shared by all chunks; a chunk-wise row order
+// (rgcn_csr_t::order_chunk_rows) keeps every chunk's rows a contiguous range, which is what the transform needs.
+static int pipeline_mode(const rgcn_layer_fwd_args* a, cudaStream_t st, SideStream** ss_out) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("RGCN_PIPELINE");
+    env = !e ? 2 : (e[0] == '0' ? 0 : 1);
+  }
+  *ss_out = nullptr;
+  int want = a->pipeline == 1 ? 0 : (a->pipeline == 2 ? 1 : env);        // 0 never, 1 always, 2 library decides
+  if (want == 0) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+  SideStream* ss = side_stream(!capturing);
+  if (!ss) return 0;
+  if (want == 2 && !capturing && a->csr->n_rows < 200000) return 0;       // eager + small: the host is the limiter
+  *ss_out = ss;
+  return 1;
+}
+
+static int64_t pipeline_chunk_rows(const rgcn_csr_t* g) {
+  if (g->row_order) return g->order_chunk_rows;                           // 0: global order, cannot be walked in ranges
+  int64_t c = (g->n_rows + 7) / 8;                                         // ~8 chunks, whole 128-row tiles
+  c = (c + 127) / 128 * 128;
+  return c < 8192 ? 8192 : c;
+}
+
 extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(a && a->csr, "layer_fwd: null arguments");
   const int R = a->csr->R;
-  const int K1 = R * a->d_in, K2 = a->d_in;
+  const int K1 = R * a->d_in, K2 = a->d_in, K = K1 + K2;
   const int out_mode = a->mode == 0 ? 2 : 1;
   RGCN_CHECK_ARG(a->mode == 0 || a->mode == 1, "layer_fwd: mode must be 0 (fp32) or 1 (bf16)");
   RGCN_CHECK_ARG(a->A_hi && (a->mode == 1 || a->A_lo) && a->lda >= K1 + K2, "layer_fwd: operand planes missing or too narrow");
-  // the row walk also appends x_root[i] as the last block of row i: the operand [H | X] in one kernel
-  int rc = rgcn_aggregate_fwd(a->csr, a->x_src, a->ld_x_src, a->d_in, nullptr, 0, a->A_hi, a->mode == 0 ? a->A_lo : nullptr,
-                              a->lda, out_mode, nullptr, 0, nullptr, a->x_root, a->ld_x_root, a->agg_workspace,
-                              a->agg_workspace_bytes, stream);
+  if (!a->w_planes) {
+    // the row walk also appends x_root[i] as the last block of row i: the operand [H | X] in one kernel
+    int rc = rgcn_aggregate_fwd(a->csr, a->x_src, a->ld_x_src, a->d_in, nullptr, 0, a->A_hi, a->mode == 0 ? a->A_lo : nullptr,
+                                a->lda, out_mode, nullptr, 0, nullptr, a->x_root, a->ld_x_root, a->agg_workspace,
+                                a->agg_workspace_bytes, stream);
+    if (rc) return rc;
+    return rgcn_transform_fwd(a->A_hi, a->A_lo, a->lda, K1, K2, a->weight, a->root, a->bias, a->relu, a->csr->n_rows, a->d_out,
+                              a->out, a->ldo, a->mode, a->dropout_p, a->dropout_seed, a->dropout_counter, a->peer_out_host,
+                              a->n_peer, a->peer_row0, a->peer_ld, a->gemm_workspace, a->gemm_workspace_bytes, stream);
+  }
+  RGCN_CHECK_ARG(a->w_planes_bytes >= rgcn_weight_planes_bytes(K, a->d_out), "layer_fwd: w_planes too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = a->csr->n_rows;
+  int rc = rgcn_prepare_weights(a->weight, K1, a->root, K2, a->d_out, a->mode, a->w_planes,
+                                a->dropout_p > 0.f ? a->dropout_counter : nullptr, stream);
   if (rc) return rc;
-  return rgcn_transform_fwd(a->A_hi, a->A_lo, a->lda, K1, K2, a->weight, a->root, a->bias, a->relu, a->csr->n_rows, a->d_out,
-                            a->out, a->ldo, a->mode, a->dropout_p, a->dropout_seed, a->dropout_counter, a->peer_out_host,
-                            a->n_peer, a->peer_row0, a->peer_ld, a->gemm_workspace, a->gemm_workspace_bytes, stream);
+  void* A_lo = a->mode == 0 ? a->A_lo : nullptr;
+  auto transform = [&](int64_t r0, int64_t r1, rgcn_stream_t s) {
+    const char* hi = (const char*)a->A_hi + (size_t)r0 * a->lda * 2;
+    const char* lo = A_lo ? (const char*)A_lo + (size_t)r0 * a->lda * 2 : nullptr;
+    return rgcn_transform_fwd_w(hi, lo, a->lda, K, a->w_planes, a->bias, a->relu, r1 - r0, a->d_out, a->out + r0 * a->ldo,
+                                a->ldo, a->mode, a->dropout_p, a->dropout_seed, a->dropout_counter, r0, a->peer_out_host,
+                                a->n_peer, a->peer_row0 + r0, a->peer_ld, s);
+  };
+  SideStream* ss = nullptr;
+  const int64_t chunk = pipeline_chunk_rows(a->csr);
+  if (chunk <= 0 || n < 2 * chunk || !pipeline_mode(a, st, &ss)) {
+    rc = rgcn_aggregate_fwd(a->csr, a->x_src, a->ld_x_src, a->d_in, nullptr, 0, a->A_hi, A_lo, a->lda, out_mode, nullptr, 0,
+                            nullptr, a->x_root, a->ld_x_root, a->agg_workspace, a->agg_workspace_bytes, stream);
+    if (rc) return rc;
+    return transform(0, n, stream);
+  }
+  // hub chunks first (all rows' hub segments), then chunk by chunk
+  if (a->csr->n_chunks > 0) {
+    rc = rgcn_aggregate_fwd_rows(a->csr, a->x_src, a->ld_x_src, a->d_in, a->A_hi, A_lo, a->lda, out_mode, a->x_root, a->ld_x_root,
+                                 0, 0, 1, a->agg_workspace, a->agg_workspace_bytes, stream);
+    if (rc) return rc;
+  }
+  RGCN_CUDA(cudaEventRecord(ss->fork, st));
+  RGCN_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+  for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+    const int64_t r1 = r0 + chunk < n ? r0 + chunk : n;
+    rc = rgcn_aggregate_fwd_rows(a->csr, a->x_src, a->ld_x_src, a->d_in, a->A_hi, A_lo, a->lda, out_mode, a->x_root, a->ld_x_root,
+                                 r0, r1, 0, a->agg_workspace, a->agg_workspace_bytes, stream);
+    if (rc) return rc;
+    if (r1 < n) {
+      RGCN_CUDA(cudaEventRecord(ss->fork, st));
+      RGCN_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
+      rc = transform(r0, r1, (rgcn_stream_t)ss->side);
+    } else {
+      // the last chunk's transform has nothing left to hide behind: join first, then run it on the main stream
+      RGCN_CUDA(cudaEventRecord(ss->join, ss->side));
+      RGCN_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
+      rc = transform(r0, r1, stream);
+    }
+    if (rc) return rc;
+  }
+  return RGCN_OK;
 }
 
 // g_out is zero outside the listed rows (csrc/rowsparse.cu): compact, then the same four steps over m_c rows

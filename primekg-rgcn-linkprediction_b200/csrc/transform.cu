@@ -157,6 +157,7 @@ struct GemmKParams {
   float* out; int64_t ldo;
   // fused dropout after the ReLU (training): keep iff drop_bits(...) >= drop_thresh, kept values times drop_scale
   uint32_t drop_thresh; float drop_scale; uint32_t drop_seed; const unsigned long long* drop_ctr;
+  int64_t row_offset;                         // row of the layer's output that local row 0 is (row-chunked calls): dropout index
   // fused all-gather: every output tile is also stored into the same-shaped slot (rows peer_row0 ...) of up to
   // kMaxPeers feature buffers that live in OTHER GPUs' memory (peer-mapped, NVLink stores issued by the epilogue)
   float* peer_out[kMaxPeers]; int n_peer; int64_t peer_row0; int64_t peer_ld;
@@ -181,7 +182,10 @@ struct KStage {
 // Persistent, warp-specialised: CTA c walks tiles c, c + grid, ... (column tile fastest, so neighbouring CTAs share
 // the A rows in L2).  The smem ring and the two TMEM accumulators are continuous across tiles: the MMA warp starts
 // tile i+1 while the epilogue warps drain tile i.
-template <bool SPLIT>
+// B_MN = false: B is K-major ([N, K] rows of K, the dgrad / all-pairs operand);  B_MN = true: B is MN-major ([K, N] rows
+// of N — the weight matrix exactly as PyTorch stores it, so the forward needs no transposed copy): the stage then holds
+// ceil(BN / 64) chunks of 64 k-rows x 128 B, the layout of the weight-gradient kernel's operands.
+template <bool SPLIT, bool B_MN>
 __global__ void __launch_bounds__(K_THREADS, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -270,7 +274,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             float4 v = *reinterpret_cast<const float4*>(patch + rl * 20 + c4);
             if (p.drop_thresh) {
               // N % 4 == 0, so the four elements of one store never straddle a 2^32 block
-              const uint64_t e0 = (uint64_t)row * (uint64_t)p.N + (uint64_t)(n0 + cc + c4);
+              const uint64_t e0 = (uint64_t)(row + p.row_offset) * (uint64_t)p.N + (uint64_t)(n0 + cc + c4);
               // two hashes per store, 16 random bits per element (p is resolved to 2^-16)
               const uint32_t bk = drop_block_key(drop_key, e0), e32 = (uint32_t)e0;
               const uint32_t h0 = pcg_hash(e32 ^ bk), h1 = pcg_hash((e32 + 2) ^ bk);
@@ -292,7 +296,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   } else if (warp == K_EPI_WARPS) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t bytes = (uint32_t)(BM + p.BN) * 128u * (SPLIT ? 2u : 1u);
+      // a TMA box always delivers its full byte count (out-of-range elements arrive as zeros)
+      const int b_chunks = (p.BN + 63) / 64;                                // MN-major B: boxes of 64 n x BK k
+      const uint32_t b_bytes = B_MN ? (uint32_t)b_chunks * (uint32_t)(BK * 128) : (uint32_t)p.BN * 128u;
+      const uint32_t bytes = ((uint32_t)BM * 128u + b_bytes) * (SPLIT ? 2u : 1u);
       uint32_t it = 0;
       for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
         const int m0 = (int)((t / p.n_tiles) * BM);
@@ -304,10 +311,15 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           uint8_t* st = smem + (size_t)s * S::BYTES;
           mbar_arrive_expect_tx(&full_bar[s], bytes);
           tma_load_2d(st + S::A_HI, &tm_a_hi, &full_bar[s], kb * BK, m0);
-          tma_load_2d(st + S::B_HI, &tm_b_hi, &full_bar[s], kb * BK, n0);
-          if (SPLIT) {
-            tma_load_2d(st + S::A_LO, &tm_a_lo, &full_bar[s], kb * BK, m0);
-            tma_load_2d(st + S::B_LO, &tm_b_lo, &full_bar[s], kb * BK, n0);
+          if (SPLIT) tma_load_2d(st + S::A_LO, &tm_a_lo, &full_bar[s], kb * BK, m0);
+          if (B_MN) {
+            for (int ch = 0; ch < b_chunks; ++ch) {
+              tma_load_2d(st + S::B_HI + ch * (BK * 128), &tm_b_hi, &full_bar[s], n0 + ch * 64, kb * BK);
+              if (SPLIT) tma_load_2d(st + S::B_LO + ch * (BK * 128), &tm_b_lo, &full_bar[s], n0 + ch * 64, kb * BK);
+            }
+          } else {
+            tma_load_2d(st + S::B_HI, &tm_b_hi, &full_bar[s], kb * BK, n0);
+            if (SPLIT) tma_load_2d(st + S::B_LO, &tm_b_lo, &full_bar[s], kb * BK, n0);
           }
         }
       }
@@ -315,7 +327,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   } else {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(BM, p.BN, 0, 0);
+      const uint32_t idesc = idesc_bf16(BM, p.BN, 0, B_MN ? 1 : 0);
       uint32_t it = 0;
       int iter = 0;
       for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++iter) {
@@ -330,16 +342,18 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           fence_after_sync();
           const uint32_t base = smem_u32(smem + (size_t)s * S::BYTES);
           const uint64_t da_hi = smem_desc_sw128(base + S::A_HI, 16, 1024);
-          const uint64_t db_hi = smem_desc_sw128(base + S::B_HI, 16, 1024);
           const uint64_t da_lo = smem_desc_sw128(base + S::A_LO, 16, 1024);
-          const uint64_t db_lo = smem_desc_sw128(base + S::B_LO, 16, 1024);
+          // MN-major B: LBO = stride between the 64-column chunks, SBO = stride between 8-k groups (as in the wgrad kernel)
+          const uint64_t db_hi = B_MN ? smem_desc_sw128(base + S::B_HI, BK * 128, 1024) : smem_desc_sw128(base + S::B_HI, 16, 1024);
+          const uint64_t db_lo = B_MN ? smem_desc_sw128(base + S::B_LO, BK * 128, 1024) : smem_desc_sw128(base + S::B_LO, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 16 bf16 = 32 bytes along K inside the swizzle row
-            mma_bf16_ss(tacc, da_hi + adv, db_hi + adv, idesc, (kb | k) ? 1u : 0u);
+            const uint64_t adv_b = B_MN ? (uint64_t)(k * 2048 >> 4) : adv;   // MN-major: 16 k = two 8-k atoms of 1024 B
+            mma_bf16_ss(tacc, da_hi + adv, db_hi + adv_b, idesc, (kb | k) ? 1u : 0u);
             if (SPLIT) {
-              mma_bf16_ss(tacc, da_hi + adv, db_lo + adv, idesc, 1u);
-              mma_bf16_ss(tacc, da_lo + adv, db_hi + adv, idesc, 1u);
+              mma_bf16_ss(tacc, da_hi + adv, db_lo + adv_b, idesc, 1u);
+              mma_bf16_ss(tacc, da_lo + adv, db_hi + adv_b, idesc, 1u);
             }
           }
           mma_commit(&empty_bar[s]);            // frees the stage once these MMAs have read it
@@ -589,7 +603,7 @@ static EncodeTiledFn encode_fn() {
 struct MapKey { const void* base; int64_t rows, cols, ld; int box_rows; };
 static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   // the same planes / weight buffers come back every step: a small thread-local cache skips the driver call
-  constexpr int NC = 32;
+  constexpr int NC = 128;
   static thread_local MapKey keys[NC];
   static thread_local CUtensorMap vals[NC];
   static thread_local int n_cached = 0, next = 0;
@@ -657,32 +671,37 @@ static int check_plane(const void* p, int64_t ld, const char* what) {
 }
 
 // out[M, N] = A @ B^T with A planes [M, K] (ld lda) and weight planes [n_pad, k_pad]
+// B operand: a bf16 matrix [b_rows, b_cols] with leading dimension b_ld.  K-major (b_mn = false): rows = N, cols = K;
+// MN-major (b_mn = true): rows = K, cols = N (TMA boxes of 64 columns x BK rows).
+template <bool SPLIT, bool B_MN>
+static int launch_kmajor_t(const GemmKParams& p, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
+                           const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
+  int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN>, KStage<SPLIT>::SMEM);
+  if (rc) return rc;
+  RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN>, dim3(grid), dim3(K_THREADS), KStage<SPLIT>::SMEM, st, ahi, alo, mhi, mlo, p));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
 static int launch_kmajor(GemmKParams p, const void* a_hi, const void* a_lo, int64_t lda, int K,
-                         const __nv_bfloat16* bhi, const __nv_bfloat16* blo, int n_pad, int k_pad, int n_tiles, bool split,
-                         cudaStream_t st) {
+                         const __nv_bfloat16* bhi, const __nv_bfloat16* blo, int64_t b_rows, int64_t b_cols, int64_t b_ld,
+                         bool b_mn, int n_tiles, bool split, cudaStream_t st) {
   CUtensorMap ahi, alo, mhi, mlo;
   int rc = make_map(&ahi, a_hi, p.M, K, lda, BM);
   if (rc) return rc;
   rc = make_map(&alo, split ? a_lo : a_hi, p.M, K, lda, BM);
   if (rc) return rc;
-  rc = make_map(&mhi, bhi, n_pad, k_pad, k_pad, p.BN);
+  rc = make_map(&mhi, bhi, b_rows, b_cols, b_ld, b_mn ? BK : p.BN);
   if (rc) return rc;
-  rc = make_map(&mlo, split ? blo : bhi, n_pad, k_pad, k_pad, p.BN);
+  rc = make_map(&mlo, split ? blo : bhi, b_rows, b_cols, b_ld, b_mn ? BK : p.BN);
   if (rc) return rc;
   p.n_tiles = n_tiles;
   const int64_t tiles = ((p.M + BM - 1) / BM) * n_tiles;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  if (split) {
-    rc = set_smem(gemm_kmajor_kernel<true>, KStage<true>::SMEM);
-    if (rc) return rc;
-    RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<true>, dim3(grid), dim3(K_THREADS), KStage<true>::SMEM, st, ahi, alo, mhi, mlo, p));
-  } else {
-    rc = set_smem(gemm_kmajor_kernel<false>, KStage<false>::SMEM);
-    if (rc) return rc;
-    RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<false>, dim3(grid), dim3(K_THREADS), KStage<false>::SMEM, st, ahi, alo, mhi, mlo, p));
-  }
-  RGCN_LAUNCH_CHECK();
-  return RGCN_OK;
+  if (split) return b_mn ? launch_kmajor_t<true, true>(p, ahi, alo, mhi, mlo, grid, st)
+                         : launch_kmajor_t<true, false>(p, ahi, alo, mhi, mlo, grid, st);
+  return b_mn ? launch_kmajor_t<false, true>(p, ahi, alo, mhi, mlo, grid, st)
+              : launch_kmajor_t<false, false>(p, ahi, alo, mhi, mlo, grid, st);
 }
 
 static int wgrad_splits(int64_t nodes, int tiles) {
@@ -804,7 +823,7 @@ extern "C" int rgcn_transform_fwd(const void* A_hi, const void* A_lo, int64_t ld
     RGCN_CHECK_ARG(peer_out_host[q] && ((uintptr_t)peer_out_host[q] & 15) == 0, "transform_fwd: peer output %d is null or misaligned", q);
     p.peer_out[q] = peer_out_host[q];
   }
-  return launch_kmajor(p, A_hi, A_lo, lda, K, bhi, blo, t.n_pad, k_pad, t.n_tiles, split, st);
+  return launch_kmajor(p, A_hi, A_lo, lda, K, bhi, blo, t.n_pad, k_pad, k_pad, false, t.n_tiles, split, st);
 }
 
 extern "C" int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const float* W1,
@@ -840,7 +859,7 @@ extern "C" int rgcn_transform_dgrad(const void* G_hi, const void* G_lo, int64_t 
   GemmKParams p{};
   p.M = n_rows; p.N = K; p.BN = t.BN; p.num_kb = k_pad / BK;
   p.bias = nullptr; p.relu = 0; p.out = gA; p.ldo = ldga;
-  return launch_kmajor(p, G_hi, G_lo, ldg, d_out, bhi, blo, t.n_pad, k_pad, t.n_tiles, split, st);
+  return launch_kmajor(p, G_hi, G_lo, ldg, d_out, bhi, blo, t.n_pad, k_pad, k_pad, false, t.n_tiles, split, st);
 }
 
 extern "C" int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t lda, int32_t K1, int32_t K2,
@@ -900,4 +919,91 @@ extern "C" int rgcn_transform_wgrad(const void* A_hi, const void* A_lo, int64_t 
       colsum_partial, n_colsum, gbias));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weights converted ONCE per layer call: bf16 hi (, lo) planes of the row-major [K1 + K2, d_out] weight block exactly as
+// PyTorch stores it.  The forward reads them as the MN-major B operand (no transposed copy), the dgrad as the K-major one;
+// row-chunked calls of one layer share them.
+// ------------------------------------------------------------------------------------------------
+namespace rgcn {
+static int64_t wplane_ld(int d_out) { return round_up(d_out, 8); }          // TMA row stride: a multiple of 16 bytes
+static size_t wplane_bytes(int K, int d_out) { return align_up((size_t)K * wplane_ld(d_out) * 2, 1024); }
+}  // namespace rgcn
+
+extern "C" size_t rgcn_weight_planes_bytes(int32_t K, int32_t d_out) {
+  if (K <= 0 || d_out <= 0) return 0;
+  return 2 * wplane_bytes(K, d_out) + 1024;
+}
+
+extern "C" int rgcn_prepare_weights(const float* W1, int32_t K1, const float* W2, int32_t K2, int32_t d_out, int32_t mode,
+                                    void* w_planes, unsigned long long* dropout_counter, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(W1 && K1 > 0 && K2 >= 0 && (K2 == 0 || W2) && d_out > 0 && d_out % 4 == 0, "prepare_weights: bad sizes");
+  RGCN_CHECK_ARG(mode == 0 || mode == 1, "prepare_weights: mode must be 0 (fp32) or 1 (bf16)");
+  RGCN_CHECK_ARG(w_planes && ((uintptr_t)w_planes & 255) == 0, "prepare_weights: w_planes must be 256-byte aligned");
+  const int K = K1 + K2;
+  const int ld = (int)wplane_ld(d_out);
+  __nv_bfloat16* hi = (__nv_bfloat16*)w_planes;
+  __nv_bfloat16* lo = (__nv_bfloat16*)((char*)w_planes + wplane_bytes(K, d_out));
+  const int64_t total = (int64_t)K * ld;
+  RGCN_CUDA(launch_pdl(split_weights_kernel, dim3(grid_cap((total + 255) / 256, 1184)), dim3(256), 0, (cudaStream_t)stream,
+                       W1, K1, W2, K2, d_out, 0, hi, mode == 0 ? lo : (__nv_bfloat16*)nullptr, K, ld, dropout_counter));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t lda, int32_t K, const void* w_planes,
+                                    const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
+                                    int32_t mode, float dropout_p, uint32_t dropout_seed,
+                                    const unsigned long long* dropout_counter, int64_t row_offset,
+                                    float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
+                                    rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n_peer >= 0 && n_peer <= kMaxPeers && (n_peer == 0 || (peer_out_host && peer_ld % 4 == 0 && peer_row0 >= 0)),
+                 "transform_fwd_w: bad peer outputs (at most %d, ld %% 4 == 0)", kMaxPeers);
+  RGCN_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && K > 0 && K % 4 == 0 && d_out > 0 && d_out % 4 == 0, "transform_fwd_w: bad sizes");
+  RGCN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || (dropout_counter && relu)),
+                 "transform_fwd_w: dropout_p in [0, 1), fused dropout needs relu = 1 and a counter");
+  RGCN_CHECK_ARG(mode == 0 || mode == 1, "transform_fwd_w: mode must be 0 (fp32) or 1 (bf16)");
+  RGCN_CHECK_ARG(w_planes && ((uintptr_t)w_planes & 255) == 0, "transform_fwd_w: w_planes must come from rgcn_prepare_weights");
+  int rc = check_plane(A_hi, lda, "A_hi"); if (rc) return rc;
+  if (mode == 0) { rc = check_plane(A_lo, lda, "A_lo"); if (rc) return rc; }
+  RGCN_CHECK_ARG(out && ((uintptr_t)out & 15) == 0 && ldo % 4 == 0, "transform_fwd_w: out must be 16-byte aligned, ld %% 4 == 0");
+  RGCN_CHECK_ARG(!bias || d_out <= 1024, "transform_fwd_w: bias needs d_out <= 1024");
+  if (n_rows == 0) return RGCN_OK;
+  const Tiling t = tile_n(d_out, 32, KBN);
+  const __nv_bfloat16* bhi = (const __nv_bfloat16*)w_planes;
+  const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)w_planes + wplane_bytes(K, d_out));
+  GemmKParams p{};
+  p.M = n_rows; p.N = d_out; p.BN = t.BN; p.num_kb = round_up(K, BK) / BK;
+  p.bias = bias; p.relu = relu; p.out = out; p.ldo = ldo; p.row_offset = row_offset;
+  if (dropout_p > 0.f) {
+    const double th = (double)dropout_p * 65536.0 + 0.5;
+    p.drop_thresh = th >= 65535.0 ? 65535u : (th < 1.0 ? 1u : (uint32_t)th);
+    p.drop_scale = 1.f / (1.f - dropout_p);
+    p.drop_seed = dropout_seed; p.drop_ctr = dropout_counter;
+  }
+  p.n_peer = n_peer; p.peer_row0 = peer_row0; p.peer_ld = peer_ld;
+  for (int q = 0; q < n_peer; ++q) {
+    RGCN_CHECK_ARG(peer_out_host[q] && ((uintptr_t)peer_out_host[q] & 15) == 0, "transform_fwd_w: peer output %d is null or misaligned", q);
+    p.peer_out[q] = peer_out_host[q];
+  }
+  return launch_kmajor(p, A_hi, A_lo, lda, K, bhi, blo, K, d_out, wplane_ld(d_out), true, t.n_tiles, mode == 0, (cudaStream_t)stream);
+}
+
+extern "C" int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const void* w_planes,
+                                      int32_t K, int64_t n_rows, float* gA, int64_t ldga, int32_t mode, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && K > 0 && K % 4 == 0 && d_out > 0 && d_out % 4 == 0, "transform_dgrad_w: bad sizes");
+  RGCN_CHECK_ARG(mode == 0 || mode == 1, "transform_dgrad_w: mode must be 0 (fp32) or 1 (bf16)");
+  RGCN_CHECK_ARG(w_planes && ((uintptr_t)w_planes & 255) == 0, "transform_dgrad_w: w_planes must come from rgcn_prepare_weights");
+  int rc = check_plane(G_hi, ldg, "G_hi"); if (rc) return rc;
+  if (mode == 0) { rc = check_plane(G_lo, ldg, "G_lo"); if (rc) return rc; }
+  RGCN_CHECK_ARG(gA && ((uintptr_t)gA & 15) == 0 && ldga % 4 == 0, "transform_dgrad_w: gA must be 16-byte aligned, ld %% 4 == 0");
+  if (n_rows == 0) return RGCN_OK;
+  const Tiling t = tile_n(K, 32, KBN);
+  const __nv_bfloat16* bhi = (const __nv_bfloat16*)w_planes;
+  const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)w_planes + wplane_bytes(K, d_out));
+  GemmKParams p{};
+  p.M = n_rows; p.N = K; p.BN = t.BN; p.num_kb = round_up(d_out, BK) / BK;
+  p.out = gA; p.ldo = ldga;
+  return launch_kmajor(p, G_hi, G_lo, ldg, d_out, bhi, blo, K, d_out, wplane_ld(d_out), false, t.n_tiles, mode == 0, (cudaStream_t)stream);
 }

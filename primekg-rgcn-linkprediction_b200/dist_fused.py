@@ -89,7 +89,7 @@ class _FusedEncoderFn(torch.autograd.Function):
         ex.x.barrier()
         ops.p2p_push_rows(x0, ex.x_ptrs(0), row0, x0.size(1))
         ex.x.barrier()
-        saved, outs = [], []
+        saved, outs, wps = [], [], []
         for l in range(L):
             W, root, bias = params[3 * l: 3 * l + 3]
             R, d_in, d_out = W.shape
@@ -98,13 +98,15 @@ class _FusedEncoderFn(torch.autograd.Function):
             p_drop, seed, ctr = drops[l] if drops[l] is not None else (0.0, 0, None)
             last = l == L - 1
             # aggregate -> planes -> transform whose epilogue also stores every tile into all ranks' next buffer
-            out, A = ops.layer_fwd(graph, x_full, x_full[row0:row0 + n], W.reshape(K1, d_out), root, bias, not last, mode,
-                                   p_drop, seed, ctr, peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out)
+            out, A, wp = ops.layer_fwd(graph, x_full, x_full[row0:row0 + n], W.reshape(K1, d_out), root, bias, not last, mode,
+                                       p_drop, seed, ctr, peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out)
             ex.x.barrier()
             saved += [A[0], A[1], W, root]
+            wps.append(wp)
             outs.append(None if last else out)          # post-ReLU/dropout output = the backward mask
         ctx.ex, ctx.graph, ctx.mode, ctx.L = ex, graph, mode, L
         ctx.generation = ex.generation
+        ctx.w_planes = wps
         ctx.p_drops = [d[0] if d is not None else 0.0 for d in drops]
         ctx.d0 = x0.size(1)
         ctx.save_for_backward(*saved, *[o for o in outs if o is not None])
@@ -138,7 +140,7 @@ class _FusedEncoderFn(torch.autograd.Function):
             _, colsum = ops.p2p_reduce_split(ex.g_ptrs(l + 1), row0, d_out, n, d_out, dev, extra=extra, relu_mask=mask,
                                              mask_scale=1.0 / (1.0 - ctx.p_drops[l]), planes=G, colsum=True)
             Wf = W.reshape(K1, d_out)
-            gA = ops.transform_dgrad(G, d_out, Wf, root, mode)
+            gA = ops.transform_dgrad(G, d_out, Wf, root, mode, w_planes=ctx.w_planes[l])
             ops.aggregate_bwd(graph, gA, d_in, init=None, out=ex.g_view(l, d_in))
             extra = gA[:, K1:]
             gWf, groot, gb = ops.transform_wgrad((A_hi, A_lo), K1, K2, G, d_out, colsum, mode)

@@ -56,6 +56,9 @@ def hub_threshold() -> int:
     return t
 
 
+ORDER_CHUNK_ROWS = 8192      # rows per block of the chunk-wise row order (64 row tiles of the transform)
+
+
 class _Orientation:
     """One CSR orientation + its hub plan, and the ``rgcn_csr_t`` handed to the kernels."""
 
@@ -71,14 +74,24 @@ class _Orientation:
             raise ValueError("PRIMEKG_RGCN_ROW_ORDER must be auto, degree or none")
         # measured: +6-8 % on the L2-resident cfg2 aggregation, -3 % on cfg3 whose feature matrix does not fit the L2
         # (index order keeps neighbouring rows' gathers close) => by default only for graphs up to 64 k rows
+        self.order_chunk_rows = 0
         if self.n_rows > 1 and (order == "degree" or (order == "auto" and self.n_rows <= 65536)):
             # rows by decreasing edge count (stable): blocks get rows of similar length, the longest walks start first
             ends = rowptr[self.R::self.R]
-            deg = ends - rowptr[:-1:self.R][: ends.numel()]
-            self.row_order = torch.argsort(deg, descending=True, stable=True).to(torch.int32).contiguous()
+            deg = (ends - rowptr[:-1:self.R][: ends.numel()]).to(torch.int64)
+            if self.n_rows >= 2 * ORDER_CHUNK_ROWS:
+                # ... inside consecutive blocks of ORDER_CHUNK_ROWS rows, so that every block's rows stay a contiguous
+                # range: rgcn_layer_fwd walks block c + 1 while the transform of block c runs (csrc/layer.cu)
+                self.order_chunk_rows = ORDER_CHUNK_ROWS
+                block = torch.arange(self.n_rows, device=deg.device, dtype=torch.int64) // ORDER_CHUNK_ROWS
+                key = block * (int(deg.max()) + 1) + (int(deg.max()) - deg)
+                self.row_order = torch.argsort(key, stable=True).to(torch.int32).contiguous()
+            else:
+                self.row_order = torch.argsort(deg, descending=True, stable=True).to(torch.int32).contiguous()
         self.struct = _lib.CsrStruct(
             _ptr(rowptr), _ptr(idx), _ptr(w), self.n_rows, self.E, self.R, self.n_hubs, self.n_chunks, self.threshold,
-            _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr), _ptr(self.chunk_table), _ptr(self.row_order))
+            _ptr(self.hub_keys), _ptr(self.hub_chunk_ptr), _ptr(self.chunk_table), _ptr(self.row_order),
+            self.order_chunk_rows)
         self.ref = C.byref(self.struct)
         self.ptr = C.pointer(self.struct)          # for struct fields of type POINTER(rgcn_csr_t)
         self._ws = {}

@@ -60,7 +60,7 @@ class DrugDiseaseRGCN(nn.Module):
         """Identity of an eval-mode encoding besides the graph object: every parameter's storage + in-place version
         (optimizer steps, ``load_state_dict`` and ``.to()`` all change one of them).  Writes that bypass the version
         counter (``p.data`` tricks, raw-pointer or graph-replayed updates) are covered by the cache's LIFETIME instead:
-        it is dropped by every ``train()`` / ``eval()`` switch, ``.to()`` / ``_apply``, ``load_state_dict`` and
+        it is dropped by every ``train()`` <-> ``eval()`` switch, ``.to()`` / ``_apply``, ``load_state_dict`` and
         ``invalidate_eval_cache()``, so it only ever spans one evaluation phase."""
         ps = tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters())
         modes = tuple(c.mode for c in self._layers())
@@ -71,7 +71,8 @@ class DrugDiseaseRGCN(nn.Module):
         self._eval_cache = None
 
     def train(self, mode: bool = True):
-        self._eval_cache = None                  # also frees the [N, hidden] tensor for the training epochs
+        if bool(mode) != self.training:          # a real switch (the reference's predict / get_embeddings call eval() on
+            self._eval_cache = None              # every use): also frees the [N, hidden] tensor for the training epochs
         return super().train(mode)
 
     def _apply(self, fn, *args, **kwargs):

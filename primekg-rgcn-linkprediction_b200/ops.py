@@ -376,8 +376,47 @@ def transform_fwd(planes, K1: int, K2: int, W1: torch.Tensor, W2: Optional[torch
     return out
 
 
-def transform_dgrad(g_planes, d_out: int, W1: torch.Tensor, W2: Optional[torch.Tensor], mode: str) -> torch.Tensor:
-    """gA = G @ [W1 ; W2]^T  -> [n, K1 + K2]; G given as bf16 planes [n, d_out]."""
+def prepare_weights(W1: torch.Tensor, W2: Optional[torch.Tensor], mode: str, dropout_ctr: Optional[torch.Tensor] = None
+                    ) -> torch.Tensor:
+    """bf16 hi (, lo) planes of the row-major block [W1; W2] ([K1 + K2, d_out]) — ``rgcn_prepare_weights``; the buffer
+    serves ``transform_fwd(..., w_planes=)`` (MN-major operand) and ``transform_dgrad(..., w_planes=)`` (K-major)."""
+    lib = _lib.load()
+    W1 = _w2d(W1, "W1")
+    d_out = W1.size(-1)
+    K1 = W1.numel() // d_out
+    K2 = 0
+    if W2 is not None:
+        W2 = _w2d(W2, "W2")
+        K2 = W2.numel() // d_out
+    wp = torch.empty(weight_planes_bytes(K1 + K2, d_out), dtype=torch.uint8, device=W1.device)
+    _lib.check(lib.rgcn_prepare_weights(_ptr(W1), K1, _ptr(W2), K2, d_out, _mode_id(mode), _ptr(wp), _ptr(dropout_ctr),
+                                        _stream(W1.device)), "rgcn_prepare_weights")
+    return wp
+
+
+def transform_fwd_w(planes, K: int, w_planes: torch.Tensor, d_out: int, bias: Optional[torch.Tensor], relu: bool, mode: str,
+                    dropout_p: float = 0.0, dropout_seed: int = 0, dropout_ctr: Optional[torch.Tensor] = None,
+                    row_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = A @ W + bias (, ReLU (, dropout)) with the weights already converted (``prepare_weights``): the tcgen05 kernel
+    alone, B read MN-major.  ``row_offset``: global row of A's row 0 (row-chunked calls draw one consistent dropout mask)."""
+    lib = _lib.load()
+    hi, lo = planes
+    n = hi.size(0)
+    if bias is not None:
+        bias = bias.detach().contiguous()
+    if out is None:
+        out = torch.empty(n, d_out, dtype=torch.float32, device=hi.device)
+    _lib.check(lib.rgcn_transform_fwd_w(_ptr(hi), _ptr(lo), hi.stride(0), K, _ptr(w_planes), _ptr(bias), int(relu), n, d_out,
+                                        _ptr(out), out.stride(0), _mode_id(mode), float(dropout_p),
+                                        int(dropout_seed) & 0xFFFFFFFF, _ptr(dropout_ctr if dropout_p > 0 else None),
+                                        int(row_offset), None, 0, 0, 0, _stream(hi.device)), "rgcn_transform_fwd_w")
+    return out
+
+
+def transform_dgrad(g_planes, d_out: int, W1: torch.Tensor, W2: Optional[torch.Tensor], mode: str,
+                    w_planes: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gA = G @ [W1 ; W2]^T  -> [n, K1 + K2]; G given as bf16 planes [n, d_out].  ``w_planes``: the weights as converted
+    by ``prepare_weights`` / ``layer_fwd`` (skips the conversion kernel)."""
     lib = _lib.load()
     hi, lo = g_planes
     n = hi.size(0)
@@ -388,6 +427,10 @@ def transform_dgrad(g_planes, d_out: int, W1: torch.Tensor, W2: Optional[torch.T
         W2 = _w2d(W2, "W2")
         K2 = W2.numel() // d_out
     gA = torch.empty(n, K1 + K2, dtype=torch.float32, device=hi.device)
+    if w_planes is not None:
+        _lib.check(lib.rgcn_transform_dgrad_w(_ptr(hi), _ptr(lo), hi.stride(0), d_out, _ptr(w_planes), K1 + K2, n, _ptr(gA),
+                                              gA.stride(0), _mode_id(mode), _stream(hi.device)), "rgcn_transform_dgrad_w")
+        return gA
     nb = lib.rgcn_transform_workspace_bytes(n, K1 + K2, d_out)
     ws = _workspace(hi.device, nb)
     _lib.check(lib.rgcn_transform_dgrad(_ptr(hi), _ptr(lo), hi.stride(0), d_out, _ptr(W1), K1, _ptr(W2), K2, n,
@@ -418,6 +461,22 @@ def transform_wgrad(a_planes, K1: int, K2: int, g_planes, d_out: int, colsum_par
 
 # ---- one layer per foreign call ---------------------------------------------------------------------
 _WS_BYTES = {}
+_WP_BYTES = {}
+
+
+def prepared_weights() -> bool:
+    """Weights converted once per layer call and shared by forward and dgrad (``PRIMEKG_RGCN_PREPARED_WEIGHTS=0``: the
+    round-1 form, one conversion per GEMM)."""
+    import os
+    return os.environ.get("PRIMEKG_RGCN_PREPARED_WEIGHTS", "1") != "0"
+
+
+def weight_planes_bytes(K: int, d_out: int) -> int:
+    key = (int(K), int(d_out))
+    nb = _WP_BYTES.get(key)
+    if nb is None:
+        nb = _WP_BYTES[key] = int(_lib.load().rgcn_weight_planes_bytes(int(K), int(d_out)))
+    return nb
 
 
 def _gemm_workspace(device, n: int, K: int, d_out: int) -> torch.Tensor:
@@ -434,9 +493,13 @@ def _dp(t: Optional[torch.Tensor]):
 
 def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch.Tensor, root: torch.Tensor,
               bias: torch.Tensor, relu: bool, mode: str, dropout_p: float = 0.0, dropout_seed: int = 0,
-              dropout_ctr: Optional[torch.Tensor] = None, peer_out=None, peer_row0: int = 0, peer_ld: int = 0):
+              dropout_ctr: Optional[torch.Tensor] = None, peer_out=None, peer_row0: int = 0, peer_ld: int = 0,
+              pipeline: int = 0):
     """aggregate -> operand planes -> tensor-core transform of one layer in ONE C call (``rgcn_layer_fwd``).
-    Returns (out [n_dst, d_out], (A_hi, A_lo | None))."""
+    Returns (out [n_dst, d_out], (A_hi, A_lo | None), w_planes | None): ``w_planes`` = the layer's weights as bf16 planes,
+    converted once by the call; hand it to ``layer_bwd`` (its dgrad then skips the conversion).
+    ``pipeline``: 0 = the library decides whether the walk of row chunk c + 1 runs under the transform of chunk c (while
+    the stream is being captured, or from 200,000 rows), 1 = never, 2 = always."""
     lib = _lib.load()
     x_src = _f32c(x_src, "x")
     x_root = x_src if x_root is x_src else _f32c(x_root, "x_root")
@@ -457,20 +520,23 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
     aws = g.fwd.workspace(d_in)
     gws = _gemm_workspace(dev, g.n_dst, K, d_out)
     peers = _ptr_array(peer_out) if peer_out else None
+    # the layer's weights as bf16 planes, converted once by the call and kept for the backward's dgrad
+    wp = torch.empty(weight_planes_bytes(K, d_out), dtype=torch.uint8, device=dev) if prepared_weights() else None
     args = _lib.LayerFwdArgs(
         g.fwd.ptr, x_src.data_ptr(), x_src.stride(0), x_root.data_ptr(), x_root.stride(0), d_in, d_out, int(relu),
         _mode_id(mode), W2d.data_ptr(), root.data_ptr(), bias.data_ptr(), float(dropout_p), int(dropout_seed) & 0xFFFFFFFF,
         _dp(dropout_ctr) if dropout_p > 0 else None, A[0].data_ptr(), _dp(A[1]), A[0].stride(0), out.data_ptr(),
         out.stride(0), C.cast(peers, C.c_void_p) if peers is not None else None, len(peer_out) if peer_out else 0,
-        int(peer_row0), int(peer_ld), _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel())
+        int(peer_row0), int(peer_ld), _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel(),
+        _dp(wp), 0 if wp is None else wp.numel(), int(pipeline))
     _lib.check(lib.rgcn_layer_fwd(C.byref(args), _stream(dev)), "rgcn_layer_fwd")
-    return out, A
+    return out, A, wp
 
 
 def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], mask_scale: float, planes, W2d: torch.Tensor,
               root: torch.Tensor, d_in: int, mode: str, need_x: bool, add_root_term: bool, need_w: bool, need_b: bool,
               gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None, g_ready=None, next_mask=None,
-              slot: Optional[torch.Tensor] = None):
+              slot: Optional[torch.Tensor] = None, w_planes: Optional[torch.Tensor] = None):
     """split(gO, mask) -> dgrad -> transposed gather -> wgrad of one layer in ONE C call (``rgcn_layer_bwd``).
     Returns (g_x | None, gA | None, gW2d | None, g_root | None, g_bias | None); ``gA[:, R*d_in:]`` is the root-term
     gradient (already inside g_x when ``add_root_term``).
@@ -546,7 +612,7 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         _dp(rows), 0 if rows is None else rows.numel(), _dp(slot), _dp(Ac[0]), _dp(Ac[1]),
         0 if Ac[0] is None else Ac[0].stride(0),
         C.pointer(nxt_struct) if nxt_struct is not None else None, int(g_ready is not None),
-        0 if g_ready is None else colsum.size(0), int(slot_ready))
+        0 if g_ready is None else colsum.size(0), int(slot_ready), _dp(w_planes))
     _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
     if next_mask is not None:
         return gx, (None if sparse else gA), gW, groot, gb, nxt

@@ -64,7 +64,7 @@ def aggregate_bwd(g, gH, d, init=None):
 
 
 def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, dropout_seed=0, dropout_ctr=None,
-              peer_out=None, peer_row0=0, peer_ld=0):
+              peer_out=None, peer_row0=0, peer_ld=0, pipeline=0):
     assert not peer_out
     d_in = x_src.size(1)
     K1 = g.R * d_in
@@ -76,11 +76,11 @@ def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, drop
         # the fused ReLU + dropout epilogue: zero with probability p, the rest times 1 / (1 - p); the backward needs no
         # mask tensor (the output is zero exactly where ReLU or dropout killed the element)
         out = out * torch.bernoulli(torch.full_like(out, 1.0 - dropout_p)) / (1.0 - dropout_p)
-    return out, A
+    return out, A, None
 
 
 def layer_bwd(g, gO, relu_mask, mask_scale, planes, W2d, root, d_in, mode, need_x, add_root_term, need_w, need_b,
-              gx_out=None, rows=None, g_ready=None, next_mask=None, slot=None):
+              gx_out=None, rows=None, g_ready=None, next_mask=None, slot=None, w_planes=None):
     assert g_ready is None and next_mask is None
     d_out = gO.size(1)
     K1 = g.R * d_in

@@ -1050,7 +1050,7 @@ def test_layer_bwd_rows_equals_dense(pkg, name, d_in, d_out, mode):
     W = (torch.randn(R * d_in, d_out, generator=gen) / d_in ** 0.5).to(DEV)
     root = (torch.randn(d_in, d_out, generator=gen) / d_in ** 0.5).to(DEV)
     bias = torch.zeros(d_out, device=DEV)
-    _, A = ops.layer_fwd(g, x, x, W, root, bias, False, mode)
+    _, A, _wp = ops.layer_fwd(g, x, x, W, root, bias, False, mode)
     n_list = min(4096, N // 4)
     rows = torch.randint(0, N, (n_list,), generator=gen)
     rows[1::7] = rows[0]                                               # duplicates
@@ -1317,7 +1317,7 @@ def test_layer_bwd_rows_edge_cases(pkg, case):
     x = torch.randn(N, d_in, generator=gen).to(DEV)
     W = (torch.randn(R * d_in, d_out, generator=gen) / 8).to(DEV)
     root = (torch.randn(d_in, d_out, generator=gen) / 8).to(DEV)
-    _, A = ops.layer_fwd(g, x, x, W, root, torch.zeros(d_out, device=DEV), False, "fp32")
+    _, A, _wp = ops.layer_fwd(g, x, x, W, root, torch.zeros(d_out, device=DEV), False, "fp32")
     rows = {"single_row": torch.tensor([N // 2]), "all_duplicates": torch.full((300,), 7),
             "every_node": torch.randperm(N, generator=gen), "n_129": torch.randint(0, N, (129,), generator=gen),
             "isolated_rows": torch.tensor([4, 5, 7, 8, 4])}[case]
@@ -1506,3 +1506,54 @@ def test_graphed_step_host_io(pkg):
     torch.testing.assert_close(step.host_loss[0], g["loss"], rtol=1e-4, atol=1e-5)
     with pytest.raises(RuntimeError):
         pkg.GraphedTrainStep(m, ei, et, batch_size=b[0].numel()).replay_host()
+
+
+# ------------------------------------------------------------------------------------------------
+# pipelined layer forward: the walk of row chunk c + 1 under the transform of chunk c (csrc/layer.cu)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("d_in,d_out,relu", [(64, 256, True), (256, 256, False), (128, 96, True)])
+def test_pipelined_layer_forward_equals_sequential(pkg, mode, d_in, d_out, relu):
+    """Same kernels, same per-row arithmetic, two streams: bit-identical outputs and operand planes, on the
+    PrimeKG-shaped graph (hub rows, chunk-wise row order) and on a large uniform graph without a row order."""
+    from primekg_rgcn_linkprediction_b200 import ops, synth
+    for kg in (synth.primekg_subgraph(200_000, seed=3), synth.uniform_kg(70_000, 300_000, 5, seed=8)):
+        ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+        g = pkg.RelGraph.from_edges(ei, et, kg.num_nodes, kg.num_relations)
+        assert (g.fwd.row_order is None) or g.fwd.order_chunk_rows > 0
+        torch.manual_seed(5)
+        R = kg.num_relations
+        x = torch.randn(kg.num_nodes, d_in, device=DEV)
+        W = torch.randn(R * d_in, d_out, device=DEV) * 0.1
+        root = torch.randn(d_in, d_out, device=DEV) * 0.1
+        bias = torch.randn(d_out, device=DEV)
+        outs = []
+        for pipeline in (1, 2):
+            ctr = ops.dropout_counter(x.device)
+            drop = (0.5, 123, ctr) if relu else (0.0, 0, None)
+            out, A, wp = ops.layer_fwd(g, x, x, W, root, bias, relu, mode, *drop, pipeline=pipeline)
+            torch.cuda.synchronize()
+            outs.append((out, A[0], A[1], wp))
+        assert torch.equal(outs[0][0], outs[1][0])
+        assert torch.equal(outs[0][1], outs[1][1])
+        if mode == "fp32":
+            assert torch.equal(outs[0][2], outs[1][2])
+        assert torch.equal(outs[0][3], outs[1][3])
+        if relu:
+            assert 0.2 < float((outs[0][0] > 0).float().mean()) < 0.3          # ~half survive ReLU, half of those dropout
+
+
+def test_chunkwise_row_order_is_a_blockwise_permutation(pkg):
+    from primekg_rgcn_linkprediction_b200 import synth
+    from primekg_rgcn_linkprediction_b200.graph import ORDER_CHUNK_ROWS
+    kg = synth.primekg_subgraph(100_000, seed=2)
+    g = pkg.RelGraph.from_edges(kg.edge_index.to(DEV), kg.edge_type.to(DEV), kg.num_nodes, kg.num_relations)
+    for ori in (g.fwd, g.bwd):
+        assert ori.order_chunk_rows == ORDER_CHUNK_ROWS
+        order = ori.row_order.long()
+        assert torch.equal(torch.sort(order).values, torch.arange(kg.num_nodes, device=DEV))
+        pos = torch.arange(kg.num_nodes, device=DEV)
+        assert torch.equal(order // ORDER_CHUNK_ROWS, pos // ORDER_CHUNK_ROWS)      # every block keeps its own rows
+        deg = (ori.rowptr[kg.num_relations::kg.num_relations] - ori.rowptr[:-1:kg.num_relations]).long()
+        d = deg[order]
+        same_block = (pos[1:] // ORDER_CHUNK_ROWS) == (pos[:-1] // ORDER_CHUNK_ROWS)
+        assert torch.all(d[1:][same_block] <= d[:-1][same_block])                   # decreasing edge count inside a block

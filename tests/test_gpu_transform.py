@@ -118,3 +118,57 @@ def test_transform_wgrad(ops, shape, mode, masked):
     assert _err(gb, g.sum(0)) < 1e-5, (shape, mode, "gbias", _err(gb, g.sum(0)))
     again = ops.transform_wgrad(A, K1, K2, G, N, part, mode)
     assert torch.equal(gW1, again[0]) and torch.equal(gb, again[2])          # deterministic split-K
+
+
+# ---- weights converted once per layer call (rgcn_prepare_weights): forward reads them MN-major, dgrad K-major ----------
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_prepared_weights_forward_and_dgrad(ops, shape, mode):
+    """Same operands, same K order, same three products: the MN-major-B kernel must reproduce the K-major-B kernel's
+    bits, whole and in row chunks (the chunked layer forward), and match the fp64 product."""
+    n, K1, K2, N = shape
+    torch.manual_seed(11)
+    mats = [torch.randn(n, K1, device=DEV)] + ([torch.randn(n, K2, device=DEV)] if K2 else [])
+    W1 = torch.randn(K1, N, device=DEV) * 0.3
+    W2 = torch.randn(K2, N, device=DEV) * 0.3 if K2 else None
+    bias = torch.randn(N, device=DEV)
+    P, _ = _planes(ops, mats, mode)
+    old = ops.transform_fwd(P, K1, K2, W1, W2, bias, True, mode)
+    wp = ops.prepare_weights(W1, W2, mode)
+    new = ops.transform_fwd_w(P, K1 + K2, wp, N, bias, True, mode)
+    assert torch.equal(new, old)
+    want = torch.relu(torch.cat(mats, 1).double() @ torch.cat([W1] + ([W2] if K2 else []), 0).double() + bias.double())
+    assert _err(new, want) < TOL[mode]
+    # row chunks into one output buffer
+    out = torch.full_like(old, float("nan"))
+    step = 128 * max(1, (n // 3) // 128) if n > 256 else n
+    for r0 in range(0, n, step):
+        r1 = min(r0 + step, n)
+        Pc = (P[0][r0:r1], None if P[1] is None else P[1][r0:r1])
+        ops.transform_fwd_w(Pc, K1 + K2, wp, N, bias, True, mode, row_offset=r0, out=out[r0:r1])
+    assert torch.equal(out, old)
+    # dgrad through the same planes
+    G = torch.randn(n, N, device=DEV)
+    Gp, _ = _planes(ops, [G], mode)
+    g_old = ops.transform_dgrad(Gp, N, W1, W2, mode)
+    g_new = ops.transform_dgrad(Gp, N, W1, W2, mode, w_planes=wp)
+    assert torch.equal(g_new, g_old)
+
+
+def test_chunked_dropout_mask_is_one_consistent_mask(ops):
+    """Row-chunked calls hash the GLOBAL element index: the chunks' masks are the slices of the whole call's mask."""
+    torch.manual_seed(2)
+    n, K, N = 1024, 64, 128
+    A = torch.zeros(n, K, device=DEV)
+    P, _ = _planes(ops, [A], "bf16")
+    W = torch.zeros(K, N, device=DEV)
+    bias = torch.ones(N, device=DEV)
+    ctr = ops.dropout_counter(A.device)
+    wp = ops.prepare_weights(W, None, "bf16")
+    whole = ops.transform_fwd_w(P, K, wp, N, bias, True, "bf16", 0.5, 77, ctr)
+    parts = torch.empty_like(whole)
+    for r0 in range(0, n, 256):
+        ops.transform_fwd_w((P[0][r0:r0 + 256], None), K, wp, N, bias, True, "bf16", 0.5, 77, ctr, row_offset=r0,
+                            out=parts[r0:r0 + 256])
+    assert torch.equal(parts, whole)
+    assert 0.45 < float((whole > 0).float().mean()) < 0.55
