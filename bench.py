@@ -215,6 +215,8 @@ def roofline_block(pkg, kg, ei, et, flush, clocks, iters):
                            "alone; best of the variants in l2_probe)",
             "traffic": dram_bytes, "traffic_source": ncu.get("source"),
             "algorithmic_bytes_per_launch": fwd_b, "avg_launch_ms": round(kt["aggregate_fwd"], 5),
+            "output_bytes_per_launch": kg.num_nodes * (kg.num_relations + 0) * d2 * 4,
+            "frac_incl_output_write": round((fwd_b + kg.num_nodes * kg.num_relations * d2 * 4) / (kt["aggregate_fwd"] * 1e-3) / 1e9 / l2_peak, 4),
             "rates": {"gathered_algorithmic_gbs": round(achieved, 1), "l2_probe_peak_gbs": round(l2_peak, 1),
                       "lts_t_bytes_gbs_ncu": (None if not ncu.get("lts_t_bytes") else
                                               round(ncu["lts_t_bytes"] / (ncu["ncu_time_us"] * 1e-6) / 1e9, 1)),

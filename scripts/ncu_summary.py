@@ -23,7 +23,8 @@ KEEP = {
     "launch__registers_per_thread": "regs",
     "launch__grid_size": "grid",
     "smsp__inst_executed.sum": "inst_executed",
-    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active": "tensor_pipe_active_pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_active_pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_active_pct_of_elapsed",
 }
 
 rows = list(csv.reader(open(sys.argv[1])))
