@@ -626,12 +626,33 @@ def run_ours(args, rank, world, local_rank):
     # ---- the same step captured once into a CUDA graph (GraphedTrainStep) ----
     # N > 1: the backward kernels write every parameter gradient into ONE flat buffer (ops.GradArena), so the replicas
     # exchange a single tensor
-    gstep = pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel(), flat_grads="arena" if world > 1 else False)
+    # and they exchange it with OUR two-shot all-reduce over peer-mapped memory, captured as the last kernels of the step's
+    # CUDA graph (peer.PeerAllReduce); RGCN_DP_ALLREDUCE=nccl keeps the round-1 form (one NCCL all-reduce after the replay)
+    peer_ar = world > 1 and os.environ.get("RGCN_DP_ALLREDUCE", "peer") == "peer"
+    dp_exchange = "none"
+    if world > 1:
+        ok = torch.ones(1, device=dev)
+        if peer_ar:
+            try:
+                from primekg_rgcn_linkprediction_b200.peer import PeerBuffer
+                PeerBuffer(4096, dev)
+            except Exception:
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            peer_ar = bool(ok.item() > 0)
+        dp_exchange = ("two-shot all-reduce by our kernels over peer-mapped memory, inside the captured graph" if peer_ar else
+                       "one NCCL all-reduce of the flat gradient buffer after the graph replay")
+
+    def make_step(**kw):
+        return pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel(), flat_grads="arena" if world > 1 else False,
+                                    allreduce="peer" if peer_ar else None, **kw)
+
+    gstep = make_step()
     gstep.load_batch(*d_batch)
     flat_holder = [gstep.flat_grad]
 
     def allreduce_graphed():
-        if world > 1:
+        if world > 1 and not peer_ar:
             if flat_holder[0] is not None:
                 dist.all_reduce(flat_holder[0], op=dist.ReduceOp.AVG)   # NCCL averages in the reduction: no scaling pass
                 return
@@ -664,8 +685,7 @@ def run_ours(args, rank, world, local_rank):
     h2d_packed = packed.numel() * packed.element_size()
     for p in params:
         p.grad = None
-    ghost = pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel(), host_io=True,
-                                 flat_grads="arena" if world > 1 else False)
+    ghost = make_step(host_io=True)
     ghost.host_batch.copy_(packed)
     flat_value = flat_holder[0]
     flat_holder[0] = ghost.flat_grad
@@ -692,8 +712,7 @@ def run_ours(args, rank, world, local_rank):
             del gstep
             for p in params:
                 p.grad = None
-            gdense = pkg.GraphedTrainStep(model, ei, et, batch_size=d_batch[0].numel(),
-                                          flat_grads="arena" if world > 1 else False)
+            gdense = make_step()
             gdense.load_batch(*d_batch)
             flat_holder[0] = gdense.flat_grad
             for _ in range(3):
@@ -744,7 +763,7 @@ def run_ours(args, rank, world, local_rank):
                      "bits; gathers, means, loss in f32)" if args.mode == "fp32" else "bf16-transform / f32-accumulate"),
            "data": "synthetic", "parity": PARITY,
            "config": {"workload": WORKLOAD, "mode": args.mode, "l2": "flushed between steps (512 MiB write)",
-                      "parallelism": "single GPU" if world == 1 else f"dp{world} replicas, parameter gradients written into one flat buffer and all-reduced in one NCCL call",
+                      "parallelism": "single GPU" if world == 1 else f"dp{world} replicas, parameter gradients written into one flat buffer; exchange: {dp_exchange}",
                       "timing": "CUDA events per step on the launching stream, max over ranks",
                       "step": "one CUDA-graph replay of forward + BCE loss + backward (GraphedTrainStep)",
                       "last_layer_backward": ("dense over all N rows (PRIMEKG_RGCN_SPARSE_BWD=0)" if sparse_env == "0" else

@@ -293,8 +293,8 @@ typedef struct rgcn_layer_fwd_args {
    * it ONCE (rgcn_prepare_weights), reads it as the MN-major operand of the transform, and rgcn_layer_bwd reads the same
    * buffer for its dgrad.  With it the call may also PIPELINE: the walk of row chunk c + 1 runs on `stream` while the
    * transform of chunk c (and, in the partitioned path, its peer stores = the all-gather) runs on an internal side
-   * stream, joined before the call returns.  pipeline: 0 = the library decides (while the stream is being captured, or
-   * from 200,000 rows; RGCN_PIPELINE=0/1 overrides), 1 = never, 2 = always. */
+   * stream, joined before the call returns.  pipeline: 0 = the library decides (from 200,000 rows, where every chunk's
+   * transform is many waves long; RGCN_PIPELINE=0/1 overrides), 1 = never, 2 = always. */
   void* w_planes; size_t w_planes_bytes; int32_t pipeline;
 } rgcn_layer_fwd_args;
 
@@ -385,6 +385,20 @@ int rgcn_p2p_reduce_split(const float* const* part_host, int32_t n_part, int64_t
                           int64_t rows, int32_t cols, float* out, int64_t ldo, void* hi, void* lo, int64_t ldp,
                           float* colsum_partial, rgcn_stream_t stream);
 
+/* All-reduce of one flat fp32 buffer over the n GPUs (data-parallel replicas of graphs that fit one GPU exchange their
+ * parameter gradients with it; no reference counterpart — reference README.md:624-627 lists multi-GPU as future work).
+ * Two-shot over peer-mapped memory, CUDA-graph capturable, deterministic: rank r sums slice r of every rank's `in` in rank
+ * order, scales it and stores it into slice r of EVERY rank's `out` (in and out must be different buffers); arrival / done
+ * flags are monotone epochs kept by a device-side counter that the call itself advances.
+ *   in_host / out_host / flags_host : host arrays of n device pointers (peer-mapped; entry q = rank q); every flag block
+ *                                     is rgcn_p2p_allreduce_flag_bytes() bytes, ZEROED once before first use
+ *   epoch_counter : local device uint32, zeroed once; status (nullable): bit 1 set when a peer never arrived (the waits
+ *                   give up after a few seconds instead of hanging the GPU). */
+size_t rgcn_p2p_allreduce_flag_bytes(void);
+int rgcn_p2p_allreduce(const float* const* in_host, float* const* out_host, unsigned int* const* flags_host,
+                       int32_t n_ranks, int32_t rank, int64_t n_floats, float scale, unsigned int* epoch_counter,
+                       int32_t* status, rgcn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * DistMult decoder.  Replaces node_embeddings[head], [tail] (src/models/rgcn.py:325-326) +
  * LinkPredictor.forward (src/models/rgcn.py:207-211) with one gather-and-score kernel:
@@ -462,10 +476,11 @@ int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, con
  *                        (fp32 atomics on repeated rows: the sum order differs from run to run.)
  *   rgcn_link_loss_bwd_rows : the DETERMINISTIC form of the same backward, and the one the modules use.  No floating-point
  *                        atomics: slot[i] (int32 [n_nodes], out) = first position of node i in rows (int64 [2 n_pairs],
- *                        out: the heads then the tails) or rgcn_rows_compact_size(2 n_pairs) when nobody lists it; the
- *                        owner position's warp adds all contributions to the node in ascending position order and
- *                        every row of g_emb [n_nodes, d] is written exactly once (no pre-zeroing).  g_rel_table =
- *                        fixed-order sum of per-32-pair partials (workspace: rgcn_link_bwd_rows_workspace_bytes).
+ *                        out: the heads then the tails) or rgcn_rows_compact_size(2 n_pairs) when nobody lists it; every
+ *                        position's contribution is computed in parallel, then the owner position's warp adds the
+ *                        contributions to its node in ascending position order and every row of g_emb [n_nodes, d] is
+ *                        written exactly once (no pre-zeroing).  g_rel_table = fixed-order sum of per-32-pair partials.
+ *                        workspace (always needed, 16-byte aligned): rgcn_link_bwd_rows_workspace_bytes.
  *                        slot / rows are exactly what rgcn_layer_bwd's row-sparse form wants (slot_ready = 1).
  *   Index range: with n_nodes > 0 a pair whose head / tail is outside [0, n_nodes) or whose relation is outside
  *                        [0, n_rel) is skipped — NaN score and loss, no gradient — and bit 0 of *status (nullable) is

@@ -101,6 +101,8 @@ PROTOTYPES = {
     "rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), p]),
     "rgcn_p2p_push_rows": (C.c_int, [p, i64, i64, i32, p, i32, i64, i64, p]),
     "rgcn_p2p_reduce_split": (C.c_int, [p, i32, i64, i64, p, i64, p, i64, C.c_float, i64, i32, p, i64, p, p, i64, p, p]),
+    "rgcn_p2p_allreduce_flag_bytes": (sz, []),
+    "rgcn_p2p_allreduce": (C.c_int, [p, p, p, i32, i32, i64, C.c_float, p, p, p]),
     "rgcn_transform_dgrad": (C.c_int, [p, p, i64, i32, p, i32, p, i32, i64, p, i64, i32, p, sz, p]),
     "rgcn_transform_wgrad": (C.c_int, [p, p, i64, i32, i32, p, p, i64, i32, i64, p, i32, p, p, p, i32, p, sz, p]),
     "rgcn_distmult_fwd": (C.c_int, [p, i64, p, i64, p, p, p, p, p, p, i64, i32, p, p]),

@@ -341,40 +341,29 @@ __global__ void __launch_bounds__(256) link_loss_bwd_kernel(const LinkLossParams
 
 // ---- deterministic backward of the fused decoder (no atomics on floating-point data) --------------------------------
 // The 2 n gathered rows (positions 0 .. n-1 = the heads, n .. 2n-1 = the tails) repeat: a hub gene is the head or tail
-// of many pairs of a batch.  Instead of fp32 atomics (whose order differs from run to run) every listed node gets ONE
-// owner — the first position that lists it, slot[node], found with an integer atomicMin — and the owner's warp adds
-// the contributions of all positions listing the node in ascending position order.  Every row of the dense [N, d]
-// gradient is written exactly once (rows nobody lists are zero-filled by the same launch), so the buffer needs no
-// memset, and `slot` / `rows` are handed to the last encoder layer's row-sparse backward (csrc/rowsparse.cu) as they are.
-// The relation-table gradient is reduced the same way: per-chunk partials in pair order, then a fixed-order column sum.
-__global__ void __launch_bounds__(256) link_rows_kernel(const LinkLossParams q, int64_t* __restrict__ rows,
-                                                        int32_t* __restrict__ slot) {
-  pdl_enter();
-  const int64_t pos = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (pos >= 2 * q.n_pairs) return;
-  const int64_t p = pos < q.n_pairs ? pos : pos - q.n_pairs;
-  const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
-  if (!pair_ok(q, hi, ti, ri)) {
-    rows[pos] = 0;                                   // a valid row id that this position never owns
-    if (q.status) atomicOr(q.status, 1);
-    return;
-  }
-  const int64_t node = pos < q.n_pairs ? hi : ti;
-  rows[pos] = node;
-  atomicMin(slot + node, (int32_t)pos);
-}
-
+// of dozens of pairs of one batch.  Instead of fp32 atomics (whose order differs from run to run):
+//   1. link_contrib_kernel, one warp per POSITION (fully parallel): C[q] = the contribution of position q to its node's
+//      gradient row, T[p] = the contribution of pair p to its relation's row; the same launch writes rows[q] and finds
+//      every listed node's OWNER — its first position, slot[node] — with an integer atomicMin;
+//   2. link_gather_kernel: the owner's warp collects the positions that list its node (a scan of the position list in
+//      shared memory), then adds their C rows in ascending position order, eight loads in flight; rows nobody lists are
+//      zero-filled by other blocks of the same launch — every row of the dense [N, d] gradient is written exactly once, no
+//      memset; further blocks add T rows per relation over 32-pair chunks in pair order (partials), which
+//   3. rgcn_reduce_partials sums in a fixed order.
+// slot / rows are handed to the last encoder layer's row-sparse backward (csrc/rowsparse.cu) as they are.
 struct LinkBwdRows {
   const float* g_loss; const float* g_score;
   float* g_emb; int64_t ld_g; int64_t n_rows;       // [n_rows, d]
-  const int32_t* slot; const int64_t* rows; int32_t unlisted;
+  int32_t* slot; int64_t* rows; int32_t unlisted;
+  float* C;                                         // [2 n, d] position contributions
+  float* T;                                         // [n, d] pair contributions to the relation table, nullable
   float* tab_partial;                               // [n_tab_blocks, n_rel * d], nullable
   int32_t n_owner_blocks, n_zero_blocks, n_tab_blocks;
   int32_t rows_in_smem;                             // the launch has 2 n ints of dynamic shared memory for the position list
 };
 constexpr int kLinkZeroRows = 64;                    // rows per zero-fill block
-constexpr int kLinkTabPairs = 32;
-constexpr int kLinkList = 64;                       // positions of one node collected before they are added                    // pairs per relation-table partial
+constexpr int kLinkTabPairs = 32;                    // pairs per relation-table partial
+constexpr int kLinkList = 64;                        // positions of one node collected before they are added
 
 __device__ __forceinline__ float link_pair_grad(const LinkLossParams& q, const LinkBwdRows& b, int64_t p) {
   if (b.g_score) return b.g_score[p];
@@ -382,19 +371,63 @@ __device__ __forceinline__ float link_pair_grad(const LinkLossParams& q, const L
   return (*b.g_loss) * (1.f / (1.f + expf(-s)) - q.labels[p]) / (float)q.n_pairs;
 }
 
-__global__ void __launch_bounds__(256, 2) link_bwd_rows_kernel(const LinkLossParams q, const LinkBwdRows b) {
+__global__ void __launch_bounds__(256) link_contrib_kernel(const LinkLossParams q, const LinkBwdRows b) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int nv = q.d >> 2;
+  const int64_t n = q.n_pairs;
+  const int64_t pos = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pos >= 2 * n) return;
+  const bool is_head = pos < n;
+  const int64_t p = is_head ? pos : pos - n;
+  const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
+  const bool ok = pair_ok(q, hi, ti, ri);
+  if (lane == 0) {
+    b.rows[pos] = ok ? (is_head ? hi : ti) : 0;      // an invalid pair parks on row 0, which it never owns
+    if (ok) atomicMin(b.slot + (is_head ? hi : ti), (int32_t)pos);
+    else if (q.status) atomicOr(q.status, 1);
+  }
+  float* __restrict__ crow = b.C + pos * q.d;
+  float* __restrict__ trow = (b.T && is_head) ? b.T + p * q.d : nullptr;
+  if (!ok) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int vi = lane; vi < nv; vi += 32) {
+      *reinterpret_cast<float4*>(crow + vi * 4) = z;
+      if (trow) *reinterpret_cast<float4*>(trow + vi * 4) = z;
+    }
+    return;
+  }
+  const unsigned long long c = q.drop_thresh ? *q.state : 0ull;
+  const uint32_t key = pcg32(q.seed ^ (uint32_t)c) + (uint32_t)(c >> 32) * 0x9E3779B9u;
+  const float g = link_pair_grad(q, b, p);
+  const float* __restrict__ h = q.emb + hi * q.ld;
+  const float* __restrict__ t = q.emb + ti * q.ld;
+  const float* __restrict__ r = q.rel_table + ri * q.d;
+  for (int vi = lane; vi < nv; vi += 32) {
+    const float4 a = ldg4(h + vi * 4), cc = ldg4(t + vi * 4);
+    float4 w = ldg4(r + vi * 4);
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (q.drop_thresh) {
+      m = rel_drop4(key, p, q.d, vi, q.drop_thresh, q.drop_scale);
+      w.x *= m.x; w.y *= m.y; w.z *= m.z; w.w *= m.w;
+    }
+    const float4 o = is_head ? cc : a;               // the partner row
+    *reinterpret_cast<float4*>(crow + vi * 4) = make_float4(g * w.x * o.x, g * w.y * o.y, g * w.z * o.z, g * w.w * o.w);
+    if (trow)
+      *reinterpret_cast<float4*>(trow + vi * 4) =
+          make_float4(g * a.x * cc.x * m.x, g * a.y * cc.y * m.y, g * a.z * cc.z * m.z, g * a.w * cc.w * m.w);
+  }
+}
+
+__global__ void __launch_bounds__(256) link_gather_kernel(const LinkLossParams q, const LinkBwdRows b) {
   pdl_enter();
   extern __shared__ int s_rows[];                    // [2 n] node of every position (owner blocks, when it fits)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = q.d >> 2;
   const int64_t n = q.n_pairs, n2 = 2 * q.n_pairs;
-  const unsigned long long c = q.drop_thresh ? *q.state : 0ull;
-  const uint32_t key = pcg32(q.seed ^ (uint32_t)c) + (uint32_t)(c >> 32) * 0x9E3779B9u;
   int blk = blockIdx.x;
   if (blk < b.n_owner_blocks) {
     // ---- one warp per position; only the node's first position (its owner) works ----
-    // the owner scans the position list for its node: from shared memory (one coalesced copy per block) — a scan from
-    // global memory is a chain of 2 n / 32 exposed load latencies per warp (measured: 50 us for n = 2,048)
     if (b.rows_in_smem) {
       for (int64_t i = threadIdx.x; i < n2; i += 256) s_rows[i] = (int)b.rows[i];
       __syncthreads();
@@ -403,75 +436,27 @@ __global__ void __launch_bounds__(256, 2) link_bwd_rows_kernel(const LinkLossPar
     if (pos >= n2) return;
     const int64_t v = b.rows[pos];
     if (__ldg(b.slot + v) != (int32_t)pos) return;
-    // A hub gene heads or tails dozens of pairs of one batch: adding them one after the other would be a chain of
-    // dependent load latencies (pair indices -> partner row).  So: (1) scan, collecting the positions that list this node
-    // in ascending order into a per-warp list; (2) one lane per listed position fetches the pair's indices and its
-    // score gradient — all at once; (3) the partner rows are loaded four ahead and added strictly in list order.
     __shared__ int s_list[8][kLinkList];
     int* list = s_list[warp];
     for (int v0 = 0; v0 < nv; v0 += 64) {            // column passes of two 128-bit vectors per lane
       const int vi0 = v0 + lane, vi1 = v0 + 32 + lane;
       const bool on0 = vi0 < nv, on1 = vi1 < nv;
+      const int c0 = on0 ? vi0 * 4 : 0, c1 = on1 ? vi1 * 4 : 0;
       float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
       auto flush = [&](int count) {
         __syncwarp();
-        for (int e0 = 0; e0 < count; e0 += 32) {
-          const int e = e0 + lane;
-          int m_other = 0, m_rel = 0, m_pair = 0;
-          float m_g = 0.f;                           // 0 for an invalid pair or a lane past the list: contributes exact zeros
-          if (e < count) {
-            const int64_t qq = list[e];
-            const bool is_head = qq < n;
-            const int64_t p = is_head ? qq : qq - n;
-            const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
-            if (pair_ok(q, hi, ti, ri)) {            // (an invalid pair parks its positions on row 0)
-              m_other = (int)(is_head ? ti : hi); m_rel = (int)ri; m_pair = (int)p;
-              m_g = link_pair_grad(q, b, p);
-            }
+        for (int j = 0; j < count; j += 8) {         // eight rows in flight, added strictly in list (= position) order
+          float4 x0[8], x1[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int e = min(j + u, count - 1);
+            const float* __restrict__ row = b.C + (int64_t)list[e] * q.d;
+            x0[u] = *reinterpret_cast<const float4*>(row + c0);
+            x1[u] = *reinterpret_cast<const float4*>(row + c1);
           }
-          const int nb = min(32, count - e0);
-          for (int j = 0; j < nb; j += 4) {
-            float4 o0[4], w0[4], o1[4], w1[4];
-            float g[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int src = min(j + u, 31);
-              const int oth = __shfl_sync(0xffffffffu, m_other, src);
-              const int ri = __shfl_sync(0xffffffffu, m_rel, src);
-              const int pr = __shfl_sync(0xffffffffu, m_pair, src);
-              g[u] = (j + u < nb) ? __shfl_sync(0xffffffffu, m_g, src) : 0.f;
-              const float* __restrict__ other = q.emb + (int64_t)oth * q.ld;
-              const float* __restrict__ r = q.rel_table + (int64_t)ri * q.d;
-              if (on0) {
-                o0[u] = ldg4(other + vi0 * 4);
-                w0[u] = ldg4(r + vi0 * 4);
-                if (q.drop_thresh) {
-                  const float4 mk = rel_drop4(key, pr, q.d, vi0, q.drop_thresh, q.drop_scale);
-                  w0[u].x *= mk.x; w0[u].y *= mk.y; w0[u].z *= mk.z; w0[u].w *= mk.w;
-                }
-              }
-              if (on1) {
-                o1[u] = ldg4(other + vi1 * 4);
-                w1[u] = ldg4(r + vi1 * 4);
-                if (q.drop_thresh) {
-                  const float4 mk = rel_drop4(key, pr, q.d, vi1, q.drop_thresh, q.drop_scale);
-                  w1[u].x *= mk.x; w1[u].y *= mk.y; w1[u].z *= mk.z; w1[u].w *= mk.w;
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {            // list order = ascending position: the order of the sum is fixed
-              if (j + u < nb) {
-                if (on0) {
-                  acc0.x += g[u] * w0[u].x * o0[u].x; acc0.y += g[u] * w0[u].y * o0[u].y;
-                  acc0.z += g[u] * w0[u].z * o0[u].z; acc0.w += g[u] * w0[u].w * o0[u].w;
-                }
-                if (on1) {
-                  acc1.x += g[u] * w1[u].x * o1[u].x; acc1.y += g[u] * w1[u].y * o1[u].y;
-                  acc1.z += g[u] * w1[u].z * o1[u].z; acc1.w += g[u] * w1[u].w * o1[u].w;
-                }
-              }
-            }
+          for (int u = 0; u < 8; ++u) {
+            if (j + u < count) { add4(acc0, x0[u]); add4(acc1, x1[u]); }
           }
         }
         __syncwarp();
@@ -489,8 +474,8 @@ __global__ void __launch_bounds__(256, 2) link_bwd_rows_kernel(const LinkLossPar
         cnt += k;
       }
       flush(cnt);
-      if (on0) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + vi0 * 4) = acc0;
-      if (on1) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + vi1 * 4) = acc1;
+      if (on0) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + c0) = acc0;
+      if (on1) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + c1) = acc1;
     }
     return;
   }
@@ -506,36 +491,34 @@ __global__ void __launch_bounds__(256, 2) link_bwd_rows_kernel(const LinkLossPar
     return;
   }
   blk -= b.n_zero_blocks;
-  // ---- relation-table gradient: partial of kLinkTabPairs consecutive pairs, summed in pair order ----
-  __shared__ float s_g[kLinkTabPairs];
+  // ---- relation-table gradient: partial of kLinkTabPairs consecutive pairs, their T rows added in pair order ----
   __shared__ int s_r[kLinkTabPairs];
-  __shared__ long long s_h[kLinkTabPairs], s_t[kLinkTabPairs];
   const int64_t p0 = (int64_t)blk * kLinkTabPairs;
   if (threadIdx.x < kLinkTabPairs) {
     const int64_t p = p0 + threadIdx.x;
     int r = -1;
-    float g = 0.f;
-    long long hi = 0, ti = 0;
     if (p < n) {
-      hi = q.head[p]; ti = q.tail[p];
-      const int64_t ri = q.rel[p];
-      if (pair_ok(q, hi, ti, ri)) { r = (int)ri; g = link_pair_grad(q, b, p); }
+      const int64_t hi = q.head[p], ti = q.tail[p], ri = q.rel[p];
+      if (pair_ok(q, hi, ti, ri)) r = (int)ri;
     }
-    s_g[threadIdx.x] = g; s_r[threadIdx.x] = r; s_h[threadIdx.x] = hi; s_t[threadIdx.x] = ti;
+    s_r[threadIdx.x] = r;
   }
   __syncthreads();
   float* __restrict__ part = b.tab_partial + (size_t)blk * q.n_rel * q.d;
+  const int np = (int)min((int64_t)kLinkTabPairs, n - p0);
   for (int o = threadIdx.x; o < q.n_rel * nv; o += 256) {
     const int r = o / nv, vi = o % nv;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = 0; k < kLinkTabPairs; ++k) {
-      if (s_r[k] != r) continue;
-      const float4 a = ldg4(q.emb + s_h[k] * q.ld + vi * 4), cc = ldg4(q.emb + s_t[k] * q.ld + vi * 4);
-      float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (q.drop_thresh) mk = rel_drop4(key, p0 + k, q.d, vi, q.drop_thresh, q.drop_scale);
-      const float g = s_g[k];
-      acc.x += g * a.x * cc.x * mk.x; acc.y += g * a.y * cc.y * mk.y;
-      acc.z += g * a.z * cc.z * mk.z; acc.w += g * a.w * cc.w * mk.w;
+    for (int k0 = 0; k0 < np; k0 += 8) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = min(k0 + u, np - 1);
+        x[u] = *reinterpret_cast<const float4*>(b.T + (p0 + k) * q.d + vi * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k0 + u < np && s_r[k0 + u] == r) add4(acc, x[u]);
     }
     *reinterpret_cast<float4*>(part + (size_t)r * q.d + vi * 4) = acc;
   }
@@ -716,10 +699,13 @@ __global__ void __launch_bounds__(256) link_slot_fill_kernel(int32_t* __restrict
 }
 }
 
+static size_t link_ws_C(int64_t n_pairs, int32_t d) { return align_up((size_t)(2 * n_pairs) * d * sizeof(float), 256); }
+static size_t link_ws_T(int64_t n_pairs, int32_t d) { return align_up((size_t)n_pairs * d * sizeof(float), 256); }
+
 extern "C" size_t rgcn_link_bwd_rows_workspace_bytes(int64_t n_pairs, int32_t n_rel, int32_t d) {
   if (n_pairs <= 0 || n_rel <= 0 || d <= 0) return 256;
   const size_t chunks = (size_t)((n_pairs + kLinkTabPairs - 1) / kLinkTabPairs);
-  return align_up(chunks * (size_t)n_rel * (size_t)d * sizeof(float), 256) + 256;
+  return link_ws_C(n_pairs, d) + link_ws_T(n_pairs, d) + align_up(chunks * (size_t)n_rel * (size_t)d * sizeof(float), 256) + 256;
 }
 
 extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64_t* head, const int64_t* tail,
@@ -737,23 +723,25 @@ extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64
   RGCN_CHECK_ARG(g_score || (score && g_loss && labels), "link_loss_bwd_rows: need g_score, or score + labels + g_loss");
   RGCN_CHECK_ARG(dropout_p == 0.f || state, "link_loss_bwd_rows: dropout needs the state the forward wrote");
   RGCN_CHECK_ARG(!g_rel_table || ((uintptr_t)g_rel_table & 15) == 0, "link_loss_bwd_rows: g_rel_table misaligned");
-  if (g_rel_table && (!workspace || workspace_bytes < rgcn_link_bwd_rows_workspace_bytes(n_pairs, n_rel, d))) {
-    set_error("link_loss_bwd_rows: workspace too small"); return RGCN_EWORKSPACE;
+  if (!workspace || ((uintptr_t)workspace & 15) != 0 || workspace_bytes < rgcn_link_bwd_rows_workspace_bytes(n_pairs, n_rel, d)) {
+    set_error("link_loss_bwd_rows: workspace missing, misaligned or too small"); return RGCN_EWORKSPACE;
   }
   q.state = const_cast<unsigned long long*>(state); q.score = const_cast<float*>(score);
   cudaStream_t st = (cudaStream_t)stream;
   const int32_t m_c = (int32_t)rgcn_rows_compact_size(2 * n_pairs);
   RGCN_CUDA(launch_pdl(link_slot_fill_kernel, dim3((unsigned)((n_nodes + 255) / 256)), dim3(256), 0, st, slot, n_nodes, m_c));
   RGCN_LAUNCH_CHECK();
-  RGCN_CUDA(launch_pdl(link_rows_kernel, dim3((unsigned)((2 * n_pairs + 255) / 256)), dim3(256), 0, st, q, rows, slot));
-  RGCN_LAUNCH_CHECK();
   LinkBwdRows b{};
   b.g_loss = g_loss; b.g_score = g_score; b.g_emb = g_emb; b.ld_g = ld_g; b.n_rows = n_nodes;
   b.slot = slot; b.rows = rows; b.unlisted = m_c;
+  b.C = (float*)workspace;
+  b.T = g_rel_table ? (float*)((char*)workspace + link_ws_C(n_pairs, d)) : nullptr;
+  b.tab_partial = g_rel_table ? (float*)((char*)workspace + link_ws_C(n_pairs, d) + link_ws_T(n_pairs, d)) : nullptr;
   b.n_owner_blocks = (int32_t)((2 * n_pairs + 7) / 8);
   b.n_zero_blocks = (int32_t)((n_nodes + kLinkZeroRows - 1) / kLinkZeroRows);
   b.n_tab_blocks = g_rel_table ? (int32_t)((n_pairs + kLinkTabPairs - 1) / kLinkTabPairs) : 0;
-  b.tab_partial = g_rel_table ? (float*)align_up((size_t)workspace, 16) : nullptr;
+  RGCN_CUDA(launch_pdl(link_contrib_kernel, dim3((unsigned)b.n_owner_blocks), dim3(256), 0, st, q, b));
+  RGCN_LAUNCH_CHECK();
   size_t smem = (size_t)(2 * n_pairs) * sizeof(int);
   b.rows_in_smem = smem <= 200 * 1024 ? 1 : 0;       // (larger batches scan the list in global memory)
   if (!b.rows_in_smem) smem = 0;
@@ -762,11 +750,11 @@ extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64
     int dev = 0;
     RGCN_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && granted[dev] < smem) {
-      RGCN_CUDA(cudaFuncSetAttribute(link_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RGCN_CUDA(cudaFuncSetAttribute(link_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       granted[dev] = 200 * 1024;
     }
   }
-  RGCN_CUDA(launch_pdl(link_bwd_rows_kernel, dim3((unsigned)(b.n_owner_blocks + b.n_zero_blocks + b.n_tab_blocks)), dim3(256),
+  RGCN_CUDA(launch_pdl(link_gather_kernel, dim3((unsigned)(b.n_owner_blocks + b.n_zero_blocks + b.n_tab_blocks)), dim3(256),
                        smem, st, q, b));
   RGCN_LAUNCH_CHECK();
   if (g_rel_table) {

@@ -131,9 +131,136 @@ __global__ void __launch_bounds__(256) reduce_split_kernel(ConstPeerPtrs part, i
   }
 }
 
+// ---- all-reduce (average) of one flat fp32 buffer over the GPUs of one NVSwitch domain ----------------------------
+// The data-parallel gradient exchange (every replica holds the whole cfg1-4 graph; the reference is single-device, its
+// README lists multi-GPU as future work).  Two-shot over peer-mapped memory, no collective library, CUDA-graph capturable:
+//   signal : after the producers of `in` (stream order) -> arrive flag (epoch) in every peer's flag block
+//   reduce : every block waits for all arrive flags, then this rank's 1/P slice is summed over all ranks' `in` buffers in
+//            RANK ORDER (every rank computes the same bits), scaled, and stored into the slice of EVERY rank's `out`
+//   done   : done flag to every peer, then wait for everybody's: all slices of this rank's `out` have landed
+// Flags are monotone epochs (device-side counter, advanced by the signal kernel, so a graph replay needs no host help).
+// Waits are bounded (~seconds): a missing peer sets bit 1 of *status instead of hanging the GPU.
+struct FlagPtrs {
+  unsigned int* p[kMaxPeers];                    // every rank's flag block: arrive[kMaxPeers], done[kMaxPeers]
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// true when the flag reached `epoch` (wrap-safe comparison); false after ~4 s of polling
+__device__ __forceinline__ bool wait_flag(const unsigned int* p, unsigned int epoch) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(p) - epoch) < 0) {
+    if (clock64() - t0 > 8000000000ll) return false;
+    __nanosleep(64);
+  }
+  return true;
+}
+
+// which = 0: advance the epoch and raise the arrive flags; which = 1: raise the done flags, then wait for all of them
+__global__ void __launch_bounds__(32) allreduce_flag_kernel(FlagPtrs flags, int n, int rank, unsigned int* epoch_ctr,
+                                                            int which, int* status) {
+  pdl_enter();                                   // everything before this launch in the stream is complete and flushed
+  unsigned int e = 0;
+  if (threadIdx.x == 0) {
+    e = *epoch_ctr + (which == 0 ? 1u : 0u);
+    if (which == 0) *epoch_ctr = e;
+  }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  __threadfence_system();
+  const int q = threadIdx.x;
+  if (q < n) st_release_sys(flags.p[q] + which * kMaxPeers + rank, e);
+  if (which == 1 && q < n) {
+    if (!wait_flag(flags.p[rank] + kMaxPeers + q, e) && status) atomicOr(status, 2);
+  }
+}
+
+__global__ void __launch_bounds__(256) allreduce_reduce_kernel(ConstPeerPtrs in, PeerPtrs out, int n, int rank,
+                                                               int64_t n_vec, float scale, const unsigned int* my_flags,
+                                                               const unsigned int* epoch_ctr, int* status) {
+  pdl_enter();
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if (threadIdx.x < n) {
+    const unsigned int e = *epoch_ctr;
+    if (!wait_flag(my_flags + threadIdx.x, e)) { s_ok = 0; if (status) atomicOr(status, 2); }
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  // this rank's slice, in units of float4
+  const int64_t per = (n_vec + n - 1) / n;
+  const int64_t v0 = per * rank, v1 = min(v0 + per, n_vec);
+  constexpr int U = 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = v0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < v1; i0 += stride * U) {
+    float4 pv[U][kMaxPeers];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+#pragma unroll
+      for (int q = 0; q < kMaxPeers; ++q)
+        if (q < n) pv[u][q] = i < v1 ? __ldcg(reinterpret_cast<const float4*>(in.p[q]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < v1) {
+        float4 v = pv[u][0];
+#pragma unroll
+        for (int q = 1; q < kMaxPeers; ++q)
+          if (q < n) add4(v, pv[u][q]);
+        v = scale4(v, scale);
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+          if (q < n) *(reinterpret_cast<float4*>(out.p[q]) + i) = v;
+      }
+    }
+  }
+}
+
 }  // namespace rgcn
 
 using namespace rgcn;
+
+extern "C" size_t rgcn_p2p_allreduce_flag_bytes(void) { return 2 * kMaxPeers * sizeof(unsigned int); }
+
+extern "C" int rgcn_p2p_allreduce(const float* const* in_host, float* const* out_host, unsigned int* const* flags_host,
+                                  int32_t n_ranks, int32_t rank, int64_t n_floats, float scale, unsigned int* epoch_counter,
+                                  int32_t* status, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(n_ranks >= 1 && n_ranks <= kMaxPeers && rank >= 0 && rank < n_ranks, "p2p_allreduce: between 1 and %d ranks", kMaxPeers);
+  RGCN_CHECK_ARG(in_host && out_host && flags_host && epoch_counter, "p2p_allreduce: null argument");
+  RGCN_CHECK_ARG(n_floats >= 0 && n_floats % 4 == 0, "p2p_allreduce: the buffer length must be a multiple of 4 floats");
+  ConstPeerPtrs in{};
+  PeerPtrs out{};
+  FlagPtrs fl{};
+  for (int q = 0; q < n_ranks; ++q) {
+    RGCN_CHECK_ARG(in_host[q] && out_host[q] && flags_host[q] && (((uintptr_t)in_host[q] | (uintptr_t)out_host[q]) & 15) == 0 &&
+                   ((uintptr_t)flags_host[q] & 3) == 0, "p2p_allreduce: buffer %d is null or misaligned", q);
+    in.p[q] = in_host[q]; out.p[q] = out_host[q]; fl.p[q] = flags_host[q];
+  }
+  if (n_floats == 0) return RGCN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  RGCN_CUDA(launch_pdl(allreduce_flag_kernel, dim3(1), dim3(32), 0, st, fl, (int)n_ranks, (int)rank, epoch_counter, 0, (int*)status));
+  RGCN_LAUNCH_CHECK();
+  const int64_t n_vec = n_floats / 4;
+  const int64_t slice = (n_vec + n_ranks - 1) / n_ranks;
+  int64_t blocks = (slice + 256 * 2 - 1) / (256 * 2);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  RGCN_CUDA(launch_pdl(allreduce_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, st, in, out, (int)n_ranks, (int)rank, n_vec,
+                       scale, (const unsigned int*)fl.p[rank], (const unsigned int*)epoch_counter, (int*)status));
+  RGCN_LAUNCH_CHECK();
+  RGCN_CUDA(launch_pdl(allreduce_flag_kernel, dim3(1), dim3(32), 0, st, fl, (int)n_ranks, (int)rank, epoch_counter, 1, (int*)status));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
 
 extern "C" int rgcn_p2p_push_rows(const float* src, int64_t ld_src, int64_t rows, int32_t cols,
                                   float* const* dst_host, int32_t n_dst, int64_t row0, int64_t ld_dst,

@@ -24,7 +24,7 @@ from .ops import bce_with_logits
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, edge_index: torch.Tensor, edge_type: torch.Tensor, batch_size: int,
                  loss_fn: Optional[Callable] = None, warmup: int = 3, flat_grads: bool = False, sampler=None,
-                 host_io: bool = False):
+                 host_io: bool = False, allreduce: Optional[str] = None):
         """``host_io``: the captured graph starts with the host-to-device copy of the batch from a pinned staging block
         (``self.host_batch``, int64 [4, B] in ``pack_batch`` layout) and ends with the device-to-host copy of the loss
         and the correct-count into pinned memory (``self.host_loss``, ``self.host_correct``): one graph launch per step
@@ -36,6 +36,10 @@ class GraphedTrainStep:
         POSITIVE edges and draws the negatives, the concatenation and the labels on the device inside the graph
         (reference src/train.py:276-288) — ``step.run_positives(pos_head, pos_tail, pos_rel)``; fresh negatives on every
         replay."""
+        """``allreduce="peer"`` (needs ``flat_grads="arena"`` and an initialised process group of GPUs with peer access):
+        data-parallel replicas — the backward kernels write the parameter gradients into a peer-visible flat buffer and the
+        LAST kernels of the captured step average it over the ranks (``peer.PeerAllReduce``: our two-shot all-reduce over
+        NVLink, no collective call); ``p.grad`` then are views of the averaged buffer.  Every rank must replay in step."""
         if not edge_index.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors")
         dev = edge_index.device
@@ -67,11 +71,22 @@ class GraphedTrainStep:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.flat_grad = None
         self.arena = None
+        self.peer_ar = None
+        if allreduce not in (None, "peer"):
+            raise ValueError("allreduce must be None or 'peer'")
+        if allreduce == "peer" and flat_grads != "arena":
+            raise ValueError("allreduce='peer' needs flat_grads='arena'")
         if flat_grads == "arena":
             # the backward kernels write the parameter gradients straight into one flat buffer (ops.GradArena): no zero
             # fill, no accumulate kernels, and ONE tensor to all-reduce
             from . import ops
-            self.arena = ops.GradArena(sum((p.numel() + 63) // 64 * 64 for p in self.params), dev)
+            numel = sum((p.numel() + 63) // 64 * 64 for p in self.params)
+            if allreduce == "peer":
+                from .peer import PeerAllReduce
+                self.peer_ar = PeerAllReduce(numel, dev)
+                self.arena = ops.GradArena(numel, dev, buf=self.peer_ar.inp)
+            else:
+                self.arena = ops.GradArena(numel, dev)
             for p in self.params:
                 p.grad = None
         elif flat_grads:
@@ -99,12 +114,20 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.scores = self._step()
-        self._bind_grads()
         if self.arena is not None:
             lo, hi = self.arena.buf.data_ptr(), self.arena.buf.data_ptr() + self.arena.buf.numel() * 4
-            if all(g is not None and lo <= g.data_ptr() < hi for g in self._grads):
+            inside = all(g is not None and lo <= g.data_ptr() < hi for g in self._grads)
+            if inside:
                 self.flat_grad = self.arena.used        # every parameter gradient lives inside: all-reduce this one tensor
             # else (e.g. basis layers, whose gradients autograd assembles): p.grad are ordinary tensors, flat_grad stays None
+            if self.peer_ar is not None:
+                if not inside:
+                    raise RuntimeError("allreduce='peer': a parameter gradient was not written into the arena")
+                # the averaged gradients: same offsets, in the exchange's output buffer
+                self._avg = [self.peer_ar.out[(g.data_ptr() - lo) // 4: (g.data_ptr() - lo) // 4 + g.numel()].view_as(g)
+                             for g in self._grads]
+                self.flat_grad = self.peer_ar.out[: self.arena.off]
+        self._bind_grads()
 
     def _step(self):
         if self.arena is not None:
@@ -121,6 +144,8 @@ class GraphedTrainStep:
         if self.host_io:
             self.batch_buf.copy_(self.host_batch, non_blocking=True)          # a memcpy node of the captured graph
         out = self._step_compute()
+        if self.peer_ar is not None:
+            self.peer_ar(self.arena.off)               # gradient exchange = the last kernels of the (captured) step
         if self.host_io:
             self.host_loss.copy_(out[0].reshape(1), non_blocking=True)
             if self.correct is not None:
@@ -145,7 +170,10 @@ class GraphedTrainStep:
         return loss.detach(), scores.detach()
 
     def _bind_grads(self) -> None:
-        if self.flat_grad is None or self.arena is not None:
+        if self.peer_ar is not None and getattr(self, "_avg", None) is not None:
+            for p, g in zip(self.params, self._avg):
+                p.grad = g
+        elif self.flat_grad is None or self.arena is not None:
             for p, g in zip(self.params, self._grads):
                 p.grad = g
 

@@ -51,6 +51,7 @@ class DrugDiseaseRGCN(nn.Module):
                 RGCNConv(hidden_dim, hidden_dim, num_relations, num_bases=num_bases) for _ in range(num_layers - 2))
         self.dropout = nn.Dropout(dropout)
         self._eval_cache = None
+        self._register_load_state_dict_pre_hook(self._drop_cache_on_load)
         self._init_embeddings()
 
     def _init_embeddings(self) -> None:
@@ -79,9 +80,10 @@ class DrugDiseaseRGCN(nn.Module):
         self._eval_cache = None
         return super()._apply(fn, *args, **kwargs)
 
-    def load_state_dict(self, *args, **kwargs):
+    def _drop_cache_on_load(self, *args, **kwargs) -> None:
+        # (a pre-hook, not a load_state_dict override: a PARENT's load_state_dict reaches this module through
+        # _load_from_state_dict, which runs the hook)
         self._eval_cache = None
-        return super().load_state_dict(*args, **kwargs)
 
     def _layers(self):
         yield self.conv1

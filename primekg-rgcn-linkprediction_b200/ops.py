@@ -21,8 +21,11 @@ class GradArena:
     9.2 MB as a coalesced group.  ``GraphedTrainStep(flat_grads="arena")`` activates it; every step starts with
     ``reset()`` and takes the same slices, so the addresses are static under CUDA-graph capture."""
 
-    def __init__(self, numel: int, device):
-        self.buf = torch.zeros(int(numel), dtype=torch.float32, device=device)
+    def __init__(self, numel: int, device, buf: Optional[torch.Tensor] = None):
+        """``buf``: use this flat fp32 tensor (e.g. the peer-visible input of ``peer.PeerAllReduce``) as the storage."""
+        if buf is not None and (buf.dtype != torch.float32 or buf.dim() != 1 or buf.numel() < int(numel)):
+            raise ValueError("arena storage must be a flat float32 tensor of at least numel entries")
+        self.buf = torch.zeros(int(numel), dtype=torch.float32, device=device) if buf is None else buf
         self.off = 0
 
     def reset(self) -> None:
@@ -498,8 +501,8 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
     """aggregate -> operand planes -> tensor-core transform of one layer in ONE C call (``rgcn_layer_fwd``).
     Returns (out [n_dst, d_out], (A_hi, A_lo | None), w_planes | None): ``w_planes`` = the layer's weights as bf16 planes,
     converted once by the call; hand it to ``layer_bwd`` (its dgrad then skips the conversion).
-    ``pipeline``: 0 = the library decides whether the walk of row chunk c + 1 runs under the transform of chunk c (while
-    the stream is being captured, or from 200,000 rows), 1 = never, 2 = always."""
+    ``pipeline``: 0 = the library decides whether the walk of row chunk c + 1 runs under the transform of chunk c (from
+    200,000 rows), 1 = never, 2 = always."""
     lib = _lib.load()
     x_src = _f32c(x_src, "x")
     x_root = x_src if x_root is x_src else _f32c(x_root, "x_root")
@@ -769,8 +772,7 @@ def _link_bwd(ctx_p_drop, ctx_seed, emb, rel_table, head, tail, rel, labels, sco
     g_tab = param_grad(*rel_table.shape, device=dev) if need_tab else None
     slot = torch.empty(n_nodes, dtype=torch.int32, device=dev)
     rows = torch.empty(2 * n, dtype=torch.int64, device=dev)
-    nb = int(lib.rgcn_link_bwd_rows_workspace_bytes(n, n_rel, d)) if need_tab else 0
-    ws = _workspace(dev, nb) if need_tab else None
+    ws = _workspace(dev, int(lib.rgcn_link_bwd_rows_workspace_bytes(n, n_rel, d)))     # position / pair contributions
     _lib.check(lib.rgcn_link_loss_bwd_rows(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
                                            _ptr(labels), _ptr(score), _ptr(g_loss), _ptr(g_score), n, d, ctx_p_drop,
                                            ctx_seed & 0xFFFFFFFF, _ptr(state), n_nodes, n_rel, _ptr(g_emb), g_emb.stride(0),

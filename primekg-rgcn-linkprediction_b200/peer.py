@@ -49,3 +49,50 @@ class PeerBuffer:
         is complete and visible before anything enqueued after it starts."""
         self._hdl.barrier(channel=self._chan)
         self._chan ^= 1
+
+
+class PeerAllReduce:
+    """All-reduce (average) of one flat fp32 buffer over the ranks by OUR kernels (``rgcn_p2p_allreduce``: two-shot over
+    peer-mapped memory, rank-ordered sums, device-side epoch flags) — no collective call, CUDA-graph capturable.
+
+    ``inp`` (write the local contribution here) and ``out`` (read the average here) are views of one ``PeerBuffer``; the
+    data-parallel ``GraphedTrainStep(flat_grads="arena", allreduce="peer")`` lets the backward kernels write the parameter
+    gradients straight into ``inp`` and runs the exchange as the last kernels of the captured step."""
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        from . import _lib
+        self.n = (int(numel) + 63) // 64 * 64
+        flag_floats = 64                                           # >= rgcn_p2p_allreduce_flag_bytes() / 4
+        assert int(_lib.load().rgcn_p2p_allreduce_flag_bytes()) <= 4 * flag_floats
+        self.buf = PeerBuffer((2 * self.n + flag_floats) * 4, device, group)
+        self.buf.local.zero_()
+        self.inp = self.buf.local[: self.n]
+        self.out = self.buf.local[self.n: 2 * self.n]
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.rank, self.world = self.buf.rank, self.buf.world
+        torch.cuda.synchronize(device)
+        dist.barrier(self.buf.group)                               # every rank's flags are zero before anybody signals
+        self._in = self.buf.peer_ptrs(0)
+        self._out = self.buf.peer_ptrs(self.n)
+        self._flags = self.buf.peer_ptrs(2 * self.n)
+
+    def __call__(self, n_floats: int = None, scale: float = None) -> torch.Tensor:
+        """Exchange the first ``n_floats`` (default: all) entries of ``inp``; returns ``out`` (valid in stream order)."""
+        import ctypes as C
+        from . import _lib
+        from .graph import _ptr, _stream
+        lib = _lib.load()
+        n = self.n if n_floats is None else (int(n_floats) + 3) // 4 * 4
+        if n > self.n:
+            raise ValueError("n_floats exceeds the buffer")
+        arr = lambda ptrs: (C.c_void_p * len(ptrs))(*[int(a) for a in ptrs])     # noqa: E731
+        _lib.check(lib.rgcn_p2p_allreduce(arr(self._in), arr(self._out), arr(self._flags), self.world, self.rank, n,
+                                          float(1.0 / self.world if scale is None else scale), _ptr(self.epoch),
+                                          _ptr(self.status), _stream(self.inp.device)), "rgcn_p2p_allreduce")
+        return self.out
+
+    def check(self) -> None:
+        """Raise if a wait gave up (a peer never arrived).  Synchronises."""
+        if int(self.status.item()) & 2:
+            raise RuntimeError("peer all-reduce: a rank did not arrive within the wait bound")

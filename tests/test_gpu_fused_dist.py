@@ -117,3 +117,55 @@ def test_only_one_forward_may_be_outstanding(pg):
         s1.sum().backward()
     s2.sum().backward()
     assert model.encoder.node_embeddings.grad is not None
+
+
+def test_peer_allreduce_world1_and_graph_capture(pg):
+    """rgcn_p2p_allreduce with one rank: out = in * scale; flags / epochs advance on the device, so a captured graph
+    replays it without host help; the data-parallel GraphedTrainStep(allreduce='peer') binds p.grad to the averaged buffer."""
+    import primekg_rgcn_linkprediction_b200 as pkg
+    from primekg_rgcn_linkprediction_b200 import synth
+    from primekg_rgcn_linkprediction_b200.peer import PeerAllReduce
+    ar = PeerAllReduce(1000, torch.device(DEV))
+    torch.manual_seed(0)
+    x = torch.randn(ar.n, device=DEV)
+    ar.inp.copy_(x)
+    out = ar(scale=0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(out, x * 0.5)
+    gr = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ar()
+        with torch.cuda.graph(gr):
+            ar(scale=2.0)
+    torch.cuda.current_stream().wait_stream(side)
+    for k in range(3):
+        ar.inp.copy_(x + k)
+        gr.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ar.out, (x + k) * 2.0)
+    assert int(ar.epoch.item()) == 5
+    ar.check()
+    # the training step with the exchange captured inside
+    kg = synth.primekg_subgraph(40_000, seed=3)
+    heads, tails, rels, labels = (t.to(DEV) for t in synth.link_batch(kg, 256, seed=3))
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    torch.manual_seed(1)
+    model = pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, 64, 128, dropout=0.0, decoder_dropout=0.0).to(DEV)
+    model.train()
+    plain = pkg.GraphedTrainStep(model, ei, et, batch_size=512, flat_grads="arena")
+    plain.load_batch(heads, tails, rels, labels)
+    plain()
+    want = {k: p.grad.clone() for k, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    step = pkg.GraphedTrainStep(model, ei, et, batch_size=512, flat_grads="arena", allreduce="peer")
+    step.load_batch(heads, tails, rels, labels)
+    step()
+    torch.cuda.synchronize()
+    lo, hi = step.peer_ar.out.data_ptr(), step.peer_ar.out.data_ptr() + step.peer_ar.out.numel() * 4
+    for k, p in model.named_parameters():
+        assert lo <= p.grad.data_ptr() < hi, k
+        assert torch.equal(p.grad, want[k]), k                    # one rank: the average is the gradient itself
+    step.peer_ar.check()

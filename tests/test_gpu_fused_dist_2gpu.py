@@ -58,3 +58,49 @@ def test_forward_only_loop_with_skewed_ranks_two_gpus(lib_built):
     ret = mp.get_context("spawn").Manager().dict()
     mp.spawn(_two_rank_worker, args=(port, ret), nprocs=2, join=True)
     assert ret.get(0) is True and ret.get(1) is True
+
+
+def _allreduce_worker(rank, port, ret):
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=2, device_id=dev)
+    try:
+        from primekg_rgcn_linkprediction_b200.peer import PeerAllReduce
+        n = 2_300_000
+        ar = PeerAllReduce(n, dev)
+        ok = True
+        for it in range(4):
+            g = torch.Generator(device=dev).manual_seed(100 * it + rank)
+            x = torch.randn(ar.n, generator=g, device=dev)
+            ar.inp.copy_(x)
+            if rank == it % 2:
+                torch.cuda._sleep(50_000_000)                  # skew the ranks
+            out = ar().clone()
+            ref = x.clone()
+            dist.all_reduce(ref)
+            ref /= 2
+            ok = ok and bool(torch.allclose(out, ref, rtol=0, atol=1e-6))
+            both = [torch.empty_like(out) for _ in range(2)]
+            dist.all_gather(both, out)
+            ok = ok and bool(torch.equal(both[0], both[1]))   # rank-ordered sums: every rank holds the same bits
+        ar.check()
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_peer_allreduce_two_gpus(lib_built):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_allreduce_worker, args=(port, ret), nprocs=2, join=True)
+    assert ret.get(0) is True and ret.get(1) is True

@@ -22,7 +22,7 @@ DEV = "cuda:0"
 def test_replay_reference_call_sequence(lib_built):
     pkg = lib_built
     doc = json.load(open(os.path.join(GOLDEN, "ref_call_sequence.json")))
-    assert doc["data"] == H.DATA
+    assert doc["data"] == json.loads(json.dumps(H.DATA))
     train, val, test, full, _ = H.build_splits(doc["data"])
     N, R = doc["model"]["num_nodes"], doc["model"]["num_relations"]
     d_e, d_h = doc["model"]["embedding_dim"], doc["model"]["hidden_dim"]
