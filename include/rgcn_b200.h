@@ -293,8 +293,8 @@ typedef struct rgcn_layer_fwd_args {
    * it ONCE (rgcn_prepare_weights), reads it as the MN-major operand of the transform, and rgcn_layer_bwd reads the same
    * buffer for its dgrad.  With it the call may also PIPELINE: the walk of row chunk c + 1 runs on `stream` while the
    * transform of chunk c (and, in the partitioned path, its peer stores = the all-gather) runs on an internal side
-   * stream, joined before the call returns.  pipeline: 0 = the library decides (from 200,000 rows, where every chunk's
-   * transform is many waves long; RGCN_PIPELINE=0/1 overrides), 1 = never, 2 = always. */
+   * stream, joined before the call returns.  pipeline: 0 = the library decides (from 200,000 rows with peer outputs: every
+   * chunk's transform is many waves long and has NVLink stores to hide; RGCN_PIPELINE=0/1 overrides), 1 = never, 2 = always. */
   void* w_planes; size_t w_planes_bytes; int32_t pipeline;
 } rgcn_layer_fwd_args;
 

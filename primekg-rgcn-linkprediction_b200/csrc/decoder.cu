@@ -363,7 +363,7 @@ struct LinkBwdRows {
 };
 constexpr int kLinkZeroRows = 64;                    // rows per zero-fill block
 constexpr int kLinkTabPairs = 32;                    // pairs per relation-table partial
-constexpr int kLinkList = 64;                        // positions of one node collected before they are added
+constexpr int kLinkList = 128;                        // positions of one node collected before they are added
 
 __device__ __forceinline__ float link_pair_grad(const LinkLossParams& q, const LinkBwdRows& b, int64_t p) {
   if (b.g_score) return b.g_score[p];
@@ -419,17 +419,18 @@ __global__ void __launch_bounds__(256) link_contrib_kernel(const LinkLossParams 
   }
 }
 
-__global__ void __launch_bounds__(256) link_gather_kernel(const LinkLossParams q, const LinkBwdRows b) {
+__global__ void __launch_bounds__(256, 4) link_gather_kernel(const LinkLossParams q, const LinkBwdRows b) {
   pdl_enter();
-  extern __shared__ int s_rows[];                    // [2 n] node of every position (owner blocks, when it fits)
+  extern __shared__ int s_rows[];                    // [2 n rounded up to 128] node of every position (owner blocks)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = q.d >> 2;
   const int64_t n = q.n_pairs, n2 = 2 * q.n_pairs;
   int blk = blockIdx.x;
   if (blk < b.n_owner_blocks) {
     // ---- one warp per position; only the node's first position (its owner) works ----
+    const int64_t n2p = (n2 + 127) & ~int64_t(127);
     if (b.rows_in_smem) {
-      for (int64_t i = threadIdx.x; i < n2; i += 256) s_rows[i] = (int)b.rows[i];
+      for (int64_t i = threadIdx.x; i < n2p; i += 256) s_rows[i] = i < n2 ? (int)b.rows[i] : -1;
       __syncthreads();
     }
     const int64_t pos = (int64_t)blk * 8 + warp;
@@ -445,33 +446,60 @@ __global__ void __launch_bounds__(256) link_gather_kernel(const LinkLossParams q
       float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
       auto flush = [&](int count) {
         __syncwarp();
-        for (int j = 0; j < count; j += 8) {         // eight rows in flight, added strictly in list (= position) order
-          float4 x0[8], x1[8];
+        for (int j = 0; j < count; j += 4) {         // four rows in flight, added strictly in list (= position) order
+          float4 x0[4], x1[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             const int e = min(j + u, count - 1);
             const float* __restrict__ row = b.C + (int64_t)list[e] * q.d;
             x0[u] = *reinterpret_cast<const float4*>(row + c0);
             x1[u] = *reinterpret_cast<const float4*>(row + c1);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 4; ++u) {
             if (j + u < count) { add4(acc0, x0[u]); add4(acc1, x1[u]); }
           }
         }
         __syncwarp();
       };
       int cnt = 0;
-      for (int64_t base = pos & ~int64_t(31); base < n2; base += 32) {
-        const int64_t pp = base + lane;
-        bool match = false;
-        if (pp >= pos && pp < n2) match = (b.rows_in_smem ? (int64_t)s_rows[pp] : b.rows[pp]) == v;
-        const unsigned m = __ballot_sync(0xffffffffu, match);
-        if (!m) continue;
-        const int k = __popc(m);
-        if (cnt + k > kLinkList) { flush(cnt); cnt = 0; }
-        if (match) list[cnt + __popc(m & ((1u << lane) - 1u))] = (int)pp;
-        cnt += k;
+      const int vi = (int)v;
+      if (b.rows_in_smem) {
+        // windows of 128 positions, four per lane (one 128-bit shared-memory load); a window without a match — nearly
+        // all of them — costs one vote
+        for (int64_t base = pos & ~int64_t(127); base < n2p; base += 128) {
+          const int4 w = *reinterpret_cast<const int4*>(s_rows + base + lane * 4);
+          const int64_t p0 = base + lane * 4;
+          const unsigned mk = (unsigned)(w.x == vi && p0 >= pos) | ((unsigned)(w.y == vi && p0 + 1 >= pos) << 1) |
+                              ((unsigned)(w.z == vi && p0 + 2 >= pos) << 2) | ((unsigned)(w.w == vi && p0 + 3 >= pos) << 3);
+          if (!__any_sync(0xffffffffu, mk != 0u)) continue;
+          // ascending positions = lane-major, then the lane's four: exclusive prefix of the lanes' match counts
+          int mine = __popc(mk), before = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, before, o);
+            if (lane >= o) before += up;
+          }
+          const int total = __shfl_sync(0xffffffffu, before, 31);
+          before -= mine;
+          if (cnt + total > kLinkList) { flush(cnt); cnt = 0; }
+          int at = cnt + before;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (mk & (1u << j)) list[at++] = (int)(p0 + j);
+          cnt += total;
+        }
+      } else {
+        for (int64_t base = pos & ~int64_t(31); base < n2; base += 32) {
+          const int64_t pp = base + lane;
+          const bool match = pp >= pos && pp < n2 && b.rows[pp] == v;
+          const unsigned m = __ballot_sync(0xffffffffu, match);
+          if (!m) continue;
+          const int k = __popc(m);
+          if (cnt + k > kLinkList) { flush(cnt); cnt = 0; }
+          if (match) list[cnt + __popc(m & ((1u << lane) - 1u))] = (int)pp;
+          cnt += k;
+        }
       }
       flush(cnt);
       if (on0) *reinterpret_cast<float4*>(b.g_emb + v * b.ld_g + c0) = acc0;
@@ -742,7 +770,7 @@ extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64
   b.n_tab_blocks = g_rel_table ? (int32_t)((n_pairs + kLinkTabPairs - 1) / kLinkTabPairs) : 0;
   RGCN_CUDA(launch_pdl(link_contrib_kernel, dim3((unsigned)b.n_owner_blocks), dim3(256), 0, st, q, b));
   RGCN_LAUNCH_CHECK();
-  size_t smem = (size_t)(2 * n_pairs) * sizeof(int);
+  size_t smem = (size_t)((2 * n_pairs + 127) / 128 * 128) * sizeof(int);
   b.rows_in_smem = smem <= 200 * 1024 ? 1 : 0;       // (larger batches scan the list in global memory)
   if (!b.rows_in_smem) smem = 0;
   if (smem > 48 * 1024) {

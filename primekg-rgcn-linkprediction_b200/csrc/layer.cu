@@ -109,7 +109,9 @@ static int pipeline_mode(const rgcn_layer_fwd_args* a, cudaStream_t st, SideStre
   // measured on cfg2 (30,926 rows, 4 chunks): chunk transforms of one wave each lose more (prologue + pipeline fill per
   // tile, SMs held by walk blocks) than the overlap wins — 0.530 against 0.446 ms per step — so the library only pipelines
   // when every chunk's transform is many waves long (the partitioned cfg5 shards: 1.25 M rows per GPU)
-  if (want == 2 && a->csr->n_rows < 200000) return 0;
+  // ... and has peer stores to hide: on ONE GPU the two streams only compete (1.25 M rows / 50 M edges / 30 relations:
+  // 89.1 against 84.6 ms per step)
+  if (want == 2 && (a->csr->n_rows < 200000 || a->n_peer <= 1)) return 0;
   *ss_out = ss;
   return 1;
 }

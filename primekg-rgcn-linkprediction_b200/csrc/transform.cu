@@ -158,11 +158,22 @@ struct GemmKParams {
   // fused dropout after the ReLU (training): keep iff drop_bits(...) >= drop_thresh, kept values times drop_scale
   uint32_t drop_thresh; float drop_scale; uint32_t drop_seed; const unsigned long long* drop_ctr;
   int64_t row_offset;                         // row of the layer's output that local row 0 is (row-chunked calls): dropout index
+  // ---- epilogues that consume the accumulator instead of storing it (all-pairs scoring, csrc/rank.cu comments) ----
+  int tile_contig;                            // CTA c takes a CONTIGUOUS run of tiles (mostly one row tile): per-row state
+                                              // stays in registers across column tiles
+  int diag;                                   // only the diagonal tiles (row tile t with column tile t), BN == 128
+  int64_t n_cols_valid;                       // candidates beyond this column are padding
+  const float* thr_in; float* thr_out;        // EPI_RANK: per-row threshold;  EPI_THR: out[row] = acc[row, row]
+  const int64_t* true_pos; int32_t* greater; int32_t* equal;
+  float alpha, beta;                          // EPI_TOPK: reported value = alpha * acc + beta (alpha > 0)
+  float* cand_val; int32_t* cand_idx; int32_t* slot_ctr; int32_t n_slots;    // [M, n_slots, kTopK] partial lists, [M] counters
   // fused all-gather: every output tile is also stored into the same-shaped slot (rows peer_row0 ...) of up to
   // kMaxPeers feature buffers that live in OTHER GPUs' memory (peer-mapped, NVLink stores issued by the epilogue)
   float* peer_out[kMaxPeers]; int n_peer; int64_t peer_row0; int64_t peer_ld;
 };
 
+enum { EPI_STORE = 0, EPI_RANK = 1, EPI_THR = 2, EPI_TOPK = 3 };
+constexpr int kTopK = 16;                     // entries every epilogue lane keeps per row (top-K requests up to this)
 constexpr int KBN = 128;                      // N tile of the persistent kernel: two accumulators fit 256 TMEM columns
 constexpr int K_EPI_WARPS = 8;                // two warps per TMEM lane quarter, each draining half of the tile's columns
 constexpr int K_PATCH = 32 * 20 * 4;          // per-warp transpose patch: 32 rows x (16 + 4) floats
@@ -185,7 +196,7 @@ struct KStage {
 // B_MN = false: B is K-major ([N, K] rows of K, the dgrad / all-pairs operand);  B_MN = true: B is MN-major ([K, N] rows
 // of N — the weight matrix exactly as PyTorch stores it, so the forward needs no transposed copy): the stage then holds
 // ceil(BN / 64) chunks of 64 k-rows x 128 B, the layout of the weight-gradient kernel's operands.
-template <bool SPLIT, bool B_MN>
+template <bool SPLIT, bool B_MN, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(K_THREADS, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -199,7 +210,17 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m_tiles = (p.M + BM - 1) / BM;
-  const int64_t n_tiles_total = m_tiles * p.n_tiles;
+  const int64_t n_tiles_total = p.diag ? m_tiles : m_tiles * p.n_tiles;
+  // tile schedule, the same in all three roles: strided (neighbouring CTAs share the A rows in L2) or contiguous runs
+  int64_t t_begin = blockIdx.x, t_end = n_tiles_total, t_step = gridDim.x;
+  if (p.tile_contig) {
+    const int64_t per = (n_tiles_total + gridDim.x - 1) / gridDim.x;
+    t_begin = (int64_t)blockIdx.x * per;
+    t_end = t_begin + per < n_tiles_total ? t_begin + per : n_tiles_total;
+    t_step = 1;
+  }
+  auto tile_mi = [&](int64_t t) { return p.diag ? t : t / p.n_tiles; };
+  auto tile_ni = [&](int64_t t) { return p.diag ? t : t % p.n_tiles; };
   const uint32_t acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;     // columns of one accumulator
   const uint32_t tmem_cols = 2 * acc_cols;
 
@@ -241,11 +262,49 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const unsigned long long ctr = *p.drop_ctr;
       drop_key = pcg_hash(p.drop_seed ^ (uint32_t)ctr) + (uint32_t)(ctr >> 32);
     }
+    // per-row state of the consuming epilogues (one row per lane)
+    int64_t cur_m0 = -1;
+    int cnt_g = 0, cnt_e = 0;
+    float thr = 0.f;
+    int64_t tpos = -1;
+    float topv[EPI == EPI_TOPK ? kTopK : 1];
+    int topi[EPI == EPI_TOPK ? kTopK : 1];
+    auto flush_row_state = [&]() {
+      if (cur_m0 < 0) return;
+      const int64_t row = cur_m0 + quarter * 32 + lane;
+      if (row >= p.M) return;
+      if (EPI == EPI_RANK) {
+        if (cnt_g) atomicAdd(p.greater + row, cnt_g);        // integer adds: order independent, deterministic
+        if (cnt_e) atomicAdd(p.equal + row, cnt_e);
+      } else if (EPI == EPI_TOPK) {
+        const int slot = atomicAdd(p.slot_ctr + row, 1);     // (slot order varies; the merge sorts by value, then index)
+        if (slot < p.n_slots) {
+          float* cv = p.cand_val + ((size_t)row * p.n_slots + slot) * kTopK;
+          int32_t* ci = p.cand_idx + ((size_t)row * p.n_slots + slot) * kTopK;
+#pragma unroll
+          for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) { cv[i] = topv[i]; ci[i] = topi[i]; }
+        }
+      }
+    };
     int iter = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++iter) {
-      const int64_t m0 = (t / p.n_tiles) * BM;
-      const int n0 = (int)(t % p.n_tiles) * p.BN;
+    for (int64_t t = t_begin; t < t_end; t += t_step, ++iter) {
+      const int64_t m0 = tile_mi(t) * BM;
+      const int n0 = (int)tile_ni(t) * p.BN;
       const int a = iter & 1;
+      if (EPI != EPI_STORE && m0 != cur_m0) {
+        flush_row_state();
+        cur_m0 = m0;
+        const int64_t row = m0 + quarter * 32 + lane;
+        cnt_g = cnt_e = 0;
+        if (EPI == EPI_RANK) {
+          thr = row < p.M ? p.thr_in[row] : 0.f;
+          tpos = row < p.M ? p.true_pos[row] : -1;
+        }
+        if (EPI == EPI_TOPK) {
+#pragma unroll
+          for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) { topv[i] = -INFINITY; topi[i] = -1; }
+        }
+      }
       mbar_wait(&tfull_bar[a], (uint32_t)((iter >> 1) & 1));
       fence_after_sync();
       const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
@@ -253,6 +312,42 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         uint32_t r[16];
         tmem_ld_32x16(t_lane + cc, r);
         tmem_ld_wait();
+        if (EPI != EPI_STORE) {
+          const int64_t row = m0 + quarter * 32 + lane;
+          if (EPI == EPI_RANK) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int64_t col = n0 + cc + j;
+              const float v = __uint_as_float(r[j]);
+              if (row < p.M && col < p.n_cols_valid && col != tpos) { cnt_g += v > thr; cnt_e += v == thr; }
+            }
+          } else if (EPI == EPI_THR) {
+            // the diagonal element of this lane's row, if it lies in this warp's 16 columns
+            const int want = quarter * 32 + lane - cc;
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j == want) v = __uint_as_float(r[j]);
+            if (want >= 0 && want < 16 && row < p.M) p.thr_out[row] = v;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = n0 + cc + j;
+              float v = __uint_as_float(r[j]);
+              if (row < p.M && col < p.n_cols_valid && v > topv[(EPI == EPI_TOPK ? kTopK : 1) - 1]) {
+                int ci = col;                                // insertion into the descending list (columns arrive in
+#pragma unroll                                               // ascending order: an equal value keeps the earlier one first)
+                for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) {
+                  if (v > topv[i]) {
+                    const float tv = topv[i]; const int ti = topi[i];
+                    topv[i] = v; topi[i] = ci; v = tv; ci = ti;
+                  }
+                }
+              }
+            }
+          }
+          continue;
+        }
         // registers (one row per lane) -> patch, + bias / ReLU
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -293,6 +388,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       fence_before_sync();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);       // accumulator a may be overwritten
     }
+    if (EPI != EPI_STORE) flush_row_state();
   } else if (warp == K_EPI_WARPS) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -301,9 +397,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const uint32_t b_bytes = B_MN ? (uint32_t)b_chunks * (uint32_t)(BK * 128) : (uint32_t)p.BN * 128u;
       const uint32_t bytes = ((uint32_t)BM * 128u + b_bytes) * (SPLIT ? 2u : 1u);
       uint32_t it = 0;
-      for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x) {
-        const int m0 = (int)((t / p.n_tiles) * BM);
-        const int n0 = (int)(t % p.n_tiles) * p.BN;
+      for (int64_t t = t_begin; t < t_end; t += t_step) {
+        const int m0 = (int)(tile_mi(t) * BM);
+        const int n0 = (int)tile_ni(t) * p.BN;
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % S::STAGES;
           const uint32_t ph = (it / S::STAGES) & 1;
@@ -330,7 +426,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       const uint32_t idesc = idesc_bf16(BM, p.BN, 0, B_MN ? 1 : 0);
       uint32_t it = 0;
       int iter = 0;
-      for (int64_t t = blockIdx.x; t < n_tiles_total; t += gridDim.x, ++iter) {
+      for (int64_t t = t_begin; t < t_end; t += t_step, ++iter) {
         const int a = iter & 1;
         mbar_wait(&tempty_bar[a], (uint32_t)(((iter >> 1) & 1) ^ 1));   // epilogue has drained this accumulator
         fence_after_sync();
@@ -683,9 +779,19 @@ static int launch_kmajor_t(const GemmKParams& p, const CUtensorMap& ahi, const C
   return RGCN_OK;
 }
 
+template <bool SPLIT, bool B_MN, int EPI>
+static int launch_kmajor_e(const GemmKParams& p, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
+                           const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
+  int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN, EPI>, KStage<SPLIT>::SMEM);
+  if (rc) return rc;
+  RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN, EPI>, dim3(grid), dim3(K_THREADS), KStage<SPLIT>::SMEM, st, ahi, alo, mhi, mlo, p));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
 static int launch_kmajor(GemmKParams p, const void* a_hi, const void* a_lo, int64_t lda, int K,
                          const __nv_bfloat16* bhi, const __nv_bfloat16* blo, int64_t b_rows, int64_t b_cols, int64_t b_ld,
-                         bool b_mn, int n_tiles, bool split, cudaStream_t st) {
+                         bool b_mn, int n_tiles, bool split, cudaStream_t st, int epi = EPI_STORE) {
   CUtensorMap ahi, alo, mhi, mlo;
   int rc = make_map(&ahi, a_hi, p.M, K, lda, BM);
   if (rc) return rc;
@@ -696,8 +802,15 @@ static int launch_kmajor(GemmKParams p, const void* a_hi, const void* a_lo, int6
   rc = make_map(&mlo, split ? blo : bhi, b_rows, b_cols, b_ld, b_mn ? BK : p.BN);
   if (rc) return rc;
   p.n_tiles = n_tiles;
-  const int64_t tiles = ((p.M + BM - 1) / BM) * n_tiles;
+  const int64_t tiles = p.diag ? (p.M + BM - 1) / BM : ((p.M + BM - 1) / BM) * n_tiles;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  if (epi != EPI_STORE) {
+    // the consuming epilogues serve the all-pairs scorers: K-major candidates, three-product (fp32) mode
+    if (b_mn || !split) { set_error("transform: the scoring epilogues need K-major candidates in fp32 mode"); return RGCN_EINVAL; }
+    if (epi == EPI_RANK) return launch_kmajor_e<true, false, EPI_RANK>(p, ahi, alo, mhi, mlo, grid, st);
+    if (epi == EPI_THR) return launch_kmajor_e<true, false, EPI_THR>(p, ahi, alo, mhi, mlo, grid, st);
+    return launch_kmajor_e<true, false, EPI_TOPK>(p, ahi, alo, mhi, mlo, grid, st);
+  }
   if (split) return b_mn ? launch_kmajor_t<true, true>(p, ahi, alo, mhi, mlo, grid, st)
                          : launch_kmajor_t<true, false>(p, ahi, alo, mhi, mlo, grid, st);
   return b_mn ? launch_kmajor_t<false, true>(p, ahi, alo, mhi, mlo, grid, st)
@@ -1006,4 +1119,144 @@ extern "C" int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_
   p.M = n_rows; p.N = K; p.BN = t.BN; p.num_kb = round_up(d_out, BK) / BK;
   p.out = gA; p.ldo = ldga;
   return launch_kmajor(p, G_hi, G_lo, ldg, d_out, bhi, blo, K, d_out, wplane_ld(d_out), false, t.n_tiles, mode == 0, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// All-pairs scoring WITHOUT the score matrix: the tcgen05 kernel's epilogue consumes the accumulator.
+//   queries   : bf16 hi / lo planes [n_q, d] (rgcn_split_planes of the prepared rows, csrc/rank.cu rows_prepare)
+//   candidates: rgcn_prepare_weights planes of the fp32 candidate rows [n_cand, d] (K-major operand)
+//   rgcn_scores_diag_w : thr[i] = <q_i, c_i>  — the diagonal tiles of Q x C'^T with C' = the true tails gathered per query;
+//                        same K order and products as the full sweep, so thr[i] carries the bits the sweep computes for
+//                        (i, true_pos[i]) and exact ties with other candidates are counted as ties
+//   rgcn_scores_rank_w : greater[i] / equal[i] += #{j != true_pos[i] : s_ij > / == thr[i]}   (zero them first)
+//   rgcn_scores_topk_w : per query the k <= 16 best candidates (alpha * s + beta, index), sorted by value then index;
+//                        every epilogue lane keeps a 16-entry list per row across its run of column tiles, the partial
+//                        lists (n_slots per row, rgcn_scores_topk_slots) are merged by a second small kernel
+// Replaces score_all_tails + the per-row argsort of src/evaluate.py:260-276 and the cosine sweeps + top-k / threshold
+// filters of src/compare_methods.py:384-397, src/medical_validation.py:222-239, src/case_studies.py:260-274.
+// ------------------------------------------------------------------------------------------------
+namespace rgcn {
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+                                                         const int32_t* __restrict__ slot_ctr, int n_slots, int64_t n_q, int k,
+                                                         float alpha, float beta, float* __restrict__ out_val,
+                                                         int64_t* __restrict__ out_idx) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_q) return;
+  int used = slot_ctr[row];
+  if (used > n_slots) used = n_slots;
+  const int total = used * kTopK;
+  const float* cv = cand_val + (size_t)row * n_slots * kTopK;
+  const int32_t* ci = cand_idx + (size_t)row * n_slots * kTopK;
+  constexpr int PER = 8;                              // up to 256 candidates per row (16 slots)
+  float v[PER];
+  int id[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int e = u * 32 + lane;
+    const bool ok = e < total;
+    v[u] = ok ? cv[e] : -INFINITY;
+    id[u] = ok ? ci[e] : -1;
+    if (id[u] < 0) v[u] = -INFINITY;
+  }
+  for (int j = 0; j < k; ++j) {
+    // warp arg-max by (value desc, index asc)
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+      if (id[u] >= 0 && (v[u] > bv || (v[u] == bv && id[u] < bi))) { bv = v[u]; bi = id[u]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u)
+      if (id[u] == bi) { id[u] = -1; v[u] = -INFINITY; }      // (an index occurs once: column ranges are disjoint)
+    if (lane == 0) {
+      const bool have = bi != 0x7fffffff;
+      out_val[row * k + j] = have ? alpha * bv + beta : -INFINITY;
+      out_idx[row * k + j] = have ? (int64_t)bi : -1;
+    }
+  }
+}
+}  // namespace rgcn
+
+static int scores_common(GemmKParams& p, const void* Q_hi, const void* Q_lo, int64_t ldq, int32_t d, const void* cand_planes,
+                         int64_t n_q, const char* what) {
+  RGCN_CHECK_ARG(n_q >= 0 && n_q < (1ll << 31) && d > 0 && d % 4 == 0, "%s: bad sizes", what);
+  RGCN_CHECK_ARG(cand_planes && ((uintptr_t)cand_planes & 255) == 0, "%s: candidate planes must come from rgcn_prepare_weights", what);
+  int rc = check_plane(Q_hi, ldq, "Q_hi"); if (rc) return rc;
+  rc = check_plane(Q_lo, ldq, "Q_lo"); if (rc) return rc;
+  p.M = n_q; p.BN = KBN; p.num_kb = round_up(d, BK) / BK;
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_scores_diag_w(const void* Q_hi, const void* Q_lo, int64_t ldq, int32_t d, const void* tail_planes,
+                                  int64_t n_q, float* thr, rgcn_stream_t stream) {
+  GemmKParams p{};
+  int rc = scores_common(p, Q_hi, Q_lo, ldq, d, tail_planes, n_q, "scores_diag_w");
+  if (rc) return rc;
+  RGCN_CHECK_ARG(thr, "scores_diag_w: null output");
+  if (n_q == 0) return RGCN_OK;
+  p.N = (int)(n_q < KBN ? KBN : KBN); p.diag = 1; p.thr_out = thr;
+  const __nv_bfloat16* bhi = (const __nv_bfloat16*)tail_planes;
+  const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)tail_planes + wplane_bytes((int)n_q, d));
+  return launch_kmajor(p, Q_hi, Q_lo, ldq, d, bhi, blo, n_q, d, wplane_ld(d), false, 1, true, (cudaStream_t)stream, EPI_THR);
+}
+
+extern "C" int rgcn_scores_rank_w(const void* Q_hi, const void* Q_lo, int64_t ldq, int32_t d, const void* cand_planes,
+                                  int64_t n_cand, int64_t n_q, const float* thr, const int64_t* true_pos, int32_t* greater,
+                                  int32_t* equal, rgcn_stream_t stream) {
+  GemmKParams p{};
+  int rc = scores_common(p, Q_hi, Q_lo, ldq, d, cand_planes, n_q, "scores_rank_w");
+  if (rc) return rc;
+  RGCN_CHECK_ARG(n_cand > 0 && n_cand < (1ll << 31) && thr && true_pos && greater && equal, "scores_rank_w: null argument");
+  if (n_q == 0) return RGCN_OK;
+  p.N = (int)n_cand; p.n_cols_valid = n_cand; p.tile_contig = 1;
+  p.thr_in = thr; p.true_pos = true_pos; p.greater = greater; p.equal = equal;
+  const int n_tiles = (int)((n_cand + KBN - 1) / KBN);
+  const __nv_bfloat16* bhi = (const __nv_bfloat16*)cand_planes;
+  const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)cand_planes + wplane_bytes((int)n_cand, d));
+  return launch_kmajor(p, Q_hi, Q_lo, ldq, d, bhi, blo, n_cand, d, wplane_ld(d), false, n_tiles, true, (cudaStream_t)stream, EPI_RANK);
+}
+
+extern "C" int32_t rgcn_scores_topk_slots(int64_t n_q, int64_t n_cand) {
+  if (n_q <= 0 || n_cand <= 0) return 0;
+  const int64_t n_tiles = (n_cand + KBN - 1) / KBN, m_tiles = (n_q + BM - 1) / BM;
+  const int64_t tiles = n_tiles * m_tiles;
+  const int64_t grid = tiles < sm_count() ? tiles : sm_count();
+  const int64_t per = (tiles + grid - 1) / grid;
+  int64_t slots = 2 * ((n_tiles + per - 1) / per + 1);           // CTA runs touching one row tile x two column halves
+  return (int32_t)(slots > 16 ? 16 : slots);
+}
+
+extern "C" int rgcn_scores_topk_w(const void* Q_hi, const void* Q_lo, int64_t ldq, int32_t d, const void* cand_planes,
+                                  int64_t n_cand, int64_t n_q, int32_t k, float alpha, float beta, float* cand_val,
+                                  int32_t* cand_idx, int32_t* slot_ctr, int32_t n_slots, float* out_val, int64_t* out_idx,
+                                  rgcn_stream_t stream) {
+  GemmKParams p{};
+  int rc = scores_common(p, Q_hi, Q_lo, ldq, d, cand_planes, n_q, "scores_topk_w");
+  if (rc) return rc;
+  RGCN_CHECK_ARG(n_cand > 0 && n_cand < (1ll << 31) && k >= 1 && k <= kTopK && alpha > 0.f, "scores_topk_w: 1 <= k <= %d, alpha > 0", kTopK);
+  RGCN_CHECK_ARG(cand_val && cand_idx && slot_ctr && out_val && out_idx, "scores_topk_w: null argument");
+  RGCN_CHECK_ARG(n_slots >= rgcn_scores_topk_slots(n_q, n_cand) || n_slots == 16, "scores_topk_w: too few slots (rgcn_scores_topk_slots)");
+  RGCN_CHECK_ARG(rgcn_scores_topk_slots(n_q, n_cand) <= 16 && 2 * ((n_cand + KBN - 1) / KBN) + 2 >= 0, "scores_topk_w: bad sizes");
+  if (n_q == 0) return RGCN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  RGCN_CUDA(cudaMemsetAsync(slot_ctr, 0, (size_t)n_q * sizeof(int32_t), st));
+  p.N = (int)n_cand; p.n_cols_valid = n_cand; p.tile_contig = 1;
+  p.alpha = alpha; p.beta = beta; p.cand_val = cand_val; p.cand_idx = cand_idx; p.slot_ctr = slot_ctr; p.n_slots = n_slots;
+  const int n_tiles = (int)((n_cand + KBN - 1) / KBN);
+  const __nv_bfloat16* bhi = (const __nv_bfloat16*)cand_planes;
+  const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)cand_planes + wplane_bytes((int)n_cand, d));
+  rc = launch_kmajor(p, Q_hi, Q_lo, ldq, d, bhi, blo, n_cand, d, wplane_ld(d), false, n_tiles, true, st, EPI_TOPK);
+  if (rc) return rc;
+  RGCN_CUDA(launch_pdl(topk_merge_kernel, dim3((unsigned)((n_q + 7) / 8)), dim3(256), 0, st, (const float*)cand_val,
+                       (const int32_t*)cand_idx, (const int32_t*)slot_ctr, (int)n_slots, n_q, (int)k, alpha, beta, out_val, out_idx));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
 }
