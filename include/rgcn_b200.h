@@ -448,6 +448,29 @@ int rgcn_allpairs_rank(const float* A, int64_t lda, int64_t nq, const float* B, 
  * excluded by index.  thr (optional) receives the thresholds. */
 int rgcn_rank_count(const float* scores, int64_t ld, int64_t nq, int64_t n_cand, const int64_t* true_pos,
                     float* thr, int32_t* greater, int32_t* equal, rgcn_stream_t stream);
+/* The same sweeps on the tensor cores WITHOUT the [queries, candidates] matrix: the tcgen05 kernel's epilogue consumes the
+ * accumulator (three bf16 products, fp32 accumulation, as the fp32 mode of the transforms).
+ *   Q_hi / Q_lo     : the prepared query rows (rgcn_rows_prepare) as bf16 planes [n_q, d] (rgcn_split_planes)
+ *   cand_planes     : rgcn_prepare_weights(candidate rows [n_cand, d], K1 = n_cand, d_out = d, mode 0)
+ *   rgcn_scores_diag_w : thr[i] = <q_i, c_i> from the DIAGONAL tiles of Q x T^T, T = the true tails gathered per query and
+ *                        prepared like cand_planes ([n_q, d]): same K order and products as the sweep, so thr[i] carries the
+ *                        bits the sweep computes for (i, true_pos[i]) and exact ties with other candidates count as ties
+ *   rgcn_scores_rank_w : greater[i] / equal[i] += #{j != true_pos[i] : s_ij > / == thr[i]}   (zero both first)
+ *                        -> rank = 1 + greater: score_all_tails + the per-row argsort of src/evaluate.py:260-276
+ *   rgcn_scores_topk_w : per query the k <= 16 best candidates, value alpha * s + beta (alpha > 0) and position in the
+ *                        candidate list, sorted by value (ties: lower position first): the cosine sweeps + top-k /
+ *                        threshold filters of src/compare_methods.py:384-397, src/medical_validation.py:222-239,
+ *                        src/case_studies.py:260-274.  Scratch: cand_val / cand_idx [n_q, n_slots, 16] with n_slots =
+ *                        rgcn_scores_topk_slots(n_q, n_cand), slot_ctr [n_q] (cleared by the call). */
+int rgcn_scores_diag_w(const void* Q_hi, const void* Q_lo, int64_t ldq, int32_t d, const void* tail_planes, int64_t n_q,
+                       float* thr, rgcn_stream_t stream);
+int rgcn_scores_rank_w(const void* Q_hi, const void* Q_lo, int64_t ldq, int32_t d, const void* cand_planes, int64_t n_cand,
+                       int64_t n_q, const float* thr, const int64_t* true_pos, int32_t* greater, int32_t* equal,
+                       rgcn_stream_t stream);
+int32_t rgcn_scores_topk_slots(int64_t n_q, int64_t n_cand);
+int rgcn_scores_topk_w(const void* Q_hi, const void* Q_lo, int64_t ldq, int32_t d, const void* cand_planes, int64_t n_cand,
+                       int64_t n_q, int32_t k, float alpha, float beta, float* cand_val, int32_t* cand_idx,
+                       int32_t* slot_ctr, int32_t n_slots, float* out_val, int64_t* out_idx, rgcn_stream_t stream);
 /* ------------------------------------------------------------------------------------------
  * Fused link-prediction loss.  Replaces nn.BCEWithLogitsLoss (mean) over the batch logits and the
  * sigmoid > 0.5 accuracy count (src/train.py:139, :300, :321-322):

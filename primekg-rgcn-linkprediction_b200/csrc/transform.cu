@@ -23,6 +23,7 @@
 //   MMA warp : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) and tcgen05.commit
 //   epilogue : tcgen05.ld -> bias / ReLU -> staging tile in the idle operand smem -> coalesced 128-bit row stores
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -179,12 +180,15 @@ constexpr int K_EPI_WARPS = 8;                // two warps per TMEM lane quarter
 constexpr int K_PATCH = 32 * 20 * 4;          // per-warp transpose patch: 32 rows x (16 + 4) floats
 constexpr int K_THREADS = (K_EPI_WARPS + 2) * 32;
 
-template <bool SPLIT>
+// BNT = widest column tile the instantiation can hold: 128 (two accumulators in 256 TMEM columns, 3 / 6 stages) or 256
+// (two accumulators fill the 512 TMEM columns; A is then read once for 256 output columns — the K = 1,024 forward is
+// bound by the L2 -> SM ingest of its operands, not by the tensor pipe — at the price of a 2 / 4 stage ring)
+template <bool SPLIT, int BNT = 128>
 struct KStage {
   static constexpr int A_BYTES = BM * 128;              // 128 rows x 64 bf16
-  static constexpr int B_BYTES = KBN * 128;
+  static constexpr int B_BYTES = BNT * 128;
   static constexpr int BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = SPLIT ? 3 : 6;
+  static constexpr int STAGES = BNT == 256 ? (SPLIT ? 2 : 4) : (SPLIT ? 3 : 6);
   static constexpr int A_HI = 0, A_LO = A_BYTES;
   static constexpr int B_HI = (SPLIT ? 2 : 1) * A_BYTES, B_LO = B_HI + B_BYTES;
   static constexpr int SMEM = STAGES * BYTES + K_EPI_WARPS * K_PATCH + 1024;
@@ -196,12 +200,12 @@ struct KStage {
 // B_MN = false: B is K-major ([N, K] rows of K, the dgrad / all-pairs operand);  B_MN = true: B is MN-major ([K, N] rows
 // of N — the weight matrix exactly as PyTorch stores it, so the forward needs no transposed copy): the stage then holds
 // ceil(BN / 64) chunks of 64 k-rows x 128 B, the layout of the weight-gradient kernel's operands.
-template <bool SPLIT, bool B_MN, int EPI = EPI_STORE>
+template <bool SPLIT, bool B_MN, int EPI = EPI_STORE, int BNT = 128>
 __global__ void __launch_bounds__(K_THREADS, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmKParams p) {
-  using S = KStage<SPLIT>;
+  using S = KStage<SPLIT, BNT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[S::STAGES], empty_bar[S::STAGES], tfull_bar[2], tempty_bar[2];
@@ -221,7 +225,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   }
   auto tile_mi = [&](int64_t t) { return p.diag ? t : t / p.n_tiles; };
   auto tile_ni = [&](int64_t t) { return p.diag ? t : t % p.n_tiles; };
-  const uint32_t acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;     // columns of one accumulator
+  const uint32_t acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;     // columns of one accumulator
   const uint32_t tmem_cols = 2 * acc_cols;
 
   if (threadIdx.x == 0) {
@@ -772,11 +776,29 @@ static int check_plane(const void* p, int64_t ld, const char* what) {
 template <bool SPLIT, bool B_MN>
 static int launch_kmajor_t(const GemmKParams& p, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
                            const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
+  if (p.BN > 128) {
+    int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, 256>, KStage<SPLIT, 256>::SMEM);
+    if (rc) return rc;
+    RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, 256>, dim3(grid), dim3(K_THREADS), KStage<SPLIT, 256>::SMEM, st,
+                         ahi, alo, mhi, mlo, p));
+    RGCN_LAUNCH_CHECK();
+    return RGCN_OK;
+  }
   int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN>, KStage<SPLIT>::SMEM);
   if (rc) return rc;
   RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN>, dim3(grid), dim3(K_THREADS), KStage<SPLIT>::SMEM, st, ahi, alo, mhi, mlo, p));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
+}
+
+// widest column tile of the prepared-weights transforms (RGCN_WIDE_TILES=0: always 128)
+static int wide_bn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RGCN_WIDE_TILES");
+    v = (e && e[0] == '0') ? KBN : 256;
+  }
+  return v;
 }
 
 template <bool SPLIT, bool B_MN, int EPI>
@@ -1083,7 +1105,7 @@ extern "C" int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t 
   RGCN_CHECK_ARG(out && ((uintptr_t)out & 15) == 0 && ldo % 4 == 0, "transform_fwd_w: out must be 16-byte aligned, ld %% 4 == 0");
   RGCN_CHECK_ARG(!bias || d_out <= 1024, "transform_fwd_w: bias needs d_out <= 1024");
   if (n_rows == 0) return RGCN_OK;
-  const Tiling t = tile_n(d_out, 32, KBN);
+  const Tiling t = tile_n(d_out, 32, d_out > KBN ? wide_bn() : KBN);
   const __nv_bfloat16* bhi = (const __nv_bfloat16*)w_planes;
   const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)w_planes + wplane_bytes(K, d_out));
   GemmKParams p{};
@@ -1112,7 +1134,7 @@ extern "C" int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_
   if (mode == 0) { rc = check_plane(G_lo, ldg, "G_lo"); if (rc) return rc; }
   RGCN_CHECK_ARG(gA && ((uintptr_t)gA & 15) == 0 && ldga % 4 == 0, "transform_dgrad_w: gA must be 16-byte aligned, ld %% 4 == 0");
   if (n_rows == 0) return RGCN_OK;
-  const Tiling t = tile_n(K, 32, KBN);
+  const Tiling t = tile_n(K, 32, K > KBN ? wide_bn() : KBN);
   const __nv_bfloat16* bhi = (const __nv_bfloat16*)w_planes;
   const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)w_planes + wplane_bytes(K, d_out));
   GemmKParams p{};

@@ -118,12 +118,111 @@ def score_all_pairs(emb: torch.Tensor, a_idx: torch.Tensor, b_idx: torch.Tensor,
     return scores_from_rows(A, emb, b_idx, method=method)
 
 
+def _query_planes(A: torch.Tensor):
+    from . import ops
+    planes = ops.alloc_planes(A.size(0), A.size(1), "fp32", A.device)
+    ops.split_planes(A, planes)
+    return planes
+
+
+def _candidate_rows(B: torch.Tensor, idx: Optional[torch.Tensor]) -> torch.Tensor:
+    """fp32 candidate rows [n, d], gathered through ``idx`` when given (contiguous)."""
+    if idx is None:
+        return B.contiguous()
+    lib = _lib.load()
+    out = torch.empty(idx.numel(), B.size(1), dtype=torch.float32, device=B.device)
+    _lib.check(lib.rgcn_rows_prepare(_ptr(B), B.stride(0), _ptr(idx), idx.numel(), B.size(1), None, None, 0, _ptr(out),
+                                     out.stride(0), _stream(B.device)), "rgcn_rows_prepare")
+    return out
+
+
+def _rank_fused(A: torch.Tensor, B: torch.Tensor, cand: Optional[torch.Tensor], tails: torch.Tensor):
+    """Tensor-core sweep whose epilogue counts instead of storing (``rgcn_scores_rank_w``); the threshold comes from the
+    diagonal tiles of queries x (their own true tails) with the same K order, so it carries the sweep's own bits."""
+    from . import ops
+    lib = _lib.load()
+    nq, d = A.shape
+    C = _candidate_rows(B, cand)
+    nb = C.size(0)
+    Q = _query_planes(A)
+    cand_planes = ops.prepare_weights(C, None, "fp32")
+    true_rows = torch.empty(nq, d, dtype=torch.float32, device=A.device)
+    _lib.check(lib.rgcn_rows_prepare(_ptr(C), C.stride(0), _ptr(tails), nq, d, None, None, 0, _ptr(true_rows), d,
+                                     _stream(A.device)), "rgcn_rows_prepare")
+    tail_planes = ops.prepare_weights(true_rows, None, "fp32")
+    thr = torch.empty(nq, dtype=torch.float32, device=A.device)
+    greater = torch.zeros(nq, dtype=torch.int32, device=A.device)
+    equal = torch.zeros(nq, dtype=torch.int32, device=A.device)
+    st = _stream(A.device)
+    _lib.check(lib.rgcn_scores_diag_w(_ptr(Q[0]), _ptr(Q[1]), Q[0].stride(0), d, _ptr(tail_planes), nq, _ptr(thr), st),
+               "rgcn_scores_diag_w")
+    _lib.check(lib.rgcn_scores_rank_w(_ptr(Q[0]), _ptr(Q[1]), Q[0].stride(0), d, _ptr(cand_planes), nb, nq, _ptr(thr),
+                                      _ptr(tails), _ptr(greater), _ptr(equal), st), "rgcn_scores_rank_w")
+    return greater, equal
+
+
+def topk_from_rows(A: torch.Tensor, B: torch.Tensor, k: int, b_idx: Optional[torch.Tensor] = None, alpha: float = 1.0,
+                   beta: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(values [n_a, k], positions [n_a, k]): per row of ``A`` the k best rows of ``B[b_idx]`` by alpha * <a, b> + beta,
+    sorted by value (ties: lower position first); positions index ``b_idx`` (or B).  Tensor cores, the score block is
+    consumed in the epilogue (``rgcn_scores_topk_w``), k <= 16."""
+    from . import ops
+    lib = _lib.load()
+    if not (1 <= k <= 16):
+        raise ValueError("fused top-k serves 1 <= k <= 16")
+    A = A.detach().to(torch.float32).contiguous()
+    B = B.detach().to(torch.float32)
+    if B.stride(1) != 1:
+        B = B.contiguous()
+    C = _candidate_rows(B, None if b_idx is None else b_idx.to(torch.int64).contiguous())
+    na, d = A.shape
+    nb = C.size(0)
+    if na == 0 or nb == 0 or d % 4:
+        raise ValueError("topk_from_rows needs non-empty operands with a feature width that is a multiple of 4")
+    Q = _query_planes(A)
+    cand_planes = ops.prepare_weights(C, None, "fp32")
+    slots = int(lib.rgcn_scores_topk_slots(na, nb))
+    dev = A.device
+    cv = torch.empty(na, slots, 16, dtype=torch.float32, device=dev)
+    ci = torch.empty(na, slots, 16, dtype=torch.int32, device=dev)
+    ctr = torch.empty(na, dtype=torch.int32, device=dev)
+    ov = torch.empty(na, k, dtype=torch.float32, device=dev)
+    oi = torch.empty(na, k, dtype=torch.int64, device=dev)
+    _lib.check(lib.rgcn_scores_topk_w(_ptr(Q[0]), _ptr(Q[1]), Q[0].stride(0), d, _ptr(cand_planes), nb, na, int(k),
+                                      float(alpha), float(beta), _ptr(cv), _ptr(ci), _ptr(ctr), slots, _ptr(ov), _ptr(oi),
+                                      _stream(dev)), "rgcn_scores_topk_w")
+    return ov, oi
+
+
+def topk_all_pairs(emb: torch.Tensor, a_idx: torch.Tensor, b_idx: torch.Tensor, k: int = 10,
+                   rel_vec: Optional[torch.Tensor] = None, cosine: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per row of ``a_idx`` the k best of ``b_idx`` — DistMult ``(emb[a] * rel_vec) . emb[b]`` or cosine ``(cos + 1) / 2`` —
+    without the [len(a), len(b)] matrix: (scores [len(a), k], node ids [len(a), k]).  The device form of the per-disease /
+    per-drug sweeps + top-k filters of src/compare_methods.py:384-397, src/medical_validation.py:222-239 and
+    src/case_studies.py:260-274 (fused L2 normalisation, fused rescale)."""
+    b_idx = b_idx.to(torch.int64)
+    if cosine:
+        A = _prep(emb, a_idx, None, None, True)
+        Bn = _prep(emb, b_idx, None, None, True)
+        val, pos = topk_from_rows(A, Bn, k, None, 0.5, 0.5)
+    else:
+        if rel_vec is not None:
+            A = _prep(emb, a_idx, rel_vec.reshape(1, -1), torch.zeros(a_idx.numel(), dtype=torch.int64, device=emb.device), False)
+        else:
+            A = _prep(emb, a_idx, None, None, False)
+        val, pos = topk_from_rows(A, emb, k, b_idx)
+    ids = torch.where(pos >= 0, b_idx[pos.clamp(min=0)], pos)
+    return val, ids
+
+
 def rank_true_tails(emb: torch.Tensor, rel_table: torch.Tensor, heads: torch.Tensor, rels: torch.Tensor,
                     tails: torch.Tensor, candidates: Optional[torch.Tensor] = None, method: str = "tc"
                     ) -> Tuple[torch.Tensor, torch.Tensor]:
     """(rank, ties): rank[i] = 1 + #{candidates scoring strictly above the true tail} (int64, 1-indexed like
     src/evaluate.py:274); ties[i] = #{other candidates with exactly the true tail's score}.  ``candidates`` = index list
-    of admissible tails (default: all entities); ``tails`` then holds POSITIONS in that list."""
+    of admissible tails (default: all entities); ``tails`` then holds POSITIONS in that list.
+    ``method``: "tc" = tensor cores, counts taken in the GEMM epilogue (no score block); "tc_block" = tensor cores through
+    materialised 2,048-query score blocks (round 1); "simt" = fp32 FMA tiles."""
     lib = _lib.load()
     A = _prep(emb, heads, rel_table, rels, False)
     B = emb.detach().to(torch.float32)
@@ -136,6 +235,9 @@ def rank_true_tails(emb: torch.Tensor, rel_table: torch.Tensor, heads: torch.Ten
     greater = torch.empty(nq, dtype=torch.int32, device=A.device)
     equal = torch.empty(nq, dtype=torch.int32, device=A.device)
     if method == "tc" and nq > 0 and nb > 0 and A.size(1) % 4 == 0:
+        greater, equal = _rank_fused(A, B, cand, tails)
+        return greater.to(torch.int64) + 1, equal.to(torch.int64)
+    if method in ("tc", "tc_block") and nq > 0 and nb > 0 and A.size(1) % 4 == 0:
         Bext = _tc_candidates(B, cand, 1.0, 0.0)
         # queries per score block: at most _RANK_BLOCK, and at most ~1 GiB of scores for very large candidate sets
         qb = max(128, min(_RANK_BLOCK, (1 << 28) // max(Bext.size(0), 1) // 128 * 128))
@@ -145,8 +247,8 @@ def rank_true_tails(emb: torch.Tensor, rel_table: torch.Tensor, heads: torch.Ten
             _lib.check(lib.rgcn_rank_count(_ptr(S), S.stride(0), q1 - q0, nb, _ptr(tails[q0:q1]), None, _ptr(greater[q0:q1]),
                                            _ptr(equal[q0:q1]), _stream(A.device)), "rgcn_rank_count")
         return greater.to(torch.int64) + 1, equal.to(torch.int64)
-    if method not in ("tc", "simt"):
-        raise ValueError("method must be 'tc' (tensor cores) or 'simt' (fp32 FMA tiles)")
+    if method not in ("tc", "tc_block", "simt"):
+        raise ValueError("method must be 'tc' (tensor cores, fused count), 'tc_block' or 'simt' (fp32 FMA tiles)")
     thr = torch.empty(nq, dtype=torch.float32, device=A.device)
     _lib.check(lib.rgcn_allpairs_rank(_ptr(A), A.stride(0), nq, _ptr(B), B.stride(0), _ptr(cand), nb, A.size(1),
                                       _ptr(tails), _ptr(thr), _ptr(greater), _ptr(equal), _stream(A.device)),

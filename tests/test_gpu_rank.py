@@ -49,7 +49,7 @@ def test_score_all_tails_backward(pkg):
                                rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("method", ["tc", "simt"])
+@pytest.mark.parametrize("method", ["tc", "tc_block", "simt"])
 @pytest.mark.parametrize("N,d,B", [(30926, 128, 1024), (777, 64, 130), (30926, 256, 2500)])
 def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B, method):
     """rank = 1 + #greater must lie inside the oracle's [optimistic, pessimistic] bracket evaluated with an epsilon
@@ -74,7 +74,7 @@ def test_rank_true_tails_brackets_reference_rank(pkg, N, d, B, method):
     assert int(ties[0]) >= 1                          # the duplicate of the true tail is an exact tie
     # exactness against our own fp32 scores
     from primekg_rgcn_linkprediction_b200.rank import _prep, scores_from_rows
-    S = scores_from_rows(_prep(emb, heads, table, rels, False), emb, method=method)
+    S = scores_from_rows(_prep(emb, heads, table, rels, False), emb, method="simt" if method == "simt" else "tc")
     st = S.gather(1, tails.view(-1, 1))
     others = torch.ones_like(S, dtype=torch.bool)
     others.scatter_(1, tails.view(-1, 1), False)
@@ -100,3 +100,56 @@ def test_all_pairs_drug_disease_sweep(pkg, method):
     gotc = pkg.score_all_pairs(emb, drugs, diseases, cosine=True, method=method)
     wantc = O.cosine_allpairs_ref(emb, drugs, diseases)
     torch.testing.assert_close(gotc, wantc, rtol=1e-5, atol=1e-5 if method == "simt" else 2e-5)
+
+
+@pytest.mark.parametrize("cosine", [False, True])
+@pytest.mark.parametrize("k", [1, 10, 16])
+def test_fused_topk_matches_sorted_score_matrix(pkg, cosine, k):
+    """``topk_all_pairs`` (score block consumed in the GEMM epilogue) against a sort of the materialised tensor-core score
+    matrix: same values bit for bit, same candidates, ties broken by the lower position; BASELINE cfg4 shape."""
+    torch.manual_seed(4)
+    emb = torch.randn(30926, 128, device=DEV)
+    emb[7000] = emb[6000]                                # duplicate candidates => exact ties
+    drugs = torch.arange(5593, 11875, device=DEV)
+    diseases = torch.arange(0, 5593, device=DEV)
+    rel = torch.randn(128, device=DEV)
+    kw = dict(cosine=True) if cosine else dict(rel_vec=rel)
+    val, ids = pkg.topk_all_pairs(emb, diseases, drugs, k=k, **kw)
+    S = pkg.score_all_pairs(emb, diseases, drugs, **kw)
+    assert val.shape == (5593, k) and ids.shape == (5593, k)
+    # reference order: value descending, position ascending
+    order = torch.argsort(S, dim=1, descending=True, stable=True)[:, :k]
+    want_val = S.gather(1, order)
+    if k > 1:
+        assert torch.all(val[:, :-1] >= val[:, 1:])
+    if not cosine:
+        # DistMult: the sweep and the matrix are the same products in the same order => the same bits, and exact ties
+        # (the duplicated candidate) are broken like the stable sort: lower position first
+        assert torch.equal(val, want_val)
+        assert torch.equal(ids, drugs[order])
+    else:
+        # cosine: the matrix folds (s + 1) / 2 into the contraction, the fused form applies it to the accumulator
+        torch.testing.assert_close(val, want_val, rtol=0, atol=2e-6)
+        pos = ids - 5593
+        torch.testing.assert_close(S.gather(1, pos), val, rtol=0, atol=2e-6)      # the returned candidates carry these scores
+        assert bool(((pos[:, :-1] != pos[:, 1:]).all())) if k > 1 else True
+
+
+def test_fused_rank_matches_block_rank_at_evaluate_size(pkg):
+    """The ranking evaluation of src/evaluate.py:219-291 at its real size (15,372 test edges x 30,926 entities, d = 256):
+    counts taken in the epilogue == counts from materialised 2,048-query score blocks."""
+    torch.manual_seed(6)
+    N, d, nq = 30926, 256, 15372
+    emb = torch.randn(N, d, device=DEV)
+    table = torch.randn(3, d, device=DEV)
+    heads = torch.randint(0, N, (nq,), device=DEV)
+    tails = torch.randint(0, N, (nq,), device=DEV)
+    rels = torch.randint(0, 3, (nq,), device=DEV)
+    r1, t1 = pkg.rank_true_tails(emb, table, heads, rels, tails, method="tc")
+    r2, t2 = pkg.rank_true_tails(emb, table, heads, rels, tails, method="tc_block")
+    assert torch.equal(r1, r2) and torch.equal(t1, t2)
+    cand = torch.arange(5593, 11875, device=DEV)
+    tpos = torch.randint(0, cand.numel(), (500,), device=DEV)
+    r3, t3 = pkg.rank_true_tails(emb, table, heads[:500], rels[:500], tpos, candidates=cand, method="tc")
+    r4, t4 = pkg.rank_true_tails(emb, table, heads[:500], rels[:500], tpos, candidates=cand, method="tc_block")
+    assert torch.equal(r3, r4) and torch.equal(t3, t4)

@@ -15,7 +15,7 @@ from oracle import rgcn_ref as O
 def _header_symbols():
     src = open(os.path.join(ROOT, "include", "rgcn_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:int|size_t|int64_t)\s+(rgcn_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:int|size_t|int64_t|int32_t)\s+(rgcn_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_library_exports_every_header_symbol(lib_built):
