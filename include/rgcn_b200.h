@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 5
+#define RGCN_B200_ABI_VERSION 6
 
 enum {
   RGCN_OK = 0,
@@ -193,6 +193,12 @@ int64_t rgcn_aggregate_row_blocks(const rgcn_csr_t* g, int32_t d);
 int rgcn_aggregate_fwd_rows(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d, void* H, void* H_lo, int64_t ldh,
                             int32_t out_mode, const float* x_root, int64_t ld_x_root, int64_t row_begin, int64_t row_end,
                             int32_t hub_pass, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+/* The same walk over a BF16 feature matrix X16 [n_src, d] (the bf16-transform mode: half the gathered bytes; sums, means and
+ * hub partials stay fp32), written as the bf16 hi plane H_hi of the transform's operand; x_root16 (bf16 [n_rows, d]) is
+ * appended as block R.  Leading dimensions in elements, multiples of 8; d % 8 == 0. */
+int rgcn_aggregate_fwd_bf16(const rgcn_csr_t* g, const void* X16, int64_t ldx, int32_t d, void* H_hi, int64_t ldh,
+                            const void* x_root16, int64_t ld_x_root, int64_t row_begin, int64_t row_end, int32_t hub_pass,
+                            void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
                        const float* init, int64_t ld_init,
@@ -296,6 +302,10 @@ typedef struct rgcn_layer_fwd_args {
    * stream, joined before the call returns.  pipeline: 0 = the library decides (from 200,000 rows with peer outputs: every
    * chunk's transform is many waves long and has NVLink stores to hide; RGCN_PIPELINE=0/1 overrides), 1 = never, 2 = always. */
   void* w_planes; size_t w_planes_bytes; int32_t pipeline;
+  /* bf16-transform mode (mode 1, needs w_planes), all optional: x_bf16 = a bf16 copy of x (x_src == x_root, d_in % 8 == 0):
+   * the walk gathers IT (half the bytes of the dominant kernel; sums stay fp32);  out_bf16 = where to leave the bf16 copy
+   * of this layer's output for the next layer (d_out % 4 == 0). */
+  const void* x_bf16; int64_t ld_x_bf16; void* out_bf16; int64_t ld_out_bf16;
 } rgcn_layer_fwd_args;
 
 typedef struct rgcn_layer_bwd_args {
@@ -351,7 +361,9 @@ int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_nodes, int3
  * of the tcgen05 kernel (no transposed copy), rgcn_transform_dgrad_w as the K-major one; otherwise they are
  * rgcn_transform_fwd / rgcn_transform_dgrad.  dropout_counter (nullable) is advanced by the conversion kernel, as the
  * conversion inside rgcn_transform_fwd does.  row_offset: row of the layer's output that row 0 of this call is (the
- * fused dropout hashes the GLOBAL element index, so row-chunked calls of one layer draw one consistent mask). */
+ * fused dropout hashes the GLOBAL element index, so row-chunked calls of one layer draw one consistent mask).
+ * out_bf16 (nullable, [n_rows, ld_out_bf16] bf16): the same output rounded to bf16 — the gather source of the next layer
+ * in the bf16-transform mode (rgcn_aggregate_fwd_bf16). */
 size_t rgcn_weight_planes_bytes(int32_t K, int32_t d_out);
 int rgcn_prepare_weights(const float* W1, int32_t K1, const float* W2, int32_t K2, int32_t d_out, int32_t mode,
                          void* w_planes, unsigned long long* dropout_counter, rgcn_stream_t stream);
@@ -359,7 +371,7 @@ int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t lda, int32_
                          const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
                          int32_t mode, float dropout_p, uint32_t dropout_seed, const unsigned long long* dropout_counter,
                          int64_t row_offset, float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
-                         rgcn_stream_t stream);
+                         void* out_bf16, int64_t ld_out_bf16, rgcn_stream_t stream);
 int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const void* w_planes, int32_t K,
                            int64_t n_rows, float* gA, int64_t ldga, int32_t mode, rgcn_stream_t stream);
 

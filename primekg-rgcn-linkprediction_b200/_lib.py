@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgcn_b200.so")
 
-ABI_VERSION = 5          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
+ABI_VERSION = 6          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
 
 _lock = threading.Lock()
 _lib = None
@@ -41,7 +41,8 @@ class LayerFwdArgs(C.Structure):
                 ("A_hi", p), ("A_lo", p), ("lda", i64), ("out", p), ("ldo", i64),
                 ("peer_out_host", p), ("n_peer", i32), ("peer_row0", i64), ("peer_ld", i64),
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
-                ("w_planes", p), ("w_planes_bytes", sz), ("pipeline", i32)]
+                ("w_planes", p), ("w_planes_bytes", sz), ("pipeline", i32),
+                ("x_bf16", p), ("ld_x_bf16", i64), ("out_bf16", p), ("ld_out_bf16", i64)]
 
 
 class MaskedPlanesOut(C.Structure):
@@ -84,7 +85,8 @@ PROTOTYPES = {
     "rgcn_weight_planes_bytes": (sz, [i32, i32]),
     "rgcn_prepare_weights": (C.c_int, [p, i32, p, i32, i32, i32, p, p, p]),
     "rgcn_transform_fwd_w": (C.c_int, [p, p, i64, i32, p, p, i32, i64, i32, p, i64, i32, C.c_float, C.c_uint32, p, i64,
-                                       p, i32, i64, i64, p]),
+                                       p, i32, i64, i64, p, i64, p]),
+    "rgcn_aggregate_fwd_bf16": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, i64, i64, i32, p, sz, p]),
     "rgcn_transform_dgrad_w": (C.c_int, [p, p, i64, i32, p, i32, i64, p, i64, i32, p]),
     "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
     "rgcn_rows_compact_size": (i64, [i64]),

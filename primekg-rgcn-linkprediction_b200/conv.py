@@ -55,7 +55,20 @@ class _RGCNLayerFn(torch.autograd.Function):
             raise ValueError(f"x has {x_root.size(0)} rows, the graph updates {graph.n_dst}")
         # drop = (p, seed, device counter): ReLU + dropout fused into the GEMM epilogue (reference :124-125)
         p_drop, seed, ctr = drop if drop is not None else (0.0, 0, None)
-        out, A, wp = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr)
+        # bf16-transform mode: the walk gathers a bf16 copy of x — left by the previous layer's epilogue (hand-over in
+        # rowsparse.py) or made here (the embedding table) — and a ReLU layer leaves the copy of ITS output for the next one
+        x16 = None
+        use16 = mode == "bf16" and shared and ops.bf16_gather() and ops.prepared_weights()
+        if use16 and d_in % 8 == 0:
+            x16 = rowsparse.claim_bf16(x_src)
+            if x16 is None:
+                x16 = ops.to_bf16(x_src.detach())
+        want16 = bool(use16 and relu and d_out % 8 == 0)
+        res = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr,
+                            x_bf16=x16, want_out_bf16=want16)
+        out, A, wp = res[:3]
+        if want16 and res[3] is not None:
+            rowsparse.announce_bf16(out, res[3])
         ctx.graph, ctx.relu, ctx.mode, ctx.shared, ctx.p_drop = graph, relu, mode, shared, p_drop
         ctx.w_planes = wp               # the weights as bf16 planes (converted once): the backward's dgrad reads them
         # in_mask_scale: x is the fused ReLU (+ dropout) output of the layer upstream, whose backward will want this

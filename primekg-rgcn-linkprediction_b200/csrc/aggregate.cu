@@ -629,6 +629,214 @@ __global__ void __launch_bounds__(256) hub_finish_kernel(const AggParams p) {
   }
 }
 
+// ---- bf16 features (the "bf16-transform" mode gathers a bf16 copy of the layer input: half the L2 / HBM bytes of the
+// dominant kernel; sums, means and hub partials stay fp32) -------------------------------------------------------------
+// Forward, unmixed form only.  A lane holds VPL vectors of EIGHT columns (one 128-bit load = 8 bf16), so a 256-wide row is
+// one load per lane; the result goes straight into the bf16 hi plane of the transform's operand (16-byte stores).
+struct f8 { float v[8]; };
+__device__ __forceinline__ void ld_bf8(const __nv_bfloat16* p, uint4& raw) { raw = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void acc_bf8(f8& a, const uint4& r) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unsigned long long acc2 = pack2(a.v[2 * i], a.v[2 * i + 1]);
+    const unsigned long long x2 = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2) : "l"(x2));
+    unpack2(acc2, a.v[2 * i], a.v[2 * i + 1]);
+  }
+}
+__device__ __forceinline__ uint4 pack_bf8(const f8& a) {
+  uint4 o;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(a.v[0], a.v[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(a.v[2], a.v[3]); o.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(a.v[4], a.v[5]); o.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(a.v[6], a.v[7]); o.w = *reinterpret_cast<uint32_t*>(&t);
+  return o;
+}
+
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) hub_partial_bf16_kernel(const AggParams p) {
+  pdl_enter();
+  constexpr int GROUPS = 256 / G;
+  __shared__ float red[GROUPS][G * VPL * 8];
+  const __nv_bfloat16* __restrict__ F = reinterpret_cast<const __nv_bfloat16*>(p.F);
+  const int chunk = blockIdx.x;
+  const int4 t = __ldg(reinterpret_cast<const int4*>(p.chunk_table) + chunk);
+  const int key = t.x;
+  const int seg_beg = __ldg(p.rowptr + key), seg_end = __ldg(p.rowptr + key + 1);
+  const int c_beg = seg_beg + (chunk - t.y) * kHubChunk;
+  const int c_end = min(c_beg + kHubChunk, seg_end);
+  const int nvec = p.d >> 3;
+  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+  constexpr int PER = kHubChunk / GROUPS;
+  const int g_beg = c_beg + grp * PER, g_end = min(g_beg + PER, c_end);
+  f8 acc[VPL];
+  int vcol[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[k].v[i] = 0.f;
+    const int vi = k * G + lane;
+    vcol[k] = vi < nvec ? vi * 8 : 0;
+  }
+  constexpr int U0 = VPL >= 2 ? 4 : 8;
+  constexpr int U = U0 < PER ? U0 : PER;
+  int e = g_beg;
+  for (; e + U <= g_end; e += U) {
+    uint4 v[U][VPL];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = __ldg(p.idx + e + u);
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) ld_bf8(F + (size_t)j * p.ldf + vcol[k], v[u][k]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) acc_bf8(acc[k], v[u][k]);
+  }
+  for (; e < g_end; ++e) {
+    const int j = __ldg(p.idx + e);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) { uint4 r; ld_bf8(F + (size_t)j * p.ldf + vcol[k], r); acc_bf8(acc[k], r); }
+  }
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[grp][(k * G + lane) * 8 + i] = acc[k].v[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.d; c += 256) {
+    float sum = red[0][c];
+    for (int g = 1; g < GROUPS; ++g) sum += red[g][c];       // fixed order over the groups
+    p.partials[(size_t)chunk * p.d + c] = sum;
+  }
+}
+
+template <int G, int VPL>
+__global__ void __launch_bounds__(256, (VPL == 1 ? 4 : 3)) aggregate_rows_bf16_kernel(const AggParams p) {
+  pdl_enter();
+  constexpr int GROUPS = 256 / G;
+  constexpr int U0 = VPL >= 2 ? 4 : 8;
+  constexpr int U = U0 < G ? U0 : G;
+  const __nv_bfloat16* __restrict__ F = reinterpret_cast<const __nv_bfloat16*>(p.F);
+  __nv_bfloat16* __restrict__ O = reinterpret_cast<__nv_bfloat16*>(p.O);
+  const int lane = threadIdx.x % G, grp = threadIdx.x / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  int64_t row = p.row_begin + (int64_t)blockIdx.x * GROUPS + grp;
+  if (row >= p.row_end) return;
+  if (p.row_order) row = __ldg(p.row_order + row);
+  const int R = p.R, d = p.d, nvec = p.d >> 3;
+  const int64_t key0 = row * R;
+  const int32_t* __restrict__ rowptr = p.rowptr + key0;
+  const int32_t* __restrict__ idx = p.idx;
+  const int64_t ldf = p.ldf;
+  bool act[VPL];
+  int vcol[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = k * G + lane;
+    act[k] = vi < nvec;
+    vcol[k] = act[k] ? vi * 8 : 0;
+  }
+  if (p.root_rows) {                                  // self-loop block: the bf16 copy of x[row] as it is
+    const __nv_bfloat16* __restrict__ xr = reinterpret_cast<const __nv_bfloat16*>(p.root_rows) + row * p.ld_root;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (act[k]) *reinterpret_cast<uint4*>(O + row * p.ldo + R * p.block_stride + vcol[k]) = __ldg(reinterpret_cast<const uint4*>(xr + vcol[k]));
+  }
+  const int row_end = __ldg(rowptr + R);
+  int wbase = -(1 << 30), wi0 = 0, wi1 = 0;
+  auto refill = [&](int e) {
+    wbase = e;
+    wi0 = (e + lane < row_end) ? __ldg(idx + e + lane) : 0;
+    wi1 = (e + G + lane < row_end) ? __ldg(idx + e + G + lane) : 0;
+  };
+  for (int rbase = 0; rbase < R; rbase += G) {
+    const int rl = rbase + lane;
+    const int my_beg = (rl < R) ? __ldg(rowptr + rl) : 0;
+    const int my_end = (rl < R) ? __ldg(rowptr + rl + 1) : 0;
+    const int rcount = min(G, R - rbase);
+    for (int rr = 0; rr < rcount; ++rr) {
+      const int r = rbase + rr;
+      const int beg = __shfl_sync(gmask, my_beg, rr, G);
+      const int end = __shfl_sync(gmask, my_end, rr, G);
+      const int len = end - beg;
+      f8 acc[VPL];
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k].v[i] = 0.f;
+      if (len > p.hub_threshold) {
+        const int key = (int)(key0 + r);
+        int lo = 0, hi = p.n_hubs;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(p.hub_keys + mid) <= key) lo = mid; else hi = mid;
+        }
+        const int c0 = __ldg(p.hub_chunk_ptr + lo), c1 = __ldg(p.hub_chunk_ptr + lo + 1);
+        for (int c = c0; c < c1; ++c) {               // chunk partials (fp32), strictly in chunk order
+#pragma unroll
+          for (int k = 0; k < VPL; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k]);
+            const float4 b = *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vcol[k] + 4);
+            acc[k].v[0] += a.x; acc[k].v[1] += a.y; acc[k].v[2] += a.z; acc[k].v[3] += a.w;
+            acc[k].v[4] += b.x; acc[k].v[5] += b.y; acc[k].v[6] += b.z; acc[k].v[7] += b.w;
+          }
+        }
+      } else if (len > 0) {
+        int e = beg;
+        auto batch = [&](auto ub) {
+          constexpr int UB = decltype(ub)::value;
+          if (e + UB > wbase + 2 * G) refill(e);
+          uint4 v[UB][VPL];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int off = e + u - wbase;
+            const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) ld_bf8(F + (size_t)j * ldf + vcol[k], v[u][k]);
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u)
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) acc_bf8(acc[k], v[u][k]);
+          e += UB;
+        };
+        while (e + U <= end) batch(std::integral_constant<int, U>{});
+        if (U > 4 && e + 4 <= end) batch(std::integral_constant<int, (U > 4 ? 4 : 1)>{});
+        if (U > 2 && e + 2 <= end) batch(std::integral_constant<int, (U > 2 ? 2 : 1)>{});
+        if (e < end) batch(std::integral_constant<int, 1>{});
+      }
+      if (len > 1) {
+        const float c = (float)len;                   // s / clamp(cnt, 1): a true division, like the reference
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[k].v[i] = acc[k].v[i] / c;
+      }
+#pragma unroll
+      for (int k = 0; k < VPL; ++k)
+        if (act[k]) *reinterpret_cast<uint4*>(O + row * p.ldo + r * p.block_stride + vcol[k]) = pack_bf8(acc[k]);
+    }
+  }
+}
+
+template <int G, int VPL>
+static int launch_agg_bf16(AggParams p, int n_chunks, cudaStream_t st) {
+  constexpr int GROUPS = 256 / G;
+  if (!p.range_mode) { p.row_begin = 0; p.row_end = p.n_rows; }
+  if (n_chunks > 0 && !p.no_hub_pass) {
+    RGCN_CUDA(launch_pdl(hub_partial_bf16_kernel<G, VPL>, dim3(n_chunks), dim3(256), 0, st, p));
+    RGCN_LAUNCH_CHECK();
+  }
+  const int64_t n_walk = p.row_end - p.row_begin;
+  if (n_walk <= 0) return RGCN_OK;
+  RGCN_CUDA(launch_pdl(aggregate_rows_bf16_kernel<G, VPL>, dim3((unsigned)((n_walk + GROUPS - 1) / GROUPS)), dim3(256), 0, st, p));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
 // side stream + events for the fork / join of the hub pass (one set per device, created on first use)
 struct ForkJoin {
   cudaStream_t side = nullptr;
@@ -871,6 +1079,45 @@ extern "C" int rgcn_aggregate_fwd_rows(const rgcn_csr_t* g, const float* X, int6
   p.range_mode = 1; p.row_begin = row_begin; p.row_end = row_end; p.no_hub_pass = hub_pass ? 0 : 1;
   if (row_end == row_begin && !hub_pass) return RGCN_OK;            // (an empty range with hub_pass = the hub pass alone)
   return dispatch_agg(p, MIX_NONE, g->n_chunks, (cudaStream_t)stream);
+}
+
+// bf16 features -> bf16 hi plane (the bf16-transform mode): X16 [n_src, d] and x_root16 [n_rows, d] are bf16 matrices
+// (leading dimensions in ELEMENTS, multiples of 8, 16-byte aligned rows); H_hi as in out_mode 1.  Row range / hub_pass as in
+// rgcn_aggregate_fwd_rows (row_begin = 0, row_end = n_rows, hub_pass = 1: everything).
+extern "C" int rgcn_aggregate_fwd_bf16(const rgcn_csr_t* g, const void* X16, int64_t ldx, int32_t d, void* H_hi, int64_t ldh,
+                                       const void* x_root16, int64_t ld_x_root, int64_t row_begin, int64_t row_end,
+                                       int32_t hub_pass, void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(g && g->rowptr && (g->idx || g->E == 0) && g->R >= 1 && g->n_rows >= 0 && g->hub_threshold >= 1, "aggregate_fwd_bf16: bad CSR");
+  RGCN_CHECK_ARG(d >= 8 && d <= 1024 && d % 8 == 0, "aggregate_fwd_bf16: d=%d must be a multiple of 8 in [8, 1024]", d);
+  RGCN_CHECK_ARG(X16 && ((uintptr_t)X16 & 15) == 0 && ldx % 8 == 0, "aggregate_fwd_bf16: features must be 16-byte aligned rows");
+  RGCN_CHECK_ARG(H_hi && ((uintptr_t)H_hi & 15) == 0 && ldh % 8 == 0, "aggregate_fwd_bf16: output plane must be 16-byte aligned, ld %% 8 == 0");
+  RGCN_CHECK_ARG(!x_root16 || (((uintptr_t)x_root16 & 15) == 0 && ld_x_root % 8 == 0), "aggregate_fwd_bf16: x_root misaligned");
+  RGCN_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= g->n_rows, "aggregate_fwd_bf16: bad row range");
+  RGCN_CHECK_ARG(g->n_chunks == 0 || (g->hub_keys && g->hub_chunk_ptr && g->n_hubs > 0 && g->chunk_table), "aggregate_fwd_bf16: hub plan missing");
+  if (g->n_chunks > 0 && (!workspace || workspace_bytes < (size_t)g->n_chunks * d * sizeof(float))) {
+    set_error("aggregate_fwd_bf16: workspace too small"); return RGCN_EWORKSPACE;
+  }
+  const bool whole = row_begin == 0 && row_end == g->n_rows;
+  RGCN_CHECK_ARG(whole || !g->row_order || (g->order_chunk_rows > 0 && row_begin % g->order_chunk_rows == 0 &&
+                                            (row_end % g->order_chunk_rows == 0 || row_end == g->n_rows)),
+                 "aggregate_fwd_bf16: with a row order the range must consist of whole order chunks");
+  AggParams p{};
+  p.rowptr = g->rowptr; p.idx = g->idx;
+  p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs; p.chunk_table = g->chunk_table;
+  p.row_order = g->row_order; p.hub_threshold = g->hub_threshold;
+  p.n_rows = g->n_rows; p.R = g->R;
+  p.F = (const float*)X16; p.ldf = ldx; p.d = d; p.block_stride = d;
+  p.O = H_hi; p.ldo = ldh; p.out_mode = 1; p.partials = (float*)workspace;
+  p.root_rows = (const float*)x_root16; p.ld_root = ld_x_root;
+  p.range_mode = 1; p.row_begin = row_begin; p.row_end = row_end; p.no_hub_pass = hub_pass ? 0 : 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nvec = d >> 3;
+  if (nvec <= 4) return launch_agg_bf16<4, 1>(p, g->n_chunks, st);
+  if (nvec <= 8) return launch_agg_bf16<8, 1>(p, g->n_chunks, st);
+  if (nvec <= 16) return launch_agg_bf16<16, 1>(p, g->n_chunks, st);
+  if (nvec <= 32) return launch_agg_bf16<32, 1>(p, g->n_chunks, st);
+  if (nvec <= 64) return launch_agg_bf16<32, 2>(p, g->n_chunks, st);
+  return launch_agg_bf16<32, 4>(p, g->n_chunks, st);
 }
 
 static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,

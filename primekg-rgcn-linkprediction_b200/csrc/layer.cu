@@ -150,30 +150,40 @@ extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream
   auto transform = [&](int64_t r0, int64_t r1, rgcn_stream_t s) {
     const char* hi = (const char*)a->A_hi + (size_t)r0 * a->lda * 2;
     const char* lo = A_lo ? (const char*)A_lo + (size_t)r0 * a->lda * 2 : nullptr;
+    void* o16 = a->out_bf16 ? (void*)((char*)a->out_bf16 + (size_t)r0 * a->ld_out_bf16 * 2) : nullptr;
     return rgcn_transform_fwd_w(hi, lo, a->lda, K, a->w_planes, a->bias, a->relu, r1 - r0, a->d_out, a->out + r0 * a->ldo,
                                 a->ldo, a->mode, a->dropout_p, a->dropout_seed, a->dropout_counter, r0, a->peer_out_host,
-                                a->n_peer, a->peer_row0 + r0, a->peer_ld, s);
+                                a->n_peer, a->peer_row0 + r0, a->peer_ld, o16, a->ld_out_bf16, s);
+  };
+  // bf16-transform mode with a bf16 copy of the input: the walk gathers the copy
+  const bool g16 = a->mode == 1 && a->x_bf16 && a->d_in % 8 == 0 && a->lda % 8 == 0 && a->x_src == a->x_root;
+  auto walk = [&](int64_t r0, int64_t r1, int hub_pass, bool whole) {
+    if (g16)
+      return rgcn_aggregate_fwd_bf16(a->csr, a->x_bf16, a->ld_x_bf16, a->d_in, a->A_hi, a->lda, a->x_bf16, a->ld_x_bf16, r0, r1,
+                                     hub_pass, a->agg_workspace, a->agg_workspace_bytes, stream);
+    if (whole)
+      return rgcn_aggregate_fwd(a->csr, a->x_src, a->ld_x_src, a->d_in, nullptr, 0, a->A_hi, A_lo, a->lda, out_mode, nullptr, 0,
+                                nullptr, a->x_root, a->ld_x_root, a->agg_workspace, a->agg_workspace_bytes, stream);
+    return rgcn_aggregate_fwd_rows(a->csr, a->x_src, a->ld_x_src, a->d_in, a->A_hi, A_lo, a->lda, out_mode, a->x_root,
+                                   a->ld_x_root, r0, r1, hub_pass, a->agg_workspace, a->agg_workspace_bytes, stream);
   };
   SideStream* ss = nullptr;
   const int64_t chunk = pipeline_chunk_rows(a->csr);
   if (chunk <= 0 || n < 2 * chunk || !pipeline_mode(a, st, &ss)) {
-    rc = rgcn_aggregate_fwd(a->csr, a->x_src, a->ld_x_src, a->d_in, nullptr, 0, a->A_hi, A_lo, a->lda, out_mode, nullptr, 0,
-                            nullptr, a->x_root, a->ld_x_root, a->agg_workspace, a->agg_workspace_bytes, stream);
+    rc = walk(0, n, 1, true);
     if (rc) return rc;
     return transform(0, n, stream);
   }
   // hub chunks first (all rows' hub segments), then chunk by chunk
   if (a->csr->n_chunks > 0) {
-    rc = rgcn_aggregate_fwd_rows(a->csr, a->x_src, a->ld_x_src, a->d_in, a->A_hi, A_lo, a->lda, out_mode, a->x_root, a->ld_x_root,
-                                 0, 0, 1, a->agg_workspace, a->agg_workspace_bytes, stream);
+    rc = walk(0, 0, 1, false);
     if (rc) return rc;
   }
   RGCN_CUDA(cudaEventRecord(ss->fork, st));
   RGCN_CUDA(cudaStreamWaitEvent(ss->side, ss->fork, 0));
   for (int64_t r0 = 0; r0 < n; r0 += chunk) {
     const int64_t r1 = r0 + chunk < n ? r0 + chunk : n;
-    rc = rgcn_aggregate_fwd_rows(a->csr, a->x_src, a->ld_x_src, a->d_in, a->A_hi, A_lo, a->lda, out_mode, a->x_root, a->ld_x_root,
-                                 r0, r1, 0, a->agg_workspace, a->agg_workspace_bytes, stream);
+    rc = walk(r0, r1, 0, false);
     if (rc) return rc;
     if (r1 < n) {
       RGCN_CUDA(cudaEventRecord(ss->fork, st));

@@ -156,6 +156,8 @@ struct GemmKParams {
   int num_kb;                                 // K blocks of 64 (TMA zero-fills past the true K)
   const float* bias; int relu;
   float* out; int64_t ldo;
+  __nv_bfloat16* out16; int64_t ldo16;        // optional second output: the same values rounded to bf16 (the next layer's
+                                              // gather source in the bf16-transform mode)
   // fused dropout after the ReLU (training): keep iff drop_bits(...) >= drop_thresh, kept values times drop_scale
   uint32_t drop_thresh; float drop_scale; uint32_t drop_seed; const unsigned long long* drop_ctr;
   int64_t row_offset;                         // row of the layer's output that local row 0 is (row-chunked calls): dropout index
@@ -167,6 +169,7 @@ struct GemmKParams {
   const float* thr_in; float* thr_out;        // EPI_RANK: per-row threshold;  EPI_THR: out[row] = acc[row, row]
   const int64_t* true_pos; int32_t* greater; int32_t* equal;
   float alpha, beta;                          // EPI_TOPK: reported value = alpha * acc + beta (alpha > 0)
+  int topk;                                   // entries actually wanted (<= kTopK): the insertion threshold is the topk-th best
   float* cand_val; int32_t* cand_idx; int32_t* slot_ctr; int32_t n_slots;    // [M, n_slots, kTopK] partial lists, [M] counters
   // fused all-gather: every output tile is also stored into the same-shaped slot (rows peer_row0 ...) of up to
   // kMaxPeers feature buffers that live in OTHER GPUs' memory (peer-mapped, NVLink stores issued by the epilogue)
@@ -269,7 +272,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // per-row state of the consuming epilogues (one row per lane)
     int64_t cur_m0 = -1;
     int cnt_g = 0, cnt_e = 0;
-    float thr = 0.f;
+    float thr = 0.f, kth = -INFINITY;
     int64_t tpos = -1;
     float topv[EPI == EPI_TOPK ? kTopK : 1];
     int topi[EPI == EPI_TOPK ? kTopK : 1];
@@ -307,6 +310,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (EPI == EPI_TOPK) {
 #pragma unroll
           for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) { topv[i] = -INFINITY; topi[i] = -1; }
+          kth = -INFINITY;
         }
       }
       mbar_wait(&tfull_bar[a], (uint32_t)((iter >> 1) & 1));
@@ -334,11 +338,16 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               if (j == want) v = __uint_as_float(r[j]);
             if (want >= 0 && want < 16 && row < p.M) p.thr_out[row] = v;
           } else {
+            // most 16-column chunks hold nothing above the row's current threshold: one max per chunk, then skip
+            float cmax = __uint_as_float(r[0]);
+#pragma unroll
+            for (int j = 1; j < 16; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
+            if (!__any_sync(0xffffffffu, cmax > kth && row < p.M)) continue;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = n0 + cc + j;
               float v = __uint_as_float(r[j]);
-              if (row < p.M && col < p.n_cols_valid && v > topv[(EPI == EPI_TOPK ? kTopK : 1) - 1]) {
+              if (row < p.M && col < p.n_cols_valid && v > kth) {
                 int ci = col;                                // insertion into the descending list (columns arrive in
 #pragma unroll                                               // ascending order: an equal value keeps the earlier one first)
                 for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) {
@@ -347,6 +356,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     topv[i] = v; topi[i] = ci; v = tv; ci = ti;
                   }
                 }
+                kth = -INFINITY;                             // the topk-th best so far (static register indexing)
+#pragma unroll
+                for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i)
+                  if (i == p.topk - 1) kth = topv[i];
               }
             }
           }
@@ -383,6 +396,13 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               v.w = (h1 >> 16) >= p.drop_thresh ? v.w * p.drop_scale : 0.f;
             }
             *reinterpret_cast<float4*>(p.out + row * p.ldo + n0 + cc + c4) = v;
+            if (p.out16) {
+              __nv_bfloat162 b01 = __floats2bfloat162_rn(v.x, v.y), b23 = __floats2bfloat162_rn(v.z, v.w);
+              uint2 o;
+              o.x = *reinterpret_cast<uint32_t*>(&b01);
+              o.y = *reinterpret_cast<uint32_t*>(&b23);
+              *reinterpret_cast<uint2*>(p.out16 + row * p.ldo16 + n0 + cc + c4) = o;
+            }
             for (int q = 0; q < p.n_peer; ++q)
               *reinterpret_cast<float4*>(p.peer_out[q] + (p.peer_row0 + row) * p.peer_ld + n0 + cc + c4) = v;
           }
@@ -1092,9 +1112,10 @@ extern "C" int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t 
                                     int32_t mode, float dropout_p, uint32_t dropout_seed,
                                     const unsigned long long* dropout_counter, int64_t row_offset,
                                     float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
-                                    rgcn_stream_t stream) {
+                                    void* out_bf16, int64_t ld_out_bf16, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(n_peer >= 0 && n_peer <= kMaxPeers && (n_peer == 0 || (peer_out_host && peer_ld % 4 == 0 && peer_row0 >= 0)),
                  "transform_fwd_w: bad peer outputs (at most %d, ld %% 4 == 0)", kMaxPeers);
+  RGCN_CHECK_ARG(!out_bf16 || (((uintptr_t)out_bf16 & 7) == 0 && ld_out_bf16 % 4 == 0), "transform_fwd_w: bf16 output misaligned");
   RGCN_CHECK_ARG(n_rows >= 0 && n_rows < (1ll << 31) && K > 0 && K % 4 == 0 && d_out > 0 && d_out % 4 == 0, "transform_fwd_w: bad sizes");
   RGCN_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || (dropout_counter && relu)),
                  "transform_fwd_w: dropout_p in [0, 1), fused dropout needs relu = 1 and a counter");
@@ -1105,12 +1126,15 @@ extern "C" int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t 
   RGCN_CHECK_ARG(out && ((uintptr_t)out & 15) == 0 && ldo % 4 == 0, "transform_fwd_w: out must be 16-byte aligned, ld %% 4 == 0");
   RGCN_CHECK_ARG(!bias || d_out <= 1024, "transform_fwd_w: bias needs d_out <= 1024");
   if (n_rows == 0) return RGCN_OK;
-  const Tiling t = tile_n(d_out, 32, d_out > KBN ? wide_bn() : KBN);
+  // measured (scripts/ab_gemm.py, 30,926 x 1,024 x 256): 256-wide tiles win with one product per k-step (4-stage ring:
+  // 34.3 against 36.9 us) and lose with three (2-stage ring: 63.5 against 57.4 us)
+  const Tiling t = tile_n(d_out, 32, (d_out > KBN && mode == 1) ? wide_bn() : KBN);
   const __nv_bfloat16* bhi = (const __nv_bfloat16*)w_planes;
   const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)w_planes + wplane_bytes(K, d_out));
   GemmKParams p{};
   p.M = n_rows; p.N = d_out; p.BN = t.BN; p.num_kb = round_up(K, BK) / BK;
   p.bias = bias; p.relu = relu; p.out = out; p.ldo = ldo; p.row_offset = row_offset;
+  p.out16 = (__nv_bfloat16*)out_bf16; p.ldo16 = ld_out_bf16;
   if (dropout_p > 0.f) {
     const double th = (double)dropout_p * 65536.0 + 0.5;
     p.drop_thresh = th >= 65535.0 ? 65535u : (th < 1.0 ? 1u : (uint32_t)th);
@@ -1271,7 +1295,7 @@ extern "C" int rgcn_scores_topk_w(const void* Q_hi, const void* Q_lo, int64_t ld
   cudaStream_t st = (cudaStream_t)stream;
   RGCN_CUDA(cudaMemsetAsync(slot_ctr, 0, (size_t)n_q * sizeof(int32_t), st));
   p.N = (int)n_cand; p.n_cols_valid = n_cand; p.tile_contig = 1;
-  p.alpha = alpha; p.beta = beta; p.cand_val = cand_val; p.cand_idx = cand_idx; p.slot_ctr = slot_ctr; p.n_slots = n_slots;
+  p.alpha = alpha; p.beta = beta; p.topk = k; p.cand_val = cand_val; p.cand_idx = cand_idx; p.slot_ctr = slot_ctr; p.n_slots = n_slots;
   const int n_tiles = (int)((n_cand + KBN - 1) / KBN);
   const __nv_bfloat16* bhi = (const __nv_bfloat16*)cand_planes;
   const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)cand_planes + wplane_bytes((int)n_cand, d));

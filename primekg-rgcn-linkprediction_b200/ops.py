@@ -399,7 +399,8 @@ def prepare_weights(W1: torch.Tensor, W2: Optional[torch.Tensor], mode: str, dro
 
 def transform_fwd_w(planes, K: int, w_planes: torch.Tensor, d_out: int, bias: Optional[torch.Tensor], relu: bool, mode: str,
                     dropout_p: float = 0.0, dropout_seed: int = 0, dropout_ctr: Optional[torch.Tensor] = None,
-                    row_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    row_offset: int = 0, out: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None
+                    ) -> torch.Tensor:
     """out = A @ W + bias (, ReLU (, dropout)) with the weights already converted (``prepare_weights``): the tcgen05 kernel
     alone, B read MN-major.  ``row_offset``: global row of A's row 0 (row-chunked calls draw one consistent dropout mask)."""
     lib = _lib.load()
@@ -412,7 +413,8 @@ def transform_fwd_w(planes, K: int, w_planes: torch.Tensor, d_out: int, bias: Op
     _lib.check(lib.rgcn_transform_fwd_w(_ptr(hi), _ptr(lo), hi.stride(0), K, _ptr(w_planes), _ptr(bias), int(relu), n, d_out,
                                         _ptr(out), out.stride(0), _mode_id(mode), float(dropout_p),
                                         int(dropout_seed) & 0xFFFFFFFF, _ptr(dropout_ctr if dropout_p > 0 else None),
-                                        int(row_offset), None, 0, 0, 0, _stream(hi.device)), "rgcn_transform_fwd_w")
+                                        int(row_offset), None, 0, 0, 0, _ptr(out_bf16),
+                                        0 if out_bf16 is None else out_bf16.stride(0), _stream(hi.device)), "rgcn_transform_fwd_w")
     return out
 
 
@@ -467,6 +469,20 @@ _WS_BYTES = {}
 _WP_BYTES = {}
 
 
+def bf16_gather() -> bool:
+    """bf16-transform mode: gather a bf16 copy of the layer input (``PRIMEKG_RGCN_BF16_GATHER=0``: gather fp32 as round 1)."""
+    import os
+    return os.environ.get("PRIMEKG_RGCN_BF16_GATHER", "1") != "0"
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of an fp32 matrix by our conversion kernel (row stride padded to a multiple of 8)."""
+    x = _f32c(x, "x")
+    hi, _ = alloc_planes(x.size(0), x.size(1), "bf16", x.device)
+    split_planes(x, (hi, None))
+    return hi
+
+
 def prepared_weights() -> bool:
     """Weights converted once per layer call and shared by forward and dgrad (``PRIMEKG_RGCN_PREPARED_WEIGHTS=0``: the
     round-1 form, one conversion per GEMM)."""
@@ -497,8 +513,10 @@ def _dp(t: Optional[torch.Tensor]):
 def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch.Tensor, root: torch.Tensor,
               bias: torch.Tensor, relu: bool, mode: str, dropout_p: float = 0.0, dropout_seed: int = 0,
               dropout_ctr: Optional[torch.Tensor] = None, peer_out=None, peer_row0: int = 0, peer_ld: int = 0,
-              pipeline: int = 0):
+              pipeline: int = 0, x_bf16: Optional[torch.Tensor] = None, want_out_bf16: bool = False):
     """aggregate -> operand planes -> tensor-core transform of one layer in ONE C call (``rgcn_layer_fwd``).
+    bf16 mode: ``x_bf16`` = a bf16 copy of x (the walk gathers it: half the bytes); ``want_out_bf16``: also return the
+    layer output rounded to bf16 as a fourth result (the next layer's ``x_bf16``).
     Returns (out [n_dst, d_out], (A_hi, A_lo | None), w_planes | None): ``w_planes`` = the layer's weights as bf16 planes,
     converted once by the call; hand it to ``layer_bwd`` (its dgrad then skips the conversion).
     ``pipeline``: 0 = the library decides whether the walk of row chunk c + 1 runs under the transform of chunk c (from
@@ -525,14 +543,22 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
     peers = _ptr_array(peer_out) if peer_out else None
     # the layer's weights as bf16 planes, converted once by the call and kept for the backward's dgrad
     wp = torch.empty(weight_planes_bytes(K, d_out), dtype=torch.uint8, device=dev) if prepared_weights() else None
+    use16 = mode == "bf16" and wp is not None and x_root is x_src
+    if x_bf16 is not None and (not use16 or x_bf16.dtype != torch.bfloat16 or x_bf16.shape != x_src.shape or d_in % 8
+                               or x_bf16.stride(1) != 1 or x_bf16.stride(0) % 8 or x_bf16.data_ptr() % 16):
+        x_bf16 = None
+    out16 = torch.empty(g.n_dst, d_out, dtype=torch.bfloat16, device=dev) if (want_out_bf16 and use16) else None
     args = _lib.LayerFwdArgs(
         g.fwd.ptr, x_src.data_ptr(), x_src.stride(0), x_root.data_ptr(), x_root.stride(0), d_in, d_out, int(relu),
         _mode_id(mode), W2d.data_ptr(), root.data_ptr(), bias.data_ptr(), float(dropout_p), int(dropout_seed) & 0xFFFFFFFF,
         _dp(dropout_ctr) if dropout_p > 0 else None, A[0].data_ptr(), _dp(A[1]), A[0].stride(0), out.data_ptr(),
         out.stride(0), C.cast(peers, C.c_void_p) if peers is not None else None, len(peer_out) if peer_out else 0,
         int(peer_row0), int(peer_ld), _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel(),
-        _dp(wp), 0 if wp is None else wp.numel(), int(pipeline))
+        _dp(wp), 0 if wp is None else wp.numel(), int(pipeline),
+        _dp(x_bf16), 0 if x_bf16 is None else x_bf16.stride(0), _dp(out16), 0 if out16 is None else out16.stride(0))
     _lib.check(lib.rgcn_layer_fwd(C.byref(args), _stream(dev)), "rgcn_layer_fwd")
+    if want_out_bf16:
+        return out, A, wp, out16
     return out, A, wp
 
 

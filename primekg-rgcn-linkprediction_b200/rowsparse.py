@@ -84,7 +84,30 @@ def claim_planes(grad: torch.Tensor, mask: Optional[torch.Tensor], scale: float,
     return payload if ok else None
 
 
+# ---- third hand-over (forward): a layer's transform has also left its output rounded to bf16; the next layer's walk
+#      gathers that copy (bf16-transform mode) ----
+_bf16 = None            # (output tensor, version, bf16 copy)
+
+
+def announce_bf16(out: torch.Tensor, out16: torch.Tensor) -> None:
+    global _bf16
+    _bf16 = (out, out._version, out16)
+
+
+def claim_bf16(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """The announced bf16 copy if ``x`` is the announced tensor, untouched; consumed by the first attempt."""
+    global _bf16
+    a, _bf16 = _bf16, None
+    if a is None:
+        return None
+    out, version, out16 = a
+    ok = (x.data_ptr() == out.data_ptr() and x.shape == out.shape and x.stride() == out.stride() and x._version == version
+          and out._version == version)
+    return out16 if ok else None
+
+
 def clear() -> None:
-    global _announced, _planes
+    global _announced, _planes, _bf16
     _announced = None
     _planes = None
+    _bf16 = None

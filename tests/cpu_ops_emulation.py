@@ -64,8 +64,8 @@ def aggregate_bwd(g, gH, d, init=None):
 
 
 def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, dropout_seed=0, dropout_ctr=None,
-              peer_out=None, peer_row0=0, peer_ld=0, pipeline=0):
-    assert not peer_out
+              peer_out=None, peer_row0=0, peer_ld=0, pipeline=0, x_bf16=None, want_out_bf16=False):
+    assert not peer_out and not want_out_bf16
     d_in = x_src.size(1)
     K1 = g.R * d_in
     A = alloc_planes(g.n_dst, K1 + d_in, mode, None)

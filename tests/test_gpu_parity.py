@@ -1556,3 +1556,61 @@ def test_chunkwise_row_order_is_a_blockwise_permutation(pkg):
         d = deg[order]
         same_block = (pos[1:] // ORDER_CHUNK_ROWS) == (pos[:-1] // ORDER_CHUNK_ROWS)
         assert torch.all(d[1:][same_block] <= d[:-1][same_block])                   # decreasing edge count inside a block
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16-transform mode: the walk gathers a bf16 copy of the features (csrc/aggregate.cu, *_bf16_kernel)
+@pytest.mark.parametrize("d", [64, 128, 256, 72])
+def test_bf16_feature_walk_equals_fp32_walk_over_the_same_values(pkg, d):
+    """Same bf16 values, fp32 sums in the same edge order, true division, one rounding to bf16 at the end: without hub
+    segments the operand plane is bit-identical to the fp32-feature walk over the up-converted copy; with hubs (other
+    chunk grouping at some widths) it agrees to one bf16 ulp.  The self-loop block is the copy itself."""
+    from primekg_rgcn_linkprediction_b200 import ops, synth
+    for kg, exact in ((synth.uniform_kg(20_000, 150_000, 4, seed=3), True), (synth.primekg_subgraph(120_000, seed=5), False)):
+        ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+        g = pkg.RelGraph.from_edges(ei, et, kg.num_nodes, kg.num_relations)
+        R = kg.num_relations
+        torch.manual_seed(d)
+        x16 = ops.to_bf16(torch.randn(kg.num_nodes, d, device=DEV))
+        x = x16.float().contiguous()
+        W = torch.randn(R * d, 64, device=DEV) * 0.1
+        root = torch.randn(d, 64, device=DEV) * 0.1
+        bias = torch.zeros(64, device=DEV)
+        _, A_ref, _ = ops.layer_fwd(g, x, x, W, root, bias, False, "bf16")
+        out, A, _, out16 = ops.layer_fwd(g, x, x, W, root, bias, True, "bf16", x_bf16=x16, want_out_bf16=True)
+        K = (R + 1) * d
+        if exact:
+            assert torch.equal(A[0][:, :K], A_ref[0][:, :K])
+        else:
+            torch.testing.assert_close(A[0][:, :K].float(), A_ref[0][:, :K].float(), rtol=2.0 ** -7, atol=1e-6)
+            same_rows = (A[0][:, :K] == A_ref[0][:, :K]).all(1).float().mean()
+            assert float(same_rows) > 0.97                                   # only rows with a hub segment may differ
+        assert torch.equal(A[0][:, R * d:K], x16[:, :d])
+        assert torch.equal(out16, out.to(torch.bfloat16))                    # the epilogue's bf16 copy of the output
+
+
+def test_bf16_mode_hands_the_bf16_copy_from_layer_to_layer(pkg, monkeypatch):
+    """Encoder in bf16 mode: layer 1 gathers a bf16 copy of the table, its epilogue leaves the bf16 copy of its output and
+    layer 2 claims it; results stay within the bf16 budget of the fp32-gather form (PRIMEKG_RGCN_BF16_GATHER=0)."""
+    from primekg_rgcn_linkprediction_b200 import rowsparse
+    g = load_golden("small_full")
+    m = _product_model(pkg, g)
+    for c in (m.encoder.conv1, m.encoder.conv2):
+        c.mode = "bf16"
+    ei, et = g["edge_index"].to(DEV), g["edge_type"].to(DEV)
+    m.train()
+    claimed = []
+    orig = rowsparse.claim_bf16
+    monkeypatch.setattr(rowsparse, "claim_bf16", lambda x: claimed.append(orig(x)) or claimed[-1])
+    a = m.encoder(ei, et)
+    assert len(claimed) == 2 and claimed[0] is None and claimed[1] is not None and claimed[1].dtype == torch.bfloat16
+    a.sum().backward()
+    ga = m.encoder.node_embeddings.weight.grad.clone()
+    monkeypatch.setenv("PRIMEKG_RGCN_BF16_GATHER", "0")
+    m.zero_grad()
+    b = m.encoder(ei, et)
+    b.sum().backward()
+    scale = float(b.abs().max())
+    torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2 * scale)
+    gb = m.encoder.node_embeddings.weight.grad
+    assert float((ga - gb).norm() / gb.norm()) < 2e-2
