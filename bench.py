@@ -679,6 +679,13 @@ def run_ours(args, rank, world, local_rank):
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     value = world * kg.num_edges / (ms_per_step * 1e-3)
+    dp_exchange_ok = None
+    if peer_ar:
+        try:
+            gstep.peer_ar.check()                       # a wait that gave up (a peer never arrived) would void the number
+            dp_exchange_ok = True
+        except Exception as ex:  # pragma: no cover
+            dp_exchange_ok = repr(ex)[:200]
 
     # ---- end to end: batch in pinned host memory, H2D of the step's inputs and D2H of the loss inside ----
     packed = pkg.GraphedTrainStep.pack_batch(heads, tails, rels, labels)
@@ -784,6 +791,8 @@ def run_ours(args, rank, world, local_rank):
                                              "(PRIMEKG_RGCN_SPARSE_BWD=0)"}),
            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
            "wall_s_timed_region": t_wall, "clocks": clocks, "roofline": roofline, "partitioned": part}
+    if world > 1:
+        out["dp_exchange"] = {"form": dp_exchange, "all_ranks_arrived": dp_exchange_ok}
     if world == 1 and not args.quick:
         out["configs"] = other_configs(pkg, dev, flush, args.mode)
         try:

@@ -116,6 +116,14 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
   const int64_t ldf = p.ldf;
   constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   constexpr int U = U0 < PER ? U0 : PER;
+  // the group's PER (<= G) edge indices, slots and weights in ONE coalesced load per array, handed out by shuffle: the
+  // gathers of all batches then depend on a single index latency instead of one per batch
+  static_assert(PER <= G, "a group's slice of a hub chunk must fit its lanes");
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const bool mine = lane < PER && g_beg + lane < g_end;
+  int my_j = mine ? __ldg(idx + g_beg + lane) : 0;
+  if (SLOT) my_j = mine ? __ldg(p.slot + my_j) : p.zero_row;
+  const float my_w = (W && mine) ? __ldg(ew + g_beg + lane) : 0.f;
   int e = g_beg;
   for (; e + U <= g_end; e += U) {
     float4 v[U][VPL];
@@ -124,14 +132,14 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
     bool any = !SLOT;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      js[u] = __ldg(idx + e + u);
-      if (SLOT) { js[u] = __ldg(p.slot + js[u]); any |= js[u] != p.zero_row; }
+      js[u] = __shfl_sync(gmask, my_j, e + u - g_beg, G);
+      if (W) w[u] = __shfl_sync(gmask, my_w, e + u - g_beg, G);
+      if (SLOT) any |= js[u] != p.zero_row;
     }
     if (!any) continue;                            // (group-uniform) every edge of the batch points at a zero row
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = js[u];
-      if (W) w[u] = __ldg(ew + e + u);
       const float* __restrict__ rp = Fb + (size_t)j * ldf;
       const bool on = !SLOT || j != p.zero_row;
 #pragma unroll
@@ -144,14 +152,15 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
         if (W) fma4(acc[k], w[u], v[u][k]); else add4(acc[k], v[u][k]);
       }
   }
-  for (; e < g_end; ++e) {
-    int j = __ldg(idx + e);
-    if (SLOT) { j = __ldg(p.slot + j); if (j == p.zero_row) continue; }
+  for (; e < g_end; ++e) {                         // (group-uniform trip count)
+    const int j = __shfl_sync(gmask, my_j, e - g_beg, G);
+    const float wv = W ? __shfl_sync(gmask, my_w, e - g_beg, G) : 1.f;
+    if (SLOT && j == p.zero_row) continue;
     const float* __restrict__ rp = Fb + (size_t)j * ldf;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const float4 v = ldg4(rp + vcol[k]);
-      if (W) fma4(acc[k], __ldg(ew + e), v); else add4(acc[k], v);
+      if (W) fma4(acc[k], wv, v); else add4(acc[k], v);
     }
   }
 #pragma unroll
@@ -682,12 +691,15 @@ __global__ void __launch_bounds__(256) hub_partial_bf16_kernel(const AggParams p
   }
   constexpr int U0 = VPL >= 2 ? 4 : 8;
   constexpr int U = U0 < PER ? U0 : PER;
+  static_assert(PER <= G, "a group's slice of a hub chunk must fit its lanes");
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+  const int my_j = (lane < PER && g_beg + lane < g_end) ? __ldg(p.idx + g_beg + lane) : 0;     // one coalesced index load
   int e = g_beg;
   for (; e + U <= g_end; e += U) {
     uint4 v[U][VPL];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int j = __ldg(p.idx + e + u);
+      const int j = __shfl_sync(gmask, my_j, e + u - g_beg, G);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) ld_bf8(F + (size_t)j * p.ldf + vcol[k], v[u][k]);
     }
@@ -697,7 +709,7 @@ __global__ void __launch_bounds__(256) hub_partial_bf16_kernel(const AggParams p
       for (int k = 0; k < VPL; ++k) acc_bf8(acc[k], v[u][k]);
   }
   for (; e < g_end; ++e) {
-    const int j = __ldg(p.idx + e);
+    const int j = __shfl_sync(gmask, my_j, e - g_beg, G);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) { uint4 r; ld_bf8(F + (size_t)j * p.ldf + vcol[k], r); acc_bf8(acc[k], r); }
   }

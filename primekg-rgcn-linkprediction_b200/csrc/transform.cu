@@ -169,7 +169,6 @@ struct GemmKParams {
   const float* thr_in; float* thr_out;        // EPI_RANK: per-row threshold;  EPI_THR: out[row] = acc[row, row]
   const int64_t* true_pos; int32_t* greater; int32_t* equal;
   float alpha, beta;                          // EPI_TOPK: reported value = alpha * acc + beta (alpha > 0)
-  int topk;                                   // entries actually wanted (<= kTopK): the insertion threshold is the topk-th best
   float* cand_val; int32_t* cand_idx; int32_t* slot_ctr; int32_t n_slots;    // [M, n_slots, kTopK] partial lists, [M] counters
   // fused all-gather: every output tile is also stored into the same-shaped slot (rows peer_row0 ...) of up to
   // kMaxPeers feature buffers that live in OTHER GPUs' memory (peer-mapped, NVLink stores issued by the epilogue)
@@ -272,7 +271,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     // per-row state of the consuming epilogues (one row per lane)
     int64_t cur_m0 = -1;
     int cnt_g = 0, cnt_e = 0;
-    float thr = 0.f, kth = -INFINITY;
+    float thr = 0.f;
     int64_t tpos = -1;
     float topv[EPI == EPI_TOPK ? kTopK : 1];
     int topi[EPI == EPI_TOPK ? kTopK : 1];
@@ -310,7 +309,6 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (EPI == EPI_TOPK) {
 #pragma unroll
           for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) { topv[i] = -INFINITY; topi[i] = -1; }
-          kth = -INFINITY;
         }
       }
       mbar_wait(&tfull_bar[a], (uint32_t)((iter >> 1) & 1));
@@ -338,16 +336,11 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               if (j == want) v = __uint_as_float(r[j]);
             if (want >= 0 && want < 16 && row < p.M) p.thr_out[row] = v;
           } else {
-            // most 16-column chunks hold nothing above the row's current threshold: one max per chunk, then skip
-            float cmax = __uint_as_float(r[0]);
-#pragma unroll
-            for (int j = 1; j < 16; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
-            if (!__any_sync(0xffffffffu, cmax > kth && row < p.M)) continue;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = n0 + cc + j;
               float v = __uint_as_float(r[j]);
-              if (row < p.M && col < p.n_cols_valid && v > kth) {
+              if (row < p.M && col < p.n_cols_valid && v > topv[(EPI == EPI_TOPK ? kTopK : 1) - 1]) {
                 int ci = col;                                // insertion into the descending list (columns arrive in
 #pragma unroll                                               // ascending order: an equal value keeps the earlier one first)
                 for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) {
@@ -356,10 +349,6 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     topv[i] = v; topi[i] = ci; v = tv; ci = ti;
                   }
                 }
-                kth = -INFINITY;                             // the topk-th best so far (static register indexing)
-#pragma unroll
-                for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i)
-                  if (i == p.topk - 1) kth = topv[i];
               }
             }
           }
@@ -1295,7 +1284,7 @@ extern "C" int rgcn_scores_topk_w(const void* Q_hi, const void* Q_lo, int64_t ld
   cudaStream_t st = (cudaStream_t)stream;
   RGCN_CUDA(cudaMemsetAsync(slot_ctr, 0, (size_t)n_q * sizeof(int32_t), st));
   p.N = (int)n_cand; p.n_cols_valid = n_cand; p.tile_contig = 1;
-  p.alpha = alpha; p.beta = beta; p.topk = k; p.cand_val = cand_val; p.cand_idx = cand_idx; p.slot_ctr = slot_ctr; p.n_slots = n_slots;
+  p.alpha = alpha; p.beta = beta; p.cand_val = cand_val; p.cand_idx = cand_idx; p.slot_ctr = slot_ctr; p.n_slots = n_slots;
   const int n_tiles = (int)((n_cand + KBN - 1) / KBN);
   const __nv_bfloat16* bhi = (const __nv_bfloat16*)cand_planes;
   const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)cand_planes + wplane_bytes((int)n_cand, d));
