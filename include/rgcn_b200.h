@@ -299,8 +299,8 @@ typedef struct rgcn_layer_fwd_args {
    * it ONCE (rgcn_prepare_weights), reads it as the MN-major operand of the transform, and rgcn_layer_bwd reads the same
    * buffer for its dgrad.  With it the call may also PIPELINE: the walk of row chunk c + 1 runs on `stream` while the
    * transform of chunk c (and, in the partitioned path, its peer stores = the all-gather) runs on an internal side
-   * stream, joined before the call returns.  pipeline: 0 = the library decides (from 200,000 rows with peer outputs: every
-   * chunk's transform is many waves long and has NVLink stores to hide; RGCN_PIPELINE=0/1 overrides), 1 = never, 2 = always. */
+   * stream, joined before the call returns.  pipeline: 0 = the library decides (never: measured slower on one and
+   * two GPUs, see csrc/layer.cu; RGCN_PIPELINE=1 opts in), 1 = never, 2 = always. */
   void* w_planes; size_t w_planes_bytes; int32_t pipeline;
   /* bf16-transform mode (mode 1, needs w_planes), all optional: x_bf16 = a bf16 copy of x (x_src == x_root, d_in % 8 == 0):
    * the walk gathers IT (half the bytes of the dominant kernel; sums stay fp32);  out_bf16 = where to leave the bf16 copy

@@ -106,12 +106,12 @@ static int pipeline_mode(const rgcn_layer_fwd_args* a, cudaStream_t st, SideStre
   const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
   SideStream* ss = side_stream(!capturing);
   if (!ss) return 0;
-  // measured on cfg2 (30,926 rows, 4 chunks): chunk transforms of one wave each lose more (prologue + pipeline fill per
-  // tile, SMs held by walk blocks) than the overlap wins — 0.530 against 0.446 ms per step — so the library only pipelines
-  // when every chunk's transform is many waves long (the partitioned cfg5 shards: 1.25 M rows per GPU)
-  // ... and has peer stores to hide: on ONE GPU the two streams only compete (1.25 M rows / 50 M edges / 30 relations:
-  // 89.1 against 84.6 ms per step)
-  if (want == 2 && (a->csr->n_rows < 200000 || a->n_peer <= 1)) return 0;
+  // Measured, and it LOSES everywhere it was tried, so the library never pipelines on its own (RGCN_PIPELINE=1 or
+  // pipeline = 2 opt in): cfg2 (30,926 rows, 4 chunks) 0.530 against 0.446 ms per step — one-wave chunk transforms pay
+  // their prologue and pipeline fill per tile while walk blocks hold the SMs; one GPU, 1.25 M rows / 50 M edges / 30
+  // relations 89.1 against 84.6 ms; two GPUs with the peer stores in the epilogue 98.5 against 92.8 ms — walk and
+  // transform are both bound by the same memory system there (operand planes of 19.8 GB per layer), not by different units.
+  if (want == 2) return 0;
   *ss_out = ss;
   return 1;
 }

@@ -275,8 +275,36 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     int64_t tpos = -1;
     float topv[EPI == EPI_TOPK ? kTopK : 1];
     int topi[EPI == EPI_TOPK ? kTopK : 1];
+    constexpr int kTopBuf = 10;                               // staged candidates per lane (K_PATCH = 32 lanes x 10 x 8 B)
+    uint2* tbuf = reinterpret_cast<uint2*>(patch);
+    int bcnt = 0;
+    float kth = -INFINITY;                                    // the list's last entry as of the last drain
+    auto drain = [&]() {
+      const int mx = __reduce_max_sync(0xffffffffu, bcnt);
+      for (int e = 0; e < mx; ++e) {
+        const bool has = e < bcnt;
+        const uint2 c = has ? tbuf[lane + 32 * e] : make_uint2(0u, 0u);
+        float v = __uint_as_float(c.x);
+        int ci = (int)c.y;
+        if (has && v > topv[(EPI == EPI_TOPK ? kTopK : 1) - 1]) {
+          // insertion into the descending list; candidates arrive in ascending column order, so an equal value keeps
+          // the earlier (lower) column first
+#pragma unroll
+          for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) {
+            if (v > topv[i]) {
+              const float tv = topv[i]; const int ti = topi[i];
+              topv[i] = v; topi[i] = ci; v = tv; ci = ti;
+            }
+          }
+        }
+      }
+      bcnt = 0;
+      kth = topv[(EPI == EPI_TOPK ? kTopK : 1) - 1];
+      __syncwarp();
+    };
     auto flush_row_state = [&]() {
       if (cur_m0 < 0) return;
+      if (EPI == EPI_TOPK) drain();
       const int64_t row = cur_m0 + quarter * 32 + lane;
       if (row >= p.M) return;
       if (EPI == EPI_RANK) {
@@ -309,6 +337,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         if (EPI == EPI_TOPK) {
 #pragma unroll
           for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) { topv[i] = -INFINITY; topi[i] = -1; }
+          kth = -INFINITY;
+          bcnt = 0;
         }
       }
       mbar_wait(&tfull_bar[a], (uint32_t)((iter >> 1) & 1));
@@ -336,20 +366,22 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               if (j == want) v = __uint_as_float(r[j]);
             if (want >= 0 && want < 16 && row < p.M) p.thr_out[row] = v;
           } else {
+            // Staged insertion.  A lane inserting into its sorted list costs the whole warp ~80 instructions, and with 32
+            // rows per warp SOME lane wants to insert at almost every column.  So a passing element is only appended
+            // to the lane's small buffer in shared memory (the idle transpose patch), and when any lane's buffer fills
+            // the warp drains all 32 buffers together: the insertion cost is paid once per ~5 elements per lane.
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = n0 + cc + j;
-              float v = __uint_as_float(r[j]);
-              if (row < p.M && col < p.n_cols_valid && v > topv[(EPI == EPI_TOPK ? kTopK : 1) - 1]) {
-                int ci = col;                                // insertion into the descending list (columns arrive in
-#pragma unroll                                               // ascending order: an equal value keeps the earlier one first)
-                for (int i = 0; i < (EPI == EPI_TOPK ? kTopK : 1); ++i) {
-                  if (v > topv[i]) {
-                    const float tv = topv[i]; const int ti = topi[i];
-                    topv[i] = v; topi[i] = ci; v = tv; ci = ti;
-                  }
+            for (int j0 = 0; j0 < 16; j0 += 4) {
+#pragma unroll
+              for (int j = j0; j < j0 + 4; ++j) {
+                const int col = n0 + cc + j;
+                const float v = __uint_as_float(r[j]);
+                if (row < p.M && col < p.n_cols_valid && v > kth) {
+                  tbuf[lane + 32 * bcnt] = make_uint2(r[j], (uint32_t)col);
+                  ++bcnt;
                 }
               }
+              if (__any_sync(0xffffffffu, bcnt >= kTopBuf - 4)) drain();
             }
           }
           continue;

@@ -519,8 +519,8 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
     layer output rounded to bf16 as a fourth result (the next layer's ``x_bf16``).
     Returns (out [n_dst, d_out], (A_hi, A_lo | None), w_planes | None): ``w_planes`` = the layer's weights as bf16 planes,
     converted once by the call; hand it to ``layer_bwd`` (its dgrad then skips the conversion).
-    ``pipeline``: 0 = the library decides whether the walk of row chunk c + 1 runs under the transform of chunk c (from
-    200,000 rows with peer outputs), 1 = never, 2 = always."""
+    ``pipeline``: 0 = the library decides whether the walk of row chunk c + 1 runs under the transform of chunk c (it does
+    not: measured slower; RGCN_PIPELINE=1 opts in), 1 = never, 2 = always."""
     lib = _lib.load()
     x_src = _f32c(x_src, "x")
     x_root = x_src if x_root is x_src else _f32c(x_root, "x_root")
