@@ -390,6 +390,11 @@ int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream);
  *                           written as fp32 `out` and / or as bf16 planes hi (, lo) with the same column-sum partials
  *                           as rgcn_split_planes (rgcn_split_planes_blocks(rows, cols) rows of `cols` floats).
  * ------------------------------------------------------------------------------------------ */
+/*   rgcn_p2p_pull_rows    : out[rows[c], :] = sum_q part_q[row0 + rows[c], :] (rank order) for the n_list listed LOCAL rows only
+ *                           (int64 device list, duplicates allowed; out is [n_rows_out, ldo], other rows untouched): the
+ *                           reduce-scatter of a gradient that is zero outside a short row list. */
+int rgcn_p2p_pull_rows(const float* const* part_host, int32_t n_part, int64_t row0, int64_t ld_part, const int64_t* rows,
+                       int64_t n_list, int64_t n_rows_out, int32_t cols, float* out, int64_t ldo, rgcn_stream_t stream);
 int rgcn_p2p_push_rows(const float* src, int64_t ld_src, int64_t rows, int32_t cols,
                        float* const* dst_host, int32_t n_dst, int64_t row0, int64_t ld_dst, rgcn_stream_t stream);
 int rgcn_p2p_reduce_split(const float* const* part_host, int32_t n_part, int64_t row0, int64_t ld_part,

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "rgcn_basis_combine_bwd": (C.c_int, [p, p, p, i32, i32, i64, p, p, p]),
     "rgcn_layer_fwd": (C.c_int, [C.POINTER(LayerFwdArgs), p]),
     "rgcn_layer_bwd": (C.c_int, [C.POINTER(LayerBwdArgs), p]),
+    "rgcn_p2p_pull_rows": (C.c_int, [p, i32, i64, i64, p, i64, i64, i32, p, i64, p]),
     "rgcn_p2p_push_rows": (C.c_int, [p, i64, i64, i32, p, i32, i64, i64, p]),
     "rgcn_p2p_reduce_split": (C.c_int, [p, i32, i64, i64, p, i64, p, i64, C.c_float, i64, i32, p, i64, p, p, i64, p, p]),
     "rgcn_p2p_allreduce_flag_bytes": (sz, []),

@@ -208,7 +208,8 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
   const int64_t m_c = rgcn_rows_compact_size(a->n_list);
   RGCN_CHECK_ARG(a->n_list > 0 && a->slot, "layer_bwd: the row-sparse form needs a row list and the slot scratch");
   RGCN_CHECK_ARG(!a->relu_mask && !a->g_ready, "layer_bwd: the row-sparse form serves a layer without ReLU (the last one)");
-  RGCN_CHECK_ARG(!a->gA || a->add_root_term || !a->g_x, "layer_bwd: the row-sparse form is the one-GPU form (root term added)");
+  // add_root_term = 0 (a destination-range shard: sources and destinations live in different id spaces): the root-term
+  // gradient stays in the compact gA[:, R d_in:] rows for the caller
   RGCN_CHECK_ARG(!need_w || (a->Ac_hi && (a->mode == 1 || a->Ac_lo)), "layer_bwd: compact operand planes missing");
   int rc = rgcn_rows_compact(a->rows, a->n_list, a->n_dst, a->slot, a->g_out, a->ld_g_out, a->d_out, a->G_hi,
                              a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->A_hi, a->mode == 0 ? a->A_lo : nullptr, a->lda, K,
@@ -217,8 +218,9 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
                              a->slot_ready, stream);
   if (rc) return rc;
   return dgrad_walk_wgrad(a, m_c, a->Ac_hi, a->Ac_lo, a->ldac, (int32_t)rgcn_rows_compact_blocks(a->n_list), [&]() {
-    return rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c, a->gA + K1, a->ld_gA, a->g_x,
-                                   a->ld_g_x, a->next_G, a->agg_workspace, a->agg_workspace_bytes, stream);
+    return rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c,
+                                   a->add_root_term ? a->gA + K1 : nullptr, a->ld_gA, a->g_x, a->ld_g_x, a->next_G,
+                                   a->agg_workspace, a->agg_workspace_bytes, stream);
   }, stream);
 }
 

@@ -131,6 +131,25 @@ __global__ void __launch_bounds__(256) reduce_split_kernel(ConstPeerPtrs part, i
   }
 }
 
+// out[rows[c], :] = sum_q part_q[row0 + rows[c], :]  (rank order) for the listed rows only — the reduce-scatter of a gradient
+// that is zero outside a short row list (the last layer of the partitioned encoder: the loss reads 2 * batch rows), so the
+// exchange moves kilobytes instead of this rank's whole shard of every rank's buffer.  One warp per list entry; duplicates
+// write the same value twice.
+__global__ void __launch_bounds__(256) pull_rows_kernel(ConstPeerPtrs part, int n_part, int64_t row0, int64_t ld_part,
+                                                        const int64_t* __restrict__ rows, int64_t n_list, int cols,
+                                                        float* __restrict__ out, int64_t ldo) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= n_list) return;
+  const int64_t r = rows[c];
+  for (int vi = lane; vi < (cols >> 2); vi += 32) {
+    float4 v = __ldcg(reinterpret_cast<const float4*>(part.p[0] + (row0 + r) * ld_part + vi * 4));
+    for (int q = 1; q < n_part; ++q) add4(v, __ldcg(reinterpret_cast<const float4*>(part.p[q] + (row0 + r) * ld_part + vi * 4)));
+    *reinterpret_cast<float4*>(out + r * ldo + vi * 4) = v;
+  }
+}
+
 // ---- all-reduce (average) of one flat fp32 buffer over the GPUs of one NVSwitch domain ----------------------------
 // The data-parallel gradient exchange (every replica holds the whole cfg1-4 graph; the reference is single-device, its
 // README lists multi-GPU as future work).  Two-shot over peer-mapped memory, no collective library, CUDA-graph capturable:
@@ -258,6 +277,24 @@ extern "C" int rgcn_p2p_allreduce(const float* const* in_host, float* const* out
                        scale, (const unsigned int*)fl.p[rank], (const unsigned int*)epoch_counter, (int*)status));
   RGCN_LAUNCH_CHECK();
   RGCN_CUDA(launch_pdl(allreduce_flag_kernel, dim3(1), dim3(32), 0, st, fl, (int)n_ranks, (int)rank, epoch_counter, 1, (int*)status));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+extern "C" int rgcn_p2p_pull_rows(const float* const* part_host, int32_t n_part, int64_t row0, int64_t ld_part,
+                                  const int64_t* rows, int64_t n_list, int64_t n_rows_out, int32_t cols, float* out, int64_t ldo,
+                                  rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(cols >= 4 && cols % 4 == 0 && n_list >= 0 && n_rows_out >= 0, "p2p_pull_rows: cols=%d must be a positive multiple of 4", cols);
+  RGCN_CHECK_ARG(n_part >= 1 && n_part <= kMaxPeers && part_host, "p2p_pull_rows: between 1 and %d partial buffers", kMaxPeers);
+  RGCN_CHECK_ARG(ld_part % 4 == 0 && row0 >= 0 && rows && out && ((uintptr_t)out & 15) == 0 && ldo % 4 == 0, "p2p_pull_rows: bad buffers");
+  ConstPeerPtrs pp{};
+  for (int q = 0; q < n_part; ++q) {
+    RGCN_CHECK_ARG(part_host[q] && ((uintptr_t)part_host[q] & 15) == 0, "p2p_pull_rows: partial %d is null or misaligned", q);
+    pp.p[q] = part_host[q];
+  }
+  if (n_list == 0) return RGCN_OK;
+  RGCN_CUDA(launch_pdl(pull_rows_kernel, dim3((unsigned)((n_list + 7) / 8)), dim3(256), 0, (cudaStream_t)stream, pp, (int)n_part, row0,
+                       ld_part, rows, n_list, (int)cols, out, ldo));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

@@ -32,10 +32,17 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+import os
+
+from . import ops, rowsparse
 from .conv import default_mode
 from .dist import PartitionPlan, PartitionedRGCN
 from .peer import PeerBuffer
+
+
+def sparse_last_layer() -> bool:
+    """Row-sparse backward of the last layer in the partitioned path (``PRIMEKG_RGCN_SPARSE_BWD=0`` turns it off)."""
+    return os.environ.get("PRIMEKG_RGCN_SPARSE_BWD", "1") != "0"
 
 
 class _Exchange:
@@ -127,6 +134,23 @@ class _FusedEncoderFn(torch.autograd.Function):
         dev = g_full.device
         d_last = t[4 * (L - 1) + 2].shape[2]
         ex.g_view(L, d_last).copy_(g_full)              # this rank's partial gradient of ALL rows, peer visible
+        # The loss reads 2 * batch rows of the output (src/models/rgcn.py:325-326): every rank's g_full is zero outside the
+        # rows ITS slice of the batch names (the decoder's backward announces them, rowsparse.py).  With all ranks' lists
+        # the LAST layer's backward runs row-sparse, like the one-GPU model: a pull of the listed rows only (kilobytes
+        # instead of this rank's shard of every rank's buffer) and dgrad / walk / wgrad over <= 2 * batch compact rows.
+        sparse_rows = None
+        claimed = rowsparse.claim(g_full) if sparse_last_layer() else None
+        if claimed is not None:
+            mine_rows = claimed[0]                                          # padded global ids, 2 * local batch entries
+            all_rows = torch.empty(ex.world * mine_rows.numel(), dtype=torch.int64, device=dev)
+            if ex.world > 1:
+                dist.all_gather_into_tensor(all_rows, mine_rows.contiguous())
+            else:
+                all_rows = mine_rows
+            inside = (all_rows >= row0) & (all_rows < row0 + n)
+            # rows of other shards are replaced by local row 0: listing a row that nobody's loss touches is harmless, its
+            # pulled gradient is exactly zero (fixed list length: no host synchronisation)
+            sparse_rows = torch.where(inside, all_rows - row0, torch.zeros_like(all_rows))
         ex.g.barrier()
         extra = None
         grads = [None] * (3 * L)
@@ -135,11 +159,23 @@ class _FusedEncoderFn(torch.autograd.Function):
             R, d_in, d_out = W.shape
             K1, K2 = R * d_in, d_in
             mask = masks[l] if l < L - 1 else None
+            Wf = W.reshape(K1, d_out)
+            if l == L - 1 and sparse_rows is not None:
+                g_local = torch.empty(n, d_out, dtype=torch.float32, device=dev)      # only the listed rows are read
+                ops.p2p_pull_rows(ex.g_ptrs(l + 1), row0, d_out, sparse_rows, g_local)
+                _, gA_c, gWf, groot, gb, slot = ops.layer_bwd(
+                    graph, g_local, None, 1.0, (A_hi, A_lo), Wf, root, d_in, mode, need_x=True, add_root_term=False,
+                    need_w=True, need_b=True, gx_out=ex.g_view(l, d_in), rows=sparse_rows, w_planes=ctx.w_planes[l],
+                    return_compact=True)
+                # root-term gradient of this rank's rows: the compact rows scattered back (unlisted rows read the zero row)
+                extra = gA_c[:, K1:].index_select(0, slot.long())
+                grads[3 * l: 3 * l + 3] = [gWf.view(R, d_in, d_out), groot, gb]
+                ex.g.barrier()
+                continue
             G = ops.alloc_planes(n, d_out, mode, dev)
             # reduce-scatter by pull + root-term gradient + ReLU/dropout mask + operand conversion, one kernel
             _, colsum = ops.p2p_reduce_split(ex.g_ptrs(l + 1), row0, d_out, n, d_out, dev, extra=extra, relu_mask=mask,
                                              mask_scale=1.0 / (1.0 - ctx.p_drops[l]), planes=G, colsum=True)
-            Wf = W.reshape(K1, d_out)
             gA = ops.transform_dgrad(G, d_out, Wf, root, mode, w_planes=ctx.w_planes[l])
             ops.aggregate_bwd(graph, gA, d_in, init=None, out=ex.g_view(l, d_in))
             extra = gA[:, K1:]

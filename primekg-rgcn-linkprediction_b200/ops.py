@@ -161,8 +161,9 @@ def aggregate_bwd(g: RelGraph, gH: torch.Tensor, d: int, init: Optional[torch.Te
     gH = _f32c(gH, "gH")
     rows_form = slot is not None
     if rows_form:
-        if slot.dtype != torch.int32 or slot.numel() != g.n_dst or not (0 <= zero_row < gH.size(0)) or g.n_src != g.n_dst:
-            raise ValueError("slot must be int32 [n_dst] and zero_row a row of gH")
+        if slot.dtype != torch.int32 or slot.numel() != g.n_dst or not (0 <= zero_row < gH.size(0)) or \
+                (init is not None and g.n_src != g.n_dst):
+            raise ValueError("slot must be int32 [n_dst] and zero_row a row of gH (init needs n_src == n_dst)")
         slot = slot.contiguous()
     if (not rows_form and gH.size(0) != g.n_dst) or gH.size(1) < g.R * d:
         raise ValueError("gH must be [n_dst, >= R*d]")
@@ -565,13 +566,15 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
 def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], mask_scale: float, planes, W2d: torch.Tensor,
               root: torch.Tensor, d_in: int, mode: str, need_x: bool, add_root_term: bool, need_w: bool, need_b: bool,
               gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None, g_ready=None, next_mask=None,
-              slot: Optional[torch.Tensor] = None, w_planes: Optional[torch.Tensor] = None):
+              slot: Optional[torch.Tensor] = None, w_planes: Optional[torch.Tensor] = None, return_compact: bool = False):
     """split(gO, mask) -> dgrad -> transposed gather -> wgrad of one layer in ONE C call (``rgcn_layer_bwd``).
     Returns (g_x | None, gA | None, gW2d | None, g_root | None, g_bias | None); ``gA[:, R*d_in:]`` is the root-term
     gradient (already inside g_x when ``add_root_term``).
     ``rows`` (int64 device list, duplicates allowed): the caller guarantees gO is zero outside these rows; the backward
     then runs on the compacted rows (csrc/rowsparse.cu) with the same results, and gA comes back compact (``None`` here).
     ``slot`` (int32 [n]): the node -> first-position map of ``rows``, already built by the decoder's backward.
+    ``return_compact`` (row-sparse form): return the compact gA [m_c + 1, K] (row m_c = zeros) instead of None and append
+    the slot map to the result — a shard (add_root_term=False) reads its root-term gradient rows from it.
     ``g_ready`` = ((G_hi, G_lo | None), colsum [n, d_out]): this layer's masked output gradient as planes, already written
     by the downstream layer (skips the split pass).  ``next_mask`` = (mask [n_src, d_in], scale): also produce g_x masked
     for the upstream layer; the result gains a sixth entry ((hi, lo | None), colsum)."""
@@ -589,8 +592,9 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
     A_hi, A_lo = planes
     sparse = rows is not None
     if sparse:
-        if relu_mask is not None or not add_root_term or g.n_src != g.n_dst:
-            raise ValueError("the row-sparse backward serves an unpartitioned layer without ReLU")
+        if relu_mask is not None or (add_root_term and g.n_src != g.n_dst):
+            raise ValueError("the row-sparse backward serves a layer without ReLU; on a destination-range shard "
+                             "(n_src != n_dst) the root term stays separate (add_root_term=False)")
         rows = _idx(rows, "rows").reshape(-1)
         m = int(lib.rgcn_rows_compact_size(rows.numel()))
     else:
@@ -643,6 +647,8 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         C.pointer(nxt_struct) if nxt_struct is not None else None, int(g_ready is not None),
         0 if g_ready is None else colsum.size(0), int(slot_ready), _dp(w_planes))
     _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
+    if sparse and return_compact:
+        return gx, gA, gW, groot, gb, slot
     if next_mask is not None:
         return gx, (None if sparse else gA), gW, groot, gb, nxt
     return gx, (None if sparse else gA), gW, groot, gb
@@ -655,6 +661,17 @@ def p2p_push_rows(src: torch.Tensor, dst_ptrs, row0: int, ld_dst: int) -> None:
     src = _f32c(src, "src")
     _lib.check(lib.rgcn_p2p_push_rows(_ptr(src), src.stride(0), src.size(0), src.size(1), _ptr_array(dst_ptrs),
                                       len(dst_ptrs), int(row0), int(ld_dst), _stream(src.device)), "rgcn_p2p_push_rows")
+
+
+def p2p_pull_rows(part_ptrs, row0: int, ld_part: int, rows: torch.Tensor, out: torch.Tensor) -> None:
+    """out[rows[c], :] = sum_q part_q[row0 + rows[c], :] (rank order) for the listed local rows only (reduce-scatter of a
+    row-sparse gradient by pull); the other rows of ``out`` are left untouched."""
+    lib = _lib.load()
+    rows = _idx(rows, "rows").reshape(-1)
+    out = _f32c(out, "out")
+    _lib.check(lib.rgcn_p2p_pull_rows(_ptr_array(part_ptrs), len(part_ptrs), int(row0), int(ld_part), _ptr(rows), rows.numel(),
+                                      out.size(0), out.size(1), _ptr(out), out.stride(0), _stream(out.device)),
+               "rgcn_p2p_pull_rows")
 
 
 def p2p_reduce_split(part_ptrs, row0: int, ld_part: int, rows: int, cols: int, device,
