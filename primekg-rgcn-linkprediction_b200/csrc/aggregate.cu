@@ -1078,7 +1078,7 @@ extern "C" int rgcn_aggregate_fwd_rows(const rgcn_csr_t* g, const float* X, int6
   RGCN_CHECK_ARG(!g->row_order || g->order_chunk_rows == 0 ||
                  ((row_begin % g->order_chunk_rows == 0) && (row_end % g->order_chunk_rows == 0 || row_end == g->n_rows)),
                  "aggregate_fwd_rows: with a chunk-wise row order the range must consist of whole order chunks");
-  RGCN_CHECK_ARG(!g->row_order || g->order_chunk_rows > 0 || (row_begin == 0 && row_end == g->n_rows),
+  RGCN_CHECK_ARG(!g->row_order || g->order_chunk_rows > 0 || (row_begin == 0 && row_end == g->n_rows) || row_begin == row_end,
                  "aggregate_fwd_rows: a global row order cannot be walked in ranges");
   AggParams p{};
   p.rowptr = g->rowptr; p.idx = g->idx; p.edge_w = g->w;

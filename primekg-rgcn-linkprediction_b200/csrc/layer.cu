@@ -9,6 +9,12 @@
 
 using namespace rgcn;
 
+// csrc/fused_layer.cu: walk + transform of one layer in one kernel (the operand [H | X] goes through shared memory)
+namespace rgcn {
+int fused_layer_fwd_eligible(const rgcn_layer_fwd_args* a);
+int fused_layer_fwd_launch(const rgcn_layer_fwd_args* a, cudaStream_t st);
+}
+
 // The weight-gradient contraction (tensor pipe) and the transposed walk (L2 / latency bound) of one layer's backward
 // both depend only on G and on the dgrad output respectively, not on each other: the wgrad runs on a side stream while
 // the main stream walks the graph, forked AFTER the dgrad launch (so the dgrad, which the walk waits for, gets the SMs
@@ -147,6 +153,15 @@ extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream
                                 a->dropout_p > 0.f ? a->dropout_counter : nullptr, stream);
   if (rc) return rc;
   void* A_lo = a->mode == 0 ? a->A_lo : nullptr;
+  if (fused_layer_fwd_eligible(a)) {
+    // hub chunks first (their partials are what the fused kernel's row walk adds for the long segments)
+    if (a->csr->n_chunks > 0) {
+      rc = rgcn_aggregate_fwd_rows(a->csr, a->x_src, a->ld_x_src, a->d_in, a->A_hi, A_lo, a->lda, out_mode, a->x_root,
+                                   a->ld_x_root, 0, 0, 1, a->agg_workspace, a->agg_workspace_bytes, stream);
+      if (rc) return rc;
+    }
+    return fused_layer_fwd_launch(a, st);
+  }
   auto transform = [&](int64_t r0, int64_t r1, rgcn_stream_t s) {
     const char* hi = (const char*)a->A_hi + (size_t)r0 * a->lda * 2;
     const char* lo = A_lo ? (const char*)A_lo + (size_t)r0 * a->lda * 2 : nullptr;
