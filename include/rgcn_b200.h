@@ -300,7 +300,10 @@ typedef struct rgcn_layer_fwd_args {
    * buffer for its dgrad.  With it the call may also PIPELINE: the walk of row chunk c + 1 runs on `stream` while the
    * transform of chunk c (and, in the partitioned path, its peer stores = the all-gather) runs on an internal side
    * stream, joined before the call returns.  pipeline: 0 = the library decides (never: measured slower on one and
-   * two GPUs, see csrc/layer.cu; RGCN_PIPELINE=1 opts in), 1 = never, 2 = always. */
+   * two GPUs, see csrc/layer.cu; RGCN_PIPELINE=1 opts in), 1 = never, 2 = always, 3 = the FUSED schedule: walk and
+   * transform in one kernel, the operand [H | X] handed over through shared memory (csrc/fused_layer.cu; d_in a
+   * multiple of 64, d_out a multiple of 16 up to 256, fp32 gathers; otherwise the call falls back to schedule 1;
+   * RGCN_FUSED_FWD=1 selects it for schedule 0.  Measured slower than schedule 1 on the B200, so never the default). */
   void* w_planes; size_t w_planes_bytes; int32_t pipeline;
   /* bf16-transform mode (mode 1, needs w_planes), all optional: x_bf16 = a bf16 copy of x (x_src == x_root, d_in % 8 == 0):
    * the walk gathers IT (half the bytes of the dominant kernel; sums stay fp32);  out_bf16 = where to leave the bf16 copy

@@ -18,6 +18,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+from . import autograph
 from . import ops
 from . import rowsparse
 from .conv import RGCNConv
@@ -282,8 +283,20 @@ class DrugDiseaseModel(nn.Module):
         self.decoder = LinkPredictor(num_relations=num_relations, embedding_dim=hidden_dim, dropout=decoder_dropout)
 
     def forward(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:
+        # training calls that repeat (same graph tensors, batch size, parameters) replay two captured CUDA graphs —
+        # forward, backward — behind this very signature (autograph.py): the reference's loop is bound by the host
+        fn = autograph.lookup(self, edge_index, edge_type, head_indices, tail_indices, relation_types)
+        if fn is not None:
+            return fn(head_indices, tail_indices, relation_types)
+        return self._forward_eager(edge_index, edge_type, head_indices, tail_indices, relation_types)
+
+    def _forward_eager(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:
         node_embeddings = self.encoder(edge_index, edge_type)
         return self.decoder.score_pairs(node_embeddings, head_indices, tail_indices, relation_types)
+
+    def invalidate_graphs(self) -> None:
+        """Drop the captured training-call graphs (autograph.py), e.g. before freeing the graph tensors."""
+        autograph.invalidate(self)
 
     def link_loss(self, edge_index, edge_type, head_indices, tail_indices, relation_types, labels):
         """Encoder + fused decoder / loss / accuracy: the whole of src/train.py:291-300 and :321-322 -> (loss, scores,

@@ -1614,3 +1614,47 @@ def test_bf16_mode_hands_the_bf16_copy_from_layer_to_layer(pkg, monkeypatch):
     torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-2 * scale)
     gb = m.encoder.node_embeddings.weight.grad
     assert float((ga - gb).norm() / gb.norm()) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# the unmodified training call as two captured CUDA graphs (autograph.py)
+def test_training_call_graph_capture_equals_eager(pkg, monkeypatch):
+    """model(...) -> BCEWithLogitsLoss -> backward() of reference src/train.py:291-306, driven eagerly: after three
+    identical calls the model replays captured graphs.  Same kernels => the same scores and gradients as a twin model
+    that stays eager (dropout off so the two draw nothing), on batches that change every step."""
+    from primekg_rgcn_linkprediction_b200 import autograph, synth
+    kg = synth.primekg_subgraph(120_000, seed=5)
+    ei, et = kg.edge_index.to(DEV), kg.edge_type.to(DEV)
+    torch.manual_seed(3)
+    twins = []
+    for _ in range(2):
+        torch.manual_seed(3)
+        twins.append(pkg.DrugDiseaseModel(kg.num_nodes, kg.num_relations, embedding_dim=64, hidden_dim=128, dropout=0.0,
+                                          decoder_dropout=0.0).to(DEV).train())
+    graphed, eager = twins
+    alive = {}                       # the previous step's scores and loss stay referenced while the next call runs, as
+    for step in range(8):            # the variables of the reference's for-loop do (src/train.py:291-306)
+        h, t, r, y = [x.to(DEV) for x in synth.link_batch(kg, 256, seed=100 + step)]
+        outs = []
+        for m, on in ((graphed, "1"), (eager, "0")):
+            monkeypatch.setenv("PRIMEKG_RGCN_AUTOGRAPH", on)
+            for p in m.parameters():
+                p.grad = None
+            s = m(ei, et, h, t, r)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(s, y)
+            loss.backward()
+            alive[on] = (s, loss)
+            outs.append((s.detach().clone(), [p.grad.clone() for p in m.parameters()]))
+        (s1, g1), (s0, g0) = outs
+        assert torch.equal(s1, s0), step
+        for a, b in zip(g1, g0):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7 * float(b.abs().max()) + 1e-12)
+    state = graphed.__dict__["_autograph"]
+    assert any(e[1] is not None for e in state.values())              # the capture happened
+    assert "_autograph" not in eager.__dict__ or all(e[1] is None for e in eager.__dict__["_autograph"].values())
+    # eval-mode and no-grad calls stay eager and see the current parameters
+    graphed.eval()
+    with torch.no_grad():
+        torch.testing.assert_close(graphed(ei, et, h, t, r), eager.eval()(ei, et, h, t, r))
+    graphed.invalidate_graphs()
+    assert "_autograph" not in graphed.__dict__
