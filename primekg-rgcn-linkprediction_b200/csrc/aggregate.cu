@@ -822,10 +822,11 @@ __global__ void __launch_bounds__(256, (VPL == 1 ? 4 : 3)) aggregate_rows_bf16_k
       }
       if (len > 1) {
         const float c = (float)len;                   // s / clamp(cnt, 1): a true division, like the reference
+        const float rc = __frcp_rn(c);
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[k].v[i] = acc[k].v[i] / c;
+          for (int i = 0; i < 8; ++i) acc[k].v[i] = div_by(acc[k].v[i], c, rc);
       }
 #pragma unroll
       for (int k = 0; k < VPL; ++k)
