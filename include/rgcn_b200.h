@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RGCN_B200_ABI_VERSION 6
+#define RGCN_B200_ABI_VERSION 7
 
 enum {
   RGCN_OK = 0,
@@ -200,6 +200,20 @@ int rgcn_aggregate_fwd_bf16(const rgcn_csr_t* g, const void* X16, int64_t ldx, i
                             const void* x_root16, int64_t ld_x_root, int64_t row_begin, int64_t row_end, int32_t hub_pass,
                             void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
+/* Listed-rows forward walk (the last layer of a link-prediction step is only read at the 2 * batch head / tail rows of its
+ * output, src/models/rgcn.py:325-326): position c of rows[0 .. n_list) walks row rows[c] and writes row c of a COMPACT
+ * operand [rgcn_rows_compact_size(n_list), >= (R+1) d] (duplicates are computed twice, padding rows are zero).
+ * slot (nullable): node -> first list position or m_c (rgcn_rows_list_build); hub chunks of unlisted rows are skipped.
+ * rgcn_rows_list_build: rows [2 n] = heads then tails (out-of-range indices parked on row 0), slot [n_nodes]. */
+int rgcn_rows_list_build(const int64_t* head, const int64_t* tail, int64_t n_pairs, int64_t n_nodes, int64_t* rows,
+                         int32_t* slot, rgcn_stream_t stream);
+int rgcn_aggregate_fwd_list(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d, void* H, void* H_lo, int64_t ldh,
+                            int32_t out_mode, const float* x_root, int64_t ld_x_root, const int64_t* rows, int64_t n_list,
+                            const int32_t* slot, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+int rgcn_aggregate_fwd_bf16_list(const rgcn_csr_t* g, const void* X16, int64_t ldx, int32_t d, void* H_hi, int64_t ldh,
+                                 const void* x_root16, int64_t ld_x_root, const int64_t* rows, int64_t n_list,
+                                 const int32_t* slot, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
 int rgcn_aggregate_bwd(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d,
                        const float* init, int64_t ld_init,
                        float* gX, int64_t ldgx, const rgcn_masked_planes_out* masked_planes,
@@ -309,6 +323,13 @@ typedef struct rgcn_layer_fwd_args {
    * the walk gathers IT (half the bytes of the dominant kernel; sums stay fp32);  out_bf16 = where to leave the bf16 copy
    * of this layer's output for the next layer (d_out % 4 == 0). */
   const void* x_bf16; int64_t ld_x_bf16; void* out_bf16; int64_t ld_out_bf16;
+  /* Listed-rows form (rows != NULL; needs w_planes, no peers, no dropout): only rows[0 .. n_list) of the layer's output
+   * are wanted — the 2 * batch (head, tail) rows the link-prediction decoder reads from the LAST layer,
+   * src/models/rgcn.py:325-326.  The walk visits those rows only, A_hi / A_lo are COMPACT planes
+   * [rgcn_rows_compact_size(n_list), >= (R+1) d_in] in list order (padding rows zero; hand them to rgcn_layer_bwd with
+   * a_compact = 1), the transform runs over them and stores row c at out[rows[c], :]; all other rows of `out` are left
+   * untouched.  rows / slot as built by rgcn_rows_list_build (slot may be NULL: every hub chunk is then reduced). */
+  const int64_t* rows; int64_t n_list; const int32_t* slot;
 } rgcn_layer_fwd_args;
 
 typedef struct rgcn_layer_bwd_args {
@@ -344,6 +365,8 @@ typedef struct rgcn_layer_bwd_args {
   int32_t slot_ready;                       /* row-sparse form: `slot` already holds the map for `rows` (written by
                                                rgcn_link_loss_bwd_rows for this very list): skip building it        */
   const void* w_planes;                     /* optional: the weight planes rgcn_layer_fwd prepared (dgrad reads them) */
+  int32_t a_compact;                        /* row-sparse form: A_hi / A_lo are the compact planes of the listed-rows
+                                               forward over this very list (no copy; Ac_* unused)                   */
 } rgcn_layer_bwd_args;
 
 /* Compaction step of the row-sparse backward (csrc/rowsparse.cu), also callable on its own:
@@ -377,6 +400,11 @@ int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t lda, int32_
                          void* out_bf16, int64_t ld_out_bf16, rgcn_stream_t stream);
 int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const void* w_planes, int32_t K,
                            int64_t n_rows, float* gA, int64_t ldga, int32_t mode, rgcn_stream_t stream);
+/* rgcn_transform_fwd_w over a COMPACT operand [n_rows, K] whose row c belongs to node out_rows[c] (c < n_list; the rows
+ * beyond are padding): the epilogue stores row c at out[out_rows[c], :]; only the listed rows of `out` are written. */
+int rgcn_transform_fwd_w_rows(const void* A_hi, const void* A_lo, int64_t lda, int32_t K, const void* w_planes,
+                              const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
+                              int32_t mode, const int64_t* out_rows, int64_t n_list, rgcn_stream_t stream);
 
 int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream);
 int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream);

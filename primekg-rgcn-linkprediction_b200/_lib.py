@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librgcn_b200.so")
 
-ABI_VERSION = 6          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
+ABI_VERSION = 7          # RGCN_B200_ABI_VERSION of include/rgcn_b200.h
 
 _lock = threading.Lock()
 _lib = None
@@ -42,7 +42,8 @@ class LayerFwdArgs(C.Structure):
                 ("peer_out_host", p), ("n_peer", i32), ("peer_row0", i64), ("peer_ld", i64),
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
                 ("w_planes", p), ("w_planes_bytes", sz), ("pipeline", i32),
-                ("x_bf16", p), ("ld_x_bf16", i64), ("out_bf16", p), ("ld_out_bf16", i64)]
+                ("x_bf16", p), ("ld_x_bf16", i64), ("out_bf16", p), ("ld_out_bf16", i64),
+                ("rows", p), ("n_list", i64), ("slot", p)]
 
 
 class MaskedPlanesOut(C.Structure):
@@ -60,7 +61,7 @@ class LayerBwdArgs(C.Structure):
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
                 ("rows", p), ("n_list", i64), ("slot", p), ("Ac_hi", p), ("Ac_lo", p), ("ldac", i64),
                 ("next_G", C.POINTER(MaskedPlanesOut)), ("g_ready", i32), ("n_colsum_ready", i32), ("slot_ready", i32),
-                ("w_planes", p)]
+                ("w_planes", p), ("a_compact", i32)]
 
 # name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
 PROTOTYPES = {
@@ -87,6 +88,10 @@ PROTOTYPES = {
     "rgcn_transform_fwd_w": (C.c_int, [p, p, i64, i32, p, p, i32, i64, i32, p, i64, i32, C.c_float, C.c_uint32, p, i64,
                                        p, i32, i64, i64, p, i64, p]),
     "rgcn_aggregate_fwd_bf16": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, i64, i64, i32, p, sz, p]),
+    "rgcn_rows_list_build": (C.c_int, [p, p, i64, i64, p, p, p]),
+    "rgcn_aggregate_fwd_list": (C.c_int, [PCSR, p, i64, i32, p, p, i64, i32, p, i64, p, i64, p, p, sz, p]),
+    "rgcn_aggregate_fwd_bf16_list": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, p, i64, p, p, sz, p]),
+    "rgcn_transform_fwd_w_rows": (C.c_int, [p, p, i64, i32, p, p, i32, i64, i32, p, i64, i32, p, i64, p]),
     "rgcn_transform_dgrad_w": (C.c_int, [p, p, i64, i32, p, i32, i64, p, i64, i32, p]),
     "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
     "rgcn_rows_compact_size": (i64, [i64]),

@@ -44,7 +44,8 @@ class _RGCNLayerFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x_src, x_root, W, root, bias, graph: RelGraph, relu: bool, mode: str, drop=None, in_mask_scale=None):
+    def forward(ctx, x_src, x_root, W, root, bias, graph: RelGraph, relu: bool, mode: str, drop=None, in_mask_scale=None,
+                listed=None):
         """x_src [n_src, d_in]: rows the edges gather from; x_root [n_dst, d_in]: the rows being updated (self-loop
         term).  On one GPU they are the same tensor; on a destination-range shard x_src is the all-gathered matrix."""
         R, d_in, d_out = W.shape
@@ -64,8 +65,12 @@ class _RGCNLayerFn(torch.autograd.Function):
             if x16 is None:
                 x16 = ops.to_bf16(x_src.detach())
         want16 = bool(use16 and relu and d_out % 8 == 0)
+        # listed = (rows, slot): only these output rows will be read (the decoder's head / tail rows): walk and transform
+        # them alone; the planes come back compact, in list order — what the row-sparse backward wants
+        ctx.listed = listed if (listed is not None and shared and p_drop == 0.0 and not want16) else None
+        rows_l, slot_l = ctx.listed if ctx.listed is not None else (None, None)
         res = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr,
-                            x_bf16=x16, want_out_bf16=want16)
+                            x_bf16=x16, want_out_bf16=want16, rows=rows_l, slot=slot_l)
         out, A, wp = res[:3]
         if want16 and res[3] is not None:
             rowsparse.announce_bf16(out, res[3])
@@ -89,7 +94,14 @@ class _RGCNLayerFn(torch.autograd.Function):
         need_x = need_src or need_root_x
         # gO zero outside a short, announced row list (the decoder's backward, rowsparse.py): compact backward
         rows = slot = None
-        if out is None and ctx.shared and graph.n_src == graph.n_dst:
+        a_compact = False
+        if ctx.listed is not None:
+            # the forward computed the listed rows only (the others were never defined, nothing may flow into them): the
+            # compaction of gO runs over the forward's own list, and its compact planes are the weight gradient's operand
+            rowsparse.claim(gO)
+            rows, slot = ctx.listed
+            a_compact = True
+        elif out is None and ctx.shared and graph.n_src == graph.n_dst:
             claimed = rowsparse.claim(gO)
             if claimed is not None:
                 rows, slot = claimed
@@ -101,7 +113,7 @@ class _RGCNLayerFn(torch.autograd.Function):
         res = ops.layer_bwd(
             graph, gO.contiguous(), out, mask_scale, (A_hi, A_lo), W.reshape(K1, d_out), root, d_in, mode,
             need_x=need_x, add_root_term=ctx.shared, need_w=need_w_any, need_b=need_w_any, rows=rows, g_ready=g_ready,
-            next_mask=next_mask, slot=slot, w_planes=ctx.w_planes,
+            next_mask=next_mask, slot=slot, w_planes=ctx.w_planes, a_compact=a_compact,
             gx_out=ops.param_grad(graph.n_src, d_in, device=gO.device) if (need_x and ctx.x_is_param) else None)
         gx, gA, gWf, groot, gb = res[:5]
         if next_mask is not None:
@@ -114,7 +126,7 @@ class _RGCNLayerFn(torch.autograd.Function):
                 gx_src = gx if need_src else None             # full-length partial, reduced by the caller
                 gx_root = gA[:, K1:]
         gW = gWf.view(R, d_in, d_out) if gWf is not None else None
-        return gx_src, gx_root, gW, groot, gb, None, None, None, None, None
+        return gx_src, gx_root, gW, groot, gb, None, None, None, None, None, None
 
 
 class _RGCNBasisLayerFn(torch.autograd.Function):
@@ -244,9 +256,11 @@ class RGCNConv(nn.Module):
         return (float(p), self._drop_seed, ctr)
 
     def forward_graph(self, x: torch.Tensor, graph: RelGraph, relu: bool = False, dropout_p: float = 0.0,
-                      in_mask_scale: Optional[float] = None) -> torch.Tensor:
+                      in_mask_scale: Optional[float] = None, listed=None) -> torch.Tensor:
         """``dropout_p`` > 0 (training): ReLU and dropout are applied in the transform's epilogue (needs relu=True).
-        ``in_mask_scale``: ``x`` is the fused ReLU / dropout output of the previous layer (whose 1 / (1 - p) this is)."""
+        ``in_mask_scale``: ``x`` is the fused ReLU / dropout output of the previous layer (whose 1 / (1 - p) this is).
+        ``listed`` = (rows, slot) from ``ops.rows_list_build``: the caller reads ONLY these rows of the result (the last
+        layer under a link-prediction decoder, reference src/models/rgcn.py:325-326); every other row is left undefined."""
         if x.dim() != 2 or x.size(1) != self.in_channels:
             raise ValueError(f"x must be [N, {self.in_channels}]")
         if graph.R != self.num_relations:
@@ -257,8 +271,10 @@ class RGCNConv(nn.Module):
         if self._use_z_form(graph):
             return _RGCNBasisLayerFn.apply(x, self.weight, self.comp, self.root, self.bias, graph, relu,
                                            self.mode or default_mode(), drop)
+        if listed is not None and (relu or dropout_p > 0.0 or not ops.prepared_weights() or not rowsparse.enabled()):
+            listed = None
         return _RGCNLayerFn.apply(x, x, self.relation_weights(), self.root, self.bias, graph, relu,
-                                  self.mode or default_mode(), drop, in_mask_scale)
+                                  self.mode or default_mode(), drop, in_mask_scale, listed)
 
     def _use_z_form(self, graph: RelGraph) -> bool:
         """B-accumulator form of the basis decomposition (``PRIMEKG_RGCN_BASIS_FORM=z``).  It halves the layer's

@@ -81,6 +81,14 @@ struct AggParams {
   const float* mp_mask; int64_t ld_mp_mask; float mp_scale;
   void* mp_hi; void* mp_lo; int64_t ld_mp;
   float* mp_colsum;          // nullable, [gridDim.x, d]
+  // Listed-rows forward (LIST instantiations; the last layer of a link-prediction step is only read at the 2 * batch
+  // head / tail rows): position c of the launch walks row list[c] and writes OUTPUT row c of a compact [m_c, ...] matrix;
+  // positions >= n_list (padding up to a multiple of 128) get all-zero rows.
+  const int64_t* list;
+  int64_t n_list;
+  // hub pass filter (nullable): node -> first list position map; chunks of rows with hub_filter[row] == hub_unlisted are skipped
+  const int32_t* hub_filter;
+  int32_t hub_unlisted;
 };
 
 // ---- hub chunks: one block per chunk --------------------------------------------------------
@@ -94,6 +102,7 @@ __global__ void __launch_bounds__(256) hub_partial_kernel(const AggParams p) {
   const int4 t = __ldg(reinterpret_cast<const int4*>(p.chunk_table) + chunk);
   const int key = t.x;
   const int r = key % p.R;
+  if (p.hub_filter && __ldg(p.hub_filter + key / p.R) == p.hub_unlisted) return;     // (block-uniform) nobody reads this row
   const int seg_beg = __ldg(p.rowptr + key), seg_end = __ldg(p.rowptr + key + 1);
   const int c_beg = seg_beg + (chunk - t.y) * kHubChunk;
   const int c_end = min(c_beg + kHubChunk, seg_end);
@@ -217,9 +226,10 @@ constexpr int agg_min_blocks(int G, int vpl, int mix, bool w) {
 }
 
 // MP: the masked-planes second output (MIX_SUM only) is compiled in; one resident block less buys it the registers
-template <int G, int VPL, int MIX, bool W, bool SLOT = false, bool MP = false>
+template <int G, int VPL, int MIX, bool W, bool SLOT = false, bool MP = false, bool LIST = false>
 __global__ void __launch_bounds__(256, agg_min_blocks(G, VPL, MIX, W) - ((MP && agg_min_blocks(G, VPL, MIX, W) > 1) ? 1 : 0))
 aggregate_rows_kernel(const AggParams p) {
+  static_assert(!LIST || (MIX == MIX_NONE && !W && !SLOT && !MP), "the listed-rows walk is the unmixed forward form");
   pdl_enter();
   constexpr int GROUPS = 256 / G;
   constexpr int NB = (MIX == MIX_BASIS) ? kMaxBasis : 1;
@@ -244,8 +254,20 @@ aggregate_rows_kernel(const AggParams p) {
     if (with_cs)
       for (int t = lane; t < p.d; t += G) s_comp[grp * p.d + t] = 0.f;
   } else {
-  // longest rows first: neighbouring groups get rows of similar length and the long walks start at time zero
-  if (p.row_order) row = __ldg(p.row_order + row);
+  const int64_t orow = row;                      // LIST: the output row is the list position
+  if (LIST) {
+    if (row >= p.n_list) {
+      // padding position: an all-zero operand row (stale memory could hold NaN patterns)
+      const int nblk = p.R + (p.root_rows ? 1 : 0);
+      for (int b = 0; b < nblk; ++b)
+        for (int vi = lane; vi < (p.d >> 2); vi += G) store_vec(p, orow, b * p.block_stride + vi * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+      return;
+    }
+    row = __ldg(p.list + row);
+  } else if (p.row_order) {
+    // longest rows first: neighbouring groups get rows of similar length and the long walks start at time zero
+    row = __ldg(p.row_order + row);
+  }
   const int R = p.R, d = p.d, nvec = p.d >> 2;
   const int64_t key0 = row * R;
   const int32_t* __restrict__ rowptr = p.rowptr + key0;
@@ -266,7 +288,7 @@ aggregate_rows_kernel(const AggParams p) {
   if (MIX == MIX_NONE && p.root_rows) {
 #pragma unroll
     for (int k = 0; k < VPL; ++k)
-      if (act[k]) store_vec(p, row, R * p.block_stride + vcol[k], ldg4(p.root_rows + row * p.ld_root + vcol[k]));
+      if (act[k]) store_vec(p, LIST ? orow : row, R * p.block_stride + vcol[k], ldg4(p.root_rows + row * p.ld_root + vcol[k]));
   }
   float4 mix[NB][VPL];
   if (MIX != MIX_NONE) {
@@ -476,7 +498,7 @@ aggregate_rows_kernel(const AggParams p) {
       if (MIX == MIX_NONE) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k)
-          if (act[k]) store_vec(p, row, r * p.block_stride + vcol[k], acc[k]);
+          if (act[k]) store_vec(p, LIST ? orow : row, r * p.block_stride + vcol[k], acc[k]);
       } else if (MIX == MIX_SUM) {
 #pragma unroll
         for (int k = 0; k < VPL; ++k) add4(mix[0][k], acc[k]);
@@ -673,6 +695,7 @@ __global__ void __launch_bounds__(256) hub_partial_bf16_kernel(const AggParams p
   const int chunk = blockIdx.x;
   const int4 t = __ldg(reinterpret_cast<const int4*>(p.chunk_table) + chunk);
   const int key = t.x;
+  if (p.hub_filter && __ldg(p.hub_filter + key / p.R) == p.hub_unlisted) return;     // (block-uniform) nobody reads this row
   const int seg_beg = __ldg(p.rowptr + key), seg_end = __ldg(p.rowptr + key + 1);
   const int c_beg = seg_beg + (chunk - t.y) * kHubChunk;
   const int c_end = min(c_beg + kHubChunk, seg_end);
@@ -725,7 +748,7 @@ __global__ void __launch_bounds__(256) hub_partial_bf16_kernel(const AggParams p
   }
 }
 
-template <int G, int VPL>
+template <int G, int VPL, bool LIST = false>
 __global__ void __launch_bounds__(256, (VPL == 1 ? 4 : 3)) aggregate_rows_bf16_kernel(const AggParams p) {
   pdl_enter();
   constexpr int GROUPS = 256 / G;
@@ -737,7 +760,19 @@ __global__ void __launch_bounds__(256, (VPL == 1 ? 4 : 3)) aggregate_rows_bf16_k
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
   int64_t row = p.row_begin + (int64_t)blockIdx.x * GROUPS + grp;
   if (row >= p.row_end) return;
-  if (p.row_order) row = __ldg(p.row_order + row);
+  const int64_t orow = row;                           // LIST: the output row is the list position
+  if (LIST) {
+    if (row >= p.n_list) {                            // padding position: an all-zero operand row
+      const int nblk = p.R + (p.root_rows ? 1 : 0);
+      for (int b = 0; b < nblk; ++b)
+        for (int vi = lane; vi < (p.d >> 3); vi += G)
+          *reinterpret_cast<uint4*>(O + orow * p.ldo + b * p.block_stride + vi * 8) = make_uint4(0u, 0u, 0u, 0u);
+      return;
+    }
+    row = __ldg(p.list + row);
+  } else if (p.row_order) {
+    row = __ldg(p.row_order + row);
+  }
   const int R = p.R, d = p.d, nvec = p.d >> 3;
   const int64_t key0 = row * R;
   const int32_t* __restrict__ rowptr = p.rowptr + key0;
@@ -755,7 +790,7 @@ __global__ void __launch_bounds__(256, (VPL == 1 ? 4 : 3)) aggregate_rows_bf16_k
     const __nv_bfloat16* __restrict__ xr = reinterpret_cast<const __nv_bfloat16*>(p.root_rows) + row * p.ld_root;
 #pragma unroll
     for (int k = 0; k < VPL; ++k)
-      if (act[k]) *reinterpret_cast<uint4*>(O + row * p.ldo + R * p.block_stride + vcol[k]) = __ldg(reinterpret_cast<const uint4*>(xr + vcol[k]));
+      if (act[k]) *reinterpret_cast<uint4*>(O + (LIST ? orow : row) * p.ldo + R * p.block_stride + vcol[k]) = __ldg(reinterpret_cast<const uint4*>(xr + vcol[k]));
   }
   const int row_end = __ldg(rowptr + R);
   int wbase = -(1 << 30), wi0 = 0, wi1 = 0;
@@ -830,7 +865,7 @@ __global__ void __launch_bounds__(256, (VPL == 1 ? 4 : 3)) aggregate_rows_bf16_k
       }
 #pragma unroll
       for (int k = 0; k < VPL; ++k)
-        if (act[k]) *reinterpret_cast<uint4*>(O + row * p.ldo + r * p.block_stride + vcol[k]) = pack_bf8(acc[k]);
+        if (act[k]) *reinterpret_cast<uint4*>(O + (LIST ? orow : row) * p.ldo + r * p.block_stride + vcol[k]) = pack_bf8(acc[k]);
     }
   }
 }
@@ -845,7 +880,8 @@ static int launch_agg_bf16(AggParams p, int n_chunks, cudaStream_t st) {
   }
   const int64_t n_walk = p.row_end - p.row_begin;
   if (n_walk <= 0) return RGCN_OK;
-  RGCN_CUDA(launch_pdl(aggregate_rows_bf16_kernel<G, VPL>, dim3((unsigned)((n_walk + GROUPS - 1) / GROUPS)), dim3(256), 0, st, p));
+  if (p.list) RGCN_CUDA(launch_pdl(aggregate_rows_bf16_kernel<G, VPL, true>, dim3((unsigned)((n_walk + GROUPS - 1) / GROUPS)), dim3(256), 0, st, p));
+  else RGCN_CUDA(launch_pdl(aggregate_rows_bf16_kernel<G, VPL>, dim3((unsigned)((n_walk + GROUPS - 1) / GROUPS)), dim3(256), 0, st, p));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }
@@ -905,11 +941,24 @@ static int launch_agg(const AggParams& p_in, int mix, int n_chunks, cudaStream_t
   if (!p.range_mode) { p.row_begin = 0; p.row_end = p.n_rows; }
   if (p.no_hub_pass) n_chunks = 0;
   const int64_t n_walk = p.row_end - p.row_begin;
-  if (!p.slot && !p.mp_hi && n_chunks > 0 && p.n_rows > 0 && n_walk == p.n_rows && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
+  if (!p.list && !p.slot && !p.mp_hi && n_chunks > 0 && p.n_rows > 0 && n_walk == p.n_rows && mix != MIX_BASIS && overlap_hubs_enabled() && (mix == MIX_NONE || p.out_mode == 0)) {
     const bool w = p.edge_w != nullptr;
     if (mix == MIX_NONE)
       return w ? launch_agg_overlapped<G, VPL, MIX_NONE, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_NONE, false>(p, n_chunks, st);
     return w ? launch_agg_overlapped<G, VPL, MIX_SUM, true>(p, n_chunks, st) : launch_agg_overlapped<G, VPL, MIX_SUM, false>(p, n_chunks, st);
+  }
+  if (p.list) {
+    // listed-rows walk: forward, unmixed, unweighted (the last layer of a link-prediction step)
+    if (mix != MIX_NONE || p.edge_w || p.slot || p.mp_hi) { set_error("aggregate: the listed-rows walk serves the unmixed forward only"); return RGCN_EINVAL; }
+    if (n_chunks > 0) {
+      RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, false>, dim3(n_chunks), dim3(256), 0, st, p));
+      RGCN_LAUNCH_CHECK();
+    }
+    if (n_walk <= 0) return RGCN_OK;
+    RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, false, false, false, true>, dim3((unsigned)((n_walk + GROUPS - 1) / GROUPS)),
+                         dim3(256), 0, st, p));
+    RGCN_LAUNCH_CHECK();
+    return RGCN_OK;
   }
   if (p.slot) {
     // row-sparse gather: backward form only (summed relations, weighted edges)
@@ -1184,4 +1233,66 @@ static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg
     p.mp_hi = mp->hi; p.mp_lo = mp->lo; p.ld_mp = mp->ldp; p.mp_colsum = mp->colsum_partial;
   }
   return dispatch_agg(p, MIX_SUM, gt->n_chunks, (cudaStream_t)stream);
+}
+
+// ---- listed-rows forward walk --------------------------------------------------------------------------------------------
+// The last layer of the reference's training step is only read at the 2 * batch head / tail rows of its output
+// (src/models/rgcn.py:325-326): the walk visits the listed rows only and writes a COMPACT operand [m_c, (R+1) d]
+// (m_c = rgcn_rows_compact_size(n_list); position c = row rows[c], duplicates are simply computed twice, padding positions
+// are zero rows).  slot (nullable): node -> first list position or m_c, used to skip the hub chunks of unlisted rows.
+static int aggregate_fwd_list_impl(const rgcn_csr_t* g, const void* X, int64_t ldx, int32_t d, bool x_bf16, void* H, void* H_lo,
+                                   int64_t ldh, int32_t out_mode, const void* x_root, int64_t ld_x_root, const int64_t* rows,
+                                   int64_t n_list, const int32_t* slot, void* workspace, size_t workspace_bytes,
+                                   rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(g && g->rowptr && (g->idx || g->E == 0) && g->R >= 1 && g->n_rows >= 0 && g->hub_threshold >= 1, "aggregate_fwd_list: bad CSR");
+  RGCN_CHECK_ARG(rows && n_list > 0 && n_list < (1ll << 30), "aggregate_fwd_list: bad row list");
+  const int64_t m_c = rgcn_rows_compact_size(n_list);
+  RGCN_CHECK_ARG(g->n_chunks == 0 || (g->hub_keys && g->hub_chunk_ptr && g->n_hubs > 0 && g->chunk_table), "aggregate_fwd_list: hub plan missing");
+  if (g->n_chunks > 0 && (!workspace || workspace_bytes < (size_t)g->n_chunks * d * sizeof(float))) {
+    set_error("aggregate_fwd_list: workspace too small"); return RGCN_EWORKSPACE;
+  }
+  AggParams p{};
+  p.rowptr = g->rowptr; p.idx = g->idx;
+  p.hub_keys = g->hub_keys; p.hub_chunk_ptr = g->hub_chunk_ptr; p.n_hubs = g->n_hubs; p.chunk_table = g->chunk_table;
+  p.hub_threshold = g->hub_threshold;
+  p.n_rows = g->n_rows; p.R = g->R;
+  p.F = (const float*)X; p.ldf = ldx; p.src_rel_stride = 0; p.d = d; p.block_stride = d;
+  p.O = H; p.O_lo = H_lo; p.ldo = ldh; p.out_mode = out_mode; p.partials = (float*)workspace;
+  p.root_rows = (const float*)x_root; p.ld_root = ld_x_root;
+  p.range_mode = 1; p.row_begin = 0; p.row_end = m_c;
+  p.list = rows; p.n_list = n_list; p.hub_filter = slot; p.hub_unlisted = (int32_t)m_c;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!x_bf16) return dispatch_agg(p, MIX_NONE, g->n_chunks, st);
+  const int nvec = d >> 3;
+  if (nvec <= 4) return launch_agg_bf16<4, 1>(p, g->n_chunks, st);
+  if (nvec <= 8) return launch_agg_bf16<8, 1>(p, g->n_chunks, st);
+  if (nvec <= 16) return launch_agg_bf16<16, 1>(p, g->n_chunks, st);
+  if (nvec <= 32) return launch_agg_bf16<32, 1>(p, g->n_chunks, st);
+  if (nvec <= 64) return launch_agg_bf16<32, 2>(p, g->n_chunks, st);
+  return launch_agg_bf16<32, 4>(p, g->n_chunks, st);
+}
+
+extern "C" int rgcn_aggregate_fwd_list(const rgcn_csr_t* g, const float* X, int64_t ldx, int32_t d, void* H, void* H_lo,
+                                       int64_t ldh, int32_t out_mode, const float* x_root, int64_t ld_x_root,
+                                       const int64_t* rows, int64_t n_list, const int32_t* slot, void* workspace,
+                                       size_t workspace_bytes, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(d >= 4 && d <= 1024 && d % 4 == 0, "aggregate_fwd_list: feature width d=%d must be a multiple of 4 in [4,1024]", d);
+  RGCN_CHECK_ARG(X && ldx % 4 == 0 && ((uintptr_t)X & 15) == 0, "aggregate_fwd_list: feature matrix must be 16-byte aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(!x_root || (((uintptr_t)x_root & 15) == 0 && ld_x_root % 4 == 0), "aggregate_fwd_list: x_root misaligned");
+  RGCN_CHECK_ARG(out_mode >= 0 && out_mode <= 2, "aggregate_fwd_list: out_mode must be 0 (fp32), 1 (bf16) or 2 (bf16 hi+lo)");
+  RGCN_CHECK_ARG(H && ((uintptr_t)H & (out_mode ? 7 : 15)) == 0 && ldh % 4 == 0, "aggregate_fwd_list: output must be aligned with ld %% 4 == 0");
+  RGCN_CHECK_ARG(out_mode != 2 || (H_lo && ((uintptr_t)H_lo & 7) == 0), "aggregate_fwd_list: out_mode 2 needs the lo plane");
+  return aggregate_fwd_list_impl(g, X, ldx, d, false, H, H_lo, ldh, out_mode, x_root, ld_x_root, rows, n_list, slot, workspace,
+                                 workspace_bytes, stream);
+}
+
+extern "C" int rgcn_aggregate_fwd_bf16_list(const rgcn_csr_t* g, const void* X16, int64_t ldx, int32_t d, void* H_hi, int64_t ldh,
+                                            const void* x_root16, int64_t ld_x_root, const int64_t* rows, int64_t n_list,
+                                            const int32_t* slot, void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(d >= 8 && d <= 1024 && d % 8 == 0, "aggregate_fwd_bf16_list: d=%d must be a multiple of 8 in [8, 1024]", d);
+  RGCN_CHECK_ARG(X16 && ((uintptr_t)X16 & 15) == 0 && ldx % 8 == 0, "aggregate_fwd_bf16_list: features must be 16-byte aligned rows");
+  RGCN_CHECK_ARG(H_hi && ((uintptr_t)H_hi & 15) == 0 && ldh % 8 == 0, "aggregate_fwd_bf16_list: output plane must be 16-byte aligned, ld %% 8 == 0");
+  RGCN_CHECK_ARG(!x_root16 || (((uintptr_t)x_root16 & 15) == 0 && ld_x_root % 8 == 0), "aggregate_fwd_bf16_list: x_root misaligned");
+  return aggregate_fwd_list_impl(g, X16, ldx, d, true, H_hi, nullptr, ldh, 1, x_root16, ld_x_root, rows, n_list, slot, workspace,
+                                 workspace_bytes, stream);
 }

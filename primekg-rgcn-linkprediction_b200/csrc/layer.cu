@@ -153,6 +153,23 @@ extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream
                                 a->dropout_p > 0.f ? a->dropout_counter : nullptr, stream);
   if (rc) return rc;
   void* A_lo = a->mode == 0 ? a->A_lo : nullptr;
+  if (a->rows) {
+    // listed-rows form: only the rows the caller will read (the 2 * batch head / tail rows of a link-prediction step,
+    // src/models/rgcn.py:325-326) are walked and transformed; A comes back COMPACT [m_c, K] in list order, which is the
+    // operand layout the row-sparse backward wants (rgcn_layer_bwd, a_compact)
+    RGCN_CHECK_ARG(a->n_list > 0 && a->n_peer == 0 && a->dropout_p == 0.f, "layer_fwd: the listed-rows form excludes peers and dropout");
+    const int64_t m_c = rgcn_rows_compact_size(a->n_list);
+    const bool g16l = a->mode == 1 && a->x_bf16 && a->d_in % 8 == 0 && a->lda % 8 == 0 && a->x_src == a->x_root;
+    if (g16l)
+      rc = rgcn_aggregate_fwd_bf16_list(a->csr, a->x_bf16, a->ld_x_bf16, a->d_in, a->A_hi, a->lda, a->x_bf16, a->ld_x_bf16, a->rows,
+                                        a->n_list, a->slot, a->agg_workspace, a->agg_workspace_bytes, stream);
+    else
+      rc = rgcn_aggregate_fwd_list(a->csr, a->x_src, a->ld_x_src, a->d_in, a->A_hi, A_lo, a->lda, out_mode, a->x_root, a->ld_x_root,
+                                   a->rows, a->n_list, a->slot, a->agg_workspace, a->agg_workspace_bytes, stream);
+    if (rc) return rc;
+    return rgcn_transform_fwd_w_rows(a->A_hi, A_lo, a->lda, K, a->w_planes, a->bias, a->relu, m_c, a->d_out, a->out, a->ldo,
+                                     a->mode, a->rows, a->n_list, stream);
+  }
   if (fused_layer_fwd_eligible(a)) {
     // hub chunks first (their partials are what the fused kernel's row walk adds for the long segments)
     if (a->csr->n_chunks > 0) {
@@ -225,14 +242,19 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(!a->relu_mask && !a->g_ready, "layer_bwd: the row-sparse form serves a layer without ReLU (the last one)");
   // add_root_term = 0 (a destination-range shard: sources and destinations live in different id spaces): the root-term
   // gradient stays in the compact gA[:, R d_in:] rows for the caller
-  RGCN_CHECK_ARG(!need_w || (a->Ac_hi && (a->mode == 1 || a->Ac_lo)), "layer_bwd: compact operand planes missing");
+  // a_compact: the forward was the listed-rows form over this very list, so A already is the compact operand
+  const bool copy_a = need_w && !a->a_compact;
+  RGCN_CHECK_ARG(!copy_a || (a->Ac_hi && (a->mode == 1 || a->Ac_lo)), "layer_bwd: compact operand planes missing");
   int rc = rgcn_rows_compact(a->rows, a->n_list, a->n_dst, a->slot, a->g_out, a->ld_g_out, a->d_out, a->G_hi,
                              a->mode == 0 ? a->G_lo : nullptr, a->ldg, a->A_hi, a->mode == 0 ? a->A_lo : nullptr, a->lda, K,
-                             need_w ? a->Ac_hi : nullptr, (need_w && a->mode == 0) ? a->Ac_lo : nullptr, a->ldac,
+                             copy_a ? a->Ac_hi : nullptr, (copy_a && a->mode == 0) ? a->Ac_lo : nullptr, a->ldac,
                              a->g_bias ? a->colsum_partial : nullptr, a->gA ? a->gA + m_c * a->ld_gA : nullptr, a->gA ? K : 0,
                              a->slot_ready, stream);
   if (rc) return rc;
-  return dgrad_walk_wgrad(a, m_c, a->Ac_hi, a->Ac_lo, a->ldac, (int32_t)rgcn_rows_compact_blocks(a->n_list), [&]() {
+  const void* Aw_hi = a->a_compact ? a->A_hi : a->Ac_hi;
+  const void* Aw_lo = a->a_compact ? a->A_lo : a->Ac_lo;
+  const int64_t ldw = a->a_compact ? a->lda : a->ldac;
+  return dgrad_walk_wgrad(a, m_c, Aw_hi, Aw_lo, ldw, (int32_t)rgcn_rows_compact_blocks(a->n_list), [&]() {
     return rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c,
                                    a->add_root_term ? a->gA + K1 : nullptr, a->ld_gA, a->g_x, a->ld_g_x, a->next_G,
                                    a->agg_workspace, a->agg_workspace_bytes, stream);

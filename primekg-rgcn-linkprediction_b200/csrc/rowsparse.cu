@@ -35,6 +35,20 @@ __global__ void __launch_bounds__(256) rows_slot_min_kernel(const int64_t* __res
   if (c < n_list) atomicMin(slot + rows[c], (int32_t)c);
 }
 
+// rows[c] = head[c] (c < n) or tail[c - n], an out-of-range index parked on row 0 (which it never owns);
+// slot[rows[c]] = min over the valid positions that list the node
+__global__ void __launch_bounds__(256) rows_list_kernel(const int64_t* __restrict__ head, const int64_t* __restrict__ tail,
+                                                        int64_t n, int64_t n_nodes, int64_t* __restrict__ rows,
+                                                        int32_t* __restrict__ slot) {
+  pdl_enter();
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c >= 2 * n) return;
+  const int64_t v = c < n ? head[c] : tail[c - n];
+  const bool ok = v >= 0 && v < n_nodes;
+  rows[c] = ok ? v : 0;
+  if (ok) atomicMin(slot + v, (int32_t)c);
+}
+
 // 8 warps per block, one compact row per warp: G planes from g_out, operand planes copied, column sums of G per block
 constexpr int kRowsPerBlock = 8;
 
@@ -167,6 +181,22 @@ extern "C" int rgcn_rows_compact(const int64_t* rows, int64_t n_list, int64_t n_
   p.zero_row = zero_row; p.zero_cols = zero_cols;
   const size_t smem = (size_t)8 * (d_out / 4) * sizeof(float4);
   RGCN_CUDA(launch_pdl(rows_compact_kernel, dim3((unsigned)rgcn_rows_compact_blocks(n_list)), dim3(256), smem, st, p));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
+// Row list of a link-prediction batch for the listed-rows FORWARD of the last layer (rgcn_layer_fwd, rows != NULL):
+// rows [2 n] = heads then tails (the order rgcn_link_loss_bwd_rows uses), slot [n_nodes] = node -> first position or m_c.
+extern "C" int rgcn_rows_list_build(const int64_t* head, const int64_t* tail, int64_t n_pairs, int64_t n_nodes,
+                                    int64_t* rows, int32_t* slot, rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(head && tail && rows && slot && n_pairs > 0 && n_nodes > 0 && 2 * n_pairs < (1ll << 30), "rows_list_build: bad arguments");
+  const int64_t m_c = rgcn_rows_compact_size(2 * n_pairs);
+  cudaStream_t st = (cudaStream_t)stream;
+  RGCN_CUDA(launch_pdl(rows_slot_fill_kernel, dim3((unsigned)((n_nodes + 255) / 256)), dim3(256), 0, st, slot, n_nodes,
+                       (int32_t)m_c, (float*)nullptr, 0));
+  RGCN_LAUNCH_CHECK();
+  RGCN_CUDA(launch_pdl(rows_list_kernel, dim3((unsigned)((2 * n_pairs + 255) / 256)), dim3(256), 0, st, head, tail, n_pairs, n_nodes,
+                       rows, slot));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
 }

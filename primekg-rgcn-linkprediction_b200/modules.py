@@ -25,6 +25,11 @@ from .conv import RGCNConv
 from .graph import get_graph
 
 
+def sparse_forward_enabled() -> bool:
+    """Listed-rows forward of the last layer in ``DrugDiseaseModel``'s training call (it needs the row-sparse backward)."""
+    return os.environ.get("PRIMEKG_RGCN_SPARSE_FWD", "1") != "0" and rowsparse.enabled()
+
+
 def _need_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{what}: this is the B200 (sm_100a) implementation and has no CPU path; "
@@ -94,6 +99,13 @@ class DrugDiseaseRGCN(nn.Module):
 
     def forward(self, edge_index: torch.Tensor, edge_type: torch.Tensor,
                 node_indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self._encode(edge_index, edge_type, node_indices)
+
+    def _encode(self, edge_index, edge_type, node_indices=None, read_rows=None) -> torch.Tensor:
+        """``read_rows`` = (head, tail): the caller — ``DrugDiseaseModel``'s training call — reads ONLY these rows of the
+        result (``node_embeddings[head]``, ``[tail]``, reference :325-326).  The last layer then walks and transforms the
+        listed rows alone (``PRIMEKG_RGCN_SPARSE_FWD=0`` or ``PRIMEKG_RGCN_SPARSE_BWD=0``: all rows); every other row of
+        the returned matrix is UNDEFINED, which is why only the model's own forward uses this form."""
         x = self.node_embeddings.weight if node_indices is None else self.node_embeddings(node_indices)
         _need_cuda(x, "DrugDiseaseRGCN.forward")
         graph = get_graph(edge_index, edge_type, x.size(0), self.num_relations)
@@ -107,12 +119,18 @@ class DrugDiseaseRGCN(nn.Module):
             if hit is not None and hit[1] is graph and hit[0] == key and hit[2]._version == hit[3]:
                 return hit[2]
         layers = list(self._layers())
+        listed = None
+        if read_rows is not None and not cacheable and node_indices is None and sparse_forward_enabled():
+            head, tail = read_rows
+            if 0 < 2 * head.numel() <= rowsparse.MAX_FRACTION * x.size(0) and head.numel() == tail.numel():
+                listed = ops.rows_list_build(head, tail, x.size(0))
         in_scale = None         # 1 / (1 - p) of the fused ReLU / dropout that produced x (None: x is not such an output)
         for li, conv in enumerate(layers):
             last = li == len(layers) - 1
             # ReLU and (in training) dropout live in the layer's GEMM epilogue; p == 1 keeps nn.Dropout's all-zero output
             p = self.dropout.p if (self.training and not last) else 0.0
-            x = conv.forward_graph(x, graph, relu=not last, dropout_p=p if p < 1.0 else 0.0, in_mask_scale=in_scale)
+            x = conv.forward_graph(x, graph, relu=not last, dropout_p=p if p < 1.0 else 0.0, in_mask_scale=in_scale,
+                                   listed=listed if last else None)
             in_scale = 1.0 / (1.0 - p) if (not last and p < 1.0) else None
             if not last and p >= 1.0:
                 x = self.dropout(x)
@@ -291,8 +309,15 @@ class DrugDiseaseModel(nn.Module):
         return self._forward_eager(edge_index, edge_type, head_indices, tail_indices, relation_types)
 
     def _forward_eager(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:
-        node_embeddings = self.encoder(edge_index, edge_type)
+        node_embeddings = self._encode_for(edge_index, edge_type, head_indices, tail_indices)
         return self.decoder.score_pairs(node_embeddings, head_indices, tail_indices, relation_types)
+
+    def _encode_for(self, edge_index, edge_type, head_indices, tail_indices) -> torch.Tensor:
+        """Encoder output for a decoder that reads rows ``head`` / ``tail`` only (reference :325-326): with autograd on
+        (a training step) the last layer computes just those rows; eval / no-grad calls keep the full, cached matrix."""
+        if torch.is_grad_enabled() and head_indices.is_cuda and head_indices.numel() == tail_indices.numel():
+            return self.encoder._encode(edge_index, edge_type, None, (head_indices, tail_indices))
+        return self.encoder(edge_index, edge_type)
 
     def invalidate_graphs(self) -> None:
         """Drop the captured training-call graphs (autograph.py), e.g. before freeing the graph tensors."""
@@ -301,7 +326,7 @@ class DrugDiseaseModel(nn.Module):
     def link_loss(self, edge_index, edge_type, head_indices, tail_indices, relation_types, labels):
         """Encoder + fused decoder / loss / accuracy: the whole of src/train.py:291-300 and :321-322 -> (loss, scores,
         n_correct), all on the device."""
-        node_embeddings = self.encoder(edge_index, edge_type)
+        node_embeddings = self._encode_for(edge_index, edge_type, head_indices, tail_indices)
         return self.decoder.link_loss(node_embeddings, head_indices, tail_indices, relation_types, labels)
 
     def predict(self, edge_index, edge_type, head_indices, tail_indices, relation_types) -> torch.Tensor:

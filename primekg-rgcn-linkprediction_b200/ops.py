@@ -514,14 +514,18 @@ def _dp(t: Optional[torch.Tensor]):
 def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch.Tensor, root: torch.Tensor,
               bias: torch.Tensor, relu: bool, mode: str, dropout_p: float = 0.0, dropout_seed: int = 0,
               dropout_ctr: Optional[torch.Tensor] = None, peer_out=None, peer_row0: int = 0, peer_ld: int = 0,
-              pipeline: int = 0, x_bf16: Optional[torch.Tensor] = None, want_out_bf16: bool = False):
+              pipeline: int = 0, x_bf16: Optional[torch.Tensor] = None, want_out_bf16: bool = False,
+              rows: Optional[torch.Tensor] = None, slot: Optional[torch.Tensor] = None):
     """aggregate -> operand planes -> tensor-core transform of one layer in ONE C call (``rgcn_layer_fwd``).
     bf16 mode: ``x_bf16`` = a bf16 copy of x (the walk gathers it: half the bytes); ``want_out_bf16``: also return the
     layer output rounded to bf16 as a fourth result (the next layer's ``x_bf16``).
     Returns (out [n_dst, d_out], (A_hi, A_lo | None), w_planes | None): ``w_planes`` = the layer's weights as bf16 planes,
     converted once by the call; hand it to ``layer_bwd`` (its dgrad then skips the conversion).
     ``pipeline``: 0 = the library decides whether the walk of row chunk c + 1 runs under the transform of chunk c (it does
-    not: measured slower; RGCN_PIPELINE=1 opts in), 1 = never, 2 = always."""
+    not: measured slower; RGCN_PIPELINE=1 opts in), 1 = never, 2 = always.
+    ``rows`` (int64 device list from ``rows_list_build``, with its ``slot`` map): the LISTED-ROWS form — only these rows of
+    the output are computed (``out`` is uninitialised elsewhere) and the returned planes are compact
+    [rows_compact_size(len(rows)), K] in list order; pass them to ``layer_bwd(..., rows=, slot=, a_compact=True)``."""
     lib = _lib.load()
     x_src = _f32c(x_src, "x")
     x_root = x_src if x_root is x_src else _f32c(x_root, "x_root")
@@ -537,7 +541,16 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
     if W2d.numel() != g.R * d_in * d_out or root.numel() != d_in * d_out:
         raise ValueError("weight shapes do not match the operands")
     dev = x_src.device
-    A = alloc_planes(g.n_dst, K, mode, dev)
+    listed = rows is not None
+    if listed:
+        if not prepared_weights() or peer_out or dropout_p > 0 or want_out_bf16:
+            raise ValueError("the listed-rows forward needs prepared weights and excludes peers, dropout and the bf16 output copy")
+        if rows.dtype != torch.int64 or rows.dim() != 1 or not rows.is_contiguous() or rows.numel() == 0:
+            raise ValueError("rows must be a non-empty contiguous int64 list (rows_list_build)")
+        if slot is not None and (slot.dtype != torch.int32 or slot.numel() != g.n_dst or not slot.is_contiguous()):
+            raise ValueError("slot must be a contiguous int32 [n_dst] tensor")
+    n_a = int(lib.rgcn_rows_compact_size(rows.numel())) if listed else g.n_dst
+    A = alloc_planes(n_a, K, mode, dev)
     out = torch.empty(g.n_dst, d_out, dtype=torch.float32, device=dev)
     aws = g.fwd.workspace(d_in)
     gws = _gemm_workspace(dev, g.n_dst, K, d_out)
@@ -556,7 +569,8 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
         out.stride(0), C.cast(peers, C.c_void_p) if peers is not None else None, len(peer_out) if peer_out else 0,
         int(peer_row0), int(peer_ld), _dp(aws), 0 if aws is None else aws.numel() * 4, gws.data_ptr(), gws.numel(),
         _dp(wp), 0 if wp is None else wp.numel(), int(pipeline),
-        _dp(x_bf16), 0 if x_bf16 is None else x_bf16.stride(0), _dp(out16), 0 if out16 is None else out16.stride(0))
+        _dp(x_bf16), 0 if x_bf16 is None else x_bf16.stride(0), _dp(out16), 0 if out16 is None else out16.stride(0),
+        _dp(rows), rows.numel() if listed else 0, _dp(slot) if listed else None)
     _lib.check(lib.rgcn_layer_fwd(C.byref(args), _stream(dev)), "rgcn_layer_fwd")
     if want_out_bf16:
         return out, A, wp, out16
@@ -566,7 +580,8 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
 def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], mask_scale: float, planes, W2d: torch.Tensor,
               root: torch.Tensor, d_in: int, mode: str, need_x: bool, add_root_term: bool, need_w: bool, need_b: bool,
               gx_out: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None, g_ready=None, next_mask=None,
-              slot: Optional[torch.Tensor] = None, w_planes: Optional[torch.Tensor] = None, return_compact: bool = False):
+              slot: Optional[torch.Tensor] = None, w_planes: Optional[torch.Tensor] = None, return_compact: bool = False,
+              a_compact: bool = False):
     """split(gO, mask) -> dgrad -> transposed gather -> wgrad of one layer in ONE C call (``rgcn_layer_bwd``).
     Returns (g_x | None, gA | None, gW2d | None, g_root | None, g_bias | None); ``gA[:, R*d_in:]`` is the root-term
     gradient (already inside g_x when ``add_root_term``).
@@ -575,6 +590,7 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
     ``slot`` (int32 [n]): the node -> first-position map of ``rows``, already built by the decoder's backward.
     ``return_compact`` (row-sparse form): return the compact gA [m_c + 1, K] (row m_c = zeros) instead of None and append
     the slot map to the result — a shard (add_root_term=False) reads its root-term gradient rows from it.
+    ``a_compact`` (row-sparse form): ``planes`` are the compact planes of the listed-rows forward over this very list.
     ``g_ready`` = ((G_hi, G_lo | None), colsum [n, d_out]): this layer's masked output gradient as planes, already written
     by the downstream layer (skips the split pass).  ``next_mask`` = (mask [n_src, d_in], scale): also produce g_x masked
     for the upstream layer; the result gains a sixth entry ((hi, lo | None), colsum)."""
@@ -623,7 +639,9 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         raise ValueError("slot must be a contiguous int32 [n_dst] tensor")
     if not slot_ready:
         slot = torch.empty(n, dtype=torch.int32, device=dev) if sparse else None
-    Ac = alloc_planes(m, K, mode, dev) if (sparse and need_w) else (None, None)
+    if a_compact and (not sparse or A_hi.size(0) != m):
+        raise ValueError("a_compact needs the row list of the listed-rows forward that made the planes")
+    Ac = alloc_planes(m, K, mode, dev) if (sparse and need_w and not a_compact) else (None, None)
     nxt = nxt_struct = None
     if next_mask is not None and need_x:
         nmask, nscale = next_mask
@@ -645,13 +663,28 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         _dp(rows), 0 if rows is None else rows.numel(), _dp(slot), _dp(Ac[0]), _dp(Ac[1]),
         0 if Ac[0] is None else Ac[0].stride(0),
         C.pointer(nxt_struct) if nxt_struct is not None else None, int(g_ready is not None),
-        0 if g_ready is None else colsum.size(0), int(slot_ready), _dp(w_planes))
+        0 if g_ready is None else colsum.size(0), int(slot_ready), _dp(w_planes), int(bool(a_compact)))
     _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
     if sparse and return_compact:
         return gx, gA, gW, groot, gb, slot
     if next_mask is not None:
         return gx, (None if sparse else gA), gW, groot, gb, nxt
     return gx, (None if sparse else gA), gW, groot, gb
+
+
+def rows_list_build(head: torch.Tensor, tail: torch.Tensor, n_nodes: int):
+    """(rows int64 [2 n], slot int32 [n_nodes]) of a link-prediction batch — ``rgcn_rows_list_build``: heads then tails
+    (out-of-range indices parked on row 0), slot = node -> first list position or rows_compact_size(2 n)."""
+    lib = _lib.load()
+    head, tail = _idx(head, "head").reshape(-1), _idx(tail, "tail").reshape(-1)
+    n = head.numel()
+    if tail.numel() != n or n == 0:
+        raise ValueError("head and tail must be non-empty and equally long")
+    rows = torch.empty(2 * n, dtype=torch.int64, device=head.device)
+    slot = torch.empty(int(n_nodes), dtype=torch.int32, device=head.device)
+    _lib.check(lib.rgcn_rows_list_build(_ptr(head), _ptr(tail), n, int(n_nodes), _ptr(rows), _ptr(slot), _stream(head.device)),
+               "rgcn_rows_list_build")
+    return rows, slot
 
 
 # ---- peer-memory exchange (destination-range partition over the GPUs of one NVSwitch domain) -----------

@@ -64,8 +64,8 @@ def aggregate_bwd(g, gH, d, init=None):
 
 
 def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, dropout_seed=0, dropout_ctr=None,
-              peer_out=None, peer_row0=0, peer_ld=0, pipeline=0, x_bf16=None, want_out_bf16=False):
-    assert not peer_out and not want_out_bf16
+              peer_out=None, peer_row0=0, peer_ld=0, pipeline=0, x_bf16=None, want_out_bf16=False, rows=None, slot=None):
+    assert not peer_out and not want_out_bf16 and rows is None          # (the listed-rows forward needs CUDA index tensors)
     d_in = x_src.size(1)
     K1 = g.R * d_in
     A = alloc_planes(g.n_dst, K1 + d_in, mode, None)
@@ -80,8 +80,8 @@ def layer_fwd(g, x_src, x_root, W2d, root, bias, relu, mode, dropout_p=0.0, drop
 
 
 def layer_bwd(g, gO, relu_mask, mask_scale, planes, W2d, root, d_in, mode, need_x, add_root_term, need_w, need_b,
-              gx_out=None, rows=None, g_ready=None, next_mask=None, slot=None, w_planes=None):
-    assert g_ready is None and next_mask is None
+              gx_out=None, rows=None, g_ready=None, next_mask=None, slot=None, w_planes=None, a_compact=False):
+    assert g_ready is None and next_mask is None and not a_compact
     d_out = gO.size(1)
     K1 = g.R * d_in
     G = alloc_planes(gO.size(0), d_out, mode, None)

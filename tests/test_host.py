@@ -26,7 +26,7 @@ def test_library_exports_every_header_symbol(lib_built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/rgcn_b200.h but not exported"
     assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
-    assert _lib.load().rgcn_abi_version() == _lib.ABI_VERSION == 6
+    assert _lib.load().rgcn_abi_version() == _lib.ABI_VERSION == 7
 
 
 def test_library_argument_errors_without_gpu(lib_built):
