@@ -202,8 +202,10 @@ int rgcn_aggregate_fwd_bf16(const rgcn_csr_t* g, const void* X16, int64_t ldx, i
 
 /* Listed-rows forward walk (the last layer of a link-prediction step is only read at the 2 * batch head / tail rows of its
  * output, src/models/rgcn.py:325-326): position c of rows[0 .. n_list) walks row rows[c] and writes row c of a COMPACT
- * operand [rgcn_rows_compact_size(n_list), >= (R+1) d] (duplicates are computed twice, padding rows are zero).
- * slot (nullable): node -> first list position or m_c (rgcn_rows_list_build); hub chunks of unlisted rows are skipped.
+ * operand [rgcn_rows_compact_size(n_list), >= (R+1) d]; a row listed several times is walked ONCE, into its first position
+ * (slot: node -> first list position or m_c, rgcn_rows_list_build); later duplicates and padding positions are zero rows.
+ * Hub chunks of unlisted rows are skipped.  On graphs of moderate size the walk goes through the rows in the CSR's
+ * degree order and unlisted rows leave at once (long walks start first), otherwise through the list positions.
  * rgcn_rows_list_build: rows [2 n] = heads then tails (out-of-range indices parked on row 0), slot [n_nodes]. */
 int rgcn_rows_list_build(const int64_t* head, const int64_t* tail, int64_t n_pairs, int64_t n_nodes, int64_t* rows,
                          int32_t* slot, rgcn_stream_t stream);
@@ -328,7 +330,8 @@ typedef struct rgcn_layer_fwd_args {
    * src/models/rgcn.py:325-326.  The walk visits those rows only, A_hi / A_lo are COMPACT planes
    * [rgcn_rows_compact_size(n_list), >= (R+1) d_in] in list order (padding rows zero; hand them to rgcn_layer_bwd with
    * a_compact = 1), the transform runs over them and stores row c at out[rows[c], :]; all other rows of `out` are left
-   * untouched.  rows / slot as built by rgcn_rows_list_build (slot may be NULL: every hub chunk is then reduced). */
+   * untouched.  rows / slot as built by rgcn_rows_list_build; a row listed twice is computed once (later duplicate
+   * positions of A are zero rows). */
   const int64_t* rows; int64_t n_list; const int32_t* slot;
 } rgcn_layer_fwd_args;
 
@@ -401,10 +404,12 @@ int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t lda, int32_
 int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const void* w_planes, int32_t K,
                            int64_t n_rows, float* gA, int64_t ldga, int32_t mode, rgcn_stream_t stream);
 /* rgcn_transform_fwd_w over a COMPACT operand [n_rows, K] whose row c belongs to node out_rows[c] (c < n_list; the rows
- * beyond are padding): the epilogue stores row c at out[out_rows[c], :]; only the listed rows of `out` are written. */
+ * beyond are padding): the epilogue stores row c at out[out_rows[c], :]; only the listed rows of `out` are written.
+ * slot (nullable): node -> first list position; a later duplicate position is then not stored. */
 int rgcn_transform_fwd_w_rows(const void* A_hi, const void* A_lo, int64_t lda, int32_t K, const void* w_planes,
                               const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
-                              int32_t mode, const int64_t* out_rows, int64_t n_list, rgcn_stream_t stream);
+                              int32_t mode, const int64_t* out_rows, int64_t n_list, const int32_t* slot,
+                              rgcn_stream_t stream);
 
 int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream);
 int rgcn_layer_bwd(const rgcn_layer_bwd_args* a, rgcn_stream_t stream);

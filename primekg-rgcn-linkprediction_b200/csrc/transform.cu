@@ -155,6 +155,7 @@ struct GemmKParams {
   // scattered output rows (listed-rows forward of the last layer): row c of the product goes to out[out_rows[c]] for
   // c < n_out_rows, the padding rows beyond are dropped (duplicates in the list write identical values)
   const int64_t* out_rows; int64_t n_out_rows;
+  const int32_t* out_slot;                    // nullable: node -> first list position; later duplicates are not stored
 };
 
 enum { EPI_STORE = 0, EPI_RANK = 1, EPI_THR = 2, EPI_TOPK = 3 };
@@ -388,7 +389,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (row < p.M && col_ok) {
             if (p.out_rows) {
               if (row >= p.n_out_rows) continue;
-              row = __ldg(p.out_rows + row);
+              const int64_t pos = row;
+              row = __ldg(p.out_rows + pos);
+              if (p.out_slot && __ldg(p.out_slot + row) != (int32_t)pos) continue;
             }
             float4 v = *reinterpret_cast<const float4*>(patch + rl * 20 + c4);
             if (p.drop_thresh) {
@@ -1047,7 +1050,7 @@ static int transform_fwd_w_impl(const void* A_hi, const void* A_lo, int64_t lda,
                                 const unsigned long long* dropout_counter, int64_t row_offset,
                                 float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
                                 void* out_bf16, int64_t ld_out_bf16, const int64_t* out_rows, int64_t n_out_rows,
-                                rgcn_stream_t stream) {
+                                const int32_t* out_slot, rgcn_stream_t stream) {
   RGCN_CHECK_ARG(!out_rows || (n_out_rows >= 0 && n_out_rows <= n_rows && dropout_p == 0.f && n_peer == 0),
                  "transform_fwd_w: scattered output rows exclude the fused dropout and the peer stores");
   RGCN_CHECK_ARG(n_peer >= 0 && n_peer <= kMaxPeers && (n_peer == 0 || (peer_out_host && peer_ld % 4 == 0 && peer_row0 >= 0)),
@@ -1072,7 +1075,7 @@ static int transform_fwd_w_impl(const void* A_hi, const void* A_lo, int64_t lda,
   p.M = n_rows; p.N = d_out; p.BN = t.BN; p.num_kb = round_up(K, BK) / BK;
   p.bias = bias; p.relu = relu; p.out = out; p.ldo = ldo; p.row_offset = row_offset;
   p.out16 = (__nv_bfloat16*)out_bf16; p.ldo16 = ld_out_bf16;
-  p.out_rows = out_rows; p.n_out_rows = n_out_rows;
+  p.out_rows = out_rows; p.n_out_rows = n_out_rows; p.out_slot = out_slot;
   if (dropout_p > 0.f) {
     const double th = (double)dropout_p * 65536.0 + 0.5;
     p.drop_thresh = th >= 65535.0 ? 65535u : (th < 1.0 ? 1u : (uint32_t)th);
@@ -1095,17 +1098,19 @@ extern "C" int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t 
                                     void* out_bf16, int64_t ld_out_bf16, rgcn_stream_t stream) {
   return transform_fwd_w_impl(A_hi, A_lo, lda, K, w_planes, bias, relu, n_rows, d_out, out, ldo, mode, dropout_p, dropout_seed,
                               dropout_counter, row_offset, peer_out_host, n_peer, peer_row0, peer_ld, out_bf16, ld_out_bf16,
-                              nullptr, 0, stream);
+                              nullptr, 0, nullptr, stream);
 }
 
 // The same product over a COMPACT operand [n_rows, K] whose row c belongs to node out_rows[c] (c < n_list; the rows
 // beyond are padding): the epilogue stores row c at out[out_rows[c], :] — only the listed rows of `out` are written.
+// slot (nullable): node -> first list position; a later duplicate position is not stored (its operand row may be zero).
 extern "C" int rgcn_transform_fwd_w_rows(const void* A_hi, const void* A_lo, int64_t lda, int32_t K, const void* w_planes,
                                          const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
-                                         int32_t mode, const int64_t* out_rows, int64_t n_list, rgcn_stream_t stream) {
+                                         int32_t mode, const int64_t* out_rows, int64_t n_list, const int32_t* slot,
+                                         rgcn_stream_t stream) {
   RGCN_CHECK_ARG(out_rows && n_list >= 0 && n_list <= n_rows, "transform_fwd_w_rows: bad row list");
   return transform_fwd_w_impl(A_hi, A_lo, lda, K, w_planes, bias, relu, n_rows, d_out, out, ldo, mode, 0.f, 0u, nullptr, 0,
-                              nullptr, 0, 0, 0, nullptr, 0, out_rows, n_list, stream);
+                              nullptr, 0, 0, 0, nullptr, 0, out_rows, n_list, slot, stream);
 }
 
 extern "C" int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const void* w_planes,

@@ -547,8 +547,8 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
             raise ValueError("the listed-rows forward needs prepared weights and excludes peers, dropout and the bf16 output copy")
         if rows.dtype != torch.int64 or rows.dim() != 1 or not rows.is_contiguous() or rows.numel() == 0:
             raise ValueError("rows must be a non-empty contiguous int64 list (rows_list_build)")
-        if slot is not None and (slot.dtype != torch.int32 or slot.numel() != g.n_dst or not slot.is_contiguous()):
-            raise ValueError("slot must be a contiguous int32 [n_dst] tensor")
+        if slot is None or slot.dtype != torch.int32 or slot.numel() != g.n_dst or not slot.is_contiguous():
+            raise ValueError("slot must be the contiguous int32 [n_dst] map of rows_list_build")
     n_a = int(lib.rgcn_rows_compact_size(rows.numel())) if listed else g.n_dst
     A = alloc_planes(n_a, K, mode, dev)
     out = torch.empty(g.n_dst, d_out, dtype=torch.float32, device=dev)

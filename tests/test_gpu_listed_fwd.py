@@ -63,13 +63,15 @@ def test_listed_layer_forward_equals_dense_rows(pkg, name, d_in, d_out, n, mode)
         if pl is None:
             assert pd is None
             continue
-        assert torch.equal(pl[:2 * n, :K], pd[rows][:, :K])             # compact planes = the dense planes' listed rows
-        assert not pl[2 * n:, :K].any()                                 # padding rows are zero
+        first = slot[rows].to(torch.int64) == torch.arange(2 * n, device=DEV)    # a row lives at its FIRST position
+        assert torch.equal(pl[:2 * n, :K][first], pd[rows][:, :K][first])        # compact planes = the dense planes' rows
+        assert not pl[:2 * n, :K][~first].any()                                   # later duplicates are zero rows
+        assert not pl[2 * n:, :K].any()                                           # and so is the padding
     assert torch.equal(out_l[rows], out_d[rows])                        # same bits at every listed row
 
 
-def test_listed_forward_without_slot_and_without_hubs(pkg):
-    """slot = None reduces every hub chunk; a list that avoids the hub rows skips them all — same listed rows either way."""
+def test_listed_forward_without_hubs(pkg):
+    """A list that avoids the hub rows skips every hub chunk; the slot map is mandatory."""
     from primekg_rgcn_linkprediction_b200 import ops
     ei, et, N, R, x, W, root, bias, gen = _layer_inputs("primekg_100k", 64, 64)
     g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
@@ -80,8 +82,9 @@ def test_listed_forward_without_slot_and_without_hubs(pkg):
     rows, slot = ops.rows_list_build(head, tail, N)
     out_d, _, _ = ops.layer_fwd(g, x, x, W, root, bias, False, "fp32")
     out_a, _, _ = ops.layer_fwd(g, x, x, W, root, bias, False, "fp32", rows=rows, slot=slot)
-    out_b, _, _ = ops.layer_fwd(g, x, x, W, root, bias, False, "fp32", rows=rows, slot=None)
-    assert torch.equal(out_a[rows], out_d[rows]) and torch.equal(out_b[rows], out_d[rows])
+    assert torch.equal(out_a[rows], out_d[rows])
+    with pytest.raises(ValueError):
+        ops.layer_fwd(g, x, x, W, root, bias, False, "fp32", rows=rows, slot=None)
 
 
 def test_rows_list_build_parks_bad_indices(pkg):
