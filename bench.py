@@ -513,8 +513,11 @@ def partitioned_record(rank, world, dev, steps=5, warmup=2):
     rec["local_edges_rank0"] = local_edges
     dims = [d_e] + [d_h] * L
     # forward: every rank receives the other ranks' rows of each layer's input and of the output; backward: the transpose
-    fwd_in = (world - 1) * plan.max_n * 4 * sum(dims)
-    rec["exchange_bytes_per_gpu_per_step"] = {"forward_received": fwd_in, "backward_pulled": (world - 1) * plan.max_n * 4 * sum(dims),
+    # (peer-memory form: of the OUTPUT only the 2 * batch rows some decoder reads travel, and of the last layer's gradient
+    # only those rows are pulled; the NCCL form exchanges full matrices)
+    fwd_in = (world - 1) * plan.max_n * 4 * sum(dims[:-1]) + (world - 1) * 2 * B * 4 * dims[-1]
+    rec["exchange_bytes_per_gpu_per_step"] = {"forward_received": fwd_in, "backward_pulled": fwd_in,
+                                              "nccl_form_each_direction": (world - 1) * plan.max_n * 4 * sum(dims),
                                               "weight_grad_allreduce": 4 * sum((R + 1) * dims[i] * dims[i + 1] + dims[i + 1] for i in range(L))}
     for exchange in ("fused", "nccl"):
         try:
@@ -526,13 +529,17 @@ def partitioned_record(rank, world, dev, steps=5, warmup=2):
                 rec["value"] = edges / (ms * 1e-3)
                 rec["unit"] = UNIT
                 rec["exchange"] = "our kernels over peer-mapped memory (all-gather = the transform's epilogue stores, " \
-                                  "reduce-scatter = rank-ordered pull fused with mask + operand conversion)"
+                                  "reduce-scatter = rank-ordered pull fused with mask + operand conversion); the last " \
+                                  "layer runs on the rows the decoders read only (listed-rows forward + row-sparse backward)"
             del model, step
             torch.cuda.empty_cache()
         except Exception as ex:  # pragma: no cover
             rec[exchange + "_error"] = repr(ex)[:300]
     if "ms_per_step" in rec and "nccl_exchange_ms_per_step" in rec:
         rec["fused_vs_nccl_speedup"] = rec["nccl_exchange_ms_per_step"] / rec["ms_per_step"]
+        rec["nccl_form_note"] = ("dist.py: NCCL all-gather / reduce-scatter of full matrices, last layer over all rows "
+                                 "forward (row-sparse backward as well): the ratio covers the exchange form AND the "
+                                 "listed-rows last layer of the peer-memory path")
     rec["max_mem_GB"] = torch.cuda.max_memory_allocated() / 1e9
     rec["ceiling_survey_8d_edges_per_s"] = 2.4e9 * world
     return rec

@@ -325,7 +325,7 @@ typedef struct rgcn_layer_fwd_args {
    * the walk gathers IT (half the bytes of the dominant kernel; sums stay fp32);  out_bf16 = where to leave the bf16 copy
    * of this layer's output for the next layer (d_out % 4 == 0). */
   const void* x_bf16; int64_t ld_x_bf16; void* out_bf16; int64_t ld_out_bf16;
-  /* Listed-rows form (rows != NULL; needs w_planes, no peers, no dropout): only rows[0 .. n_list) of the layer's output
+  /* Listed-rows form (rows != NULL; needs w_planes, no dropout; peers receive the listed rows only): only rows[0 .. n_list) of the layer's output
    * are wanted — the 2 * batch (head, tail) rows the link-prediction decoder reads from the LAST layer,
    * src/models/rgcn.py:325-326.  The walk visits those rows only, A_hi / A_lo are COMPACT planes
    * [rgcn_rows_compact_size(n_list), >= (R+1) d_in] in list order (padding rows zero; hand them to rgcn_layer_bwd with
@@ -405,10 +405,12 @@ int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int3
                            int64_t n_rows, float* gA, int64_t ldga, int32_t mode, rgcn_stream_t stream);
 /* rgcn_transform_fwd_w over a COMPACT operand [n_rows, K] whose row c belongs to node out_rows[c] (c < n_list; the rows
  * beyond are padding): the epilogue stores row c at out[out_rows[c], :]; only the listed rows of `out` are written.
- * slot (nullable): node -> first list position; a later duplicate position is then not stored. */
+ * slot (nullable): node -> first list position; a later duplicate position is then not stored.  peer_out_host (n_peer
+ * > 0): the listed rows are also stored at rows peer_row0 + out_rows[c] of the peers' buffers. */
 int rgcn_transform_fwd_w_rows(const void* A_hi, const void* A_lo, int64_t lda, int32_t K, const void* w_planes,
                               const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
                               int32_t mode, const int64_t* out_rows, int64_t n_list, const int32_t* slot,
+                              float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
                               rgcn_stream_t stream);
 
 int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream);

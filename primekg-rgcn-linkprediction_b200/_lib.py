@@ -91,7 +91,7 @@ PROTOTYPES = {
     "rgcn_rows_list_build": (C.c_int, [p, p, i64, i64, p, p, p]),
     "rgcn_aggregate_fwd_list": (C.c_int, [PCSR, p, i64, i32, p, p, i64, i32, p, i64, p, i64, p, p, sz, p]),
     "rgcn_aggregate_fwd_bf16_list": (C.c_int, [PCSR, p, i64, i32, p, i64, p, i64, p, i64, p, p, sz, p]),
-    "rgcn_transform_fwd_w_rows": (C.c_int, [p, p, i64, i32, p, p, i32, i64, i32, p, i64, i32, p, i64, p, p]),
+    "rgcn_transform_fwd_w_rows": (C.c_int, [p, p, i64, i32, p, p, i32, i64, i32, p, i64, i32, p, i64, p, p, i32, i64, i64, p]),
     "rgcn_transform_dgrad_w": (C.c_int, [p, p, i64, i32, p, i32, i64, p, i64, i32, p]),
     "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
     "rgcn_rows_compact_size": (i64, [i64]),

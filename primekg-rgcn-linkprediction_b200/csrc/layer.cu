@@ -157,8 +157,7 @@ extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream
     // listed-rows form: only the rows the caller will read (the 2 * batch head / tail rows of a link-prediction step,
     // src/models/rgcn.py:325-326) are walked and transformed; A comes back COMPACT [m_c, K] in list order, which is the
     // operand layout the row-sparse backward wants (rgcn_layer_bwd, a_compact)
-    RGCN_CHECK_ARG(a->n_list > 0 && a->slot && a->n_peer == 0 && a->dropout_p == 0.f,
-                   "layer_fwd: the listed-rows form needs the slot map and excludes peers and dropout");
+    RGCN_CHECK_ARG(a->n_list > 0 && a->slot && a->dropout_p == 0.f, "layer_fwd: the listed-rows form needs the slot map and excludes dropout");
     const int64_t m_c = rgcn_rows_compact_size(a->n_list);
     const bool g16l = a->mode == 1 && a->x_bf16 && a->d_in % 8 == 0 && a->lda % 8 == 0 && a->x_src == a->x_root;
     if (g16l)
@@ -169,7 +168,8 @@ extern "C" int rgcn_layer_fwd(const rgcn_layer_fwd_args* a, rgcn_stream_t stream
                                    a->rows, a->n_list, a->slot, a->agg_workspace, a->agg_workspace_bytes, stream);
     if (rc) return rc;
     return rgcn_transform_fwd_w_rows(a->A_hi, A_lo, a->lda, K, a->w_planes, a->bias, a->relu, m_c, a->d_out, a->out, a->ldo,
-                                     a->mode, a->rows, a->n_list, a->slot, stream);
+                                     a->mode, a->rows, a->n_list, a->slot, a->peer_out_host, a->n_peer, a->peer_row0, a->peer_ld,
+                                     stream);
   }
   if (fused_layer_fwd_eligible(a)) {
     // hub chunks first (their partials are what the fused kernel's row walk adds for the long segments)

@@ -1051,8 +1051,8 @@ static int transform_fwd_w_impl(const void* A_hi, const void* A_lo, int64_t lda,
                                 float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
                                 void* out_bf16, int64_t ld_out_bf16, const int64_t* out_rows, int64_t n_out_rows,
                                 const int32_t* out_slot, rgcn_stream_t stream) {
-  RGCN_CHECK_ARG(!out_rows || (n_out_rows >= 0 && n_out_rows <= n_rows && dropout_p == 0.f && n_peer == 0),
-                 "transform_fwd_w: scattered output rows exclude the fused dropout and the peer stores");
+  RGCN_CHECK_ARG(!out_rows || (n_out_rows >= 0 && n_out_rows <= n_rows && dropout_p == 0.f),
+                 "transform_fwd_w: scattered output rows exclude the fused dropout");
   RGCN_CHECK_ARG(n_peer >= 0 && n_peer <= kMaxPeers && (n_peer == 0 || (peer_out_host && peer_ld % 4 == 0 && peer_row0 >= 0)),
                  "transform_fwd_w: bad peer outputs (at most %d, ld %% 4 == 0)", kMaxPeers);
   RGCN_CHECK_ARG(!out_bf16 || (((uintptr_t)out_bf16 & 7) == 0 && ld_out_bf16 % 4 == 0), "transform_fwd_w: bf16 output misaligned");
@@ -1104,13 +1104,16 @@ extern "C" int rgcn_transform_fwd_w(const void* A_hi, const void* A_lo, int64_t 
 // The same product over a COMPACT operand [n_rows, K] whose row c belongs to node out_rows[c] (c < n_list; the rows
 // beyond are padding): the epilogue stores row c at out[out_rows[c], :] — only the listed rows of `out` are written.
 // slot (nullable): node -> first list position; a later duplicate position is not stored (its operand row may be zero).
+// peer_out_host (n_peer > 0): the listed rows also go to rows peer_row0 + out_rows[c] of the peers' buffers (the
+// partitioned path's all-gather of the rows the decoders read).
 extern "C" int rgcn_transform_fwd_w_rows(const void* A_hi, const void* A_lo, int64_t lda, int32_t K, const void* w_planes,
                                          const float* bias, int32_t relu, int64_t n_rows, int32_t d_out, float* out, int64_t ldo,
                                          int32_t mode, const int64_t* out_rows, int64_t n_list, const int32_t* slot,
+                                         float* const* peer_out_host, int32_t n_peer, int64_t peer_row0, int64_t peer_ld,
                                          rgcn_stream_t stream) {
   RGCN_CHECK_ARG(out_rows && n_list >= 0 && n_list <= n_rows, "transform_fwd_w_rows: bad row list");
   return transform_fwd_w_impl(A_hi, A_lo, lda, K, w_planes, bias, relu, n_rows, d_out, out, ldo, mode, 0.f, 0u, nullptr, 0,
-                              nullptr, 0, 0, 0, nullptr, 0, out_rows, n_list, slot, stream);
+                              peer_out_host, n_peer, peer_row0, peer_ld, nullptr, 0, out_rows, n_list, slot, stream);
 }
 
 extern "C" int rgcn_transform_dgrad_w(const void* G_hi, const void* G_lo, int64_t ldg, int32_t d_out, const void* w_planes,

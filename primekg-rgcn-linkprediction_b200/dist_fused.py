@@ -45,6 +45,11 @@ def sparse_last_layer() -> bool:
     return os.environ.get("PRIMEKG_RGCN_SPARSE_BWD", "1") != "0"
 
 
+def listed_last_layer() -> bool:
+    """Listed-rows forward of the last layer (``PRIMEKG_RGCN_SPARSE_FWD=0`` or ``PRIMEKG_RGCN_SPARSE_BWD=0``: all rows)."""
+    return sparse_last_layer() and os.environ.get("PRIMEKG_RGCN_SPARSE_FWD", "1") != "0" and ops.prepared_weights()
+
+
 class _Exchange:
     """The two peer buffers (features forward, partial gradients backward), each cut into two halves."""
 
@@ -83,7 +88,9 @@ class _FusedEncoderFn(torch.autograd.Function):
     (this rank's copy; rows in padded id order).  Its gradient is the full-length PARTIAL gradient of this rank."""
 
     @staticmethod
-    def forward(ctx, ex: _Exchange, graph, mode: str, drops, x0, *params):
+    def forward(ctx, ex: _Exchange, graph, mode: str, drops, read_ids, x0, *params):
+        """``read_ids`` (int64 padded global ids, even length, or None): the rows THIS rank's decoder will read; with it
+        the last layer computes — and sends to every rank — only the rows some rank reads."""
         L = len(params) // 3
         n, row0 = ex.max_n, ex.row0
         x0 = x0.contiguous()
@@ -96,6 +103,21 @@ class _FusedEncoderFn(torch.autograd.Function):
         ex.x.barrier()
         ops.p2p_push_rows(x0, ex.x_ptrs(0), row0, x0.size(1))
         ex.x.barrier()
+        listed = None
+        if read_ids is not None and read_ids.numel() > 0 and read_ids.numel() % 2 == 0 and \
+                ex.world * read_ids.numel() <= rowsparse.MAX_FRACTION * n:
+            # every rank's list (a few kilobytes; plumbing): a rank computes the rows of ITS shard that anybody reads;
+            # the others are parked on local row 0 as invalid entries (never walked, never stored)
+            mine = read_ids.to(torch.int64).contiguous()
+            all_ids = torch.empty(ex.world * mine.numel(), dtype=torch.int64, device=mine.device)
+            if ex.world > 1:
+                dist.all_gather_into_tensor(all_ids, mine)
+            else:
+                all_ids = mine
+            inside = (all_ids >= row0) & (all_ids < row0 + n)
+            local = torch.where(inside, all_ids - row0, torch.full_like(all_ids, -1))
+            half = local.numel() // 2
+            listed = ops.rows_list_build(local[:half], local[half:], n)
         saved, outs, wps = [], [], []
         for l in range(L):
             W, root, bias = params[3 * l: 3 * l + 3]
@@ -105,13 +127,16 @@ class _FusedEncoderFn(torch.autograd.Function):
             p_drop, seed, ctr = drops[l] if drops[l] is not None else (0.0, 0, None)
             last = l == L - 1
             # aggregate -> planes -> transform whose epilogue also stores every tile into all ranks' next buffer
+            rows_l, slot_l = listed if (last and listed is not None) else (None, None)
             out, A, wp = ops.layer_fwd(graph, x_full, x_full[row0:row0 + n], W.reshape(K1, d_out), root, bias, not last, mode,
-                                       p_drop, seed, ctr, peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out)
+                                       p_drop, seed, ctr, peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out,
+                                       rows=rows_l, slot=slot_l)
             ex.x.barrier()
             saved += [A[0], A[1], W, root]
             wps.append(wp)
             outs.append(None if last else out)          # post-ReLU/dropout output = the backward mask
         ctx.ex, ctx.graph, ctx.mode, ctx.L = ex, graph, mode, L
+        ctx.listed = listed
         ctx.generation = ex.generation
         ctx.w_planes = wps
         ctx.p_drops = [d[0] if d is not None else 0.0 for d in drops]
@@ -138,9 +163,13 @@ class _FusedEncoderFn(torch.autograd.Function):
         # rows ITS slice of the batch names (the decoder's backward announces them, rowsparse.py).  With all ranks' lists
         # the LAST layer's backward runs row-sparse, like the one-GPU model: a pull of the listed rows only (kilobytes
         # instead of this rank's shard of every rank's buffer) and dgrad / walk / wgrad over <= 2 * batch compact rows.
-        sparse_rows = None
+        sparse_rows = slot_fwd = None
         claimed = rowsparse.claim(g_full) if sparse_last_layer() else None
-        if claimed is not None:
+        if ctx.listed is not None:
+            # the forward computed the listed rows only (the same all-ranks list, already local): its compact planes are
+            # the weight gradient's operand, its slot map serves the compaction
+            sparse_rows, slot_fwd = ctx.listed
+        elif claimed is not None:
             mine_rows = claimed[0]                                          # padded global ids, 2 * local batch entries
             all_rows = torch.empty(ex.world * mine_rows.numel(), dtype=torch.int64, device=dev)
             if ex.world > 1:
@@ -166,7 +195,7 @@ class _FusedEncoderFn(torch.autograd.Function):
                 _, gA_c, gWf, groot, gb, slot = ops.layer_bwd(
                     graph, g_local, None, 1.0, (A_hi, A_lo), Wf, root, d_in, mode, need_x=True, add_root_term=False,
                     need_w=True, need_b=True, gx_out=ex.g_view(l, d_in), rows=sparse_rows, w_planes=ctx.w_planes[l],
-                    return_compact=True)
+                    return_compact=True, slot=slot_fwd, a_compact=slot_fwd is not None)
                 # root-term gradient of this rank's rows: the compact rows scattered back (unlisted rows read the zero row)
                 extra = gA_c[:, K1:].index_select(0, slot.long())
                 grads[3 * l: 3 * l + 3] = [gWf.view(R, d_in, d_out), groot, gb]
@@ -190,7 +219,7 @@ class _FusedEncoderFn(torch.autograd.Function):
         for i, g in enumerate(grads):
             grads[i] = flat[off: off + g.numel()].view_as(g)
             off += g.numel()
-        return (None, None, None, None, gx0, *grads)
+        return (None, None, None, None, None, gx0, *grads)
 
 
 class FusedPartitionedRGCN(PartitionedRGCN):
@@ -208,7 +237,10 @@ class FusedPartitionedRGCN(PartitionedRGCN):
             self._ex = _Exchange(self.plan, self.rank, dims, self.node_embeddings.device)
         return self._ex
 
-    def forward(self) -> torch.Tensor:
+    def forward(self, read_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``read_ids`` (padded global ids, e.g. ``cat(heads, tails)`` of this rank's batch): the caller reads ONLY these
+        rows of the result; with autograd on the last layer then computes and exchanges just the rows some rank reads
+        (every other row of the returned matrix is undefined)."""
         if not self.node_embeddings.is_cuda:
             raise RuntimeError("FusedPartitionedRGCN needs CUDA devices with peer access; dist.PartitionedRGCN is the "
                                "collective-library form")
@@ -221,7 +253,9 @@ class FusedPartitionedRGCN(PartitionedRGCN):
                 raise ValueError("fused dropout needs p < 1")
             drops.append(conv.dropout_state(p, self.node_embeddings.device) if p > 0.0 else None)
         mode = self.convs[0].mode or default_mode()
-        return _FusedEncoderFn.apply(self._exchange(), self.graph, mode, drops, self.node_embeddings, *params)
+        if read_ids is not None and not (torch.is_grad_enabled() and listed_last_layer()):
+            read_ids = None
+        return _FusedEncoderFn.apply(self._exchange(), self.graph, mode, drops, read_ids, self.node_embeddings, *params)
 
 
 class FusedPartitionedModel(nn.Module):
@@ -241,8 +275,9 @@ class FusedPartitionedModel(nn.Module):
         torch.random.set_rng_state(state)
 
     def forward(self, heads: torch.Tensor, tails: torch.Tensor, rels: torch.Tensor) -> torch.Tensor:
-        emb = self.encoder()                                  # [P * max_n, hidden], padded id order
-        return self.decoder.score_pairs(emb, self.plan.to_padded(heads), self.plan.to_padded(tails), rels)
+        h, t = self.plan.to_padded(heads), self.plan.to_padded(tails)
+        emb = self.encoder(torch.cat([h.reshape(-1), t.reshape(-1)]))       # [P * max_n, hidden], padded id order
+        return self.decoder.score_pairs(emb, h, t, rels)
 
     def allreduce_decoder_grads(self) -> None:
         for p in self.decoder.parameters():

@@ -543,8 +543,8 @@ def layer_fwd(g: RelGraph, x_src: torch.Tensor, x_root: torch.Tensor, W2d: torch
     dev = x_src.device
     listed = rows is not None
     if listed:
-        if not prepared_weights() or peer_out or dropout_p > 0 or want_out_bf16:
-            raise ValueError("the listed-rows forward needs prepared weights and excludes peers, dropout and the bf16 output copy")
+        if not prepared_weights() or dropout_p > 0 or want_out_bf16:
+            raise ValueError("the listed-rows forward needs prepared weights and excludes dropout and the bf16 output copy")
         if rows.dtype != torch.int64 or rows.dim() != 1 or not rows.is_contiguous() or rows.numel() == 0:
             raise ValueError("rows must be a non-empty contiguous int64 list (rows_list_build)")
         if slot is None or slot.dtype != torch.int32 or slot.numel() != g.n_dst or not slot.is_contiguous():
