@@ -557,7 +557,10 @@ int rgcn_bce_logits_bwd(const float* logits, const float* labels, int64_t n, con
  *                        out: the heads then the tails) or rgcn_rows_compact_size(2 n_pairs) when nobody lists it; every
  *                        position's contribution is computed in parallel, then the owner position's warp adds the
  *                        contributions to its node in ascending position order and every row of g_emb [n_nodes, d] is
- *                        written exactly once (no pre-zeroing).  g_rel_table = fixed-order sum of per-32-pair partials.
+ *                        written exactly once (no pre-zeroing); listed_only != 0: only the LISTED rows are written —
+ *                        for a consumer that reads nothing else, the listed-rows form of the last encoder layer
+ *                        (rgcn_layer_fwd with rows) — and the rest of g_emb stays undefined.
+ *                        g_rel_table = fixed-order sum of per-32-pair partials.
  *                        workspace (always needed, 16-byte aligned): rgcn_link_bwd_rows_workspace_bytes.
  *                        slot / rows are exactly what rgcn_layer_bwd's row-sparse form wants (slot_ready = 1).
  *   Index range: with n_nodes > 0 a pair whose head / tail is outside [0, n_nodes) or whose relation is outside
@@ -584,8 +587,8 @@ int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64_t* head, c
                             const float* rel_table, const float* labels, const float* score, const float* g_loss,
                             const float* g_score, int64_t n_pairs, int32_t d, float dropout_p, uint32_t seed,
                             const unsigned long long* state, int64_t n_nodes, int32_t n_rel, float* g_emb, int64_t ld_g,
-                            float* g_rel_table, int32_t* slot, int64_t* rows, int32_t* status, void* workspace,
-                            size_t workspace_bytes, rgcn_stream_t stream);
+                            float* g_rel_table, int32_t* slot, int64_t* rows, int32_t* status, int32_t listed_only,
+                            void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
 /* flag[0] = 1 when any head/tail is outside [0, n_nodes) or any rel outside [0, n_rel). */
 int rgcn_check_pairs(const int64_t* head, const int64_t* tail, const int64_t* rel, int64_t n_pairs,

@@ -131,7 +131,7 @@ PROTOTYPES = {
     "rgcn_link_loss_bwd": (C.c_int, [p, i64, p, p, p, p, p, p, p, p, i64, i32, C.c_float, u32, p, p, i64, p, i32, i64, p]),
     "rgcn_link_bwd_rows_workspace_bytes": (sz, [i64, i32, i32]),
     "rgcn_link_loss_bwd_rows": (C.c_int, [p, i64, p, p, p, p, p, p, p, p, i64, i32, C.c_float, u32, p, i64, i32, p, i64, p,
-                                          p, p, p, p, sz, p]),
+                                          p, p, p, i32, p, sz, p]),
     "rgcn_check_pairs": (C.c_int, [p, p, p, i64, i64, i32, p, p]),
 }
 

@@ -72,6 +72,10 @@ class _RGCNLayerFn(torch.autograd.Function):
         res = ops.layer_fwd(graph, x_src, x_root, W.reshape(R * d_in, d_out), root, bias, relu, mode, p_drop, seed, ctr,
                             x_bf16=x16, want_out_bf16=want16, rows=rows_l, slot=slot_l)
         out, A, wp = res[:3]
+        if ctx.listed is not None:
+            rowsparse.mark_listed_output(out)
+        else:
+            rowsparse.unmark_listed_output()
         if want16 and res[3] is not None:
             rowsparse.announce_bf16(out, res[3])
         ctx.graph, ctx.relu, ctx.mode, ctx.shared, ctx.p_drop = graph, relu, mode, shared, p_drop

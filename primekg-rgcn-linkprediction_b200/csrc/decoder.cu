@@ -741,8 +741,8 @@ extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64
                                        const float* g_loss, const float* g_score, int64_t n_pairs, int32_t d,
                                        float dropout_p, uint32_t seed, const unsigned long long* state, int64_t n_nodes,
                                        int32_t n_rel, float* g_emb, int64_t ld_g, float* g_rel_table, int32_t* slot,
-                                       int64_t* rows, int32_t* status, void* workspace, size_t workspace_bytes,
-                                       rgcn_stream_t stream) {
+                                       int64_t* rows, int32_t* status, int32_t listed_only, void* workspace,
+                                       size_t workspace_bytes, rgcn_stream_t stream) {
   LinkLossParams q{};
   int rc = fill_link_params(q, emb, ld, head, tail, rel, rel_table, labels, n_pairs, d, dropout_p, seed, n_nodes, n_rel, status);
   if (rc) return rc;
@@ -766,7 +766,9 @@ extern "C" int rgcn_link_loss_bwd_rows(const float* emb, int64_t ld, const int64
   b.T = g_rel_table ? (float*)((char*)workspace + link_ws_C(n_pairs, d)) : nullptr;
   b.tab_partial = g_rel_table ? (float*)((char*)workspace + link_ws_C(n_pairs, d) + link_ws_T(n_pairs, d)) : nullptr;
   b.n_owner_blocks = (int32_t)((2 * n_pairs + 7) / 8);
-  b.n_zero_blocks = (int32_t)((n_nodes + kLinkZeroRows - 1) / kLinkZeroRows);
+  // listed_only: the consumer reads the listed rows of g_emb alone (the listed-rows form of the last encoder layer), so
+  // the other rows stay as they are instead of being zero-filled (N x d floats less to write)
+  b.n_zero_blocks = listed_only ? 0 : (int32_t)((n_nodes + kLinkZeroRows - 1) / kLinkZeroRows);
   b.n_tab_blocks = g_rel_table ? (int32_t)((n_pairs + kLinkTabPairs - 1) / kLinkTabPairs) : 0;
   RGCN_CUDA(launch_pdl(link_contrib_kernel, dim3((unsigned)b.n_owner_blocks), dim3(256), 0, st, q, b));
   RGCN_LAUNCH_CHECK();

@@ -845,6 +845,8 @@ def _link_bwd(ctx_p_drop, ctx_seed, emb, rel_table, head, tail, rel, labels, sco
     dev = emb.device
     n, d, n_nodes, n_rel = head.numel(), emb.size(1), emb.size(0), rel_table.size(0)
     g_emb = torch.empty(n_nodes, d, dtype=torch.float32, device=dev)        # every row written exactly once by the kernel
+    # ... unless emb is the output of a listed-rows last layer, whose backward reads the listed rows of g_emb alone
+    listed_only = need_emb and rowsparse.is_listed_output(emb)
     g_tab = param_grad(*rel_table.shape, device=dev) if need_tab else None
     slot = torch.empty(n_nodes, dtype=torch.int32, device=dev)
     rows = torch.empty(2 * n, dtype=torch.int64, device=dev)
@@ -852,7 +854,7 @@ def _link_bwd(ctx_p_drop, ctx_seed, emb, rel_table, head, tail, rel, labels, sco
     _lib.check(lib.rgcn_link_loss_bwd_rows(_ptr(emb), emb.stride(0), _ptr(head), _ptr(tail), _ptr(rel), _ptr(rel_table),
                                            _ptr(labels), _ptr(score), _ptr(g_loss), _ptr(g_score), n, d, ctx_p_drop,
                                            ctx_seed & 0xFFFFFFFF, _ptr(state), n_nodes, n_rel, _ptr(g_emb), g_emb.stride(0),
-                                           _ptr(g_tab), _ptr(slot), _ptr(rows), _ptr(pair_status(dev)), _ptr(ws),
+                                           _ptr(g_tab), _ptr(slot), _ptr(rows), _ptr(pair_status(dev)), int(listed_only), _ptr(ws),
                                            0 if ws is None else ws.numel(), _stream(dev)), "rgcn_link_loss_bwd_rows")
     if not need_emb:
         return None, g_tab

@@ -106,8 +106,32 @@ def claim_bf16(x: torch.Tensor) -> Optional[torch.Tensor]:
     return out16 if ok else None
 
 
+# ---- fourth hand-over (forward -> decoder backward): the encoder output was computed at a row list only (listed-rows
+#      last layer); its consumer's backward then need not define the gradient outside those rows ----
+_listed_out = None      # (data_ptr, shape, version)
+
+
+def mark_listed_output(out: torch.Tensor) -> None:
+    global _listed_out
+    _listed_out = (out.data_ptr(), tuple(out.shape), out._version)
+
+
+def unmark_listed_output() -> None:
+    """Called by every layer forward that computes ALL rows: a stale mark must never match a recycled allocation."""
+    global _listed_out
+    _listed_out = None
+
+
+def is_listed_output(emb: torch.Tensor) -> bool:
+    """True if ``emb`` is the marked tensor, untouched; the mark is consumed by the first attempt."""
+    global _listed_out
+    a, _listed_out = _listed_out, None
+    return a is not None and emb.data_ptr() == a[0] and tuple(emb.shape) == a[1] and emb._version == a[2]
+
+
 def clear() -> None:
-    global _announced, _planes, _bf16
+    global _announced, _planes, _bf16, _listed_out
     _announced = None
     _planes = None
     _bf16 = None
+    _listed_out = None
