@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(256) link_contrib_kernel(const LinkLossParams 
   }
 }
 
-__global__ void __launch_bounds__(256, 4) link_gather_kernel(const LinkLossParams q, const LinkBwdRows b) {
+constexpr int kLinkInFlight = 12;
+__global__ void __launch_bounds__(256, 2) link_gather_kernel(const LinkLossParams q, const LinkBwdRows b) {
   pdl_enter();
   extern __shared__ int s_rows[];                    // [2 n rounded up to 128] node of every position (owner blocks)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -446,17 +447,19 @@ __global__ void __launch_bounds__(256, 4) link_gather_kernel(const LinkLossParam
       float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
       auto flush = [&](int count) {
         __syncwarp();
-        for (int j = 0; j < count; j += 4) {         // four rows in flight, added strictly in list (= position) order
-          float4 x0[4], x1[4];
+        // kLinkInFlight rows in flight, added strictly in list (= position) order: a hub gene heads or tails dozens of
+        // pairs of one batch, and its owner's chain of dependent load rounds is what the kernel's duration is
+        for (int j = 0; j < count; j += kLinkInFlight) {
+          float4 x0[kLinkInFlight], x1[kLinkInFlight];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < kLinkInFlight; ++u) {
             const int e = min(j + u, count - 1);
             const float* __restrict__ row = b.C + (int64_t)list[e] * q.d;
             x0[u] = *reinterpret_cast<const float4*>(row + c0);
             x1[u] = *reinterpret_cast<const float4*>(row + c1);
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < kLinkInFlight; ++u) {
             if (j + u < count) { add4(acc0, x0[u]); add4(acc1, x1[u]); }
           }
         }

@@ -1068,7 +1068,10 @@ static int transform_fwd_w_impl(const void* A_hi, const void* A_lo, int64_t lda,
   if (n_rows == 0) return RGCN_OK;
   // measured (scripts/ab_gemm.py, 30,926 x 1,024 x 256): 256-wide tiles win with one product per k-step (4-stage ring:
   // 34.3 against 36.9 us) and lose with three (2-stage ring: 63.5 against 57.4 us)
-  const Tiling t = tile_n(d_out, 32, (d_out > KBN && mode == 1) ? wide_bn() : KBN);
+  static int wide_fp32 = -1;                       // A/B switch: 256-wide tiles in the three-product mode too
+  if (wide_fp32 < 0) { const char* e = getenv("RGCN_WIDE_FP32"); wide_fp32 = e ? atoi(e) : 0; }
+  const bool wide = d_out > KBN && (mode == 1 || (wide_fp32 == 1) || (wide_fp32 == 2 && K <= 256));
+  const Tiling t = tile_n(d_out, 32, wide ? wide_bn() : KBN);
   const __nv_bfloat16* bhi = (const __nv_bfloat16*)w_planes;
   const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)w_planes + wplane_bytes(K, d_out));
   GemmKParams p{};

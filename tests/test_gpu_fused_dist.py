@@ -51,9 +51,12 @@ def test_peer_kernels(pg):
     torch.testing.assert_close(part.sum(0), want.sum(0), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("listed", [True, False])
 @pytest.mark.parametrize("layers,dropout", [(2, 0.0), (3, 0.0), (2, 0.5)])
-def test_fused_partition_matches_single_gpu(pg, layers, dropout):
+def test_fused_partition_matches_single_gpu(pg, monkeypatch, layers, dropout, listed):
+    """``listed``: the last layer computes and exchanges only the rows the decoder reads (the default) / all rows."""
     import primekg_rgcn_linkprediction_b200 as pkg
+    monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_FWD", "1" if listed else "0")
     from primekg_rgcn_linkprediction_b200 import dist as D
     from primekg_rgcn_linkprediction_b200 import dist_fused as DF
     from primekg_rgcn_linkprediction_b200 import synth
