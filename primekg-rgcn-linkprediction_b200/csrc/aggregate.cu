@@ -96,6 +96,7 @@ struct AggParams {
   // Either way a row that the list names several times is walked once.
   int64_t list_walkers;
   int32_t list_by_rows;
+  int32_t stream_rel;        // backward walk: stream a row's edges across relation boundaries (short segments, many relations)
   // hub pass filter (nullable): node -> first list position map; chunks of rows with hub_filter[row] == hub_unlisted are skipped
   const int32_t* hub_filter;
   int32_t hub_unlisted;
@@ -246,6 +247,7 @@ aggregate_rows_kernel(const AggParams p) {
   constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
   constexpr int U = U0 < G ? U0 : G;             // a batch never exceeds the index window
   constexpr bool TAILPRED = MIX != MIX_BASIS && VPL <= RGCN_TAILPRED_MAX_VPL;
+  constexpr bool CHAIN = MIX == MIX_SUM && W;    // backward walk: weighted sums, all relations into one accumulator
   extern __shared__ float s_comp[];   // [R * B] for MIX_BASIS, then [GROUPS][R * B] coefficient-gradient sums
   const bool with_gc = MIX == MIX_BASIS && p.dotP != nullptr;
   const bool with_cs = MP && MIX == MIX_SUM && p.mp_colsum != nullptr;       // s_comp then holds [GROUPS][d] column-sum rows
@@ -364,6 +366,52 @@ aggregate_rows_kernel(const AggParams p) {
     const int my_beg = (rl < r_hi) ? __ldg(rowptr + rl) : 0;
     const int my_end = (rl < r_hi) ? __ldg(rowptr + rl + 1) : 0;
     const int rcount = min(G, r_hi - rbase);
+    if (CHAIN && !SLOT && p.stream_rel) {
+      // Backward (summed relations, weighted edges): the row's sum does not care where one relation ends and the next
+      // begins, only the column block of the gathered slice does.  So the edges of the G relations this pass covers are
+      // streamed as ONE list, U loads in flight across segment boundaries — a graph with 30 relations has mostly one- and
+      // two-edge segments, and a batch per segment leaves the memory system idle.  The relation of an edge is the number
+      // of segments that end at or before it (one ballot over the lanes' segment ends).  Same additions in the same
+      // (edge) order as the per-relation loop below, which serves the passes that contain a hub segment.
+      const bool lane_hub = rl < r_hi && my_end - my_beg > p.hub_threshold;
+      if ((__ballot_sync(gmask, lane_hub) & gmask) == 0u) {
+        const int cbeg = __shfl_sync(gmask, my_beg, 0, G);
+        const int cend = __shfl_sync(gmask, my_end, rcount - 1, G);
+        const int endk = rl < r_hi ? my_end : 0x7fffffff;          // lanes beyond the pass never count
+        const float* __restrict__ Fb = F + (size_t)rbase * rel_stride;
+        int e = cbeg;
+        auto fbatch = [&](auto ub, const bool pred) {
+          constexpr int UB = decltype(ub)::value;
+          if (e + UB > wbase + 2 * G) refill(e);
+          float4 v[UB][VPL];
+          float w[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int off = e + u - wbase;             // uniform across the group, < 2 * G
+            const int j = __shfl_sync(gmask, (off & G) ? wi1 : wi0, off & (G - 1), G);
+            const float wv = __shfl_sync(gmask, (off & G) ? ww1 : ww0, off & (G - 1), G);
+            const int rel = __popc(__ballot_sync(gmask, endk <= e + u) & gmask);
+            const bool on = !pred || e + u < cend;
+            w[u] = on ? wv : 0.f;
+            const float* __restrict__ rp = Fb + (size_t)j * ldf + (size_t)rel * rel_stride;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) v[u][k] = on ? ldg4(rp + vcol[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < UB; ++u)
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) fma4(mix[0][k], w[u], v[u][k]);
+          e += UB;
+        };
+        while (e + U <= cend) fbatch(std::integral_constant<int, U>{}, false);
+        const int n_left = cend - e;
+        if (n_left == 1) fbatch(std::integral_constant<int, 1>{}, false);
+        else if (n_left == 2) fbatch(std::integral_constant<int, (U >= 2 ? 2 : 1)>{}, U < 2);
+        else if (n_left > 0 && n_left <= 4 && U > 4) fbatch(std::integral_constant<int, (U > 4 ? 4 : 1)>{}, true);
+        else if (n_left > 0) fbatch(std::integral_constant<int, U>{}, true);
+        continue;
+      }
+    }
     for (int rr = 0; rr < rcount; ++rr) {
       const int r = rbase + rr;
       const int beg = __shfl_sync(gmask, my_beg, rr, G);
@@ -372,8 +420,11 @@ aggregate_rows_kernel(const AggParams p) {
       if (len == 0 && MIX != MIX_NONE) continue;
       if (MIX != MIX_BASIS && p.skip_hubs && len > p.hub_threshold) continue;   // added by hub_finish_kernel
       float4 acc[VPL];
+      // CHAIN: the weighted sums of the non-hub segments continue the row's accumulator itself (one chain of additions in
+      // edge order, whichever of the three code paths — streamed, per relation, row-sparse — walks the row)
+      const bool chained = CHAIN && len <= p.hub_threshold;
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < VPL; ++k) acc[k] = chained ? mix[0][k] : make_float4(0.f, 0.f, 0.f, 0.f);
       if (len > p.hub_threshold) {
         // hub: add the chunk partials in chunk order
         const int key = (int)(key0 + r);
@@ -531,7 +582,9 @@ aggregate_rows_kernel(const AggParams p) {
           if (act[k]) store_vec(p, LIST ? orow : row, r * p.block_stride + coff + vcol[k], acc[k]);
       } else if (MIX == MIX_SUM) {
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) add4(mix[0][k], acc[k]);
+        for (int k = 0; k < VPL; ++k) {
+          if (chained) mix[0][k] = acc[k]; else add4(mix[0][k], acc[k]);
+        }
       } else {
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -1280,6 +1333,13 @@ static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg
   p.init = init; p.ld_init = ld_init; p.B = 1;
   p.O = gX; p.ldo = ldgx; p.out_mode = 0; p.partials = (float*)workspace;
   p.slot = slot; p.zero_row = zero_row;
+  // OPT-IN (RGCN_STREAM_REL=1; =2: only where segments average fewer than four edges).  Measured on the B200 it LOSES
+  // everywhere: cfg2 (3 relations, nine edges per segment) step 0.331 -> 0.342 ms; cfg3 (30 relations) 2.80 -> 2.99 ms;
+  // the partitioned shard (1.25 M rows / 50 M edges / 30 relations, 1 GPU) 58.7 -> 78.1 ms per step — those walks already
+  // run at the HBM rate (45 GB in 6 ms), and the per-edge relation lookup is pure overhead there.
+  static int env_stream = -1;
+  if (env_stream < 0) { const char* e = getenv("RGCN_STREAM_REL"); env_stream = e ? atoi(e) : 0; }
+  p.stream_rel = env_stream == 2 ? (gt->E < 4 * gt->n_rows * (int64_t)gt->R ? 1 : 0) : (env_stream ? 1 : 0);
   if (mp) {
     p.mp_mask = mp->mask; p.ld_mp_mask = mp->ld_mask; p.mp_scale = mp->scale;
     p.mp_hi = mp->hi; p.mp_lo = mp->lo; p.ld_mp = mp->ldp; p.mp_colsum = mp->colsum_partial;
