@@ -374,9 +374,12 @@ aggregate_rows_kernel(const AggParams p) {
       // of segments that end at or before it (one ballot over the lanes' segment ends).  Same additions in the same
       // (edge) order as the per-relation loop below, which serves the passes that contain a hub segment.
       const bool lane_hub = rl < r_hi && my_end - my_beg > p.hub_threshold;
-      if ((__ballot_sync(gmask, lane_hub) & gmask) == 0u) {
-        const int cbeg = __shfl_sync(gmask, my_beg, 0, G);
-        const int cend = __shfl_sync(gmask, my_end, rcount - 1, G);
+      const int cbeg = __shfl_sync(gmask, my_beg, 0, G);
+      const int cend = __shfl_sync(gmask, my_end, rcount - 1, G);
+      // ... where it pays: passes whose non-empty segments average fewer than four edges (stream_rel = 1; 3 = always).  A
+      // power-law row is mostly a few long segments, whose batches are full anyway (cfg3: streaming everything costs 7 %)
+      const int n_seg = __popc(__ballot_sync(gmask, rl < r_hi && my_end > my_beg) & gmask);
+      if ((__ballot_sync(gmask, lane_hub) & gmask) == 0u && (p.stream_rel == 3 || cend - cbeg < 4 * n_seg)) {
         const int endk = rl < r_hi ? my_end : 0x7fffffff;          // lanes beyond the pass never count
         const float* __restrict__ Fb = F + (size_t)rbase * rel_stride;
         int e = cbeg;
@@ -1333,13 +1336,16 @@ static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg
   p.init = init; p.ld_init = ld_init; p.B = 1;
   p.O = gX; p.ldo = ldgx; p.out_mode = 0; p.partials = (float*)workspace;
   p.slot = slot; p.zero_row = zero_row;
-  // OPT-IN (RGCN_STREAM_REL=1; =2: only where segments average fewer than four edges).  Measured on the B200 it LOSES
-  // everywhere: cfg2 (3 relations, nine edges per segment) step 0.331 -> 0.342 ms; cfg3 (30 relations) 2.80 -> 2.99 ms;
-  // the partitioned shard (1.25 M rows / 50 M edges / 30 relations, 1 GPU) 58.7 -> 78.1 ms per step — those walks already
-  // run at the HBM rate (45 GB in 6 ms), and the per-edge relation lookup is pure overhead there.
+  // RGCN_STREAM_REL: 0 = never, 3 = every hub-free pass, 1 = per pass where the non-empty segments average fewer than
+  // four edges, 2 (default) = 3 on graphs whose segments average fewer than four edges and whose hub segments hold less
+  // than 1/16 of the edges, else 0.  Measured on the B200, everything streamed: the partitioned shard (1.25 M rows /
+  // 50 M edges / 30 relations, uniform; 1 GPU) 57.5 -> 54.8 ms per step (backward walks 7.84 + 5.96 -> 6.12 + 4.36 ms),
+  // but cfg3 (30 relations, power law: most edges sit in long segments whose batches are full anyway) 2.79 -> 2.99 ms;
+  // the per-pass rule (1) gives cfg3 2.80 ms but lets the two lane groups of a warp take different paths.
   static int env_stream = -1;
-  if (env_stream < 0) { const char* e = getenv("RGCN_STREAM_REL"); env_stream = e ? atoi(e) : 0; }
-  p.stream_rel = env_stream == 2 ? (gt->E < 4 * gt->n_rows * (int64_t)gt->R ? 1 : 0) : (env_stream ? 1 : 0);
+  if (env_stream < 0) { const char* e = getenv("RGCN_STREAM_REL"); env_stream = e ? atoi(e) : 2; }
+  p.stream_rel = env_stream != 2 ? env_stream
+                                 : ((gt->E < 4 * gt->n_rows * (int64_t)gt->R && (int64_t)gt->n_chunks * kHubChunk * 16 < gt->E) ? 3 : 0);
   if (mp) {
     p.mp_mask = mp->mask; p.ld_mp_mask = mp->ld_mask; p.mp_scale = mp->scale;
     p.mp_hi = mp->hi; p.mp_lo = mp->lo; p.ld_mp = mp->ldp; p.mp_colsum = mp->colsum_partial;

@@ -117,7 +117,7 @@ class _FusedEncoderFn(torch.autograd.Function):
             inside = (all_ids >= row0) & (all_ids < row0 + n)
             local = torch.where(inside, all_ids - row0, torch.full_like(all_ids, -1))
             half = local.numel() // 2
-            listed = ops.rows_list_build(local[:half], local[half:], n)
+            listed = ops.rows_list_build(local[:half], local[half:], n) + (all_ids, mine)
         saved, outs, wps = [], [], []
         for l in range(L):
             W, root, bias = params[3 * l: 3 * l + 3]
@@ -127,7 +127,7 @@ class _FusedEncoderFn(torch.autograd.Function):
             p_drop, seed, ctr = drops[l] if drops[l] is not None else (0.0, 0, None)
             last = l == L - 1
             # aggregate -> planes -> transform whose epilogue also stores every tile into all ranks' next buffer
-            rows_l, slot_l = listed if (last and listed is not None) else (None, None)
+            rows_l, slot_l = listed[:2] if (last and listed is not None) else (None, None)
             out, A, wp = ops.layer_fwd(graph, x_full, x_full[row0:row0 + n], W.reshape(K1, d_out), root, bias, not last, mode,
                                        p_drop, seed, ctr, peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out,
                                        rows=rows_l, slot=slot_l)
@@ -143,7 +143,12 @@ class _FusedEncoderFn(torch.autograd.Function):
         ctx.d0 = x0.size(1)
         ctx.save_for_backward(*saved, *[o for o in outs if o is not None])
         d_last = params[3 * (L - 1)].shape[2]
-        return ex.x_view(L, d_last)
+        out = ex.x_view(L, d_last)
+        if listed is not None:
+            rowsparse.mark_listed_output(out)       # the decoder's backward may leave the unlisted gradient rows undefined
+        else:
+            rowsparse.unmark_listed_output()
+        return out
 
     @staticmethod
     def backward(ctx, g_full):
@@ -158,7 +163,15 @@ class _FusedEncoderFn(torch.autograd.Function):
         masks = list(t[4 * L:])
         dev = g_full.device
         d_last = t[4 * (L - 1) + 2].shape[2]
-        ex.g_view(L, d_last).copy_(g_full)              # this rank's partial gradient of ALL rows, peer visible
+        if ctx.listed is not None:
+            # only the rows some rank's decoder read can carry a gradient, and only those are pulled: zero them in the peer
+            # visible buffer, then copy this rank's own rows (g_full is undefined elsewhere) — kilobytes instead of N x d
+            all_ids, mine = ctx.listed[2:]
+            gv = ex.g_view(L, d_last)
+            gv.index_fill_(0, all_ids, 0.0)
+            gv.index_copy_(0, mine, g_full.index_select(0, mine))       # (a repeated id carries the same row)
+        else:
+            ex.g_view(L, d_last).copy_(g_full)          # this rank's partial gradient of ALL rows, peer visible
         # The loss reads 2 * batch rows of the output (src/models/rgcn.py:325-326): every rank's g_full is zero outside the
         # rows ITS slice of the batch names (the decoder's backward announces them, rowsparse.py).  With all ranks' lists
         # the LAST layer's backward runs row-sparse, like the one-GPU model: a pull of the listed rows only (kilobytes
@@ -168,7 +181,7 @@ class _FusedEncoderFn(torch.autograd.Function):
         if ctx.listed is not None:
             # the forward computed the listed rows only (the same all-ranks list, already local): its compact planes are
             # the weight gradient's operand, its slot map serves the compaction
-            sparse_rows, slot_fwd = ctx.listed
+            sparse_rows, slot_fwd = ctx.listed[:2]
         elif claimed is not None:
             mine_rows = claimed[0]                                          # padded global ids, 2 * local batch entries
             all_rows = torch.empty(ex.world * mine_rows.numel(), dtype=torch.int64, device=dev)
