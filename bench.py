@@ -400,7 +400,7 @@ def library_gpu_baseline(kg, batch, dev, steps=5):
 # ---------------------------------------------------------------------------------------------
 # node-range partitioned path (north_star config 5), measured at every N
 # ---------------------------------------------------------------------------------------------
-def partitioned_record(rank, world, dev, steps=5, warmup=2):
+def partitioned_record(rank, world, dev, steps=5, warmup=4):
     """Destination-range partition of a cfg5-shaped graph sized per GPU (weak scaling).  Both exchange forms are timed:
     our kernels over peer-mapped memory (dist_fused.py, the product path) and NCCL all-gather / reduce-scatter (dist.py).
     Timing: CUDA events per step, barrier + synchronize on both sides, max over ranks."""

@@ -45,6 +45,12 @@ def sparse_last_layer() -> bool:
     return os.environ.get("PRIMEKG_RGCN_SPARSE_BWD", "1") != "0"
 
 
+def push_after_transform() -> bool:
+    """A/B switch (``RGCN_PEER_PUSH=1``): the all-gather of a layer's output as a separate row push after the transform
+    instead of peer stores from its epilogue."""
+    return os.environ.get("RGCN_PEER_PUSH", "0") == "1"
+
+
 def listed_last_layer() -> bool:
     """Listed-rows forward of the last layer (``PRIMEKG_RGCN_SPARSE_FWD=0`` or ``PRIMEKG_RGCN_SPARSE_BWD=0``: all rows)."""
     return sparse_last_layer() and os.environ.get("PRIMEKG_RGCN_SPARSE_FWD", "1") != "0" and ops.prepared_weights()
@@ -128,9 +134,14 @@ class _FusedEncoderFn(torch.autograd.Function):
             last = l == L - 1
             # aggregate -> planes -> transform whose epilogue also stores every tile into all ranks' next buffer
             rows_l, slot_l = listed[:2] if (last and listed is not None) else (None, None)
+            push_after = rows_l is None and push_after_transform()
             out, A, wp = ops.layer_fwd(graph, x_full, x_full[row0:row0 + n], W.reshape(K1, d_out), root, bias, not last, mode,
-                                       p_drop, seed, ctr, peer_out=ex.x_ptrs(l + 1), peer_row0=row0, peer_ld=d_out,
-                                       rows=rows_l, slot=slot_l)
+                                       p_drop, seed, ctr, peer_out=None if push_after else ex.x_ptrs(l + 1), peer_row0=row0,
+                                       peer_ld=d_out, rows=rows_l, slot=slot_l)
+            if push_after:
+                # all-gather as a separate push of whole rows (512-byte bursts per warp) instead of the epilogue's 64-byte
+                # pieces: no overlap with the MMA main loop, but a far better NVLink packet mix
+                ops.p2p_push_rows(out, ex.x_ptrs(l + 1), row0, d_out)
             ex.x.barrier()
             saved += [A[0], A[1], W, root]
             wps.append(wp)

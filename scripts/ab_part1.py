@@ -44,9 +44,16 @@ def step():
     return loss
 
 
-for _ in range(2):
+W = int(os.environ.get("AB_WARMUP", "2"))
+for _ in range(W):
     step()
 torch.cuda.synchronize()
+per = []
+for _ in range(int(os.environ.get("AB_STEPS", "5"))):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); loss = step(); b.record(); torch.cuda.synchronize()
+    per.append(round(a.elapsed_time(b), 1))
+print("per-step ms:", per)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(5):
