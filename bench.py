@@ -243,7 +243,14 @@ def roofline_block(pkg, kg, ei, et, flush, clocks, iters):
         roof["d64"] = {"fwd_achieved": round(f1 / (k1["aggregate_fwd"] * 1e-3) / 1e9, 1),
                        "bwd_achieved": round(b1 / (k1["aggregate_bwd"] * 1e-3) / 1e9, 1),
                        "l2_probe_peak": round(p1, 1), "fwd_frac": round(f1 / (k1["aggregate_fwd"] * 1e-3) / 1e9 / p1, 4),
-                       "unit": "GB/s", "fwd_ms": round(k1["aggregate_fwd"], 5), "bwd_ms": round(k1["aggregate_bwd"], 5)}
+                       "bwd_frac": round(b1 / (k1["aggregate_bwd"] * 1e-3) / 1e9 / p1, 4),
+                       "unit": "GB/s", "fwd_ms": round(k1["aggregate_fwd"], 5), "bwd_ms": round(k1["aggregate_bwd"], 5),
+                       "fwd_algorithmic_bytes_per_launch": f1, "bwd_algorithmic_bytes_per_launch": b1,
+                       "kernel": "hub_partial_kernel + aggregate_rows_kernel<16, 1, ...> (layer-1 gathers, 256-byte rows)",
+                       "note": "since the last layer runs on the listed rows only, these two dense walks are the largest "
+                               "kernels of the default step (timeline: forward 11 + 29 us, backward 10 + 50 us with the "
+                               "weight gradient running beside it); the d = 256 walk above is the dominant kernel of the "
+                               "all-rows formulation (dense_last_layer) and the reference point carried over from round 1"}
         del t1
     except Exception as ex:  # pragma: no cover
         roof["d64"] = {"error": repr(ex)[:200]}
