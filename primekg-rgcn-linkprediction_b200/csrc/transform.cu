@@ -32,6 +32,15 @@
 namespace rgcn {
 using namespace tc05;
 
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 constexpr int BM = 128;         // UMMA M
 constexpr int BK = 64;          // K per stage for K-major operands (= one 128-byte swizzle row of bf16)
 constexpr int BNMAX = 256;      // UMMA N max = TMEM columns per accumulator
@@ -185,7 +194,9 @@ struct KStage {
 // B_MN = false: B is K-major ([N, K] rows of K, the dgrad / all-pairs operand);  B_MN = true: B is MN-major ([K, N] rows
 // of N — the weight matrix exactly as PyTorch stores it, so the forward needs no transposed copy): the stage then holds
 // ceil(BN / 64) chunks of 64 k-rows x 128 B, the layout of the weight-gradient kernel's operands.
-template <bool SPLIT, bool B_MN, int EPI = EPI_STORE, int BNT = 128>
+// XF (EPI_STORE only) specialises the store loop, which is where an epilogue-bound launch spends its instructions:
+// 0 = plain store, 1 = + fused dropout, 2 = everything decided at run time (bf16 copy, peer stores, scattered rows)
+template <bool SPLIT, bool B_MN, int EPI = EPI_STORE, int BNT = 128, int XF = 2>
 __global__ void __launch_bounds__(K_THREADS, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -246,10 +257,17 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int quarter = warp & 3, half = warp >> 2;
     const int c_lo = half * (p.BN >> 1), c_hi = c_lo + (p.BN >> 1);
     float* patch = reinterpret_cast<float*>(smem + (size_t)S::STAGES * S::BYTES + (size_t)warp * K_PATCH);
-    uint32_t drop_key = 0;
-    if (p.drop_thresh) {
+    const uint32_t patch_s = smem_u32(patch);              // (explicit shared-space accesses: the pointer arithmetic above
+                                                           //  hides the address space from the compiler -> generic LD / ST)
+    constexpr bool DROP = XF >= 1, EXTRA = XF == 2;
+    uint32_t drop_key = 0, bk_small = 0;
+    bool drop_small = false;
+    if (DROP && p.drop_thresh) {
       const unsigned long long ctr = *p.drop_ctr;
       drop_key = pcg_hash(p.drop_seed ^ (uint32_t)ctr) + (uint32_t)(ctr >> 32);
+      // fewer than 2^32 elements: every element lies in block 0, whose key is computed once
+      drop_small = (unsigned long long)(p.M + p.row_offset) * (unsigned long long)p.N < (1ull << 32);
+      bk_small = drop_block_key(drop_key, 0);
     }
     // per-row state of the consuming epilogues (one row per lane)
     int64_t cur_m0 = -1;
@@ -376,7 +394,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           float4 qv = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
                                   __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
           if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
-          *reinterpret_cast<float4*>(patch + lane * 20 + j) = qv;
+          sts4(patch_s + (uint32_t)(lane * 20 + j) * 4u, qv);
         }
         __syncwarp();
         // patch -> global: each instruction writes 8 rows x 64 contiguous bytes
@@ -387,18 +405,20 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           const int rl = rr + (lane >> 2);
           int64_t row = m0 + quarter * 32 + rl;
           if (row < p.M && col_ok) {
-            if (p.out_rows) {
+            if (EXTRA && p.out_rows) {
               if (row >= p.n_out_rows) continue;
               const int64_t pos = row;
               row = __ldg(p.out_rows + pos);
               if (p.out_slot && __ldg(p.out_slot + row) != (int32_t)pos) continue;
             }
-            float4 v = *reinterpret_cast<const float4*>(patch + rl * 20 + c4);
-            if (p.drop_thresh) {
-              // N % 4 == 0, so the four elements of one store never straddle a 2^32 block
-              const uint64_t e0 = (uint64_t)(row + p.row_offset) * (uint64_t)p.N + (uint64_t)(n0 + cc + c4);
+            float4 v = lds4(patch_s + (uint32_t)(rl * 20 + c4) * 4u);
+            if (DROP && (XF == 1 || p.drop_thresh)) {
+              // N % 4 == 0, so the four elements of one store never straddle a 2^32 block; the low 32 bits of the element
+              // index are a 32-bit product, the block key needs the high part only beyond 2^32 elements
+              const uint32_t e32 = (uint32_t)(row + p.row_offset) * (uint32_t)p.N + (uint32_t)(n0 + cc + c4);
+              const uint32_t bk = drop_small ? bk_small
+                                             : drop_block_key(drop_key, (uint64_t)(row + p.row_offset) * (uint64_t)p.N + (uint64_t)(n0 + cc + c4));
               // two hashes per store, 16 random bits per element (p is resolved to 2^-16)
-              const uint32_t bk = drop_block_key(drop_key, e0), e32 = (uint32_t)e0;
               const uint32_t h0 = pcg_hash(e32 ^ bk), h1 = pcg_hash((e32 + 2) ^ bk);
               v.x = (h0 & 0xffffu) >= p.drop_thresh ? v.x * p.drop_scale : 0.f;
               v.y = (h0 >> 16) >= p.drop_thresh ? v.y * p.drop_scale : 0.f;
@@ -406,15 +426,17 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               v.w = (h1 >> 16) >= p.drop_thresh ? v.w * p.drop_scale : 0.f;
             }
             *reinterpret_cast<float4*>(p.out + row * p.ldo + n0 + cc + c4) = v;
-            if (p.out16) {
-              __nv_bfloat162 b01 = __floats2bfloat162_rn(v.x, v.y), b23 = __floats2bfloat162_rn(v.z, v.w);
-              uint2 o;
-              o.x = *reinterpret_cast<uint32_t*>(&b01);
-              o.y = *reinterpret_cast<uint32_t*>(&b23);
-              *reinterpret_cast<uint2*>(p.out16 + row * p.ldo16 + n0 + cc + c4) = o;
+            if (EXTRA) {
+              if (p.out16) {
+                __nv_bfloat162 b01 = __floats2bfloat162_rn(v.x, v.y), b23 = __floats2bfloat162_rn(v.z, v.w);
+                uint2 o;
+                o.x = *reinterpret_cast<uint32_t*>(&b01);
+                o.y = *reinterpret_cast<uint32_t*>(&b23);
+                *reinterpret_cast<uint2*>(p.out16 + row * p.ldo16 + n0 + cc + c4) = o;
+              }
+              for (int q = 0; q < p.n_peer; ++q)
+                *reinterpret_cast<float4*>(p.peer_out[q] + (p.peer_row0 + row) * p.peer_ld + n0 + cc + c4) = v;
             }
-            for (int q = 0; q < p.n_peer; ++q)
-              *reinterpret_cast<float4*>(p.peer_out[q] + (p.peer_row0 + row) * p.peer_ld + n0 + cc + c4) = v;
           }
         }
         __syncwarp();
@@ -732,22 +754,32 @@ static int check_plane(const void* p, int64_t ld, const char* what) {
 // out[M, N] = A @ B^T with A planes [M, K] (ld lda) and weight planes [n_pad, k_pad]
 // B operand: a bf16 matrix [b_rows, b_cols] with leading dimension b_ld.  K-major (b_mn = false): rows = N, cols = K;
 // MN-major (b_mn = true): rows = K, cols = N (TMA boxes of 64 columns x BK rows).
+template <bool SPLIT, bool B_MN, int BNT, int XF>
+static int launch_kmajor_x(const GemmKParams& p, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
+                           const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
+  int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, BNT, XF>, KStage<SPLIT, BNT>::SMEM);
+  if (rc) return rc;
+  RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, BNT, XF>, dim3(grid), dim3(K_THREADS), KStage<SPLIT, BNT>::SMEM, st,
+                       ahi, alo, mhi, mlo, p));
+  RGCN_LAUNCH_CHECK();
+  return RGCN_OK;
+}
+
 template <bool SPLIT, bool B_MN>
 static int launch_kmajor_t(const GemmKParams& p, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
                            const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
+  // the store loop's variant: 2 = run-time everything (bf16 copy, peer stores, scattered rows), 1 = dropout, 0 = plain
+  static int force_generic = -1;
+  if (force_generic < 0) { const char* e = getenv("RGCN_GENERIC_EPILOGUE"); force_generic = (e && e[0] == '1') ? 1 : 0; }
+  const int xf = (force_generic || p.out_rows || p.out16 || p.n_peer) ? 2 : (p.drop_thresh ? 1 : 0);
   if (p.BN > 128) {
-    int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, 256>, KStage<SPLIT, 256>::SMEM);
-    if (rc) return rc;
-    RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, 256>, dim3(grid), dim3(K_THREADS), KStage<SPLIT, 256>::SMEM, st,
-                         ahi, alo, mhi, mlo, p));
-    RGCN_LAUNCH_CHECK();
-    return RGCN_OK;
+    if (xf == 0) return launch_kmajor_x<SPLIT, B_MN, 256, 0>(p, ahi, alo, mhi, mlo, grid, st);
+    if (xf == 1) return launch_kmajor_x<SPLIT, B_MN, 256, 1>(p, ahi, alo, mhi, mlo, grid, st);
+    return launch_kmajor_x<SPLIT, B_MN, 256, 2>(p, ahi, alo, mhi, mlo, grid, st);
   }
-  int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN>, KStage<SPLIT>::SMEM);
-  if (rc) return rc;
-  RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN>, dim3(grid), dim3(K_THREADS), KStage<SPLIT>::SMEM, st, ahi, alo, mhi, mlo, p));
-  RGCN_LAUNCH_CHECK();
-  return RGCN_OK;
+  if (xf == 0) return launch_kmajor_x<SPLIT, B_MN, 128, 0>(p, ahi, alo, mhi, mlo, grid, st);
+  if (xf == 1) return launch_kmajor_x<SPLIT, B_MN, 128, 1>(p, ahi, alo, mhi, mlo, grid, st);
+  return launch_kmajor_x<SPLIT, B_MN, 128, 2>(p, ahi, alo, mhi, mlo, grid, st);
 }
 
 // widest column tile of the prepared-weights transforms (RGCN_WIDE_TILES=0: always 128)
