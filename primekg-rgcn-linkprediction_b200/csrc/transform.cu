@@ -170,9 +170,18 @@ struct GemmKParams {
 enum { EPI_STORE = 0, EPI_RANK = 1, EPI_THR = 2, EPI_TOPK = 3 };
 constexpr int kTopK = 16;                     // entries every epilogue lane keeps per row (top-K requests up to this)
 constexpr int KBN = 128;                      // N tile of the persistent kernel: two accumulators fit 256 TMEM columns
-constexpr int K_EPI_WARPS = 8;                // two warps per TMEM lane quarter, each draining half of the tile's columns
-constexpr int K_PATCH = 32 * 20 * 4;          // per-warp transpose patch: 32 rows x (16 + 4) floats
+// Epilogue warps: a warp may only address the TMEM lane quarter 32 (w % 4) .. +31, so the warps of a quarter share the
+// tile's COLUMNS.  The storing epilogue is latency bound (TMEM load -> patch -> global stores, a few hundred dependent
+// cycles per 16-column chunk) and takes four warps per quarter; the consuming epilogues (rank / threshold / top-k) keep
+// per-row state over a contiguous half of the columns and stay at two.
+constexpr int K_EPI_WARPS = 8;                // consuming epilogues: two warps per quarter, half of the columns each
+constexpr int K_EPI_WARPS_STORE = 16;         // storing epilogue: four per quarter, 16-column chunks dealt round robin
+constexpr int K_PATCH = 32 * 20 * 4;          // per-warp patch, consuming epilogues: 32 lanes x 10 staged (value, index) pairs
+constexpr int K_PATCH_STORE = 32 * 16 * 4;    // per-warp transpose patch, storing epilogue: 32 rows x 16 floats, XOR swizzled
 constexpr int K_THREADS = (K_EPI_WARPS + 2) * 32;
+constexpr int K_THREADS_STORE = (K_EPI_WARPS_STORE + 2) * 32;
+constexpr int epi_warps(int epi) { return epi == 0 ? K_EPI_WARPS_STORE : K_EPI_WARPS; }
+constexpr int epi_patch(int epi) { return epi == 0 ? K_PATCH_STORE : K_PATCH; }
 
 // BNT = widest column tile the instantiation can hold: 128 (two accumulators in 256 TMEM columns, 3 / 6 stages) or 256
 // (two accumulators fill the 512 TMEM columns; A is then read once for 256 output columns — the K = 1,024 forward is
@@ -185,7 +194,8 @@ struct KStage {
   static constexpr int STAGES = BNT == 256 ? (SPLIT ? 2 : 4) : (SPLIT ? 3 : 6);
   static constexpr int A_HI = 0, A_LO = A_BYTES;
   static constexpr int B_HI = (SPLIT ? 2 : 1) * A_BYTES, B_LO = B_HI + B_BYTES;
-  static constexpr int SMEM = STAGES * BYTES + K_EPI_WARPS * K_PATCH + 1024;
+  static constexpr int SMEM = STAGES * BYTES + K_EPI_WARPS * K_PATCH + 1024;                    // consuming epilogues
+  static constexpr int SMEM_STORE = STAGES * BYTES + K_EPI_WARPS_STORE * K_PATCH_STORE + 1024;  // storing epilogue
 };
 
 // Persistent, warp-specialised: CTA c walks tiles c, c + grid, ... (column tile fastest, so neighbouring CTAs share
@@ -197,16 +207,17 @@ struct KStage {
 // XF (EPI_STORE only) specialises the store loop, which is where an epilogue-bound launch spends its instructions:
 // 0 = plain store, 1 = + fused dropout, 2 = everything decided at run time (bf16 copy, peer stores, scattered rows)
 template <bool SPLIT, bool B_MN, int EPI = EPI_STORE, int BNT = 128, int XF = 2>
-__global__ void __launch_bounds__(K_THREADS, 1)
+__global__ void __launch_bounds__((epi_warps(EPI) + 2) * 32, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmKParams p) {
   using S = KStage<SPLIT, BNT>;
+  constexpr int EW = epi_warps(EPI);              // epilogue warps; warp EW = TMA producer, warp EW + 1 = MMA issuer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[S::STAGES], empty_bar[S::STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_bias[1024];
+  __shared__ __align__(16) float s_bias[256];      // the whole bias when N <= 256 (wider layers read it from global memory)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m_tiles = (p.M + BM - 1) / BM;
@@ -231,11 +242,11 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);              // tcgen05.commit after the tile's last MMA
-      mbar_init(&tempty_bar[a], K_EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], EW);            // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
-  if (warp == K_EPI_WARPS && lane == 0) {
+  if (warp == EW && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
     tma_prefetch_desc(&tm_b_hi);
     if (SPLIT) { tma_prefetch_desc(&tm_a_lo); tma_prefetch_desc(&tm_b_lo); }
@@ -248,15 +259,18 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   // everything above is independent of the predecessor's data: barriers, TMEM, descriptor prefetch
   pdl_launch_dependents();
   pdl_wait();
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   __syncthreads();
 
-  if (warp < K_EPI_WARPS) {
-    // ===================== epilogue: warp w drains TMEM lanes 32 (w % 4) .. +31 (the quarter a warp may address),
-    // columns [half * BN / 2, (half + 1) * BN / 2) with half = w / 4, in sub-chunks of 16 columns ===============
+  if (warp < EW) {
+    // ===================== epilogue: warp w drains TMEM lanes 32 (w % 4) .. +31 (the quarter a warp may address) in
+    // sub-chunks of 16 columns: the storing epilogue deals the chunks round robin to the quarter's four warps (chunk
+    // w / 4, w / 4 + 4, ...), the consuming ones give warp w the contiguous half w / 4 of the columns ===============
     const int quarter = warp & 3, half = warp >> 2;
-    const int c_lo = half * (p.BN >> 1), c_hi = c_lo + (p.BN >> 1);
-    float* patch = reinterpret_cast<float*>(smem + (size_t)S::STAGES * S::BYTES + (size_t)warp * K_PATCH);
+    const int c_lo = EPI == EPI_STORE ? half * 16 : half * (p.BN >> 1);
+    const int c_hi = EPI == EPI_STORE ? p.BN : c_lo + (p.BN >> 1);
+    constexpr int c_step = EPI == EPI_STORE ? (EW / 4) * 16 : 16;
+    float* patch = reinterpret_cast<float*>(smem + (size_t)S::STAGES * S::BYTES + (size_t)warp * epi_patch(EPI));
     const uint32_t patch_s = smem_u32(patch);              // (explicit shared-space accesses: the pointer arithmetic above
                                                            //  hides the address space from the compiler -> generic LD / ST)
     constexpr bool DROP = XF >= 1, EXTRA = XF == 2;
@@ -345,7 +359,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       mbar_wait(&tfull_bar[a], (uint32_t)((iter >> 1) & 1));
       fence_after_sync();
       const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * acc_cols;
-      for (int cc = c_lo; cc < c_hi; cc += 16) {
+      for (int cc = c_lo; cc < c_hi; cc += c_step) {
         uint32_t r[16];
         tmem_ld_32x16(t_lane + cc, r);
         tmem_ld_wait();
@@ -390,11 +404,21 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // registers (one row per lane) -> patch, + bias / ReLU
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(s_bias + ((n0 + cc + j) & 1023));
+          float4 b;
+          if (p.N <= 256) {
+            b = *reinterpret_cast<const float4*>(s_bias + ((n0 + cc + j) & 255));
+          } else {
+            const int c0 = n0 + cc + j;
+            const bool on = p.bias != nullptr && c0 < p.N;                   // (N % 4 == 0)
+            b = on ? make_float4(__ldg(p.bias + c0), __ldg(p.bias + c0 + 1), __ldg(p.bias + c0 + 2), __ldg(p.bias + c0 + 3))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           float4 qv = make_float4(__uint_as_float(r[j]) + b.x, __uint_as_float(r[j + 1]) + b.y,
                                   __uint_as_float(r[j + 2]) + b.z, __uint_as_float(r[j + 3]) + b.w);
           if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
-          sts4(patch_s + (uint32_t)(lane * 20 + j) * 4u, qv);
+          // row `lane`, 16-byte chunk j / 4, XOR swizzled by the row pair: conflict-free for the row-wise writes here and
+          // for the 8-rows x 64-byte reads below, without padding (16 warps' patches must fit beside the operand ring)
+          sts4(patch_s + (uint32_t)(lane * 16 + (((j >> 2) ^ ((lane >> 1) & 3)) << 2)) * 4u, qv);
         }
         __syncwarp();
         // patch -> global: each instruction writes 8 rows x 64 contiguous bytes
@@ -411,7 +435,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
               row = __ldg(p.out_rows + pos);
               if (p.out_slot && __ldg(p.out_slot + row) != (int32_t)pos) continue;
             }
-            float4 v = lds4(patch_s + (uint32_t)(rl * 20 + c4) * 4u);
+            float4 v = lds4(patch_s + (uint32_t)(rl * 16 + (((c4 >> 2) ^ ((rl >> 1) & 3)) << 2)) * 4u);
             if (DROP && (XF == 1 || p.drop_thresh)) {
               // N % 4 == 0, so the four elements of one store never straddle a 2^32 block; the low 32 bits of the element
               // index are a 32-bit product, the block key needs the high part only beyond 2^32 elements
@@ -445,7 +469,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (lane == 0) mbar_arrive(&tempty_bar[a]);       // accumulator a may be overwritten
     }
     if (EPI != EPI_STORE) flush_row_state();
-  } else if (warp == K_EPI_WARPS) {
+  } else if (warp == EW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       // a TMA box always delivers its full byte count (out-of-range elements arrive as zeros)
@@ -757,9 +781,9 @@ static int check_plane(const void* p, int64_t ld, const char* what) {
 template <bool SPLIT, bool B_MN, int BNT, int XF>
 static int launch_kmajor_x(const GemmKParams& p, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
                            const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
-  int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, BNT, XF>, KStage<SPLIT, BNT>::SMEM);
+  int rc = set_smem(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, BNT, XF>, KStage<SPLIT, BNT>::SMEM_STORE);
   if (rc) return rc;
-  RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, BNT, XF>, dim3(grid), dim3(K_THREADS), KStage<SPLIT, BNT>::SMEM, st,
+  RGCN_CUDA(launch_pdl(gemm_kmajor_kernel<SPLIT, B_MN, EPI_STORE, BNT, XF>, dim3(grid), dim3(K_THREADS_STORE), KStage<SPLIT, BNT>::SMEM_STORE, st,
                        ahi, alo, mhi, mlo, p));
   RGCN_LAUNCH_CHECK();
   return RGCN_OK;
