@@ -229,6 +229,15 @@ int rgcn_aggregate_bwd_rows(const rgcn_csr_t* gt, const float* gH_rows, int64_t 
                             float* gX, int64_t ldgx, const rgcn_masked_planes_out* masked_planes,
                             void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
 
+/* rgcn_aggregate_bwd_rows on a graph much larger than the row list (a partitioned shard walks ALL sources of the graph for
+ * the ~2 * batch listed rows): src_flag (scratch, gt->n_rows bytes) is cleared, the sources of the listed rows' in-edges are
+ * marked from the FORWARD-orientation CSR g_fwd (rows / slot of rgcn_rows_list_build or rgcn_link_loss_bwd_rows), and
+ * unmarked rows leave the walk at once.  Same results (the skipped rows only ever add exact zeros). */
+int rgcn_aggregate_bwd_rows_marked(const rgcn_csr_t* gt, const rgcn_csr_t* g_fwd, const int64_t* rows, int64_t n_list,
+                                   uint8_t* src_flag, const float* gH_rows, int64_t ldg, int32_t d, const int32_t* slot,
+                                   int32_t zero_row, const float* init_rows, int64_t ld_init, float* gX, int64_t ldgx,
+                                   void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Relational transform on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM, every operand tile
  * streamed by TMA).  Replaces the R+1 matmuls `h_r @ W_r`, `x @ root` per layer of RGCNConv's loop path
@@ -370,6 +379,10 @@ typedef struct rgcn_layer_bwd_args {
   const void* w_planes;                     /* optional: the weight planes rgcn_layer_fwd prepared (dgrad reads them) */
   int32_t a_compact;                        /* row-sparse form: A_hi / A_lo are the compact planes of the listed-rows
                                                forward over this very list (no copy; Ac_* unused)                   */
+  const rgcn_csr_t* csr_fwd; uint8_t* src_flag;   /* row-sparse form, optional (both or none): the forward-orientation CSR
+                                               and n_src bytes of scratch -> the walk skips the sources that have no edge
+                                               into a listed row (rgcn_aggregate_bwd_rows_marked); for graphs much
+                                               larger than the row list                                             */
 } rgcn_layer_bwd_args;
 
 /* Compaction step of the row-sparse backward (csrc/rowsparse.cu), also callable on its own:

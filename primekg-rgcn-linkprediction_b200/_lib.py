@@ -61,7 +61,7 @@ class LayerBwdArgs(C.Structure):
                 ("agg_workspace", p), ("agg_workspace_bytes", sz), ("gemm_workspace", p), ("gemm_workspace_bytes", sz),
                 ("rows", p), ("n_list", i64), ("slot", p), ("Ac_hi", p), ("Ac_lo", p), ("ldac", i64),
                 ("next_G", C.POINTER(MaskedPlanesOut)), ("g_ready", i32), ("n_colsum_ready", i32), ("slot_ready", i32),
-                ("w_planes", p), ("a_compact", i32)]
+                ("w_planes", p), ("a_compact", i32), ("csr_fwd", PCSR), ("src_flag", p)]
 
 # name -> (restype, argtypes); must list every symbol of include/rgcn_b200.h
 PROTOTYPES = {
@@ -94,6 +94,7 @@ PROTOTYPES = {
     "rgcn_transform_fwd_w_rows": (C.c_int, [p, p, i64, i32, p, p, i32, i64, i32, p, i64, i32, p, i64, p, p, i32, i64, i64, p]),
     "rgcn_transform_dgrad_w": (C.c_int, [p, p, i64, i32, p, i32, i64, p, i64, i32, p]),
     "rgcn_aggregate_bwd_rows": (C.c_int, [PCSR, p, i64, i32, p, i32, p, i64, p, i64, C.POINTER(MaskedPlanesOut), p, sz, p]),
+    "rgcn_aggregate_bwd_rows_marked": (C.c_int, [PCSR, PCSR, p, i64, p, p, i64, i32, p, i32, p, i64, p, i64, p, sz, p]),
     "rgcn_rows_compact_size": (i64, [i64]),
     "rgcn_rows_compact_blocks": (i64, [i64]),
     "rgcn_rows_compact": (C.c_int, [p, i64, i64, p, p, i64, i32, p, p, i64, p, p, i64, i32, p, p, i64, p, p, i32, i32, p]),

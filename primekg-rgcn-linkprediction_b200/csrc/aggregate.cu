@@ -97,6 +97,10 @@ struct AggParams {
   int64_t list_walkers;
   int32_t list_by_rows;
   int32_t stream_rel;        // backward walk: stream a row's edges across relation boundaries (short segments, many relations)
+  // row-sparse backward on large graphs (nullable): row_flag[j] != 0 iff some edge of source row j gathers a LISTED row
+  // (marked beforehand from the forward-orientation CSR of the listed rows, mark_sources_kernel); the other rows leave at
+  // once with their init row — the walk then costs per marked row, not per row of the graph
+  const uint8_t* row_flag;
   // hub pass filter (nullable): node -> first list position map; chunks of rows with hub_filter[row] == hub_unlisted are skipped
   const int32_t* hub_filter;
   int32_t hub_unlisted;
@@ -333,6 +337,13 @@ aggregate_rows_kernel(const AggParams p) {
 #pragma unroll
       for (int k = 0; k < VPL; ++k) mix[0][k] = ldg4(p.init + irow * p.ld_init + vcol[k]);
     }
+  }
+  if (SLOT && !MP && MIX == MIX_SUM && p.row_flag && !__ldg(p.row_flag + row)) {
+    // (group-uniform) none of this row's edges gathers a listed row: every term of its sum is an exact zero
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+      if (act[k]) store_vec(p, row, vcol[k], mix[0][k]);
+    return;
   }
 
   // A row's edges are contiguous in the CSR (sorted by (row, relation)).  The group keeps a window of 2*G edge
@@ -1292,7 +1303,8 @@ extern "C" int rgcn_aggregate_fwd_bf16(const rgcn_csr_t* g, const void* X16, int
 
 static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,
                               int32_t zero_row, const float* init, int64_t ld_init, float* gX, int64_t ldgx,
-                              const rgcn_masked_planes_out* mp, void* workspace, size_t workspace_bytes, rgcn_stream_t stream);
+                              const rgcn_masked_planes_out* mp, void* workspace, size_t workspace_bytes, rgcn_stream_t stream,
+                              const uint8_t* row_flag = nullptr);
 
 // grid of the (unmixed / summed) row walk = rows of the column-sum partials of rgcn_masked_planes_out
 extern "C" int64_t rgcn_aggregate_row_blocks(const rgcn_csr_t* g, int32_t d) {
@@ -1315,9 +1327,45 @@ extern "C" int rgcn_aggregate_bwd_rows(const rgcn_csr_t* gt, const float* gH_row
   return aggregate_bwd_impl(gt, gH_rows, ldg, d, slot, zero_row, init_rows, ld_init, gX, ldgx, mp, workspace, workspace_bytes, stream);
 }
 
+namespace rgcn {
+// one warp per list position (first positions only): flag every source of the listed row's in-edges
+__global__ void __launch_bounds__(256) mark_sources_kernel(const int32_t* __restrict__ rowptr_f, const int32_t* __restrict__ idx_f,
+                                                           int32_t R, const int64_t* __restrict__ rows, int64_t n_list,
+                                                           const int32_t* __restrict__ slot, uint8_t* __restrict__ flag) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= n_list) return;
+  const int64_t row = rows[c];
+  if (__ldg(slot + row) != (int32_t)c) return;
+  const int beg = __ldg(rowptr_f + row * R), end = __ldg(rowptr_f + row * R + R);
+  for (int e = beg + lane; e < end; e += 32) flag[__ldg(idx_f + e)] = 1;
+}
+}  // namespace rgcn
+
+// Row-sparse backward walk on a graph much larger than the row list: src_flag [gt->n_rows] (scratch) is cleared, the
+// sources of the listed rows' in-edges are marked from the FORWARD-orientation CSR g_fwd, and unmarked rows leave the walk
+// at once.  Same results as rgcn_aggregate_bwd_rows (the skipped rows only ever add exact zeros).
+extern "C" int rgcn_aggregate_bwd_rows_marked(const rgcn_csr_t* gt, const rgcn_csr_t* g_fwd, const int64_t* rows, int64_t n_list,
+                                              uint8_t* src_flag, const float* gH_rows, int64_t ldg, int32_t d,
+                                              const int32_t* slot, int32_t zero_row, const float* init_rows, int64_t ld_init,
+                                              float* gX, int64_t ldgx, void* workspace, size_t workspace_bytes,
+                                              rgcn_stream_t stream) {
+  RGCN_CHECK_ARG(gt && g_fwd && rows && n_list > 0 && src_flag && slot && zero_row >= 0, "aggregate_bwd_rows_marked: null argument");
+  RGCN_CHECK_ARG(g_fwd->R == gt->R && g_fwd->rowptr && (g_fwd->idx || g_fwd->E == 0), "aggregate_bwd_rows_marked: the two orientations disagree");
+  cudaStream_t st = (cudaStream_t)stream;
+  RGCN_CUDA(cudaMemsetAsync(src_flag, 0, (size_t)gt->n_rows, st));
+  RGCN_CUDA(launch_pdl(mark_sources_kernel, dim3((unsigned)((n_list + 7) / 8)), dim3(256), 0, st, g_fwd->rowptr, g_fwd->idx, g_fwd->R,
+                       rows, n_list, slot, src_flag));
+  RGCN_LAUNCH_CHECK();
+  return aggregate_bwd_impl(gt, gH_rows, ldg, d, slot, zero_row, init_rows, ld_init, gX, ldgx, nullptr, workspace, workspace_bytes,
+                            stream, src_flag);
+}
+
 static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg, int32_t d, const int32_t* slot,
                               int32_t zero_row, const float* init, int64_t ld_init, float* gX, int64_t ldgx,
-                              const rgcn_masked_planes_out* mp, void* workspace, size_t workspace_bytes, rgcn_stream_t stream) {
+                              const rgcn_masked_planes_out* mp, void* workspace, size_t workspace_bytes, rgcn_stream_t stream,
+                              const uint8_t* row_flag) {
   int rc = check_common(gt, gH, ldg, d, workspace, workspace_bytes);
   if (rc) return rc;
   RGCN_CHECK_ARG(!mp || (mp->mask && mp->hi && ((uintptr_t)mp->mask & 15) == 0 && mp->ld_mask % 4 == 0 &&
@@ -1335,7 +1383,7 @@ static int aggregate_bwd_impl(const rgcn_csr_t* gt, const float* gH, int64_t ldg
   p.F = gH; p.ldf = ldg; p.src_rel_stride = d; p.d = d; p.block_stride = d;
   p.init = init; p.ld_init = ld_init; p.B = 1;
   p.O = gX; p.ldo = ldgx; p.out_mode = 0; p.partials = (float*)workspace;
-  p.slot = slot; p.zero_row = zero_row;
+  p.slot = slot; p.zero_row = zero_row; p.row_flag = row_flag;
   // RGCN_STREAM_REL: 0 = never, 3 = every hub-free pass, 1 = per pass where the non-empty segments average fewer than
   // four edges, 2 (default) = 3 on graphs whose segments average fewer than four edges and whose hub segments hold less
   // than 1/16 of the edges, else 0.  Measured on the B200, everything streamed: the partitioned shard (1.25 M rows /

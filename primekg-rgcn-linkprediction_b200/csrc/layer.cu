@@ -256,6 +256,10 @@ static int layer_bwd_rows(const rgcn_layer_bwd_args* a, rgcn_stream_t stream) {
   const void* Aw_lo = a->a_compact ? a->A_lo : a->Ac_lo;
   const int64_t ldw = a->a_compact ? a->lda : a->ldac;
   return dgrad_walk_wgrad(a, m_c, Aw_hi, Aw_lo, ldw, (int32_t)rgcn_rows_compact_blocks(a->n_list), [&]() {
+    if (a->csr_fwd && a->src_flag && !a->next_G)
+      return rgcn_aggregate_bwd_rows_marked(a->csr_t, a->csr_fwd, a->rows, a->n_list, a->src_flag, a->gA, a->ld_gA, a->d_in, a->slot,
+                                            (int32_t)m_c, a->add_root_term ? a->gA + K1 : nullptr, a->ld_gA, a->g_x, a->ld_g_x,
+                                            a->agg_workspace, a->agg_workspace_bytes, stream);
     return rgcn_aggregate_bwd_rows(a->csr_t, a->gA, a->ld_gA, a->d_in, a->slot, (int32_t)m_c,
                                    a->add_root_term ? a->gA + K1 : nullptr, a->ld_gA, a->g_x, a->ld_g_x, a->next_G,
                                    a->agg_workspace, a->agg_workspace_bytes, stream);

@@ -507,6 +507,14 @@ def _gemm_workspace(device, n: int, K: int, d_out: int) -> torch.Tensor:
     return _workspace(device, nb)
 
 
+MARK_SOURCES_RATIO = 8       # rows of the graph per list entry from which the row-sparse walk marks its sources first
+
+
+def mark_sources() -> bool:
+    import os
+    return os.environ.get("RGCN_MARK_SOURCES", "1") != "0"
+
+
 def _dp(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -653,6 +661,10 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         nxt_struct = masked_planes_struct(nmask, nscale, nplanes, ncs)
     aws = g.bwd.workspace(d_in)
     gws = _gemm_workspace(dev, m, K, d_out)
+    # graphs much larger than the row list: the walk skips the sources without an edge into a listed row
+    src_flag = None
+    if sparse and need_x and next_mask is None and g.n_src >= MARK_SOURCES_RATIO * rows.numel() and mark_sources():
+        src_flag = torch.empty(g.n_src, dtype=torch.uint8, device=dev)
     args = _lib.LayerBwdArgs(
         g.bwd.ptr, gO.data_ptr(), gO.stride(0), _dp(relu_mask), 0 if relu_mask is None else relu_mask.stride(0),
         float(mask_scale), n, d_in, d_out, _mode_id(mode), int(add_root_term), W2d.data_ptr(), root.data_ptr(),
@@ -663,7 +675,8 @@ def layer_bwd(g: RelGraph, gO: torch.Tensor, relu_mask: Optional[torch.Tensor], 
         _dp(rows), 0 if rows is None else rows.numel(), _dp(slot), _dp(Ac[0]), _dp(Ac[1]),
         0 if Ac[0] is None else Ac[0].stride(0),
         C.pointer(nxt_struct) if nxt_struct is not None else None, int(g_ready is not None),
-        0 if g_ready is None else colsum.size(0), int(slot_ready), _dp(w_planes), int(bool(a_compact)))
+        0 if g_ready is None else colsum.size(0), int(slot_ready), _dp(w_planes), int(bool(a_compact)),
+        g.fwd.ptr if src_flag is not None else None, _dp(src_flag))
     _lib.check(lib.rgcn_layer_bwd(C.byref(args), _stream(dev)), "rgcn_layer_bwd")
     if sparse and return_compact:
         return gx, gA, gW, groot, gb, slot

@@ -59,6 +59,21 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
 dist.barrier()
+# every rank: one line with its own kernel time by category (is some rank systematically slower than the others?)
+cat = collections.defaultdict(float)
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        n = e.name
+        k = ("barrier" if "barrier_kernel" in n else "walk_fwd" if ("aggregate_rows" in n and "false, false, false" in n.split("<")[-1] and ", 0, false" in n)
+             else "walk_bwd" if "aggregate_rows" in n else "hub" if "hub_partial" in n else "gemm_fwd" if "gemm_kmajor_kernel<true, true" in n
+             else "dgrad" if "gemm_kmajor" in n else "wgrad" if "wgrad" in n else "pull" if ("reduce_split" in n or "pull_rows" in n)
+             else "push" if "push_rows" in n else "other")
+        cat[k] += e.device_time / 1e3
+line = f"rank {rank}: step {step_ms:7.2f} ms | " + " ".join(f"{k} {v:6.2f}" for k, v in sorted(cat.items()))
+lines = [None] * world
+dist.all_gather_object(lines, line)
+if rank == 0:
+    print("\n".join(lines))
 if rank == 0:
     tot = collections.defaultdict(lambda: [0.0, 0])
     for e in prof.events():

@@ -165,3 +165,25 @@ def test_eval_and_no_grad_calls_keep_the_dense_cached_encoding(pkg, monkeypatch)
     want = (emb[h] * m.decoder.relation_embeddings.weight[r] * emb[t]).sum(-1)
     torch.testing.assert_close(s, want, rtol=1e-5, atol=1e-6)
     assert m.encoder._eval_cache is not None and torch.isfinite(emb).all()
+
+
+@pytest.mark.parametrize("mode", ["fp32"])
+def test_marked_sources_walk_equals_plain_row_sparse_walk(pkg, monkeypatch, mode):
+    """layer_bwd on a graph much larger than the row list: with the sources marked from the forward CSR first
+    (rgcn_aggregate_bwd_rows_marked) the input gradient carries the same bits as without, and as the dense backward."""
+    from primekg_rgcn_linkprediction_b200 import ops
+    ei, et, N, R, x, W, root, bias, gen = _layer_inputs("primekg_100k", 64, 64)
+    g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
+    head, tail = _pairs(ei, N, 200, gen)                                # 400 listed rows of 100,000: ratio 250
+    rows, slot = ops.rows_list_build(head, tail, N)
+    _, A_d, wp = ops.layer_fwd(g, x, x, W, root, bias, False, mode)
+    gO = torch.zeros(N, 64)
+    uniq = torch.unique(rows.cpu())
+    gO[uniq] = torch.randn(uniq.numel(), 64, generator=gen)
+    gO = gO.to(DEV)
+    dense = ops.layer_bwd(g, gO, None, 1.0, A_d, W, root, 64, mode, True, True, False, False)
+    monkeypatch.setenv("RGCN_MARK_SOURCES", "1")
+    marked = ops.layer_bwd(g, gO, None, 1.0, A_d, W, root, 64, mode, True, True, False, False, rows=rows, slot=slot)
+    monkeypatch.setenv("RGCN_MARK_SOURCES", "0")
+    plain = ops.layer_bwd(g, gO, None, 1.0, A_d, W, root, 64, mode, True, True, False, False, rows=rows, slot=slot)
+    assert torch.equal(marked[0], plain[0]) and torch.equal(marked[0], dense[0])
