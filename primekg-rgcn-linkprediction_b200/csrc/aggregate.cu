@@ -241,9 +241,12 @@ constexpr int agg_min_blocks(int G, int vpl, int mix, bool w) {
 }
 
 // MP: the masked-planes second output (MIX_SUM only) is compiled in; one resident block less buys it the registers
-template <int G, int VPL, int MIX, bool W, bool SLOT = false, bool MP = false, bool LIST = false>
-__global__ void __launch_bounds__(256, LIST ? (VPL > 2 ? 1 : 3) : agg_min_blocks(G, VPL, MIX, W) - ((MP && agg_min_blocks(G, VPL, MIX, W) > 1) ? 1 : 0))
+// MARK (row-sparse backward only): rows whose row_flag byte is zero leave at once — a separate instantiation, so that the
+// unmarked walk keeps its register allocation (with the test compiled in, the d = 256 row-sparse walk spilled: 33 -> 66 us)
+template <int G, int VPL, int MIX, bool W, bool SLOT = false, bool MP = false, bool LIST = false, bool MARK = false>
+__global__ void __launch_bounds__(256, LIST ? (VPL > 2 ? 1 : 3) : agg_min_blocks(G, VPL, MIX, W) - (((MP || MARK) && agg_min_blocks(G, VPL, MIX, W) > 1) ? 1 : 0))
 aggregate_rows_kernel(const AggParams p) {
+  static_assert(!MARK || (SLOT && !MP && MIX == MIX_SUM), "marked sources serve the row-sparse backward walk");
   static_assert(!LIST || (MIX == MIX_NONE && !W && !SLOT && !MP), "the listed-rows walk is the unmixed forward form");
   pdl_enter();
   constexpr int GROUPS = 256 / G;
@@ -296,6 +299,14 @@ aggregate_rows_kernel(const AggParams p) {
     // longest rows first: neighbouring groups get rows of similar length and the long walks start at time zero
     row = __ldg(p.row_order + row);
   }
+  if (MARK && !__ldg(p.row_flag + row)) {
+    // (group-uniform) none of this row's edges gathers a listed row: every term of its sum is an exact zero, the result is
+    // the init row alone.  Kept ahead of everything else so that the walk below compiles exactly as without the test.
+    const float* __restrict__ ir = p.init ? p.init + (int64_t)__ldg(p.slot + row) * p.ld_init : nullptr;
+    for (int vi = lane; vi < (p.d >> 2); vi += G)
+      store_vec(p, row, vi * 4, ir ? ldg4(ir + vi * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
   const int R = p.R, d = p.d, nvec = p.d >> 2;
   const int64_t key0 = row * R;
   const int32_t* __restrict__ rowptr = p.rowptr + key0;
@@ -337,13 +348,6 @@ aggregate_rows_kernel(const AggParams p) {
 #pragma unroll
       for (int k = 0; k < VPL; ++k) mix[0][k] = ldg4(p.init + irow * p.ld_init + vcol[k]);
     }
-  }
-  if (SLOT && !MP && MIX == MIX_SUM && p.row_flag && !__ldg(p.row_flag + row)) {
-    // (group-uniform) none of this row's edges gathers a listed row: every term of its sum is an exact zero
-#pragma unroll
-    for (int k = 0; k < VPL; ++k)
-      if (act[k]) store_vec(p, row, vcol[k], mix[0][k]);
-    return;
   }
 
   // A row's edges are contiguous in the CSR (sorted by (row, relation)).  The group keeps a window of 2*G edge
@@ -1090,6 +1094,7 @@ static int launch_agg(const AggParams& p_in, int mix, int n_chunks, cudaStream_t
     const dim3 sgrid((unsigned)((n_walk + GROUPS - 1) / GROUPS));
     if (p.mp_hi) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true, true>, sgrid, dim3(256),
                                       p.mp_colsum ? (size_t)GROUPS * p.d * sizeof(float) : 0, st, p));
+    else if (p.row_flag) RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true, false, false, true>, sgrid, dim3(256), 0, st, p));
     else RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_SUM, true, true>, sgrid, dim3(256), 0, st, p));
     RGCN_LAUNCH_CHECK();
     return RGCN_OK;

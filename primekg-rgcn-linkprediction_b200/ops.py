@@ -507,7 +507,8 @@ def _gemm_workspace(device, n: int, K: int, d_out: int) -> torch.Tensor:
     return _workspace(device, nb)
 
 
-MARK_SOURCES_RATIO = 8       # rows of the graph per list entry from which the row-sparse walk marks its sources first
+MARK_SOURCES_RATIO = 64      # rows of the graph per list entry from which the row-sparse walk marks its sources first (cfg3, ratio 32:
+                             # most rows are marked anyway and the marked variant costs 7 %; a partitioned shard: ratio 300+)
 
 
 def mark_sources() -> bool:

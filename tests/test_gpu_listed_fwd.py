@@ -174,7 +174,7 @@ def test_marked_sources_walk_equals_plain_row_sparse_walk(pkg, monkeypatch, mode
     from primekg_rgcn_linkprediction_b200 import ops
     ei, et, N, R, x, W, root, bias, gen = _layer_inputs("primekg_100k", 64, 64)
     g = pkg.RelGraph.from_edges(ei.to(DEV), et.to(DEV), N, R)
-    head, tail = _pairs(ei, N, 200, gen)                                # 400 listed rows of 100,000: ratio 250
+    head, tail = _pairs(ei, N, 200, gen)                                # 400 listed rows of 100,000: ratio 250 (> 64)
     rows, slot = ops.rows_list_build(head, tail, N)
     _, A_d, wp = ops.layer_fwd(g, x, x, W, root, bias, False, mode)
     gO = torch.zeros(N, 64)
