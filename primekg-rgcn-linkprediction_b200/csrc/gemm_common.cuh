@@ -87,6 +87,37 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int64_t cols
   return RGCN_OK;
 }
 
+// fp32 matrix [rows, cols] row-major with leading dimension ld (elements); box = 16 cols x 32 rows, 64-byte swizzle: the
+// per-warp output patch of the transform's storing epilogue (TMA store; partial boxes are clipped)
+static int make_out_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  struct Key { const void* base; int64_t rows, cols, ld; };
+  constexpr int NC = 32;
+  static thread_local Key keys[NC];
+  static thread_local CUtensorMap vals[NC];
+  static thread_local int n_cached = 0, next = 0;
+  for (int i = 0; i < n_cached; ++i)
+    if (keys[i].base == base && keys[i].rows == rows && keys[i].cols == cols && keys[i].ld == ld) { *m = vals[i]; return RGCN_OK; }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return RGCN_EUNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {16u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed with code %d (rows %lld cols %lld ld %lld)", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return RGCN_ECUDA;
+  }
+  keys[next] = Key{base, rows, cols, ld};
+  vals[next] = *m;
+  next = (next + 1) % NC;
+  if (n_cached < NC) ++n_cached;
+  return RGCN_OK;
+}
+
 static unsigned grid_cap(int64_t blocks, int64_t cap) { return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks)); }
 
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }

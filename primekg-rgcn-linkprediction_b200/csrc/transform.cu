@@ -165,6 +165,11 @@ struct GemmKParams {
   // c < n_out_rows, the padding rows beyond are dropped (duplicates in the list write identical values)
   const int64_t* out_rows; int64_t n_out_rows;
   const int32_t* out_slot;                    // nullable: node -> first list position; later duplicates are not stored
+  // TMA-store epilogue (plain / dropout store loops): every warp's 32 x 16 patch leaves shared memory as ONE bulk tensor
+  // store (cp.async.bulk.tensor: the patch's XOR swizzle is the tensor map's 64-byte swizzle); rows / columns beyond the
+  // matrix are clipped by the copy engine
+  int tma_store;
+  alignas(64) CUtensorMap tm_out;
 };
 
 enum { EPI_STORE = 0, EPI_RANK = 1, EPI_THR = 2, EPI_TOPK = 3 };
@@ -210,7 +215,7 @@ template <bool SPLIT, bool B_MN, int EPI = EPI_STORE, int BNT = 128, int XF = 2>
 __global__ void __launch_bounds__((epi_warps(EPI) + 2) * 32, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                   const GemmKParams p) {
+                   const __grid_constant__ GemmKParams p) {
   using S = KStage<SPLIT, BNT>;
   constexpr int EW = epi_warps(EPI);              // epilogue warps; warp EW = TMA producer, warp EW + 1 = MMA issuer
   extern __shared__ uint8_t smem_raw[];
@@ -401,6 +406,12 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           }
           continue;
         }
+        const bool tma_out = XF < 2 && p.tma_store;            // (kernel-uniform)
+        if (tma_out) {
+          // the previous chunk's bulk store must have read the patch before it is rewritten
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
         // registers (one row per lane) -> patch, + bias / ReLU
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -418,7 +429,28 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           if (p.relu) { qv.x = fmaxf(qv.x, 0.f); qv.y = fmaxf(qv.y, 0.f); qv.z = fmaxf(qv.z, 0.f); qv.w = fmaxf(qv.w, 0.f); }
           // row `lane`, 16-byte chunk j / 4, XOR swizzled by the row pair: conflict-free for the row-wise writes here and
           // for the 8-rows x 64-byte reads below, without padding (16 warps' patches must fit beside the operand ring)
+          if (tma_out && DROP && (XF == 1 || p.drop_thresh)) {
+            // lane = row: the same (row, column) -> bits map as the store loop below
+            const int64_t row = m0 + quarter * 32 + lane;
+            const uint32_t e32 = (uint32_t)(row + p.row_offset) * (uint32_t)p.N + (uint32_t)(n0 + cc + j);
+            const uint32_t bk = drop_small ? bk_small
+                                           : drop_block_key(drop_key, (uint64_t)(row + p.row_offset) * (uint64_t)p.N + (uint64_t)(n0 + cc + j));
+            const uint32_t h0 = pcg_hash(e32 ^ bk), h1 = pcg_hash((e32 + 2) ^ bk);
+            qv.x = (h0 & 0xffffu) >= p.drop_thresh ? qv.x * p.drop_scale : 0.f;
+            qv.y = (h0 >> 16) >= p.drop_thresh ? qv.y * p.drop_scale : 0.f;
+            qv.z = (h1 & 0xffffu) >= p.drop_thresh ? qv.z * p.drop_scale : 0.f;
+            qv.w = (h1 >> 16) >= p.drop_thresh ? qv.w * p.drop_scale : 0.f;
+          }
           sts4(patch_s + (uint32_t)(lane * 16 + (((j >> 2) ^ ((lane >> 1) & 3)) << 2)) * 4u, qv);
+        }
+        if (tma_out) {
+          fence_proxy_async();                                   // generic-proxy patch writes -> visible to the copy engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tm_out, patch_s, n0 + cc, (int)(m0 + quarter * 32));
+            bulk_commit();
+          }
+          continue;
         }
         __syncwarp();
         // patch -> global: each instruction writes 8 rows x 64 contiguous bytes
@@ -469,6 +501,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       if (lane == 0) mbar_arrive(&tempty_bar[a]);       // accumulator a may be overwritten
     }
     if (EPI != EPI_STORE) flush_row_state();
+    if (EPI == EPI_STORE && XF < 2 && p.tma_store && lane == 0) bulk_wait0();     // the last bulk stores have landed
   } else if (warp == EW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -790,12 +823,30 @@ static int launch_kmajor_x(const GemmKParams& p, const CUtensorMap& ahi, const C
 }
 
 template <bool SPLIT, bool B_MN>
+static int launch_kmajor_q(const GemmKParams& p, int xf, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
+                           const CUtensorMap& mlo, unsigned grid, cudaStream_t st);
+
+template <bool SPLIT, bool B_MN>
 static int launch_kmajor_t(const GemmKParams& p, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
                            const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
   // the store loop's variant: 2 = run-time everything (bf16 copy, peer stores, scattered rows), 1 = dropout, 0 = plain
   static int force_generic = -1;
   if (force_generic < 0) { const char* e = getenv("RGCN_GENERIC_EPILOGUE"); force_generic = (e && e[0] == '1') ? 1 : 0; }
   const int xf = (force_generic || p.out_rows || p.out16 || p.n_peer) ? 2 : (p.drop_thresh ? 1 : 0);
+  static int tma_store = -1;                           // RGCN_TMA_STORE=0: the st.global store loop
+  if (tma_store < 0) { const char* e = getenv("RGCN_TMA_STORE"); tma_store = (e && e[0] == '0') ? 0 : 1; }
+  GemmKParams q = p;
+  if (xf < 2 && tma_store && ((uintptr_t)p.out & 15) == 0 && p.ldo % 4 == 0 && p.N % 4 == 0) {
+    int rc = make_out_map(&q.tm_out, p.out, p.M, p.N, p.ldo);
+    if (rc) return rc;
+    q.tma_store = 1;
+  }
+  return launch_kmajor_q<SPLIT, B_MN>(q, xf, ahi, alo, mhi, mlo, grid, st);
+}
+
+template <bool SPLIT, bool B_MN>
+static int launch_kmajor_q(const GemmKParams& p, int xf, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& mhi,
+                           const CUtensorMap& mlo, unsigned grid, cudaStream_t st) {
   if (p.BN > 128) {
     if (xf == 0) return launch_kmajor_x<SPLIT, B_MN, 256, 0>(p, ahi, alo, mhi, mlo, grid, st);
     if (xf == 1) return launch_kmajor_x<SPLIT, B_MN, 256, 1>(p, ahi, alo, mhi, mlo, grid, st);
