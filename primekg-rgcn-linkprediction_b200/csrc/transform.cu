@@ -1178,7 +1178,11 @@ static int transform_fwd_w_impl(const void* A_hi, const void* A_lo, int64_t lda,
   static int wide_fp32 = -1;                       // A/B switch: 256-wide tiles in the three-product mode too
   if (wide_fp32 < 0) { const char* e = getenv("RGCN_WIDE_FP32"); wide_fp32 = e ? atoi(e) : 0; }
   const bool wide = d_out > KBN && (mode == 1 || (wide_fp32 == 1) || (wide_fp32 == 2 && K <= 256));
-  const Tiling t = tile_n(d_out, 32, wide ? wide_bn() : KBN);
+  Tiling t = tile_n(d_out, 32, wide ? wide_bn() : KBN);
+  // few rows (the listed-rows transform: 4,096 x 1,024 -> 256 is 64 tiles of 128 x 128): 64-wide tiles fill the machine
+  static int narrow_small = -1;
+  if (narrow_small < 0) { const char* e = getenv("RGCN_NARROW_SMALL"); narrow_small = (e && e[0] == '0') ? 0 : 1; }
+  if (narrow_small && d_out % 64 == 0 && d_out >= 128 && ((n_rows + BM - 1) / BM) * t.n_tiles * 2 <= sm_count()) t = tile_n(d_out, 32, 64);
   const __nv_bfloat16* bhi = (const __nv_bfloat16*)w_planes;
   const __nv_bfloat16* blo = (const __nv_bfloat16*)((const char*)w_planes + wplane_bytes(K, d_out));
   GemmKParams p{};
