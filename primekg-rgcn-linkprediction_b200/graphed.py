@@ -111,8 +111,10 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         from . import ops as _ops
         _ops.raise_on_bad_pairs(dev)                     # an out-of-range index in the warm-up batch surfaces here
+        # capture on the stream the warm-up ran on: the per-stream workspaces (ops._workspace, the fused loss's ticket
+        # buffer) exist already, so no allocation — and no zero-fill node — ends up inside the graph
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.loss, self.scores = self._step()
         if self.arena is not None:
             lo, hi = self.arena.buf.data_ptr(), self.arena.buf.data_ptr() + self.arena.buf.numel() * 4
@@ -166,7 +168,9 @@ class GraphedTrainStep:
             self.flat_grad.zero_()
             loss.backward()
         else:
-            self._grads = torch.autograd.grad(loss, self.params, allow_unused=True)
+            if getattr(self, "_one", None) is None or self._one.device != loss.device:
+                self._one = torch.ones((), dtype=loss.dtype, device=loss.device)     # the seed gradient: no fill kernel per step
+            self._grads = torch.autograd.grad(loss, self.params, grad_outputs=self._one, allow_unused=True)
         return loss.detach(), scores.detach()
 
     def _bind_grads(self) -> None:
