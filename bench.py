@@ -599,10 +599,20 @@ def run_ours(args, rank, world, local_rank):
         eager_step(d_batch)
         allreduce_grads()
     barrier()
-    l0 = lib.rgcn_launch_count()
-    eager_step(d_batch)
-    torch.cuda.synchronize()
-    launches_per_step = int(lib.rgcn_launch_count() - l0)
+    # our kernels per step, counted on ONE truly eager step (the captured forms replay without passing the library's host
+    # entry points, and the step in which the module captures its graphs would count the capture's warm-up passes too)
+    ag_env = os.environ.get("PRIMEKG_RGCN_AUTOGRAPH")
+    os.environ["PRIMEKG_RGCN_AUTOGRAPH"] = "0"
+    try:
+        l0 = lib.rgcn_launch_count()
+        eager_step(d_batch)
+        torch.cuda.synchronize()
+        launches_per_step = int(lib.rgcn_launch_count() - l0)
+    finally:
+        if ag_env is None:
+            del os.environ["PRIMEKG_RGCN_AUTOGRAPH"]
+        else:
+            os.environ["PRIMEKG_RGCN_AUTOGRAPH"] = ag_env
 
     def timed(run_one, steps):
         """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps."""
