@@ -613,6 +613,9 @@ def run_ours(args, rank, world, local_rank):
             del os.environ["PRIMEKG_RGCN_AUTOGRAPH"]
         else:
             os.environ["PRIMEKG_RGCN_AUTOGRAPH"] = ag_env
+    for _ in range(6):                                 # (the module re-captures its graphs after the eager detour: not timed)
+        eager_step(d_batch)
+    barrier()
 
     def timed(run_one, steps):
         """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps."""
