@@ -197,6 +197,53 @@ def test_rowsparse_handover_guards(lib_built, monkeypatch):
     rowsparse.clear()
 
 
+def test_listed_rows_switches_and_output_mark(lib_built, monkeypatch):
+    """Host logic of the listed-rows last layer: the environment switches, and the mark that lets the decoder's backward
+    leave the unlisted gradient rows undefined — honoured only for the very tensor that was marked, untouched, consumed by
+    the first look, dropped by any layer forward that computes all rows."""
+    from primekg_rgcn_linkprediction_b200 import dist_fused, modules, ops, rowsparse
+    for k in ("PRIMEKG_RGCN_SPARSE_FWD", "PRIMEKG_RGCN_SPARSE_BWD", "RGCN_MARK_SOURCES", "RGCN_PEER_PUSH"):
+        monkeypatch.delenv(k, raising=False)
+    assert modules.sparse_forward_enabled() and dist_fused.listed_last_layer() and ops.mark_sources()
+    assert not dist_fused.push_after_transform()
+    monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_FWD", "0")
+    assert not modules.sparse_forward_enabled() and not dist_fused.listed_last_layer()
+    monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_FWD", "1")
+    monkeypatch.setenv("PRIMEKG_RGCN_SPARSE_BWD", "0")                 # the listed forward needs the row-sparse backward
+    assert not modules.sparse_forward_enabled() and not dist_fused.listed_last_layer()
+    monkeypatch.setenv("RGCN_MARK_SOURCES", "0")
+    assert not ops.mark_sources() and ops.MARK_SOURCES_RATIO >= 8
+    rowsparse.clear()
+    out = torch.zeros(50, 8)
+    assert not rowsparse.is_listed_output(out)
+    rowsparse.mark_listed_output(out)
+    assert rowsparse.is_listed_output(out) and not rowsparse.is_listed_output(out)          # consumed by the first look
+    rowsparse.mark_listed_output(out)
+    assert not rowsparse.is_listed_output(out.clone())                                      # another tensor
+    rowsparse.mark_listed_output(out)
+    out.add_(1.0)
+    assert not rowsparse.is_listed_output(out)                                              # written since
+    rowsparse.mark_listed_output(out)
+    rowsparse.unmark_listed_output()                                                        # a dense layer forward ran
+    assert not rowsparse.is_listed_output(out)
+    rowsparse.clear()
+
+
+def test_model_forward_on_cpu_indices_keeps_the_dense_encoder(lib_built, monkeypatch):
+    """``DrugDiseaseModel._encode_for`` only takes the listed form for CUDA index tensors with autograd on; anything else
+    goes through ``encoder(...)`` (here: stubbed, so the routing alone is checked on the CPU box)."""
+    import primekg_rgcn_linkprediction_b200 as pkg
+    m = pkg.DrugDiseaseModel(20, 2, 8, 8)
+    calls = []
+    monkeypatch.setattr(m.encoder, "_encode", lambda *a, **k: calls.append(("listed", a[3] if len(a) > 3 else k.get("read_rows"))) or "L")
+    monkeypatch.setattr(type(m.encoder), "forward", lambda self, ei, et, node_indices=None: calls.append(("dense", None)) or "D")
+    h = torch.tensor([1, 2]); t = torch.tensor([3, 4])
+    assert m._encode_for(None, None, h, t) == "D"                                           # CPU indices
+    with torch.no_grad():
+        assert m._encode_for(None, None, h, t) == "D"
+    assert [c[0] for c in calls] == ["dense", "dense"]
+
+
 def test_grad_arena_slices(lib_built):
     """ops.GradArena: call-order slices of one flat buffer, 256-byte aligned, reset per step, overflow falls back."""
     from primekg_rgcn_linkprediction_b200 import ops
