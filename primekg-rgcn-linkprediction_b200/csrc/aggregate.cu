@@ -96,6 +96,7 @@ struct AggParams {
   // Either way a row that the list names several times is walked once.
   int64_t list_walkers;
   int32_t list_by_rows;
+  int32_t list_overlap_hubs;   // hub chunks on a side stream beside the listed walk (which skips the hub segments) + finish kernel
   int32_t stream_rel;        // backward walk: stream a row's edges across relation boundaries (short segments, many relations)
   // row-sparse backward on large graphs (nullable): row_flag[j] != 0 iff some edge of source row j gathers a LISTED row
   // (marked beforehand from the forward-orientation CSR of the listed rows, mark_sources_kernel); the other rows leave at
@@ -761,6 +762,45 @@ __global__ void __launch_bounds__(256) hub_finish_kernel(const AggParams p) {
   }
 }
 
+// ---- hub finish of the LISTED walk: one G-lane group per hub segment of a listed row ---------------------------------
+// The listed walk is latency bound and so is its hub pass (few long rows / a few hundred chunks): run side by side they
+// overlap almost completely.  The walk then skips the hub segments (skip_hubs) and this kernel adds them afterwards — the
+// same additions in the same order as the walk's own hub branch (chunk partials in chunk order, one true division).
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) hub_finish_list_kernel(const AggParams p) {
+  pdl_enter();
+  constexpr int GROUPS = 256 / G;
+  const int lane = threadIdx.x % G;
+  const int h = blockIdx.x * GROUPS + threadIdx.x / G;
+  if (h >= p.n_hubs) return;
+  const int key = __ldg(p.hub_keys + h);
+  const int64_t row = key / p.R;
+  const int r = key - (int)row * p.R;
+  const int64_t orow = __ldg(p.hub_filter + row);
+  if (orow == p.hub_unlisted) return;
+  const int d = p.d, nvec = p.d >> 2;
+  const int c0 = __ldg(p.hub_chunk_ptr + h), c1 = __ldg(p.hub_chunk_ptr + h + 1);
+  const float len = (float)(__ldg(p.rowptr + key + 1) - __ldg(p.rowptr + key));
+  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = k * G + lane;
+    if (vi >= nvec) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = c0;
+    for (; c + U <= c1; c += U) {                    // loads U chunks ahead, adds strictly in chunk order
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const float4*>(p.partials + (size_t)(c + u) * d + vi * 4);
+#pragma unroll
+      for (int u = 0; u < U; ++u) add4(acc, v[u]);
+    }
+    for (; c < c1; ++c) add4(acc, *reinterpret_cast<const float4*>(p.partials + (size_t)c * d + vi * 4));
+    acc = div4(acc, len);
+    store_vec(p, orow, r * p.block_stride + vi * 4, acc);
+  }
+}
+
 // ---- bf16 features (the "bf16-transform" mode gathers a bf16 copy of the layer input: half the L2 / HBM bytes of the
 // dominant kernel; sums, means and hub partials stay fp32) -------------------------------------------------------------
 // Forward, unmixed form only.  A lane holds VPL vectors of EIGHT columns (one 128-bit load = 8 bf16), so a 256-wide row is
@@ -1025,6 +1065,17 @@ static ForkJoin* fork_join() {
   }
   return &f;
 }
+// the side stream if it exists already or may be created now (never while a stream capture is in progress)
+static ForkJoin* fork_join_existing(cudaStream_t st) {
+  static ForkJoin* made[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (made[dev]) return made[dev];
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;
+  made[dev] = fork_join();
+  return made[dev];
+}
 // Opt-in (RGCN_OVERLAP_HUBS=1).  Measured on the B200 it LOSES against the plain order hub pass -> row walk
 // (cfg2 d = 256 forward 93 vs 75 us, step 0.595 vs 0.533 ms): the two latency-bound kernels slow each other down and
 // the finish kernel adds a serial tail, so the default stays the single-stream order.
@@ -1072,14 +1123,30 @@ static int launch_agg(const AggParams& p_in, int mix, int n_chunks, cudaStream_t
   if (p.list) {
     // listed-rows walk: forward, unmixed, unweighted (the last layer of a link-prediction step)
     if (mix != MIX_NONE || p.edge_w || p.slot || p.mp_hi) { set_error("aggregate: the listed-rows walk serves the unmixed forward only"); return RGCN_EINVAL; }
+    const dim3 lgrid((unsigned)((n_walk + GROUPS - 1) / GROUPS), (unsigned)(p.list_slices > 0 ? p.list_slices : 1),
+                     (unsigned)(p.list_rsplit > 0 ? p.list_rsplit : 1));
+    ForkJoin* fj = (p.list_overlap_hubs && n_chunks > 0 && n_walk > 0 && p.list_slices <= 1) ? fork_join_existing(st) : nullptr;
+    if (fj) {
+      // hub chunks on the side stream, the walk (without the hub segments) on this one, then the finish kernel
+      RGCN_CUDA(cudaEventRecord(fj->fork, st));
+      RGCN_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+      hub_partial_kernel<G, VPL, false><<<n_chunks, 256, 0, fj->side>>>(p);
+      RGCN_LAUNCH_CHECK();
+      RGCN_CUDA(cudaEventRecord(fj->join, fj->side));
+      p.skip_hubs = 1;
+      RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, false, false, false, true>, lgrid, dim3(256), 0, st, p));
+      RGCN_LAUNCH_CHECK();
+      RGCN_CUDA(cudaStreamWaitEvent(st, fj->join, 0));
+      hub_finish_list_kernel<G, VPL><<<(unsigned)((p.n_hubs + GROUPS - 1) / GROUPS), 256, 0, st>>>(p);
+      RGCN_LAUNCH_CHECK();
+      return RGCN_OK;
+    }
     if (n_chunks > 0) {
       RGCN_CUDA(launch_pdl(hub_partial_kernel<G, VPL, false>, dim3(n_chunks), dim3(256), 0, st, p));
       RGCN_LAUNCH_CHECK();
     }
     if (n_walk <= 0) return RGCN_OK;
-    RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, false, false, false, true>,
-                         dim3((unsigned)((n_walk + GROUPS - 1) / GROUPS), (unsigned)(p.list_slices > 0 ? p.list_slices : 1),
-                              (unsigned)(p.list_rsplit > 0 ? p.list_rsplit : 1)), dim3(256), 0, st, p));
+    RGCN_CUDA(launch_pdl(aggregate_rows_kernel<G, VPL, MIX_NONE, false, false, false, true>, lgrid, dim3(256), 0, st, p));
     RGCN_LAUNCH_CHECK();
     return RGCN_OK;
   }
@@ -1451,6 +1518,27 @@ static int aggregate_fwd_list_impl(const rgcn_csr_t* g, const void* X, int64_t l
     if (nvec <= 64) return launch_agg_bf16<32, 2>(q, n_chunks, st);
     return launch_agg_bf16<32, 4>(q, n_chunks, st);
   };
+  // RGCN_LIST_OVERLAP_HUBS: 0 (default) never, 1 always, 2 while capturing.  OPT-IN: measured on the B200 the hub pass beside
+  // the listed walk LOSES like it does for the dense walk — cfg2 layer 2 listed forward 54.8 against 51.6 us, step 0.300
+  // against 0.293 ms (two latency-bound kernels sharing the L2 queues, plus the finish kernel's serial tail)
+  static int env_overlap = -1;
+  if (env_overlap < 0) { const char* e = getenv("RGCN_LIST_OVERLAP_HUBS"); env_overlap = e ? atoi(e) : 0; }
+  static int env_slice0 = -1;
+  if (env_slice0 < 0) { const char* e = getenv("RGCN_LIST_SLICE"); env_slice0 = e ? atoi(e) : 0; }
+  if (!x_bf16 && env_overlap && env_slice0 == 0 && g->n_chunks > 0) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+    if (!capturing) (void)fork_join_existing(st);   // (the side stream is made by the first eager call: GraphedTrainStep and
+                                                    //  the module's own capture both warm up eagerly before they capture)
+    if (env_overlap == 1 || capturing) {
+      // one dispatch: hub chunks beside the walk (side stream; two branches of a captured graph), then the finish kernel
+      static int env_rs = -1;
+      if (env_rs < 0) { const char* e = getenv("RGCN_LIST_RSPLIT"); env_rs = e ? atoi(e) : 1; }
+      p.list_overlap_hubs = 1; p.list_slices = 1;
+      p.list_rsplit = env_rs < 1 ? 1 : (env_rs > g->R ? g->R : env_rs);
+      return run(p, g->n_chunks);
+    }
+  }
   // hub chunks (full width, only the listed rows' chunks), then the walk in column slices x relation ranges
   if (g->n_chunks > 0) {
     AggParams h = p;
